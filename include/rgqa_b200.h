@@ -1,0 +1,148 @@
+/*
+ * rgqa_b200 — C ABI of the B200-native RGQA evaluation hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every function returns 0
+ * on success and non-zero on failure; the message of the last failure on the calling thread is
+ * rgqa_last_error().  Nothing throws across this boundary.  All device pointers are borrowed for the
+ * duration of the call; the handle owns only its packed weights and its workspace.  All work is
+ * enqueued on the caller's CUDA stream (`stream` is a cudaStream_t / CUstream passed as void*).
+ *
+ * Reference interface each entry point replaces (paths relative to chihhuiho/RGQA):
+ *   rgqa_create / rgqa_load_weight / rgqa_finalize_weights
+ *        GQAModel.__init__ + load_state_dict        src/tasks/gqa_model.py:14-28, src/tasks/gqa_conf.py:375-381,
+ *        LXRTEncoder.load                            src/lxrt/entry.py:126-152
+ *   rgqa_lxmert_forward
+ *        LXRTFeatureExtraction.forward (mode 'x')    src/lxrt/modeling.py:1020-1030
+ *        + GQAModel.logit_fc                         src/tasks/gqa_model.py:22-43
+ *   rgqa_uniter_forward
+ *        UniterFeatureExtraction.forward             src/uniter/modeling.py:651-656
+ *        + GQAUNITER.logit_fc                        src/uniter/uniter.py:23-44
+ *   rgqa_score
+ *        MSP scorer                                  src/tasks/gqa_conf.py:326
+ *        energy scorers                              src/tasks/gqa_energy.py:131,185,204-206
+ *        Mahalanobis scorer (noise = 0)              src/tasks/gqa_maha.py:228-236,270
+ *   rgqa_set_maha
+ *        sample_estimator() output {mean, precision} src/tasks/gqa_maha.py:120-201
+ *   rgqa_gemm_* / rgqa_attention / rgqa_embed_ln / rgqa_layernorm / rgqa_visn_combine
+ *        the individual nn.Module forwards of src/lxrt/modeling.py (BertAttention :320-347,
+ *        BertAttOutput :357-361, BertIntermediate :398-401, BertOutput :411-415, BertEmbeddings :278-292,
+ *        VisualFeatEncoder :507-517) — exported so each kernel is testable on its own.
+ */
+#ifndef RGQA_B200_H_
+#define RGQA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGQA_ABI_VERSION 1
+
+/* architectures */
+#define RGQA_ARCH_LXMERT 0
+#define RGQA_ARCH_UNITER 1
+/* arithmetic of the path */
+#define RGQA_PREC_FP32 0 /* fp32 weights + activations, CUDA-core GEMMs (tolerance 1e-4 on logits)       */
+#define RGQA_PREC_BF16 1 /* bf16 weights + activations, tcgen05 GEMMs with fp32 accumulate / LN / softmax */
+/* element types of borrowed buffers */
+#define RGQA_DT_F32 0
+#define RGQA_DT_BF16 1
+/* GEMM epilogues */
+#define RGQA_EPI_BIAS 0
+#define RGQA_EPI_GELU 1
+#define RGQA_EPI_TANH 2
+#define RGQA_EPI_RESID 3
+/* scorers */
+#define RGQA_SCORE_MSP 0
+#define RGQA_SCORE_ENERGY_TOP2 1
+#define RGQA_SCORE_ENERGY_SUM 2
+#define RGQA_SCORE_LSE 3
+#define RGQA_SCORE_MAHA 4
+
+typedef struct rgqa_handle rgqa_handle;
+
+typedef struct rgqa_config {
+  int32_t arch;            /* RGQA_ARCH_*                                                        */
+  int32_t l_layers;        /* language layers (LXMERT: 9; UNITER: 12 single-stream layers)       */
+  int32_t x_layers;        /* cross-modality layers (LXMERT: 5; UNITER: 0)                       */
+  int32_t r_layers;        /* object-relational layers (LXMERT: 5; UNITER: 0)                    */
+  int32_t hidden;          /* 768                                                                */
+  int32_t heads;           /* 12                                                                 */
+  int32_t intermediate;    /* 3072                                                               */
+  int32_t vocab_size;      /* 30522 (bert-base-uncased) / 28996 (bert-base-cased, UNITER)        */
+  int32_t max_position;    /* 512                                                                */
+  int32_t type_vocab;      /* 2                                                                  */
+  int32_t visual_feat_dim; /* 2048                                                               */
+  int32_t visual_pos_dim;  /* 4 (LXMERT boxes) / 7 (UNITER)                                      */
+  int32_t num_rois;        /* 36                                                                 */
+  int32_t num_answers;     /* 1842; 0 = encoder only (no logit_fc)                               */
+  int32_t precision;       /* RGQA_PREC_*                                                        */
+  float ln_eps;            /* 1e-12                                                              */
+} rgqa_config;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int rgqa_abi_version(void);
+const char* rgqa_last_error(void);
+int rgqa_create(const rgqa_config* cfg, rgqa_handle** out);
+void rgqa_destroy(rgqa_handle* h);
+
+/* Number / names of the reference state-dict tensors this handle expects (for the host shim). */
+int rgqa_num_weights(const rgqa_handle* h);
+const char* rgqa_weight_name(const rgqa_handle* h, int index);
+/* Copy one fp32 tensor, named by its reference state-dict key (a leading "module.",
+ * "lxrt_encoder.model." or "encoder.model." prefix is accepted and ignored), into the handle.
+ * `data` is a host pointer (on_device = 0) or a device pointer (on_device = 1). */
+int rgqa_load_weight(rgqa_handle* h, const char* ref_key, const float* data, int on_device, const int64_t* shape,
+                     int ndim);
+/* Verify every expected tensor arrived, then pack: fused Q|K|V, bf16 casts (PREC_BF16). */
+int rgqa_finalize_weights(rgqa_handle* h);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* feat: [B, num_rois, visual_feat_dim] (feat_dtype F32 or BF16), pos: [B, num_rois, 4] f32,
+ * ids / seg / mask: [B, L] int32 (mask: 1 = real token).  pooled_out: [B, hidden] f32 or NULL;
+ * logits_out: [B, num_answers] f32 or NULL (must be NULL when num_answers == 0). */
+int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos,
+                        const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
+                        float* pooled_out, float* logits_out);
+/* UNITER: pos7 is [B, num_rois, 7] f32, the vector GQATorchDataset._uniterBoxes builds
+ * (src/tasks/gqa_data.py:240-250: [y1,x1,y2,x2,w,h,w*h]); passed through untouched. */
+int rgqa_uniter_forward(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos7,
+                        const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
+                        float* pooled_out, float* logits_out);
+
+/* Mahalanobis statistics: class means mu [num_answers, hidden] f32 and precision P [hidden, hidden] f32. */
+int rgqa_set_maha(rgqa_handle* h, const float* mu, const float* precision, int on_device);
+/* score_out: [B] f32, label_out: [B] int32.  MSP / ENERGY_* / LSE read `logits` [B, num_answers];
+ * MAHA reads `pooled` [B, hidden] (and optionally writes the full [B, num_answers] score matrix). */
+int rgqa_score(rgqa_handle* h, void* stream, int mode, const float* logits, const float* pooled, int B,
+               float* score_out, int32_t* label_out, float* maha_full_out);
+
+/* ---- per-kernel entry points (unit tests, integration of single ops) ------------------------- */
+int rgqa_gemm_bf16(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                   const void* resid, int64_t ldr, void* out, int64_t ldo, int out_dtype, int M, int N, int K,
+                   int epilogue);
+int rgqa_gemm_f32(void* stream, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                  const float* resid, int64_t ldr, float* out, int64_t ldo, int M, int N, int K, int epilogue);
+int rgqa_attention(void* stream, int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                   int64_t ldv, const int32_t* key_mask, void* out, int64_t ldo, int B, int Lq, int Lk, int heads);
+int rgqa_embed_ln(void* stream, int out_dtype, const int32_t* ids, const int32_t* seg, const float* word,
+                  const float* pos, const float* type, const float* gamma, const float* beta, void* out, int B,
+                  int L, int H, int vocab, int max_pos, int n_types, float eps);
+int rgqa_layernorm(void* stream, int out_dtype, const float* x, int64_t ldx, const float* gamma, const float* beta,
+                   void* y, int M, int H, float eps);
+int rgqa_visn_combine(void* stream, int out_dtype, const float* x_pre, const float* boxes, int box_dim,
+                      const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
+                      const float* b2, void* out, int M, int H, float eps);
+int rgqa_cast_f32_to_bf16(void* stream, const float* in, void* out, int64_t n);
+int rgqa_score_logits(void* stream, int mode, const float* logits, int64_t ld, int B, int A, float* score,
+                      int32_t* label);
+/* Stand-alone Mahalanobis: x [B,H], mu [A,H], P [H,H] (symmetric) all f32 device pointers;
+ * work: >= B*(H+A+1) + 4 + A*(H+1) floats of device scratch. */
+int rgqa_mahalanobis(void* stream, const float* x, const float* mu, const float* P, int B, int A, int H,
+                     float* work, float* score, int32_t* label, float* full_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGQA_B200_H_ */

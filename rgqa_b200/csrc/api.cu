@@ -1,0 +1,845 @@
+// rgqa_b200 — C ABI (include/rgqa_b200.h): handle, weight ingestion by reference state-dict key,
+// the LXMERT / UNITER forward wiring over the kernels, and the scorers.
+//
+// Data layout in HBM (per handle, grown on demand for the largest (B, L) seen):
+//   hidA/hidB  [Mt, 768]   activation ping-pong; LXMERT keeps the language rows [0, B*L) and the
+//                          visual rows [B*L, B*L + B*36) in ONE buffer so the cross-modality layer's
+//                          shared Q|K|V and output projections (one weight set for both directions,
+//                          src/lxrt/modeling.py:455-459) run as a single GEMM over all Mt rows
+//   qkv        [Mt, 2304]  fused Q|K|V projection, read in place (strided) by the attention kernel
+//   ctx        [Mt, 768]   attention output
+//   inter      [Mt, 3072]  FFN intermediate (after erf-GELU)
+//   pre        [Mt, 768]   fp32 pre-LayerNorm sums (GEMM + bias + residual)
+//   featb      [Mv, 2048]  bf16 copy of the RoI features when the caller hands fp32 ones
+// Weights: nn.Linear weights stay [out, in] row-major (= N x K, K contiguous: the K-major B operand
+// of the tcgen05 GEMM), cast to bf16 in PREC_BF16; Q, K, V are concatenated along N.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rgqa_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rgqa {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p != nullptr) {
+      RGQA_CUDA_OK(cudaFree(p));
+      p = nullptr;
+      bytes = 0;
+    }
+    RGQA_CUDA_OK(cudaMalloc(&p, need));
+    bytes = need;
+    return 0;
+  }
+  void release() {
+    if (p != nullptr) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+struct RawTensor {
+  float* p = nullptr;  // device fp32
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+};
+
+struct Linear {
+  void* W = nullptr;      // [N, K] bf16 or f32 (precision of the handle)
+  float* b = nullptr;     // [N] f32
+  int N = 0, K = 0;
+};
+struct LNp {
+  float* g = nullptr;
+  float* b = nullptr;
+};
+struct AttW {
+  Linear qkv;  // [3H, H]
+  Linear out;  // [H, H]
+  LNp ln;
+};
+struct FfnW {
+  Linear inter;  // [I, H]
+  Linear out;    // [H, I]
+  LNp ln;
+};
+struct LayerW {
+  AttW att;
+  FfnW ffn;
+};
+struct XLayerW {
+  AttW cross, lang_self, visn_self;
+  FfnW lang_ffn, visn_ffn;
+};
+
+}  // namespace
+}  // namespace rgqa
+
+using namespace rgqa;
+
+struct rgqa_handle {
+  rgqa_config cfg;
+  std::vector<std::string> names;           // expected reference keys
+  std::map<std::string, RawTensor> raw;     // uploaded fp32 tensors
+  std::vector<void*> owned;                 // packed allocations
+  bool finalized = false;
+
+  // embeddings (fp32)
+  float *word = nullptr, *posemb = nullptr, *typeemb = nullptr;
+  LNp emb_ln;
+  // visual embedding
+  Linear visn_fc;                 // [H, 2048]
+  float *box_W = nullptr, *box_b = nullptr;  // [H, pos_dim], [H] fp32
+  LNp visn_ln, box_ln, img_ln;    // img_ln: UNITER's third LN
+  std::vector<LayerW> l_layers, r_layers;
+  std::vector<XLayerW> x_layers;
+  Linear pooler, fc0, fc3;
+  LNp fc_ln;
+  // Mahalanobis
+  float *maha_mu = nullptr, *maha_P = nullptr, *maha_m = nullptr;
+  bool has_maha = false;
+
+  // workspace
+  DevBuf hidA, hidB, qkv, ctx, inter, pre, featb, headbuf, mahabuf;
+};
+
+namespace {
+
+int act_dtype(const rgqa_handle* h) { return h->cfg.precision == RGQA_PREC_BF16 ? DT_BF16 : DT_F32; }
+size_t act_size(const rgqa_handle* h) { return h->cfg.precision == RGQA_PREC_BF16 ? 2 : 4; }
+
+void add_linear_names(std::vector<std::string>& v, const std::string& p) {
+  v.push_back(p + ".weight");
+  v.push_back(p + ".bias");
+}
+void add_att_names(std::vector<std::string>& v, const std::string& p, const char* self_name) {
+  add_linear_names(v, p + "." + self_name + ".query");
+  add_linear_names(v, p + "." + self_name + ".key");
+  add_linear_names(v, p + "." + self_name + ".value");
+  add_linear_names(v, p + ".output.dense");
+  add_linear_names(v, p + ".output.LayerNorm");
+}
+void add_bert_layer_names(std::vector<std::string>& v, const std::string& p) {
+  add_att_names(v, p + ".attention", "self");
+  add_linear_names(v, p + ".intermediate.dense");
+  add_linear_names(v, p + ".output.dense");
+  add_linear_names(v, p + ".output.LayerNorm");
+}
+
+void build_names(rgqa_handle* h) {
+  auto& v = h->names;
+  const rgqa_config& c = h->cfg;
+  if (c.arch == RGQA_ARCH_LXMERT) {
+    const std::string b = "bert.";
+    v.push_back(b + "embeddings.word_embeddings.weight");
+    v.push_back(b + "embeddings.position_embeddings.weight");
+    v.push_back(b + "embeddings.token_type_embeddings.weight");
+    add_linear_names(v, b + "embeddings.LayerNorm");
+    add_linear_names(v, b + "encoder.visn_fc.visn_fc");
+    add_linear_names(v, b + "encoder.visn_fc.visn_layer_norm");
+    add_linear_names(v, b + "encoder.visn_fc.box_fc");
+    add_linear_names(v, b + "encoder.visn_fc.box_layer_norm");
+    for (int i = 0; i < c.l_layers; ++i) add_bert_layer_names(v, b + "encoder.layer." + std::to_string(i));
+    for (int i = 0; i < c.r_layers; ++i) add_bert_layer_names(v, b + "encoder.r_layers." + std::to_string(i));
+    for (int i = 0; i < c.x_layers; ++i) {
+      const std::string x = b + "encoder.x_layers." + std::to_string(i);
+      add_att_names(v, x + ".visual_attention", "att");
+      add_att_names(v, x + ".lang_self_att", "self");
+      add_att_names(v, x + ".visn_self_att", "self");
+      add_linear_names(v, x + ".lang_inter.dense");
+      add_linear_names(v, x + ".lang_output.dense");
+      add_linear_names(v, x + ".lang_output.LayerNorm");
+      add_linear_names(v, x + ".visn_inter.dense");
+      add_linear_names(v, x + ".visn_output.dense");
+      add_linear_names(v, x + ".visn_output.LayerNorm");
+    }
+    add_linear_names(v, b + "pooler.dense");
+  } else {
+    const std::string u = "uniter.";
+    v.push_back(u + "embeddings.word_embeddings.weight");
+    v.push_back(u + "embeddings.position_embeddings.weight");
+    v.push_back(u + "embeddings.token_type_embeddings.weight");
+    add_linear_names(v, u + "embeddings.LayerNorm");
+    add_linear_names(v, u + "img_embeddings.img_linear");
+    add_linear_names(v, u + "img_embeddings.img_layer_norm");
+    add_linear_names(v, u + "img_embeddings.pos_linear");
+    add_linear_names(v, u + "img_embeddings.pos_layer_norm");
+    add_linear_names(v, u + "img_embeddings.LayerNorm");
+    for (int i = 0; i < c.l_layers; ++i) add_bert_layer_names(v, u + "encoder.layer." + std::to_string(i));
+    add_linear_names(v, u + "pooler.dense");
+  }
+  if (c.num_answers > 0) {
+    add_linear_names(v, "logit_fc.0");
+    add_linear_names(v, "logit_fc.2");
+    add_linear_names(v, "logit_fc.3");
+  }
+}
+
+std::string strip_prefix(const char* key) {
+  std::string k(key);
+  const char* prefixes[] = {"module.", "lxrt_encoder.model.", "encoder.model.", "module."};
+  for (const char* p : prefixes) {
+    const size_t n = strlen(p);
+    if (k.compare(0, n, p) == 0) k = k.substr(n);
+  }
+  return k;
+}
+
+int get_raw(rgqa_handle* h, const std::string& name, int64_t d0, int64_t d1, float** out) {
+  auto it = h->raw.find(name);
+  RGQA_CHECK(it != h->raw.end(), "weight '%s' was never loaded", name.c_str());
+  const RawTensor& t = it->second;
+  const int64_t want = d1 > 0 ? d0 * d1 : d0;
+  RGQA_CHECK(t.numel == want, "weight '%s': expected %lld elements, got %lld", name.c_str(),
+             static_cast<long long>(want), static_cast<long long>(t.numel));
+  *out = t.p;
+  return 0;
+}
+
+// Pack rows of up to three fp32 [n_i, K] matrices into one [sum n_i, K] matrix of the handle's precision.
+int pack_matrix(rgqa_handle* h, const float* const* srcs, const int* rows, int nsrc, int K, void** out) {
+  int N = 0;
+  for (int i = 0; i < nsrc; ++i) N += rows[i];
+  const size_t esz = act_size(h);
+  void* dst = nullptr;
+  RGQA_CUDA_OK(cudaMalloc(&dst, static_cast<size_t>(N) * K * esz));
+  h->owned.push_back(dst);
+  size_t off = 0;
+  for (int i = 0; i < nsrc; ++i) {
+    const long long n = static_cast<long long>(rows[i]) * K;
+    if (h->cfg.precision == RGQA_PREC_BF16) {
+      if (cast_f32_to_bf16(nullptr, srcs[i], static_cast<char*>(dst) + off * 2, n)) return 1;
+    } else {
+      RGQA_CUDA_OK(cudaMemcpy(static_cast<char*>(dst) + off * 4, srcs[i], n * 4, cudaMemcpyDeviceToDevice));
+    }
+    off += n;
+  }
+  *out = dst;
+  return 0;
+}
+
+int pack_vec(rgqa_handle* h, const float* const* srcs, const int* lens, int nsrc, float** out) {
+  int N = 0;
+  for (int i = 0; i < nsrc; ++i) N += lens[i];
+  float* dst = nullptr;
+  RGQA_CUDA_OK(cudaMalloc(&dst, static_cast<size_t>(N) * 4));
+  h->owned.push_back(dst);
+  size_t off = 0;
+  for (int i = 0; i < nsrc; ++i) {
+    RGQA_CUDA_OK(cudaMemcpy(dst + off, srcs[i], static_cast<size_t>(lens[i]) * 4, cudaMemcpyDeviceToDevice));
+    off += lens[i];
+  }
+  *out = dst;
+  return 0;
+}
+
+int make_linear(rgqa_handle* h, const std::string& p, int N, int K, Linear* out) {
+  float *w, *b;
+  if (get_raw(h, p + ".weight", N, K, &w)) return 1;
+  if (get_raw(h, p + ".bias", N, 0, &b)) return 1;
+  const float* ws[1] = {w};
+  const int rows[1] = {N};
+  if (pack_matrix(h, ws, rows, 1, K, &out->W)) return 1;
+  const float* bs[1] = {b};
+  if (pack_vec(h, bs, rows, 1, &out->b)) return 1;
+  out->N = N;
+  out->K = K;
+  return 0;
+}
+int make_ln(rgqa_handle* h, const std::string& p, int H, LNp* out) {
+  float *g, *b;
+  if (get_raw(h, p + ".weight", H, 0, &g)) return 1;
+  if (get_raw(h, p + ".bias", H, 0, &b)) return 1;
+  const float* gs[1] = {g};
+  const float* bs[1] = {b};
+  const int n[1] = {H};
+  if (pack_vec(h, gs, n, 1, &out->g)) return 1;
+  if (pack_vec(h, bs, n, 1, &out->b)) return 1;
+  return 0;
+}
+int make_att(rgqa_handle* h, const std::string& p, const char* self_name, AttW* out) {
+  const int H = h->cfg.hidden;
+  float *wq, *wk, *wv, *bq, *bk, *bv;
+  const std::string s = p + "." + self_name;
+  if (get_raw(h, s + ".query.weight", H, H, &wq) || get_raw(h, s + ".key.weight", H, H, &wk) ||
+      get_raw(h, s + ".value.weight", H, H, &wv) || get_raw(h, s + ".query.bias", H, 0, &bq) ||
+      get_raw(h, s + ".key.bias", H, 0, &bk) || get_raw(h, s + ".value.bias", H, 0, &bv))
+    return 1;
+  const float* ws[3] = {wq, wk, wv};
+  const float* bs[3] = {bq, bk, bv};
+  const int rows[3] = {H, H, H};
+  if (pack_matrix(h, ws, rows, 3, H, &out->qkv.W)) return 1;
+  if (pack_vec(h, bs, rows, 3, &out->qkv.b)) return 1;
+  out->qkv.N = 3 * H;
+  out->qkv.K = H;
+  if (make_linear(h, p + ".output.dense", H, H, &out->out)) return 1;
+  return make_ln(h, p + ".output.LayerNorm", H, &out->ln);
+}
+int make_ffn(rgqa_handle* h, const std::string& inter, const std::string& outp, FfnW* out) {
+  const int H = h->cfg.hidden, I = h->cfg.intermediate;
+  if (make_linear(h, inter + ".dense", I, H, &out->inter)) return 1;
+  if (make_linear(h, outp + ".dense", H, I, &out->out)) return 1;
+  return make_ln(h, outp + ".LayerNorm", H, &out->ln);
+}
+int make_bert_layer(rgqa_handle* h, const std::string& p, LayerW* out) {
+  if (make_att(h, p + ".attention", "self", &out->att)) return 1;
+  return make_ffn(h, p + ".intermediate", p + ".output", &out->ffn);
+}
+int copy_raw(rgqa_handle* h, const std::string& name, int64_t d0, int64_t d1, float** out) {
+  float* src;
+  if (get_raw(h, name, d0, d1, &src)) return 1;
+  const float* s[1] = {src};
+  const int n[1] = {static_cast<int>(d1 > 0 ? d0 * d1 : d0)};
+  return pack_vec(h, s, n, 1, out);
+}
+
+// ---- dtype-dispatched primitives over the handle's precision ------------------------------------
+int gemm(rgqa_handle* h, cudaStream_t st, const void* A, long long lda, const Linear& lin, const void* resid,
+         long long ldr, void* out, long long ldo, int out_f32, int M, int epi) {
+  if (h->cfg.precision == RGQA_PREC_BF16)
+    return gemm_bf16(st, A, lda, lin.W, lin.K, lin.b, resid, ldr, out, ldo, out_f32, M, lin.N, lin.K, epi);
+  RGQA_CHECK(out_f32, "fp32 path writes fp32 only");
+  return gemm_f32(st, static_cast<const float*>(A), lda, static_cast<const float*>(lin.W), lin.K, lin.b,
+                  static_cast<const float*>(resid), ldr, static_cast<float*>(out), ldo, M, lin.N, lin.K, epi);
+}
+
+inline char* rows_at(void* base, long long row, long long ld, size_t esz) {
+  return static_cast<char*>(base) + static_cast<size_t>(row) * ld * esz;
+}
+
+// self-attention block + output projection + LN on rows [r0, r0 + B*S) : in -> out
+int att_block(rgqa_handle* h, cudaStream_t st, const AttW& w, void* in, void* out, long long r0, int B, int S,
+              const int32_t* key_mask) {
+  const int H = h->cfg.hidden;
+  const size_t es = act_size(h);
+  const int dt = act_dtype(h);
+  const int M = B * S;
+  const int of32 = dt == DT_F32;
+  char* x = rows_at(in, r0, H, es);
+  char* qkv = rows_at(h->qkv.p, r0, 3 * H, es);
+  char* ctx = rows_at(h->ctx.p, r0, H, es);
+  float* pre = reinterpret_cast<float*>(rows_at(h->pre.p, r0, H, 4));
+  if (gemm(h, st, x, H, w.qkv, nullptr, 0, qkv, 3 * H, of32, M, EPI_BIAS)) return 1;
+  if (attention(st, dt, qkv, 3 * H, qkv + static_cast<size_t>(H) * es, 3 * H, qkv + static_cast<size_t>(2 * H) * es,
+                3 * H, key_mask, ctx, H, B, S, S, h->cfg.heads))
+    return 1;
+  if (gemm(h, st, ctx, H, w.out, x, H, pre, H, 1, M, EPI_RESID)) return 1;
+  return layernorm(st, dt, pre, H, w.ln.g, w.ln.b, rows_at(out, r0, H, es), M, H, h->cfg.ln_eps);
+}
+
+// FFN block on rows [r0, r0 + M): in -> out
+int ffn_block(rgqa_handle* h, cudaStream_t st, const FfnW& w, void* in, void* out, long long r0, int M) {
+  const int H = h->cfg.hidden, I = h->cfg.intermediate;
+  const size_t es = act_size(h);
+  const int dt = act_dtype(h);
+  const int of32 = dt == DT_F32;
+  char* x = rows_at(in, r0, H, es);
+  char* inter = rows_at(h->inter.p, r0, I, es);
+  float* pre = reinterpret_cast<float*>(rows_at(h->pre.p, r0, H, 4));
+  if (gemm(h, st, x, H, w.inter, nullptr, 0, inter, I, of32, M, EPI_GELU)) return 1;
+  if (gemm(h, st, inter, I, w.out, x, H, pre, H, 1, M, EPI_RESID)) return 1;
+  return layernorm(st, dt, pre, H, w.ln.g, w.ln.b, rows_at(out, r0, H, es), M, H, h->cfg.ln_eps);
+}
+
+int ensure_workspace(rgqa_handle* h, long long Mt, long long Mv, int B) {
+  const int H = h->cfg.hidden, I = h->cfg.intermediate;
+  const size_t es = act_size(h);
+  if (h->hidA.ensure(Mt * H * es) || h->hidB.ensure(Mt * H * es) || h->qkv.ensure(Mt * 3 * H * es) ||
+      h->ctx.ensure(Mt * H * es) || h->inter.ensure(Mt * I * es) || h->pre.ensure(Mt * H * 4))
+    return 1;
+  if (h->cfg.precision == RGQA_PREC_BF16 && h->featb.ensure(Mv * h->cfg.visual_feat_dim * 2)) return 1;
+  // head scratch: pooled f32 [B,H] | pooled act [B,H] | h1 f32 [B,2H] | h1n act [B,2H] | logits f32 [B,A]
+  const size_t head = static_cast<size_t>(B) * (H * 4 + H * es + 2 * H * 4 + 2 * H * es + (h->cfg.num_answers + 8) * 4);
+  return h->headbuf.ensure(head + 1024);
+}
+
+// pooler + answer head on the hidden rows `hid` (first token of each sample, row stride S*H)
+int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, float* pooled_out, float* logits_out) {
+  const int H = h->cfg.hidden, A = h->cfg.num_answers;
+  const size_t es = act_size(h);
+  const int dt = act_dtype(h);
+  const int of32 = dt == DT_F32;
+  char* base = static_cast<char*>(h->headbuf.p);
+  float* pooled = reinterpret_cast<float*>(base);
+  char* pooled_act = base + static_cast<size_t>(B) * H * 4;
+  float* h1 = reinterpret_cast<float*>(pooled_act + static_cast<size_t>(B) * H * es);
+  char* h1n = reinterpret_cast<char*>(h1) + static_cast<size_t>(B) * 2 * H * 4;
+  float* logits_ws = reinterpret_cast<float*>(h1n + static_cast<size_t>(B) * 2 * H * es);
+  // 16-byte align the logits scratch
+  logits_ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(logits_ws) + 15) & ~static_cast<uintptr_t>(15));
+
+  float* pdst = pooled_out != nullptr ? pooled_out : pooled;
+  if (gemm(h, st, hid, static_cast<long long>(S) * H, h->pooler, nullptr, 0, pdst, H, 1, B, EPI_TANH)) return 1;
+  if (A <= 0 || logits_out == nullptr) return 0;
+  const void* a0 = pdst;
+  if (dt == DT_BF16) {
+    if (cast_f32_to_bf16(st, pdst, pooled_act, static_cast<long long>(B) * H)) return 1;
+    a0 = pooled_act;
+  }
+  if (gemm(h, st, a0, H, h->fc0, nullptr, 0, h1, 2 * H, 1, B, EPI_GELU)) return 1;
+  if (layernorm(st, dt, h1, 2 * H, h->fc_ln.g, h->fc_ln.b, h1n, B, 2 * H, h->cfg.ln_eps)) return 1;
+  (void)of32;
+  (void)logits_ws;
+  return gemm(h, st, h1n, 2 * H, h->fc3, nullptr, 0, logits_out, A, 1, B, EPI_BIAS);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+#pragma GCC visibility push(default)
+extern "C" {
+
+int rgqa_abi_version(void) { return RGQA_ABI_VERSION; }
+const char* rgqa_last_error(void) { return g_err; }
+
+int rgqa_create(const rgqa_config* cfg, rgqa_handle** out) {
+  RGQA_CHECK(cfg != nullptr && out != nullptr, "rgqa_create: null argument");
+  RGQA_CHECK(cfg->arch == RGQA_ARCH_LXMERT || cfg->arch == RGQA_ARCH_UNITER, "rgqa_create: unknown arch %d", cfg->arch);
+  RGQA_CHECK(cfg->precision == RGQA_PREC_FP32 || cfg->precision == RGQA_PREC_BF16, "rgqa_create: unknown precision %d",
+             cfg->precision);
+  RGQA_CHECK(cfg->hidden == 768 && cfg->heads == 12, "rgqa_create: kernels are built for hidden=768, heads=12 (got %d, %d)",
+             cfg->hidden, cfg->heads);
+  RGQA_CHECK(cfg->intermediate % 64 == 0 && cfg->visual_feat_dim % 64 == 0, "rgqa_create: K dims must be multiples of 64");
+  RGQA_CHECK(cfg->visual_pos_dim >= 1 && cfg->visual_pos_dim <= 8, "rgqa_create: visual_pos_dim out of range");
+  RGQA_CHECK(cfg->num_rois >= 1 && cfg->num_rois <= 64, "rgqa_create: num_rois must be in [1,64]");
+  RGQA_CHECK(cfg->l_layers >= 0 && cfg->x_layers >= 0 && cfg->r_layers >= 0, "rgqa_create: negative layer count");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  RGQA_CHECK(e == cudaSuccess && ndev > 0, "rgqa_create: no CUDA device (%s); this library has no CPU path",
+             cudaGetErrorString(e));
+  rgqa_handle* h = new rgqa_handle();
+  h->cfg = *cfg;
+  build_names(h);
+  *out = h;
+  return 0;
+}
+
+void rgqa_destroy(rgqa_handle* h) {
+  if (h == nullptr) return;
+  for (auto& kv : h->raw)
+    if (kv.second.p != nullptr) cudaFree(kv.second.p);
+  for (void* p : h->owned) cudaFree(p);
+  h->hidA.release();
+  h->hidB.release();
+  h->qkv.release();
+  h->ctx.release();
+  h->inter.release();
+  h->pre.release();
+  h->featb.release();
+  h->headbuf.release();
+  h->mahabuf.release();
+  if (h->maha_mu) cudaFree(h->maha_mu);
+  if (h->maha_P) cudaFree(h->maha_P);
+  if (h->maha_m) cudaFree(h->maha_m);
+  delete h;
+}
+
+int rgqa_num_weights(const rgqa_handle* h) { return h == nullptr ? 0 : static_cast<int>(h->names.size()); }
+const char* rgqa_weight_name(const rgqa_handle* h, int index) {
+  if (h == nullptr || index < 0 || index >= static_cast<int>(h->names.size())) return nullptr;
+  return h->names[index].c_str();
+}
+
+int rgqa_load_weight(rgqa_handle* h, const char* ref_key, const float* data, int on_device, const int64_t* shape,
+                     int ndim) {
+  RGQA_CHECK(h != nullptr && ref_key != nullptr && data != nullptr, "rgqa_load_weight: null argument");
+  RGQA_CHECK(ndim >= 1 && ndim <= 4, "rgqa_load_weight: bad ndim %d for '%s'", ndim, ref_key);
+  const std::string key = strip_prefix(ref_key);
+  bool expected = false;
+  for (const auto& n : h->names)
+    if (n == key) {
+      expected = true;
+      break;
+    }
+  RGQA_CHECK(expected, "rgqa_load_weight: '%s' is not a tensor of this model", ref_key);
+  RawTensor t;
+  t.numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    RGQA_CHECK(shape[i] > 0, "rgqa_load_weight: non-positive dim for '%s'", ref_key);
+    t.shape.push_back(shape[i]);
+    t.numel *= shape[i];
+  }
+  auto it = h->raw.find(key);
+  if (it != h->raw.end()) {
+    cudaFree(it->second.p);
+    h->raw.erase(it);
+  }
+  RGQA_CUDA_OK(cudaMalloc(&t.p, static_cast<size_t>(t.numel) * 4));
+  RGQA_CUDA_OK(cudaMemcpy(t.p, data, static_cast<size_t>(t.numel) * 4,
+                          on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  h->raw[key] = t;
+  h->finalized = false;
+  return 0;
+}
+
+int rgqa_finalize_weights(rgqa_handle* h) {
+  RGQA_CHECK(h != nullptr, "rgqa_finalize_weights: null handle");
+  for (const auto& n : h->names)
+    RGQA_CHECK(h->raw.count(n) == 1, "rgqa_finalize_weights: missing tensor '%s'", n.c_str());
+  for (void* p : h->owned) cudaFree(p);
+  h->owned.clear();
+  h->l_layers.clear();
+  h->r_layers.clear();
+  h->x_layers.clear();
+  const rgqa_config& c = h->cfg;
+  const int H = c.hidden;
+  if (c.arch == RGQA_ARCH_LXMERT) {
+    const std::string b = "bert.";
+    if (copy_raw(h, b + "embeddings.word_embeddings.weight", c.vocab_size, H, &h->word) ||
+        copy_raw(h, b + "embeddings.position_embeddings.weight", c.max_position, H, &h->posemb) ||
+        copy_raw(h, b + "embeddings.token_type_embeddings.weight", c.type_vocab, H, &h->typeemb) ||
+        make_ln(h, b + "embeddings.LayerNorm", H, &h->emb_ln) ||
+        make_linear(h, b + "encoder.visn_fc.visn_fc", H, c.visual_feat_dim, &h->visn_fc) ||
+        make_ln(h, b + "encoder.visn_fc.visn_layer_norm", H, &h->visn_ln) ||
+        copy_raw(h, b + "encoder.visn_fc.box_fc.weight", H, c.visual_pos_dim, &h->box_W) ||
+        copy_raw(h, b + "encoder.visn_fc.box_fc.bias", H, 0, &h->box_b) ||
+        make_ln(h, b + "encoder.visn_fc.box_layer_norm", H, &h->box_ln))
+      return 1;
+    h->l_layers.resize(c.l_layers);
+    h->r_layers.resize(c.r_layers);
+    h->x_layers.resize(c.x_layers);
+    for (int i = 0; i < c.l_layers; ++i)
+      if (make_bert_layer(h, b + "encoder.layer." + std::to_string(i), &h->l_layers[i])) return 1;
+    for (int i = 0; i < c.r_layers; ++i)
+      if (make_bert_layer(h, b + "encoder.r_layers." + std::to_string(i), &h->r_layers[i])) return 1;
+    for (int i = 0; i < c.x_layers; ++i) {
+      const std::string x = b + "encoder.x_layers." + std::to_string(i);
+      XLayerW& w = h->x_layers[i];
+      if (make_att(h, x + ".visual_attention", "att", &w.cross) || make_att(h, x + ".lang_self_att", "self", &w.lang_self) ||
+          make_att(h, x + ".visn_self_att", "self", &w.visn_self) ||
+          make_ffn(h, x + ".lang_inter", x + ".lang_output", &w.lang_ffn) ||
+          make_ffn(h, x + ".visn_inter", x + ".visn_output", &w.visn_ffn))
+        return 1;
+    }
+    if (make_linear(h, b + "pooler.dense", H, H, &h->pooler)) return 1;
+  } else {
+    const std::string u = "uniter.";
+    if (copy_raw(h, u + "embeddings.word_embeddings.weight", c.vocab_size, H, &h->word) ||
+        copy_raw(h, u + "embeddings.position_embeddings.weight", c.max_position, H, &h->posemb) ||
+        copy_raw(h, u + "embeddings.token_type_embeddings.weight", c.type_vocab, H, &h->typeemb) ||
+        make_ln(h, u + "embeddings.LayerNorm", H, &h->emb_ln) ||
+        make_linear(h, u + "img_embeddings.img_linear", H, c.visual_feat_dim, &h->visn_fc) ||
+        make_ln(h, u + "img_embeddings.img_layer_norm", H, &h->visn_ln) ||
+        copy_raw(h, u + "img_embeddings.pos_linear.weight", H, c.visual_pos_dim, &h->box_W) ||
+        copy_raw(h, u + "img_embeddings.pos_linear.bias", H, 0, &h->box_b) ||
+        make_ln(h, u + "img_embeddings.pos_layer_norm", H, &h->box_ln) ||
+        make_ln(h, u + "img_embeddings.LayerNorm", H, &h->img_ln))
+      return 1;
+    h->l_layers.resize(c.l_layers);
+    for (int i = 0; i < c.l_layers; ++i)
+      if (make_bert_layer(h, u + "encoder.layer." + std::to_string(i), &h->l_layers[i])) return 1;
+    if (make_linear(h, u + "pooler.dense", H, H, &h->pooler)) return 1;
+  }
+  if (c.num_answers > 0) {
+    if (make_linear(h, "logit_fc.0", 2 * H, H, &h->fc0) || make_ln(h, "logit_fc.2", 2 * H, &h->fc_ln) ||
+        make_linear(h, "logit_fc.3", c.num_answers, 2 * H, &h->fc3))
+      return 1;
+  }
+  RGQA_CUDA_OK(cudaDeviceSynchronize());
+  // the unpacked fp32 copies are no longer needed
+  for (auto& kv : h->raw) {
+    cudaFree(kv.second.p);
+    kv.second.p = nullptr;
+  }
+  h->raw.clear();
+  h->finalized = true;
+  return 0;
+}
+
+int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos,
+                        const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
+                        float* pooled_out, float* logits_out) {
+  RGQA_CHECK(h != nullptr, "rgqa_lxmert_forward: null handle");
+  RGQA_CHECK(h->cfg.arch == RGQA_ARCH_LXMERT, "rgqa_lxmert_forward: handle was created for another architecture");
+  RGQA_CHECK(h->finalized, "rgqa_lxmert_forward: weights are not finalized");
+  RGQA_CHECK(feat != nullptr && pos != nullptr && ids != nullptr && mask != nullptr, "rgqa_lxmert_forward: null input");
+  RGQA_CHECK(B > 0, "rgqa_lxmert_forward: empty batch");
+  RGQA_CHECK(L >= 2 && L <= 64, "rgqa_lxmert_forward: L=%d out of range [2,64]", L);
+  RGQA_CHECK(logits_out == nullptr || h->cfg.num_answers > 0, "rgqa_lxmert_forward: handle has no answer head");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const rgqa_config& c = h->cfg;
+  const int H = c.hidden, V = c.num_rois;
+  const long long Ml = static_cast<long long>(B) * L, Mv = static_cast<long long>(B) * V, Mt = Ml + Mv;
+  RGQA_CHECK(Mt < (1LL << 30), "rgqa_lxmert_forward: batch too large");
+  if (ensure_workspace(h, Mt, Mv, B)) return 1;
+  const size_t es = act_size(h);
+  const int dt = act_dtype(h);
+  void* cur = h->hidA.p;
+  void* alt = h->hidB.p;
+
+  // ---- embeddings (modeling.py:876) ----
+  if (embed_ln(st, dt, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, cur, B, L, H, c.vocab_size,
+               c.max_position, c.type_vocab, c.ln_eps))
+    return 1;
+  // ---- visual feature encoder (modeling.py:507-517) ----
+  {
+    const void* a = feat;
+    if (c.precision == RGQA_PREC_BF16) {
+      if (feat_dtype == RGQA_DT_F32) {
+        if (cast_f32_to_bf16(st, static_cast<const float*>(feat), h->featb.p, Mv * c.visual_feat_dim)) return 1;
+        a = h->featb.p;
+      }
+    } else {
+      RGQA_CHECK(feat_dtype == RGQA_DT_F32, "fp32 path needs fp32 features");
+    }
+    float* pre = reinterpret_cast<float*>(rows_at(h->pre.p, Ml, H, 4));
+    if (gemm(h, st, a, c.visual_feat_dim, h->visn_fc, nullptr, 0, pre, H, 1, static_cast<int>(Mv), EPI_BIAS)) return 1;
+    if (visn_combine(st, dt, pre, pos, c.visual_pos_dim, h->box_W, h->box_b, h->visn_ln.g, h->visn_ln.b, h->box_ln.g,
+                     h->box_ln.b, rows_at(cur, Ml, H, es), static_cast<int>(Mv), H, c.ln_eps))
+      return 1;
+  }
+  // ---- language layers (modeling.py:553-554): rows [0, Ml) ----
+  for (int i = 0; i < c.l_layers; ++i) {
+    if (att_block(h, st, h->l_layers[i].att, cur, alt, 0, B, L, mask)) return 1;
+    if (ffn_block(h, st, h->l_layers[i].ffn, alt, cur, 0, static_cast<int>(Ml))) return 1;
+  }
+  // ---- object-relational layers (modeling.py:557-558): rows [Ml, Mt), no key mask (entry.py:109) ----
+  for (int i = 0; i < c.r_layers; ++i) {
+    if (att_block(h, st, h->r_layers[i].att, cur, alt, Ml, B, V, nullptr)) return 1;
+    if (ffn_block(h, st, h->r_layers[i].ffn, alt, cur, Ml, static_cast<int>(Mv))) return 1;
+  }
+  // ---- cross-modality layers (modeling.py:477-488) ----
+  for (int i = 0; i < c.x_layers; ++i) {
+    const XLayerW& w = h->x_layers[i];
+    const int of32 = dt == DT_F32;
+    char* qkv = static_cast<char*>(h->qkv.p);
+    char* qkv_v = rows_at(h->qkv.p, Ml, 3 * H, es);
+    // cross attention: ONE BertCrossattLayer serves both directions on the pre-update inputs (:455-459)
+    if (gemm(h, st, cur, H, w.cross.qkv, nullptr, 0, qkv, 3 * H, of32, static_cast<int>(Mt), EPI_BIAS)) return 1;
+    // lang queries attend visual keys/values (no mask)
+    if (attention(st, dt, qkv, 3 * H, qkv_v + static_cast<size_t>(H) * es, 3 * H, qkv_v + static_cast<size_t>(2 * H) * es,
+                  3 * H, nullptr, h->ctx.p, H, B, L, V, c.heads))
+      return 1;
+    // visual queries attend language keys/values (language mask)
+    if (attention(st, dt, qkv_v, 3 * H, qkv + static_cast<size_t>(H) * es, 3 * H, qkv + static_cast<size_t>(2 * H) * es,
+                  3 * H, mask, rows_at(h->ctx.p, Ml, H, es), H, B, V, L, c.heads))
+      return 1;
+    if (gemm(h, st, h->ctx.p, H, w.cross.out, cur, H, h->pre.p, H, 1, static_cast<int>(Mt), EPI_RESID)) return 1;
+    if (layernorm(st, dt, static_cast<const float*>(h->pre.p), H, w.cross.ln.g, w.cross.ln.b, alt, static_cast<int>(Mt), H,
+                  c.ln_eps))
+      return 1;
+    // self attention per stream (:461-465): alt -> cur
+    if (att_block(h, st, w.lang_self, alt, cur, 0, B, L, mask)) return 1;
+    if (att_block(h, st, w.visn_self, alt, cur, Ml, B, V, nullptr)) return 1;
+    // FFNs per stream (:467-475): cur -> alt
+    if (ffn_block(h, st, w.lang_ffn, cur, alt, 0, static_cast<int>(Ml))) return 1;
+    if (ffn_block(h, st, w.visn_ffn, cur, alt, Ml, static_cast<int>(Mv))) return 1;
+    void* t = cur;
+    cur = alt;
+    alt = t;
+  }
+  // ---- pooler + answer head (modeling.py:884, gqa_model.py:40-41) ----
+  if (pooled_out == nullptr && logits_out == nullptr) return 0;
+  return head_block(h, st, cur, B, L, pooled_out, logits_out);
+}
+
+int rgqa_uniter_forward(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos7,
+                        const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
+                        float* pooled_out, float* logits_out) {
+  RGQA_CHECK(h != nullptr, "rgqa_uniter_forward: null handle");
+  RGQA_CHECK(h->cfg.arch == RGQA_ARCH_UNITER, "rgqa_uniter_forward: handle was created for another architecture");
+  RGQA_CHECK(h->finalized, "rgqa_uniter_forward: weights are not finalized");
+  RGQA_CHECK(feat != nullptr && pos7 != nullptr && ids != nullptr && mask != nullptr, "rgqa_uniter_forward: null input");
+  RGQA_CHECK(B > 0, "rgqa_uniter_forward: empty batch");
+  const rgqa_config& c = h->cfg;
+  const int H = c.hidden, V = c.num_rois;
+  const int S = L + V;
+  RGQA_CHECK(L >= 2 && S <= 64, "rgqa_uniter_forward: L + num_rois = %d exceeds 64", S);
+  RGQA_CHECK(c.type_vocab >= 2, "rgqa_uniter_forward: needs token type 1 for image tokens");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long Ml = static_cast<long long>(B) * L, Mv = static_cast<long long>(B) * V, Mt = Ml + Mv;
+  if (ensure_workspace(h, Mt, Mv, B)) return 1;
+  // joint key mask [B, S] = [text mask | ones] lives at the tail of the head scratch
+  const size_t es = act_size(h);
+  const int dt = act_dtype(h);
+  if (h->mahabuf.ensure(static_cast<size_t>(B) * S * 4 + 256)) return 1;
+  int32_t* jmask = static_cast<int32_t*>(h->mahabuf.p);
+
+  // text embeddings -> ctx buffer rows [0, Ml) (scratch), image embeddings -> ctx rows [Ml, Mt),
+  // then interleave per sample into hidA as [B, S, H]
+  if (embed_ln(st, dt, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, h->ctx.p, B, L, H, c.vocab_size,
+               c.max_position, c.type_vocab, c.ln_eps))
+    return 1;
+  {
+    const void* a = feat;
+    if (c.precision == RGQA_PREC_BF16) {
+      if (feat_dtype == RGQA_DT_F32) {
+        if (cast_f32_to_bf16(st, static_cast<const float*>(feat), h->featb.p, Mv * c.visual_feat_dim)) return 1;
+        a = h->featb.p;
+      }
+    } else {
+      RGQA_CHECK(feat_dtype == RGQA_DT_F32, "fp32 path needs fp32 features");
+    }
+    float* pre = reinterpret_cast<float*>(rows_at(h->pre.p, Ml, H, 4));
+    if (gemm(h, st, a, c.visual_feat_dim, h->visn_fc, nullptr, 0, pre, H, 1, static_cast<int>(Mv), EPI_BIAS)) return 1;
+    // image tokens carry token type 1 (uniter/entry.py:92, modeling.py:629)
+    if (uniter_img_combine(st, dt, pre, pos7, c.visual_pos_dim, h->box_W, h->box_b, h->visn_ln.g, h->visn_ln.b,
+                           h->box_ln.g, h->box_ln.b, h->typeemb + H, h->img_ln.g, h->img_ln.b,
+                           rows_at(h->ctx.p, Ml, H, es), static_cast<int>(Mv), H, c.ln_eps))
+      return 1;
+  }
+  void* cur = h->hidA.p;
+  void* alt = h->hidB.p;
+  // per-sample interleave: 2-D strided copies on the stream (rows of one sample are contiguous)
+  RGQA_CUDA_OK(cudaMemcpy2DAsync(cur, static_cast<size_t>(S) * H * es, h->ctx.p, static_cast<size_t>(L) * H * es,
+                                 static_cast<size_t>(L) * H * es, B, cudaMemcpyDeviceToDevice, st));
+  RGQA_CUDA_OK(cudaMemcpy2DAsync(static_cast<char*>(cur) + static_cast<size_t>(L) * H * es, static_cast<size_t>(S) * H * es,
+                                 rows_at(h->ctx.p, Ml, H, es), static_cast<size_t>(V) * H * es,
+                                 static_cast<size_t>(V) * H * es, B, cudaMemcpyDeviceToDevice, st));
+  RGQA_CUDA_OK(cudaMemsetAsync(jmask, 0, static_cast<size_t>(B) * S * 4, st));
+  RGQA_CUDA_OK(cudaMemcpy2DAsync(jmask, static_cast<size_t>(S) * 4, mask, static_cast<size_t>(L) * 4,
+                                 static_cast<size_t>(L) * 4, B, cudaMemcpyDeviceToDevice, st));
+  {
+    // ones for the image tokens: reuse the cast kernel's neighbour — a tiny fill via memset of 0x01 would
+    // give 0x01010101 (non-zero = keep), which is all the attention kernel tests for
+    RGQA_CUDA_OK(cudaMemset2DAsync(reinterpret_cast<char*>(jmask) + static_cast<size_t>(L) * 4, static_cast<size_t>(S) * 4,
+                                   1, static_cast<size_t>(V) * 4, B, st));
+  }
+  for (int i = 0; i < c.l_layers; ++i) {
+    if (att_block(h, st, h->l_layers[i].att, cur, alt, 0, B, S, jmask)) return 1;
+    if (ffn_block(h, st, h->l_layers[i].ffn, alt, cur, 0, static_cast<int>(Mt))) return 1;
+  }
+  if (pooled_out == nullptr && logits_out == nullptr) return 0;
+  return head_block(h, st, cur, B, S, pooled_out, logits_out);
+}
+
+int rgqa_set_maha(rgqa_handle* h, const float* mu, const float* precision, int on_device) {
+  RGQA_CHECK(h != nullptr && mu != nullptr && precision != nullptr, "rgqa_set_maha: null argument");
+  const int H = h->cfg.hidden, A = h->cfg.num_answers;
+  RGQA_CHECK(A > 0, "rgqa_set_maha: handle has no answer classes");
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (h->maha_mu == nullptr) RGQA_CUDA_OK(cudaMalloc(&h->maha_mu, static_cast<size_t>(A) * H * 4));
+  if (h->maha_P == nullptr) RGQA_CUDA_OK(cudaMalloc(&h->maha_P, static_cast<size_t>(H) * H * 4));
+  if (h->maha_m == nullptr) RGQA_CUDA_OK(cudaMalloc(&h->maha_m, static_cast<size_t>(A) * 4));
+  RGQA_CUDA_OK(cudaMemcpy(h->maha_mu, mu, static_cast<size_t>(A) * H * 4, kind));
+  RGQA_CUDA_OK(cudaMemcpy(h->maha_P, precision, static_cast<size_t>(H) * H * 4, kind));
+  // m_c = mu_c^T P mu_c :  T = mu · P  (gemm_f32 computes A·Wᵀ, so hand it Pᵀ via a transposed copy)
+  float *PT = nullptr, *T = nullptr;
+  RGQA_CUDA_OK(cudaMalloc(&PT, static_cast<size_t>(H) * H * 4));
+  RGQA_CUDA_OK(cudaMalloc(&T, static_cast<size_t>(A) * H * 4));
+  int rc = 0;
+  {
+    // P is symmetric up to rounding; use (P + Pᵀ)/2 so x^T P x is evaluated on its symmetric part exactly
+    std::vector<float> hp(static_cast<size_t>(H) * H), hs(static_cast<size_t>(H) * H);
+    cudaMemcpy(hp.data(), h->maha_P, hp.size() * 4, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < H; ++i)
+      for (int j = 0; j < H; ++j) hs[static_cast<size_t>(i) * H + j] = 0.5f * (hp[static_cast<size_t>(i) * H + j] + hp[static_cast<size_t>(j) * H + i]);
+    cudaMemcpy(h->maha_P, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(PT, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice);
+  }
+  rc = gemm_f32(nullptr, h->maha_mu, H, PT, H, nullptr, nullptr, 0, T, H, A, H, H, EPI_BIAS);
+  if (!rc) rc = rowdot(nullptr, T, h->maha_mu, h->maha_m, A, H);
+  cudaDeviceSynchronize();
+  cudaFree(PT);
+  cudaFree(T);
+  if (rc) return 1;
+  h->has_maha = true;
+  return 0;
+}
+
+static int maha_core(cudaStream_t st, const float* x, const float* mu, const float* Psym, const float* m, int B, int A,
+                     int H, float* work, float* score, int32_t* label, float* full) {
+  float* t = work;                                   // [B, H]
+  float* q = t + static_cast<size_t>(B) * H;         // [B]
+  float* G = q + ((static_cast<size_t>(B) + 3) & ~static_cast<size_t>(3));  // [B, A]
+  if (gemm_f32(st, x, H, Psym, H, nullptr, nullptr, 0, t, H, B, H, H, EPI_BIAS)) return 1;  // t = x·Psymᵀ = x·Psym
+  if (rowdot(st, t, x, q, B, H)) return 1;
+  if (gemm_f32(st, t, H, mu, H, nullptr, nullptr, 0, G, A, B, A, H, EPI_BIAS)) return 1;    // G = t·muᵀ
+  return maha_finish(st, q, G, A, m, B, A, score, label, full);
+}
+
+int rgqa_score(rgqa_handle* h, void* stream, int mode, const float* logits, const float* pooled, int B,
+               float* score_out, int32_t* label_out, float* maha_full_out) {
+  RGQA_CHECK(h != nullptr && score_out != nullptr && label_out != nullptr, "rgqa_score: null argument");
+  RGQA_CHECK(B > 0, "rgqa_score: empty batch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int A = h->cfg.num_answers, H = h->cfg.hidden;
+  RGQA_CHECK(A > 0, "rgqa_score: handle has no answer classes");
+  if (mode == RGQA_SCORE_MAHA) {
+    RGQA_CHECK(h->has_maha, "rgqa_score: Mahalanobis statistics were not set (rgqa_set_maha)");
+    RGQA_CHECK(pooled != nullptr, "rgqa_score: MAHA needs the pooled feature");
+    if (h->mahabuf.ensure((static_cast<size_t>(B) * (H + A + 1) + 16) * 4)) return 1;
+    return maha_core(st, pooled, h->maha_mu, h->maha_P, h->maha_m, B, A, H, static_cast<float*>(h->mahabuf.p), score_out,
+                     label_out, maha_full_out);
+  }
+  RGQA_CHECK(logits != nullptr, "rgqa_score: this scorer needs logits");
+  return score_logits(st, mode, logits, A, B, A, score_out, label_out);
+}
+
+// ---- per-kernel entry points ----
+int rgqa_gemm_bf16(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                   const void* resid, int64_t ldr, void* out, int64_t ldo, int out_dtype, int M, int N, int K,
+                   int epilogue) {
+  return gemm_bf16(static_cast<cudaStream_t>(stream), A, lda, W, ldw, bias, resid, ldr, out, ldo,
+                   out_dtype == RGQA_DT_F32 ? 1 : 0, M, N, K, epilogue);
+}
+int rgqa_gemm_f32(void* stream, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                  const float* resid, int64_t ldr, float* out, int64_t ldo, int M, int N, int K, int epilogue) {
+  return gemm_f32(static_cast<cudaStream_t>(stream), A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, epilogue);
+}
+int rgqa_attention(void* stream, int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                   int64_t ldv, const int32_t* key_mask, void* out, int64_t ldo, int B, int Lq, int Lk, int heads) {
+  return attention(static_cast<cudaStream_t>(stream), dtype, q, ldq, k, ldk, v, ldv, key_mask, out, ldo, B, Lq, Lk, heads);
+}
+int rgqa_embed_ln(void* stream, int out_dtype, const int32_t* ids, const int32_t* seg, const float* word,
+                  const float* pos, const float* type, const float* gamma, const float* beta, void* out, int B,
+                  int L, int H, int vocab, int max_pos, int n_types, float eps) {
+  return embed_ln(static_cast<cudaStream_t>(stream), out_dtype, ids, seg, word, pos, type, gamma, beta, out, B, L, H,
+                  vocab, max_pos, n_types, eps);
+}
+int rgqa_layernorm(void* stream, int out_dtype, const float* x, int64_t ldx, const float* gamma, const float* beta,
+                   void* y, int M, int H, float eps) {
+  return layernorm(static_cast<cudaStream_t>(stream), out_dtype, x, ldx, gamma, beta, y, M, H, eps);
+}
+int rgqa_visn_combine(void* stream, int out_dtype, const float* x_pre, const float* boxes, int box_dim,
+                      const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
+                      const float* b2, void* out, int M, int H, float eps) {
+  return visn_combine(static_cast<cudaStream_t>(stream), out_dtype, x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, out, M,
+                      H, eps);
+}
+int rgqa_cast_f32_to_bf16(void* stream, const float* in, void* out, int64_t n) {
+  return cast_f32_to_bf16(static_cast<cudaStream_t>(stream), in, out, n);
+}
+int rgqa_score_logits(void* stream, int mode, const float* logits, int64_t ld, int B, int A, float* score,
+                      int32_t* label) {
+  return score_logits(static_cast<cudaStream_t>(stream), mode, logits, ld, B, A, score, label);
+}
+int rgqa_mahalanobis(void* stream, const float* x, const float* mu, const float* P, int B, int A, int H, float* work,
+                     float* score, int32_t* label, float* full_out) {
+  // stand-alone form: m_c computed on the fly into the tail of `work`; P is used as given (assumed symmetric)
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RGQA_CHECK(x && mu && P && work && score && label, "rgqa_mahalanobis: null argument");
+  RGQA_CHECK(B > 0 && A > 0 && H > 0, "rgqa_mahalanobis: empty input");
+  // layout of work: [B*H + pad(B) + B*A] core | [A*H] T | [A] m   -> caller must size for it:
+  // B*(H+A+1)+4 + A*(H+1) floats
+  float* core = work;
+  float* T = core + static_cast<size_t>(B) * H + ((static_cast<size_t>(B) + 3) & ~static_cast<size_t>(3)) + static_cast<size_t>(B) * A;
+  float* m = T + static_cast<size_t>(A) * H;
+  if (gemm_f32(st, mu, H, P, H, nullptr, nullptr, 0, T, H, A, H, H, EPI_BIAS)) return 1;  // T = mu·Pᵀ
+  if (rowdot(st, T, mu, m, A, H)) return 1;
+  return maha_core(st, x, mu, P, m, B, A, H, core, score, label, full_out);
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,133 @@
+// rgqa_b200 — fp32 GEMM on the CUDA cores (FFMA), used by the precise path (fp32 weights and
+// activations end to end, tolerance 1e-4 on logits) and by the Mahalanobis scorer, whose quadratic
+// forms need full fp32 operands.  Same contract as gemm_bf16:
+//   out[M,N] = epilogue(A[M,K] · W[N,K]ᵀ + bias[N] (+ resid[M,N]))
+// 64x64 tile per CTA, 16-deep K slices through shared memory, 4x4 micro-tile per thread.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rgqa {
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+template <int EPI>
+__device__ __forceinline__ float act_f32(float v) {
+  if constexpr (EPI == EPI_GELU) return gelu_erf(v);
+  if constexpr (EPI == EPI_TANH) return tanhf(v);
+  return v;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256)
+gemm_f32_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ W, long long ldw,
+                const float* __restrict__ bias, const float* __restrict__ resid, long long ldr,
+                float* __restrict__ out, long long ldo, int M, int N, int K) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Ws[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * TM;
+  const int n0 = blockIdx.x * TN;
+  const int tx = tid & 15;  // 16 column groups of 4
+  const int ty = tid >> 4;  // 16 row groups of 4
+  // loader mapping: 64 rows x 16 k = 256 float4 along K
+  const int lr = tid >> 2;        // 0..63
+  const int lk = (tid & 3) * 4;   // 0,4,8,12
+  const bool k_vec = ((lda & 3) == 0) && ((ldw & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, w[4] = {0.f, 0.f, 0.f, 0.f};
+    const int ar = m0 + lr, wr = n0 + lr;
+    if (ar < M) {
+      const float* src = A + static_cast<long long>(ar) * lda + k0 + lk;
+      if (k_vec && k0 + lk + 3 < K) {
+        const float4 t = *reinterpret_cast<const float4*>(src);
+        a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (k0 + lk + i < K) a[i] = src[i];
+      }
+    }
+    if (wr < N) {
+      const float* src = W + static_cast<long long>(wr) * ldw + k0 + lk;
+      if (k_vec && k0 + lk + 3 < K) {
+        const float4 t = *reinterpret_cast<const float4*>(src);
+        w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (k0 + lk + i < K) w[i] = src[i];
+      }
+    }
+    __syncthreads();  // previous slice fully consumed
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[lk + i][lr] = a[i];
+      Ws[lk + i][lr] = w[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 wv = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+      const float ar4[4] = {av.x, av.y, av.z, av.w};
+      const float wr4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar4[i], wr4[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + ty * 4 + i;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c >= N) continue;
+      float v = acc[i][j];
+      if (bias != nullptr) v += bias[c];
+      if constexpr (EPI == EPI_RESID) v += resid[static_cast<long long>(r) * ldr + c];
+      out[static_cast<long long>(r) * ldo + c] = act_f32<EPI>(v);
+    }
+  }
+}
+
+}  // namespace
+
+int gemm_f32(cudaStream_t stream, const float* A, long long lda, const float* W, long long ldw, const float* bias,
+             const float* resid, long long ldr, float* out, long long ldo, int M, int N, int K, int epi) {
+  RGQA_CHECK(M > 0 && N > 0 && K > 0, "gemm_f32: empty problem M=%d N=%d K=%d", M, N, K);
+  RGQA_CHECK(epi != EPI_RESID || resid != nullptr, "gemm_f32: EPI_RESID needs a residual pointer");
+  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
+  switch (epi) {
+    case EPI_BIAS:
+      gemm_f32_kernel<EPI_BIAS><<<grid, 256, 0, stream>>>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K);
+      break;
+    case EPI_GELU:
+      gemm_f32_kernel<EPI_GELU><<<grid, 256, 0, stream>>>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K);
+      break;
+    case EPI_TANH:
+      gemm_f32_kernel<EPI_TANH><<<grid, 256, 0, stream>>>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K);
+      break;
+    case EPI_RESID:
+      gemm_f32_kernel<EPI_RESID><<<grid, 256, 0, stream>>>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K);
+      break;
+    default:
+      set_error("gemm_f32: unknown epilogue %d", epi);
+      return 1;
+  }
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rgqa

@@ -1,0 +1,75 @@
+// rgqa_b200 — internal launcher declarations (C++ side, below the C ABI in include/rgqa_b200.h).
+// Every launcher returns 0 on success; on failure it records a message (rgqa_last_error) and returns 1.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rgqa {
+
+enum Epilogue : int {
+  EPI_BIAS = 0,   // out = acc + bias
+  EPI_GELU = 1,   // out = gelu_erf(acc + bias)            (modeling.py:398-401 + :112-118)
+  EPI_TANH = 2,   // out = tanh(acc + bias)                (modeling.py:575-581 pooler)
+  EPI_RESID = 3,  // out = acc + bias + residual           (pre-LayerNorm sum of modeling.py:357-361 / :411-415)
+};
+
+enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+
+// ---- GEMMs -------------------------------------------------------------------------------------
+// bf16 tensor-core path: A [M,K] bf16 (row stride lda), W [N,K] bf16 (row stride ldw), bias fp32,
+// resid bf16 [M,*] (EPI_RESID), out bf16 or fp32.
+int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
+              const void* resid, long long ldr, void* out, long long ldo, int out_f32, int M, int N, int K, int epi);
+// fp32 SIMT path (precise mode): everything fp32.
+int gemm_f32(cudaStream_t stream, const float* A, long long lda, const float* W, long long ldw, const float* bias,
+             const float* resid, long long ldr, float* out, long long ldo, int M, int N, int K, int epi);
+
+// ---- attention (small sequences, Lq, Lk <= 64, 12 heads x 64) -----------------------------------
+// q/k/v point at the first row of sample 0 (head 0); rows are ldq/ldk/ldv elements apart; sample b
+// owns rows [b*Lq, (b+1)*Lq) of q/out and [b*Lk, (b+1)*Lk) of k/v.  key_mask: int32 [B, Lk] (1 = keep)
+// or nullptr; masked keys get the reference's additive -10000 (modeling.py:865), not -inf.
+int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, const void* k, long long ldk,
+              const void* v, long long ldv, const int32_t* key_mask, void* out, long long ldo, int B, int Lq,
+              int Lk, int heads);
+
+// ---- row-wise ops ------------------------------------------------------------------------------
+// LN(word[ids] + pos[0..L) + type[seg]) (modeling.py:278-292); tables and gamma/beta fp32.
+int embed_ln(cudaStream_t stream, int out_dtype, const int32_t* ids, const int32_t* seg, const float* word,
+             const float* pos, const float* type, const float* gamma, const float* beta, void* out, int B, int L,
+             int H, int vocab, int max_pos, int n_types, float eps);
+// y = LN(x) * gamma + beta; x fp32 [M,H] (row stride ldx), y fp32 or bf16 [M,H] dense.
+int layernorm(cudaStream_t stream, int out_dtype, const float* x, long long ldx, const float* gamma,
+              const float* beta, void* y, int M, int H, float eps);
+// (LN(x_pre) + LN(box·Wbᵀ + bb)) / 2 (modeling.py:507-517); x_pre = feat·Wfᵀ + bf, fp32 [M,H].
+int visn_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const float* boxes, int box_dim,
+                 const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
+                 const float* b2, void* out, int M, int H, float eps);
+// UNITER image embedding tail: LN3( LN1(x_pre) + LN2(pos7·Wpᵀ + bp) + type_emb ) (uniter/modeling.py:606-612).
+int uniter_img_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const float* pos, int pos_dim,
+                       const float* Wp, const float* bp, const float* g1, const float* b1, const float* g2,
+                       const float* b2, const float* type_row, const float* g3, const float* b3, void* out, int M,
+                       int H, float eps);
+int cast_f32_to_bf16(cudaStream_t stream, const float* in, void* out, long long n);
+int cast_bf16_to_f32(cudaStream_t stream, const void* in, float* out, long long n);
+// copy rows: dst[r, :] = src[r*src_stride_rows .. ] for r < rows (strided gather of whole rows)
+int gather_rows(cudaStream_t stream, int dtype, const void* src, long long src_ld, void* dst, long long dst_ld,
+                int rows, int H);
+
+// ---- scorers -----------------------------------------------------------------------------------
+enum ScoreMode : int {
+  SCORE_MSP = 0,          // max sigmoid prob, label = argmax sigmoid            (gqa_conf.py:326)
+  SCORE_ENERGY_TOP2 = 1,  // sum_{top-2 logits} log(1+exp(x)), label as MSP      (gqa_energy.py:204-206)
+  SCORE_ENERGY_SUM = 2,   // sum_all log(1+exp(x)), label as MSP                 (gqa_energy.py:185)
+  SCORE_LSE = 3,          // logsumexp(logits), label as MSP                     (gqa_energy.py:131)
+  SCORE_MAHA = 4,         // max_c -0.5 (x-mu_c)^T P (x-mu_c), label = argmax_c  (gqa_maha.py:228-236,270)
+};
+int score_logits(cudaStream_t stream, int mode, const float* logits, long long ld, int B, int A, float* score,
+                 int32_t* label);
+// Mahalanobis finish: S[b,c] = -0.5 * (q[b] - 2 G[b,c] + m[c]); row max / argmax.
+int maha_finish(cudaStream_t stream, const float* q, const float* G, long long ldg, const float* m, int B, int A,
+                float* score, int32_t* label, float* full /* optional [B,A] */);
+// q[b] = sum_j t[b,j] * x[b,j]
+int rowdot(cudaStream_t stream, const float* a, const float* b, float* out, int M, int H);
+
+}  // namespace rgqa

@@ -1,0 +1,345 @@
+// rgqa_b200 — row-wise HBM-bound kernels: embedding gather + LayerNorm, LayerNorm, the visual
+// feature/box combine, dtype casts.  One warp owns one row; a row of H = 128*NV floats sits in
+// registers as NV float4 per lane (fully coalesced 512 B per warp per load), statistics are
+// two-pass fp32 (mean, then variance of the centred values) with warp-shuffle reductions.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rgqa {
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+
+template <int NV>
+__device__ __forceinline__ void row_stats(const float4 (&x)[NV], int H, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+  mean = warp_sum(s) / static_cast<float>(H);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = warp_sum(q) / static_cast<float>(H);
+  rstd = 1.0f / sqrtf(var + eps);
+}
+
+template <int NV>
+__device__ __forceinline__ void normalize(float4 (&x)[NV], float mean, float rstd, const float* gamma,
+                                          const float* beta, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+    x[i].x = (x[i].x - mean) * rstd * g.x + b.x;
+    x[i].y = (x[i].y - mean) * rstd * g.y + b.y;
+    x[i].z = (x[i].z - mean) * rstd * g.z + b.z;
+    x[i].w = (x[i].w - mean) * rstd * g.w + b.w;
+  }
+}
+
+template <int NV, typename OutT>
+__device__ __forceinline__ void store_row(const float4 (&x)[NV], OutT* out_row, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
+    if constexpr (sizeof(OutT) == 4) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_row) + c) = x[i];
+    } else {
+      uint2 u;
+      u.x = pack_bf16x2(x[i].x, x[i].y);
+      u.y = pack_bf16x2(x[i].z, x[i].w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out_row) + c) = u;
+    }
+  }
+}
+
+// ---- embeddings + LayerNorm (src/lxrt/modeling.py:278-292) --------------------------------------
+template <int NV, typename OutT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ seg, const float* __restrict__ word,
+                const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ gamma,
+                const float* __restrict__ beta, OutT* __restrict__ out, int rows, int L, int H, float eps, int vocab,
+                int n_types) {
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  // ids are validated by the host shim; the clamp only keeps a corrupt id from faulting the GPU
+  const int id = min(max(ids[row], 0), vocab - 1);
+  const int sg = seg != nullptr ? min(max(seg[row], 0), n_types - 1) : 0;
+  const int ps = row % L;
+  const float* w = word + static_cast<long long>(id) * H;
+  const float* p = pos + static_cast<long long>(ps) * H;
+  const float* t = type + static_cast<long long>(sg) * H;
+  float4 x[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + c));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(t + c));
+    // reference order: (words + position) + token_type  (modeling.py:289)
+    x[i] = make_float4((a.x + b.x) + d.x, (a.y + b.y) + d.y, (a.z + b.z) + d.z, (a.w + b.w) + d.w);
+  }
+  float mean, rstd;
+  row_stats<NV>(x, H, eps, mean, rstd);
+  normalize<NV>(x, mean, rstd, gamma, beta, lane);
+  store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane);
+}
+
+// ---- plain LayerNorm over fp32 rows ------------------------------------------------------------
+template <int NV, typename OutT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+layernorm_kernel(const float* __restrict__ xin, long long ldx, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, OutT* __restrict__ out, int rows, int H, float eps) {
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = xin + static_cast<long long>(row) * ldx;
+  float4 x[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) x[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+  float mean, rstd;
+  row_stats<NV>(x, H, eps, mean, rstd);
+  normalize<NV>(x, mean, rstd, gamma, beta, lane);
+  store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane);
+}
+
+// ---- small-K projection of a per-row vector (boxes, K = 4 or 7) ---------------------------------
+template <int NV>
+__device__ __forceinline__ void small_proj(float4 (&y)[NV], const float* __restrict__ vec, int K,
+                                           const float* __restrict__ W, const float* __restrict__ bias, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // torch addmm order: bias + sum_k x[k] * W[c,k]; K is tiny so the order is fixed here too
+      float a = 0.f;
+      for (int k = 0; k < K; ++k) a = fmaf(vec[k], __ldg(W + static_cast<long long>(c + j) * K + k), a);
+      o[j] = a + __ldg(bias + c + j);
+    }
+    y[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---- VisualFeatEncoder tail (src/lxrt/modeling.py:507-517) --------------------------------------
+template <int NV, typename OutT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+visn_combine_kernel(const float* __restrict__ x_pre, const float* __restrict__ boxes, int box_dim,
+                    const float* __restrict__ Wb, const float* __restrict__ bb, const float* __restrict__ g1,
+                    const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
+                    OutT* __restrict__ out, int rows, int H, float eps) {
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float4 x[NV], y[NV];
+  const float* xr = x_pre + static_cast<long long>(row) * H;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) x[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+  float bx[8];
+  for (int k = 0; k < box_dim; ++k) bx[k] = boxes[static_cast<long long>(row) * box_dim + k];
+  small_proj<NV>(y, bx, box_dim, Wb, bb, lane);
+  float mean, rstd;
+  row_stats<NV>(x, H, eps, mean, rstd);
+  normalize<NV>(x, mean, rstd, g1, b1, lane);
+  row_stats<NV>(y, H, eps, mean, rstd);
+  normalize<NV>(y, mean, rstd, g2, b2, lane);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    x[i] = make_float4((x[i].x + y[i].x) / 2.f, (x[i].y + y[i].y) / 2.f, (x[i].z + y[i].z) / 2.f,
+                       (x[i].w + y[i].w) / 2.f);
+  store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane);
+}
+
+// ---- UniterImageEmbeddings tail (src/uniter/modeling.py:606-612) --------------------------------
+template <int NV, typename OutT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+uniter_img_kernel(const float* __restrict__ x_pre, const float* __restrict__ posf, int pos_dim,
+                  const float* __restrict__ Wp, const float* __restrict__ bp, const float* __restrict__ g1,
+                  const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
+                  const float* __restrict__ type_row, const float* __restrict__ g3, const float* __restrict__ b3,
+                  OutT* __restrict__ out, int rows, int H, float eps) {
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float4 x[NV], y[NV];
+  const float* xr = x_pre + static_cast<long long>(row) * H;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) x[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+  float pv[8];
+  for (int k = 0; k < pos_dim; ++k) pv[k] = posf[static_cast<long long>(row) * pos_dim + k];
+  small_proj<NV>(y, pv, pos_dim, Wp, bp, lane);
+  float mean, rstd;
+  row_stats<NV>(x, H, eps, mean, rstd);
+  normalize<NV>(x, mean, rstd, g1, b1, lane);
+  row_stats<NV>(y, H, eps, mean, rstd);
+  normalize<NV>(y, mean, rstd, g2, b2, lane);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(type_row + i * 128 + lane * 4));
+    // reference order: (transformed_im + transformed_pos) + type_embeddings  (uniter/modeling.py:610)
+    x[i] = make_float4((x[i].x + y[i].x) + t.x, (x[i].y + y[i].y) + t.y, (x[i].z + y[i].z) + t.z,
+                       (x[i].w + y[i].w) + t.w);
+  }
+  row_stats<NV>(x, H, eps, mean, rstd);
+  normalize<NV>(x, mean, rstd, g3, b3, lane);
+  store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane);
+}
+
+// ---- casts -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in,
+                                                            __nv_bfloat16* __restrict__ out, long long n8) {
+  // 8 elements per thread per step: 2 x 16 B loads, 1 x 16 B store; grid-stride
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(in) + 2 * i);
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+    uint4 u;
+    u.x = pack_bf16x2(a.x, a.y);
+    u.y = pack_bf16x2(a.z, a.w);
+    u.z = pack_bf16x2(b.x, b.y);
+    u.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(out)[i] = u;
+  }
+}
+__global__ void cast_f32_bf16_tail(const float* in, __nv_bfloat16* out, long long start, long long n) {
+  const long long i = start + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ src, long long src_ld, T* __restrict__ dst,
+                                   long long dst_ld, int rows, int H) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < static_cast<long long>(rows) * H) {
+    const int r = static_cast<int>(i / H), c = static_cast<int>(i % H);
+    dst[r * dst_ld + c] = src[r * src_ld + c];
+  }
+}
+
+inline int row_grid(int rows) { return (rows + kWarpsPerBlock - 1) / kWarpsPerBlock; }
+
+}  // namespace
+
+#define RGQA_DISPATCH_ROW(KERNEL, OUT_T, ...)                                                              \
+  do {                                                                                                     \
+    const int nv = H / 128;                                                                                \
+    if (H % 128 == 0 && nv == 6)                                                                           \
+      KERNEL<6, OUT_T><<<row_grid(M), kWarpsPerBlock * 32, 0, stream>>>(__VA_ARGS__);                      \
+    else if (H % 128 == 0 && nv == 12)                                                                     \
+      KERNEL<12, OUT_T><<<row_grid(M), kWarpsPerBlock * 32, 0, stream>>>(__VA_ARGS__);                     \
+    else {                                                                                                 \
+      set_error("row kernel: unsupported hidden size %d (need 768 or 1536)", H);                           \
+      return 1;                                                                                            \
+    }                                                                                                      \
+  } while (0)
+
+int embed_ln(cudaStream_t stream, int out_dtype, const int32_t* ids, const int32_t* seg, const float* word,
+             const float* pos, const float* type, const float* gamma, const float* beta, void* out, int B, int L,
+             int H, int vocab, int max_pos, int n_types, float eps) {
+  RGQA_CHECK(B > 0 && L > 0 && L <= max_pos, "embed_ln: bad B=%d L=%d (max_pos=%d)", B, L, max_pos);
+  const int M = B * L;
+  if (out_dtype == DT_BF16) {
+    RGQA_DISPATCH_ROW(embed_ln_kernel, __nv_bfloat16, ids, seg, word, pos, type, gamma, beta, static_cast<__nv_bfloat16*>(out), M, L, H, eps, vocab, n_types);
+  } else {
+    RGQA_DISPATCH_ROW(embed_ln_kernel, float, ids, seg, word, pos, type, gamma, beta, static_cast<float*>(out), M, L, H, eps, vocab, n_types);
+  }
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int layernorm(cudaStream_t stream, int out_dtype, const float* x, long long ldx, const float* gamma,
+              const float* beta, void* y, int M, int H, float eps) {
+  RGQA_CHECK(M > 0, "layernorm: empty input");
+  RGQA_CHECK(ldx % 4 == 0, "layernorm: row stride must be a multiple of 4 floats");
+  if (out_dtype == DT_BF16) {
+    RGQA_DISPATCH_ROW(layernorm_kernel, __nv_bfloat16, x, ldx, gamma, beta, static_cast<__nv_bfloat16*>(y), M, H, eps);
+  } else {
+    RGQA_DISPATCH_ROW(layernorm_kernel, float, x, ldx, gamma, beta, static_cast<float*>(y), M, H, eps);
+  }
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int visn_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const float* boxes, int box_dim,
+                 const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
+                 const float* b2, void* out, int M, int H, float eps) {
+  RGQA_CHECK(M > 0 && box_dim >= 1 && box_dim <= 8, "visn_combine: bad M=%d box_dim=%d", M, box_dim);
+  if (out_dtype == DT_BF16) {
+    RGQA_DISPATCH_ROW(visn_combine_kernel, __nv_bfloat16, x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<__nv_bfloat16*>(out), M, H, eps);
+  } else {
+    RGQA_DISPATCH_ROW(visn_combine_kernel, float, x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<float*>(out), M, H, eps);
+  }
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int uniter_img_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const float* pos, int pos_dim,
+                       const float* Wp, const float* bp, const float* g1, const float* b1, const float* g2,
+                       const float* b2, const float* type_row, const float* g3, const float* b3, void* out, int M,
+                       int H, float eps) {
+  RGQA_CHECK(M > 0 && pos_dim >= 1 && pos_dim <= 8, "uniter_img_combine: bad M=%d pos_dim=%d", M, pos_dim);
+  if (out_dtype == DT_BF16) {
+    RGQA_DISPATCH_ROW(uniter_img_kernel, __nv_bfloat16, x_pre, pos, pos_dim, Wp, bp, g1, b1, g2, b2, type_row, g3, b3, static_cast<__nv_bfloat16*>(out), M, H, eps);
+  } else {
+    RGQA_DISPATCH_ROW(uniter_img_kernel, float, x_pre, pos, pos_dim, Wp, bp, g1, b1, g2, b2, type_row, g3, b3, static_cast<float*>(out), M, H, eps);
+  }
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int cast_f32_to_bf16(cudaStream_t stream, const float* in, void* out, long long n) {
+  if (n <= 0) return 0;
+  const bool aligned = (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  const long long n8 = aligned ? n / 8 : 0;
+  if (n8 > 0) {
+    long long blocks = (n8 + 255) / 256;
+    const long long cap = 148LL * 16;  // a few resident waves; grid-stride covers the rest
+    if (blocks > cap) blocks = cap;
+    cast_f32_bf16_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), n8);
+  }
+  const long long start = n8 * 8;
+  if (start < n) {
+    const long long rem = n - start;
+    cast_f32_bf16_tail<<<static_cast<int>((rem + 255) / 256), 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out),
+                                                                              start, n);
+  }
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int cast_bf16_to_f32(cudaStream_t stream, const void* in, float* out, long long n) {
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  cast_bf16_f32_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), out, n);
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gather_rows(cudaStream_t stream, int dtype, const void* src, long long src_ld, void* dst, long long dst_ld,
+                int rows, int H) {
+  if (rows <= 0) return 0;
+  const long long n = static_cast<long long>(rows) * H;
+  const int blocks = static_cast<int>((n + 255) / 256);
+  if (dtype == DT_F32)
+    gather_rows_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(src), src_ld,
+                                                         static_cast<float*>(dst), dst_ld, rows, H);
+  else
+    gather_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), src_ld,
+                                                                 static_cast<__nv_bfloat16*>(dst), dst_ld, rows, H);
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rgqa

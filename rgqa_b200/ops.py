@@ -1,0 +1,164 @@
+"""Tensor-level wrappers over the per-kernel C-ABI entry points.
+
+Each function borrows the data pointers of CUDA ``torch.Tensor`` arguments, enqueues ONE hand-written
+kernel on the current CUDA stream and returns a fresh output tensor.  They mirror single modules of
+the reference (file:line in each docstring) so that unit tests read like ``module(x)`` comparisons.
+PyTorch is only the allocator / stream provider here.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("rgqa_b200.ops: CUDA tensors required (there is no CPU path)")
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return L.DT_F32
+    if t.dtype == torch.bfloat16:
+        return L.DT_BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def linear_bf16(x, weight, bias=None, epilogue=L.EPI_BIAS, residual=None, out_dtype=torch.bfloat16):
+    """``epilogue(x @ weight.T + bias [+ residual])`` on the tcgen05 tensor cores.
+
+    x: [M, K] bf16 (row stride may exceed K), weight: [N, K] bf16 (nn.Linear layout), bias: [N] f32.
+    Reference: every ``nn.Linear`` of src/lxrt/modeling.py (e.g. :321-323, :358, :399, :412, :578).
+    """
+    _need_cuda(x, weight, bias, residual)
+    assert x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 2 and weight.dim() == 2
+    assert x.stride(1) == 1 and weight.stride(1) == 1
+    M, K = x.shape
+    N = weight.shape[0]
+    assert weight.shape[1] == K
+    out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    ldr = 0
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.stride(1) == 1
+        ldr = residual.stride(0)
+    lib = L.load()
+    L.check(lib.rgqa_gemm_bf16(L.current_stream_ptr(), L.ptr(x), x.stride(0), L.ptr(weight), weight.stride(0),
+                               L.ptr(bias), L.ptr(residual), ldr, L.ptr(out), out.stride(0), _dt(out), M, N, K,
+                               epilogue), "rgqa_gemm_bf16")
+    return out
+
+
+def linear_f32(x, weight, bias=None, epilogue=L.EPI_BIAS, residual=None):
+    """fp32 CUDA-core GEMM with the same contract as :func:`linear_bf16` (precise path)."""
+    _need_cuda(x, weight, bias, residual)
+    assert x.dtype == torch.float32 and weight.dtype == torch.float32
+    assert x.stride(1) == 1 and weight.stride(1) == 1
+    M, K = x.shape
+    N = weight.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    ldr = residual.stride(0) if residual is not None else 0
+    lib = L.load()
+    L.check(lib.rgqa_gemm_f32(L.current_stream_ptr(), L.ptr(x), x.stride(0), L.ptr(weight), weight.stride(0),
+                              L.ptr(bias), L.ptr(residual), ldr, L.ptr(out), out.stride(0), M, N, K, epilogue),
+            "rgqa_gemm_f32")
+    return out
+
+
+def attention(qkv_q, qkv_kv, B, Lq, Lk, key_mask=None, heads=12):
+    """Multi-head attention reading Q from ``qkv_q`` [B*Lq, 3H] and K, V from ``qkv_kv`` [B*Lk, 3H]
+    (fused Q|K|V projections, H = heads*64).  key_mask: int32 [B, Lk] (1 = keep) or None.
+    Reference: BertAttention.forward, src/lxrt/modeling.py:320-347."""
+    _need_cuda(qkv_q, qkv_kv, key_mask)
+    H = heads * 64
+    assert qkv_q.shape == (B * Lq, 3 * H) and qkv_kv.shape == (B * Lk, 3 * H)
+    assert qkv_q.dtype == qkv_kv.dtype and qkv_q.is_contiguous() and qkv_kv.is_contiguous()
+    out = torch.empty((B * Lq, H), dtype=qkv_q.dtype, device=qkv_q.device)
+    es = qkv_q.element_size()
+    if key_mask is not None:
+        assert key_mask.dtype == torch.int32 and key_mask.shape == (B, Lk) and key_mask.is_contiguous()
+    lib = L.load()
+    L.check(lib.rgqa_attention(L.current_stream_ptr(), _dt(qkv_q), L.ptr(qkv_q), 3 * H,
+                               qkv_kv.data_ptr() + H * es, 3 * H, qkv_kv.data_ptr() + 2 * H * es, 3 * H,
+                               L.ptr(key_mask), L.ptr(out), H, B, Lq, Lk, heads), "rgqa_attention")
+    return out
+
+
+def embed_ln(ids, seg, word, pos, type_, gamma, beta, eps=1e-12, out_dtype=torch.float32):
+    """BertEmbeddings.forward (src/lxrt/modeling.py:278-292): ids/seg int32 [B, L] -> [B*L, H]."""
+    _need_cuda(ids, seg, word, pos, type_, gamma, beta)
+    assert ids.dtype == torch.int32 and ids.is_contiguous()
+    B, Lq = ids.shape
+    H = word.shape[1]
+    out = torch.empty((B * Lq, H), dtype=out_dtype, device=ids.device)
+    lib = L.load()
+    L.check(lib.rgqa_embed_ln(L.current_stream_ptr(), _dt(out), L.ptr(ids), L.ptr(seg), L.ptr(word), L.ptr(pos),
+                              L.ptr(type_), L.ptr(gamma), L.ptr(beta), L.ptr(out), B, Lq, H, word.shape[0],
+                              pos.shape[0], type_.shape[0], eps), "rgqa_embed_ln")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-12, out_dtype=torch.float32):
+    """torch.nn.LayerNorm over the last dim of fp32 [M, H] (H in {768, 1536})."""
+    _need_cuda(x, gamma, beta)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    M, H = x.shape
+    out = torch.empty((M, H), dtype=out_dtype, device=x.device)
+    lib = L.load()
+    L.check(lib.rgqa_layernorm(L.current_stream_ptr(), _dt(out), L.ptr(x), x.stride(0), L.ptr(gamma), L.ptr(beta),
+                               L.ptr(out), M, H, eps), "rgqa_layernorm")
+    return out
+
+
+def visn_combine(x_pre, boxes, box_w, box_b, g1, b1, g2, b2, eps=1e-12, out_dtype=torch.float32):
+    """Tail of VisualFeatEncoder.forward (src/lxrt/modeling.py:507-517): (LN(x_pre) + LN(box_fc(boxes))) / 2."""
+    _need_cuda(x_pre, boxes, box_w, box_b, g1, b1, g2, b2)
+    M, H = x_pre.shape
+    boxes = boxes.reshape(M, -1).contiguous()
+    out = torch.empty((M, H), dtype=out_dtype, device=x_pre.device)
+    lib = L.load()
+    L.check(lib.rgqa_visn_combine(L.current_stream_ptr(), _dt(out), L.ptr(x_pre), L.ptr(boxes), boxes.shape[1],
+                                  L.ptr(box_w), L.ptr(box_b), L.ptr(g1), L.ptr(b1), L.ptr(g2), L.ptr(b2), L.ptr(out),
+                                  M, H, eps), "rgqa_visn_combine")
+    return out
+
+
+def cast_bf16(x):
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lib = L.load()
+    L.check(lib.rgqa_cast_f32_to_bf16(L.current_stream_ptr(), L.ptr(x), L.ptr(out), x.numel()), "rgqa_cast_f32_to_bf16")
+    return out
+
+
+def score_logits(logits, mode="msp"):
+    """(score f32 [B], label int32 [B]) for the logit scorers (gqa_conf.py:326, gqa_energy.py:131,185,204-206)."""
+    _need_cuda(logits)
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    B, A = logits.shape
+    score = torch.empty(B, dtype=torch.float32, device=logits.device)
+    label = torch.empty(B, dtype=torch.int32, device=logits.device)
+    lib = L.load()
+    L.check(lib.rgqa_score_logits(L.current_stream_ptr(), L.SCORE_MODES[mode], L.ptr(logits), logits.stride(0), B, A,
+                                  L.ptr(score), L.ptr(label)), "rgqa_score_logits")
+    return score, label
+
+
+def mahalanobis(x, mu, precision, return_full=False):
+    """score,label = max_c -0.5 (x-mu_c)^T P (x-mu_c) (src/tasks/gqa_maha.py:228-236,270), GEMM form."""
+    _need_cuda(x, mu, precision)
+    B, H = x.shape
+    A = mu.shape[0]
+    x, mu, precision = x.contiguous(), mu.contiguous(), precision.contiguous()
+    work = torch.empty(B * (H + A + 1) + 4 + A * (H + 1), dtype=torch.float32, device=x.device)
+    score = torch.empty(B, dtype=torch.float32, device=x.device)
+    label = torch.empty(B, dtype=torch.int32, device=x.device)
+    full = torch.empty((B, A), dtype=torch.float32, device=x.device) if return_full else None
+    lib = L.load()
+    L.check(lib.rgqa_mahalanobis(L.current_stream_ptr(), L.ptr(x), L.ptr(mu), L.ptr(precision), B, A, H, L.ptr(work),
+                                 L.ptr(score), L.ptr(label), L.ptr(full)), "rgqa_mahalanobis")
+    return (score, label, full) if return_full else (score, label)
