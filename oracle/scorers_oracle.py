@@ -1,0 +1,87 @@
+"""ORACLE — test infrastructure, not product code.
+
+CPU restatement of the reference's rejection scorers.  The task drivers that hold these lines cannot
+be imported (``src/tasks/gqa_conf.py:27`` pulls in ``vilt`` -> ``timm``, absent), so each scorer is
+restated from the cited lines, literally (including the 1842-iteration Mahalanobis loop).
+
+Pinning: MSP / energy are one-line torch expressions copied in meaning from the cited lines;
+``sample_estimator`` is checked in ``tests/test_oracle_cpu.py`` against scikit-learn's
+``EmpiricalCovariance`` (the third-party routine the reference calls, pinned 1.1.1 in
+environment.yml:111, 1.9.0 here).  The reference ships no test or golden vector for these lines:
+**parity unpinned** beyond that.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def msp(logit):
+    """src/tasks/gqa_conf.py:326 — max SIGMOID probability (BCE-trained head), label = its argmax."""
+    score, label = torch.sigmoid(logit).max(1)
+    return score, label
+
+
+def energy_top2(logit):
+    """src/tasks/gqa_energy.py:204-206."""
+    _, label = torch.sigmoid(logit).max(1)
+    logit_k = logit.topk(k=2).values
+    score = torch.log(1 + torch.exp(logit_k)).sum(1)
+    return score, label
+
+
+def energy_sum(logit):
+    """src/tasks/gqa_energy.py:185 (``predict``): all-class JointEnergy."""
+    _, label = torch.sigmoid(logit).max(1)
+    return torch.log(1 + torch.exp(logit)).sum(1), label
+
+
+def lse(logit):
+    """src/tasks/gqa_energy.py:131 (the --mceLoss energy)."""
+    _, label = torch.sigmoid(logit).max(1)
+    return torch.logsumexp(logit, dim=1), label
+
+
+def mahalanobis(x, sample_mean, precision):
+    """src/tasks/gqa_maha.py:228-236 (per-class loop) and :270 (max over classes), noise = 0 form.
+
+    Returns (score [B], label [B], gaussian_score [B, num_classes])."""
+    gaussian_score = 0
+    for i in range(sample_mean.shape[0]):
+        zero_f = x - sample_mean[i]
+        term_gau = -0.5 * torch.mm(torch.mm(zero_f, precision), zero_f.t()).diag()
+        if i == 0:
+            gaussian_score = term_gau.view(-1, 1)
+        else:
+            gaussian_score = torch.cat((gaussian_score, term_gau.view(-1, 1)), 1)
+    score, label = torch.max(gaussian_score, dim=1)
+    return score, label, gaussian_score
+
+
+def sample_estimator(features, targets):
+    """src/tasks/gqa_maha.py:150-183: class means over every class a sample is labelled with
+    (multi-label), then precision of the pooled, class-centred features.
+
+    features [N, D] f32, targets [N, C] (non-zero = member).  Returns (mean [C, D] f32, precision [D, D] f64),
+    the precision being numpy's restatement of sklearn EmpiricalCovariance(assume_centered=False).fit(X).precision_
+    (= pinvh of the biased covariance of X after removing X's own column means)."""
+    N, C = targets.shape
+    lists = [[] for _ in range(C)]
+    for i in range(N):
+        for j in range(C):
+            if targets[i][j] == 0:
+                continue
+            lists[j].append(features[i].view(1, -1))
+    mean = torch.zeros((C, features.shape[1]))
+    X = []
+    for j in range(C):
+        if lists[j]:
+            fj = torch.cat(lists[j], 0)
+            mean[j] = torch.mean(fj, 0)
+            X.append(fj - mean[j])
+    X = torch.cat(X, 0).numpy().astype(np.float64)
+    Xc = X - X.mean(axis=0)
+    cov = Xc.T @ Xc / X.shape[0]
+    import scipy.linalg
+    precision = scipy.linalg.pinvh(cov)
+    return mean, precision
