@@ -9,6 +9,8 @@
 //   qkv        [Mt, 2304]  fused Q|K|V projection, read in place (strided) by the attention kernel
 //   ctx        [Mt, 768]   attention output
 //   inter      [Mt, 3072]  FFN intermediate (after erf-GELU)
+//   resA/resB  [Mt, 768]   fp32 residual stream (PREC_BF16 only): every LayerNorm writes its row twice,
+//                          bf16 into hidX (next GEMM operand) and fp32 here (next residual add)
 //   pre        [Mt, 768]   fp32 pre-LayerNorm sums (GEMM + bias + residual)
 //   featb      [Mv, 2048]  bf16 copy of the RoI features when the caller hands fp32 ones
 // Weights: nn.Linear weights stay [out, in] row-major (= N x K, K contiguous: the K-major B operand
@@ -119,7 +121,7 @@ struct rgqa_handle {
   bool has_maha = false;
 
   // workspace
-  DevBuf hidA, hidB, qkv, ctx, inter, pre, featb, headbuf, mahabuf;
+  DevBuf hidA, hidB, resA, resB, qkv, ctx, inter, pre, featb, headbuf, mahabuf;
 };
 
 namespace {
@@ -326,15 +328,31 @@ inline char* rows_at(void* base, long long row, long long ld, size_t esz) {
   return static_cast<char*>(base) + static_cast<size_t>(row) * ld * esz;
 }
 
+// One hidden-state buffer: `act` is the GEMM A operand in the path's activation type; `res` is the fp32
+// residual stream.  In PREC_FP32 both are the same fp32 buffer; in PREC_BF16 every LayerNorm writes the
+// row twice (bf16 operand + fp32 residual) so the residual path never sees a bf16 rounding.
+struct Hid {
+  void* act;
+  float* res;
+};
+inline const float* resid_rows(const rgqa_handle* h, const Hid& x, long long r0) {
+  return reinterpret_cast<const float*>(rows_at(x.res, r0, h->cfg.hidden, 4));
+}
+inline float* res_copy_rows(const rgqa_handle* h, const Hid& x, long long r0) {
+  // extra fp32 copy target for row kernels; none needed when act already IS the fp32 stream
+  if (static_cast<void*>(x.res) == x.act) return nullptr;
+  return reinterpret_cast<float*>(rows_at(x.res, r0, h->cfg.hidden, 4));
+}
+
 // self-attention block + output projection + LN on rows [r0, r0 + B*S) : in -> out
-int att_block(rgqa_handle* h, cudaStream_t st, const AttW& w, void* in, void* out, long long r0, int B, int S,
+int att_block(rgqa_handle* h, cudaStream_t st, const AttW& w, const Hid& in, const Hid& out, long long r0, int B, int S,
               const int32_t* key_mask) {
   const int H = h->cfg.hidden;
   const size_t es = act_size(h);
   const int dt = act_dtype(h);
   const int M = B * S;
   const int of32 = dt == DT_F32;
-  char* x = rows_at(in, r0, H, es);
+  char* x = rows_at(in.act, r0, H, es);
   char* qkv = rows_at(h->qkv.p, r0, 3 * H, es);
   char* ctx = rows_at(h->ctx.p, r0, H, es);
   float* pre = reinterpret_cast<float*>(rows_at(h->pre.p, r0, H, 4));
@@ -342,22 +360,24 @@ int att_block(rgqa_handle* h, cudaStream_t st, const AttW& w, void* in, void* ou
   if (attention(st, dt, qkv, 3 * H, qkv + static_cast<size_t>(H) * es, 3 * H, qkv + static_cast<size_t>(2 * H) * es,
                 3 * H, key_mask, ctx, H, B, S, S, h->cfg.heads))
     return 1;
-  if (gemm(h, st, ctx, H, w.out, x, H, pre, H, 1, M, EPI_RESID)) return 1;
-  return layernorm(st, dt, pre, H, w.ln.g, w.ln.b, rows_at(out, r0, H, es), M, H, h->cfg.ln_eps);
+  if (gemm(h, st, ctx, H, w.out, resid_rows(h, in, r0), H, pre, H, 1, M, EPI_RESID)) return 1;
+  return layernorm(st, dt, pre, H, w.ln.g, w.ln.b, rows_at(out.act, r0, H, es), res_copy_rows(h, out, r0), M, H,
+                   h->cfg.ln_eps);
 }
 
 // FFN block on rows [r0, r0 + M): in -> out
-int ffn_block(rgqa_handle* h, cudaStream_t st, const FfnW& w, void* in, void* out, long long r0, int M) {
+int ffn_block(rgqa_handle* h, cudaStream_t st, const FfnW& w, const Hid& in, const Hid& out, long long r0, int M) {
   const int H = h->cfg.hidden, I = h->cfg.intermediate;
   const size_t es = act_size(h);
   const int dt = act_dtype(h);
   const int of32 = dt == DT_F32;
-  char* x = rows_at(in, r0, H, es);
+  char* x = rows_at(in.act, r0, H, es);
   char* inter = rows_at(h->inter.p, r0, I, es);
   float* pre = reinterpret_cast<float*>(rows_at(h->pre.p, r0, H, 4));
   if (gemm(h, st, x, H, w.inter, nullptr, 0, inter, I, of32, M, EPI_GELU)) return 1;
-  if (gemm(h, st, inter, I, w.out, x, H, pre, H, 1, M, EPI_RESID)) return 1;
-  return layernorm(st, dt, pre, H, w.ln.g, w.ln.b, rows_at(out, r0, H, es), M, H, h->cfg.ln_eps);
+  if (gemm(h, st, inter, I, w.out, resid_rows(h, in, r0), H, pre, H, 1, M, EPI_RESID)) return 1;
+  return layernorm(st, dt, pre, H, w.ln.g, w.ln.b, rows_at(out.act, r0, H, es), res_copy_rows(h, out, r0), M, H,
+                   h->cfg.ln_eps);
 }
 
 int ensure_workspace(rgqa_handle* h, long long Mt, long long Mv, int B) {
@@ -366,6 +386,7 @@ int ensure_workspace(rgqa_handle* h, long long Mt, long long Mv, int B) {
   if (h->hidA.ensure(Mt * H * es) || h->hidB.ensure(Mt * H * es) || h->qkv.ensure(Mt * 3 * H * es) ||
       h->ctx.ensure(Mt * H * es) || h->inter.ensure(Mt * I * es) || h->pre.ensure(Mt * H * 4))
     return 1;
+  if (h->cfg.precision == RGQA_PREC_BF16 && (h->resA.ensure(Mt * H * 4) || h->resB.ensure(Mt * H * 4))) return 1;
   if (h->cfg.precision == RGQA_PREC_BF16 && h->featb.ensure(Mv * h->cfg.visual_feat_dim * 2)) return 1;
   // head scratch: pooled f32 [B,H] | pooled act [B,H] | h1 f32 [B,2H] | h1n act [B,2H] | logits f32 [B,A]
   const size_t head = static_cast<size_t>(B) * (H * 4 + H * es + 2 * H * 4 + 2 * H * es + (h->cfg.num_answers + 8) * 4);
@@ -396,7 +417,7 @@ int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, f
     a0 = pooled_act;
   }
   if (gemm(h, st, a0, H, h->fc0, nullptr, 0, h1, 2 * H, 1, B, EPI_GELU)) return 1;
-  if (layernorm(st, dt, h1, 2 * H, h->fc_ln.g, h->fc_ln.b, h1n, B, 2 * H, h->cfg.ln_eps)) return 1;
+  if (layernorm(st, dt, h1, 2 * H, h->fc_ln.g, h->fc_ln.b, h1n, nullptr, B, 2 * H, h->cfg.ln_eps)) return 1;
   (void)of32;
   (void)logits_ws;
   return gemm(h, st, h1n, 2 * H, h->fc3, nullptr, 0, logits_out, A, 1, B, EPI_BIAS);
@@ -442,6 +463,8 @@ void rgqa_destroy(rgqa_handle* h) {
   for (void* p : h->owned) cudaFree(p);
   h->hidA.release();
   h->hidB.release();
+  h->resA.release();
+  h->resB.release();
   h->qkv.release();
   h->ctx.release();
   h->inter.release();
@@ -585,11 +608,12 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
   if (ensure_workspace(h, Mt, Mv, B)) return 1;
   const size_t es = act_size(h);
   const int dt = act_dtype(h);
-  void* cur = h->hidA.p;
-  void* alt = h->hidB.p;
+  const bool bf = c.precision == RGQA_PREC_BF16;
+  Hid cur{h->hidA.p, bf ? static_cast<float*>(h->resA.p) : static_cast<float*>(h->hidA.p)};
+  Hid alt{h->hidB.p, bf ? static_cast<float*>(h->resB.p) : static_cast<float*>(h->hidB.p)};
 
   // ---- embeddings (modeling.py:876) ----
-  if (embed_ln(st, dt, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, cur, B, L, H, c.vocab_size,
+  if (embed_ln(st, dt, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, cur.act, res_copy_rows(h, cur, 0), B, L, H, c.vocab_size,
                c.max_position, c.type_vocab, c.ln_eps))
     return 1;
   // ---- visual feature encoder (modeling.py:507-517) ----
@@ -606,7 +630,7 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
     float* pre = reinterpret_cast<float*>(rows_at(h->pre.p, Ml, H, 4));
     if (gemm(h, st, a, c.visual_feat_dim, h->visn_fc, nullptr, 0, pre, H, 1, static_cast<int>(Mv), EPI_BIAS)) return 1;
     if (visn_combine(st, dt, pre, pos, c.visual_pos_dim, h->box_W, h->box_b, h->visn_ln.g, h->visn_ln.b, h->box_ln.g,
-                     h->box_ln.b, rows_at(cur, Ml, H, es), static_cast<int>(Mv), H, c.ln_eps))
+                     h->box_ln.b, rows_at(cur.act, Ml, H, es), res_copy_rows(h, cur, Ml), static_cast<int>(Mv), H, c.ln_eps))
       return 1;
   }
   // ---- language layers (modeling.py:553-554): rows [0, Ml) ----
@@ -626,7 +650,7 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
     char* qkv = static_cast<char*>(h->qkv.p);
     char* qkv_v = rows_at(h->qkv.p, Ml, 3 * H, es);
     // cross attention: ONE BertCrossattLayer serves both directions on the pre-update inputs (:455-459)
-    if (gemm(h, st, cur, H, w.cross.qkv, nullptr, 0, qkv, 3 * H, of32, static_cast<int>(Mt), EPI_BIAS)) return 1;
+    if (gemm(h, st, cur.act, H, w.cross.qkv, nullptr, 0, qkv, 3 * H, of32, static_cast<int>(Mt), EPI_BIAS)) return 1;
     // lang queries attend visual keys/values (no mask)
     if (attention(st, dt, qkv, 3 * H, qkv_v + static_cast<size_t>(H) * es, 3 * H, qkv_v + static_cast<size_t>(2 * H) * es,
                   3 * H, nullptr, h->ctx.p, H, B, L, V, c.heads))
@@ -635,8 +659,8 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
     if (attention(st, dt, qkv_v, 3 * H, qkv + static_cast<size_t>(H) * es, 3 * H, qkv + static_cast<size_t>(2 * H) * es,
                   3 * H, mask, rows_at(h->ctx.p, Ml, H, es), H, B, V, L, c.heads))
       return 1;
-    if (gemm(h, st, h->ctx.p, H, w.cross.out, cur, H, h->pre.p, H, 1, static_cast<int>(Mt), EPI_RESID)) return 1;
-    if (layernorm(st, dt, static_cast<const float*>(h->pre.p), H, w.cross.ln.g, w.cross.ln.b, alt, static_cast<int>(Mt), H,
+    if (gemm(h, st, h->ctx.p, H, w.cross.out, resid_rows(h, cur, 0), H, h->pre.p, H, 1, static_cast<int>(Mt), EPI_RESID)) return 1;
+    if (layernorm(st, dt, static_cast<const float*>(h->pre.p), H, w.cross.ln.g, w.cross.ln.b, alt.act, res_copy_rows(h, alt, 0), static_cast<int>(Mt), H,
                   c.ln_eps))
       return 1;
     // self attention per stream (:461-465): alt -> cur
@@ -645,13 +669,13 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
     // FFNs per stream (:467-475): cur -> alt
     if (ffn_block(h, st, w.lang_ffn, cur, alt, 0, static_cast<int>(Ml))) return 1;
     if (ffn_block(h, st, w.visn_ffn, cur, alt, Ml, static_cast<int>(Mv))) return 1;
-    void* t = cur;
+    const Hid t = cur;
     cur = alt;
     alt = t;
   }
   // ---- pooler + answer head (modeling.py:884, gqa_model.py:40-41) ----
   if (pooled_out == nullptr && logits_out == nullptr) return 0;
-  return head_block(h, st, cur, B, L, pooled_out, logits_out);
+  return head_block(h, st, cur.act, B, L, pooled_out, logits_out);
 }
 
 int rgqa_uniter_forward(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos7,
@@ -673,12 +697,13 @@ int rgqa_uniter_forward(rgqa_handle* h, void* stream, const void* feat, int feat
   // joint key mask [B, S] = [text mask | ones] lives at the tail of the head scratch
   const size_t es = act_size(h);
   const int dt = act_dtype(h);
+  const bool bf = c.precision == RGQA_PREC_BF16;
   if (h->mahabuf.ensure(static_cast<size_t>(B) * S * 4 + 256)) return 1;
   int32_t* jmask = static_cast<int32_t*>(h->mahabuf.p);
 
   // text embeddings -> ctx buffer rows [0, Ml) (scratch), image embeddings -> ctx rows [Ml, Mt),
   // then interleave per sample into hidA as [B, S, H]
-  if (embed_ln(st, dt, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, h->ctx.p, B, L, H, c.vocab_size,
+  if (embed_ln(st, dt, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, h->ctx.p, bf ? static_cast<float*>(h->pre.p) : nullptr, B, L, H, c.vocab_size,
                c.max_position, c.type_vocab, c.ln_eps))
     return 1;
   {
@@ -696,17 +721,25 @@ int rgqa_uniter_forward(rgqa_handle* h, void* stream, const void* feat, int feat
     // image tokens carry token type 1 (uniter/entry.py:92, modeling.py:629)
     if (uniter_img_combine(st, dt, pre, pos7, c.visual_pos_dim, h->box_W, h->box_b, h->visn_ln.g, h->visn_ln.b,
                            h->box_ln.g, h->box_ln.b, h->typeemb + H, h->img_ln.g, h->img_ln.b,
-                           rows_at(h->ctx.p, Ml, H, es), static_cast<int>(Mv), H, c.ln_eps))
+                           rows_at(h->ctx.p, Ml, H, es), bf ? pre : nullptr, static_cast<int>(Mv), H, c.ln_eps))
       return 1;
   }
-  void* cur = h->hidA.p;
-  void* alt = h->hidB.p;
+  Hid cur{h->hidA.p, bf ? static_cast<float*>(h->resA.p) : static_cast<float*>(h->hidA.p)};
+  Hid alt{h->hidB.p, bf ? static_cast<float*>(h->resB.p) : static_cast<float*>(h->hidB.p)};
   // per-sample interleave: 2-D strided copies on the stream (rows of one sample are contiguous)
-  RGQA_CUDA_OK(cudaMemcpy2DAsync(cur, static_cast<size_t>(S) * H * es, h->ctx.p, static_cast<size_t>(L) * H * es,
+  RGQA_CUDA_OK(cudaMemcpy2DAsync(cur.act, static_cast<size_t>(S) * H * es, h->ctx.p, static_cast<size_t>(L) * H * es,
                                  static_cast<size_t>(L) * H * es, B, cudaMemcpyDeviceToDevice, st));
-  RGQA_CUDA_OK(cudaMemcpy2DAsync(static_cast<char*>(cur) + static_cast<size_t>(L) * H * es, static_cast<size_t>(S) * H * es,
-                                 rows_at(h->ctx.p, Ml, H, es), static_cast<size_t>(V) * H * es,
-                                 static_cast<size_t>(V) * H * es, B, cudaMemcpyDeviceToDevice, st));
+  RGQA_CUDA_OK(cudaMemcpy2DAsync(static_cast<char*>(cur.act) + static_cast<size_t>(L) * H * es,
+                                 static_cast<size_t>(S) * H * es, rows_at(h->ctx.p, Ml, H, es),
+                                 static_cast<size_t>(V) * H * es, static_cast<size_t>(V) * H * es, B,
+                                 cudaMemcpyDeviceToDevice, st));
+  if (bf) {  // the fp32 residual copies (written into `pre` by the two embedding kernels) take the same route
+    RGQA_CUDA_OK(cudaMemcpy2DAsync(cur.res, static_cast<size_t>(S) * H * 4, h->pre.p, static_cast<size_t>(L) * H * 4,
+                                   static_cast<size_t>(L) * H * 4, B, cudaMemcpyDeviceToDevice, st));
+    RGQA_CUDA_OK(cudaMemcpy2DAsync(cur.res + static_cast<size_t>(L) * H, static_cast<size_t>(S) * H * 4,
+                                   rows_at(h->pre.p, Ml, H, 4), static_cast<size_t>(V) * H * 4,
+                                   static_cast<size_t>(V) * H * 4, B, cudaMemcpyDeviceToDevice, st));
+  }
   RGQA_CUDA_OK(cudaMemsetAsync(jmask, 0, static_cast<size_t>(B) * S * 4, st));
   RGQA_CUDA_OK(cudaMemcpy2DAsync(jmask, static_cast<size_t>(S) * 4, mask, static_cast<size_t>(L) * 4,
                                  static_cast<size_t>(L) * 4, B, cudaMemcpyDeviceToDevice, st));
@@ -721,7 +754,7 @@ int rgqa_uniter_forward(rgqa_handle* h, void* stream, const void* feat, int feat
     if (ffn_block(h, st, h->l_layers[i].ffn, alt, cur, 0, static_cast<int>(Mt))) return 1;
   }
   if (pooled_out == nullptr && logits_out == nullptr) return 0;
-  return head_block(h, st, cur, B, S, pooled_out, logits_out);
+  return head_block(h, st, cur.act, B, S, pooled_out, logits_out);
 }
 
 int rgqa_set_maha(rgqa_handle* h, const float* mu, const float* precision, int on_device) {
@@ -805,18 +838,18 @@ int rgqa_attention(void* stream, int dtype, const void* q, int64_t ldq, const vo
 int rgqa_embed_ln(void* stream, int out_dtype, const int32_t* ids, const int32_t* seg, const float* word,
                   const float* pos, const float* type, const float* gamma, const float* beta, void* out, int B,
                   int L, int H, int vocab, int max_pos, int n_types, float eps) {
-  return embed_ln(static_cast<cudaStream_t>(stream), out_dtype, ids, seg, word, pos, type, gamma, beta, out, B, L, H,
-                  vocab, max_pos, n_types, eps);
+  return embed_ln(static_cast<cudaStream_t>(stream), out_dtype, ids, seg, word, pos, type, gamma, beta, out, nullptr, B, L,
+                  H, vocab, max_pos, n_types, eps);
 }
 int rgqa_layernorm(void* stream, int out_dtype, const float* x, int64_t ldx, const float* gamma, const float* beta,
                    void* y, int M, int H, float eps) {
-  return layernorm(static_cast<cudaStream_t>(stream), out_dtype, x, ldx, gamma, beta, y, M, H, eps);
+  return layernorm(static_cast<cudaStream_t>(stream), out_dtype, x, ldx, gamma, beta, y, nullptr, M, H, eps);
 }
 int rgqa_visn_combine(void* stream, int out_dtype, const float* x_pre, const float* boxes, int box_dim,
                       const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
                       const float* b2, void* out, int M, int H, float eps) {
-  return visn_combine(static_cast<cudaStream_t>(stream), out_dtype, x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, out, M,
-                      H, eps);
+  return visn_combine(static_cast<cudaStream_t>(stream), out_dtype, x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, out,
+                      nullptr, M, H, eps);
 }
 int rgqa_cast_f32_to_bf16(void* stream, const float* in, void* out, int64_t n) {
   return cast_f32_to_bf16(static_cast<cudaStream_t>(stream), in, out, n);

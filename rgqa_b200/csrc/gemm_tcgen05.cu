@@ -10,7 +10,7 @@
 //   warp 0      TMA producer   global -> 128B-swizzled smem ring (kStages deep), mbarrier tx-count
 //   warp 1      MMA issuer     one lane issues tcgen05.mma (128 x BN x 16), accumulators in TMEM
 //   warp 2      TMEM allocator (2 x BN fp32 columns: double-buffered accumulator)
-//   warps 4-11  epilogue       tcgen05.ld 32x32b -> registers, fused bias / erf-GELU / tanh / residual,
+//   warps 4-11  epilogue       tcgen05.ld 32x32b -> registers, fused bias / erf-GELU / tanh / fp32 residual,
 //                              bf16 or fp32 store; overlaps the next tile's main loop
 // Tails: TMA zero-fills out-of-bounds rows of A (M tail) and W (N tail); stores are predicated.
 #include <cuda.h>
@@ -44,7 +44,7 @@ struct Cfg {
 struct GemmParams {
   int M, N, K;
   const float* bias;           // [N] fp32 or nullptr
-  const __nv_bfloat16* resid;  // [M, ldr] bf16 (EPI_RESID) or nullptr
+  const float* resid;          // [M, ldr] fp32 residual stream (EPI_RESID) or nullptr
   long long ldr;
   void* out;
   long long ldo;
@@ -224,20 +224,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           if constexpr (EPI == EPI_RESID) {
             if (row_ok) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(p.resid + static_cast<long long>(row) * p.ldr + col0);
+              const float4* r4 = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * p.ldr + col0);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 r = __ldg(r4 + i);
-                float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c2 = unpack_bf16x2(r.z),
-                       d = unpack_bf16x2(r.w);
-                f[8 * i + 0] += a.x;
-                f[8 * i + 1] += a.y;
-                f[8 * i + 2] += b.x;
-                f[8 * i + 3] += b.y;
-                f[8 * i + 4] += c2.x;
-                f[8 * i + 5] += c2.y;
-                f[8 * i + 6] += d.x;
-                f[8 * i + 7] += d.y;
+              for (int i = 0; i < 8; ++i) {
+                const float4 r = __ldg(r4 + i);
+                f[4 * i + 0] += r.x;
+                f[4 * i + 1] += r.y;
+                f[4 * i + 2] += r.z;
+                f[4 * i + 3] += r.w;
               }
             }
           }
@@ -271,7 +265,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (row_ok && col < p.N) {
               float x = f[i];
               if (p.bias != nullptr) x += __ldg(p.bias + col);
-              if constexpr (EPI == EPI_RESID) x += __bfloat162float(p.resid[static_cast<long long>(row) * p.ldr + col]);
+              if constexpr (EPI == EPI_RESID) x += p.resid[static_cast<long long>(row) * p.ldr + col];
               x = apply_act<EPI>(x);
               if constexpr (sizeof(OutT) == 2)
                 reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<long long>(row) * p.ldo + col] = __float2bfloat16_rn(x);
@@ -393,13 +387,13 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
   p.N = N;
   p.K = K;
   p.bias = bias;
-  p.resid = static_cast<const __nv_bfloat16*>(resid);
+  p.resid = static_cast<const float*>(resid);
   p.ldr = ldr;
   p.out = out;
   p.ldo = ldo;
   const int esz = out_f32 ? 4 : 2;
   const bool out_al = (reinterpret_cast<uintptr_t>(out) % 16 == 0) && ((ldo * esz) % 16 == 0);
-  const bool res_al = (resid == nullptr) || ((reinterpret_cast<uintptr_t>(resid) % 16 == 0) && ((ldr * 2) % 16 == 0));
+  const bool res_al = (resid == nullptr) || ((reinterpret_cast<uintptr_t>(resid) % 16 == 0) && ((ldr * 4) % 16 == 0));
   const bool bias_al = (bias == nullptr) || (reinterpret_cast<uintptr_t>(bias) % 16 == 0);
   p.vec_ok = (out_al && res_al && bias_al) ? 1 : 0;
   return bn == 256 ? dispatch_epi<256>(stream, tmA, tmB, p, epi, out_f32)

@@ -18,7 +18,7 @@ enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
 
 // ---- GEMMs -------------------------------------------------------------------------------------
 // bf16 tensor-core path: A [M,K] bf16 (row stride lda), W [N,K] bf16 (row stride ldw), bias fp32,
-// resid bf16 [M,*] (EPI_RESID), out bf16 or fp32.
+// resid fp32 [M,*] (EPI_RESID: the fp32 residual stream), out bf16 or fp32.
 int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
               const void* resid, long long ldr, void* out, long long ldo, int out_f32, int M, int N, int K, int epi);
 // fp32 SIMT path (precise mode): everything fp32.
@@ -36,20 +36,22 @@ int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, cons
 // ---- row-wise ops ------------------------------------------------------------------------------
 // LN(word[ids] + pos[0..L) + type[seg]) (modeling.py:278-292); tables and gamma/beta fp32.
 int embed_ln(cudaStream_t stream, int out_dtype, const int32_t* ids, const int32_t* seg, const float* word,
-             const float* pos, const float* type, const float* gamma, const float* beta, void* out, int B, int L,
-             int H, int vocab, int max_pos, int n_types, float eps);
+             const float* pos, const float* type, const float* gamma, const float* beta, void* out, float* out32, int B,
+             int L, int H, int vocab, int max_pos, int n_types, float eps);
 // y = LN(x) * gamma + beta; x fp32 [M,H] (row stride ldx), y fp32 or bf16 [M,H] dense.
+// Every row kernel takes an optional fp32 copy pointer (y32 / out32): in the bf16 path the hidden state is
+// kept twice, bf16 as the next GEMM's A operand and fp32 as the residual stream.
 int layernorm(cudaStream_t stream, int out_dtype, const float* x, long long ldx, const float* gamma,
-              const float* beta, void* y, int M, int H, float eps);
+              const float* beta, void* y, float* y32, int M, int H, float eps);
 // (LN(x_pre) + LN(box·Wbᵀ + bb)) / 2 (modeling.py:507-517); x_pre = feat·Wfᵀ + bf, fp32 [M,H].
 int visn_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const float* boxes, int box_dim,
                  const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
-                 const float* b2, void* out, int M, int H, float eps);
+                 const float* b2, void* out, float* out32, int M, int H, float eps);
 // UNITER image embedding tail: LN3( LN1(x_pre) + LN2(pos7·Wpᵀ + bp) + type_emb ) (uniter/modeling.py:606-612).
 int uniter_img_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const float* pos, int pos_dim,
                        const float* Wp, const float* bp, const float* g1, const float* b1, const float* g2,
-                       const float* b2, const float* type_row, const float* g3, const float* b3, void* out, int M,
-                       int H, float eps);
+                       const float* b2, const float* type_row, const float* g3, const float* b3, void* out,
+                       float* out32, int M, int H, float eps);
 int cast_f32_to_bf16(cudaStream_t stream, const float* in, void* out, long long n);
 int cast_bf16_to_f32(cudaStream_t stream, const void* in, float* out, long long n);
 // copy rows: dst[r, :] = src[r*src_stride_rows .. ] for r < rows (strided gather of whole rows)

@@ -42,10 +42,12 @@ __device__ __forceinline__ void normalize(float4 (&x)[NV], float mean, float rst
 }
 
 template <int NV, typename OutT>
-__device__ __forceinline__ void store_row(const float4 (&x)[NV], OutT* out_row, int lane) {
+__device__ __forceinline__ void store_row(const float4 (&x)[NV], OutT* out_row, int lane, float* copy_row = nullptr) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = i * 128 + lane * 4;
+    // optional fp32 copy: the residual stream stays fp32 while the GEMM operand copy is bf16
+    if (copy_row != nullptr) *reinterpret_cast<float4*>(copy_row + c) = x[i];
     if constexpr (sizeof(OutT) == 4) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_row) + c) = x[i];
     } else {
@@ -62,7 +64,7 @@ template <int NV, typename OutT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ seg, const float* __restrict__ word,
                 const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ gamma,
-                const float* __restrict__ beta, OutT* __restrict__ out, int rows, int L, int H, float eps, int vocab,
+                const float* __restrict__ beta, OutT* __restrict__ out, float* __restrict__ out32, int rows, int L, int H, float eps, int vocab,
                 int n_types) {
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -87,14 +89,15 @@ embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ seg
   float mean, rstd;
   row_stats<NV>(x, H, eps, mean, rstd);
   normalize<NV>(x, mean, rstd, gamma, beta, lane);
-  store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane);
+  store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane,
+                      out32 != nullptr ? out32 + static_cast<long long>(row) * H : nullptr);
 }
 
 // ---- plain LayerNorm over fp32 rows ------------------------------------------------------------
 template <int NV, typename OutT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 layernorm_kernel(const float* __restrict__ xin, long long ldx, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, OutT* __restrict__ out, int rows, int H, float eps) {
+                 const float* __restrict__ beta, OutT* __restrict__ out, float* __restrict__ out32, int rows, int H, float eps) {
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -105,7 +108,8 @@ layernorm_kernel(const float* __restrict__ xin, long long ldx, const float* __re
   float mean, rstd;
   row_stats<NV>(x, H, eps, mean, rstd);
   normalize<NV>(x, mean, rstd, gamma, beta, lane);
-  store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane);
+  store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane,
+                      out32 != nullptr ? out32 + static_cast<long long>(row) * H : nullptr);
 }
 
 // ---- small-K projection of a per-row vector (boxes, K = 4 or 7) ---------------------------------
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 visn_combine_kernel(const float* __restrict__ x_pre, const float* __restrict__ boxes, int box_dim,
                     const float* __restrict__ Wb, const float* __restrict__ bb, const float* __restrict__ g1,
                     const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
-                    OutT* __restrict__ out, int rows, int H, float eps) {
+                    OutT* __restrict__ out, float* __restrict__ out32, int rows, int H, float eps) {
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -153,7 +157,8 @@ visn_combine_kernel(const float* __restrict__ x_pre, const float* __restrict__ b
   for (int i = 0; i < NV; ++i)
     x[i] = make_float4((x[i].x + y[i].x) / 2.f, (x[i].y + y[i].y) / 2.f, (x[i].z + y[i].z) / 2.f,
                        (x[i].w + y[i].w) / 2.f);
-  store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane);
+  store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane,
+                      out32 != nullptr ? out32 + static_cast<long long>(row) * H : nullptr);
 }
 
 // ---- UniterImageEmbeddings tail (src/uniter/modeling.py:606-612) --------------------------------
@@ -163,7 +168,7 @@ uniter_img_kernel(const float* __restrict__ x_pre, const float* __restrict__ pos
                   const float* __restrict__ Wp, const float* __restrict__ bp, const float* __restrict__ g1,
                   const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
                   const float* __restrict__ type_row, const float* __restrict__ g3, const float* __restrict__ b3,
-                  OutT* __restrict__ out, int rows, int H, float eps) {
+                  OutT* __restrict__ out, float* __restrict__ out32, int rows, int H, float eps) {
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -188,7 +193,8 @@ uniter_img_kernel(const float* __restrict__ x_pre, const float* __restrict__ pos
   }
   row_stats<NV>(x, H, eps, mean, rstd);
   normalize<NV>(x, mean, rstd, g3, b3, lane);
-  store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane);
+  store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane,
+                      out32 != nullptr ? out32 + static_cast<long long>(row) * H : nullptr);
 }
 
 // ---- casts -------------------------------------------------------------------------------------
@@ -245,27 +251,27 @@ inline int row_grid(int rows) { return (rows + kWarpsPerBlock - 1) / kWarpsPerBl
   } while (0)
 
 int embed_ln(cudaStream_t stream, int out_dtype, const int32_t* ids, const int32_t* seg, const float* word,
-             const float* pos, const float* type, const float* gamma, const float* beta, void* out, int B, int L,
-             int H, int vocab, int max_pos, int n_types, float eps) {
+             const float* pos, const float* type, const float* gamma, const float* beta, void* out, float* out32, int B,
+             int L, int H, int vocab, int max_pos, int n_types, float eps) {
   RGQA_CHECK(B > 0 && L > 0 && L <= max_pos, "embed_ln: bad B=%d L=%d (max_pos=%d)", B, L, max_pos);
   const int M = B * L;
   if (out_dtype == DT_BF16) {
-    RGQA_DISPATCH_ROW(embed_ln_kernel, __nv_bfloat16, ids, seg, word, pos, type, gamma, beta, static_cast<__nv_bfloat16*>(out), M, L, H, eps, vocab, n_types);
+    RGQA_DISPATCH_ROW(embed_ln_kernel, __nv_bfloat16, ids, seg, word, pos, type, gamma, beta, static_cast<__nv_bfloat16*>(out), out32, M, L, H, eps, vocab, n_types);
   } else {
-    RGQA_DISPATCH_ROW(embed_ln_kernel, float, ids, seg, word, pos, type, gamma, beta, static_cast<float*>(out), M, L, H, eps, vocab, n_types);
+    RGQA_DISPATCH_ROW(embed_ln_kernel, float, ids, seg, word, pos, type, gamma, beta, static_cast<float*>(out), out32, M, L, H, eps, vocab, n_types);
   }
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int layernorm(cudaStream_t stream, int out_dtype, const float* x, long long ldx, const float* gamma,
-              const float* beta, void* y, int M, int H, float eps) {
+              const float* beta, void* y, float* y32, int M, int H, float eps) {
   RGQA_CHECK(M > 0, "layernorm: empty input");
   RGQA_CHECK(ldx % 4 == 0, "layernorm: row stride must be a multiple of 4 floats");
   if (out_dtype == DT_BF16) {
-    RGQA_DISPATCH_ROW(layernorm_kernel, __nv_bfloat16, x, ldx, gamma, beta, static_cast<__nv_bfloat16*>(y), M, H, eps);
+    RGQA_DISPATCH_ROW(layernorm_kernel, __nv_bfloat16, x, ldx, gamma, beta, static_cast<__nv_bfloat16*>(y), y32, M, H, eps);
   } else {
-    RGQA_DISPATCH_ROW(layernorm_kernel, float, x, ldx, gamma, beta, static_cast<float*>(y), M, H, eps);
+    RGQA_DISPATCH_ROW(layernorm_kernel, float, x, ldx, gamma, beta, static_cast<float*>(y), y32, M, H, eps);
   }
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
@@ -273,12 +279,12 @@ int layernorm(cudaStream_t stream, int out_dtype, const float* x, long long ldx,
 
 int visn_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const float* boxes, int box_dim,
                  const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
-                 const float* b2, void* out, int M, int H, float eps) {
+                 const float* b2, void* out, float* out32, int M, int H, float eps) {
   RGQA_CHECK(M > 0 && box_dim >= 1 && box_dim <= 8, "visn_combine: bad M=%d box_dim=%d", M, box_dim);
   if (out_dtype == DT_BF16) {
-    RGQA_DISPATCH_ROW(visn_combine_kernel, __nv_bfloat16, x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<__nv_bfloat16*>(out), M, H, eps);
+    RGQA_DISPATCH_ROW(visn_combine_kernel, __nv_bfloat16, x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<__nv_bfloat16*>(out), out32, M, H, eps);
   } else {
-    RGQA_DISPATCH_ROW(visn_combine_kernel, float, x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<float*>(out), M, H, eps);
+    RGQA_DISPATCH_ROW(visn_combine_kernel, float, x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<float*>(out), out32, M, H, eps);
   }
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
@@ -286,13 +292,13 @@ int visn_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const f
 
 int uniter_img_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const float* pos, int pos_dim,
                        const float* Wp, const float* bp, const float* g1, const float* b1, const float* g2,
-                       const float* b2, const float* type_row, const float* g3, const float* b3, void* out, int M,
-                       int H, float eps) {
+                       const float* b2, const float* type_row, const float* g3, const float* b3, void* out,
+                       float* out32, int M, int H, float eps) {
   RGQA_CHECK(M > 0 && pos_dim >= 1 && pos_dim <= 8, "uniter_img_combine: bad M=%d pos_dim=%d", M, pos_dim);
   if (out_dtype == DT_BF16) {
-    RGQA_DISPATCH_ROW(uniter_img_kernel, __nv_bfloat16, x_pre, pos, pos_dim, Wp, bp, g1, b1, g2, b2, type_row, g3, b3, static_cast<__nv_bfloat16*>(out), M, H, eps);
+    RGQA_DISPATCH_ROW(uniter_img_kernel, __nv_bfloat16, x_pre, pos, pos_dim, Wp, bp, g1, b1, g2, b2, type_row, g3, b3, static_cast<__nv_bfloat16*>(out), out32, M, H, eps);
   } else {
-    RGQA_DISPATCH_ROW(uniter_img_kernel, float, x_pre, pos, pos_dim, Wp, bp, g1, b1, g2, b2, type_row, g3, b3, static_cast<float*>(out), M, H, eps);
+    RGQA_DISPATCH_ROW(uniter_img_kernel, float, x_pre, pos, pos_dim, Wp, bp, g1, b1, g2, b2, type_row, g3, b3, static_cast<float*>(out), out32, M, H, eps);
   }
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;

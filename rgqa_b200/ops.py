@@ -29,7 +29,8 @@ def _dt(t: torch.Tensor) -> int:
 def linear_bf16(x, weight, bias=None, epilogue=L.EPI_BIAS, residual=None, out_dtype=torch.bfloat16):
     """``epilogue(x @ weight.T + bias [+ residual])`` on the tcgen05 tensor cores.
 
-    x: [M, K] bf16 (row stride may exceed K), weight: [N, K] bf16 (nn.Linear layout), bias: [N] f32.
+    x: [M, K] bf16 (row stride may exceed K), weight: [N, K] bf16 (nn.Linear layout), bias: [N] f32,
+    residual: [M, N] f32.
     Reference: every ``nn.Linear`` of src/lxrt/modeling.py (e.g. :321-323, :358, :399, :412, :578).
     """
     _need_cuda(x, weight, bias, residual)
@@ -43,7 +44,7 @@ def linear_bf16(x, weight, bias=None, epilogue=L.EPI_BIAS, residual=None, out_dt
         assert bias.dtype == torch.float32 and bias.is_contiguous()
     ldr = 0
     if residual is not None:
-        assert residual.dtype == torch.bfloat16 and residual.stride(1) == 1
+        assert residual.dtype == torch.float32 and residual.stride(1) == 1  # the fp32 residual stream
         ldr = residual.stride(0)
     lib = L.load()
     L.check(lib.rgqa_gemm_bf16(L.current_stream_ptr(), L.ptr(x), x.stride(0), L.ptr(weight), weight.stride(0),

@@ -158,7 +158,7 @@ def golden_tokenizer():
             words.add(w)
     pieces = set()
     for w in sorted(words):
-        if len(w) <= 4 or hash(w) % 3:
+        if len(w) <= 4 or __import__('zlib').crc32(w.encode()) % 3:
             pieces.add(w)
         else:  # force sub-word splitting for a third of the longer words
             pieces.add(w[:3]); pieces.add("##" + w[3:])

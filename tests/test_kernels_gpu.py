@@ -42,7 +42,7 @@ def test_gemm_bf16_matches_torch(cuda_device, M, N, K, epi, out_dtype, lda):
     a = a_full[:, :K]
     w = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(cuda_device)
     bias = torch.randn(N, generator=g).to(cuda_device)
-    resid = (torch.randn(M, N, generator=g)).to(torch.bfloat16).to(cuda_device) if epi == "resid" else None
+    resid = torch.randn(M, N, generator=g).to(cuda_device) if epi == "resid" else None  # fp32 residual stream
     code = {"bias": L.EPI_BIAS, "gelu": L.EPI_GELU, "tanh": L.EPI_TANH, "resid": L.EPI_RESID}[epi]
     out = ops.linear_bf16(a, w, bias, epilogue=code, residual=resid, out_dtype=out_dtype)
     torch.cuda.synchronize()
