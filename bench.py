@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — the RGQA evaluation hot path on N B200s (one process per GPU).
+
+Workload (BASELINE.json configs[1]): LXMERT-base (9/5/5) GQA eval forward + energy (top-2) and Mahalanobis
+scoring, batch 1024 questions per GPU per step, 36 x 2048 RoI features + 20 tokens, bf16 tensor-core path,
+random-init weights (seed 9595), synthetic inputs (seed 1234).  A "step" is one batch through the whole path.
+
+  value   questions/s with inputs (fp32 features, boxes, ids) already resident in HBM; the fp32->bf16 feature
+          cast is part of every step.  Two resident batches (2 x 302 MB > 126 MB L2) alternate.
+  e2e     the same metric through the public sweep API (rgqa_b200.tasks.gqa_eval.SweepRunner over
+          GQAModel.forward_ids + Engine.score) from PINNED HOST buffers: per step one H2D of the batch and one
+          D2H of (score, label) for both scorers, uploads double-buffered against compute.
+  --impl reference   the reference algorithm on the host cores (the CPU oracle, a port: the reference is
+          pure Python/PyTorch with no build), all threads, bounded sample of B=32 per step.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GQA questions/sec, LXMERT fwd+OOD score, 1/2/4/8 B200; tensor-pipe % of peak"
+GFLOP_PER_Q = {20: 10.5827, 30: 12.8330}  # 2*M*N*K per GEMM + 4*Sq*Sk*H per attention
+MAHA_GFLOP_PER_Q = 0.00401
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="questions per GPU per step")
+    ap.add_argument("--seq-len", type=int, default=20)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-batch", type=int, default=32)
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained)"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML every 100 ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the CPU oracle (port of the reference algorithm) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(seq_len, batch, steps, warmup, budget_s=None):
+    from oracle import lxmert_oracle as O
+    from oracle import scorers_oracle as S
+    from rgqa_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = syn.lxmert_state_dict()
+    inp = syn.make_inputs(batch, seq_len, seed=1234)
+    mu, P = syn.maha_stats()
+
+    def step():
+        logit, x = O.gqa_model_forward(sd, inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"])
+        S.energy_top2(logit)
+        S.mahalanobis(x, mu, P)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        step()
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": batch * done / dt, "unit": "questions/s", "cores": cores, "kind": "port",
+            "sample": f"{done} steps of B={batch}, L={seq_len}: oracle LXMERT forward + energy + literal 1842-class "
+                      f"Mahalanobis loop, fp32, torch {torch.__version__} with {cores} threads",
+            "ms_per_step": 1e3 * dt / done, "steps": done}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_rate(a.seq_len, a.ref_batch, a.steps, min(a.warmup, 2), budget_s=150)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "questions/s", "n_gpus": a.gpus,
+            "steps": r["steps"], "warmup": min(a.warmup, 2), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "LXMERT-base 9/5/5 GQA eval forward + energy(top-2) + Mahalanobis, "
+                                   f"B={a.ref_batch} per step (bounded sample of the B={a.batch} workload), L={a.seq_len}, "
+                                   "36x2048 RoI, random-init seed 9595"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "questions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import ctypes as C
+    import torch.distributed as dist
+    from rgqa_b200 import _lib as L
+    from rgqa_b200 import synthetic as syn
+    from rgqa_b200.tasks.gqa_eval import SweepRunner, gather_results
+    from rgqa_b200.tasks.gqa_model import GQAModel_maha
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device; there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+
+    class Ns:  # the flags GQAModel reads (rgqa_b200.param)
+        llayers, xlayers, rlayers, from_scratch, precision, vocab, max_seq_length = 9, 5, 5, False, a.precision, None, a.seq_len
+    model = GQAModel_maha(1842, args=Ns, max_seq_length=a.seq_len)
+    model.load_state_dict(syn.lxmert_state_dict(seed=9595, variant="init"), strict=True)
+    model = model.to(dev)
+    eng = model.engine()
+    mu, P = syn.maha_stats()
+    eng.set_maha(mu, P)
+
+    B, Lq = a.batch, a.seq_len
+    methods = ("energy", "maha")
+    runner = SweepRunner(model, methods, device=dev)
+    # two distinct batches, host (pinned) and device-resident copies
+    host = []
+    for i in range(2):
+        inp = syn.make_inputs(B, Lq, seed=1234 + 17 * i + 1000 * rank)
+        host.append(tuple(t.pin_memory() for t in (inp["feat"], inp["pos"], inp["ids"].to(torch.int32),
+                                                   inp["mask"].to(torch.int32), inp["seg"].to(torch.int32))))
+    resident = [tuple(t.to(dev) for t in hb) for hb in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    d2h_bytes = len(methods) * B * 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident timing ----------------
+    def dev_step(i):
+        f, p, ids, mask, seg = resident[i & 1]
+        return runner.score_device_batch(f, p, ids, mask, seg)
+
+    for i in range(a.warmup):
+        dev_step(i)
+    barrier()
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    lib.rgqa_prof_enable(1)
+    launches0 = lib.rgqa_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    keep = []
+    for i in range(a.steps):
+        keep.append(dev_step(i))
+    # the sweep ends with ONE all-gather of (score, label) per scorer (N > 1)
+    for m in range(len(methods)):
+        gather_results(torch.cat([k[m][0] for k in keep]), torch.cat([k[m][1] for k in keep]))
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    lib.rgqa_prof_enable(0)
+    launches = (lib.rgqa_launch_count() - launches0) // max(a.steps, 1)
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_step = ms_total / a.steps
+    value = world * B * a.steps / (ms_total * 1e-3)
+    nk = 4
+    ms_sum, fl_sum, cnt = (C.c_double * nk)(), (C.c_double * nk)(), (C.c_longlong * nk)()
+    L.check(lib.rgqa_prof_collect(ms_sum, fl_sum, cnt), "rgqa_prof_collect")
+    peak_tf, peak_gbs, peak_src = peaks()
+    gemm_tf = (fl_sum[0] / (ms_sum[0] * 1e-3)) / 1e12 if ms_sum[0] > 0 else 0.0
+    gq = GFLOP_PER_Q.get(Lq, GFLOP_PER_Q[20]) + MAHA_GFLOP_PER_Q
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all encoder/head GEMM launches)",
+                "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf, "traffic": None,
+                "peak_source": peak_src, "launches_per_step": int(cnt[0] // max(a.steps, 1)),
+                "gemm_ms_per_step": ms_sum[0] / a.steps, "gemm_share_of_step": (ms_sum[0] / a.steps) / ms_step,
+                "attention_ms_per_step": ms_sum[2] / a.steps, "fp32_gemm_ms_per_step": ms_sum[1] / a.steps,
+                "whole_step_tflops": (value / world) * gq * 1e9 / 1e12,
+                "whole_step_frac": (value / world) * gq * 1e9 / 1e12 / peak_tf}
+
+    # ---------------- end-to-end from pinned host memory ----------------
+    e2e = None
+    if not a.no_e2e:
+        out_host = [[(torch.empty(B, dtype=torch.float32).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory())
+                     for _ in methods] for _ in range(2)]
+
+        def e2e_step(i):
+            f, p, ids, mask, seg = host[i & 1]
+            res = runner.submit(f, p, ids, mask, seg)
+            for (s, l), (hs, hl) in zip(res, out_host[i & 1]):
+                hs.copy_(s, non_blocking=True)
+                hl.copy_(l, non_blocking=True)
+
+        for i in range(a.warmup):
+            e2e_step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(a.steps):
+            e2e_step(i)
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        e2e = {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": "questions/s", "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / a.steps,
+               "host_feature_dtype": "f32 (reference loader format, src/tasks/gqa_data.py:173-238)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = {k: v for k, v in cpu_reference_rate(Lq, a.ref_batch, 16, 1, budget_s=25).items()
+               if k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "questions/s", "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
+                "config": {"workload": "LXMERT-base 9/5/5 GQA eval forward + energy(top-2) + Mahalanobis scoring "
+                                       f"(BASELINE.json configs[1]), B={B} questions per GPU per step, L={Lq}, 36x2048 RoI, "
+                                       "random-init seed 9595",
+                           "questions_per_step": world * B, "parallelism": f"batch-sharded x{world}, one all-gather per sweep",
+                           "l2": "inputs larger than L2: two alternating 302 MB fp32 feature batches per GPU"},
+                "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

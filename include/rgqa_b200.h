@@ -118,6 +118,16 @@ int rgqa_set_maha(rgqa_handle* h, const float* mu, const float* precision, int o
 int rgqa_score(rgqa_handle* h, void* stream, int mode, const float* logits, const float* pooled, int B,
                float* score_out, int32_t* label_out, float* maha_full_out);
 
+/* ---- measurement hooks (bench.py) ----------------------------------------------------------- */
+/* Kernels enqueued by this library since it was loaded. */
+long long rgqa_launch_count(void);
+/* When on, every GEMM / attention launch is bracketed by CUDA events on its own stream. */
+void rgqa_prof_enable(int on);
+/* Sum of event-timed durations (ms), algorithmic FLOPs and launch counts per kernel kind since the last
+ * collect; arrays of RGQA_PROF_NKINDS entries: 0 tcgen05 GEMM, 1 fp32 GEMM, 2 attention, 3 other. */
+#define RGQA_PROF_NKINDS 4
+int rgqa_prof_collect(double* ms_sum, double* flops_sum, long long* count);
+
 /* ---- per-kernel entry points (unit tests, integration of single ops) ------------------------- */
 int rgqa_gemm_bf16(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                    const void* resid, int64_t ldr, void* out, int64_t ldo, int out_dtype, int M, int N, int K,

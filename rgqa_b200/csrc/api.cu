@@ -820,6 +820,14 @@ int rgqa_score(rgqa_handle* h, void* stream, int mode, const float* logits, cons
   return score_logits(st, mode, logits, A, B, A, score_out, label_out);
 }
 
+// ---- measurement hooks ----
+long long rgqa_launch_count(void) { return launch_count(); }
+void rgqa_prof_enable(int on) { prof_enable(on != 0); }
+int rgqa_prof_collect(double* ms_sum, double* flops_sum, long long* count) {
+  RGQA_CHECK(ms_sum && flops_sum && count, "rgqa_prof_collect: null argument");
+  return prof_collect(ms_sum, flops_sum, count, PROF_NKINDS);
+}
+
 // ---- per-kernel entry points ----
 int rgqa_gemm_bf16(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                    const void* resid, int64_t ldr, void* out, int64_t ldo, int out_dtype, int M, int N, int K,

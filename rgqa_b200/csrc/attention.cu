@@ -151,6 +151,7 @@ int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, cons
              "attention: row strides must be multiples of 16 bytes");
   const size_t smem = static_cast<size_t>(Lk) * (2 * HD + kThreads + 1) * sizeof(float);
   const int grid = B * heads;
+  void* tok = prof_begin(stream);
   if (dtype == DT_F32) {
     static bool cfg = false;
     if (!cfg) {
@@ -171,6 +172,8 @@ int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, cons
         static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), ldk,
         static_cast<const __nv_bfloat16*>(v), ldv, key_mask, static_cast<__nv_bfloat16*>(out), ldo, Lq, Lk, heads);
   }
+  prof_end(tok, stream, 4.0 * B * static_cast<double>(Lq) * Lk * heads * HD, PROF_ATTENTION);
+  note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }

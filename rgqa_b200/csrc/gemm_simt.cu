@@ -109,6 +109,7 @@ int gemm_f32(cudaStream_t stream, const float* A, long long lda, const float* W,
   RGQA_CHECK(M > 0 && N > 0 && K > 0, "gemm_f32: empty problem M=%d N=%d K=%d", M, N, K);
   RGQA_CHECK(epi != EPI_RESID || resid != nullptr, "gemm_f32: EPI_RESID needs a residual pointer");
   dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
+  void* tok = prof_begin(stream);
   switch (epi) {
     case EPI_BIAS:
       gemm_f32_kernel<EPI_BIAS><<<grid, 256, 0, stream>>>(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K);
@@ -126,6 +127,8 @@ int gemm_f32(cudaStream_t stream, const float* A, long long lda, const float* W,
       set_error("gemm_f32: unknown epilogue %d", epi);
       return 1;
   }
+  prof_end(tok, stream, 2.0 * M * static_cast<double>(N) * K, PROF_GEMM_F32);
+  note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }

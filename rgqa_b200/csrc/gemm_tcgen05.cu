@@ -347,7 +347,10 @@ int launch(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   }
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  void* tok = prof_begin(stream);
   kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
+  prof_end(tok, stream, 2.0 * p.M * static_cast<double>(p.N) * p.K, PROF_GEMM_TC);
+  note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -74,4 +74,15 @@ int maha_finish(cudaStream_t stream, const float* q, const float* G, long long l
 // q[b] = sum_j t[b,j] * x[b,j]
 int rowdot(cudaStream_t stream, const float* a, const float* b, float* out, int M, int H);
 
+
+// ---- measurement hooks (prof.cu) ----------------------------------------------------------------
+void note_launch(int n = 1);
+long long launch_count();
+void prof_enable(bool on);
+bool prof_on();
+void* prof_begin(cudaStream_t st);
+void prof_end(void* tok, cudaStream_t st, double flops, int kind);
+int prof_collect(double* ms_sum, double* flops_sum, long long* count, int nkinds);
+enum ProfKind : int { PROF_GEMM_TC = 0, PROF_GEMM_F32 = 1, PROF_ATTENTION = 2, PROF_OTHER = 3, PROF_NKINDS = 4 };
+
 }  // namespace rgqa

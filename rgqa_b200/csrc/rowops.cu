@@ -260,6 +260,7 @@ int embed_ln(cudaStream_t stream, int out_dtype, const int32_t* ids, const int32
   } else {
     RGQA_DISPATCH_ROW(embed_ln_kernel, float, ids, seg, word, pos, type, gamma, beta, static_cast<float*>(out), out32, M, L, H, eps, vocab, n_types);
   }
+  note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -273,6 +274,7 @@ int layernorm(cudaStream_t stream, int out_dtype, const float* x, long long ldx,
   } else {
     RGQA_DISPATCH_ROW(layernorm_kernel, float, x, ldx, gamma, beta, static_cast<float*>(y), y32, M, H, eps);
   }
+  note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -286,6 +288,7 @@ int visn_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const f
   } else {
     RGQA_DISPATCH_ROW(visn_combine_kernel, float, x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<float*>(out), out32, M, H, eps);
   }
+  note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -300,6 +303,7 @@ int uniter_img_combine(cudaStream_t stream, int out_dtype, const float* x_pre, c
   } else {
     RGQA_DISPATCH_ROW(uniter_img_kernel, float, x_pre, pos, pos_dim, Wp, bp, g1, b1, g2, b2, type_row, g3, b3, static_cast<float*>(out), out32, M, H, eps);
   }
+  note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -320,6 +324,7 @@ int cast_f32_to_bf16(cudaStream_t stream, const float* in, void* out, long long 
     cast_f32_bf16_tail<<<static_cast<int>((rem + 255) / 256), 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out),
                                                                               start, n);
   }
+  note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -329,6 +334,7 @@ int cast_bf16_to_f32(cudaStream_t stream, const void* in, float* out, long long 
   long long blocks = (n + 255) / 256;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
   cast_bf16_f32_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), out, n);
+  note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -344,6 +350,7 @@ int gather_rows(cudaStream_t stream, int dtype, const void* src, long long src_l
   else
     gather_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), src_ld,
                                                                  static_cast<__nv_bfloat16*>(dst), dst_ld, rows, H);
+  note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -131,6 +131,7 @@ int score_logits(cudaStream_t stream, int mode, const float* logits, long long l
   RGQA_CHECK(B > 0 && A > 0, "score_logits: empty input B=%d A=%d", B, A);
   RGQA_CHECK(mode >= SCORE_MSP && mode <= SCORE_LSE, "score_logits: mode %d is not a logit scorer", mode);
   score_logits_kernel<<<(B + kWarps - 1) / kWarps, kWarps * 32, 0, stream>>>(mode, logits, ld, B, A, score, label);
+  note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -139,6 +140,7 @@ int maha_finish(cudaStream_t stream, const float* q, const float* G, long long l
                 float* score, int32_t* label, float* full) {
   RGQA_CHECK(B > 0 && A > 0, "maha_finish: empty input");
   maha_finish_kernel<<<(B + kWarps - 1) / kWarps, kWarps * 32, 0, stream>>>(q, G, ldg, m, B, A, score, label, full);
+  note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -146,6 +148,7 @@ int maha_finish(cudaStream_t stream, const float* q, const float* G, long long l
 int rowdot(cudaStream_t stream, const float* a, const float* b, float* out, int M, int H) {
   RGQA_CHECK(M > 0 && H > 0, "rowdot: empty input");
   rowdot_kernel<<<(M + kWarps - 1) / kWarps, kWarps * 32, 0, stream>>>(a, b, out, M, H);
+  note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }
