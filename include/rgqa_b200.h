@@ -119,6 +119,9 @@ int rgqa_score(rgqa_handle* h, void* stream, int mode, const float* logits, cons
                float* score_out, int32_t* label_out, float* maha_full_out);
 
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------- */
+/* Kernel-selection switches for A/B measurements: "gemm_pair" (1 = CTA-pair tcgen05 kernel when
+ * M >= 1024), "gemm_staged" (1 = swizzled-smem + TMA-store epilogue in the pair kernel). */
+int rgqa_set_option(const char* name, int value);
 /* Kernels enqueued by this library since it was loaded. */
 long long rgqa_launch_count(void);
 /* When on, every GEMM / attention launch is bracketed by CUDA events on its own stream. */

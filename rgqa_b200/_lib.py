@@ -48,6 +48,7 @@ SIGNATURES = {
     "rgqa_uniter_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "rgqa_set_maha": (_i, [_vp, _vp, _vp, _i]),
     "rgqa_score": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "rgqa_set_option": (_i, [C.c_char_p, _i]),
     "rgqa_launch_count": (C.c_longlong, []),
     "rgqa_prof_enable": (None, [_i]),
     "rgqa_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -821,6 +821,19 @@ int rgqa_score(rgqa_handle* h, void* stream, int mode, const float* logits, cons
 }
 
 // ---- measurement hooks ----
+int rgqa_set_option(const char* name, int value) {
+  RGQA_CHECK(name != nullptr, "rgqa_set_option: null name");
+  if (strcmp(name, "gemm_pair") == 0) {
+    option_set(OPT_GEMM_PAIR, value);
+    return 0;
+  }
+  if (strcmp(name, "gemm_staged") == 0) {
+    option_set(OPT_GEMM_STAGED, value);
+    return 0;
+  }
+  set_error("rgqa_set_option: unknown option '%s'", name);
+  return 1;
+}
 long long rgqa_launch_count(void) { return launch_count(); }
 void rgqa_prof_enable(int on) { prof_enable(on != 0); }
 int rgqa_prof_collect(double* ms_sum, double* flops_sum, long long* count) {

@@ -138,6 +138,165 @@ attention_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__ k
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// bf16 path: the same attention on the warp-level tensor-core path (mma.sync m16n8k16, bf16 -> fp32).
+// The tiles are far too small for tcgen05 (its minimum M is 64 and one instruction is a whole-CTA
+// operation); one WARP owns one (sample, head): S = QK^T as 16-row query tiles against the K rows in
+// shared memory, the softmax on the accumulator fragments (quad shuffles), P re-used in registers as
+// the A operand of P·V, V^T fragments fetched with ldmatrix.trans.  Keys are padded to 16*KS with
+// zero rows (score -inf, probability 0); masked keys get the reference's additive -10000.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLds = 72;  // smem row stride in bf16: 144 B -> the 8 rows of a fragment load hit 32 distinct banks
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
+
+template <int KS>
+__global__ void __launch_bounds__(128)
+attention_mma_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ k,
+                     long long ldk, const __nv_bfloat16* __restrict__ v, long long ldv,
+                     const int32_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out, long long ldo, int Lq,
+                     int Lk, int heads, int items) {
+  constexpr int NT = 2 * KS;     // 8-key score tiles
+  constexpr int ROWS = 16 * KS;  // padded key count
+  extern __shared__ __align__(16) unsigned char smem_att[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int item = blockIdx.x * 4 + warp;
+  if (item >= items) return;  // warp-uniform; no block-wide barrier below
+  const int b = item / heads, h = item % heads;
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_att) + static_cast<size_t>(warp) * (2 * ROWS * kLds);
+  __nv_bfloat16* Vs = Ks + ROWS * kLds;
+
+  // stage this head's K and V rows (16 B per lane per access, rows >= Lk zero-filled)
+  for (int idx = lane; idx < ROWS * 8; idx += 32) {
+    const int r = idx >> 3, c = (idx & 7) * 8;
+    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+    if (r < Lk) {
+      kv = __ldg(reinterpret_cast<const uint4*>(k + (static_cast<long long>(b) * Lk + r) * ldk + h * HD + c));
+      vv = __ldg(reinterpret_cast<const uint4*>(v + (static_cast<long long>(b) * Lk + r) * ldv + h * HD + c));
+    }
+    *reinterpret_cast<uint4*>(Ks + r * kLds + c) = kv;
+    *reinterpret_cast<uint4*>(Vs + r * kLds + c) = vv;
+  }
+  __syncwarp();
+
+  float madd[NT][2];
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int key = 8 * j + 2 * t + e;
+      madd[j][e] = key >= Lk ? -INFINITY : ((key_mask != nullptr && key_mask[b * Lk + key] == 0) ? -10000.f : 0.f);
+    }
+
+  for (int m0 = 0; m0 < Lq; m0 += 16) {
+    const int r0 = m0 + g, r1 = r0 + 8;
+    const __nv_bfloat16* q0 = q + (static_cast<long long>(b) * Lq + r0) * ldq + h * HD;
+    const __nv_bfloat16* q1 = q + (static_cast<long long>(b) * Lq + r1) * ldq + h * HD;
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int c = ks * 16 + 2 * t;
+      qa[ks][0] = r0 < Lq ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c)) : 0u;
+      qa[ks][1] = r1 < Lq ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c)) : 0u;
+      qa[ks][2] = r0 < Lq ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c + 8)) : 0u;
+      qa[ks][3] = r1 < Lq ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c + 8)) : 0u;
+    }
+    float s[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      const __nv_bfloat16* kr = Ks + (8 * j + g) * kLds + 2 * t;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
+        mma_bf16_16816(s[j], qa[ks], b0, b1);
+      }
+    }
+    // scores / sqrt(64) + additive mask (modeling.py:333-336); row max over this row's 8*NT keys
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      s[j][0] = s[j][0] * 0.125f + madd[j][0];
+      s[j][1] = s[j][1] * 0.125f + madd[j][1];
+      s[j][2] = s[j][2] * 0.125f + madd[j][0];
+      s[j][3] = s[j][3] * 0.125f + madd[j][1];
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+    uint32_t pa[KS][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const float p0 = __expf(s[j][0] - mx0), p1 = __expf(s[j][1] - mx0);
+      const float p2 = __expf(s[j][2] - mx1), p3 = __expf(s[j][3] - mx1);
+      sum0 += p0 + p1;
+      sum1 += p2 + p3;
+      // accumulator tiles (2ks, 2ks+1) of S are exactly the A fragment of k-step ks of P·V
+      pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+
+    float o[8][4];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t vb[4];
+        const __nv_bfloat16* vrow = Vs + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kLds + dp * 16 + (lane >> 4) * 8;
+        ldmatrix_x4_trans(vb, vrow);
+        mma_bf16_16816(o[2 * dp], pa[ks], vb[0], vb[1]);
+        mma_bf16_16816(o[2 * dp + 1], pa[ks], vb[2], vb[3]);
+      }
+    }
+    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+    __nv_bfloat16* o0 = out + (static_cast<long long>(b) * Lq + r0) * ldo + h * HD + 2 * t;
+    __nv_bfloat16* o1 = out + (static_cast<long long>(b) * Lq + r1) * ldo + h * HD + 2 * t;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      if (r0 < Lq) *reinterpret_cast<uint32_t*>(o0 + 8 * d) = pack_bf16x2(o[d][0] * inv0, o[d][1] * inv0);
+      if (r1 < Lq) *reinterpret_cast<uint32_t*>(o1 + 8 * d) = pack_bf16x2(o[d][2] * inv1, o[d][3] * inv1);
+    }
+  }
+}
+
+template <int KS>
+int launch_attention_mma(cudaStream_t stream, const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* k, long long ldk,
+                         const __nv_bfloat16* v, long long ldv, const int32_t* key_mask, __nv_bfloat16* out, long long ldo,
+                         int B, int Lq, int Lk, int heads) {
+  const int items = B * heads;
+  const size_t smem = static_cast<size_t>(4) * 2 * (16 * KS) * kLds * sizeof(__nv_bfloat16);
+  static bool cfg = false;
+  if (!cfg) {
+    RGQA_CUDA_OK(cudaFuncSetAttribute(attention_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    cfg = true;
+  }
+  attention_mma_kernel<KS><<<(items + 3) / 4, 128, smem, stream>>>(q, ldq, k, ldk, v, ldv, key_mask, out, ldo, Lq, Lk, heads,
+                                                                 items);
+  return 0;
+}
+
 }  // namespace
 
 int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, const void* k, long long ldk,
@@ -151,6 +310,7 @@ int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, cons
              "attention: row strides must be multiples of 16 bytes");
   const size_t smem = static_cast<size_t>(Lk) * (2 * HD + kThreads + 1) * sizeof(float);
   const int grid = B * heads;
+  (void)smem;
   void* tok = prof_begin(stream);
   if (dtype == DT_F32) {
     static bool cfg = false;
@@ -162,15 +322,18 @@ int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, cons
         static_cast<const float*>(q), ldq, static_cast<const float*>(k), ldk, static_cast<const float*>(v), ldv,
         key_mask, static_cast<float*>(out), ldo, Lq, Lk, heads);
   } else {
-    static bool cfg = false;
-    if (!cfg) {
-      RGQA_CUDA_OK(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        64 * 1024));
-      cfg = true;
+    const __nv_bfloat16* qb = static_cast<const __nv_bfloat16*>(q);
+    const __nv_bfloat16* kb = static_cast<const __nv_bfloat16*>(k);
+    const __nv_bfloat16* vb = static_cast<const __nv_bfloat16*>(v);
+    __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
+    int rc = 0;
+    switch ((Lk + 15) / 16) {
+      case 1: rc = launch_attention_mma<1>(stream, qb, ldq, kb, ldk, vb, ldv, key_mask, ob, ldo, B, Lq, Lk, heads); break;
+      case 2: rc = launch_attention_mma<2>(stream, qb, ldq, kb, ldk, vb, ldv, key_mask, ob, ldo, B, Lq, Lk, heads); break;
+      case 3: rc = launch_attention_mma<3>(stream, qb, ldq, kb, ldk, vb, ldv, key_mask, ob, ldo, B, Lq, Lk, heads); break;
+      default: rc = launch_attention_mma<4>(stream, qb, ldq, kb, ldk, vb, ldv, key_mask, ob, ldo, B, Lq, Lk, heads); break;
     }
-    attention_kernel<__nv_bfloat16><<<grid, kThreads, smem, stream>>>(
-        static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), ldk,
-        static_cast<const __nv_bfloat16*>(v), ldv, key_mask, static_cast<__nv_bfloat16*>(out), ldo, Lq, Lk, heads);
+    if (rc) return 1;
   }
   prof_end(tok, stream, 4.0 * B * static_cast<double>(Lq) * Lk * heads * HD, PROF_ATTENTION);
   note_launch();

@@ -2,20 +2,28 @@
 //
 //   out[M,N] = epilogue( A[M,K] (bf16, row stride lda) · W[N,K]ᵀ (bf16, nn.Linear layout) + bias[N] )
 //
-// This one kernel carries every nn.Linear of the LXMERT / UNITER forward in the bf16 path
+// This file carries every nn.Linear of the LXMERT / UNITER forward in the bf16 path
 // (reference call sites: src/lxrt/modeling.py:321-323 Q/K/V, :358 and :412 output dense,
 // :399 intermediate dense, :578 pooler, src/tasks/gqa_model.py:22-27 answer head).
 //
-// Structure (persistent, warp-specialised, one CTA per SM):
-//   warp 0      TMA producer   global -> 128B-swizzled smem ring (kStages deep), mbarrier tx-count
-//   warp 1      MMA issuer     one lane issues tcgen05.mma (128 x BN x 16), accumulators in TMEM
-//   warp 2      TMEM allocator (2 x BN fp32 columns: double-buffered accumulator)
-//   warps 4-11  epilogue       tcgen05.ld 32x32b -> registers, fused bias / erf-GELU / tanh / fp32 residual,
-//                              bf16 or fp32 store; overlaps the next tile's main loop
-// Tails: TMA zero-fills out-of-bounds rows of A (M tail) and W (N tail); stores are predicated.
+// Two persistent, warp-specialised kernels share one structure:
+//   warp 0      TMA producer   global -> 128B-swizzled smem ring, mbarrier tx-count
+//   warp 1      MMA issuer     one lane issues tcgen05.mma, accumulators in TMEM (2 x 256 fp32 columns:
+//                              double buffered, so the epilogue of tile i overlaps the main loop of tile i+1)
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue       tcgen05.ld 32x32b -> registers (one accumulator ROW per thread), fused bias /
+//                              erf-GELU / tanh / fp32 residual, then either
+//                                staged : 16-byte st.shared into a 128B-swizzled slab + TMA bulk store
+//                                         (full-line writes; the TMA clips the M and N tails), or
+//                                direct : predicated global stores (tiny or unaligned outputs)
+//   * gemm_bf16_tcgen05_kernel  one CTA per tile (128 x BN), for small M
+//   * gemm_bf16_pair_kernel     a CTA PAIR (cta_group::2) per 256 x 256 tile: each CTA stages its own 128 rows of
+//                               A and only half of the W tile, the leader issues one 256-row MMA for both SMs
+// Tails: TMA zero-fills out-of-bounds rows of A (M tail) and W (N tail).
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -29,6 +37,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int kNumEpiWarps = 8;
 constexpr int kNumThreads = (4 + kNumEpiWarps) * 32;
+constexpr int kSlabBytes = 128 * 128;  // staged epilogue: 128 rows x 128 B, 128B-swizzled, one TMA store box
 
 template <int BN>
 struct Cfg {
@@ -43,12 +52,12 @@ struct Cfg {
 
 struct GemmParams {
   int M, N, K;
-  const float* bias;           // [N] fp32 or nullptr
-  const float* resid;          // [M, ldr] fp32 residual stream (EPI_RESID) or nullptr
+  const float* bias;   // [N] fp32 or nullptr
+  const float* resid;  // [M, ldr] fp32 residual stream (EPI_RESID) or nullptr
   long long ldr;
   void* out;
   long long ldo;
-  int vec_ok;  // rows of out (and resid) are 16-byte aligned -> vector stores allowed
+  int vec_ok;  // direct path: rows of out (and resid) are 16-byte aligned -> vector stores allowed
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -80,6 +89,121 @@ __device__ __forceinline__ float apply_act(float v) {
   return v;
 }
 
+// acc + bias (+ fp32 residual) -> activation, for one 32-column chunk of one accumulator row
+template <int EPI>
+__device__ __forceinline__ void epilogue_math(const uint32_t (&v)[32], float (&f)[32], int row, bool row_ok, int col0,
+                                              const GemmParams& p, bool aligned) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  if (col0 + 32 <= p.N && aligned) {
+    if (p.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(b4 + i);
+        f[4 * i + 0] += b.x;
+        f[4 * i + 1] += b.y;
+        f[4 * i + 2] += b.z;
+        f[4 * i + 3] += b.w;
+      }
+    }
+    if constexpr (EPI == EPI_RESID) {
+      if (row_ok) {
+        const float4* r4 = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * p.ldr + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 r = __ldg(r4 + i);
+          f[4 * i + 0] += r.x;
+          f[4 * i + 1] += r.y;
+          f[4 * i + 2] += r.z;
+          f[4 * i + 3] += r.w;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int col = col0 + i;
+      if (col < p.N) {
+        if (p.bias != nullptr) f[i] += __ldg(p.bias + col);
+        if constexpr (EPI == EPI_RESID) {
+          if (row_ok) f[i] += p.resid[static_cast<long long>(row) * p.ldr + col];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = apply_act<EPI>(f[i]);
+}
+
+// direct path: one 32-column chunk straight to global memory (vector stores when aligned, else scalar, guarded)
+template <int EPI, typename OutT>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row, bool row_ok, int col0,
+                                               const GemmParams& p) {
+  float f[32];
+  epilogue_math<EPI>(v, f, row, row_ok, col0, p, p.vec_ok != 0);
+  if (!row_ok) return;
+  if (col0 + 32 <= p.N && p.vec_ok) {
+    if constexpr (sizeof(OutT) == 2) {
+      uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 o;
+        o.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
+        o.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+        o.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
+        o.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+        o4[i] = o;
+      }
+    } else {
+      float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int col = col0 + i;
+      if (col < p.N) {
+        if constexpr (sizeof(OutT) == 2)
+          reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<long long>(row) * p.ldo + col] = __float2bfloat16_rn(f[i]);
+        else
+          reinterpret_cast<float*>(p.out)[static_cast<long long>(row) * p.ldo + col] = f[i];
+      }
+    }
+  }
+}
+
+// staged path: the chunk goes into the 128B-swizzled slab (row r_local, 16-byte piece j at physical piece
+// j ^ (r_local & 7)) that a TMA bulk store then writes out as full lines
+template <typename OutT>
+__device__ __forceinline__ void store_chunk_swizzled(uint8_t* slab, int r_local, int chunk_in_slab, const float (&f)[32]) {
+  uint8_t* rowp = slab + r_local * 128;
+  const int sw = r_local & 7;
+  if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 o;
+      o.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
+      o.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+      o.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
+      o.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+      *reinterpret_cast<uint4*>(rowp + (((chunk_in_slab * 4 + i) ^ sw) << 4)) = o;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float4*>(rowp + ((i ^ sw) << 4)) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-CTA kernel (small M): 128 x BN tiles, direct epilogue
+// ------------------------------------------------------------------------------------------------
 template <int BN, int EPI, typename OutT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -184,8 +308,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
     const int e = warp - 4;
-    const int quarter = e & 3;        // == warp % 4: the TMEM lane quarter this warp may touch
-    const int half = e >> 2;          // column half of the tile
+    const int quarter = e & 3;  // == warp % 4: the TMEM lane quarter this warp may touch
+    const int half = e >> 2;    // column half of the tile
     constexpr int kColsPerWarp = BN / 2;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -206,74 +330,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint32_t v[32];
         tmem_ld32(t_row + static_cast<uint32_t>(c), v);
         tmem_ld_wait_dep(v);
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        const bool full_chunk = (col0 + 32 <= p.N);
-        if (full_chunk && p.vec_ok) {
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(b4 + i);
-              f[4 * i + 0] += b.x;
-              f[4 * i + 1] += b.y;
-              f[4 * i + 2] += b.z;
-              f[4 * i + 3] += b.w;
-            }
-          }
-          if constexpr (EPI == EPI_RESID) {
-            if (row_ok) {
-              const float4* r4 = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * p.ldr + col0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 r = __ldg(r4 + i);
-                f[4 * i + 0] += r.x;
-                f[4 * i + 1] += r.y;
-                f[4 * i + 2] += r.z;
-                f[4 * i + 3] += r.w;
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = apply_act<EPI>(f[i]);
-          if (row_ok) {
-            if constexpr (sizeof(OutT) == 2) {
-              uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                                   static_cast<long long>(row) * p.ldo + col0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 o;
-                o.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
-                o.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
-                o.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
-                o.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
-                o4[i] = o;
-              }
-            } else {
-              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
-                                                     static_cast<long long>(row) * p.ldo + col0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-            }
-          }
-        } else {
-          // ragged tail (N % 32 != 0 or unaligned rows): scalar, fully guarded
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int col = col0 + i;
-            if (row_ok && col < p.N) {
-              float x = f[i];
-              if (p.bias != nullptr) x += __ldg(p.bias + col);
-              if constexpr (EPI == EPI_RESID) x += p.resid[static_cast<long long>(row) * p.ldr + col];
-              x = apply_act<EPI>(x);
-              if constexpr (sizeof(OutT) == 2)
-                reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<long long>(row) * p.ldo + col] = __float2bfloat16_rn(x);
-              else
-                reinterpret_cast<float*>(p.out)[static_cast<long long>(row) * p.ldo + col] = x;
-            }
-          }
-        }
+        epilogue_chunk<EPI, OutT>(v, row, row_ok, col0, p);
       }
       // all TMEM reads of this accumulator buffer are complete (wait::ld above): hand it back
       tc_fence_before();
@@ -285,6 +342,210 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): two SMs of a TPC form a cluster and issue ONE 256 x 256 x 16 MMA per
+// step.  Each CTA stages its own 128 rows of A and only HALF of the W tile (128 of the 256 N rows); the
+// pair's tensor cores read both halves, so a CTA pulls 32 KB per k-block instead of 48 KB.
+//   leader (cluster rank 0): arms the full barriers for BOTH CTAs' bytes, issues every MMA, multicasts the
+//                            tcgen05.commit arrivals (smem-slot release, accumulator ready) to both CTAs
+//   both CTAs             : TMA producer (credits the leader's barrier), 8 epilogue warps on their own
+//                            128 TMEM lanes; accumulator hand-back arrives on the leader's barrier.
+// STAGED epilogue: the 4 warps that share a column half fill a [128 rows x 128 B] swizzled slab (64 bf16 or
+// 32 fp32 columns), one of them issues the TMA bulk store; two slabs per half alternate.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairBN = 256;
+constexpr int kPairStageBytes = BM * BK * 2 + (kPairBN / 2) * BK * 2;  // 16 KB A + 16 KB half of W
+template <bool STAGED>
+struct PairCfg {
+  static constexpr int kStages = STAGED ? 5 : 6;
+  static constexpr int kSlabRegion = STAGED ? 4 * kSlabBytes : 0;  // 2 halves x 2 buffers
+  static constexpr int kSmemBytes = kStages * kPairStageBytes + kSlabRegion + 1024 + 256;
+};
+
+template <int EPI, typename OutT, bool STAGED>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmOut, const GemmParams p) {
+  using PC = PairCfg<STAGED>;
+  constexpr int kStages = PC::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* slabs = smem + kStages * kPairStageBytes;  // 1024-aligned: stage size is a multiple of 1024
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slabs + PC::kSlabRegion);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  const int tiles_n = (p.N + kPairBN - 1) / kPairBN;
+  const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if constexpr (STAGED) tma_prefetch_desc(&tmOut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader's producer: arrive.expect_tx for both CTAs' bytes
+      mbar_init(&empty_bar[s], 1);  // one multicast commit arrival per use
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 2 * kNumEpiWarps);  // epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair<512>(tmem_ptr_smem);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int m0 = (t / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = (t % tiles_n) * kPairBN + static_cast<int>(rank) * (kPairBN / 2);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (lane == 0) {
+          uint8_t* sa = smem + stage * kPairStageBytes;
+          uint8_t* sb = sa + BM * BK * 2;
+          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
+          tma_load_2d_pair(sa, &tmA, leader_full, kb * BK, m0);
+          tma_load_2d_pair(sb, &tmB, leader_full, kb * BK, n0);
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, kPairBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kPairBN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * kPairStageBytes);
+            const uint64_t adesc = umma_smem_desc_sw128(sa);
+            const uint64_t bdesc = umma_smem_desc_sw128(sa + BM * BK * 2);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit_pair(&tmem_full_bar[acc]);
+          }
+          __syncwarp();
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
+    const int e = warp - 4;
+    const int quarter = e & 3;
+    const int half = e >> 2;
+    constexpr int kColsPerWarp = kPairBN / 2;
+    const uint32_t leader_tmem_empty0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
+    const uint32_t leader_tmem_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
+    [[maybe_unused]] const bool issuer = (quarter == 0 && lane == 0);
+    [[maybe_unused]] int slab_ctr = 0;
+    int it = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int m0 = (t / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = (t % tiles_n) * kPairBN;
+      const int r_local = quarter * 32 + lane;
+      const int row = m0 + r_local;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             static_cast<uint32_t>(acc * kPairBN + half * kColsPerWarp);
+      if constexpr (STAGED) {
+        constexpr int kColsPerSlab = 128 / static_cast<int>(sizeof(OutT));  // 64 bf16 / 32 fp32
+        constexpr int kChunksPerSlab = kColsPerSlab / 32;
+        constexpr int kSlabsPerHalf = kColsPerWarp / kColsPerSlab;
+        const bool tile_rows_live = m0 < p.M;  // a fully out-of-range row block stores nothing (TMA would clip anyway)
+#pragma unroll 1
+        for (int sl = 0; sl < kSlabsPerHalf; ++sl) {
+          const int col_slab = n0 + half * kColsPerWarp + sl * kColsPerSlab;
+          if (col_slab >= p.N) break;  // uniform over the 4 warps of this half
+          uint8_t* buf = slabs + (half * 2 + (slab_ctr & 1)) * kSlabBytes;
+          if (issuer) tma_store_wait_read<1>();  // the store that last read this buffer (2 slabs ago) is done with it
+          named_bar_sync(1 + half, 128);
+#pragma unroll
+          for (int cc = 0; cc < kChunksPerSlab; ++cc) {
+            uint32_t v[32];
+            tmem_ld32(t_row + static_cast<uint32_t>(sl * kColsPerSlab + cc * 32), v);
+            tmem_ld_wait_dep(v);
+            float f[32];
+            epilogue_math<EPI>(v, f, row, row_ok, col_slab + cc * 32, p, true);
+            store_chunk_swizzled<OutT>(buf, r_local, cc, f);
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          named_bar_sync(1 + half, 128);
+          if (issuer && tile_rows_live) {
+            tma_store_2d(&tmOut, buf, col_slab, m0);
+            tma_store_commit();
+          }
+          ++slab_ctr;
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < kColsPerWarp; c += 32) {
+          const int col0 = n0 + half * kColsPerWarp + c;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(t_row + static_cast<uint32_t>(c), v);
+          tmem_ld_wait_dep(v);
+          epilogue_chunk<EPI, OutT>(v, row, row_ok, col0, p);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc == 0 ? leader_tmem_empty0 : leader_tmem_empty1);
+    }
+    if constexpr (STAGED) {
+      if (issuer) tma_store_wait<0>();  // smem must outlive every bulk store that reads it
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -307,20 +568,20 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map over a row-major [rows, cols] matrix with row stride ld (elements);
-// box = [box_rows, 64 cols], 128-byte swizzle, out-of-bounds elements read as zero.
-int make_tmap_bf16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+// 2-D tensor map over a row-major [rows, cols] matrix with row stride ld (elements); box = [box_rows, 128 B of
+// columns], 128-byte swizzle, out-of-bounds elements read as zero / are not written.
+int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows, int elem_bytes) {
   EncodeTiledFn enc = get_encode_fn();
   RGQA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
   RGQA_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "TMA operand must be 16-byte aligned");
-  RGQA_CHECK((ld * 2) % 16 == 0, "TMA operand row stride must be a multiple of 16 bytes (ld=%lld)", ld);
+  RGQA_CHECK((ld * elem_bytes) % 16 == 0, "TMA operand row stride must be a multiple of 16 bytes (ld=%lld)", ld);
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estride[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estride,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RGQA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
   return 0;
 }
@@ -373,6 +634,54 @@ int dispatch_epi(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, con
   }
 }
 
+template <int EPI, typename OutT, bool STAGED>
+int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                const GemmParams& p) {
+  auto kern = gemm_bf16_pair_kernel<EPI, OutT, STAGED>;
+  constexpr int smem = PairCfg<STAGED>::kSmemBytes;
+  static bool configured = false;
+  if (!configured) {
+    RGQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + kPairBN - 1) / kPairBN);
+  const int max_pairs = num_sms() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  void* tok = prof_begin(stream);
+  kern<<<2 * pairs, kNumThreads, smem, stream>>>(tmA, tmB, tmOut, p);
+  prof_end(tok, stream, 2.0 * p.M * static_cast<double>(p.N) * p.K, PROF_GEMM_TC);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int EPI, typename OutT>
+int launch_pair_sel(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const GemmParams& p,
+                    bool staged) {
+  return staged ? launch_pair<EPI, OutT, true>(s, a, b, o, p) : launch_pair<EPI, OutT, false>(s, a, b, o, p);
+}
+
+int dispatch_pair(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const GemmParams& p,
+                  int epi, int out_f32, bool staged) {
+  switch (epi) {
+    case EPI_BIAS:
+      return out_f32 ? launch_pair_sel<EPI_BIAS, float>(s, a, b, o, p, staged)
+                     : launch_pair_sel<EPI_BIAS, __nv_bfloat16>(s, a, b, o, p, staged);
+    case EPI_GELU:
+      return out_f32 ? launch_pair_sel<EPI_GELU, float>(s, a, b, o, p, staged)
+                     : launch_pair_sel<EPI_GELU, __nv_bfloat16>(s, a, b, o, p, staged);
+    case EPI_TANH:
+      return out_f32 ? launch_pair_sel<EPI_TANH, float>(s, a, b, o, p, staged)
+                     : launch_pair_sel<EPI_TANH, __nv_bfloat16>(s, a, b, o, p, staged);
+    case EPI_RESID:
+      return out_f32 ? launch_pair_sel<EPI_RESID, float>(s, a, b, o, p, staged)
+                     : launch_pair_sel<EPI_RESID, __nv_bfloat16>(s, a, b, o, p, staged);
+    default:
+      set_error("gemm_bf16: unknown epilogue %d", epi);
+      return 1;
+  }
+}
+
 }  // namespace
 
 int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
@@ -382,9 +691,21 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
   RGQA_CHECK(epi != EPI_RESID || resid != nullptr, "gemm_bf16: EPI_RESID needs a residual pointer");
   // Tile width: 256 when it does not waste more than a quarter of the last N tile, else 128.
   const int bn = (N % 256 == 0 || N >= 1024) ? 256 : 128;
-  CUtensorMap tmA, tmB;
-  if (make_tmap_bf16(&tmA, A, M, K, lda, BM)) return 1;
-  if (make_tmap_bf16(&tmB, W, N, K, ldw, bn)) return 1;
+  // CTA pairs (256-row MMA, half the W traffic per CTA) once there are enough 256-row tiles to go round
+  const bool use_pair = option_get(OPT_GEMM_PAIR) != 0 && bn == 256 && M >= 1024;
+  const int esz = out_f32 ? 4 : 2;
+  const bool out_al = (reinterpret_cast<uintptr_t>(out) % 16 == 0) && ((ldo * esz) % 16 == 0);
+  const bool res_al = (resid == nullptr) || ((reinterpret_cast<uintptr_t>(resid) % 16 == 0) && ((ldr * 4) % 16 == 0));
+  const bool bias_al = (bias == nullptr) || (reinterpret_cast<uintptr_t>(bias) % 16 == 0);
+  const bool staged = use_pair && option_get(OPT_GEMM_STAGED) != 0 && out_al && res_al && bias_al;
+  CUtensorMap tmA, tmB, tmOut;
+  if (make_tmap(&tmA, A, M, K, lda, BM, 2)) return 1;
+  if (make_tmap(&tmB, W, N, K, ldw, use_pair ? kPairBN / 2 : bn, 2)) return 1;
+  if (staged) {
+    if (make_tmap(&tmOut, out, M, N, ldo, BM, esz)) return 1;
+  } else {
+    tmOut = tmA;  // unused by the direct epilogue
+  }
   GemmParams p;
   p.M = M;
   p.N = N;
@@ -394,11 +715,8 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
   p.ldr = ldr;
   p.out = out;
   p.ldo = ldo;
-  const int esz = out_f32 ? 4 : 2;
-  const bool out_al = (reinterpret_cast<uintptr_t>(out) % 16 == 0) && ((ldo * esz) % 16 == 0);
-  const bool res_al = (resid == nullptr) || ((reinterpret_cast<uintptr_t>(resid) % 16 == 0) && ((ldr * 4) % 16 == 0));
-  const bool bias_al = (bias == nullptr) || (reinterpret_cast<uintptr_t>(bias) % 16 == 0);
   p.vec_ok = (out_al && res_al && bias_al) ? 1 : 0;
+  if (use_pair) return dispatch_pair(stream, tmA, tmB, tmOut, p, epi, out_f32, staged);
   return bn == 256 ? dispatch_epi<256>(stream, tmA, tmB, p, epi, out_f32)
                    : dispatch_epi<128>(stream, tmA, tmB, p, epi, out_f32);
 }

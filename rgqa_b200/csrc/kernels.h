@@ -75,6 +75,11 @@ int maha_finish(cudaStream_t stream, const float* q, const float* G, long long l
 int rowdot(cudaStream_t stream, const float* a, const float* b, float* out, int M, int H);
 
 
+// ---- runtime options (prof.cu): kernel-selection switches for A/B measurements ---------------------
+enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_COUNT = 8 };
+int option_get(int key);
+void option_set(int key, int value);
+
 // ---- measurement hooks (prof.cu) ----------------------------------------------------------------
 void note_launch(int n = 1);
 long long launch_count();

@@ -31,6 +31,14 @@ cudaEvent_t get_event() {
 }
 }  // namespace
 
+namespace {
+int g_options[OPT_COUNT] = {/*OPT_GEMM_PAIR*/ 1, /*OPT_GEMM_STAGED*/ 1, 0, 0, 0, 0, 0, 0};
+}
+int option_get(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
+void option_set(int key, int value) {
+  if (key >= 0 && key < OPT_COUNT) g_options[key] = value;
+}
+
 void note_launch(int n) { g_launches += n; }
 long long launch_count() { return g_launches; }
 void prof_enable(bool on) { g_on = on; }

@@ -30,6 +30,11 @@ GEMM_CASES = [
     (32, 1842, 1536, "bias", torch.float32, 0),       # logit_fc.3: ragged N, unaligned rows
     (5000, 2304, 768, "bias", torch.bfloat16, 0),     # > 148 tiles: persistent loop, both TMEM buffers
     (1152, 768, 2048, "bias", torch.float32, 0),      # visn_fc
+    # CTA-pair kernel (M >= 1024): 256-row tiles, ragged M and N, every epilogue
+    (1100, 1842, 1536, "bias", torch.float32, 0),
+    (1024, 3072, 768, "gelu", torch.bfloat16, 0),
+    (20480, 768, 3072, "resid", torch.float32, 0),    # FFN2 at B = 1024: 240 tiles over 74 pairs
+    (4097, 768, 768, "tanh", torch.float32, 0),
 ]
 
 
