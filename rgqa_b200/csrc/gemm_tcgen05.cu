@@ -357,18 +357,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 // ------------------------------------------------------------------------------------------------
 constexpr int kPairBN = 256;
 constexpr int kPairStageBytes = BM * BK * 2 + (kPairBN / 2) * BK * 2;  // 16 KB A + 16 KB half of W
-template <bool STAGED>
+// RESID_SMEM (staged EPI_RESID with fp32 output): the residual slab is TMA-LOADED into the very buffer the
+// output is staged in — each thread reads its own row of it, adds, and writes the sum back in place — so both
+// the residual read and the pre-LayerNorm write are full-line bulk copies; 3 buffers per half, 2-deep prefetch.
+template <bool STAGED, bool RESID_SMEM>
 struct PairCfg {
-  static constexpr int kStages = STAGED ? 5 : 6;
-  static constexpr int kSlabRegion = STAGED ? 4 * kSlabBytes : 0;  // 2 halves x 2 buffers
+  static constexpr int kStages = RESID_SMEM ? 4 : (STAGED ? 5 : 6);
+  static constexpr int kBufsPerHalf = RESID_SMEM ? 3 : (STAGED ? 2 : 0);
+  static constexpr int kSlabRegion = 2 * kBufsPerHalf * kSlabBytes;
   static constexpr int kSmemBytes = kStages * kPairStageBytes + kSlabRegion + 1024 + 256;
 };
 
 template <int EPI, typename OutT, bool STAGED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const __grid_constant__ CUtensorMap tmOut, const GemmParams p) {
-  using PC = PairCfg<STAGED>;
+                      const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+                      const GemmParams p) {
+  constexpr bool kResidSmem = STAGED && EPI == EPI_RESID && sizeof(OutT) == 4;
+  using PC = PairCfg<STAGED, kResidSmem>;
   constexpr int kStages = PC::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -378,7 +384,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* resid_bar = tmem_empty_bar + 2;  // [2 halves][3 buffers], used by the RESID_SMEM epilogue only
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(resid_bar + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -395,6 +402,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if constexpr (STAGED) tma_prefetch_desc(&tmOut);
+    if constexpr (kResidSmem) tma_prefetch_desc(&tmRes);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -405,6 +413,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 2 * kNumEpiWarps);  // epilogue warps of both CTAs
     }
+    for (int i = 0; i < 6; ++i) mbar_init(&resid_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<512>(tmem_ptr_smem);
@@ -481,6 +490,80 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t leader_tmem_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
     [[maybe_unused]] const bool issuer = (quarter == 0 && lane == 0);
     [[maybe_unused]] int slab_ctr = 0;
+    if constexpr (kResidSmem) {
+      // flat sequence of (tile, 32-column slab) for this column half; 4 slabs per tile
+      const int my_tiles = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
+      const int total = my_tiles * 4;
+      const int r_local = quarter * 32 + lane;
+      auto coords = [&](int k, int& row0, int& col) {
+        const int t = pair + (k >> 2) * num_pairs;
+        row0 = (t / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        col = (t % tiles_n) * kPairBN + half * kColsPerWarp + (k & 3) * 32;
+      };
+      auto issue_load = [&](int k) {
+        int row0, col;
+        coords(k, row0, col);
+        const int b = k % 3;
+        mbar_expect_tx(&resid_bar[half * 3 + b], kSlabBytes);
+        tma_load_2d(slabs + (half * 3 + b) * kSlabBytes, &tmRes, &resid_bar[half * 3 + b], col, row0);
+      };
+      if (issuer) {
+        if (total > 0) issue_load(0);
+        if (total > 1) issue_load(1);
+      }
+      for (int k = 0; k < total; ++k) {
+        const int itile = k >> 2, sl = k & 3;
+        const int acc = itile & 1;
+        int row0, col;
+        coords(k, row0, col);
+        const int row = row0 + r_local;
+        if (sl == 0) {
+          mbar_wait(&tmem_full_bar[acc], (itile >> 1) & 1u);
+          tc_fence_after();
+        }
+        const int b = k % 3;
+        uint8_t* buf = slabs + (half * 3 + b) * kSlabBytes;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                      static_cast<uint32_t>(acc * kPairBN + half * kColsPerWarp + sl * 32), v);
+        mbar_wait(&resid_bar[half * 3 + b], (k / 3) & 1u);  // this slab's residual rows have landed
+        tmem_ld_wait_dep(v);
+        float f[32];
+        {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+          const uint8_t* rowp = buf + r_local * 128;
+          const int sw = r_local & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr) bb = __ldg(b4 + i);
+            const float4 rr = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 4));
+            f[4 * i + 0] = (__uint_as_float(v[4 * i + 0]) + bb.x) + rr.x;
+            f[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) + bb.y) + rr.y;
+            f[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + bb.z) + rr.z;
+            f[4 * i + 3] = (__uint_as_float(v[4 * i + 3]) + bb.w) + rr.w;
+          }
+        }
+        store_chunk_swizzled<float>(buf, r_local, 0, f);  // in place: this thread's own row
+        (void)row;
+        if (sl == 3) {  // the tile's four chunks are in registers / smem: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc == 0 ? leader_tmem_empty0 : leader_tmem_empty1);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + half, 128);
+        if (issuer) {
+          if (row0 < p.M) tma_store_2d(&tmOut, buf, col, row0);
+          tma_store_commit();
+          if (k + 2 < total) {
+            tma_store_wait_read<1>();  // the store of slab k-1 has drained the buffer slab k+2 will land in
+            issue_load(k + 2);
+          }
+        }
+      }
+      if (issuer) tma_store_wait<0>();
+    } else {
     int it = 0;
     for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
       const int acc = it & 1;
@@ -541,6 +624,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if constexpr (STAGED) {
       if (issuer) tma_store_wait<0>();  // smem must outlive every bulk store that reads it
     }
+    }  // !kResidSmem
   }
 
   tc_fence_before();
@@ -636,9 +720,9 @@ int dispatch_epi(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, con
 
 template <int EPI, typename OutT, bool STAGED>
 int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                const GemmParams& p) {
+                const CUtensorMap& tmRes, const GemmParams& p) {
   auto kern = gemm_bf16_pair_kernel<EPI, OutT, STAGED>;
-  constexpr int smem = PairCfg<STAGED>::kSmemBytes;
+  constexpr int smem = PairCfg<STAGED, (STAGED && EPI == EPI_RESID && sizeof(OutT) == 4)>::kSmemBytes;
   static bool configured = false;
   if (!configured) {
     RGQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -648,7 +732,7 @@ int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& 
   const int max_pairs = num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   void* tok = prof_begin(stream);
-  kern<<<2 * pairs, kNumThreads, smem, stream>>>(tmA, tmB, tmOut, p);
+  kern<<<2 * pairs, kNumThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, p);
   prof_end(tok, stream, 2.0 * p.M * static_cast<double>(p.N) * p.K, PROF_GEMM_TC);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
@@ -656,26 +740,26 @@ int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& 
 }
 
 template <int EPI, typename OutT>
-int launch_pair_sel(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const GemmParams& p,
-                    bool staged) {
-  return staged ? launch_pair<EPI, OutT, true>(s, a, b, o, p) : launch_pair<EPI, OutT, false>(s, a, b, o, p);
+int launch_pair_sel(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& r,
+                    const GemmParams& p, bool staged) {
+  return staged ? launch_pair<EPI, OutT, true>(s, a, b, o, r, p) : launch_pair<EPI, OutT, false>(s, a, b, o, r, p);
 }
 
-int dispatch_pair(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const GemmParams& p,
-                  int epi, int out_f32, bool staged) {
+int dispatch_pair(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& r,
+                  const GemmParams& p, int epi, int out_f32, bool staged) {
   switch (epi) {
     case EPI_BIAS:
-      return out_f32 ? launch_pair_sel<EPI_BIAS, float>(s, a, b, o, p, staged)
-                     : launch_pair_sel<EPI_BIAS, __nv_bfloat16>(s, a, b, o, p, staged);
+      return out_f32 ? launch_pair_sel<EPI_BIAS, float>(s, a, b, o, r, p, staged)
+                     : launch_pair_sel<EPI_BIAS, __nv_bfloat16>(s, a, b, o, r, p, staged);
     case EPI_GELU:
-      return out_f32 ? launch_pair_sel<EPI_GELU, float>(s, a, b, o, p, staged)
-                     : launch_pair_sel<EPI_GELU, __nv_bfloat16>(s, a, b, o, p, staged);
+      return out_f32 ? launch_pair_sel<EPI_GELU, float>(s, a, b, o, r, p, staged)
+                     : launch_pair_sel<EPI_GELU, __nv_bfloat16>(s, a, b, o, r, p, staged);
     case EPI_TANH:
-      return out_f32 ? launch_pair_sel<EPI_TANH, float>(s, a, b, o, p, staged)
-                     : launch_pair_sel<EPI_TANH, __nv_bfloat16>(s, a, b, o, p, staged);
+      return out_f32 ? launch_pair_sel<EPI_TANH, float>(s, a, b, o, r, p, staged)
+                     : launch_pair_sel<EPI_TANH, __nv_bfloat16>(s, a, b, o, r, p, staged);
     case EPI_RESID:
-      return out_f32 ? launch_pair_sel<EPI_RESID, float>(s, a, b, o, p, staged)
-                     : launch_pair_sel<EPI_RESID, __nv_bfloat16>(s, a, b, o, p, staged);
+      return out_f32 ? launch_pair_sel<EPI_RESID, float>(s, a, b, o, r, p, staged)
+                     : launch_pair_sel<EPI_RESID, __nv_bfloat16>(s, a, b, o, r, p, staged);
     default:
       set_error("gemm_bf16: unknown epilogue %d", epi);
       return 1;
@@ -697,14 +781,21 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
   const bool out_al = (reinterpret_cast<uintptr_t>(out) % 16 == 0) && ((ldo * esz) % 16 == 0);
   const bool res_al = (resid == nullptr) || ((reinterpret_cast<uintptr_t>(resid) % 16 == 0) && ((ldr * 4) % 16 == 0));
   const bool bias_al = (bias == nullptr) || (reinterpret_cast<uintptr_t>(bias) % 16 == 0);
-  const bool staged = use_pair && option_get(OPT_GEMM_STAGED) != 0 && out_al && res_al && bias_al;
-  CUtensorMap tmA, tmB, tmOut;
+  bool staged = use_pair && option_get(OPT_GEMM_STAGED) != 0 && out_al && res_al && bias_al;
+  // the in-smem residual variant walks whole 128-column halves: ragged N falls back to the direct epilogue
+  if (staged && epi == EPI_RESID && out_f32 && (N % 128 != 0)) staged = false;
+  CUtensorMap tmA, tmB, tmOut, tmRes;
   if (make_tmap(&tmA, A, M, K, lda, BM, 2)) return 1;
   if (make_tmap(&tmB, W, N, K, ldw, use_pair ? kPairBN / 2 : bn, 2)) return 1;
   if (staged) {
     if (make_tmap(&tmOut, out, M, N, ldo, BM, esz)) return 1;
   } else {
     tmOut = tmA;  // unused by the direct epilogue
+  }
+  if (staged && epi == EPI_RESID && out_f32) {
+    if (make_tmap(&tmRes, resid, M, N, ldr, BM, 4)) return 1;
+  } else {
+    tmRes = tmA;  // unused
   }
   GemmParams p;
   p.M = M;
@@ -716,7 +807,7 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
   p.out = out;
   p.ldo = ldo;
   p.vec_ok = (out_al && res_al && bias_al) ? 1 : 0;
-  if (use_pair) return dispatch_pair(stream, tmA, tmB, tmOut, p, epi, out_f32, staged);
+  if (use_pair) return dispatch_pair(stream, tmA, tmB, tmOut, tmRes, p, epi, out_f32, staged);
   return bn == 256 ? dispatch_epi<256>(stream, tmA, tmB, p, epi, out_f32)
                    : dispatch_epi<128>(stream, tmA, tmB, p, epi, out_f32);
 }
