@@ -1,0 +1,96 @@
+"""Evaluation driver with the reference's command line (``src/tasks/gqa_conf.py:384-453`` test branch, and the
+energy / Mahalanobis variants ``gqa_energy.py``, ``gqa_maha.py`` selected with ``--method``):
+
+    python -m rgqa_b200.tasks.gqa_conf --test ClipEasy --load snap/gqa/x/BEST --batchSize 1024 --method msp \
+        --output snap/out [--precision bf16] [--syntheticN 11158]
+    torchrun --nproc-per-node 8 -m rgqa_b200.tasks.gqa_conf ...        # batch-sharded sweep, one all-gather
+
+Writes ``<output>/<test>_predict.json`` and ``<output>/<test>_result.json`` like the reference (:406-415).
+No RGQA data, features or checkpoints exist offline: without ``--load`` the weights are the seeded random init
+and the data set is ``SyntheticRGQA`` (seeded features / questions / labels)."""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+from ..param import get_parser
+from .gqa_data import dump_results_json
+from .gqa_eval import GQAEval, SyntheticRGQA, shard_range
+from .gqa_model import GQAModel_maha
+
+
+class GQA:
+    def __init__(self, args):
+        self.args = args
+        if args.backbone == "uniter":
+            from ..uniter.uniter import GQAUNITER_maha
+            self.model = GQAUNITER_maha(1842, args=args)
+        elif args.backbone == "lxmert":
+            self.model = GQAModel_maha(1842, args=args, max_seq_length=args.max_seq_length)
+        else:
+            raise ValueError("Backbone is not defined")  # gqa_conf.py:91
+        self.output = args.output
+        os.makedirs(self.output, exist_ok=True)
+
+    def load(self, path):
+        """gqa_conf.py:375-381: strip '.module', non-strict load."""
+        print("Load model from %s" % path)
+        state_dict = torch.load("%s.pth" % path, map_location="cpu")
+        state_dict = {k.replace(".module", ""): v for k, v in state_dict.items()}
+        self.model.load_state_dict(state_dict, strict=False)
+
+    def save(self, name):
+        torch.save(self.model.state_dict(), os.path.join(self.output, "%s.pth" % name))
+
+    def ood_evaluate(self, dataset, batch_size, method, dump=None, maha=None):
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        lo, hi = shard_range(dataset.n, rank, world)
+        if method == "maha":
+            if maha is None:
+                raise RuntimeError("Mahalanobis needs {mean, precision} (sample_estimator pickle, gqa_maha.py:185-188)")
+            self.model.engine().set_maha(*maha)
+        ev = GQAEval(self.model, dataset, method=method, tau=self.args.tau)
+        return ev.ood_evaluate(dataset.loader(batch_size, lo, hi), dump=dump if rank == 0 else None)
+
+
+def main(argv=None):
+    p = argparse.ArgumentParser(parents=[get_parser()])
+    p.add_argument("--syntheticN", type=int, default=4096)
+    args, _ = p.parse_known_args(argv)
+    if not torch.cuda.is_available():
+        raise RuntimeError("rgqa_b200 needs a CUDA device; there is no CPU path")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.max_seq_length is None:
+        args.max_seq_length = 30  # MAX_GQA_LENGTH, gqa_model.py:11
+    gqa = GQA(args)
+    if args.load is not None:
+        gqa.load(args.load)
+    gqa.model = gqa.model.cuda()
+    test = args.test or "synthetic"
+    L = 20 if args.backbone == "uniter" else args.max_seq_length
+    dataset = SyntheticRGQA(args.syntheticN, L=L, seed=args.seed)
+    if args.backbone == "uniter":
+        raise SystemExit("the synthetic data set carries 4-d boxes; drive GQAUNITER through GQAEval with 7-d boxes")
+    maha = None
+    if args.method == "maha":
+        from .. import synthetic as syn
+        maha = syn.maha_stats()
+    results = gqa.ood_evaluate(dataset, args.batch_size, args.method,
+                               dump=os.path.join(args.output, "%s_predict.json" % test), maha=maha)
+    if results is not None:
+        print(results)
+        dump_results_json(results, os.path.join(args.output, "%s_result.json" % test))
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

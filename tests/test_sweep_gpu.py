@@ -1,0 +1,99 @@
+"""The public Python seam on the GPU: GQAModel.forward(feat, pos, sent), the GQAEval sweep (pinned host batches,
+double-buffered H2D, device scorers) and the JSON it writes, against the CPU oracle run on the same inputs."""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from rgqa_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+LAYERS = dict(l_layers=2, x_layers=1, r_layers=1)
+
+
+def _args(precision):
+    return types.SimpleNamespace(llayers=2, xlayers=1, rlayers=1, from_scratch=False, precision=precision, vocab=None,
+                                 max_seq_length=20)
+
+
+@pytest.fixture(scope="module")
+def small_model(cuda_device):
+    sys.argv = ["x"]
+    from rgqa_b200.tasks.gqa_model import GQAModel_maha
+    m = GQAModel_maha(1842, args=_args("fp32"), max_seq_length=20)
+    sd = syn.lxmert_state_dict(variant="rich", head_sigma=0.2, **LAYERS)
+    m.load_state_dict(sd, strict=True)
+    return m.to(cuda_device), sd
+
+
+def test_model_forward_with_sentences_matches_oracle(small_model, cuda_device):
+    from oracle import lxmert_oracle as O
+    m, sd = small_model
+    sents = ["Is the cat on the mat?", "what color is the large bus to the left of the tree", "", "Are there any zebras?"]
+    inp = syn.make_inputs(len(sents), 20, seed=5)
+    logits, pooled = m(inp["feat"].to(cuda_device), inp["pos"].to(cuda_device), sents)
+    ids, mask, seg = m.lxrt_encoder.tokenizer.encode_batch(sents, 20)
+    ref_logits, ref_pooled = O.gqa_model_forward(sd, inp["feat"], inp["pos"], torch.from_numpy(ids).long(),
+                                                 torch.from_numpy(seg).long(), torch.from_numpy(mask).long())
+    assert (pooled.cpu() - ref_pooled).abs().max() <= 1e-4
+    assert (logits.cpu() - ref_logits).abs().max() <= 1e-3  # head02 logits reach +-30
+    # the packed engine is rebuilt when a parameter changes
+    with torch.no_grad():
+        m.logit_fc._parameters["3|bias"].add_(1.0)
+    logits2, _ = m(inp["feat"].to(cuda_device), inp["pos"].to(cuda_device), sents)
+    torch.testing.assert_close(logits2, logits + 1.0, atol=1e-4, rtol=0)
+    with torch.no_grad():
+        m.logit_fc._parameters["3|bias"].sub_(1.0)
+
+
+@pytest.mark.parametrize("method", ["msp", "energy", "maha"])
+def test_sweep_matches_oracle_and_writes_reference_json(small_model, cuda_device, tmp_path, method):
+    from oracle import lxmert_oracle as O
+    from oracle import metrics_oracle as MO
+    from oracle import scorers_oracle as S
+    from rgqa_b200.tasks.gqa_eval import GQAEval, SyntheticRGQA
+    m, sd = small_model
+    ds = SyntheticRGQA(50, L=20, seed=11, pool=50)
+    mu, P = syn.maha_stats()
+    m.engine().set_maha(mu, P)
+    dump = str(tmp_path / f"{method}_predict.json")
+    res = GQAEval(m, ds, method=method, tau=0.5).ood_evaluate(ds.loader(16), dump=dump)  # ragged last batch (50 = 3*16+2)
+    logit, x = O.gqa_model_forward(sd, ds.feat.float(), ds.pos, ds.ids.long(), torch.zeros_like(ds.ids).long(), ds.mask.long())
+    rs, rl = {"msp": S.msp, "energy": S.energy_top2, "maha": lambda _: S.mahalanobis(x, mu, P)[:2]}[method](logit)
+    rows = json.load(open(dump))
+    assert [r["questionId"] for r in rows] == ds.qids
+    assert [r["prediction"] for r in rows] == [ds.label2ans[int(i)] for i in rl]
+    np.testing.assert_allclose([r["confidence"] for r in rows], np.round(rs.numpy().astype(np.float64), 4), rtol=1e-3, atol=2e-4)
+    # metrics of OUR scores through the product evaluator == the sklearn oracle on the same triples (bit-exact)
+    q2l = {q: ds.id2datum[q]["label"] for q in ds.qids}
+    want = MO.evaluate(q2l, _triples(m, ds, method, cuda_device))
+    for k, v in want.items():
+        assert float(res[k]) == float(v), k
+
+
+def _triples(m, ds, method, dev):
+    from rgqa_b200.tasks.gqa_eval import SweepRunner
+    r = SweepRunner(m, method, device=dev)
+    out = []
+    for qids, f, p, i, mk in ds.loader(16):
+        s, l = r.submit(f, p, i, mk)
+        out += [(q, ds.label2ans[int(a)], b) for q, a, b in zip(qids, l.cpu().numpy(), s.cpu().numpy())]
+    return out
+
+
+def test_uniter_module_matches_golden(cuda_device):
+    sys.argv = ["x"]
+    from rgqa_b200.uniter.uniter import GQAUNITER
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "uniter_rich_L20_B4.npz"))
+    meta = json.loads(str(z["meta"]))
+    m = GQAUNITER(1842, args=_args("fp32"))
+    m.load_state_dict(syn.uniter_state_dict(variant="rich"), strict=True)
+    m = m.to(cuda_device)
+    inp = syn.make_inputs(4, 20, seed=meta["inputs_seed"], vocab=28996)
+    logits, _ = m.forward_ids(inp["feat"].to(cuda_device), inp["pos7"].to(cuda_device), inp["ids"].to(cuda_device),
+                              inp["seg"].to(cuda_device), inp["mask"].to(cuda_device))
+    assert np.abs(logits.cpu().numpy() - z["logits"]).max() <= 1e-4
