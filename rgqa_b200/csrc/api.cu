@@ -831,6 +831,10 @@ int rgqa_set_option(const char* name, int value) {
     option_set(OPT_GEMM_STAGED, value);
     return 0;
   }
+  if (strcmp(name, "gemm_debug") == 0) {  // measurement only: results are wrong while non-zero
+    option_set(OPT_GEMM_DEBUG, value);
+    return 0;
+  }
   set_error("rgqa_set_option: unknown option '%s'", name);
   return 1;
 }

@@ -58,6 +58,7 @@ struct GemmParams {
   void* out;
   long long ldo;
   int vec_ok;  // direct path: rows of out (and resid) are 16-byte aligned -> vector stores allowed
+  int debug;   // measurement only (rgqa_set_option "gemm_debug"): bit0 skip TMA stores, bit1 skip epilogue math+smem
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -68,18 +69,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. far below one bf16 ulp of the output);
 // two MUFU ops + a 5-term Horner instead of erff's branchy path: the FFN1 epilogue has ~24 issue
 // slots per output element before it, not the MMA, paces the tile.
+// 13 instructions per element: erf(|x|/sqrt2) = 1 - t(a1 + t(a2 + t(a3 + t(a4 + t a5)))) exp(-x^2/2),
+// t = 1/(1 + p|x|/sqrt2); gelu = x/2 + |x/2| erf(|x|/sqrt2)  (odd extension folded into the last FMA).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = ex2_approx(-z * z * 1.44269504088896340736f);
-  const float erf_abs = fmaf(-p, e, 1.0f);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  q *= t;
+  const float e = ex2_approx((x * -0.72134752044448170368f) * x);  // exp(-x^2/2) = 2^(-x^2 * log2(e)/2)
+  const float erf_abs = fmaf(-q, e, 1.0f);
+  const float h = 0.5f * x;
+  return fmaf(fabsf(h), erf_abs, h);
 }
 
 template <int EPI>
@@ -589,18 +596,23 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           uint8_t* buf = slabs + (half * 2 + (slab_ctr & 1)) * kSlabBytes;
           if (issuer) tma_store_wait_read<1>();  // the store that last read this buffer (2 slabs ago) is done with it
           named_bar_sync(1 + half, 128);
+          // both 32-column chunks of the slab are requested from TMEM before either is consumed
+          uint32_t v[kChunksPerSlab][32];
+#pragma unroll
+          for (int cc = 0; cc < kChunksPerSlab; ++cc)
+            tmem_ld32(t_row + static_cast<uint32_t>(sl * kColsPerSlab + cc * 32), v[cc]);
+#pragma unroll
+          for (int cc = 0; cc < kChunksPerSlab; ++cc) tmem_ld_wait_dep(v[cc]);
 #pragma unroll
           for (int cc = 0; cc < kChunksPerSlab; ++cc) {
-            uint32_t v[32];
-            tmem_ld32(t_row + static_cast<uint32_t>(sl * kColsPerSlab + cc * 32), v);
-            tmem_ld_wait_dep(v);
+            if (p.debug & 2) continue;
             float f[32];
-            epilogue_math<EPI>(v, f, row, row_ok, col_slab + cc * 32, p, true);
+            epilogue_math<EPI>(v[cc], f, row, row_ok, col_slab + cc * 32, p, true);
             store_chunk_swizzled<OutT>(buf, r_local, cc, f);
           }
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           named_bar_sync(1 + half, 128);
-          if (issuer && tile_rows_live) {
+          if (issuer && tile_rows_live && !(p.debug & 1)) {
             tma_store_2d(&tmOut, buf, col_slab, m0);
             tma_store_commit();
           }
@@ -807,6 +819,7 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
   p.out = out;
   p.ldo = ldo;
   p.vec_ok = (out_al && res_al && bias_al) ? 1 : 0;
+  p.debug = option_get(OPT_GEMM_DEBUG);
   if (use_pair) return dispatch_pair(stream, tmA, tmB, tmOut, tmRes, p, epi, out_f32, staged);
   return bn == 256 ? dispatch_epi<256>(stream, tmA, tmB, p, epi, out_f32)
                    : dispatch_epi<128>(stream, tmA, tmB, p, epi, out_f32);

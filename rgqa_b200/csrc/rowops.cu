@@ -113,21 +113,33 @@ layernorm_kernel(const float* __restrict__ xin, long long ldx, const float* __re
 }
 
 // ---- small-K projection of a per-row vector (boxes, K = 4 or 7) ---------------------------------
+// The [H, K] weight is staged once per CTA into shared memory TRANSPOSED ([K][H] followed by the bias [H]) so a
+// lane's four output columns are one conflict-free 16-byte read per k; CTAs then walk many rows.
+__device__ __forceinline__ void stage_small_weight(float* wsm, const float* __restrict__ W, const float* __restrict__ bias,
+                                                   int H, int K) {
+  for (int idx = threadIdx.x; idx < H * K; idx += blockDim.x) {
+    const int c = idx / K, k = idx - c * K;
+    wsm[k * H + c] = W[idx];
+  }
+  for (int c = threadIdx.x; c < H; c += blockDim.x) wsm[K * H + c] = bias[c];
+  __syncthreads();
+}
 template <int NV>
-__device__ __forceinline__ void small_proj(float4 (&y)[NV], const float* __restrict__ vec, int K,
-                                           const float* __restrict__ W, const float* __restrict__ bias, int lane) {
+__device__ __forceinline__ void small_proj(float4 (&y)[NV], const float* vec, int K, const float* wsm, int H, int lane) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = i * 128 + lane * 4;
-    float o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      // torch addmm order: bias + sum_k x[k] * W[c,k]; K is tiny so the order is fixed here too
-      float a = 0.f;
-      for (int k = 0; k < K; ++k) a = fmaf(vec[k], __ldg(W + static_cast<long long>(c + j) * K + k), a);
-      o[j] = a + __ldg(bias + c + j);
+    // torch addmm order: sum_k x[k] * W[c,k], then + bias; K is tiny so the order is fixed here too
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < K; ++k) {
+      const float4 w = *reinterpret_cast<const float4*>(wsm + k * H + c);
+      a.x = fmaf(vec[k], w.x, a.x);
+      a.y = fmaf(vec[k], w.y, a.y);
+      a.z = fmaf(vec[k], w.z, a.z);
+      a.w = fmaf(vec[k], w.w, a.w);
     }
-    y[i] = make_float4(o[0], o[1], o[2], o[3]);
+    const float4 b = *reinterpret_cast<const float4*>(wsm + K * H + c);
+    y[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
   }
 }
 
@@ -138,16 +150,17 @@ visn_combine_kernel(const float* __restrict__ x_pre, const float* __restrict__ b
                     const float* __restrict__ Wb, const float* __restrict__ bb, const float* __restrict__ g1,
                     const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
                     OutT* __restrict__ out, float* __restrict__ out32, int rows, int H, float eps) {
-  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  extern __shared__ __align__(16) float wsm[];
+  stage_small_weight(wsm, Wb, bb, H, box_dim);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  for (int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += gridDim.x * kWarpsPerBlock) {
   float4 x[NV], y[NV];
   const float* xr = x_pre + static_cast<long long>(row) * H;
 #pragma unroll
   for (int i = 0; i < NV; ++i) x[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
   float bx[8];
   for (int k = 0; k < box_dim; ++k) bx[k] = boxes[static_cast<long long>(row) * box_dim + k];
-  small_proj<NV>(y, bx, box_dim, Wb, bb, lane);
+  small_proj<NV>(y, bx, box_dim, wsm, H, lane);
   float mean, rstd;
   row_stats<NV>(x, H, eps, mean, rstd);
   normalize<NV>(x, mean, rstd, g1, b1, lane);
@@ -159,6 +172,7 @@ visn_combine_kernel(const float* __restrict__ x_pre, const float* __restrict__ b
                        (x[i].w + y[i].w) / 2.f);
   store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane,
                       out32 != nullptr ? out32 + static_cast<long long>(row) * H : nullptr);
+  }
 }
 
 // ---- UniterImageEmbeddings tail (src/uniter/modeling.py:606-612) --------------------------------
@@ -169,16 +183,17 @@ uniter_img_kernel(const float* __restrict__ x_pre, const float* __restrict__ pos
                   const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
                   const float* __restrict__ type_row, const float* __restrict__ g3, const float* __restrict__ b3,
                   OutT* __restrict__ out, float* __restrict__ out32, int rows, int H, float eps) {
-  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  extern __shared__ __align__(16) float wsm[];
+  stage_small_weight(wsm, Wp, bp, H, pos_dim);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  for (int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += gridDim.x * kWarpsPerBlock) {
   float4 x[NV], y[NV];
   const float* xr = x_pre + static_cast<long long>(row) * H;
 #pragma unroll
   for (int i = 0; i < NV; ++i) x[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
   float pv[8];
   for (int k = 0; k < pos_dim; ++k) pv[k] = posf[static_cast<long long>(row) * pos_dim + k];
-  small_proj<NV>(y, pv, pos_dim, Wp, bp, lane);
+  small_proj<NV>(y, pv, pos_dim, wsm, H, lane);
   float mean, rstd;
   row_stats<NV>(x, H, eps, mean, rstd);
   normalize<NV>(x, mean, rstd, g1, b1, lane);
@@ -195,6 +210,7 @@ uniter_img_kernel(const float* __restrict__ x_pre, const float* __restrict__ pos
   normalize<NV>(x, mean, rstd, g3, b3, lane);
   store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane,
                       out32 != nullptr ? out32 + static_cast<long long>(row) * H : nullptr);
+  }
 }
 
 // ---- casts -------------------------------------------------------------------------------------
@@ -236,6 +252,19 @@ __global__ void gather_rows_kernel(const T* __restrict__ src, long long src_ld, 
 inline int row_grid(int rows) { return (rows + kWarpsPerBlock - 1) / kWarpsPerBlock; }
 
 }  // namespace
+
+#define RGQA_DISPATCH_ROW_SMEM(KERNEL, OUT_T, SMEM, ...)                                                   \
+  do {                                                                                                     \
+    const int nv = H / 128;                                                                                \
+    int grid_ = row_grid(M);                                                                               \
+    if (grid_ > 148 * 8) grid_ = 148 * 8; /* a few resident waves; warps stride over the rows */           \
+    if (H % 128 == 0 && nv == 6)                                                                           \
+      KERNEL<6, OUT_T><<<grid_, kWarpsPerBlock * 32, (SMEM), stream>>>(__VA_ARGS__);                       \
+    else {                                                                                                 \
+      set_error("row kernel: unsupported hidden size %d (need 768)", H);                                   \
+      return 1;                                                                                            \
+    }                                                                                                      \
+  } while (0)
 
 #define RGQA_DISPATCH_ROW(KERNEL, OUT_T, ...)                                                              \
   do {                                                                                                     \
@@ -284,9 +313,9 @@ int visn_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const f
                  const float* b2, void* out, float* out32, int M, int H, float eps) {
   RGQA_CHECK(M > 0 && box_dim >= 1 && box_dim <= 8, "visn_combine: bad M=%d box_dim=%d", M, box_dim);
   if (out_dtype == DT_BF16) {
-    RGQA_DISPATCH_ROW(visn_combine_kernel, __nv_bfloat16, x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<__nv_bfloat16*>(out), out32, M, H, eps);
+    RGQA_DISPATCH_ROW_SMEM(visn_combine_kernel, __nv_bfloat16, (box_dim + 1) * H * sizeof(float), x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<__nv_bfloat16*>(out), out32, M, H, eps);
   } else {
-    RGQA_DISPATCH_ROW(visn_combine_kernel, float, x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<float*>(out), out32, M, H, eps);
+    RGQA_DISPATCH_ROW_SMEM(visn_combine_kernel, float, (box_dim + 1) * H * sizeof(float), x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<float*>(out), out32, M, H, eps);
   }
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
@@ -299,9 +328,9 @@ int uniter_img_combine(cudaStream_t stream, int out_dtype, const float* x_pre, c
                        float* out32, int M, int H, float eps) {
   RGQA_CHECK(M > 0 && pos_dim >= 1 && pos_dim <= 8, "uniter_img_combine: bad M=%d pos_dim=%d", M, pos_dim);
   if (out_dtype == DT_BF16) {
-    RGQA_DISPATCH_ROW(uniter_img_kernel, __nv_bfloat16, x_pre, pos, pos_dim, Wp, bp, g1, b1, g2, b2, type_row, g3, b3, static_cast<__nv_bfloat16*>(out), out32, M, H, eps);
+    RGQA_DISPATCH_ROW_SMEM(uniter_img_kernel, __nv_bfloat16, (pos_dim + 1) * H * sizeof(float), x_pre, pos, pos_dim, Wp, bp, g1, b1, g2, b2, type_row, g3, b3, static_cast<__nv_bfloat16*>(out), out32, M, H, eps);
   } else {
-    RGQA_DISPATCH_ROW(uniter_img_kernel, float, x_pre, pos, pos_dim, Wp, bp, g1, b1, g2, b2, type_row, g3, b3, static_cast<float*>(out), out32, M, H, eps);
+    RGQA_DISPATCH_ROW_SMEM(uniter_img_kernel, float, (pos_dim + 1) * H * sizeof(float), x_pre, pos, pos_dim, Wp, bp, g1, b1, g2, b2, type_row, g3, b3, static_cast<float*>(out), out32, M, H, eps);
   }
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
