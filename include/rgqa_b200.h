@@ -135,6 +135,11 @@ int rgqa_prof_collect(double* ms_sum, double* flops_sum, long long* count);
 int rgqa_gemm_bf16(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                    const void* resid, int64_t ldr, void* out, int64_t ldo, int out_dtype, int M, int N, int K,
                    int epilogue);
+/* out_act (bf16 [M,768]) and out_res (f32 [M,768], may be NULL) = LayerNorm(A·Wᵀ + bias + resid) * gamma + beta,
+ * one kernel; N must be 768 (BertAttOutput / BertOutput, src/lxrt/modeling.py:357-361, :411-415). */
+int rgqa_gemm_bf16_ln(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                      const float* resid, int64_t ldr, const float* gamma, const float* beta, float eps, void* out_act,
+                      float* out_res, int M, int N, int K);
 int rgqa_gemm_f32(void* stream, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                   const float* resid, int64_t ldr, float* out, int64_t ldo, int M, int N, int K, int epilogue);
 int rgqa_attention(void* stream, int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,

@@ -344,6 +344,22 @@ inline float* res_copy_rows(const rgqa_handle* h, const Hid& x, long long r0) {
   return reinterpret_cast<float*>(rows_at(x.res, r0, h->cfg.hidden, 4));
 }
 
+// out = LayerNorm(A · Wᵀ + b + residual(in)) on rows [r0, r0 + M)  (BertAttOutput / BertOutput, modeling.py:357-361,
+// :411-415).  bf16 path: ONE kernel (full 768-wide rows per CTA in TMEM, gemm_ln_tcgen05.cu); otherwise the GEMM
+// writes the fp32 pre-LayerNorm sum and a row kernel normalises it.
+int dense_resid_ln(rgqa_handle* h, cudaStream_t st, const void* A, long long lda, const Linear& lin, const LNp& ln,
+                   const Hid& in, const Hid& out, long long r0, int M) {
+  const int H = h->cfg.hidden;
+  const size_t es = act_size(h);
+  if (h->cfg.precision == RGQA_PREC_BF16 && option_get(OPT_GEMM_LN) != 0 && M >= 256)
+    return gemm_bf16_ln(st, A, lda, lin.W, lin.K, lin.b, resid_rows(h, in, r0), H, ln.g, ln.b, h->cfg.ln_eps,
+                        rows_at(out.act, r0, H, es), res_copy_rows(h, out, r0), M, lin.N, lin.K);
+  float* pre = reinterpret_cast<float*>(rows_at(h->pre.p, r0, H, 4));
+  if (gemm(h, st, A, lda, lin, resid_rows(h, in, r0), H, pre, H, 1, M, EPI_RESID)) return 1;
+  return layernorm(st, act_dtype(h), pre, H, ln.g, ln.b, rows_at(out.act, r0, H, es), res_copy_rows(h, out, r0), M, H,
+                   h->cfg.ln_eps);
+}
+
 // self-attention block + output projection + LN on rows [r0, r0 + B*S) : in -> out
 int att_block(rgqa_handle* h, cudaStream_t st, const AttW& w, const Hid& in, const Hid& out, long long r0, int B, int S,
               const int32_t* key_mask) {
@@ -355,14 +371,11 @@ int att_block(rgqa_handle* h, cudaStream_t st, const AttW& w, const Hid& in, con
   char* x = rows_at(in.act, r0, H, es);
   char* qkv = rows_at(h->qkv.p, r0, 3 * H, es);
   char* ctx = rows_at(h->ctx.p, r0, H, es);
-  float* pre = reinterpret_cast<float*>(rows_at(h->pre.p, r0, H, 4));
   if (gemm(h, st, x, H, w.qkv, nullptr, 0, qkv, 3 * H, of32, M, EPI_BIAS)) return 1;
   if (attention(st, dt, qkv, 3 * H, qkv + static_cast<size_t>(H) * es, 3 * H, qkv + static_cast<size_t>(2 * H) * es,
                 3 * H, key_mask, ctx, H, B, S, S, h->cfg.heads))
     return 1;
-  if (gemm(h, st, ctx, H, w.out, resid_rows(h, in, r0), H, pre, H, 1, M, EPI_RESID)) return 1;
-  return layernorm(st, dt, pre, H, w.ln.g, w.ln.b, rows_at(out.act, r0, H, es), res_copy_rows(h, out, r0), M, H,
-                   h->cfg.ln_eps);
+  return dense_resid_ln(h, st, ctx, H, w.out, w.ln, in, out, r0, M);
 }
 
 // FFN block on rows [r0, r0 + M): in -> out
@@ -373,11 +386,8 @@ int ffn_block(rgqa_handle* h, cudaStream_t st, const FfnW& w, const Hid& in, con
   const int of32 = dt == DT_F32;
   char* x = rows_at(in.act, r0, H, es);
   char* inter = rows_at(h->inter.p, r0, I, es);
-  float* pre = reinterpret_cast<float*>(rows_at(h->pre.p, r0, H, 4));
   if (gemm(h, st, x, H, w.inter, nullptr, 0, inter, I, of32, M, EPI_GELU)) return 1;
-  if (gemm(h, st, inter, I, w.out, resid_rows(h, in, r0), H, pre, H, 1, M, EPI_RESID)) return 1;
-  return layernorm(st, dt, pre, H, w.ln.g, w.ln.b, rows_at(out.act, r0, H, es), res_copy_rows(h, out, r0), M, H,
-                   h->cfg.ln_eps);
+  return dense_resid_ln(h, st, inter, I, w.out, w.ln, in, out, r0, M);
 }
 
 int ensure_workspace(rgqa_handle* h, long long Mt, long long Mv, int B) {
@@ -659,10 +669,7 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
     if (attention(st, dt, qkv_v, 3 * H, qkv + static_cast<size_t>(H) * es, 3 * H, qkv + static_cast<size_t>(2 * H) * es,
                   3 * H, mask, rows_at(h->ctx.p, Ml, H, es), H, B, V, L, c.heads))
       return 1;
-    if (gemm(h, st, h->ctx.p, H, w.cross.out, resid_rows(h, cur, 0), H, h->pre.p, H, 1, static_cast<int>(Mt), EPI_RESID)) return 1;
-    if (layernorm(st, dt, static_cast<const float*>(h->pre.p), H, w.cross.ln.g, w.cross.ln.b, alt.act, res_copy_rows(h, alt, 0), static_cast<int>(Mt), H,
-                  c.ln_eps))
-      return 1;
+    if (dense_resid_ln(h, st, h->ctx.p, H, w.cross.out, w.cross.ln, cur, alt, 0, static_cast<int>(Mt))) return 1;
     // self attention per stream (:461-465): alt -> cur
     if (att_block(h, st, w.lang_self, alt, cur, 0, B, L, mask)) return 1;
     if (att_block(h, st, w.visn_self, alt, cur, Ml, B, V, nullptr)) return 1;
@@ -831,6 +838,14 @@ int rgqa_set_option(const char* name, int value) {
     option_set(OPT_GEMM_STAGED, value);
     return 0;
   }
+  if (strcmp(name, "gemm_ln") == 0) {
+    option_set(OPT_GEMM_LN, value);
+    return 0;
+  }
+  if (strcmp(name, "pdl") == 0) {
+    option_set(OPT_PDL, value);
+    return 0;
+  }
   if (strcmp(name, "gemm_debug") == 0) {  // measurement only: results are wrong while non-zero
     option_set(OPT_GEMM_DEBUG, value);
     return 0;
@@ -851,6 +866,12 @@ int rgqa_gemm_bf16(void* stream, const void* A, int64_t lda, const void* W, int6
                    int epilogue) {
   return gemm_bf16(static_cast<cudaStream_t>(stream), A, lda, W, ldw, bias, resid, ldr, out, ldo,
                    out_dtype == RGQA_DT_F32 ? 1 : 0, M, N, K, epilogue);
+}
+int rgqa_gemm_bf16_ln(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                      const float* resid, int64_t ldr, const float* gamma, const float* beta, float eps, void* out_act,
+                      float* out_res, int M, int N, int K) {
+  return gemm_bf16_ln(static_cast<cudaStream_t>(stream), A, lda, W, ldw, bias, resid, ldr, gamma, beta, eps, out_act,
+                      out_res, M, N, K);
 }
 int rgqa_gemm_f32(void* stream, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                   const float* resid, int64_t ldr, float* out, int64_t ldo, int M, int N, int K, int epilogue) {

@@ -154,6 +154,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -172,23 +178,25 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int item = blockIdx.x * 4 + warp;
+  pdl_launch_dependents();
+  pdl_wait();
   if (item >= items) return;  // warp-uniform; no block-wide barrier below
   const int b = item / heads, h = item % heads;
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_att) + static_cast<size_t>(warp) * (2 * ROWS * kLds);
   __nv_bfloat16* Vs = Ks + ROWS * kLds;
 
-  // stage this head's K and V rows (16 B per lane per access, rows >= Lk zero-filled)
-  for (int idx = lane; idx < ROWS * 8; idx += 32) {
+  // stage this head's K and V rows with cp.async (16 B per lane per copy, no register staging, all 8*KS copies
+  // in flight at once; rows >= Lk are zero-filled through src-size 0)
+#pragma unroll
+  for (int it = 0; it < ROWS * 8 / 32; ++it) {
+    const int idx = it * 32 + lane;
     const int r = idx >> 3, c = (idx & 7) * 8;
-    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
-    if (r < Lk) {
-      kv = __ldg(reinterpret_cast<const uint4*>(k + (static_cast<long long>(b) * Lk + r) * ldk + h * HD + c));
-      vv = __ldg(reinterpret_cast<const uint4*>(v + (static_cast<long long>(b) * Lk + r) * ldv + h * HD + c));
-    }
-    *reinterpret_cast<uint4*>(Ks + r * kLds + c) = kv;
-    *reinterpret_cast<uint4*>(Vs + r * kLds + c) = vv;
+    const bool ok = r < Lk;
+    const long long grow = static_cast<long long>(b) * Lk + (ok ? r : 0);
+    cp_async_16(Ks + r * kLds + c, k + grow * ldk + h * HD + c, ok ? 16u : 0u);
+    cp_async_16(Vs + r * kLds + c, v + grow * ldv + h * HD + c, ok ? 16u : 0u);
   }
-  __syncwarp();
+  cp_async_commit();
 
   float madd[NT][2];
 #pragma unroll
@@ -199,19 +207,29 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const _
       madd[j][e] = key >= Lk ? -INFINITY : ((key_mask != nullptr && key_mask[b * Lk + key] == 0) ? -10000.f : 0.f);
     }
 
-  for (int m0 = 0; m0 < Lq; m0 += 16) {
+  // Q fragments come straight from global memory (4 B per lane); the next tile's are requested before the
+  // current tile is computed, and the first tile's before the K/V copies are waited for
+  auto load_q = [&](int m0, uint32_t (&qf)[4][4]) {
     const int r0 = m0 + g, r1 = r0 + 8;
     const __nv_bfloat16* q0 = q + (static_cast<long long>(b) * Lq + r0) * ldq + h * HD;
     const __nv_bfloat16* q1 = q + (static_cast<long long>(b) * Lq + r1) * ldq + h * HD;
-    uint32_t qa[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       const int c = ks * 16 + 2 * t;
-      qa[ks][0] = r0 < Lq ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c)) : 0u;
-      qa[ks][1] = r1 < Lq ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c)) : 0u;
-      qa[ks][2] = r0 < Lq ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c + 8)) : 0u;
-      qa[ks][3] = r1 < Lq ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c + 8)) : 0u;
+      qf[ks][0] = r0 < Lq ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c)) : 0u;
+      qf[ks][1] = r1 < Lq ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c)) : 0u;
+      qf[ks][2] = r0 < Lq ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c + 8)) : 0u;
+      qf[ks][3] = r1 < Lq ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c + 8)) : 0u;
     }
+  };
+  uint32_t qa[4][4], qn[4][4];
+  load_q(0, qa);
+  cp_async_wait_all();
+  __syncwarp();
+
+  for (int m0 = 0; m0 < Lq; m0 += 16) {
+    const int r0 = m0 + g, r1 = r0 + 8;
+    if (m0 + 16 < Lq) load_q(m0 + 16, qn);
     float s[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
@@ -278,6 +296,12 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const _
       if (r0 < Lq) *reinterpret_cast<uint32_t*>(o0 + 8 * d) = pack_bf16x2(o[d][0] * inv0, o[d][1] * inv0);
       if (r1 < Lq) *reinterpret_cast<uint32_t*>(o1 + 8 * d) = pack_bf16x2(o[d][2] * inv1, o[d][3] * inv1);
     }
+    if (m0 + 16 < Lq) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qa[ks][i] = qn[ks][i];
+    }
   }
 }
 
@@ -292,8 +316,7 @@ int launch_attention_mma(cudaStream_t stream, const __nv_bfloat16* q, long long 
     RGQA_CUDA_OK(cudaFuncSetAttribute(attention_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     cfg = true;
   }
-  attention_mma_kernel<KS><<<(items + 3) / 4, 128, smem, stream>>>(q, ldq, k, ldk, v, ldv, key_mask, out, ldo, Lq, Lk, heads,
-                                                                 items);
+  RGQA_CUDA_OK(launch_pdl(attention_mma_kernel<KS>, dim3((items + 3) / 4), dim3(128), smem, stream, q, ldq, k, ldk, v, ldv, key_mask, out, ldo, Lq, Lk, heads, items));
   return 0;
 }
 

@@ -34,6 +34,31 @@ void set_error(const char* fmt, ...);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the hot kernels of the forward are launched with the
+// programmatic-stream-serialization attribute so kernel N+1's CTAs are scheduled (and run their
+// prologue: barrier init, TMEM alloc, descriptor prefetch) while kernel N drains.  Every such kernel
+// executes pdl_wait() before its first global-memory access; without the attribute it is a no-op.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();  // prof.cu (runtime option "pdl")
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ----------------------------------------------------------------------------------------------
 // Small device utilities
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -254,6 +254,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -428,6 +430,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
@@ -644,6 +648,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 2) tmem_dealloc_pair<512>(tmem_base);
 }
 
+}  // namespace
+
 // ------------------------------------------------------------------------------------------------
 // Host side: tensor-map encoding through the driver entry point (no link-time libcuda dependency,
 // so the library loads on a CPU-only box for the symbol check).
@@ -652,7 +658,7 @@ using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-EncodeTiledFn get_encode_fn() {
+static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -693,6 +699,8 @@ int num_sms() {
   return n;
 }
 
+namespace {
+
 template <int BN, int EPI, typename OutT>
 int launch(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
   using C = Cfg<BN>;
@@ -705,7 +713,7 @@ int launch(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   void* tok = prof_begin(stream);
-  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
+  RGQA_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kNumThreads), C::kSmemBytes, stream, tmA, tmB, p));
   prof_end(tok, stream, 2.0 * p.M * static_cast<double>(p.N) * p.K, PROF_GEMM_TC);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
@@ -744,7 +752,7 @@ int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& 
   const int max_pairs = num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   void* tok = prof_begin(stream);
-  kern<<<2 * pairs, kNumThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, p);
+  RGQA_CUDA_OK(launch_pdl(kern, dim3(2 * pairs), dim3(kNumThreads), smem, stream, tmA, tmB, tmOut, tmRes, p));
   prof_end(tok, stream, 2.0 * p.M * static_cast<double>(p.N) * p.K, PROF_GEMM_TC);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+struct CUtensorMap_st;  // <cuda.h>, only needed by the tcgen05 translation units
+
 namespace rgqa {
 
 enum Epilogue : int {
@@ -24,6 +26,16 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
 // fp32 SIMT path (precise mode): everything fp32.
 int gemm_f32(cudaStream_t stream, const float* A, long long lda, const float* W, long long ldw, const float* bias,
              const float* resid, long long ldr, float* out, long long ldo, int M, int N, int K, int epi);
+
+// Full-row GEMM + LayerNorm (bf16 path): out_act/out_res = LN(A·Wᵀ + bias + resid) for N == 768, one kernel
+// (BertAttOutput / BertOutput, modeling.py:357-361, :411-415).  out_res may be null.
+int gemm_bf16_ln(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                 const float* resid, long long ldr, const float* gamma, const float* beta, float eps, void* out_act,
+                 float* out_res, int M, int N, int K);
+// host helpers shared by the tcgen05 GEMM translation units (gemm_tcgen05.cu)
+int make_tmap(::CUtensorMap_st* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
+              int elem_bytes);
+int num_sms();
 
 // ---- attention (small sequences, Lq, Lk <= 64, 12 heads x 64) -----------------------------------
 // q/k/v point at the first row of sample 0 (head 0); rows are ldq/ldk/ldv elements apart; sample b
@@ -76,7 +88,7 @@ int rowdot(cudaStream_t stream, const float* a, const float* b, float* out, int 
 
 
 // ---- runtime options (prof.cu): kernel-selection switches for A/B measurements ---------------------
-enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_GEMM_DEBUG = 2, OPT_COUNT = 8 };
+enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_GEMM_DEBUG = 2, OPT_PDL = 3, OPT_GEMM_LN = 4, OPT_COUNT = 8 };
 int option_get(int key);
 void option_set(int key, int value);
 

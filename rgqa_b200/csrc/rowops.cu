@@ -66,6 +66,8 @@ embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ seg
                 const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ gamma,
                 const float* __restrict__ beta, OutT* __restrict__ out, float* __restrict__ out32, int rows, int L, int H, float eps, int vocab,
                 int n_types) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -98,6 +100,8 @@ template <int NV, typename OutT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 layernorm_kernel(const float* __restrict__ xin, long long ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, OutT* __restrict__ out, float* __restrict__ out32, int rows, int H, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -151,6 +155,8 @@ visn_combine_kernel(const float* __restrict__ x_pre, const float* __restrict__ b
                     const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
                     OutT* __restrict__ out, float* __restrict__ out32, int rows, int H, float eps) {
   extern __shared__ __align__(16) float wsm[];
+  pdl_launch_dependents();
+  pdl_wait();
   stage_small_weight(wsm, Wb, bb, H, box_dim);
   const int lane = threadIdx.x & 31;
   for (int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += gridDim.x * kWarpsPerBlock) {
@@ -184,6 +190,8 @@ uniter_img_kernel(const float* __restrict__ x_pre, const float* __restrict__ pos
                   const float* __restrict__ type_row, const float* __restrict__ g3, const float* __restrict__ b3,
                   OutT* __restrict__ out, float* __restrict__ out32, int rows, int H, float eps) {
   extern __shared__ __align__(16) float wsm[];
+  pdl_launch_dependents();
+  pdl_wait();
   stage_small_weight(wsm, Wp, bp, H, pos_dim);
   const int lane = threadIdx.x & 31;
   for (int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += gridDim.x * kWarpsPerBlock) {
@@ -259,7 +267,7 @@ inline int row_grid(int rows) { return (rows + kWarpsPerBlock - 1) / kWarpsPerBl
     int grid_ = row_grid(M);                                                                               \
     if (grid_ > 148 * 8) grid_ = 148 * 8; /* a few resident waves; warps stride over the rows */           \
     if (H % 128 == 0 && nv == 6)                                                                           \
-      KERNEL<6, OUT_T><<<grid_, kWarpsPerBlock * 32, (SMEM), stream>>>(__VA_ARGS__);                       \
+      RGQA_CUDA_OK(launch_pdl(KERNEL<6, OUT_T>, dim3(grid_), dim3(kWarpsPerBlock * 32), (SMEM), stream, __VA_ARGS__)); \
     else {                                                                                                 \
       set_error("row kernel: unsupported hidden size %d (need 768)", H);                                   \
       return 1;                                                                                            \
@@ -270,9 +278,9 @@ inline int row_grid(int rows) { return (rows + kWarpsPerBlock - 1) / kWarpsPerBl
   do {                                                                                                     \
     const int nv = H / 128;                                                                                \
     if (H % 128 == 0 && nv == 6)                                                                           \
-      KERNEL<6, OUT_T><<<row_grid(M), kWarpsPerBlock * 32, 0, stream>>>(__VA_ARGS__);                      \
+      RGQA_CUDA_OK(launch_pdl(KERNEL<6, OUT_T>, dim3(row_grid(M)), dim3(kWarpsPerBlock * 32), 0, stream, __VA_ARGS__)); \
     else if (H % 128 == 0 && nv == 12)                                                                     \
-      KERNEL<12, OUT_T><<<row_grid(M), kWarpsPerBlock * 32, 0, stream>>>(__VA_ARGS__);                     \
+      RGQA_CUDA_OK(launch_pdl(KERNEL<12, OUT_T>, dim3(row_grid(M)), dim3(kWarpsPerBlock * 32), 0, stream, __VA_ARGS__)); \
     else {                                                                                                 \
       set_error("row kernel: unsupported hidden size %d (need 768 or 1536)", H);                           \
       return 1;                                                                                            \

@@ -53,6 +53,21 @@ def linear_bf16(x, weight, bias=None, epilogue=L.EPI_BIAS, residual=None, out_dt
     return out
 
 
+def linear_residual_layernorm_bf16(x, weight, bias, residual, gamma, beta, eps=1e-12, want_f32=True):
+    """(bf16 [M,768], f32 [M,768]) = LayerNorm(x @ weight.T + bias + residual) — BertAttOutput / BertOutput
+    (src/lxrt/modeling.py:357-361, :411-415) in one tcgen05 kernel; x bf16 [M,K], weight bf16 [768,K], residual f32."""
+    _need_cuda(x, weight, bias, residual, gamma, beta)
+    M, K = x.shape
+    N = weight.shape[0]
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    out32 = torch.empty((M, N), dtype=torch.float32, device=x.device) if want_f32 else None
+    lib = L.load()
+    L.check(lib.rgqa_gemm_bf16_ln(L.current_stream_ptr(), L.ptr(x), x.stride(0), L.ptr(weight), weight.stride(0), L.ptr(bias),
+                                  L.ptr(residual), residual.stride(0), L.ptr(gamma), L.ptr(beta), eps, L.ptr(out), L.ptr(out32),
+                                  M, N, K), "rgqa_gemm_bf16_ln")
+    return out, out32
+
+
 def linear_f32(x, weight, bias=None, epilogue=L.EPI_BIAS, residual=None):
     """fp32 CUDA-core GEMM with the same contract as :func:`linear_bf16` (precise path)."""
     _need_cuda(x, weight, bias, residual)

@@ -68,6 +68,28 @@ def test_gemm_bf16_matches_torch(cuda_device, M, N, K, epi, out_dtype, lda):
         torch.testing.assert_close(out, ref, atol=2e-3, rtol=1e-3)
 
 
+@pytest.mark.parametrize("M,K", [(128, 768), (300, 768), (1000, 3072), (20480, 768), (36864, 3072)])
+def test_gemm_ln_fused_matches_torch(cuda_device, M, K):
+    """GEMM + bias + fp32 residual + LayerNorm in one kernel vs the three reference modules
+    (modeling.py:357-361 / :411-415): dense -> (+ input_tensor) -> LayerNorm(eps 1e-12)."""
+    from rgqa_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + K)
+    N = 768
+    a = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    w = (torch.randn(N, K, generator=g) * 0.03).to(torch.bfloat16).to(cuda_device)
+    bias = (torch.randn(N, generator=g) * 0.1).to(cuda_device)
+    resid = (torch.randn(M, N, generator=g) + 0.3).to(cuda_device)
+    gamma = (1 + 0.1 * torch.randn(N, generator=g)).to(cuda_device)
+    beta = (0.1 * torch.randn(N, generator=g)).to(cuda_device)
+    out, out32 = ops.linear_residual_layernorm_bf16(a, w, bias, resid, gamma, beta)
+    torch.cuda.synchronize()
+    pre = a.float() @ w.float().t() + bias + resid
+    ref = torch.nn.functional.layer_norm(pre, (N,), gamma, beta, eps=1e-12)
+    torch.testing.assert_close(out32, ref, atol=3e-3, rtol=1e-3)   # fp32 accumulation order only
+    assert (out.float() - _bf16r(ref)).abs().max().item() <= 3e-2   # one bf16 rounding of O(1..4) values
+    assert torch.equal(out, out32.to(torch.bfloat16))               # the two copies are the same numbers
+
+
 @pytest.mark.parametrize("M,N,K,epi", [(77, 130, 96, "bias"), (640, 768, 3072, "resid"), (33, 1842, 1536, "bias"),
                                       (64, 768, 768, "gelu"), (32, 768, 768, "tanh")])
 def test_gemm_f32_matches_torch(cuda_device, M, N, K, epi):
