@@ -182,6 +182,9 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = L.load()
+    for kv in filter(None, os.environ.get("RGQA_OPTS", "").split(",")):  # e.g. RGQA_OPTS=two_streams=0,gemm_ln=1
+        k, v = kv.split("=")
+        L.check(lib.rgqa_set_option(k.encode(), int(v)), "rgqa_set_option")
 
     class Ns:  # the flags GQAModel reads (rgqa_b200.param)
         llayers, xlayers, rlayers, from_scratch, precision, vocab, max_seq_length = 9, 5, 5, False, a.precision, None, a.seq_len

@@ -120,6 +120,10 @@ struct rgqa_handle {
   float *maha_mu = nullptr, *maha_P = nullptr, *maha_m = nullptr;
   bool has_maha = false;
 
+  // second stream for the visual branch (language / visual layers are independent between joins)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+
   // workspace
   DevBuf hidA, hidB, resA, resB, qkv, ctx, inter, pre, featb, headbuf, mahabuf;
 };
@@ -471,6 +475,9 @@ void rgqa_destroy(rgqa_handle* h) {
   for (auto& kv : h->raw)
     if (kv.second.p != nullptr) cudaFree(kv.second.p);
   for (void* p : h->owned) cudaFree(p);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   h->hidA.release();
   h->hidB.release();
   h->resA.release();
@@ -622,6 +629,31 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
   Hid cur{h->hidA.p, bf ? static_cast<float*>(h->resA.p) : static_cast<float*>(h->hidA.p)};
   Hid alt{h->hidB.p, bf ? static_cast<float*>(h->resB.p) : static_cast<float*>(h->hidB.p)};
 
+  // The language rows [0, Ml) and the visual rows [Ml, Mt) are independent up to the first cross-modality layer
+  // and again inside each of them after the shared cross attention; the visual branch runs on a second stream
+  // (fork / join with events) so one branch's kernels fill the other's tail waves.  Every workspace buffer is
+  // indexed by row, so the two branches never touch the same bytes.
+  const bool two = option_get(OPT_TWO_STREAMS) != 0 && B >= 64;
+  if (two && h->side == nullptr) {
+    RGQA_CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    RGQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    RGQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
+  cudaStream_t sv = two ? h->side : st;  // stream of the visual branch
+  auto fork = [&]() -> int {
+    if (!two) return 0;
+    RGQA_CUDA_OK(cudaEventRecord(h->ev_fork, st));
+    RGQA_CUDA_OK(cudaStreamWaitEvent(sv, h->ev_fork, 0));
+    return 0;
+  };
+  auto join = [&]() -> int {
+    if (!two) return 0;
+    RGQA_CUDA_OK(cudaEventRecord(h->ev_join, sv));
+    RGQA_CUDA_OK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    return 0;
+  };
+  if (fork()) return 1;
+
   // ---- embeddings (modeling.py:876) ----
   if (embed_ln(st, dt, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, cur.act, res_copy_rows(h, cur, 0), B, L, H, c.vocab_size,
                c.max_position, c.type_vocab, c.ln_eps))
@@ -631,15 +663,15 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
     const void* a = feat;
     if (c.precision == RGQA_PREC_BF16) {
       if (feat_dtype == RGQA_DT_F32) {
-        if (cast_f32_to_bf16(st, static_cast<const float*>(feat), h->featb.p, Mv * c.visual_feat_dim)) return 1;
+        if (cast_f32_to_bf16(sv, static_cast<const float*>(feat), h->featb.p, Mv * c.visual_feat_dim)) return 1;
         a = h->featb.p;
       }
     } else {
       RGQA_CHECK(feat_dtype == RGQA_DT_F32, "fp32 path needs fp32 features");
     }
     float* pre = reinterpret_cast<float*>(rows_at(h->pre.p, Ml, H, 4));
-    if (gemm(h, st, a, c.visual_feat_dim, h->visn_fc, nullptr, 0, pre, H, 1, static_cast<int>(Mv), EPI_BIAS)) return 1;
-    if (visn_combine(st, dt, pre, pos, c.visual_pos_dim, h->box_W, h->box_b, h->visn_ln.g, h->visn_ln.b, h->box_ln.g,
+    if (gemm(h, sv, a, c.visual_feat_dim, h->visn_fc, nullptr, 0, pre, H, 1, static_cast<int>(Mv), EPI_BIAS)) return 1;
+    if (visn_combine(sv, dt, pre, pos, c.visual_pos_dim, h->box_W, h->box_b, h->visn_ln.g, h->visn_ln.b, h->box_ln.g,
                      h->box_ln.b, rows_at(cur.act, Ml, H, es), res_copy_rows(h, cur, Ml), static_cast<int>(Mv), H, c.ln_eps))
       return 1;
   }
@@ -650,9 +682,10 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
   }
   // ---- object-relational layers (modeling.py:557-558): rows [Ml, Mt), no key mask (entry.py:109) ----
   for (int i = 0; i < c.r_layers; ++i) {
-    if (att_block(h, st, h->r_layers[i].att, cur, alt, Ml, B, V, nullptr)) return 1;
-    if (ffn_block(h, st, h->r_layers[i].ffn, alt, cur, Ml, static_cast<int>(Mv))) return 1;
+    if (att_block(h, sv, h->r_layers[i].att, cur, alt, Ml, B, V, nullptr)) return 1;
+    if (ffn_block(h, sv, h->r_layers[i].ffn, alt, cur, Ml, static_cast<int>(Mv))) return 1;
   }
+  if (join()) return 1;
   // ---- cross-modality layers (modeling.py:477-488) ----
   for (int i = 0; i < c.x_layers; ++i) {
     const XLayerW& w = h->x_layers[i];
@@ -670,12 +703,13 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
                   3 * H, mask, rows_at(h->ctx.p, Ml, H, es), H, B, V, L, c.heads))
       return 1;
     if (dense_resid_ln(h, st, h->ctx.p, H, w.cross.out, w.cross.ln, cur, alt, 0, static_cast<int>(Mt))) return 1;
-    // self attention per stream (:461-465): alt -> cur
+    // self attention (:461-465, alt -> cur) and FFN (:467-475, cur -> alt) per modality, the two chains side by side
+    if (fork()) return 1;
     if (att_block(h, st, w.lang_self, alt, cur, 0, B, L, mask)) return 1;
-    if (att_block(h, st, w.visn_self, alt, cur, Ml, B, V, nullptr)) return 1;
-    // FFNs per stream (:467-475): cur -> alt
     if (ffn_block(h, st, w.lang_ffn, cur, alt, 0, static_cast<int>(Ml))) return 1;
-    if (ffn_block(h, st, w.visn_ffn, cur, alt, Ml, static_cast<int>(Mv))) return 1;
+    if (att_block(h, sv, w.visn_self, alt, cur, Ml, B, V, nullptr)) return 1;
+    if (ffn_block(h, sv, w.visn_ffn, cur, alt, Ml, static_cast<int>(Mv))) return 1;
+    if (join()) return 1;
     const Hid t = cur;
     cur = alt;
     alt = t;
@@ -836,6 +870,10 @@ int rgqa_set_option(const char* name, int value) {
   }
   if (strcmp(name, "gemm_staged") == 0) {
     option_set(OPT_GEMM_STAGED, value);
+    return 0;
+  }
+  if (strcmp(name, "two_streams") == 0) {
+    option_set(OPT_TWO_STREAMS, value);
     return 0;
   }
   if (strcmp(name, "gemm_ln") == 0) {

@@ -19,8 +19,11 @@
 //               pass 1  v = acc + bias + resid  -> back into TMEM, row sum
 //               pass 1b centred sum of squares (two-pass variance, like torch.nn.LayerNorm)
 //               pass 2  normalise, gamma/beta, store bf16 + fp32
-//               residual loads and both stores go through a per-warp 32 x 32 shared-memory transpose so that
-//               global accesses are row-contiguous (a thread owns a ROW; neighbouring lanes own different rows)
+//               The fp32 residual arrives by TMA: each warp owns a ring of three 4 KB buffers (32 rows x 32 fp32,
+//               128B-swizzled); the first three chunks of a tile are requested while its main loop still runs and
+//               every consumed buffer is refilled at once, so ~12 KB per warp stay in flight (a thread owns a ROW,
+//               neighbouring lanes own different rows: direct loads would be 32 lines per instruction AND one
+//               chunk deep).  Pass 2 reuses the buffers as a swizzled transpose so stores are row-contiguous.
 // The accumulator is single-buffered (384 of 512 columns): the next tile's MMAs wait for pass 2, its TMA loads
 // do not.  Rows >= M are zero-filled on load and never stored.
 #include <cuda.h>
@@ -41,8 +44,9 @@ constexpr int kStageBytes = kABytes + kNT * kBTileBytes;  // 56 KB
 constexpr int kStages = 3;
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = (4 + kEpiWarps) * 32;
-constexpr int kXposeBytes = 32 * 33 * 4;            // per-warp 32 x 32 fp32 transpose tile, padded
-constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * 2 * kXposeBytes + 128 * 4 + 1024 + 256;
+constexpr int kRing = 3;                            // residual / staging buffers per epilogue warp
+constexpr int kBufBytes = 32 * 128;                 // 32 rows x 32 fp32, 128B-swizzled (one TMA box)
+constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kRing * kBufBytes + 128 * 4 + 1024 + 512;
 
 struct LnParams {
   int M, K;
@@ -54,6 +58,7 @@ struct LnParams {
   float eps;
   __nv_bfloat16* out_act;
   float* out_res;  // may be null
+  int debug;       // measurement only: bit0 no pass-2 global stores, bit1 no pass 1b, bit2 no residual (zeros), bit3 no pass 2 at all
 };
 
 __device__ __forceinline__ void named_bar(int id, int threads) {
@@ -66,17 +71,19 @@ __device__ __forceinline__ int chunk_col(int c, int half) { return (c >> 2) * 25
 __device__ __forceinline__ uint32_t chunk_tcol(int c) { return static_cast<uint32_t>((c >> 2) * 128 + (c & 3) * 32); }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const LnParams p) {
+gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmRes, const LnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  float* xpose = reinterpret_cast<float*>(smem + kStages * kStageBytes);       // [kEpiWarps][2][32*33]
-  float* stats = xpose + kEpiWarps * 2 * (kXposeBytes / 4);                    // [128] per-lane partials
+  uint8_t* ring = smem + kStages * kStageBytes;  // [kEpiWarps][kRing][4 KB], 1024-aligned (stage size is 56 KB)
+  float* stats = reinterpret_cast<float*>(ring + kEpiWarps * kRing * kBufBytes);  // [128] per-lane partials
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stats + 128);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+  uint64_t* ring_bar = tmem_empty_bar + 1;  // [kEpiWarps][kRing]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ring_bar + kEpiWarps * kRing);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,6 +96,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmRes);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -97,6 +105,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     mbar_init(tmem_full_bar, 1);
     mbar_init(tmem_empty_bar, 2 * kEpiWarps);
+    for (int i = 0; i < kEpiWarps * kRing; ++i) mbar_init(&ring_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<512>(tmem_ptr_smem);
@@ -171,49 +180,54 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int tl = q * 32 + lane;           // TMEM lane of this thread
     const int half = tl >> 6;               // column half held by this lane
     const int r_local = tl & 63;            // row within the CTA's 64-row block
-    float* xp = xpose + q * 2 * (kXposeBytes / 4);  // two 32x33 tiles of this warp
+    uint8_t* my_ring = ring + q * kRing * kBufBytes;
+    uint64_t* my_bar = ring_bar + q * kRing;
     const uint32_t leader_tmem_empty = mapa_u32(smem_u32(tmem_empty_bar), 0);
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    // the 32 rows this warp owns, as seen by the coalesced side of the transpose: lane l handles
-    // row (l >> 3) + 4*i, 16-byte piece (l & 7) of a 128-byte (32 x fp32) row segment
+    // coalesced side of the staging transpose: lane l handles row (l >> 3) + 4*i, 16-byte piece (l & 7)
     const int crow = lane >> 3, cpiece = lane & 7;
+    const int sw = lane & 7;  // swizzle key of this thread's own row (row index within the 32-row buffer = lane)
+    uint32_t loads_issued = 0;  // residual chunks requested so far (buffer = n % kRing, parity = (n / kRing) & 1)
+    uint32_t loads_used = 0;
     int it = 0;
     for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
       const int row_base = t * (2 * kRowsPerCta) + static_cast<int>(rank) * kRowsPerCta + (q & 1) * 32;  // first row of this warp
       const int row = row_base + lane;
       (void)r_local;
+      auto issue_resid = [&](int c) {  // lane 0 only
+        const uint32_t b = loads_issued % kRing;
+        mbar_expect_tx(&my_bar[b], kBufBytes);
+        tma_load_2d(my_ring + b * kBufBytes, &tmRes, &my_bar[b], chunk_col(c, half), row_base);
+        ++loads_issued;
+      };
+      // the first kRing residual chunks fly while this tile's main loop is still running
+      if (lane == 0 && !(p.debug & 4)) {
+#pragma unroll
+        for (int c = 0; c < kRing; ++c) issue_resid(c);
+      }
       mbar_wait(tmem_full_bar, it & 1u);
       tc_fence_after();
 
       // ---------------- pass 1: v = acc + bias + resid -> TMEM, row sum ----------------
       float sum = 0.f;
-      float4 rpre[8];  // residual chunk in flight (coalesced layout)
-      auto load_resid = [&](int c) {
-        const int col = chunk_col(c, half) + cpiece * 4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = row_base + crow + 4 * i;
-          rpre[i] = r < p.M ? __ldg(reinterpret_cast<const float4*>(p.resid + static_cast<long long>(r) * p.ldr + col))
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      load_resid(0);
 #pragma unroll 1
       for (int c = 0; c < 12; ++c) {
         uint32_t v[32];
         tmem_ld32(t_lane + chunk_tcol(c), v);
-        // residual chunk c: registers -> smem (row-major 32 x 33) -> this thread's own row
-        float* tile = xp + (c & 1) * (kXposeBytes / 4);
+        const uint32_t b = loads_used % kRing;
+        float4 rr[8];
+        if (!(p.debug & 4)) {
+        mbar_wait(&my_bar[b], (loads_used / kRing) & 1u);
+        ++loads_used;
+        const uint8_t* rowp = my_ring + b * kBufBytes + lane * 128;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float* d = tile + (crow + 4 * i) * 33 + cpiece * 4;
-          d[0] = rpre[i].x;
-          d[1] = rpre[i].y;
-          d[2] = rpre[i].z;
-          d[3] = rpre[i].w;
+        for (int i = 0; i < 8; ++i) rr[i] = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 4));
+        __syncwarp();  // every lane has its row in registers: the buffer can be refilled
+        if (lane == 0 && c + kRing < 12) issue_resid(c + kRing);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        __syncwarp();
-        if (c + 1 < 12) load_resid(c + 1);
         tmem_ld_wait_dep(v);
         const int col0 = chunk_col(c, half);
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
@@ -221,11 +235,10 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 bb = __ldg(b4 + i);
-          const float* rr = tile + lane * 33 + 4 * i;
-          const float x0 = (__uint_as_float(v[4 * i + 0]) + bb.x) + rr[0];
-          const float x1 = (__uint_as_float(v[4 * i + 1]) + bb.y) + rr[1];
-          const float x2 = (__uint_as_float(v[4 * i + 2]) + bb.z) + rr[2];
-          const float x3 = (__uint_as_float(v[4 * i + 3]) + bb.w) + rr[3];
+          const float x0 = (__uint_as_float(v[4 * i + 0]) + bb.x) + rr[i].x;
+          const float x1 = (__uint_as_float(v[4 * i + 1]) + bb.y) + rr[i].y;
+          const float x2 = (__uint_as_float(v[4 * i + 2]) + bb.z) + rr[i].z;
+          const float x3 = (__uint_as_float(v[4 * i + 3]) + bb.w) + rr[i].w;
           sum += (x0 + x1) + (x2 + x3);
           w[4 * i + 0] = __float_as_uint(x0);
           w[4 * i + 1] = __float_as_uint(x1);
@@ -233,7 +246,6 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           w[4 * i + 3] = __float_as_uint(x3);
         }
         tmem_st32(t_lane + chunk_tcol(c), w);
-        __syncwarp();  // tile (c & 1) is rewritten two chunks later; all lanes are done reading it
       }
       tmem_st_wait();
       // row mean: the other column half of this row lives in lane tl ^ 64 (another warp)
@@ -245,39 +257,46 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // ---------------- pass 1b: centred sum of squares ----------------
       float sq = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 12; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_lane + chunk_tcol(c), v);
-        tmem_ld_wait_dep(v);
+      for (int c = 0; c < ((p.debug & 2) ? 0 : 12); c += 2) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(t_lane + chunk_tcol(c), v0);
+        tmem_ld32(t_lane + chunk_tcol(c + 1), v1);
+        tmem_ld_wait_dep(v0);
+        tmem_ld_wait_dep(v1);
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float d = __uint_as_float(v[i]) - mean;
-          sq = fmaf(d, d, sq);
+          const float d0 = __uint_as_float(v0[i]) - mean, d1 = __uint_as_float(v1[i]) - mean;
+          s0 = fmaf(d0, d0, s0);
+          s1 = fmaf(d1, d1, s1);
         }
+        sq += s0 + s1;
       }
       stats[tl] = sq;
       named_bar(1, kEpiWarps * 32);
       const float rstd = 1.0f / sqrtf((sq + stats[tl ^ 64]) * (1.0f / N_LN) + p.eps);
       named_bar(1, kEpiWarps * 32);
 
-      // ---------------- pass 2: normalise, gamma/beta, coalesced bf16 + fp32 stores ----------------
+      // ---------------- pass 2: normalise, gamma/beta, row-contiguous bf16 + fp32 stores ----------------
 #pragma unroll 1
-      for (int c = 0; c < 12; ++c) {
+      for (int c = 0; c < ((p.debug & 8) ? 0 : 12); ++c) {
         uint32_t v[32];
         tmem_ld32(t_lane + chunk_tcol(c), v);
         tmem_ld_wait_dep(v);
         const int col0 = chunk_col(c, half);
         const float4* g4 = reinterpret_cast<const float4*>(p.gamma + col0);
         const float4* e4 = reinterpret_cast<const float4*>(p.beta + col0);
-        float* tile = xp + (c & 1) * (kXposeBytes / 4);
+        uint8_t* buf = my_ring + (c % kRing) * kBufBytes;  // all residual chunks of this tile are consumed
+        uint8_t* rowp = buf + lane * 128;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 gg = __ldg(g4 + i), ee = __ldg(e4 + i);
-          float* d = tile + lane * 33 + 4 * i;
-          d[0] = (__uint_as_float(v[4 * i + 0]) - mean) * rstd * gg.x + ee.x;
-          d[1] = (__uint_as_float(v[4 * i + 1]) - mean) * rstd * gg.y + ee.y;
-          d[2] = (__uint_as_float(v[4 * i + 2]) - mean) * rstd * gg.z + ee.z;
-          d[3] = (__uint_as_float(v[4 * i + 3]) - mean) * rstd * gg.w + ee.w;
+          float4 y;
+          y.x = (__uint_as_float(v[4 * i + 0]) - mean) * rstd * gg.x + ee.x;
+          y.y = (__uint_as_float(v[4 * i + 1]) - mean) * rstd * gg.y + ee.y;
+          y.z = (__uint_as_float(v[4 * i + 2]) - mean) * rstd * gg.z + ee.z;
+          y.w = (__uint_as_float(v[4 * i + 3]) - mean) * rstd * gg.w + ee.w;
+          *reinterpret_cast<float4*>(rowp + ((i ^ sw) << 4)) = y;
         }
         __syncwarp();
         const int col = col0 + cpiece * 4;
@@ -285,9 +304,8 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int i = 0; i < 8; ++i) {
           const int rl = crow + 4 * i;
           const int r = row_base + rl;
-          const float* sft = tile + rl * 33 + cpiece * 4;
-          const float4 y = make_float4(sft[0], sft[1], sft[2], sft[3]);
-          if (r < p.M) {
+          const float4 y = *reinterpret_cast<const float4*>(buf + rl * 128 + ((cpiece ^ (rl & 7)) << 4));
+          if (r < p.M && !(p.debug & 1)) {
             if (p.out_res != nullptr) *reinterpret_cast<float4*>(p.out_res + static_cast<long long>(r) * N_LN + col) = y;
             uint2 o;
             o.x = pack_bf16x2(y.x, y.y);
@@ -295,8 +313,10 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             *reinterpret_cast<uint2*>(p.out_act + static_cast<long long>(r) * N_LN + col) = o;
           }
         }
-        __syncwarp();
+        __syncwarp();  // buffer (c % kRing) is rewritten kRing chunks later (or refilled by the TMA next tile)
       }
+      fence_proxy_async_smem();  // staging writes (generic proxy) before the next tile's TMA refills these buffers
+      __syncwarp();
       (void)row;
       // accumulators fully consumed: let the leader start the next tile's MMAs
       tc_fence_before();
@@ -325,9 +345,10 @@ int gemm_bf16_ln(cudaStream_t stream, const void* A, long long lda, const void* 
                  (reinterpret_cast<uintptr_t>(bias) % 16 == 0) && (reinterpret_cast<uintptr_t>(gamma) % 16 == 0) &&
                  (reinterpret_cast<uintptr_t>(beta) % 16 == 0),
              "gemm_bf16_ln: operands must be 16-byte aligned");
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmRes;
   if (make_tmap(&tmA, A, M, K, lda, kRowsPerCta, 2)) return 1;
   if (make_tmap(&tmB, W, N, K, ldw, 128, 2)) return 1;
+  if (make_tmap(&tmRes, resid, M, N, ldr, 32, 4)) return 1;  // box: 32 rows x 32 fp32 (128 B), 128B swizzle
   LnParams p;
   p.M = M;
   p.K = K;
@@ -339,6 +360,7 @@ int gemm_bf16_ln(cudaStream_t stream, const void* A, long long lda, const void* 
   p.eps = eps;
   p.out_act = static_cast<__nv_bfloat16*>(out_act);
   p.out_res = out_res;
+  p.debug = option_get(OPT_GEMM_DEBUG);
   static bool configured = false;
   if (!configured) {
     RGQA_CUDA_OK(cudaFuncSetAttribute(gemm_ln_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -348,7 +370,7 @@ int gemm_bf16_ln(cudaStream_t stream, const void* A, long long lda, const void* 
   const int max_pairs = num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   void* tok = prof_begin(stream);
-  gemm_ln_pair_kernel<<<2 * pairs, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+  gemm_ln_pair_kernel<<<2 * pairs, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmRes, p);
   prof_end(tok, stream, 2.0 * M * static_cast<double>(N) * K, PROF_GEMM_TC);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());

@@ -25,4 +25,10 @@ for name, M, K in [("attn-out lang", 20480, 768), ("attn-out visn", 36864, 768),
         ops.layernorm(pre, g, b, out_dtype=torch.bfloat16)
     t_2 = timeit(two)
     fl = 2.0 * M * N * K
+    if os.environ.get("PROBE"):
+        lib = L.load()
+        for dbg in (1, 2, 4, 8, 15):
+            lib.rgqa_set_option(b"gemm_debug", dbg)
+            print(f"    debug={dbg:2d} (1 no stores, 2 no pass1b, 4 no resid, 8 no pass2): {timeit(lambda: ops.linear_residual_layernorm_bf16(a, w, bias, resid, g, b))*1e3:7.1f} us")
+        lib.rgqa_set_option(b"gemm_debug", 0)
     print(f"{name:15s} M={M:6d} K={K:5d}: fused {t_f*1e3:7.1f} us ({fl/t_f/1e9:6.0f} TF/s) | gemm+ln {t_2*1e3:7.1f} us")
