@@ -369,21 +369,26 @@ constexpr int kPairStageBytes = BM * BK * 2 + (kPairBN / 2) * BK * 2;  // 16 KB 
 // RESID_SMEM (staged EPI_RESID with fp32 output): the residual slab is TMA-LOADED into the very buffer the
 // output is staged in — each thread reads its own row of it, adds, and writes the sum back in place — so both
 // the residual read and the pre-LayerNorm write are full-line bulk copies; 3 buffers per half, 2-deep prefetch.
-template <bool STAGED, bool RESID_SMEM>
+// EW = number of epilogue warps (8 or 16).  Warps come in groups of four (one per TMEM lane quarter); a group owns
+// 256 / (EW/4) columns of the tile.  16 warps (bf16 outputs): each group stages exactly one 64-column slab per
+// tile, so one buffer per group suffices and the erf-GELU math gets four warps per scheduler instead of two.
+template <bool STAGED, bool RESID_SMEM, int EW>
 struct PairCfg {
+  static constexpr int kGroups = EW / 4;
   static constexpr int kStages = RESID_SMEM ? 4 : (STAGED ? 5 : 6);
-  static constexpr int kBufsPerHalf = RESID_SMEM ? 3 : (STAGED ? 2 : 0);
-  static constexpr int kSlabRegion = 2 * kBufsPerHalf * kSlabBytes;
+  static constexpr int kBufsPerGroup = RESID_SMEM ? 3 : (STAGED ? (EW == 16 ? 1 : 2) : 0);
+  static constexpr int kSlabRegion = kGroups * kBufsPerGroup * kSlabBytes;
   static constexpr int kSmemBytes = kStages * kPairStageBytes + kSlabRegion + 1024 + 256;
 };
 
-template <int EPI, typename OutT, bool STAGED>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+template <int EPI, typename OutT, bool STAGED, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + EW) * 32, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                       const GemmParams p) {
   constexpr bool kResidSmem = STAGED && EPI == EPI_RESID && sizeof(OutT) == 4;
-  using PC = PairCfg<STAGED, kResidSmem>;
+  static_assert(EW == 8 || (EW == 16 && STAGED && !kResidSmem), "16 epilogue warps: staged, non-residual epilogues only");
+  using PC = PairCfg<STAGED, kResidSmem, EW>;
   constexpr int kStages = PC::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -420,7 +425,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 2 * kNumEpiWarps);  // epilogue warps of both CTAs
+      mbar_init(&tmem_empty_bar[a], 2 * EW);  // epilogue warps of both CTAs
     }
     for (int i = 0; i < 6; ++i) mbar_init(&resid_bar[i], 1);
     fence_barrier_init();
@@ -495,8 +500,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
     const int e = warp - 4;
     const int quarter = e & 3;
-    const int half = e >> 2;
-    constexpr int kColsPerWarp = kPairBN / 2;
+    const int half = e >> 2;  // column group of this warp: 0..EW/4-1 ("half" when EW == 8)
+    constexpr int kColsPerWarp = kPairBN / (EW / 4);
     const uint32_t leader_tmem_empty0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t leader_tmem_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
     [[maybe_unused]] const bool issuer = (quarter == 0 && lane == 0);
@@ -597,8 +602,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int sl = 0; sl < kSlabsPerHalf; ++sl) {
           const int col_slab = n0 + half * kColsPerWarp + sl * kColsPerSlab;
           if (col_slab >= p.N) break;  // uniform over the 4 warps of this half
-          uint8_t* buf = slabs + (half * 2 + (slab_ctr & 1)) * kSlabBytes;
-          if (issuer) tma_store_wait_read<1>();  // the store that last read this buffer (2 slabs ago) is done with it
+          constexpr int kBufs = PC::kBufsPerGroup;
+          uint8_t* buf = slabs + (half * kBufs + (slab_ctr % kBufs)) * kSlabBytes;
+          if (issuer) tma_store_wait_read<kBufs - 1>();  // the store that last read this buffer is done with it
           named_bar_sync(1 + half, 128);
           // both 32-column chunks of the slab are requested from TMEM before either is consumed
           uint32_t v[kChunksPerSlab][32];
@@ -741,8 +747,11 @@ int dispatch_epi(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, con
 template <int EPI, typename OutT, bool STAGED>
 int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                 const CUtensorMap& tmRes, const GemmParams& p) {
-  auto kern = gemm_bf16_pair_kernel<EPI, OutT, STAGED>;
-  constexpr int smem = PairCfg<STAGED, (STAGED && EPI == EPI_RESID && sizeof(OutT) == 4)>::kSmemBytes;
+  // 16 epilogue warps were measured on B200 (bf16 outputs): FFN1 1043 vs 1056 TFLOP/s, QKV 1180 vs 1274 — no gain,
+  // the erf-GELU epilogue is bound by its dependent FMA/MUFU chains, not by warps in flight.  8 it is.
+  constexpr int EW = 8;
+  auto kern = gemm_bf16_pair_kernel<EPI, OutT, STAGED, EW>;
+  constexpr int smem = PairCfg<STAGED, (STAGED && EPI == EPI_RESID && sizeof(OutT) == 4), EW>::kSmemBytes;
   static bool configured = false;
   if (!configured) {
     RGQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -752,7 +761,7 @@ int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& 
   const int max_pairs = num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   void* tok = prof_begin(stream);
-  RGQA_CUDA_OK(launch_pdl(kern, dim3(2 * pairs), dim3(kNumThreads), smem, stream, tmA, tmB, tmOut, tmRes, p));
+  RGQA_CUDA_OK(launch_pdl(kern, dim3(2 * pairs), dim3((4 + EW) * 32), smem, stream, tmA, tmB, tmOut, tmRes, p));
   prof_end(tok, stream, 2.0 * p.M * static_cast<double>(p.N) * p.K, PROF_GEMM_TC);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
