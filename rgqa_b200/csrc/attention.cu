@@ -146,6 +146,8 @@ attention_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__ k
 // the A operand of P·V, V^T fragments fetched with ldmatrix.trans.  Keys are padded to 16*KS with
 // zero rows (score -inf, probability 0); masked keys get the reference's additive -10000.
 // ------------------------------------------------------------------------------------------------
+constexpr float kLog2e = 1.44269504088896340736f;
+constexpr float kScaleLog2e = 0.125f * kLog2e;
 constexpr int kLds = 72;  // smem row stride in bf16: 144 B -> the 8 rows of a fragment load hit 32 distinct banks
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -160,6 +162,11 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -204,7 +211,7 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const _
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int key = 8 * j + 2 * t + e;
-      madd[j][e] = key >= Lk ? -INFINITY : ((key_mask != nullptr && key_mask[b * Lk + key] == 0) ? -10000.f : 0.f);
+      madd[j][e] = key >= Lk ? -INFINITY : ((key_mask != nullptr && key_mask[b * Lk + key] == 0) ? -10000.f * kLog2e : 0.f);
     }
 
   // Q fragments come straight from global memory (4 B per lane); the next tile's are requested before the
@@ -234,22 +241,25 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const _
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      const __nv_bfloat16* kr = Ks + (8 * j + g) * kLds + 2 * t;
+      // one ldmatrix.x4 = the (b0, b1) fragments of two 16-wide k-steps for these 8 keys
+      const __nv_bfloat16* kr = Ks + (8 * j + (lane & 7)) * kLds + 8 * (lane >> 3);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
-        mma_bf16_16816(s[j], qa[ks], b0, b1);
+      for (int kp = 0; kp < 2; ++kp) {
+        uint32_t kb[4];
+        ldmatrix_x4(kb, kr + kp * 32);
+        mma_bf16_16816(s[j], qa[2 * kp], kb[0], kb[1]);
+        mma_bf16_16816(s[j], qa[2 * kp + 1], kb[2], kb[3]);
       }
     }
     // scores / sqrt(64) + additive mask (modeling.py:333-336); row max over this row's 8*NT keys
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      s[j][0] = s[j][0] * 0.125f + madd[j][0];
-      s[j][1] = s[j][1] * 0.125f + madd[j][1];
-      s[j][2] = s[j][2] * 0.125f + madd[j][0];
-      s[j][3] = s[j][3] * 0.125f + madd[j][1];
+      // (q.k / 8 + mask) * log2(e): the softmax below is then a bare ex2
+      s[j][0] = fmaf(s[j][0], kScaleLog2e, madd[j][0]);
+      s[j][1] = fmaf(s[j][1], kScaleLog2e, madd[j][1]);
+      s[j][2] = fmaf(s[j][2], kScaleLog2e, madd[j][0]);
+      s[j][3] = fmaf(s[j][3], kScaleLog2e, madd[j][1]);
       mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
       mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
     }
@@ -261,8 +271,8 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const _
     uint32_t pa[KS][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      const float p0 = __expf(s[j][0] - mx0), p1 = __expf(s[j][1] - mx0);
-      const float p2 = __expf(s[j][2] - mx1), p3 = __expf(s[j][3] - mx1);
+      const float p0 = exp2f(s[j][0] - mx0), p1 = exp2f(s[j][1] - mx0);
+      const float p2 = exp2f(s[j][2] - mx1), p3 = exp2f(s[j][3] - mx1);
       sum0 += p0 + p1;
       sum1 += p2 + p3;
       // accumulator tiles (2ks, 2ks+1) of S are exactly the A fragment of k-step ks of P·V
