@@ -372,11 +372,16 @@ constexpr int kPairStageBytes = BM * BK * 2 + (kPairBN / 2) * BK * 2;  // 16 KB 
 // EW = number of epilogue warps (8 or 16).  Warps come in groups of four (one per TMEM lane quarter); a group owns
 // 256 / (EW/4) columns of the tile.  16 warps (bf16 outputs): each group stages exactly one 64-column slab per
 // tile, so one buffer per group suffices and the erf-GELU math gets four warps per scheduler instead of two.
+// residual-in-smem epilogue: ring depth per column half (prefetch distance = ring - 1) and main-loop stages
+// (ring 4 / 3 stages was measured: O-proj 68.5 vs 66.4 us, FFN2 166.9 vs 145.3 us — the K = 3072 main loop needs
+// its 4 stages more than the epilogue needs a deeper residual prefetch)
+constexpr int kResidRing = 3;
+constexpr int kResidStages = 4;
 template <bool STAGED, bool RESID_SMEM, int EW>
 struct PairCfg {
   static constexpr int kGroups = EW / 4;
-  static constexpr int kStages = RESID_SMEM ? 4 : (STAGED ? 5 : 6);
-  static constexpr int kBufsPerGroup = RESID_SMEM ? 3 : (STAGED ? (EW == 16 ? 1 : 2) : 0);
+  static constexpr int kStages = RESID_SMEM ? kResidStages : (STAGED ? 5 : 6);
+  static constexpr int kBufsPerGroup = RESID_SMEM ? kResidRing : (STAGED ? (EW == 16 ? 1 : 2) : 0);
   static constexpr int kSlabRegion = kGroups * kBufsPerGroup * kSlabBytes;
   static constexpr int kSmemBytes = kStages * kPairStageBytes + kSlabRegion + 1024 + 256;
 };
@@ -398,8 +403,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* resid_bar = tmem_empty_bar + 2;  // [2 halves][3 buffers], used by the RESID_SMEM epilogue only
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(resid_bar + 6);
+  uint64_t* resid_bar = tmem_empty_bar + 2;  // [2 halves][kResidRing], used by the RESID_SMEM epilogue only
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(resid_bar + 2 * kResidRing);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -427,7 +432,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 2 * EW);  // epilogue warps of both CTAs
     }
-    for (int i = 0; i < 6; ++i) mbar_init(&resid_bar[i], 1);
+    for (int i = 0; i < 2 * kResidRing; ++i) mbar_init(&resid_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<512>(tmem_ptr_smem);
@@ -519,13 +524,14 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       auto issue_load = [&](int k) {
         int row0, col;
         coords(k, row0, col);
-        const int b = k % 3;
-        mbar_expect_tx(&resid_bar[half * 3 + b], kSlabBytes);
-        tma_load_2d(slabs + (half * 3 + b) * kSlabBytes, &tmRes, &resid_bar[half * 3 + b], col, row0);
+        const int b = k % kResidRing;
+        mbar_expect_tx(&resid_bar[half * kResidRing + b], kSlabBytes);
+        tma_load_2d(slabs + (half * kResidRing + b) * kSlabBytes, &tmRes, &resid_bar[half * kResidRing + b], col, row0);
       };
       if (issuer) {
         if (total > 0) issue_load(0);
-        if (total > 1) issue_load(1);
+        for (int j = 1; j < kResidRing - 1; ++j)
+          if (total > j) issue_load(j);
       }
       for (int k = 0; k < total; ++k) {
         const int itile = k >> 2, sl = k & 3;
@@ -537,12 +543,12 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_wait(&tmem_full_bar[acc], (itile >> 1) & 1u);
           tc_fence_after();
         }
-        const int b = k % 3;
-        uint8_t* buf = slabs + (half * 3 + b) * kSlabBytes;
+        const int b = k % kResidRing;
+        uint8_t* buf = slabs + (half * kResidRing + b) * kSlabBytes;
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                       static_cast<uint32_t>(acc * kPairBN + half * kColsPerWarp + sl * 32), v);
-        mbar_wait(&resid_bar[half * 3 + b], (k / 3) & 1u);  // this slab's residual rows have landed
+        mbar_wait(&resid_bar[half * kResidRing + b], (k / kResidRing) & 1u);  // this slab's residual rows have landed
         tmem_ld_wait_dep(v);
         float f[32];
         {
@@ -572,9 +578,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (issuer) {
           if (row0 < p.M) tma_store_2d(&tmOut, buf, col, row0);
           tma_store_commit();
-          if (k + 2 < total) {
+          if (k + kResidRing - 1 < total) {
             tma_store_wait_read<1>();  // the store of slab k-1 has drained the buffer slab k+2 will land in
-            issue_load(k + 2);
+            issue_load(k + kResidRing - 1);
           }
         }
       }
