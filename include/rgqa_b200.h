@@ -121,7 +121,8 @@ int rgqa_score(rgqa_handle* h, void* stream, int mode, const float* logits, cons
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------- */
 /* Kernel-selection switches for A/B measurements: "gemm_pair" (1 = CTA-pair tcgen05 kernel when
  * M >= 1024), "gemm_staged" (1 = swizzled-smem + TMA-store epilogue in the pair kernel), "gemm_ln" (1 = fused
- * GEMM + residual + LayerNorm kernel), "two_streams" (1 = visual branch on a second stream), "pdl", "gemm_debug". */
+ * GEMM + residual + LayerNorm kernel), "two_streams" (1 = visual branch on a second stream), "graphs" (1 = CUDA-graph replay of the forward for
+ * B <= 128), "pdl", "gemm_debug". */
 int rgqa_set_option(const char* name, int value);
 /* Kernels enqueued by this library since it was loaded. */
 long long rgqa_launch_count(void);

@@ -98,6 +98,8 @@ struct XLayerW {
 
 using namespace rgqa;
 
+struct rgqa_handle;
+
 struct rgqa_handle {
   rgqa_config cfg;
   std::vector<std::string> names;           // expected reference keys
@@ -122,7 +124,17 @@ struct rgqa_handle {
 
   // second stream for the visual branch (language / visual layers are independent between joins)
   cudaStream_t side = nullptr;
+  cudaStream_t cap = nullptr;  // capture stream for the small-batch CUDA graphs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+
+  // CUDA graphs of the whole forward for small batches, keyed by shape
+  struct GraphEntryT {
+    int seen = 0;
+    int kernels = 0;
+    cudaGraphExec_t exec = nullptr;
+    DevBuf feat, pos, ids, seg, mask, pooled, logits;
+  };
+  std::map<long long, GraphEntryT> graphs;
 
   // workspace
   DevBuf hidA, hidB, resA, resB, qkv, ctx, inter, pre, featb, headbuf, mahabuf;
@@ -394,9 +406,24 @@ int ffn_block(rgqa_handle* h, cudaStream_t st, const FfnW& w, const Hid& in, con
   return dense_resid_ln(h, st, inter, I, w.out, w.ln, in, out, r0, M);
 }
 
+void drop_graphs(rgqa_handle* h) {  // captured graphs bake workspace / weight pointers: any reallocation voids them
+  for (auto& kv : h->graphs) {
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    kv.second.exec = nullptr;
+  }
+}
+
 int ensure_workspace(rgqa_handle* h, long long Mt, long long Mv, int B) {
   const int H = h->cfg.hidden, I = h->cfg.intermediate;
   const size_t es = act_size(h);
+  const void* before[4] = {h->hidA.p, h->qkv.p, h->inter.p, h->headbuf.p};
+  struct Guard {
+    rgqa_handle* h;
+    const void* const* b;
+    ~Guard() {
+      if (b[0] != h->hidA.p || b[1] != h->qkv.p || b[2] != h->inter.p || b[3] != h->headbuf.p) drop_graphs(h);
+    }
+  } guard{h, before};
   if (h->hidA.ensure(Mt * H * es) || h->hidB.ensure(Mt * H * es) || h->qkv.ensure(Mt * 3 * H * es) ||
       h->ctx.ensure(Mt * H * es) || h->inter.ensure(Mt * I * es) || h->pre.ensure(Mt * H * 4))
     return 1;
@@ -475,6 +502,12 @@ void rgqa_destroy(rgqa_handle* h) {
   for (auto& kv : h->raw)
     if (kv.second.p != nullptr) cudaFree(kv.second.p);
   for (void* p : h->owned) cudaFree(p);
+  for (auto& kv : h->graphs) {
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    kv.second.feat.release(); kv.second.pos.release(); kv.second.ids.release(); kv.second.seg.release();
+    kv.second.mask.release(); kv.second.pooled.release(); kv.second.logits.release();
+  }
+  if (h->cap) cudaStreamDestroy(h->cap);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -537,6 +570,7 @@ int rgqa_finalize_weights(rgqa_handle* h) {
   RGQA_CHECK(h != nullptr, "rgqa_finalize_weights: null handle");
   for (const auto& n : h->names)
     RGQA_CHECK(h->raw.count(n) == 1, "rgqa_finalize_weights: missing tensor '%s'", n.c_str());
+  drop_graphs(h);
   for (void* p : h->owned) cudaFree(p);
   h->owned.clear();
   h->l_layers.clear();
@@ -607,17 +641,9 @@ int rgqa_finalize_weights(rgqa_handle* h) {
   return 0;
 }
 
-int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos,
-                        const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
-                        float* pooled_out, float* logits_out) {
-  RGQA_CHECK(h != nullptr, "rgqa_lxmert_forward: null handle");
-  RGQA_CHECK(h->cfg.arch == RGQA_ARCH_LXMERT, "rgqa_lxmert_forward: handle was created for another architecture");
-  RGQA_CHECK(h->finalized, "rgqa_lxmert_forward: weights are not finalized");
-  RGQA_CHECK(feat != nullptr && pos != nullptr && ids != nullptr && mask != nullptr, "rgqa_lxmert_forward: null input");
-  RGQA_CHECK(B > 0, "rgqa_lxmert_forward: empty batch");
-  RGQA_CHECK(L >= 2 && L <= 64, "rgqa_lxmert_forward: L=%d out of range [2,64]", L);
-  RGQA_CHECK(logits_out == nullptr || h->cfg.num_answers > 0, "rgqa_lxmert_forward: handle has no answer head");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int lxmert_forward_impl(rgqa_handle* h, cudaStream_t st, const void* feat, int feat_dtype, const float* pos,
+                               const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
+                               float* pooled_out, float* logits_out) {
   const rgqa_config& c = h->cfg;
   const int H = c.hidden, V = c.num_rois;
   const long long Ml = static_cast<long long>(B) * L, Mv = static_cast<long long>(B) * V, Mt = Ml + Mv;
@@ -717,6 +743,78 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
   // ---- pooler + answer head (modeling.py:884, gqa_model.py:40-41) ----
   if (pooled_out == nullptr && logits_out == nullptr) return 0;
   return head_block(h, st, cur.act, B, L, pooled_out, logits_out);
+}
+
+// Small batches are launch-bound (207 kernels + 330 tensor-map encodes per forward: ~3 ms of host time at B = 32, the
+// reference scripts' default batch size).  For B <= 128 the whole forward is captured ONCE per (B, L, dtype, outputs)
+// into a CUDA graph over handle-owned staging buffers; later calls are: copy inputs in, one graph launch, copy outputs
+// out.  The first call of a shape runs eagerly (lazy per-kernel attribute setup must not happen under capture).
+int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos,
+                        const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
+                        float* pooled_out, float* logits_out) {
+  RGQA_CHECK(h != nullptr, "rgqa_lxmert_forward: null handle");
+  RGQA_CHECK(h->cfg.arch == RGQA_ARCH_LXMERT, "rgqa_lxmert_forward: handle was created for another architecture");
+  RGQA_CHECK(h->finalized, "rgqa_lxmert_forward: weights are not finalized");
+  RGQA_CHECK(feat != nullptr && pos != nullptr && ids != nullptr && mask != nullptr, "rgqa_lxmert_forward: null input");
+  RGQA_CHECK(B > 0, "rgqa_lxmert_forward: empty batch");
+  RGQA_CHECK(L >= 2 && L <= 64, "rgqa_lxmert_forward: L=%d out of range [2,64]", L);
+  RGQA_CHECK(logits_out == nullptr || h->cfg.num_answers > 0, "rgqa_lxmert_forward: handle has no answer head");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool use_graph = option_get(OPT_GRAPHS) != 0 && B <= 128 && !prof_on();
+  if (!use_graph)
+    return lxmert_forward_impl(h, st, feat, feat_dtype, pos, ids, seg, mask, B, L, pooled_out, logits_out);
+
+  const rgqa_config& c = h->cfg;
+  const long long key = (static_cast<long long>(B) << 20) | (static_cast<long long>(L) << 8) | (feat_dtype << 4) |
+                        ((seg != nullptr) << 2) | ((pooled_out != nullptr) << 1) | (logits_out != nullptr);
+  rgqa_handle::GraphEntryT& g = h->graphs[key];
+  const size_t fe = feat_dtype == RGQA_DT_F32 ? 4 : 2;
+  const size_t n_feat = static_cast<size_t>(B) * c.num_rois * c.visual_feat_dim * fe;
+  const size_t n_pos = static_cast<size_t>(B) * c.num_rois * c.visual_pos_dim * 4;
+  const size_t n_ids = static_cast<size_t>(B) * L * 4;
+  if (g.seen == 0) {  // first sight of this shape: eager run (also grows the workspace), capture on the next call
+    g.seen = 1;
+    return lxmert_forward_impl(h, st, feat, feat_dtype, pos, ids, seg, mask, B, L, pooled_out, logits_out);
+  }
+  if (g.exec == nullptr) {
+    if (g.feat.ensure(n_feat) || g.pos.ensure(n_pos) || g.ids.ensure(n_ids) || g.seg.ensure(n_ids) || g.mask.ensure(n_ids) ||
+        g.pooled.ensure(static_cast<size_t>(B) * c.hidden * 4) ||
+        g.logits.ensure(static_cast<size_t>(B) * (c.num_answers > 0 ? c.num_answers : 1) * 4))
+      return 1;
+    cudaGraph_t graph = nullptr;
+    const long long n0 = launch_count();
+    // capture on a handle-owned stream: the caller's stream is usually the legacy default stream, which cannot capture
+    if (h->cap == nullptr) RGQA_CUDA_OK(cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking));
+    RGQA_CUDA_OK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal));
+    const int rc = lxmert_forward_impl(h, h->cap, g.feat.p, feat_dtype, static_cast<const float*>(g.pos.p),
+                                       static_cast<const int32_t*>(g.ids.p),
+                                       seg != nullptr ? static_cast<const int32_t*>(g.seg.p) : nullptr,
+                                       static_cast<const int32_t*>(g.mask.p), B, L,
+                                       pooled_out != nullptr ? static_cast<float*>(g.pooled.p) : nullptr,
+                                       logits_out != nullptr ? static_cast<float*>(g.logits.p) : nullptr);
+    const cudaError_t ce = cudaStreamEndCapture(h->cap, &graph);
+    g.kernels = static_cast<int>(launch_count() - n0);
+    note_launch(-g.kernels);  // captured, not launched: each replay is counted below
+    if (rc != 0) {
+      if (graph) cudaGraphDestroy(graph);
+      return 1;
+    }
+    RGQA_CUDA_OK(ce);
+    RGQA_CUDA_OK(cudaGraphInstantiate(&g.exec, graph, 0));
+    RGQA_CUDA_OK(cudaGraphDestroy(graph));
+  }
+  RGQA_CUDA_OK(cudaMemcpyAsync(g.feat.p, feat, n_feat, cudaMemcpyDeviceToDevice, st));
+  RGQA_CUDA_OK(cudaMemcpyAsync(g.pos.p, pos, n_pos, cudaMemcpyDeviceToDevice, st));
+  RGQA_CUDA_OK(cudaMemcpyAsync(g.ids.p, ids, n_ids, cudaMemcpyDeviceToDevice, st));
+  if (seg != nullptr) RGQA_CUDA_OK(cudaMemcpyAsync(g.seg.p, seg, n_ids, cudaMemcpyDeviceToDevice, st));
+  RGQA_CUDA_OK(cudaMemcpyAsync(g.mask.p, mask, n_ids, cudaMemcpyDeviceToDevice, st));
+  RGQA_CUDA_OK(cudaGraphLaunch(g.exec, st));
+  note_launch(g.kernels);
+  if (pooled_out != nullptr)
+    RGQA_CUDA_OK(cudaMemcpyAsync(pooled_out, g.pooled.p, static_cast<size_t>(B) * c.hidden * 4, cudaMemcpyDeviceToDevice, st));
+  if (logits_out != nullptr)
+    RGQA_CUDA_OK(cudaMemcpyAsync(logits_out, g.logits.p, static_cast<size_t>(B) * c.num_answers * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
 }
 
 int rgqa_uniter_forward(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos7,
@@ -870,6 +968,10 @@ int rgqa_set_option(const char* name, int value) {
   }
   if (strcmp(name, "gemm_staged") == 0) {
     option_set(OPT_GEMM_STAGED, value);
+    return 0;
+  }
+  if (strcmp(name, "graphs") == 0) {
+    option_set(OPT_GRAPHS, value);
     return 0;
   }
   if (strcmp(name, "two_streams") == 0) {

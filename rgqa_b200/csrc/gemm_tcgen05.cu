@@ -808,8 +808,16 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
   RGQA_CHECK(M > 0 && N > 0 && K > 0, "gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   RGQA_CHECK(K % BK == 0, "gemm_bf16: K=%d must be a multiple of %d", K, BK);
   RGQA_CHECK(epi != EPI_RESID || resid != nullptr, "gemm_bf16: EPI_RESID needs a residual pointer");
-  // Tile width: 256 when it does not waste more than a quarter of the last N tile, else 128.
-  const int bn = (N % 256 == 0 || N >= 1024) ? 256 : 128;
+  // Tile width: 256 when it does not waste more than a quarter of the last N tile, else 128; small problems
+  // (B = 32: 5-14 row tiles) shrink the tile further so that more than a handful of SMs get a CTA.
+  int bn = (N % 256 == 0 || N >= 1024) ? 256 : 128;
+  {
+    const int tm = (M + BM - 1) / BM;
+    if (M < 1024) {
+      if (tm * ((N + bn - 1) / bn) < 96 && bn > 128) bn = 128;
+      if (tm * ((N + bn - 1) / bn) < 96 && bn > 64) bn = 64;
+    }
+  }
   // CTA pairs (256-row MMA, half the W traffic per CTA) once there are enough 256-row tiles to go round
   const bool use_pair = option_get(OPT_GEMM_PAIR) != 0 && bn == 256 && M >= 1024;
   const int esz = out_f32 ? 4 : 2;
@@ -844,8 +852,9 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
   p.vec_ok = (out_al && res_al && bias_al) ? 1 : 0;
   p.debug = option_get(OPT_GEMM_DEBUG);
   if (use_pair) return dispatch_pair(stream, tmA, tmB, tmOut, tmRes, p, epi, out_f32, staged);
-  return bn == 256 ? dispatch_epi<256>(stream, tmA, tmB, p, epi, out_f32)
-                   : dispatch_epi<128>(stream, tmA, tmB, p, epi, out_f32);
+  if (bn == 256) return dispatch_epi<256>(stream, tmA, tmB, p, epi, out_f32);
+  if (bn == 128) return dispatch_epi<128>(stream, tmA, tmB, p, epi, out_f32);
+  return dispatch_epi<64>(stream, tmA, tmB, p, epi, out_f32);
 }
 
 }  // namespace rgqa

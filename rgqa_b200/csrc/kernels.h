@@ -88,7 +88,7 @@ int rowdot(cudaStream_t stream, const float* a, const float* b, float* out, int 
 
 
 // ---- runtime options (prof.cu): kernel-selection switches for A/B measurements ---------------------
-enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_GEMM_DEBUG = 2, OPT_PDL = 3, OPT_GEMM_LN = 4, OPT_TWO_STREAMS = 5, OPT_COUNT = 8 };
+enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_GEMM_DEBUG = 2, OPT_PDL = 3, OPT_GEMM_LN = 4, OPT_TWO_STREAMS = 5, OPT_GRAPHS = 6, OPT_COUNT = 8 };
 int option_get(int key);
 void option_set(int key, int value);
 

@@ -176,3 +176,32 @@ def test_engine_error_paths(cuda_device):
         e.score("maha", pooled=torch.zeros(2, 768, device=dev))
     assert logits.shape == (2, 1842) and torch.isfinite(logits).all()
     e.close()
+
+
+def test_small_batch_graph_replay_matches_eager(cuda_device):
+    """B <= 128: the second call of a shape captures a CUDA graph, later calls replay it — results must be identical
+    to the eager path, survive a workspace growth in between, and follow changed inputs."""
+    from rgqa_b200 import _lib as L
+    eng = _engine("lxmert", "rich", "bf16", 0.2)
+    lib = L.load()
+    dev = eng.device
+    def run(inp):
+        p, l = eng.forward(inp["feat"].to(dev), inp["pos"].to(dev), inp["ids"].to(dev), inp["seg"].to(dev), inp["mask"].to(dev))
+        torch.cuda.synchronize()
+        return p.cpu(), l.cpu()
+    a, b = syn.make_inputs(32, 20, seed=1), syn.make_inputs(32, 20, seed=2)
+    lib.rgqa_set_option(b"graphs", 0)
+    n0 = lib.rgqa_launch_count()
+    ref_a, ref_b = run(a), run(b)
+    per_forward = (lib.rgqa_launch_count() - n0) // 2
+    lib.rgqa_set_option(b"graphs", 1)
+    n0 = lib.rgqa_launch_count()
+    outs = [run(a), run(a), run(b), run(a)]            # eager, capture+replay, replay x2
+    assert lib.rgqa_launch_count() - n0 == 4 * per_forward  # replays are still counted kernel by kernel
+    for (p, l), (rp, rl) in zip(outs, [ref_a, ref_a, ref_b, ref_a]):
+        assert torch.equal(l, rl) and torch.equal(p, rp)
+    run(syn.make_inputs(200, 20, seed=3))               # grows the workspace: captured graphs must be dropped
+    p, l = run(b)
+    assert torch.equal(l, ref_b[1])
+    p, l = run(b)
+    assert torch.equal(l, ref_b[1])
