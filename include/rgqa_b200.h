@@ -122,7 +122,8 @@ int rgqa_score(rgqa_handle* h, void* stream, int mode, const float* logits, cons
 /* Kernel-selection switches for A/B measurements: "gemm_pair" (1 = CTA-pair tcgen05 kernel when
  * M >= 1024), "gemm_staged" (1 = swizzled-smem + TMA-store epilogue in the pair kernel), "gemm_ln" (1 = fused
  * GEMM + residual + LayerNorm kernel), "two_streams" (1 = visual branch on a second stream), "graphs" (1 = CUDA-graph replay of the forward for
- * B <= 128), "pdl", "gemm_debug". */
+ * B <= 128), "defer_ln" (1 = LXMERT bf16 batches of >= 1024 token rows run without LayerNorm kernels: hidden states stay
+ * pre-LayerNorm as bf16 hi/lo pairs + row statistics, see rgqa_gemm_bf16_resid_hl), "pdl", "gemm_debug". */
 int rgqa_set_option(const char* name, int value);
 /* Kernels enqueued by this library since it was loaded. */
 long long rgqa_launch_count(void);
@@ -142,6 +143,24 @@ int rgqa_gemm_bf16(void* stream, const void* A, int64_t lda, const void* W, int6
 int rgqa_gemm_bf16_ln(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                       const float* resid, int64_t ldr, const float* gamma, const float* beta, float eps, void* out_act,
                       float* out_res, int M, int N, int K);
+/* Deferred LayerNorm (BertAttOutput / BertOutput, src/lxrt/modeling.py:357-361, :411-415, without ever materialising
+ * the normalised rows).  A hidden state is kept pre-LayerNorm as a bf16 pair (hi, lo; value = hi + lo) plus partial row
+ * statistics stats[M][6][2] = (sum, sum of squares) over each 128-column slice.
+ *  - rgqa_fold_ln_weight: W'[n,k] = bf16(W[n,k]·gamma[k] − mean_k(W[n,:]·gamma)) (rows centred, so x·W'ᵀ = (x − mean x)·(W∘gamma)ᵀ),
+ *    c[n] = sum_k W'[n,k] (bf16 rounding residue of the centring), bias'[n] = bias[n] + sum_k W[n,k]·beta[k]
+ *    (W, bias, gamma, beta f32 device pointers; W [N,K]).
+ *  - rgqa_gemm_bf16_folded: out = epilogue(rstd·(A_hi·W'ᵀ − mean·c) + bias') with mean/rstd from ln_stats; ln_c may be
+ *    NULL (term dropped: it is below the bf16 rounding of W'); K = 768.
+ *  - rgqa_gemm_bf16_resid_hl: v = A·Wᵀ + bias + LayerNorm_prev(in_hi + in_lo); writes v as (out_hi, out_lo, out_stats). N = 768. */
+int rgqa_fold_ln_weight(void* stream, const float* W, const float* bias, const float* gamma, const float* beta, int N,
+                        int K, void* W_out_bf16, float* c_out, float* bias_out);
+int rgqa_gemm_bf16_folded(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                          const void* resid, int64_t ldr, void* out, int64_t ldo, int out_dtype, int M, int N, int K,
+                          int epilogue, const float* ln_stats, const float* ln_c, float eps);
+int rgqa_gemm_bf16_resid_hl(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                            const void* in_hi, const void* in_lo, const float* in_stats, const float* in_gamma,
+                            const float* in_beta, float eps, void* out_hi, void* out_lo, float* out_stats, int M, int N,
+                            int K);
 int rgqa_gemm_f32(void* stream, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                   const float* resid, int64_t ldr, float* out, int64_t ldo, int M, int N, int K, int epilogue);
 int rgqa_attention(void* stream, int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,

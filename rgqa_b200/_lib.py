@@ -54,6 +54,9 @@ SIGNATURES = {
     "rgqa_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "rgqa_gemm_bf16": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i]),
     "rgqa_gemm_bf16_ln": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _f, _vp, _vp, _i, _i, _i]),
+    "rgqa_fold_ln_weight": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "rgqa_gemm_bf16_folded": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _f]),
+    "rgqa_gemm_bf16_resid_hl": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i]),
     "rgqa_gemm_f32": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i]),
     "rgqa_attention": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i]),
     "rgqa_embed_ln": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f]),

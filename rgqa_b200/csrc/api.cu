@@ -74,15 +74,24 @@ struct LNp {
   float* g = nullptr;
   float* b = nullptr;
 };
+// A consumer weight with the LayerNorm of its input folded in (deferred LayerNorm): W' = bf16(W∘gamma -
+// rowmean), b' = b + W·beta.  W == nullptr when the input is not behind a LayerNorm (first layer) or in fp32 mode.
+struct Folded {
+  void* W = nullptr;
+  float* b = nullptr;
+};
 struct AttW {
   Linear qkv;  // [3H, H]
   Linear out;  // [H, H]
   LNp ln;
+  Folded qkv_f;   // folded with the LayerNorm that produced this block's input (language rows for the cross block)
+  Folded qkv_f2;  // cross block only: folded with the visual branch's LayerNorm
 };
 struct FfnW {
   Linear inter;  // [I, H]
   Linear out;    // [H, I]
   LNp ln;
+  Folded inter_f;  // folded with the attention block's output LayerNorm
 };
 struct LayerW {
   AttW att;
@@ -117,6 +126,8 @@ struct rgqa_handle {
   std::vector<LayerW> l_layers, r_layers;
   std::vector<XLayerW> x_layers;
   Linear pooler, fc0, fc3;
+  Folded pooler_f;
+  float *ones = nullptr, *zeros = nullptr;  // [H] identity LayerNorm
   LNp fc_ln;
   // Mahalanobis
   float *maha_mu = nullptr, *maha_P = nullptr, *maha_m = nullptr;
@@ -330,6 +341,40 @@ int copy_raw(rgqa_handle* h, const std::string& name, int64_t d0, int64_t d1, fl
   return pack_vec(h, s, n, 1, out);
 }
 
+// ---- deferred-LayerNorm weight folding (bf16 path) ------------------------------------------------
+// names[i] (+ ".weight" / ".bias") are stacked row-wise, each [rows, K]; folded with the LayerNorm `ln` of the input.
+int fold_stack(rgqa_handle* h, const std::vector<std::string>& names, int rows, int K, const LNp& ln, Folded* out) {
+  const size_t n = names.size();
+  void* W = nullptr;
+  float *b = nullptr, *c = nullptr;
+  RGQA_CUDA_OK(cudaMalloc(&W, n * rows * static_cast<size_t>(K) * 2));
+  h->owned.push_back(W);
+  RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b), n * rows * sizeof(float)));
+  h->owned.push_back(b);
+  RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&c), n * rows * sizeof(float)));  // rounding residue, unused
+  h->owned.push_back(c);
+  for (size_t i = 0; i < n; ++i) {
+    float *w, *bias;
+    if (get_raw(h, names[i] + ".weight", rows, K, &w) || get_raw(h, names[i] + ".bias", rows, 0, &bias)) return 1;
+    if (fold_ln_weight(nullptr, w, bias, ln.g, ln.b, rows, K, static_cast<char*>(W) + i * rows * static_cast<size_t>(K) * 2,
+                       c + i * rows, b + i * rows))
+      return 1;
+  }
+  out->W = W;
+  out->b = b;
+  return 0;
+}
+int fold_qkv(rgqa_handle* h, const std::string& p, const char* self_name, const LNp* pred, Folded* out) {
+  if (pred == nullptr) return 0;
+  const std::string s = p + "." + self_name;
+  return fold_stack(h, {s + ".query", s + ".key", s + ".value"}, h->cfg.hidden, h->cfg.hidden, *pred, out);
+}
+// folds of one BertLayer whose input comes out of LayerNorm `pred` (nullptr: not behind a LayerNorm)
+int fold_bert_layer(rgqa_handle* h, const std::string& p, LayerW* w, const LNp* pred) {
+  if (fold_qkv(h, p + ".attention", "self", pred, &w->att.qkv_f)) return 1;
+  return fold_stack(h, {p + ".intermediate.dense"}, h->cfg.intermediate, h->cfg.hidden, w->att.ln, &w->ffn.inter_f);
+}
+
 // ---- dtype-dispatched primitives over the handle's precision ------------------------------------
 int gemm(rgqa_handle* h, cudaStream_t st, const void* A, long long lda, const Linear& lin, const void* resid,
          long long ldr, void* out, long long ldo, int out_f32, int M, int epi) {
@@ -435,7 +480,10 @@ int ensure_workspace(rgqa_handle* h, long long Mt, long long Mv, int B) {
 }
 
 // pooler + answer head on the hidden rows `hid` (first token of each sample, row stride S*H)
-int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, float* pooled_out, float* logits_out) {
+// `stats` != nullptr: `hid` is a deferred-LayerNorm state (un-normalised bf16 rows + statistics) and the pooler uses its
+// folded weight.
+int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, float* pooled_out, float* logits_out,
+               const float* stats = nullptr) {
   const int H = h->cfg.hidden, A = h->cfg.num_answers;
   const size_t es = act_size(h);
   const int dt = act_dtype(h);
@@ -450,7 +498,13 @@ int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, f
   logits_ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(logits_ws) + 15) & ~static_cast<uintptr_t>(15));
 
   float* pdst = pooled_out != nullptr ? pooled_out : pooled;
-  if (gemm(h, st, hid, static_cast<long long>(S) * H, h->pooler, nullptr, 0, pdst, H, 1, B, EPI_TANH)) return 1;
+  if (stats != nullptr) {
+    if (gemm_bf16_folded(st, hid, static_cast<long long>(S) * H, h->pooler_f.W, H, h->pooler_f.b, nullptr, 0, pdst, H, 1, B, H,
+                         H, EPI_TANH, stats, nullptr, h->cfg.ln_eps, static_cast<long long>(S) * 12))
+      return 1;
+  } else if (gemm(h, st, hid, static_cast<long long>(S) * H, h->pooler, nullptr, 0, pdst, H, 1, B, EPI_TANH)) {
+    return 1;
+  }
   if (A <= 0 || logits_out == nullptr) return 0;
   const void* a0 = pdst;
   if (dt == DT_BF16) {
@@ -607,6 +661,41 @@ int rgqa_finalize_weights(rgqa_handle* h) {
         return 1;
     }
     if (make_linear(h, b + "pooler.dense", H, H, &h->pooler)) return 1;
+    h->pooler_f = Folded{};
+    if (c.precision == RGQA_PREC_BF16) {
+      // deferred LayerNorm: every consumer of a hidden state gets a copy of its weight folded with the LayerNorm that
+      // (notionally) produced that state; the embeddings' outputs are not behind one (nullptr)
+      std::vector<float> one(H, 1.0f), zero(H, 0.0f);
+      RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->ones), H * sizeof(float)));
+      h->owned.push_back(h->ones);
+      RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->zeros), H * sizeof(float)));
+      h->owned.push_back(h->zeros);
+      RGQA_CUDA_OK(cudaMemcpy(h->ones, one.data(), H * sizeof(float), cudaMemcpyHostToDevice));
+      RGQA_CUDA_OK(cudaMemcpy(h->zeros, zero.data(), H * sizeof(float), cudaMemcpyHostToDevice));
+      const LNp *pl = nullptr, *pv = nullptr;
+      for (int i = 0; i < c.l_layers; ++i) {
+        if (fold_bert_layer(h, b + "encoder.layer." + std::to_string(i), &h->l_layers[i], pl)) return 1;
+        pl = &h->l_layers[i].ffn.ln;
+      }
+      for (int i = 0; i < c.r_layers; ++i) {
+        if (fold_bert_layer(h, b + "encoder.r_layers." + std::to_string(i), &h->r_layers[i], pv)) return 1;
+        pv = &h->r_layers[i].ffn.ln;
+      }
+      for (int i = 0; i < c.x_layers; ++i) {
+        const std::string x = b + "encoder.x_layers." + std::to_string(i);
+        XLayerW& w = h->x_layers[i];
+        if (fold_qkv(h, x + ".visual_attention", "att", pl, &w.cross.qkv_f) ||
+            fold_qkv(h, x + ".visual_attention", "att", pv, &w.cross.qkv_f2) ||
+            fold_qkv(h, x + ".lang_self_att", "self", &w.cross.ln, &w.lang_self.qkv_f) ||
+            fold_qkv(h, x + ".visn_self_att", "self", &w.cross.ln, &w.visn_self.qkv_f) ||
+            fold_stack(h, {x + ".lang_inter.dense"}, c.intermediate, H, w.lang_self.ln, &w.lang_ffn.inter_f) ||
+            fold_stack(h, {x + ".visn_inter.dense"}, c.intermediate, H, w.visn_self.ln, &w.visn_ffn.inter_f))
+          return 1;
+        pl = &w.lang_ffn.ln;
+        pv = &w.visn_ffn.ln;
+      }
+      if (pl != nullptr && fold_stack(h, {b + "pooler.dense"}, H, H, *pl, &h->pooler_f)) return 1;
+    }
   } else {
     const std::string u = "uniter.";
     if (copy_raw(h, u + "embeddings.word_embeddings.weight", c.vocab_size, H, &h->word) ||
@@ -641,6 +730,172 @@ int rgqa_finalize_weights(rgqa_handle* h) {
   return 0;
 }
 
+// ---- deferred-LayerNorm forward (bf16, large batches) ----------------------------------------------------------------
+// No LayerNorm kernel runs between the encoder GEMMs.  A hidden state is kept PRE-LayerNorm as a bf16 pair (hi + lo =
+// the fp32 value to 2^-17) plus per-row partial (sum, sumsq); the LayerNorm itself is applied
+//  - by the next GEMM that consumes the state as its A operand: gamma and the centring are folded into the weight, beta
+//    into the bias, and 1/std is the scale of the epilogue's bias FMA (gemm_bf16_folded);
+//  - by the next GEMM that adds the state as its residual: the epilogue normalises the hi/lo rows it loads (TMA) on the
+//    fly, adds them to acc + bias and writes the new pre-LayerNorm state and its statistics (gemm_bf16_resid_hl).
+// Same math as modeling.py:357-361 / :411-415, 53 fewer kernels and ~10 B per hidden element less HBM traffic per block.
+namespace {
+struct DState {
+  char* hi;      // bf16 [Mt, H]
+  char* lo;      // bf16 [Mt, H]
+  float* stats;  // [Mt, 6, 2]
+};
+struct DefCtx {
+  rgqa_handle* h;
+  int H;
+  char* hi_rows(const DState& s, long long r0) const { return s.hi + static_cast<size_t>(r0) * H * 2; }
+  char* lo_rows(const DState& s, long long r0) const { return s.lo + static_cast<size_t>(r0) * H * 2; }
+  float* st_rows(const DState& s, long long r0) const { return s.stats + r0 * 12; }
+  // out = epi(LN_ln(in) · Wᵀ + b); ln == nullptr: `in` holds already-normalised rows
+  int consume(cudaStream_t st, const DState& in, const LNp* ln, const Linear& lin, const Folded& f, long long r0, int M,
+              void* out, long long ldo, int epi) const {
+    if (ln == nullptr)
+      return gemm_bf16(st, hi_rows(in, r0), H, lin.W, lin.K, lin.b, nullptr, 0, out, ldo, 0, M, lin.N, lin.K, epi);
+    RGQA_CHECK(f.W != nullptr, "deferred LayerNorm: folded weight missing");
+    return gemm_bf16_folded(st, hi_rows(in, r0), H, f.W, lin.K, f.b, nullptr, 0, out, ldo, 0, M, lin.N, lin.K, epi,
+                            st_rows(in, r0), nullptr, h->cfg.ln_eps, 12);
+  }
+  // out (pre-LayerNorm) = A · Wᵀ + b + LN_ln(in)
+  int produce(cudaStream_t st, const void* A, long long lda, const Linear& lin, const DState& in, const LNp* ln,
+              const DState& out, long long r0, int M) const {
+    return gemm_bf16_resid_hl(st, A, lda, lin.W, lin.K, lin.b, hi_rows(in, r0), lo_rows(in, r0), st_rows(in, r0),
+                              ln ? ln->g : h->ones, ln ? ln->b : h->zeros, h->cfg.ln_eps, hi_rows(out, r0), lo_rows(out, r0),
+                              st_rows(out, r0), M, lin.N, lin.K);
+  }
+  // BertAttention (self) on rows [r0, r0 + B*S): in (LayerNorm ln_in) -> out (LayerNorm w.ln)
+  int att(cudaStream_t st, const AttW& w, const DState& in, const LNp* ln_in, const DState& out, long long r0, int B, int S,
+          const int32_t* key_mask) const {
+    char* qkv = rows_at(h->qkv.p, r0, 3 * H, 2);
+    char* ctx = rows_at(h->ctx.p, r0, H, 2);
+    if (consume(st, in, ln_in, w.qkv, w.qkv_f, r0, B * S, qkv, 3 * H, EPI_BIAS)) return 1;
+    if (attention(st, DT_BF16, qkv, 3 * H, qkv + static_cast<size_t>(H) * 2, 3 * H, qkv + static_cast<size_t>(2 * H) * 2, 3 * H,
+                  key_mask, ctx, H, B, S, S, h->cfg.heads))
+      return 1;
+    return produce(st, ctx, H, w.out, in, ln_in, out, r0, B * S);
+  }
+  // BertIntermediate + BertOutput: in (LayerNorm ln_in) -> out (LayerNorm w.ln)
+  int ffn(cudaStream_t st, const FfnW& w, const DState& in, const LNp* ln_in, const DState& out, long long r0, int M) const {
+    const int I = h->cfg.intermediate;
+    char* inter = rows_at(h->inter.p, r0, I, 2);
+    if (consume(st, in, ln_in, w.inter, w.inter_f, r0, M, inter, I, EPI_GELU)) return 1;
+    return produce(st, inter, I, w.out, in, ln_in, out, r0, M);
+  }
+};
+}  // namespace
+
+static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* feat, int feat_dtype, const float* pos,
+                                   const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
+                                   float* pooled_out, float* logits_out) {
+  const rgqa_config& c = h->cfg;
+  const int H = c.hidden, V = c.num_rois;
+  const long long Ml = static_cast<long long>(B) * L, Mv = static_cast<long long>(B) * V, Mt = Ml + Mv;
+  // resA / resB (fp32-sized) hold the lo rows in their first half and the statistics behind them
+  DState cur{static_cast<char*>(h->hidA.p), static_cast<char*>(h->resA.p),
+             reinterpret_cast<float*>(static_cast<char*>(h->resA.p) + static_cast<size_t>(Mt) * H * 2)};
+  DState alt{static_cast<char*>(h->hidB.p), static_cast<char*>(h->resB.p),
+             reinterpret_cast<float*>(static_cast<char*>(h->resB.p) + static_cast<size_t>(Mt) * H * 2)};
+  const DefCtx d{h, H};
+
+  const bool two = option_get(OPT_TWO_STREAMS) != 0;
+  if (two && h->side == nullptr) {
+    RGQA_CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    RGQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    RGQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
+  cudaStream_t sv = two ? h->side : st;
+  auto fork = [&]() -> int {
+    if (!two) return 0;
+    RGQA_CUDA_OK(cudaEventRecord(h->ev_fork, st));
+    RGQA_CUDA_OK(cudaStreamWaitEvent(sv, h->ev_fork, 0));
+    return 0;
+  };
+  auto join = [&]() -> int {
+    if (!two) return 0;
+    RGQA_CUDA_OK(cudaEventRecord(h->ev_join, sv));
+    RGQA_CUDA_OK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    return 0;
+  };
+  if (fork()) return 1;
+
+  // ---- embeddings (modeling.py:876) and visual feature encoder (:507-517): normalised rows -> identity states ----
+  // fp32 scratch for the normalised rows: language rows in the (idle) FFN buffer, visual rows in the visual part of the
+  // (idle) Q|K|V buffer -- regions only their own branch's stream touches
+  float* y32 = static_cast<float*>(h->inter.p);
+  float* yv = reinterpret_cast<float*>(rows_at(h->qkv.p, Ml, 3 * H, 2));
+  if (embed_ln(st, DT_BF16, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, cur.hi, y32, B, L, H,
+               c.vocab_size, c.max_position, c.type_vocab, c.ln_eps) ||
+      identity_state(st, y32, cur.hi, cur.lo, cur.stats, Ml, H))
+    return 1;
+  {
+    const void* a = feat;
+    if (feat_dtype == RGQA_DT_F32) {
+      if (cast_f32_to_bf16(sv, static_cast<const float*>(feat), h->featb.p, Mv * c.visual_feat_dim)) return 1;
+      a = h->featb.p;
+    }
+    float* pre = reinterpret_cast<float*>(rows_at(h->pre.p, Ml, H, 4));
+    if (gemm_bf16(sv, a, c.visual_feat_dim, h->visn_fc.W, h->visn_fc.K, h->visn_fc.b, nullptr, 0, pre, H, 1, static_cast<int>(Mv),
+                  H, h->visn_fc.K, EPI_BIAS) ||
+        visn_combine(sv, DT_BF16, pre, pos, c.visual_pos_dim, h->box_W, h->box_b, h->visn_ln.g, h->visn_ln.b, h->box_ln.g,
+                     h->box_ln.b, d.hi_rows(cur, Ml), yv, static_cast<int>(Mv), H, c.ln_eps) ||
+        identity_state(sv, yv, d.hi_rows(cur, Ml), d.lo_rows(cur, Ml), d.st_rows(cur, Ml), Mv, H))
+      return 1;
+  }
+  const LNp *ln_l = nullptr, *ln_v = nullptr;  // LayerNorm still owed to the language / visual rows of `cur`
+  for (int i = 0; i < c.l_layers; ++i) {  // modeling.py:553-554
+    const LayerW& w = h->l_layers[i];
+    if (d.att(st, w.att, cur, ln_l, alt, 0, B, L, mask) || d.ffn(st, w.ffn, alt, &w.att.ln, cur, 0, static_cast<int>(Ml)))
+      return 1;
+    ln_l = &w.ffn.ln;
+  }
+  for (int i = 0; i < c.r_layers; ++i) {  // modeling.py:557-558
+    const LayerW& w = h->r_layers[i];
+    if (d.att(sv, w.att, cur, ln_v, alt, Ml, B, V, nullptr) || d.ffn(sv, w.ffn, alt, &w.att.ln, cur, Ml, static_cast<int>(Mv)))
+      return 1;
+    ln_v = &w.ffn.ln;
+  }
+  if (join()) return 1;
+  for (int i = 0; i < c.x_layers; ++i) {  // modeling.py:477-488
+    const XLayerW& w = h->x_layers[i];
+    char* qkv = static_cast<char*>(h->qkv.p);
+    char* qkv_v = rows_at(h->qkv.p, Ml, 3 * H, 2);
+    char* ctx = static_cast<char*>(h->ctx.p);
+    // ONE BertCrossattLayer for both directions (:455-459); its Q|K|V of each modality behind that modality's LayerNorm
+    if (fork()) return 1;
+    if (d.consume(st, cur, ln_l, w.cross.qkv, w.cross.qkv_f, 0, static_cast<int>(Ml), qkv, 3 * H, EPI_BIAS) ||
+        d.consume(sv, cur, ln_v, w.cross.qkv, w.cross.qkv_f2, Ml, static_cast<int>(Mv), qkv_v, 3 * H, EPI_BIAS))
+      return 1;
+    if (join()) return 1;
+    if (attention(st, DT_BF16, qkv, 3 * H, qkv_v + static_cast<size_t>(H) * 2, 3 * H, qkv_v + static_cast<size_t>(2 * H) * 2, 3 * H,
+                  nullptr, ctx, H, B, L, V, c.heads) ||
+        attention(st, DT_BF16, qkv_v, 3 * H, qkv + static_cast<size_t>(H) * 2, 3 * H, qkv + static_cast<size_t>(2 * H) * 2, 3 * H, mask,
+                  rows_at(ctx, Ml, H, 2), H, B, V, L, c.heads))
+      return 1;
+    if (fork()) return 1;
+    // cross output + self attention + FFN per modality (:455-475), the two chains side by side
+    if (d.produce(st, ctx, H, w.cross.out, cur, ln_l, alt, 0, static_cast<int>(Ml)) ||
+        d.att(st, w.lang_self, alt, &w.cross.ln, cur, 0, B, L, mask) ||
+        d.ffn(st, w.lang_ffn, cur, &w.lang_self.ln, alt, 0, static_cast<int>(Ml)))
+      return 1;
+    if (d.produce(sv, rows_at(ctx, Ml, H, 2), H, w.cross.out, cur, ln_v, alt, Ml, static_cast<int>(Mv)) ||
+        d.att(sv, w.visn_self, alt, &w.cross.ln, cur, Ml, B, V, nullptr) ||
+        d.ffn(sv, w.visn_ffn, cur, &w.visn_self.ln, alt, Ml, static_cast<int>(Mv)))
+      return 1;
+    if (join()) return 1;
+    ln_l = &w.lang_ffn.ln;
+    ln_v = &w.visn_ffn.ln;
+    const DState t = cur;
+    cur = alt;
+    alt = t;
+  }
+  if (pooled_out == nullptr && logits_out == nullptr) return 0;
+  if (ln_l == nullptr) return head_block(h, st, cur.hi, B, L, pooled_out, logits_out);
+  return head_block(h, st, cur.hi, B, L, pooled_out, logits_out, cur.stats);
+}
+
 static int lxmert_forward_impl(rgqa_handle* h, cudaStream_t st, const void* feat, int feat_dtype, const float* pos,
                                const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
                                float* pooled_out, float* logits_out) {
@@ -652,6 +907,10 @@ static int lxmert_forward_impl(rgqa_handle* h, cudaStream_t st, const void* feat
   const size_t es = act_size(h);
   const int dt = act_dtype(h);
   const bool bf = c.precision == RGQA_PREC_BF16;
+  // large bf16 batches: no LayerNorm kernels at all (every encoder GEMM then runs on the CTA-pair kernel)
+  if (bf && option_get(OPT_DEFER_LN) != 0 && option_get(OPT_GEMM_PAIR) != 0 && option_get(OPT_GEMM_STAGED) != 0 &&
+      H == 768 && Ml >= 1024 && h->ones != nullptr)
+    return lxmert_forward_deferred(h, st, feat, feat_dtype, pos, ids, seg, mask, B, L, pooled_out, logits_out);
   Hid cur{h->hidA.p, bf ? static_cast<float*>(h->resA.p) : static_cast<float*>(h->hidA.p)};
   Hid alt{h->hidB.p, bf ? static_cast<float*>(h->resB.p) : static_cast<float*>(h->hidB.p)};
 
@@ -766,6 +1025,7 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
 
   const rgqa_config& c = h->cfg;
   const long long key = (static_cast<long long>(B) << 20) | (static_cast<long long>(L) << 8) | (feat_dtype << 4) |
+                        ((option_get(OPT_DEFER_LN) != 0) << 3) |
                         ((seg != nullptr) << 2) | ((pooled_out != nullptr) << 1) | (logits_out != nullptr);
   rgqa_handle::GraphEntryT& g = h->graphs[key];
   const size_t fe = feat_dtype == RGQA_DT_F32 ? 4 : 2;
@@ -974,6 +1234,10 @@ int rgqa_set_option(const char* name, int value) {
     option_set(OPT_GRAPHS, value);
     return 0;
   }
+  if (strcmp(name, "defer_ln") == 0) {
+    option_set(OPT_DEFER_LN, value);
+    return 0;
+  }
   if (strcmp(name, "two_streams") == 0) {
     option_set(OPT_TWO_STREAMS, value);
     return 0;
@@ -1012,6 +1276,23 @@ int rgqa_gemm_bf16_ln(void* stream, const void* A, int64_t lda, const void* W, i
                       float* out_res, int M, int N, int K) {
   return gemm_bf16_ln(static_cast<cudaStream_t>(stream), A, lda, W, ldw, bias, resid, ldr, gamma, beta, eps, out_act,
                       out_res, M, N, K);
+}
+int rgqa_fold_ln_weight(void* stream, const float* W, const float* bias, const float* gamma, const float* beta, int N,
+                        int K, void* W_out_bf16, float* c_out, float* bias_out) {
+  return fold_ln_weight(static_cast<cudaStream_t>(stream), W, bias, gamma, beta, N, K, W_out_bf16, c_out, bias_out);
+}
+int rgqa_gemm_bf16_folded(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                          const void* resid, int64_t ldr, void* out, int64_t ldo, int out_dtype, int M, int N, int K,
+                          int epilogue, const float* ln_stats, const float* ln_c, float eps) {
+  return gemm_bf16_folded(static_cast<cudaStream_t>(stream), A, lda, W, ldw, bias, resid, ldr, out, ldo,
+                          out_dtype == RGQA_DT_F32 ? 1 : 0, M, N, K, epilogue, ln_stats, ln_c, eps, 12);
+}
+int rgqa_gemm_bf16_resid_hl(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                            const void* in_hi, const void* in_lo, const float* in_stats, const float* in_gamma,
+                            const float* in_beta, float eps, void* out_hi, void* out_lo, float* out_stats, int M, int N,
+                            int K) {
+  return gemm_bf16_resid_hl(static_cast<cudaStream_t>(stream), A, lda, W, ldw, bias, in_hi, in_lo, in_stats, in_gamma,
+                            in_beta, eps, out_hi, out_lo, out_stats, M, N, K);
 }
 int rgqa_gemm_f32(void* stream, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                   const float* resid, int64_t ldr, float* out, int64_t ldo, int M, int N, int K, int epilogue) {

@@ -57,6 +57,18 @@ struct GemmParams {
   long long ldr;
   void* out;
   long long ldo;
+  // deferred LayerNorm of the A operand: A holds bf16(x) of the PRE-LayerNorm rows, W is scaled by
+  // gamma, bias carries W·beta; the epilogue applies the per-row (x - mu) * rstd: out = rstd*(acc - mu*c[n]) + bias[n]
+  // EPI_RESID_HL (producer of a deferred-LayerNorm hidden state): the residual is LN_prev(x_prev) recomputed from the
+  // previous pre-LN rows (bf16 hi + lo pair), their statistics and the previous LayerNorm's gamma/beta
+  const float* in_stats;   // [M][6][2]
+  const float* in_gamma;   // [N]
+  const float* in_beta;    // [N]
+  float* out_stats;        // [M][6][2] partial (sum, sumsq) of the rows this GEMM writes
+  const float* ln_stats;  // [M][6][2] partial (sum, sum of squares) of each 768-wide row, or nullptr
+  const float* ln_c;      // [N] sum_k W'[n,k]
+  float ln_eps;
+  long long ln_stats_ld;  // floats between the statistics of consecutive GEMM rows (12 when dense)
   int vec_ok;  // direct path: rows of out (and resid) are 16-byte aligned -> vector stores allowed
   int debug;   // measurement only (rgqa_set_option "gemm_debug"): bit0 skip TMA stores, bit1 skip epilogue math+smem
 };
@@ -96,22 +108,60 @@ __device__ __forceinline__ float apply_act(float v) {
   return v;
 }
 
+// mean and 1/std of one 768-wide row from its six partial (sum, sum of squares) pairs
+struct RowNorm {
+  float mu, rstd;
+};
+__device__ __forceinline__ RowNorm row_norm(const float* __restrict__ stats, int row, bool row_ok, float eps,
+                                            long long ld = 12) {
+  RowNorm r{0.f, 1.f};
+  if (stats != nullptr && row_ok) {
+    const float4* s4 = reinterpret_cast<const float4*>(stats + static_cast<long long>(row) * ld);
+    const float4 a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(s4 + 2);
+    const float sum = ((a.x + a.z) + (b.x + b.z)) + (c.x + c.z);
+    const float sq = ((a.y + a.w) + (b.y + b.w)) + (c.y + c.w);
+    r.mu = sum * (1.0f / 768.0f);
+    const float var = fmaxf(sq * (1.0f / 768.0f) - r.mu * r.mu, 0.f);
+    r.rstd = 1.0f / sqrtf(var + eps);
+  }
+  return r;
+}
+
 // acc + bias (+ fp32 residual) -> activation, for one 32-column chunk of one accumulator row
 template <int EPI>
 __device__ __forceinline__ void epilogue_math(const uint32_t (&v)[32], float (&f)[32], int row, bool row_ok, int col0,
-                                              const GemmParams& p, bool aligned) {
+                                              const GemmParams& p, bool aligned, RowNorm rn = RowNorm{0.f, 1.f}) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  // deferred LayerNorm: rstd * (acc - mu * c[n]) + bias'[n].  The folded weight rows are centred (zero sum up to bf16
+  // rounding), so c is normally omitted (ln_c == nullptr) and the whole correction is the rstd factor of the bias FMA.
+  if (p.ln_stats != nullptr && p.ln_c != nullptr) {
+    if (col0 + 32 <= p.N && aligned) {
+      const float4* c4 = reinterpret_cast<const float4*>(p.ln_c + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 c = __ldg(c4 + i);
+        f[4 * i + 0] = fmaf(-rn.mu, c.x, f[4 * i + 0]);
+        f[4 * i + 1] = fmaf(-rn.mu, c.y, f[4 * i + 1]);
+        f[4 * i + 2] = fmaf(-rn.mu, c.z, f[4 * i + 2]);
+        f[4 * i + 3] = fmaf(-rn.mu, c.w, f[4 * i + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) f[i] = fmaf(-rn.mu, __ldg(p.ln_c + col0 + i), f[i]);
+    }
+  }
   if (col0 + 32 <= p.N && aligned) {
     if (p.bias != nullptr) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 b = __ldg(b4 + i);
-        f[4 * i + 0] += b.x;
-        f[4 * i + 1] += b.y;
-        f[4 * i + 2] += b.z;
-        f[4 * i + 3] += b.w;
+        f[4 * i + 0] = fmaf(rn.rstd, f[4 * i + 0], b.x);  // rstd == 1 outside the deferred-LayerNorm consumers
+        f[4 * i + 1] = fmaf(rn.rstd, f[4 * i + 1], b.y);
+        f[4 * i + 2] = fmaf(rn.rstd, f[4 * i + 2], b.z);
+        f[4 * i + 3] = fmaf(rn.rstd, f[4 * i + 3], b.w);
       }
     }
     if constexpr (EPI == EPI_RESID) {
@@ -132,7 +182,7 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&v)[32], float (&f
     for (int i = 0; i < 32; ++i) {
       const int col = col0 + i;
       if (col < p.N) {
-        if (p.bias != nullptr) f[i] += __ldg(p.bias + col);
+        if (p.bias != nullptr) f[i] = fmaf(rn.rstd, f[i], __ldg(p.bias + col));
         if constexpr (EPI == EPI_RESID) {
           if (row_ok) f[i] += p.resid[static_cast<long long>(row) * p.ldr + col];
         }
@@ -146,9 +196,9 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&v)[32], float (&f
 // direct path: one 32-column chunk straight to global memory (vector stores when aligned, else scalar, guarded)
 template <int EPI, typename OutT>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row, bool row_ok, int col0,
-                                               const GemmParams& p) {
+                                               const GemmParams& p, RowNorm rn = RowNorm{0.f, 1.f}) {
   float f[32];
-  epilogue_math<EPI>(v, f, row, row_ok, col0, p, p.vec_ok != 0);
+  epilogue_math<EPI>(v, f, row, row_ok, col0, p, p.vec_ok != 0, rn);
   if (!row_ok) return;
   if (col0 + 32 <= p.N && p.vec_ok) {
     if constexpr (sizeof(OutT) == 2) {
@@ -328,6 +378,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int n0 = (t % tiles_n) * BN;
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < p.M;
+      const RowNorm rn = row_norm(p.ln_stats, row, row_ok, p.ln_eps, p.ln_stats_ld);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
@@ -339,7 +390,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint32_t v[32];
         tmem_ld32(t_row + static_cast<uint32_t>(c), v);
         tmem_ld_wait_dep(v);
-        epilogue_chunk<EPI, OutT>(v, row, row_ok, col0, p);
+        epilogue_chunk<EPI, OutT>(v, row, row_ok, col0, p, rn);
       }
       // all TMEM reads of this accumulator buffer are complete (wait::ld above): hand it back
       tc_fence_before();
@@ -390,8 +441,10 @@ template <int EPI, typename OutT, bool STAGED, int EW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + EW) * 32, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+                      const __grid_constant__ CUtensorMap tmOutLo, const __grid_constant__ CUtensorMap tmResLo,
                       const GemmParams p) {
-  constexpr bool kResidSmem = STAGED && EPI == EPI_RESID && sizeof(OutT) == 4;
+  constexpr bool kHiLo = STAGED && EPI == EPI_RESID_HL;  // deferred-LayerNorm producer (bf16 hi/lo pair + statistics)
+  constexpr bool kResidSmem = (STAGED && EPI == EPI_RESID && sizeof(OutT) == 4) || kHiLo;
   static_assert(EW == 8 || (EW == 16 && STAGED && !kResidSmem), "16 epilogue warps: staged, non-residual epilogues only");
   using PC = PairCfg<STAGED, kResidSmem, EW>;
   constexpr int kStages = PC::kStages;
@@ -422,6 +475,10 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tma_prefetch_desc(&tmB);
     if constexpr (STAGED) tma_prefetch_desc(&tmOut);
     if constexpr (kResidSmem) tma_prefetch_desc(&tmRes);
+    if constexpr (kHiLo) {
+      tma_prefetch_desc(&tmOutLo);
+      tma_prefetch_desc(&tmResLo);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -526,13 +583,21 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         coords(k, row0, col);
         const int b = k % kResidRing;
         mbar_expect_tx(&resid_bar[half * kResidRing + b], kSlabBytes);
-        tma_load_2d(slabs + (half * kResidRing + b) * kSlabBytes, &tmRes, &resid_bar[half * kResidRing + b], col, row0);
+        uint8_t* dst = slabs + (half * kResidRing + b) * kSlabBytes;
+        if constexpr (kHiLo) {  // hi rows then lo rows, 128 x 64 B each, 64-byte swizzle
+          tma_load_2d(dst, &tmRes, &resid_bar[half * kResidRing + b], col, row0);
+          tma_load_2d(dst + kSlabBytes / 2, &tmResLo, &resid_bar[half * kResidRing + b], col, row0);
+        } else {
+          tma_load_2d(dst, &tmRes, &resid_bar[half * kResidRing + b], col, row0);
+        }
       };
       if (issuer) {
         if (total > 0) issue_load(0);
         for (int j = 1; j < kResidRing - 1; ++j)
           if (total > j) issue_load(j);
       }
+      [[maybe_unused]] RowNorm rin{0.f, 1.f};
+      [[maybe_unused]] float st_sum = 0.f, st_sq = 0.f;
       for (int k = 0; k < total; ++k) {
         const int itile = k >> 2, sl = k & 3;
         const int acc = itile & 1;
@@ -540,6 +605,10 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         coords(k, row0, col);
         const int row = row0 + r_local;
         if (sl == 0) {
+          if constexpr (kHiLo) {
+            rin = row_norm(p.in_stats, row, row < p.M, p.ln_eps);
+            st_sum = st_sq = 0.f;
+          }
           mbar_wait(&tmem_full_bar[acc], (itile >> 1) & 1u);
           tc_fence_after();
         }
@@ -551,7 +620,59 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         mbar_wait(&resid_bar[half * kResidRing + b], (k / kResidRing) & 1u);  // this slab's residual rows have landed
         tmem_ld_wait_dep(v);
         float f[32];
-        {
+        if constexpr (kHiLo) {
+          // residual = LN_prev(x_prev) with x_prev = hi + lo; v = acc + bias + residual; then split v again
+          // 64-byte swizzle: 16-byte piece i of row r sits at piece i ^ ((r >> 1) & 3) -> conflict-free row-per-lane access
+          uint8_t* hrow = buf + r_local * 64;
+          uint8_t* lrow = buf + kSlabBytes / 2 + r_local * 64;
+          const int sw = (r_local >> 1) & 3;
+          const float ra = rin.rstd, rb = -rin.mu * rin.rstd;
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+          const float4* g4 = reinterpret_cast<const float4*>(p.in_gamma + col);
+          const float4* e4 = reinterpret_cast<const float4*>(p.in_beta + col);
+          uint32_t hw[16], lw[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 h4 = *reinterpret_cast<const uint4*>(hrow + ((i ^ sw) << 4));
+            const uint4 l4 = *reinterpret_cast<const uint4*>(lrow + ((i ^ sw) << 4));
+            hw[4 * i + 0] = h4.x; hw[4 * i + 1] = h4.y; hw[4 * i + 2] = h4.z; hw[4 * i + 3] = h4.w;
+            lw[4 * i + 0] = l4.x; lw[4 * i + 1] = l4.y; lw[4 * i + 2] = l4.z; lw[4 * i + 3] = l4.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {  // columns 4i .. 4i+3 = bf16 words 2i, 2i+1
+            const float4 bb = __ldg(b4 + i), gg = __ldg(g4 + i), ee = __ldg(e4 + i);
+            const float2 h0 = unpack_bf16x2(hw[2 * i]), l0 = unpack_bf16x2(lw[2 * i]);
+            const float2 h1 = unpack_bf16x2(hw[2 * i + 1]), l1 = unpack_bf16x2(lw[2 * i + 1]);
+            const float r0 = fmaf(fmaf(h0.x + l0.x, ra, rb), gg.x, ee.x);
+            const float r1 = fmaf(fmaf(h0.y + l0.y, ra, rb), gg.y, ee.y);
+            const float r2 = fmaf(fmaf(h1.x + l1.x, ra, rb), gg.z, ee.z);
+            const float r3 = fmaf(fmaf(h1.y + l1.y, ra, rb), gg.w, ee.w);
+            f[4 * i + 0] = (__uint_as_float(v[4 * i + 0]) + bb.x) + r0;
+            f[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) + bb.y) + r1;
+            f[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + bb.z) + r2;
+            f[4 * i + 3] = (__uint_as_float(v[4 * i + 3]) + bb.w) + r3;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t ho[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a = f[8 * i + 2 * j], b = f[8 * i + 2 * j + 1];
+              st_sum += a + b;
+              st_sq = fmaf(a, a, fmaf(b, b, st_sq));
+              ho[j] = pack_bf16x2(a, b);
+              const float2 hb = unpack_bf16x2(ho[j]);
+              lo[j] = pack_bf16x2(a - hb.x, b - hb.y);
+            }
+            *reinterpret_cast<uint4*>(hrow + ((i ^ sw) << 4)) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+            *reinterpret_cast<uint4*>(lrow + ((i ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          if (sl == 3 && row < p.M) {  // this thread's 128 columns of the row are done: publish their partial statistics
+            float2* so = reinterpret_cast<float2*>(p.out_stats + static_cast<long long>(row) * 12) +
+                         (((pair + itile * num_pairs) % tiles_n) * 2 + half);
+            *so = make_float2(st_sum, st_sq);
+          }
+        } else {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
           const uint8_t* rowp = buf + r_local * 128;
           const int sw = r_local & 7;
@@ -565,8 +686,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             f[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + bb.z) + rr.z;
             f[4 * i + 3] = (__uint_as_float(v[4 * i + 3]) + bb.w) + rr.w;
           }
+          store_chunk_swizzled<float>(buf, r_local, 0, f);  // in place: this thread's own row
         }
-        store_chunk_swizzled<float>(buf, r_local, 0, f);  // in place: this thread's own row
         (void)row;
         if (sl == 3) {  // the tile's four chunks are in registers / smem: hand the accumulator back
           tc_fence_before();
@@ -576,7 +697,10 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         fence_proxy_async_smem();
         named_bar_sync(1 + half, 128);
         if (issuer) {
-          if (row0 < p.M) tma_store_2d(&tmOut, buf, col, row0);
+          if (row0 < p.M) {
+            tma_store_2d(&tmOut, buf, col, row0);
+            if constexpr (kHiLo) tma_store_2d(&tmOutLo, buf + kSlabBytes / 2, col, row0);
+          }
           tma_store_commit();
           if (k + kResidRing - 1 < total) {
             tma_store_wait_read<1>();  // the store of slab k-1 has drained the buffer slab k+2 will land in
@@ -595,6 +719,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int r_local = quarter * 32 + lane;
       const int row = m0 + r_local;
       const bool row_ok = row < p.M;
+      const RowNorm rn = row_norm(p.ln_stats, row, row_ok, p.ln_eps, p.ln_stats_ld);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
@@ -623,7 +748,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int cc = 0; cc < kChunksPerSlab; ++cc) {
             if (p.debug & 2) continue;
             float f[32];
-            epilogue_math<EPI>(v[cc], f, row, row_ok, col_slab + cc * 32, p, true);
+            epilogue_math<EPI>(v[cc], f, row, row_ok, col_slab + cc * 32, p, true, rn);
             store_chunk_swizzled<OutT>(buf, r_local, cc, f);
           }
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
@@ -642,7 +767,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           uint32_t v[32];
           tmem_ld32(t_row + static_cast<uint32_t>(c), v);
           tmem_ld_wait_dep(v);
-          epilogue_chunk<EPI, OutT>(v, row, row_ok, col0, p);
+          epilogue_chunk<EPI, OutT>(v, row, row_ok, col0, p, rn);
         }
       }
       tc_fence_before();
@@ -700,6 +825,28 @@ int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols,
   return 0;
 }
 
+// general form: explicit box width (elements) and swizzle span in bytes (0 = none, 64, 128)
+int make_tmap_ex(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows, int box_cols,
+                 int elem_bytes, int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode_fn();
+  RGQA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  RGQA_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "TMA operand must be 16-byte aligned");
+  RGQA_CHECK((ld * elem_bytes) % 16 == 0, "TMA operand row stride must be a multiple of 16 bytes (ld=%lld)", ld);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                   : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                         : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RGQA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -752,12 +899,14 @@ int dispatch_epi(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, con
 
 template <int EPI, typename OutT, bool STAGED>
 int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                const CUtensorMap& tmRes, const GemmParams& p) {
+                const CUtensorMap& tmRes, const GemmParams& p, const CUtensorMap* tmOutLo = nullptr,
+                const CUtensorMap* tmResLo = nullptr) {
   // 16 epilogue warps were measured on B200 (bf16 outputs): FFN1 1043 vs 1056 TFLOP/s, QKV 1180 vs 1274 — no gain,
   // the erf-GELU epilogue is bound by its dependent FMA/MUFU chains, not by warps in flight.  8 it is.
   constexpr int EW = 8;
   auto kern = gemm_bf16_pair_kernel<EPI, OutT, STAGED, EW>;
-  constexpr int smem = PairCfg<STAGED, (STAGED && EPI == EPI_RESID && sizeof(OutT) == 4), EW>::kSmemBytes;
+  constexpr int smem =
+      PairCfg<STAGED, (STAGED && ((EPI == EPI_RESID && sizeof(OutT) == 4) || EPI == EPI_RESID_HL)), EW>::kSmemBytes;
   static bool configured = false;
   if (!configured) {
     RGQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -767,7 +916,8 @@ int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& 
   const int max_pairs = num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   void* tok = prof_begin(stream);
-  RGQA_CUDA_OK(launch_pdl(kern, dim3(2 * pairs), dim3((4 + EW) * 32), smem, stream, tmA, tmB, tmOut, tmRes, p));
+  RGQA_CUDA_OK(launch_pdl(kern, dim3(2 * pairs), dim3((4 + EW) * 32), smem, stream, tmA, tmB, tmOut, tmRes,
+                          tmOutLo ? *tmOutLo : tmA, tmResLo ? *tmResLo : tmA, p));
   prof_end(tok, stream, 2.0 * p.M * static_cast<double>(p.N) * p.K, PROF_GEMM_TC);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
@@ -803,8 +953,48 @@ int dispatch_pair(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, co
 
 }  // namespace
 
+int gemm_bf16_resid_hl(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                       const void* in_hi, const void* in_lo, const float* in_stats, const float* in_gamma,
+                       const float* in_beta, float eps, void* out_hi, void* out_lo, float* out_stats, int M, int N, int K) {
+  RGQA_CHECK(M > 0 && K > 0 && K % BK == 0, "gemm_bf16_resid_hl: bad problem M=%d K=%d", M, K);
+  RGQA_CHECK(N == 768, "gemm_bf16_resid_hl: built for N = 768 (got %d)", N);
+  RGQA_CHECK(bias && in_hi && in_lo && in_stats && in_gamma && in_beta && out_hi && out_lo && out_stats,
+             "gemm_bf16_resid_hl: null argument");
+  CUtensorMap tmA, tmB, tmOutHi, tmOutLo, tmInHi, tmInLo;
+  if (make_tmap(&tmA, A, M, K, lda, BM, 2)) return 1;
+  if (make_tmap(&tmB, W, N, K, ldw, kPairBN / 2, 2)) return 1;
+  // 128 rows x 32 bf16 columns (64 B), 64-byte swizzle: hi and lo halves of one 32-column slab
+  if (make_tmap_ex(&tmOutHi, out_hi, M, N, N, BM, 32, 2, 64) || make_tmap_ex(&tmOutLo, out_lo, M, N, N, BM, 32, 2, 64) ||
+      make_tmap_ex(&tmInHi, in_hi, M, N, N, BM, 32, 2, 64) || make_tmap_ex(&tmInLo, in_lo, M, N, N, BM, 32, 2, 64))
+    return 1;
+  GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.bias = bias;
+  p.in_stats = in_stats;
+  p.in_gamma = in_gamma;
+  p.in_beta = in_beta;
+  p.out_stats = out_stats;
+  p.ln_eps = eps;
+  p.ln_stats_ld = 12;
+  p.out = out_hi;
+  p.ldo = N;
+  p.vec_ok = 1;
+  p.debug = option_get(OPT_GEMM_DEBUG);
+  return launch_pair<EPI_RESID_HL, __nv_bfloat16, true>(stream, tmA, tmB, tmOutHi, tmInHi, p, &tmOutLo, &tmInLo);
+}
+
 int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
               const void* resid, long long ldr, void* out, long long ldo, int out_f32, int M, int N, int K, int epi) {
+  return gemm_bf16_folded(stream, A, lda, W, ldw, bias, resid, ldr, out, ldo, out_f32, M, N, K, epi, nullptr, nullptr, 0.f);
+}
+
+int gemm_bf16_folded(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                     const void* resid, long long ldr, void* out, long long ldo, int out_f32, int M, int N, int K, int epi,
+                     const float* ln_stats, const float* ln_c, float ln_eps, long long ln_stats_ld) {
+  RGQA_CHECK(ln_stats == nullptr || (bias != nullptr && K == 768 && epi != EPI_RESID),
+             "gemm_bf16: deferred LayerNorm needs K = 768, the folded bias and a non-residual epilogue");
   RGQA_CHECK(M > 0 && N > 0 && K > 0, "gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   RGQA_CHECK(K % BK == 0, "gemm_bf16: K=%d must be a multiple of %d", K, BK);
   RGQA_CHECK(epi != EPI_RESID || resid != nullptr, "gemm_bf16: EPI_RESID needs a residual pointer");
@@ -823,7 +1013,8 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
   const int esz = out_f32 ? 4 : 2;
   const bool out_al = (reinterpret_cast<uintptr_t>(out) % 16 == 0) && ((ldo * esz) % 16 == 0);
   const bool res_al = (resid == nullptr) || ((reinterpret_cast<uintptr_t>(resid) % 16 == 0) && ((ldr * 4) % 16 == 0));
-  const bool bias_al = (bias == nullptr) || (reinterpret_cast<uintptr_t>(bias) % 16 == 0);
+  const bool bias_al = ((bias == nullptr) || (reinterpret_cast<uintptr_t>(bias) % 16 == 0)) &&
+                       ((ln_c == nullptr) || (reinterpret_cast<uintptr_t>(ln_c) % 16 == 0));
   bool staged = use_pair && option_get(OPT_GEMM_STAGED) != 0 && out_al && res_al && bias_al;
   // the in-smem residual variant walks whole 128-column halves: ragged N falls back to the direct epilogue
   if (staged && epi == EPI_RESID && out_f32 && (N % 128 != 0)) staged = false;
@@ -840,7 +1031,7 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
   } else {
     tmRes = tmA;  // unused
   }
-  GemmParams p;
+  GemmParams p{};
   p.M = M;
   p.N = N;
   p.K = K;
@@ -849,6 +1040,10 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
   p.ldr = ldr;
   p.out = out;
   p.ldo = ldo;
+  p.ln_stats = ln_stats;
+  p.ln_c = ln_c;
+  p.ln_eps = ln_eps;
+  p.ln_stats_ld = ln_stats_ld > 0 ? ln_stats_ld : 12;
   p.vec_ok = (out_al && res_al && bias_al) ? 1 : 0;
   p.debug = option_get(OPT_GEMM_DEBUG);
   if (use_pair) return dispatch_pair(stream, tmA, tmB, tmOut, tmRes, p, epi, out_f32, staged);

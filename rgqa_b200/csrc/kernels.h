@@ -14,6 +14,7 @@ enum Epilogue : int {
   EPI_GELU = 1,   // out = gelu_erf(acc + bias)            (modeling.py:398-401 + :112-118)
   EPI_TANH = 2,   // out = tanh(acc + bias)                (modeling.py:575-581 pooler)
   EPI_RESID = 3,  // out = acc + bias + residual           (pre-LayerNorm sum of modeling.py:357-361 / :411-415)
+  EPI_RESID_HL = 4,  // same sum, residual recomputed from a deferred-LayerNorm hidden state, written as a bf16 hi/lo pair
 };
 
 enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
@@ -23,6 +24,26 @@ enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
 // resid fp32 [M,*] (EPI_RESID: the fp32 residual stream), out bf16 or fp32.
 int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
               const void* resid, long long ldr, void* out, long long ldo, int out_f32, int M, int N, int K, int epi);
+// Same GEMM with a DEFERRED LayerNorm on its A operand: A = bf16 of the pre-LayerNorm rows, W already scaled by gamma
+// and centred (fold_ln_weight), bias = b + W·beta, ln_stats = [M][6][2] partial (sum, sumsq) per row; the epilogue
+// computes rstd*acc + bias[n] before the activation.  ln_c (optional) = sum_k W'[n,k], the bf16 rounding residue of the
+// centring: when given, the epilogue also subtracts mu*c[n] from acc (exact form, one more FMA per element).  K = 768.
+int gemm_bf16_folded(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                     const void* resid, long long ldr, void* out, long long ldo, int out_f32, int M, int N, int K, int epi,
+                     const float* ln_stats, const float* ln_c, float ln_eps, long long ln_stats_ld = 12);
+// Producer of a deferred-LayerNorm hidden state: v = A·Wᵀ + bias + LN_prev(x_prev) with x_prev = in_hi + in_lo (bf16
+// pair), LN_prev from (in_stats, in_gamma, in_beta); writes v as out_hi = bf16(v), out_lo = bf16(v - out_hi) and the
+// partial (sum, sumsq) statistics [M][6][2].  N must be 768.
+int gemm_bf16_resid_hl(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                       const void* in_hi, const void* in_lo, const float* in_stats, const float* in_gamma,
+                       const float* in_beta, float eps, void* out_hi, void* out_lo, float* out_stats, int M, int N, int K);
+// W'[n,k] = bf16(W[n,k]*gamma[k] - mean_k(W[n,:]*gamma)), c[n] = sum_k float(W'[n,k]) (the bf16 rounding residue of the
+// centring), bias_out[n] = bias[n] + sum_k W[n,k]*beta[k]
+int fold_ln_weight(cudaStream_t stream, const float* W, const float* bias, const float* gamma, const float* beta, int N,
+                   int K, void* W_out_bf16, float* c_out, float* bias_out);
+// A normalised hidden state y (bf16 rows `hi` + their fp32 copy) as a deferred-LayerNorm state whose LayerNorm is the
+// identity: lo = bf16(y - hi), stats = (0, 768, 0, ...) so that mean = 0 and rstd = 1.
+int identity_state(cudaStream_t stream, const float* y_f32, const void* hi, void* lo, float* stats, long long M, int H);
 // fp32 SIMT path (precise mode): everything fp32.
 int gemm_f32(cudaStream_t stream, const float* A, long long lda, const float* W, long long ldw, const float* bias,
              const float* resid, long long ldr, float* out, long long ldo, int M, int N, int K, int epi);
@@ -88,7 +109,8 @@ int rowdot(cudaStream_t stream, const float* a, const float* b, float* out, int 
 
 
 // ---- runtime options (prof.cu): kernel-selection switches for A/B measurements ---------------------
-enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_GEMM_DEBUG = 2, OPT_PDL = 3, OPT_GEMM_LN = 4, OPT_TWO_STREAMS = 5, OPT_GRAPHS = 6, OPT_COUNT = 8 };
+enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_GEMM_DEBUG = 2, OPT_PDL = 3, OPT_GEMM_LN = 4, OPT_TWO_STREAMS = 5, OPT_GRAPHS = 6,
+  OPT_DEFER_LN = 7, OPT_COUNT = 8 };
 int option_get(int key);
 void option_set(int key, int value);
 

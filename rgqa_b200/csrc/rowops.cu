@@ -257,6 +257,49 @@ __global__ void gather_rows_kernel(const T* __restrict__ src, long long src_ld, 
   }
 }
 
+// LayerNorm folding into the consumer's weight (deferred LayerNorm): one warp per output row n
+__global__ void __launch_bounds__(128) fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      int N, int K, __nv_bfloat16* __restrict__ Wo,
+                                                      float* __restrict__ c_out, float* __restrict__ b_out) {
+  const int n = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  // centre the folded row: (x - mean(x)) · w == x · (w - mean(w)), so the consumer never needs the row mean
+  float ms = 0.f;
+  for (int k = lane; k < K; k += 32) ms = fmaf(W[static_cast<long long>(n) * K + k], gamma[k], ms);
+  const float wmean = warp_sum(ms) / static_cast<float>(K);
+  float cs = 0.f, bs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[static_cast<long long>(n) * K + k];
+    const __nv_bfloat16 wb = __float2bfloat16_rn(fmaf(w, gamma[k], -wmean));
+    Wo[static_cast<long long>(n) * K + k] = wb;
+    cs += __bfloat162float(wb);
+    bs = fmaf(w, beta[k], bs);
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) {
+    c_out[n] = cs;
+    b_out[n] = bias[n] + bs;
+  }
+}
+
+// identity deferred-LayerNorm state from a normalised row pair (bf16 hi + fp32 copy)
+__global__ void __launch_bounds__(256) identity_state_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict__ hi,
+                                                             __nv_bfloat16* __restrict__ lo, float* __restrict__ stats,
+                                                             long long n4, long long nstat, float width) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(y)[i];
+    const uint2 h = reinterpret_cast<const uint2*>(hi)[i];
+    const float2 h0 = unpack_bf16x2(h.x), h1 = unpack_bf16x2(h.y);
+    reinterpret_cast<uint2*>(lo)[i] = make_uint2(pack_bf16x2(v.x - h0.x, v.y - h0.y), pack_bf16x2(v.z - h1.x, v.w - h1.y));
+  }
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nstat; i += stride)
+    stats[i] = (i % 12 == 1) ? width : 0.f;
+}
+
 inline int row_grid(int rows) { return (rows + kWarpsPerBlock - 1) / kWarpsPerBlock; }
 
 }  // namespace
@@ -340,6 +383,29 @@ int uniter_img_combine(cudaStream_t stream, int out_dtype, const float* x_pre, c
   } else {
     RGQA_DISPATCH_ROW_SMEM(uniter_img_kernel, float, (pos_dim + 1) * H * sizeof(float), x_pre, pos, pos_dim, Wp, bp, g1, b1, g2, b2, type_row, g3, b3, static_cast<float*>(out), out32, M, H, eps);
   }
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int identity_state(cudaStream_t stream, const float* y_f32, const void* hi, void* lo, float* stats, long long M, int H) {
+  RGQA_CHECK(M > 0 && H % 4 == 0, "identity_state: bad shape");
+  const long long n4 = M * H / 4;
+  long long grid = (n4 + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  identity_state_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(y_f32, static_cast<const __nv_bfloat16*>(hi),
+                                                                       static_cast<__nv_bfloat16*>(lo), stats, n4, M * 12,
+                                                                       static_cast<float>(H));
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int fold_ln_weight(cudaStream_t stream, const float* W, const float* bias, const float* gamma, const float* beta, int N,
+                   int K, void* W_out_bf16, float* c_out, float* bias_out) {
+  RGQA_CHECK(N > 0 && K > 0, "fold_ln_weight: empty weight");
+  fold_ln_kernel<<<(N + 3) / 4, 128, 0, stream>>>(W, bias, gamma, beta, N, K, static_cast<__nv_bfloat16*>(W_out_bf16), c_out,
+                                                  bias_out);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;

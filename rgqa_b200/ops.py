@@ -68,6 +68,53 @@ def linear_residual_layernorm_bf16(x, weight, bias, residual, gamma, beta, eps=1
     return out, out32
 
 
+def fold_layernorm_weight(weight, bias, gamma, beta):
+    """(W' bf16 [N,K], c f32 [N], bias' f32 [N]) with the LayerNorm affine of the *input* folded into an nn.Linear:
+    LN(x)·Wᵀ + b = rstd·(x·W'ᵀ − mean·c) + bias', W' = bf16(W∘gamma − rowmean(W∘gamma)), c = rowsum(W') ≈ 0."""
+    _need_cuda(weight, bias, gamma, beta)
+    N, K = weight.shape
+    wf = torch.empty((N, K), dtype=torch.bfloat16, device=weight.device)
+    c = torch.empty(N, dtype=torch.float32, device=weight.device)
+    b2 = torch.empty(N, dtype=torch.float32, device=weight.device)
+    lib = L.load()
+    L.check(lib.rgqa_fold_ln_weight(L.current_stream_ptr(), L.ptr(weight), L.ptr(bias), L.ptr(gamma), L.ptr(beta), N, K,
+                                    L.ptr(wf), L.ptr(c), L.ptr(b2)), "rgqa_fold_ln_weight")
+    return wf, c, b2
+
+
+def linear_bf16_folded(x_hi, stats, w_folded, bias_folded, c=None, epilogue=L.EPI_BIAS, residual=None, out_dtype=torch.bfloat16,
+                       eps=1e-12):
+    """Consumer of a deferred-LayerNorm hidden state: epilogue(LN(x)·Wᵀ + b) from the un-normalised bf16 rows ``x_hi``,
+    their partial statistics ``stats`` [M,6,2] and the folded weight of :func:`fold_layernorm_weight`."""
+    _need_cuda(x_hi, stats, w_folded, c, bias_folded, residual)
+    M, K = x_hi.shape
+    N = w_folded.shape[0]
+    out = torch.empty((M, N), dtype=out_dtype, device=x_hi.device)
+    ldr = residual.stride(0) if residual is not None else 0
+    lib = L.load()
+    L.check(lib.rgqa_gemm_bf16_folded(L.current_stream_ptr(), L.ptr(x_hi), x_hi.stride(0), L.ptr(w_folded), w_folded.stride(0),
+                                      L.ptr(bias_folded), L.ptr(residual), ldr, L.ptr(out), out.stride(0), _dt(out), M, N, K,
+                                      epilogue, L.ptr(stats), L.ptr(c), eps), "rgqa_gemm_bf16_folded")
+    return out
+
+
+def linear_residual_hilo(x, weight, bias, in_hi, in_lo, in_stats, in_gamma, in_beta, eps=1e-12):
+    """Producer of a deferred-LayerNorm hidden state: v = x·Wᵀ + b + LN_prev(in_hi + in_lo); returns (hi, lo, stats)
+    with hi = bf16(v), lo = bf16(v − hi), stats [M,6,2] = per-128-column (sum, sumsq) of hi + lo."""
+    _need_cuda(x, weight, bias, in_hi, in_lo, in_stats, in_gamma, in_beta)
+    M, K = x.shape
+    N = weight.shape[0]
+    hi = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((M, 6, 2), dtype=torch.float32, device=x.device)
+    lib = L.load()
+    L.check(lib.rgqa_gemm_bf16_resid_hl(L.current_stream_ptr(), L.ptr(x), x.stride(0), L.ptr(weight), weight.stride(0),
+                                        L.ptr(bias), L.ptr(in_hi), L.ptr(in_lo), L.ptr(in_stats), L.ptr(in_gamma),
+                                        L.ptr(in_beta), eps, L.ptr(hi), L.ptr(lo), L.ptr(stats), M, N, K),
+            "rgqa_gemm_bf16_resid_hl")
+    return hi, lo, stats
+
+
 def linear_f32(x, weight, bias=None, epilogue=L.EPI_BIAS, residual=None):
     """fp32 CUDA-core GEMM with the same contract as :func:`linear_bf16` (precise path)."""
     _need_cuda(x, weight, bias, residual)

@@ -205,3 +205,45 @@ def test_small_batch_graph_replay_matches_eager(cuda_device):
     assert torch.equal(l, ref_b[1])
     p, l = run(b)
     assert torch.equal(l, ref_b[1])
+
+
+@pytest.mark.parametrize("B,L", [(64, 20), (40, 30)])
+def test_deferred_layernorm_forward_matches_oracle_and_standard_path(cuda_device, B, L):
+    """Batches with >= 1024 token rows can run WITHOUT LayerNorm kernels (option defer_ln: hidden states kept
+    pre-LayerNorm as bf16 hi/lo pairs + row statistics, gamma/beta folded into the consumer weights).
+    Same tolerances as the standard bf16 path, against the CPU oracle (first samples) and the fp32 CUDA path (all)."""
+    from oracle import lxmert_oracle as O
+    from rgqa_b200 import _lib as L_
+    lib = L_.load()
+    sd = _state("lxmert", "rich", 0.2)
+    inp = syn.make_inputs(B, L, seed=77 + B)
+    n_or = 6
+    ref_logits, ref_pooled = O.gqa_model_forward(sd, inp["feat"][:n_or], inp["pos"][:n_or], inp["ids"][:n_or], inp["seg"][:n_or],
+                                                 inp["mask"][:n_or])
+    p32, l32 = _run(_engine("lxmert", "rich", "fp32", 0.2), inp)
+    assert (l32[:n_or] - ref_logits).abs().max().item() <= 1e-3
+    eng = _engine("lxmert", "rich", "bf16", 0.2)
+    try:
+        lib.rgqa_set_option(b"defer_ln", 0)
+        n0 = lib.rgqa_launch_count()
+        p_std, l_std = _run(eng, inp)
+        n_std = lib.rgqa_launch_count() - n0
+        lib.rgqa_set_option(b"defer_ln", 1)
+        n0 = lib.rgqa_launch_count()
+        p_def, l_def = _run(eng, inp)
+        n_def = lib.rgqa_launch_count() - n0
+        p_def2, l_def2 = _run(eng, inp)     # second call of the shape: CUDA-graph capture + replay (B <= 128)
+        p_def3, l_def3 = _run(eng, inp)
+    finally:
+        lib.rgqa_set_option(b"defer_ln", 0)
+    assert n_def < n_std - 40, (n_def, n_std)          # the 53 LayerNorm launches are gone
+    _assert_bf16_close(l_def[:n_or].numpy(), ref_logits.numpy(), scale=10.0)
+    _assert_bf16_close(l_def.numpy(), l32.numpy(), scale=10.0)
+    e_std = float((l_std - l32).pow(2).mean().sqrt())
+    e_def = float((l_def - l32).pow(2).mean().sqrt())
+    assert e_def <= 1.3 * e_std + 1e-3, (e_def, e_std)  # no precision lost against the LayerNorm-kernel path
+    assert (p_def - p32).abs().max().item() <= 3e-2
+    assert torch.equal(l_def2, l_def) and torch.equal(l_def3, l_def) and torch.equal(p_def3, p_def)
+    top2 = l32.topk(2).values
+    confident = (top2[:, 0] - top2[:, 1]) > 0.4
+    assert torch.equal(l_def.argmax(1)[confident], l32.argmax(1)[confident])

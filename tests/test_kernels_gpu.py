@@ -90,6 +90,72 @@ def test_gemm_ln_fused_matches_torch(cuda_device, M, K):
     assert torch.equal(out, out32.to(torch.bfloat16))               # the two copies are the same numbers
 
 
+def _hilo_state(M, g, device, mean=0.2, scale=1.5):
+    """A deferred-LayerNorm hidden state: (x f64, hi, lo, stats[M,6,2]) for random pre-LayerNorm rows."""
+    x = torch.randn(M, 768, generator=g) * scale + mean
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    v = (hi.float() + lo.float()).double()
+    stats = torch.stack([v.view(M, 6, 128).sum(-1), (v * v).view(M, 6, 128).sum(-1)], dim=-1).float()
+    return v, hi.to(device), lo.to(device), stats.contiguous().to(device)
+
+
+@pytest.mark.parametrize("M,N,epi", [(2048, 2304, "bias"), (1500, 3072, "gelu"), (300, 768, "bias"), (1024, 768, "bias")])
+def test_gemm_folded_layernorm_consumer(cuda_device, M, N, epi):
+    """LN(x)·Wᵀ + b computed from the un-normalised bf16 rows + row statistics with gamma folded into W
+    (the consumer half of the deferred LayerNorm; reference modules modeling.py:321-323 / :399 after :361 / :415)."""
+    from rgqa_b200 import ops, _lib as L
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    v, hi, lo, stats = _hilo_state(M, g, cuda_device)
+    w = (torch.randn(N, 768, generator=g) * 0.03).to(cuda_device)
+    bias = (torch.randn(N, generator=g) * 0.1).to(cuda_device)
+    gamma = (1 + 0.1 * torch.randn(768, generator=g)).to(cuda_device)
+    beta = (0.1 * torch.randn(768, generator=g)).to(cuda_device)
+    wf, c, b2 = ops.fold_layernorm_weight(w, bias, gamma, beta)
+    torch.cuda.synchronize()
+    wg = w.double() * gamma.double()
+    assert (wf.double() - (wg - wg.mean(1, keepdim=True))).abs().max().item() <= 2.0 ** -9 * wg.abs().max().item()
+    torch.testing.assert_close(c, wf.float().sum(1), atol=1e-4, rtol=1e-5)
+    assert c.abs().max().item() <= 5e-3     # rows are centred up to the bf16 rounding of 768 entries
+    torch.testing.assert_close(b2.double(), bias.double() + w.double() @ beta.double(), atol=1e-5, rtol=1e-5)
+    code = {"bias": L.EPI_BIAS, "gelu": L.EPI_GELU}[epi]
+    out = ops.linear_bf16_folded(hi, stats, wf, b2, epilogue=code, out_dtype=torch.float32)
+    out_c = ops.linear_bf16_folded(hi, stats, wf, b2, c=c, epilogue=code, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert (out - out_c).abs().max().item() <= 5e-3     # the dropped mean·c term is below the bf16 noise
+    y = torch.nn.functional.layer_norm(v.to(cuda_device), (768,), gamma.double(), beta.double(), eps=1e-12)
+    ref = y @ w.double().t() + bias.double()
+    if epi == "gelu":
+        ref = _gelu_erf(ref)
+    err = (out.double() - ref).abs()
+    # bf16 rounding of the 768 operands (x and W·gamma): same error class as the un-folded bf16 GEMM
+    assert err.max().item() <= 3e-2 and err.pow(2).mean().sqrt().item() <= 5e-3, (err.max().item(), err.pow(2).mean().sqrt().item())
+
+
+@pytest.mark.parametrize("M,K", [(1024, 768), (2048, 3072), (1300, 768)])
+def test_gemm_residual_hilo_producer(cuda_device, M, K):
+    """v = A·Wᵀ + b + LN_prev(x_prev) written as a bf16 hi/lo pair + partial statistics (the producer half of the
+    deferred LayerNorm: BertAttOutput / BertOutput modeling.py:357-361, :411-415 up to — not including — the LayerNorm)."""
+    from rgqa_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + K)
+    v_in, hi_in, lo_in, st_in = _hilo_state(M, g, cuda_device)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    w = (torch.randn(768, K, generator=g) * 0.03).to(torch.bfloat16).to(cuda_device)
+    bias = (torch.randn(768, generator=g) * 0.1).to(cuda_device)
+    gamma = (1 + 0.1 * torch.randn(768, generator=g)).to(cuda_device)
+    beta = (0.1 * torch.randn(768, generator=g)).to(cuda_device)
+    hi, lo, stats = ops.linear_residual_hilo(a, w, bias, hi_in, lo_in, st_in, gamma, beta)
+    torch.cuda.synchronize()
+    resid = torch.nn.functional.layer_norm(v_in.to(cuda_device), (768,), gamma.double(), beta.double(), eps=1e-12)
+    ref = a.double() @ w.double().t() + bias.double() + resid
+    got = hi.double() + lo.double()
+    err = (got - ref).abs()
+    assert err.max().item() <= 2e-3, err.max().item()          # fp32 accumulation + the 2^-17 hi/lo split
+    assert (lo.float().abs() <= hi.float().abs() * 2.0 ** -8 + 1e-30).all()   # lo is the rounding remainder of hi
+    want = torch.stack([got.view(M, 6, 128).sum(-1), (got * got).view(M, 6, 128).sum(-1)], dim=-1)
+    torch.testing.assert_close(stats.double(), want, atol=2e-2, rtol=2e-4)
+
+
 @pytest.mark.parametrize("M,N,K,epi", [(77, 130, 96, "bias"), (640, 768, 3072, "resid"), (33, 1842, 1536, "bias"),
                                       (64, 768, 768, "gelu"), (32, 768, 768, "tanh")])
 def test_gemm_f32_matches_torch(cuda_device, M, N, K, epi):
