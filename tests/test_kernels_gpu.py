@@ -114,9 +114,10 @@ def test_gemm_folded_layernorm_consumer(cuda_device, M, N, epi):
     wf, c, b2 = ops.fold_layernorm_weight(w, bias, gamma, beta)
     torch.cuda.synchronize()
     wg = w.double() * gamma.double()
-    assert (wf.double() - (wg - wg.mean(1, keepdim=True))).abs().max().item() <= 2.0 ** -9 * wg.abs().max().item()
+    # one bf16 ulp (the fp32 fold may round the other way than this fp64 statement on a tie)
+    assert (wf.double() - (wg - wg.mean(1, keepdim=True))).abs().max().item() <= 2.0 ** -8 * 1.01 * wg.abs().max().item()
     torch.testing.assert_close(c, wf.float().sum(1), atol=1e-4, rtol=1e-5)
-    assert c.abs().max().item() <= 5e-3     # rows are centred up to the bf16 rounding of 768 entries
+    assert c.abs().max().item() <= 1e-2     # rows are centred up to the bf16 rounding of 768 entries (sigma ~1e-3)
     torch.testing.assert_close(b2.double(), bias.double() + w.double() @ beta.double(), atol=1e-5, rtol=1e-5)
     code = {"bias": L.EPI_BIAS, "gelu": L.EPI_GELU}[epi]
     out = ops.linear_bf16_folded(hi, stats, wf, b2, epilogue=code, out_dtype=torch.float32)
