@@ -226,7 +226,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+  // relaxed: the barrier hands over TMEM / smem-stage ownership that tcgen05 fences already order; a release here costs a
+  // MEMBAR.ALL + ERRBAR per arrival (12 % of the epilogue warps' samples in the FFN1 GEMM, profiles/README.md)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
 // TMA load whose completion bytes are credited to an mbarrier that may live in the PEER CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* desc, uint32_t cluster_bar_addr, int32_t c0,

@@ -101,6 +101,28 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(fabsf(h), erf_abs, h);
 }
 
+// Two elements per instruction on Blackwell's packed-fp32 pipe (FFMA2 / FMUL2): same formula as gelu_erf_fast, 18
+// issue slots per pair instead of 26.
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 d = __ffma2_rn(make_float2(0.3275911f * 0.70710678118654752440f, 0.3275911f * 0.70710678118654752440f), ax,
+                              make_float2(1.0f, 1.0f));
+  const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+  // the polynomial with negated coefficients: q = -(a1 t + ... + a5 t^5)
+  float2 q = __ffma2_rn(make_float2(-1.061405429f, -1.061405429f), t, make_float2(1.453152027f, 1.453152027f));
+  q = __ffma2_rn(q, t, make_float2(-1.421413741f, -1.421413741f));
+  q = __ffma2_rn(q, t, make_float2(0.284496736f, 0.284496736f));
+  q = __ffma2_rn(q, t, make_float2(-0.254829592f, -0.254829592f));
+  q = __fmul2_rn(q, t);
+  float2 a = __fmul2_rn(x, make_float2(-0.72134752044448170368f, -0.72134752044448170368f));
+  a = __fmul2_rn(a, x);  // -x^2 * log2(e) / 2
+  const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+  const float2 erf_abs = __ffma2_rn(q, e, make_float2(1.0f, 1.0f));
+  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  const float2 ah = __fmul2_rn(ax, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(ah, erf_abs, h);
+}
+
 template <int EPI>
 __device__ __forceinline__ float apply_act(float v) {
   if constexpr (EPI == EPI_GELU) return gelu_erf_fast(v);
@@ -158,10 +180,13 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&v)[32], float (&f
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 b = __ldg(b4 + i);
-        f[4 * i + 0] = fmaf(rn.rstd, f[4 * i + 0], b.x);  // rstd == 1 outside the deferred-LayerNorm consumers
-        f[4 * i + 1] = fmaf(rn.rstd, f[4 * i + 1], b.y);
-        f[4 * i + 2] = fmaf(rn.rstd, f[4 * i + 2], b.z);
-        f[4 * i + 3] = fmaf(rn.rstd, f[4 * i + 3], b.w);
+        // rstd == 1 outside the deferred-LayerNorm consumers; packed fp32 (FFMA2): two columns per instruction
+        const float2 lo2 = __ffma2_rn(make_float2(rn.rstd, rn.rstd), make_float2(f[4 * i + 0], f[4 * i + 1]), make_float2(b.x, b.y));
+        const float2 hi2 = __ffma2_rn(make_float2(rn.rstd, rn.rstd), make_float2(f[4 * i + 2], f[4 * i + 3]), make_float2(b.z, b.w));
+        f[4 * i + 0] = lo2.x;
+        f[4 * i + 1] = lo2.y;
+        f[4 * i + 2] = hi2.x;
+        f[4 * i + 3] = hi2.y;
       }
     }
     if constexpr (EPI == EPI_RESID) {
@@ -189,8 +214,17 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&v)[32], float (&f
       }
     }
   }
+  if constexpr (EPI == EPI_GELU) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = apply_act<EPI>(f[i]);
+    for (int i = 0; i < 32; i += 2) {
+      const float2 g = gelu_erf_fast2(make_float2(f[i], f[i + 1]));
+      f[i] = g.x;
+      f[i + 1] = g.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = apply_act<EPI>(f[i]);
+  }
 }
 
 // direct path: one 32-column chunk straight to global memory (vector stores when aligned, else scalar, guarded)
@@ -428,16 +462,18 @@ constexpr int kPairStageBytes = BM * BK * 2 + (kPairBN / 2) * BK * 2;  // 16 KB 
 // its 4 stages more than the epilogue needs a deeper residual prefetch)
 constexpr int kResidRing = 3;
 constexpr int kResidStages = 4;
-template <bool STAGED, bool RESID_SMEM, int EW>
+// RING = 2 (K >= 2048): one residual slab of prefetch is enough when a tile's main loop lasts 48 k-blocks, and the
+// smem it frees buys a fifth main-loop stage.
+template <bool STAGED, bool RESID_SMEM, int EW, int RING = kResidRing>
 struct PairCfg {
   static constexpr int kGroups = EW / 4;
-  static constexpr int kStages = RESID_SMEM ? kResidStages : (STAGED ? 5 : 6);
-  static constexpr int kBufsPerGroup = RESID_SMEM ? kResidRing : (STAGED ? (EW == 16 ? 1 : 2) : 0);
+  static constexpr int kStages = RESID_SMEM ? (RING == 2 ? kResidStages + 1 : kResidStages) : (STAGED ? 5 : 6);
+  static constexpr int kBufsPerGroup = RESID_SMEM ? RING : (STAGED ? (EW == 16 ? 1 : 2) : 0);
   static constexpr int kSlabRegion = kGroups * kBufsPerGroup * kSlabBytes;
-  static constexpr int kSmemBytes = kStages * kPairStageBytes + kSlabRegion + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kPairStageBytes + kSlabRegion + 1024 + 512;
 };
 
-template <int EPI, typename OutT, bool STAGED, int EW>
+template <int EPI, typename OutT, bool STAGED, int EW, int RING>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + EW) * 32, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -446,7 +482,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   constexpr bool kHiLo = STAGED && EPI == EPI_RESID_HL;  // deferred-LayerNorm producer (bf16 hi/lo pair + statistics)
   constexpr bool kResidSmem = (STAGED && EPI == EPI_RESID && sizeof(OutT) == 4) || kHiLo;
   static_assert(EW == 8 || (EW == 16 && STAGED && !kResidSmem), "16 epilogue warps: staged, non-residual epilogues only");
-  using PC = PairCfg<STAGED, kResidSmem, EW>;
+  using PC = PairCfg<STAGED, kResidSmem, EW, RING>;
+  constexpr int kRing = RING;
   constexpr int kStages = PC::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -456,8 +493,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* resid_bar = tmem_empty_bar + 2;  // [2 halves][kResidRing], used by the RESID_SMEM epilogue only
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(resid_bar + 2 * kResidRing);
+  uint64_t* resid_bar = tmem_empty_bar + 2;  // [EW warps][kRing], used by the RESID_SMEM epilogue only
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(resid_bar + EW * kRing);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -489,7 +526,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 2 * EW);  // epilogue warps of both CTAs
     }
-    for (int i = 0; i < 2 * kResidRing; ++i) mbar_init(&resid_bar[i], 1);
+    for (int i = 0; i < EW * kRing; ++i) mbar_init(&resid_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<512>(tmem_ptr_smem);
@@ -566,7 +603,10 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     constexpr int kColsPerWarp = kPairBN / (EW / 4);
     const uint32_t leader_tmem_empty0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t leader_tmem_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
-    [[maybe_unused]] const bool issuer = (quarter == 0 && lane == 0);
+    // Every epilogue warp owns its 32 rows of each slab end to end: it loads (residual), fills and TMA-stores that
+    // 32-row sub-slab itself, so the warps of a CTA never wait for each other (no named barriers in the epilogue).
+    [[maybe_unused]] const bool issuer = (lane == 0);
+    [[maybe_unused]] constexpr int kSubSlab = kSlabBytes / 4;  // this warp's 32 rows of a slab
     [[maybe_unused]] int slab_ctr = 0;
     if constexpr (kResidSmem) {
       // flat sequence of (tile, 32-column slab) for this column half; 4 slabs per tile
@@ -575,49 +615,50 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int r_local = quarter * 32 + lane;
       auto coords = [&](int k, int& row0, int& col) {
         const int t = pair + (k >> 2) * num_pairs;
-        row0 = (t / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        row0 = (t / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM + quarter * 32;  // this warp's first row
         col = (t % tiles_n) * kPairBN + half * kColsPerWarp + (k & 3) * 32;
       };
       auto issue_load = [&](int k) {
         int row0, col;
         coords(k, row0, col);
-        const int b = k % kResidRing;
-        mbar_expect_tx(&resid_bar[half * kResidRing + b], kSlabBytes);
-        uint8_t* dst = slabs + (half * kResidRing + b) * kSlabBytes;
+        const int b = k % kRing;
+        uint64_t* bar = &resid_bar[e * kRing + b];
+        mbar_expect_tx(bar, kSubSlab);
+        uint8_t* dst = slabs + (half * kRing + b) * kSlabBytes;
         if constexpr (kHiLo) {  // hi rows then lo rows, 128 x 64 B each, 64-byte swizzle
-          tma_load_2d(dst, &tmRes, &resid_bar[half * kResidRing + b], col, row0);
-          tma_load_2d(dst + kSlabBytes / 2, &tmResLo, &resid_bar[half * kResidRing + b], col, row0);
+          tma_load_2d(dst + quarter * (kSubSlab / 2), &tmRes, bar, col, row0);
+          tma_load_2d(dst + kSlabBytes / 2 + quarter * (kSubSlab / 2), &tmResLo, bar, col, row0);
         } else {
-          tma_load_2d(dst, &tmRes, &resid_bar[half * kResidRing + b], col, row0);
+          tma_load_2d(dst + quarter * kSubSlab, &tmRes, bar, col, row0);
         }
       };
       if (issuer) {
         if (total > 0) issue_load(0);
-        for (int j = 1; j < kResidRing - 1; ++j)
+        for (int j = 1; j < kRing - 1; ++j)
           if (total > j) issue_load(j);
       }
       [[maybe_unused]] RowNorm rin{0.f, 1.f};
-      [[maybe_unused]] float st_sum = 0.f, st_sq = 0.f;
+      [[maybe_unused]] float2 st_sum2 = make_float2(0.f, 0.f), st_sq2 = make_float2(0.f, 0.f);
       for (int k = 0; k < total; ++k) {
         const int itile = k >> 2, sl = k & 3;
         const int acc = itile & 1;
         int row0, col;
         coords(k, row0, col);
-        const int row = row0 + r_local;
+        const int row = row0 + lane;
         if (sl == 0) {
           if constexpr (kHiLo) {
             rin = row_norm(p.in_stats, row, row < p.M, p.ln_eps);
-            st_sum = st_sq = 0.f;
+            st_sum2 = st_sq2 = make_float2(0.f, 0.f);
           }
           mbar_wait(&tmem_full_bar[acc], (itile >> 1) & 1u);
           tc_fence_after();
         }
-        const int b = k % kResidRing;
-        uint8_t* buf = slabs + (half * kResidRing + b) * kSlabBytes;
+        const int b = k % kRing;
+        uint8_t* buf = slabs + (half * kRing + b) * kSlabBytes;
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                       static_cast<uint32_t>(acc * kPairBN + half * kColsPerWarp + sl * 32), v);
-        mbar_wait(&resid_bar[half * kResidRing + b], (k / kResidRing) & 1u);  // this slab's residual rows have landed
+        mbar_wait(&resid_bar[e * kRing + b], (k / kRing) & 1u);  // this warp's residual rows have landed
         tmem_ld_wait_dep(v);
         float f[32];
         if constexpr (kHiLo) {
@@ -643,26 +684,30 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const float4 bb = __ldg(b4 + i), gg = __ldg(g4 + i), ee = __ldg(e4 + i);
             const float2 h0 = unpack_bf16x2(hw[2 * i]), l0 = unpack_bf16x2(lw[2 * i]);
             const float2 h1 = unpack_bf16x2(hw[2 * i + 1]), l1 = unpack_bf16x2(lw[2 * i + 1]);
-            const float r0 = fmaf(fmaf(h0.x + l0.x, ra, rb), gg.x, ee.x);
-            const float r1 = fmaf(fmaf(h0.y + l0.y, ra, rb), gg.y, ee.y);
-            const float r2 = fmaf(fmaf(h1.x + l1.x, ra, rb), gg.z, ee.z);
-            const float r3 = fmaf(fmaf(h1.y + l1.y, ra, rb), gg.w, ee.w);
-            f[4 * i + 0] = (__uint_as_float(v[4 * i + 0]) + bb.x) + r0;
-            f[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) + bb.y) + r1;
-            f[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + bb.z) + r2;
-            f[4 * i + 3] = (__uint_as_float(v[4 * i + 3]) + bb.w) + r3;
+            // packed fp32 math (FFMA2 / FADD2): two columns per instruction
+            const float2 ra2 = make_float2(ra, ra), rb2 = make_float2(rb, rb);
+            const float2 ra0 = __ffma2_rn(__ffma2_rn(__fadd2_rn(h0, l0), ra2, rb2), make_float2(gg.x, gg.y), make_float2(ee.x, ee.y));
+            const float2 ra1 = __ffma2_rn(__ffma2_rn(__fadd2_rn(h1, l1), ra2, rb2), make_float2(gg.z, gg.w), make_float2(ee.z, ee.w));
+            const float2 o0 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1])),
+                                                    make_float2(bb.x, bb.y)), ra0);
+            const float2 o1 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])),
+                                                    make_float2(bb.z, bb.w)), ra1);
+            f[4 * i + 0] = o0.x;
+            f[4 * i + 1] = o0.y;
+            f[4 * i + 2] = o1.x;
+            f[4 * i + 3] = o1.y;
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint32_t ho[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float a = f[8 * i + 2 * j], b = f[8 * i + 2 * j + 1];
-              st_sum += a + b;
-              st_sq = fmaf(a, a, fmaf(b, b, st_sq));
-              ho[j] = pack_bf16x2(a, b);
-              const float2 hb = unpack_bf16x2(ho[j]);
-              lo[j] = pack_bf16x2(a - hb.x, b - hb.y);
+              const float2 ab = make_float2(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
+              st_sum2 = __fadd2_rn(st_sum2, ab);
+              st_sq2 = __ffma2_rn(ab, ab, st_sq2);
+              ho[j] = pack_bf16x2(ab.x, ab.y);
+              const float2 rem = __ffma2_rn(unpack_bf16x2(ho[j]), make_float2(-1.0f, -1.0f), ab);
+              lo[j] = pack_bf16x2(rem.x, rem.y);
             }
             *reinterpret_cast<uint4*>(hrow + ((i ^ sw) << 4)) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
             *reinterpret_cast<uint4*>(lrow + ((i ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -670,7 +715,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (sl == 3 && row < p.M) {  // this thread's 128 columns of the row are done: publish their partial statistics
             float2* so = reinterpret_cast<float2*>(p.out_stats + static_cast<long long>(row) * 12) +
                          (((pair + itile * num_pairs) % tiles_n) * 2 + half);
-            *so = make_float2(st_sum, st_sq);
+            *so = make_float2(st_sum2.x + st_sum2.y, st_sq2.x + st_sq2.y);
           }
         } else {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
@@ -681,10 +726,14 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias != nullptr) bb = __ldg(b4 + i);
             const float4 rr = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 4));
-            f[4 * i + 0] = (__uint_as_float(v[4 * i + 0]) + bb.x) + rr.x;
-            f[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) + bb.y) + rr.y;
-            f[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + bb.z) + rr.z;
-            f[4 * i + 3] = (__uint_as_float(v[4 * i + 3]) + bb.w) + rr.w;
+            const float2 o0 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1])),
+                                                    make_float2(bb.x, bb.y)), make_float2(rr.x, rr.y));
+            const float2 o1 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])),
+                                                    make_float2(bb.z, bb.w)), make_float2(rr.z, rr.w));
+            f[4 * i + 0] = o0.x;
+            f[4 * i + 1] = o0.y;
+            f[4 * i + 2] = o1.x;
+            f[4 * i + 3] = o1.y;
           }
           store_chunk_swizzled<float>(buf, r_local, 0, f);  // in place: this thread's own row
         }
@@ -695,16 +744,20 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (lane == 0) mbar_arrive_cluster(acc == 0 ? leader_tmem_empty0 : leader_tmem_empty1);
         }
         fence_proxy_async_smem();
-        named_bar_sync(1 + half, 128);
+        __syncwarp();
         if (issuer) {
           if (row0 < p.M) {
-            tma_store_2d(&tmOut, buf, col, row0);
-            if constexpr (kHiLo) tma_store_2d(&tmOutLo, buf + kSlabBytes / 2, col, row0);
+            if constexpr (kHiLo) {
+              tma_store_2d(&tmOut, buf + quarter * (kSubSlab / 2), col, row0);
+              tma_store_2d(&tmOutLo, buf + kSlabBytes / 2 + quarter * (kSubSlab / 2), col, row0);
+            } else {
+              tma_store_2d(&tmOut, buf + quarter * kSubSlab, col, row0);
+            }
           }
           tma_store_commit();
-          if (k + kResidRing - 1 < total) {
+          if (k + kRing - 1 < total) {
             tma_store_wait_read<1>();  // the store of slab k-1 has drained the buffer slab k+2 will land in
-            issue_load(k + kResidRing - 1);
+            issue_load(k + kRing - 1);
           }
         }
       }
@@ -728,15 +781,15 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         constexpr int kColsPerSlab = 128 / static_cast<int>(sizeof(OutT));  // 64 bf16 / 32 fp32
         constexpr int kChunksPerSlab = kColsPerSlab / 32;
         constexpr int kSlabsPerHalf = kColsPerWarp / kColsPerSlab;
-        const bool tile_rows_live = m0 < p.M;  // a fully out-of-range row block stores nothing (TMA would clip anyway)
+        const bool tile_rows_live = m0 + quarter * 32 < p.M;  // out-of-range rows store nothing (TMA would clip anyway)
 #pragma unroll 1
         for (int sl = 0; sl < kSlabsPerHalf; ++sl) {
           const int col_slab = n0 + half * kColsPerWarp + sl * kColsPerSlab;
           if (col_slab >= p.N) break;  // uniform over the 4 warps of this half
           constexpr int kBufs = PC::kBufsPerGroup;
           uint8_t* buf = slabs + (half * kBufs + (slab_ctr % kBufs)) * kSlabBytes;
-          if (issuer) tma_store_wait_read<kBufs - 1>();  // the store that last read this buffer is done with it
-          named_bar_sync(1 + half, 128);
+          if (issuer) tma_store_wait_read<kBufs - 1>();  // this warp's store that last read the buffer is done with it
+          __syncwarp();
           // both 32-column chunks of the slab are requested from TMEM before either is consumed
           uint32_t v[kChunksPerSlab][32];
 #pragma unroll
@@ -752,9 +805,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             store_chunk_swizzled<OutT>(buf, r_local, cc, f);
           }
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-          named_bar_sync(1 + half, 128);
+          __syncwarp();
           if (issuer && tile_rows_live && !(p.debug & 1)) {
-            tma_store_2d(&tmOut, buf, col_slab, m0);
+            tma_store_2d(&tmOut, buf + quarter * kSubSlab, col_slab, m0 + quarter * 32);
             tma_store_commit();
           }
           ++slab_ctr;
@@ -897,16 +950,16 @@ int dispatch_epi(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, con
   }
 }
 
-template <int EPI, typename OutT, bool STAGED>
+template <int EPI, typename OutT, bool STAGED, int RING = kResidRing>
 int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                 const CUtensorMap& tmRes, const GemmParams& p, const CUtensorMap* tmOutLo = nullptr,
                 const CUtensorMap* tmResLo = nullptr) {
   // 16 epilogue warps were measured on B200 (bf16 outputs): FFN1 1043 vs 1056 TFLOP/s, QKV 1180 vs 1274 — no gain,
   // the erf-GELU epilogue is bound by its dependent FMA/MUFU chains, not by warps in flight.  8 it is.
   constexpr int EW = 8;
-  auto kern = gemm_bf16_pair_kernel<EPI, OutT, STAGED, EW>;
+  auto kern = gemm_bf16_pair_kernel<EPI, OutT, STAGED, EW, RING>;
   constexpr int smem =
-      PairCfg<STAGED, (STAGED && ((EPI == EPI_RESID && sizeof(OutT) == 4) || EPI == EPI_RESID_HL)), EW>::kSmemBytes;
+      PairCfg<STAGED, (STAGED && ((EPI == EPI_RESID && sizeof(OutT) == 4) || EPI == EPI_RESID_HL)), EW, RING>::kSmemBytes;
   static bool configured = false;
   if (!configured) {
     RGQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -927,6 +980,9 @@ int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& 
 template <int EPI, typename OutT>
 int launch_pair_sel(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& r,
                     const GemmParams& p, bool staged) {
+  if constexpr (EPI == EPI_RESID && sizeof(OutT) == 4) {
+    if (staged && p.K >= 2048) return launch_pair<EPI, OutT, true, 2>(s, a, b, o, r, p);
+  }
   return staged ? launch_pair<EPI, OutT, true>(s, a, b, o, r, p) : launch_pair<EPI, OutT, false>(s, a, b, o, r, p);
 }
 
@@ -963,9 +1019,9 @@ int gemm_bf16_resid_hl(cudaStream_t stream, const void* A, long long lda, const 
   CUtensorMap tmA, tmB, tmOutHi, tmOutLo, tmInHi, tmInLo;
   if (make_tmap(&tmA, A, M, K, lda, BM, 2)) return 1;
   if (make_tmap(&tmB, W, N, K, ldw, kPairBN / 2, 2)) return 1;
-  // 128 rows x 32 bf16 columns (64 B), 64-byte swizzle: hi and lo halves of one 32-column slab
-  if (make_tmap_ex(&tmOutHi, out_hi, M, N, N, BM, 32, 2, 64) || make_tmap_ex(&tmOutLo, out_lo, M, N, N, BM, 32, 2, 64) ||
-      make_tmap_ex(&tmInHi, in_hi, M, N, N, BM, 32, 2, 64) || make_tmap_ex(&tmInLo, in_lo, M, N, N, BM, 32, 2, 64))
+  // 32 rows (one epilogue warp) x 32 bf16 columns (64 B), 64-byte swizzle: hi and lo halves of a 32-column slab
+  if (make_tmap_ex(&tmOutHi, out_hi, M, N, N, 32, 32, 2, 64) || make_tmap_ex(&tmOutLo, out_lo, M, N, N, 32, 32, 2, 64) ||
+      make_tmap_ex(&tmInHi, in_hi, M, N, N, 32, 32, 2, 64) || make_tmap_ex(&tmInLo, in_lo, M, N, N, 32, 32, 2, 64))
     return 1;
   GemmParams p{};
   p.M = M;
@@ -982,6 +1038,7 @@ int gemm_bf16_resid_hl(cudaStream_t stream, const void* A, long long lda, const 
   p.ldo = N;
   p.vec_ok = 1;
   p.debug = option_get(OPT_GEMM_DEBUG);
+  if (K >= 2048) return launch_pair<EPI_RESID_HL, __nv_bfloat16, true, 2>(stream, tmA, tmB, tmOutHi, tmInHi, p, &tmOutLo, &tmInLo);
   return launch_pair<EPI_RESID_HL, __nv_bfloat16, true>(stream, tmA, tmB, tmOutHi, tmInHi, p, &tmOutLo, &tmInLo);
 }
 
@@ -1022,12 +1079,12 @@ int gemm_bf16_folded(cudaStream_t stream, const void* A, long long lda, const vo
   if (make_tmap(&tmA, A, M, K, lda, BM, 2)) return 1;
   if (make_tmap(&tmB, W, N, K, ldw, use_pair ? kPairBN / 2 : bn, 2)) return 1;
   if (staged) {
-    if (make_tmap(&tmOut, out, M, N, ldo, BM, esz)) return 1;
+    if (make_tmap(&tmOut, out, M, N, ldo, 32, esz)) return 1;  // one epilogue warp's rows per store
   } else {
     tmOut = tmA;  // unused by the direct epilogue
   }
   if (staged && epi == EPI_RESID && out_f32) {
-    if (make_tmap(&tmRes, resid, M, N, ldr, BM, 4)) return 1;
+    if (make_tmap(&tmRes, resid, M, N, ldr, 32, 4)) return 1;
   } else {
     tmRes = tmA;  // unused
   }
