@@ -1238,6 +1238,10 @@ int rgqa_set_option(const char* name, int value) {
     option_set(OPT_DEFER_LN, value);
     return 0;
   }
+  if (strcmp(name, "attn_tma") == 0) {
+    option_set(OPT_ATTN_TMA, value);
+    return 0;
+  }
   if (strcmp(name, "two_streams") == 0) {
     option_set(OPT_TWO_STREAMS, value);
     return 0;

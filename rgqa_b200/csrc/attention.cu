@@ -9,6 +9,10 @@
 // shared-memory column so the softmax is the exact two-pass max/sum form in fp32.
 // Q/K/V are read straight out of the fused [tokens, 3*768] projection buffer (strided rows), so no
 // transpose / permute / contiguous copies exist (the reference makes four per call, :315-318,:344).
+#include <cuda.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -173,8 +177,10 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                : "r"(smem_u32(smem_row)));
 }
 
+// 4 CTAs (16 warps) per SM: the kernel is bound by loads in flight (46 % of its stall samples are long-scoreboard
+// waits at 12 warps / SM), so the register budget is capped at 128 and the shared-memory carve-out is maximised.
 template <int KS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 attention_mma_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ k,
                      long long ldk, const __nv_bfloat16* __restrict__ v, long long ldv,
                      const int32_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out, long long ldo, int Lq,
@@ -315,6 +321,303 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const _
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA-fed persistent variant (large batches).  The per-warp kernel above spends 46 % of its stall samples waiting for
+// its own loads (12-16 warps / SM, each load -> compute -> store in sequence).  Here one CTA per SM streams through a
+// contiguous range of (sample, head) units.  Each of the kAttnWarps compute warps owns DEPTH slots of shared memory
+// (Q, K, V tiles of one unit: [L rows x 128 B], 128-byte swizzle -> conflict-free ldmatrix); a producer warp TMA-loads
+// unit i into slot (i / W) % DEPTH of warp i % W, so every warp always has its next unit(s) in flight while it computes,
+// and every mbarrier has exactly one producer and one consumer walking it in order.  The output tile is written over the
+// consumed Q rows (same swizzle) and leaves through a TMA store; the slot goes back to the producer when that store has
+// read it.  Tiles are exactly L rows: fragment rows beyond a tile (query / key padding up to a multiple of 16) alias the
+// next tile -- always finite bf16 data or the zeros of the one-time clear -- under a score of -inf / probability 0 /
+// a row guard, so they never reach the output.  The swizzle is computed from absolute shared-memory address bits (what
+// the TMA unit does), which is why tiles need only 128-byte alignment.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAttnWarps = 8;
+// zeroed bytes behind the last slot: fragment rows up to 15 lines past a tile (line stride up to 384 B) land here
+constexpr int kAttnPad = 6144;
+
+struct AttnTmaParams {
+  const int32_t* key_mask;
+  int Lq, Lk, heads, items;
+  int slot_bytes;       // (Lq + 2 Lk) * 128
+  int q_stride;         // bytes between consecutive Q (= output) lines of a slot: 384 merged, 128 otherwise
+  int kv_stride;        // bytes between consecutive K (or V) lines: 384 merged, 256 otherwise
+  int k_off, v_off;     // first K / V line, from the slot base
+  int merged;           // self-attention: ONE 3-D box (64 cols x {q,k,v} x L rows) per unit; else Q box + {k,v} box
+  int depth;            // slots per compute warp
+  int debug;            // measurement switches (RGQA_ATTN_DEBUG): 1 no stores, 2 no P.V, 4 no math at all
+};
+
+// shared-memory address of 16-byte chunk `chunk` (0..7) of the 128-byte line at `line_addr` under the 128-byte swizzle
+__device__ __forceinline__ uint32_t sw128_addr(uint32_t line_addr, int chunk) {
+  return line_addr + ((static_cast<uint32_t>(chunk) ^ ((line_addr >> 7) & 7u)) << 4);
+}
+
+// tmA: merged -> the (64, 3, L) box over [rows][q|k|v][768]; else the 2-D Q box.  tmB: the (64, 2, Lk) {k, v} box (unused
+// when merged).  tmO: merged -> 3-D map whose middle extent is 1, so only the q-lines of the (64, 3, Lq) box are stored
+// (TMA drops out-of-range box elements); else the 2-D output box.
+template <int KS>
+__global__ void __launch_bounds__((1 + kAttnWarps) * 32, 1)
+attention_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmO, const AttnTmaParams p) {
+  constexpr int NT = 2 * KS;
+  extern __shared__ uint8_t smem_attn_raw[];
+  const uint32_t raw = smem_u32(smem_attn_raw);
+  uint8_t* smem = smem_attn_raw + ((1024u - (raw & 1023u)) & 1023u);
+  const int slot_bytes = p.slot_bytes;
+  const int nslot = kAttnWarps * p.depth;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(nslot) * slot_bytes + kAttnPad);
+  uint64_t* empty_bar = full_bar + nslot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // clear the ring once (fragment rows that alias a never-written neighbour must not hold NaN patterns), then hand it
+  // to the async proxy
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = (nslot * slot_bytes + kAttnPad) / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nslot; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  // contiguous range of units for this CTA: consecutive heads of consecutive samples (adjacent 128-byte columns of the
+  // same token rows) are requested back to back
+  const int per = (p.items + gridDim.x - 1) / gridDim.x;
+  const int u0 = blockIdx.x * per;
+  const int n = min(p.items, u0 + per) - u0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(slot_bytes);
+      for (int i = 0; i < n; ++i) {
+        const int w = i % kAttnWarps, k = i / kAttnWarps;
+        const int slot = w * p.depth + k % p.depth;
+        const int u = u0 + i;
+        const int b = u / p.heads, h = u % p.heads;
+        uint8_t* dst = smem + static_cast<size_t>(slot) * slot_bytes;
+        if (k >= p.depth) mbar_wait(&empty_bar[slot], ((k / p.depth) - 1) & 1u);
+        mbar_expect_tx(&full_bar[slot], bytes);
+        if (p.merged) {
+          tma_load_3d(dst, &tmA, &full_bar[slot], h * HD, 0, b * p.Lq);
+        } else {
+          tma_load_2d(dst, &tmA, &full_bar[slot], h * HD, b * p.Lq);
+          tma_load_3d(dst + p.k_off, &tmB, &full_bar[slot], h * HD, 0, b * p.Lk);
+        }
+      }
+    }
+    return;
+  }
+
+  const int cw = warp - 1;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t qs = static_cast<uint32_t>(p.q_stride), kvs = static_cast<uint32_t>(p.kv_stride);
+  int pending_slot = -1;  // slot whose output store may still be reading shared memory
+  int k = 0;
+  for (int i = cw; i < n; i += kAttnWarps, ++k) {
+    const int slot = cw * p.depth + k % p.depth;
+    const int u = u0 + i;
+    const int b = u / p.heads, h = u % p.heads;
+    const uint32_t Qs = smem_u32(smem + static_cast<size_t>(slot) * slot_bytes);
+    const uint32_t Ks = Qs + p.k_off;
+    const uint32_t Vs = Qs + p.v_off;
+
+    float madd[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = 8 * j + 2 * t + e;
+        madd[j][e] = key >= p.Lk ? -INFINITY
+                                 : ((p.key_mask != nullptr && __ldg(p.key_mask + b * p.Lk + key) == 0) ? -10000.f * kLog2e : 0.f);
+      }
+    if (pending_slot >= 0) {  // the previous unit's store has had this long to read its lines: give the slot back
+      if (lane == 0) {
+        tma_store_wait_read<0>();
+        mbar_arrive(&empty_bar[pending_slot]);
+      }
+      pending_slot = -1;
+    }
+    mbar_wait(&full_bar[slot], (k / p.depth) & 1u);
+    if (p.debug & 4) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[slot]);
+      continue;
+    }
+
+    for (int m0 = 0; m0 < p.Lq; m0 += 16) {
+      const int r0 = m0 + g, r1 = r0 + 8;
+      // A fragments of the 16 query rows: one ldmatrix.x4 per 16-wide k-step
+      uint32_t qa[4][4];
+      {
+        const uint32_t line = Qs + static_cast<uint32_t>(m0 + (lane & 15)) * qs;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(qa[ks][0]), "=r"(qa[ks][1]), "=r"(qa[ks][2]), "=r"(qa[ks][3])
+                       : "r"(sw128_addr(line, 2 * ks + (lane >> 4))));
+        }
+      }
+      float s[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        const uint32_t line = Ks + static_cast<uint32_t>(8 * j + (lane & 7)) * kvs;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+          uint32_t kb[4];
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(kb[0]), "=r"(kb[1]), "=r"(kb[2]), "=r"(kb[3])
+                       : "r"(sw128_addr(line, 4 * kp + (lane >> 3))));
+          mma_bf16_16816(s[j], qa[2 * kp], kb[0], kb[1]);
+          mma_bf16_16816(s[j], qa[2 * kp + 1], kb[2], kb[3]);
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        s[j][0] = fmaf(s[j][0], kScaleLog2e, madd[j][0]);
+        s[j][1] = fmaf(s[j][1], kScaleLog2e, madd[j][1]);
+        s[j][2] = fmaf(s[j][2], kScaleLog2e, madd[j][0]);
+        s[j][3] = fmaf(s[j][3], kScaleLog2e, madd[j][1]);
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pa[KS][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const float p0 = exp2f(s[j][0] - mx0), p1 = exp2f(s[j][1] - mx0);
+        const float p2 = exp2f(s[j][2] - mx1), p3 = exp2f(s[j][3] - mx1);
+        sum0 += p0 + p1;
+        sum1 += p2 + p3;
+        pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+        pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      }
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+
+      float o[8][4];
+#pragma unroll
+      for (int d = 0; d < 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        if (p.debug & 2) break;
+        const uint32_t line = Vs + static_cast<uint32_t>(ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kvs;
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t vb[4];
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(vb[0]), "=r"(vb[1]), "=r"(vb[2]), "=r"(vb[3])
+                       : "r"(sw128_addr(line, 2 * dp + (lane >> 4))));
+          mma_bf16_16816(o[2 * dp], pa[ks], vb[0], vb[1]);
+          mma_bf16_16816(o[2 * dp + 1], pa[ks], vb[2], vb[3]);
+        }
+      }
+      // the 16 query rows of this tile are in registers since the top of the iteration: their lines now take the output
+      // (rows >= Lq alias other lines of the ring and are skipped)
+      const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+      __syncwarp();  // every lane's ldmatrix of these Q lines has completed
+      const uint32_t l0 = Qs + static_cast<uint32_t>(r0) * qs, l1 = Qs + static_cast<uint32_t>(r1) * qs;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        if (r0 < p.Lq)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw128_addr(l0, d) + 4u * t), "r"(pack_bf16x2(o[d][0] * inv0, o[d][1] * inv0)) : "memory");
+        if (r1 < p.Lq)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw128_addr(l1, d) + 4u * t), "r"(pack_bf16x2(o[d][2] * inv1, o[d][3] * inv1)) : "memory");
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (!(p.debug & 1)) {
+        const uint8_t* src = smem + static_cast<size_t>(slot) * slot_bytes;
+        if (p.merged)
+          tma_store_3d(&tmO, src, h * HD, 0, b * p.Lq);
+        else
+          tma_store_2d(&tmO, src, h * HD, b * p.Lq);
+      }
+      tma_store_commit();
+    }
+    pending_slot = slot;
+  }
+  if (lane == 0) tma_store_wait<0>();  // shared memory must outlive the last store's read
+}
+
+template <int KS>
+int launch_attention_tma(cudaStream_t stream, const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* k, long long ldk,
+                         const __nv_bfloat16* v, long long ldv, const int32_t* key_mask, __nv_bfloat16* out, long long ldo,
+                         int B, int Lq, int Lk, int heads, int depth) {
+  CUtensorMap tmA, tmB, tmO;
+  const long long cols = static_cast<long long>(heads) * HD;
+  const long long kv_gap = (v - k) * 2;  // bytes between a row's K and V blocks
+  const bool merged = (k - q) * 2 == kv_gap && ldq == ldk && Lq == Lk;
+  AttnTmaParams p;
+  if (merged) {  // self-attention over one fused [rows][q|k|v] buffer
+    if (make_tmap_3d(&tmA, q, cols, 3, static_cast<long long>(B) * Lq, kv_gap, ldq * 2, HD, 3, Lq) ||
+        make_tmap_3d(&tmO, out, cols, 1, static_cast<long long>(B) * Lq, ldo * 2 /*unused: extent 1*/, ldo * 2, HD, 3, Lq))
+      return 1;
+    tmB = tmA;
+    p.q_stride = p.kv_stride = 384;
+    p.k_off = 128;
+    p.v_off = 256;
+  } else {
+    if (make_tmap_ex(&tmA, q, static_cast<long long>(B) * Lq, cols, ldq, Lq, HD, 2, 128) ||
+        make_tmap_3d(&tmB, k, cols, 2, static_cast<long long>(B) * Lk, kv_gap, ldk * 2, HD, 2, Lk) ||
+        make_tmap_ex(&tmO, out, static_cast<long long>(B) * Lq, cols, ldo, Lq, HD, 2, 128))
+      return 1;
+    p.q_stride = 128;
+    p.kv_stride = 256;
+    p.k_off = Lq * 128;
+    p.v_off = Lq * 128 + 128;
+  }
+  p.merged = merged ? 1 : 0;
+  p.key_mask = key_mask;
+  p.Lq = Lq;
+  p.Lk = Lk;
+  p.heads = heads;
+  p.items = B * heads;
+  p.slot_bytes = (Lq + 2 * Lk) * 128;
+  p.depth = depth;
+  const char* d = getenv("RGQA_ATTN_DEBUG");
+  p.debug = d ? atoi(d) : 0;
+  const int smem = kAttnWarps * depth * p.slot_bytes + 1024 + kAttnPad + 1024;
+  static bool cfg = false;
+  if (!cfg) {
+    RGQA_CUDA_OK(cudaFuncSetAttribute(attention_tma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cfg = true;
+  }
+  int grid = num_sms();
+  if (grid > p.items) grid = p.items;
+  RGQA_CUDA_OK(launch_pdl(attention_tma_kernel<KS>, dim3(grid), dim3((1 + kAttnWarps) * 32), smem, stream, tmA, tmB, tmO, p));
+  return 0;
+}
+
+// slots per compute warp that fit next to the barriers and the overrun pad; < 2 means no prefetch: use the per-warp kernel
+inline int attention_tma_depth(int Lq, int Lk) {
+  const int slot = (Lq + 2 * Lk) * 128;
+  const int budget = 227 * 1024 - 1024 /*alignment*/ - kAttnPad /*overrun pad*/ - 1024 /*barriers*/;
+  int depth = budget / (kAttnWarps * slot);
+  return depth > 4 ? 4 : depth;
+}
+
 template <int KS>
 int launch_attention_mma(cudaStream_t stream, const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* k, long long ldk,
                          const __nv_bfloat16* v, long long ldv, const int32_t* key_mask, __nv_bfloat16* out, long long ldo,
@@ -324,6 +627,7 @@ int launch_attention_mma(cudaStream_t stream, const __nv_bfloat16* q, long long 
   static bool cfg = false;
   if (!cfg) {
     RGQA_CUDA_OK(cudaFuncSetAttribute(attention_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    RGQA_CUDA_OK(cudaFuncSetAttribute(attention_mma_kernel<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     cfg = true;
   }
   RGQA_CUDA_OK(launch_pdl(attention_mma_kernel<KS>, dim3((items + 3) / 4), dim3(128), smem, stream, q, ldq, k, ldk, v, ldv, key_mask, out, ldo, Lq, Lk, heads, items));
@@ -360,6 +664,22 @@ int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, cons
     const __nv_bfloat16* vb = static_cast<const __nv_bfloat16*>(v);
     __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
     int rc = 0;
+    // large batches: TMA-fed persistent kernel (needs a few units per compute warp, room for two slots per warp, and
+    // 16-byte aligned operands)
+    const int depth = attention_tma_depth(Lq, Lk);
+    const bool tma_ok = option_get(OPT_ATTN_TMA) != 0 && depth >= 2 &&
+                        static_cast<long long>(B) * heads >= 8LL * num_sms() * kAttnWarps &&
+                        (reinterpret_cast<uintptr_t>(q) % 16 == 0) && (reinterpret_cast<uintptr_t>(k) % 16 == 0) &&
+                        (reinterpret_cast<uintptr_t>(v) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
+                        ldk == ldv && vb > kb && ((vb - kb) * 2) % 16 == 0 && (vb - kb) <= ldk - heads * HD;
+    if (tma_ok) {
+      switch ((Lk + 15) / 16) {
+        case 1: rc = launch_attention_tma<1>(stream, qb, ldq, kb, ldk, vb, ldv, key_mask, ob, ldo, B, Lq, Lk, heads, depth); break;
+        case 2: rc = launch_attention_tma<2>(stream, qb, ldq, kb, ldk, vb, ldv, key_mask, ob, ldo, B, Lq, Lk, heads, depth); break;
+        case 3: rc = launch_attention_tma<3>(stream, qb, ldq, kb, ldk, vb, ldv, key_mask, ob, ldo, B, Lq, Lk, heads, depth); break;
+        default: rc = launch_attention_tma<4>(stream, qb, ldq, kb, ldk, vb, ldv, key_mask, ob, ldo, B, Lq, Lk, heads, depth); break;
+      }
+    } else
     switch ((Lk + 15) / 16) {
       case 1: rc = launch_attention_mma<1>(stream, qb, ldq, kb, ldk, vb, ldv, key_mask, ob, ldo, B, Lq, Lk, heads); break;
       case 2: rc = launch_attention_mma<2>(stream, qb, ldq, kb, ldk, vb, ldv, key_mask, ob, ldo, B, Lq, Lk, heads); break;

@@ -900,6 +900,25 @@ int make_tmap_ex(CUtensorMap* map, const void* ptr, long long rows, long long co
   return 0;
 }
 
+// 3-D form (bf16): dims (d0 fastest, stride 1) x (d1, stride1 bytes) x (d2, stride2 bytes); box (b0, b1, b2); 128-byte
+// swizzle.  Box extents may exceed the tensor's: out-of-range elements load as zero and are not stored.
+int make_tmap_3d(CUtensorMap* map, const void* ptr, long long d0, long long d1, long long d2, long long stride1_bytes,
+                 long long stride2_bytes, int b0, int b1, int b2) {
+  EncodeTiledFn enc = get_encode_fn();
+  RGQA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  RGQA_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "TMA operand must be 16-byte aligned");
+  RGQA_CHECK(stride1_bytes % 16 == 0 && stride2_bytes % 16 == 0, "TMA strides must be multiples of 16 bytes");
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(stride1_bytes), static_cast<cuuint64_t>(stride2_bytes)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(b0), static_cast<cuuint32_t>(b1), static_cast<cuuint32_t>(b2)};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RGQA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

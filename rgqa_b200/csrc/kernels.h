@@ -56,6 +56,11 @@ int gemm_bf16_ln(cudaStream_t stream, const void* A, long long lda, const void* 
 // host helpers shared by the tcgen05 GEMM translation units (gemm_tcgen05.cu)
 int make_tmap(::CUtensorMap_st* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
               int elem_bytes);
+// general form: explicit box width (elements) and swizzle span in bytes (0 = none, 64, 128)
+int make_tmap_ex(::CUtensorMap_st* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
+                 int box_cols, int elem_bytes, int swizzle_bytes);
+int make_tmap_3d(::CUtensorMap_st* map, const void* ptr, long long d0, long long d1, long long d2, long long stride1_bytes,
+                 long long stride2_bytes, int b0, int b1, int b2);
 int num_sms();
 
 // ---- attention (small sequences, Lq, Lk <= 64, 12 heads x 64) -----------------------------------
@@ -110,7 +115,8 @@ int rowdot(cudaStream_t stream, const float* a, const float* b, float* out, int 
 
 // ---- runtime options (prof.cu): kernel-selection switches for A/B measurements ---------------------
 enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_GEMM_DEBUG = 2, OPT_PDL = 3, OPT_GEMM_LN = 4, OPT_TWO_STREAMS = 5, OPT_GRAPHS = 6,
-  OPT_DEFER_LN = 7, OPT_COUNT = 8 };
+  OPT_DEFER_LN = 7,
+  OPT_ATTN_TMA = 8, OPT_COUNT = 16 };
 int option_get(int key);
 void option_set(int key, int value);
 

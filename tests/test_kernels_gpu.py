@@ -212,6 +212,35 @@ def test_attention_matches_torch(cuda_device, dtype, B, Lq, Lk, masked):
         torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)  # one bf16 output rounding
 
 
+@pytest.mark.parametrize("B,Lq,Lk,masked", [(800, 20, 20, True), (800, 36, 36, False), (800, 20, 36, False), (800, 36, 20, True),
+                                            (801, 30, 30, True), (800, 56, 64, True), (800, 7, 9, True)])
+def test_attention_large_batch_tma_path_matches_torch_and_per_warp_kernel(cuda_device, B, Lq, Lk, masked):
+    """B * 12 heads >= 8 units per compute warp per SM: the TMA-fed persistent kernel (option attn_tma) takes over.
+    Checked against torch and bit-for-bit against the per-warp kernel (same mma.sync math on the same operands)."""
+    from rgqa_b200 import ops, _lib as L
+    lib = L.load()
+    g = torch.Generator(device="cpu").manual_seed(B + Lq * 10 + Lk)
+    H = 768
+    qkv_q = torch.randn(B * Lq, 3 * H, generator=g).to(torch.bfloat16).to(cuda_device)
+    qkv_kv = torch.randn(B * Lk, 3 * H, generator=g).to(torch.bfloat16).to(cuda_device)
+    mask = None
+    if masked:
+        lens = torch.randint(1, Lk + 1, (B,), generator=g)
+        mask = (torch.arange(Lk)[None, :] < lens[:, None]).to(torch.int32).to(cuda_device)
+    try:
+        lib.rgqa_set_option(b"attn_tma", 0)
+        old = ops.attention(qkv_q, qkv_kv, B, Lq, Lk, key_mask=mask)
+        lib.rgqa_set_option(b"attn_tma", 1)
+        out = ops.attention(qkv_q, qkv_kv, B, Lq, Lk, key_mask=mask)
+        out2 = ops.attention(qkv_q, qkv_kv, B, Lq, Lk, key_mask=mask)
+    finally:
+        lib.rgqa_set_option(b"attn_tma", 1)
+    torch.cuda.synchronize()
+    ref = _attention_ref(qkv_q[:, :H].float(), qkv_kv[:, H:2 * H].float(), qkv_kv[:, 2 * H:].float(), mask, B, Lq, Lk)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)  # one bf16 output rounding
+    assert torch.equal(out, old) and torch.equal(out, out2)
+
+
 def test_attention_fully_masked_row_matches_reference_semantics(cuda_device):
     # additive -10000 (not -inf): an all-masked sample degrades to a uniform softmax, like the reference
     from rgqa_b200 import ops
