@@ -235,8 +235,17 @@ def run_ours(a):
         f, p, ids, mask, seg = resident[i & 1]
         return runner.score_device_batch(f, p, ids, mask, seg)
 
-    for i in range(a.warmup):
+    # priming (not counted as warm-up): the library captures one CUDA graph per (shape, input buffers) on the second
+    # call of each of the two alternating batches; capture + instantiation must not land in a timed region
+    for i in range(4):
         dev_step(i)
+    warm = [dev_step(i) for i in range(a.warmup)]
+    # the end-of-sweep all-gather also gets its warm-up call: NCCL connects its channels lazily on the first collective
+    # of a shape (tens of ms), which is start-up cost like context or graph creation, not part of a sweep's steady state
+    for m in range(len(methods)):
+        gather_results(torch.cat([k[m][0] for k in warm] * max(1, a.steps // max(1, a.warmup))),
+                       torch.cat([k[m][1] for k in warm] * max(1, a.steps // max(1, a.warmup))))
+    del warm
     two_streams_default = 0 if "two_streams=0" in os.environ.get("RGQA_OPTS", "") else 1
 
     def timed_region(profile):
@@ -302,6 +311,8 @@ def run_ours(a):
                 hs.copy_(s, non_blocking=True)
                 hl.copy_(l, non_blocking=True)
 
+        for i in range(4):  # priming: the two staging slots of the runner each get their CUDA graph (see above)
+            e2e_step(i)
         for i in range(a.warmup):
             e2e_step(i)
         barrier()

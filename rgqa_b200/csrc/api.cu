@@ -138,14 +138,25 @@ struct rgqa_handle {
   cudaStream_t cap = nullptr;  // capture stream for the small-batch CUDA graphs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
-  // CUDA graphs of the whole forward for small batches, keyed by shape
+  // CUDA graphs of the whole forward, keyed by shape (small batches: inputs / outputs staged in handle-owned buffers)
+  // or by shape + the caller's feature / box pointers (large batches: the 300 MB inputs are used in place)
   struct GraphEntryT {
     int seen = 0;
     int kernels = 0;
     cudaGraphExec_t exec = nullptr;
     DevBuf feat, pos, ids, seg, mask, pooled, logits;
   };
-  std::map<long long, GraphEntryT> graphs;
+  struct GraphKey {
+    long long shape;
+    const void* feat;
+    const void* pos;
+    bool operator<(const GraphKey& o) const {
+      if (shape != o.shape) return shape < o.shape;
+      if (feat != o.feat) return feat < o.feat;
+      return pos < o.pos;
+    }
+  };
+  std::map<GraphKey, GraphEntryT> graphs;
 
   // workspace
   DevBuf hidA, hidB, resA, resB, qkv, ctx, inter, pre, featb, headbuf, mahabuf;
@@ -1004,10 +1015,14 @@ static int lxmert_forward_impl(rgqa_handle* h, cudaStream_t st, const void* feat
   return head_block(h, st, cur.act, B, L, pooled_out, logits_out);
 }
 
-// Small batches are launch-bound (207 kernels + 330 tensor-map encodes per forward: ~3 ms of host time at B = 32, the
-// reference scripts' default batch size).  For B <= 128 the whole forward is captured ONCE per (B, L, dtype, outputs)
+// Small batches are launch-bound (170-210 kernels + ~330 tensor-map encodes per forward: ~3 ms of host time at B = 32,
+// the reference scripts' default batch size).  For B <= 128 the whole forward is captured ONCE per (B, L, dtype, outputs)
 // into a CUDA graph over handle-owned staging buffers; later calls are: copy inputs in, one graph launch, copy outputs
-// out.  The first call of a shape runs eagerly (lazy per-kernel attribute setup must not happen under capture).
+// out.  Large batches are GPU-bound on an idle host, but with one process per GPU the 8 ranks of a box share its cores
+// and the ~2 ms of launch work per step starts to show (measured: 14.3 vs 12.6 ms/step at N = 8): they are captured too,
+// keyed additionally by the caller's feature / box pointers, which are then used in place (a sweep feeds them from two
+// alternating staging buffers); only the small id / mask inputs and the outputs go through staging copies.
+// The first call of a key runs eagerly (lazy per-kernel attribute setup must not happen under capture).
 int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos,
                         const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
                         float* pooled_out, float* logits_out) {
@@ -1019,7 +1034,8 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
   RGQA_CHECK(L >= 2 && L <= 64, "rgqa_lxmert_forward: L=%d out of range [2,64]", L);
   RGQA_CHECK(logits_out == nullptr || h->cfg.num_answers > 0, "rgqa_lxmert_forward: handle has no answer head");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool use_graph = option_get(OPT_GRAPHS) != 0 && B <= 128 && !prof_on();
+  const bool use_graph = option_get(OPT_GRAPHS) != 0 && !prof_on();
+  const bool big = B > 128;  // large batch: feat / pos are used in place
   if (!use_graph)
     return lxmert_forward_impl(h, st, feat, feat_dtype, pos, ids, seg, mask, B, L, pooled_out, logits_out);
 
@@ -1027,7 +1043,15 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
   const long long key = (static_cast<long long>(B) << 20) | (static_cast<long long>(L) << 8) | (feat_dtype << 4) |
                         ((option_get(OPT_DEFER_LN) != 0) << 3) |
                         ((seg != nullptr) << 2) | ((pooled_out != nullptr) << 1) | (logits_out != nullptr);
-  rgqa_handle::GraphEntryT& g = h->graphs[key];
+  if (h->graphs.size() > 16) {  // callers that never repeat a pointer: do not hoard graphs
+    drop_graphs(h);
+    for (auto& kv : h->graphs) {
+      kv.second.feat.release(); kv.second.pos.release(); kv.second.ids.release(); kv.second.seg.release();
+      kv.second.mask.release(); kv.second.pooled.release(); kv.second.logits.release();
+    }
+    h->graphs.clear();
+  }
+  rgqa_handle::GraphEntryT& g = h->graphs[rgqa_handle::GraphKey{key, big ? feat : nullptr, big ? static_cast<const void*>(pos) : nullptr}];
   const size_t fe = feat_dtype == RGQA_DT_F32 ? 4 : 2;
   const size_t n_feat = static_cast<size_t>(B) * c.num_rois * c.visual_feat_dim * fe;
   const size_t n_pos = static_cast<size_t>(B) * c.num_rois * c.visual_pos_dim * 4;
@@ -1037,7 +1061,7 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
     return lxmert_forward_impl(h, st, feat, feat_dtype, pos, ids, seg, mask, B, L, pooled_out, logits_out);
   }
   if (g.exec == nullptr) {
-    if (g.feat.ensure(n_feat) || g.pos.ensure(n_pos) || g.ids.ensure(n_ids) || g.seg.ensure(n_ids) || g.mask.ensure(n_ids) ||
+    if ((!big && (g.feat.ensure(n_feat) || g.pos.ensure(n_pos))) || g.ids.ensure(n_ids) || g.seg.ensure(n_ids) || g.mask.ensure(n_ids) ||
         g.pooled.ensure(static_cast<size_t>(B) * c.hidden * 4) ||
         g.logits.ensure(static_cast<size_t>(B) * (c.num_answers > 0 ? c.num_answers : 1) * 4))
       return 1;
@@ -1046,7 +1070,7 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
     // capture on a handle-owned stream: the caller's stream is usually the legacy default stream, which cannot capture
     if (h->cap == nullptr) RGQA_CUDA_OK(cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking));
     RGQA_CUDA_OK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal));
-    const int rc = lxmert_forward_impl(h, h->cap, g.feat.p, feat_dtype, static_cast<const float*>(g.pos.p),
+    const int rc = lxmert_forward_impl(h, h->cap, big ? feat : g.feat.p, feat_dtype, big ? pos : static_cast<const float*>(g.pos.p),
                                        static_cast<const int32_t*>(g.ids.p),
                                        seg != nullptr ? static_cast<const int32_t*>(g.seg.p) : nullptr,
                                        static_cast<const int32_t*>(g.mask.p), B, L,
@@ -1063,8 +1087,10 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
     RGQA_CUDA_OK(cudaGraphInstantiate(&g.exec, graph, 0));
     RGQA_CUDA_OK(cudaGraphDestroy(graph));
   }
-  RGQA_CUDA_OK(cudaMemcpyAsync(g.feat.p, feat, n_feat, cudaMemcpyDeviceToDevice, st));
-  RGQA_CUDA_OK(cudaMemcpyAsync(g.pos.p, pos, n_pos, cudaMemcpyDeviceToDevice, st));
+  if (!big) {
+    RGQA_CUDA_OK(cudaMemcpyAsync(g.feat.p, feat, n_feat, cudaMemcpyDeviceToDevice, st));
+    RGQA_CUDA_OK(cudaMemcpyAsync(g.pos.p, pos, n_pos, cudaMemcpyDeviceToDevice, st));
+  }
   RGQA_CUDA_OK(cudaMemcpyAsync(g.ids.p, ids, n_ids, cudaMemcpyDeviceToDevice, st));
   if (seg != nullptr) RGQA_CUDA_OK(cudaMemcpyAsync(g.seg.p, seg, n_ids, cudaMemcpyDeviceToDevice, st));
   RGQA_CUDA_OK(cudaMemcpyAsync(g.mask.p, mask, n_ids, cudaMemcpyDeviceToDevice, st));

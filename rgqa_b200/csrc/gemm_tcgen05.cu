@@ -623,6 +623,10 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         coords(k, row0, col);
         const int b = k % kRing;
         uint64_t* bar = &resid_bar[e * kRing + b];
+        if (p.debug & 4) {  // measurement: no residual traffic
+          mbar_arrive(bar);
+          return;
+        }
         mbar_expect_tx(bar, kSubSlab);
         uint8_t* dst = slabs + (half * kRing + b) * kSlabBytes;
         if constexpr (kHiLo) {  // hi rows then lo rows, 128 x 64 B each, 64-byte swizzle
@@ -661,7 +665,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         mbar_wait(&resid_bar[e * kRing + b], (k / kRing) & 1u);  // this warp's residual rows have landed
         tmem_ld_wait_dep(v);
         float f[32];
-        if constexpr (kHiLo) {
+        if (p.debug & 2) {
+          // measurement: no epilogue math / shared-memory traffic
+        } else if constexpr (kHiLo) {
           // residual = LN_prev(x_prev) with x_prev = hi + lo; v = acc + bias + residual; then split v again
           // 64-byte swizzle: 16-byte piece i of row r sits at piece i ^ ((r >> 1) & 3) -> conflict-free row-per-lane access
           uint8_t* hrow = buf + r_local * 64;
@@ -746,7 +752,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         fence_proxy_async_smem();
         __syncwarp();
         if (issuer) {
-          if (row0 < p.M) {
+          if (row0 < p.M && !(p.debug & 1)) {
             if constexpr (kHiLo) {
               tma_store_2d(&tmOut, buf + quarter * (kSubSlab / 2), col, row0);
               tma_store_2d(&tmOutLo, buf + kSlabBytes / 2 + quarter * (kSubSlab / 2), col, row0);

@@ -6,7 +6,8 @@ from rgqa_b200 import ops, _lib as L
 lib = L.load()
 dev = torch.device("cuda")
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-for name, M, N, K, epi, odt in [("qkv visn", 36864, 2304, 768, L.EPI_BIAS, torch.bfloat16), ("ffn1 visn", 36864, 3072, 768, L.EPI_GELU, torch.bfloat16)]:
+for name, M, N, K, epi, odt in [("qkv visn", 36864, 2304, 768, L.EPI_BIAS, torch.bfloat16), ("ffn1 visn", 36864, 3072, 768, L.EPI_GELU, torch.bfloat16),
+                               ("ffn2-shape plain bf16 out", 36864, 768, 3072, L.EPI_BIAS, torch.bfloat16), ("attnout-shape plain bf16 out", 36864, 768, 768, L.EPI_BIAS, torch.bfloat16)]:
     a = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
     w = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
     bias = torch.randn(N, device=dev)
