@@ -151,7 +151,8 @@ int rgqa_gemm_bf16_ln(void* stream, const void* A, int64_t lda, const void* W, i
  *    (W, bias, gamma, beta f32 device pointers; W [N,K]).
  *  - rgqa_gemm_bf16_folded: out = epilogue(rstd·(A_hi·W'ᵀ − mean·c) + bias') with mean/rstd from ln_stats; ln_c may be
  *    NULL (term dropped: it is below the bf16 rounding of W'); K = 768.
- *  - rgqa_gemm_bf16_resid_hl: v = A·Wᵀ + bias + LayerNorm_prev(in_hi + in_lo); writes v as (out_hi, out_lo, out_stats). N = 768. */
+ *  - rgqa_gemm_bf16_resid_hl: v = A·Wᵀ + bias + LayerNorm_prev(in_hi + in_lo); writes v as (out_hi, out_lo, out_stats). N = 768.
+ *    in_beta may be NULL when `bias` already includes the previous LayerNorm's beta. */
 int rgqa_fold_ln_weight(void* stream, const float* W, const float* bias, const float* gamma, const float* beta, int N,
                         int K, void* W_out_bf16, float* c_out, float* bias_out);
 int rgqa_gemm_bf16_folded(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,

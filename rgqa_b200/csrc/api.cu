@@ -86,12 +86,15 @@ struct AttW {
   LNp ln;
   Folded qkv_f;   // folded with the LayerNorm that produced this block's input (language rows for the cross block)
   Folded qkv_f2;  // cross block only: folded with the visual branch's LayerNorm
+  float* out_bb = nullptr;   // out.b + beta of the LayerNorm owed to the block's input (the producer epilogue's bias)
+  float* out_bb2 = nullptr;  // cross block only: with the visual branch's beta
 };
 struct FfnW {
   Linear inter;  // [I, H]
   Linear out;    // [H, I]
   LNp ln;
   Folded inter_f;  // folded with the attention block's output LayerNorm
+  float* out_bb = nullptr;  // out.b + beta of the attention block's output LayerNorm
 };
 struct LayerW {
   AttW att;
@@ -375,6 +378,20 @@ int fold_stack(rgqa_handle* h, const std::vector<std::string>& names, int rows, 
   out->b = b;
   return 0;
 }
+// bias + beta (both [n] f32 on the device) as one vector: the residual term LN(x) = (x-mu)*rstd*gamma + beta of a producer
+// GEMM then needs no separate beta load
+int add_vecs(rgqa_handle* h, const float* a, const float* b, int n, float** out) {
+  std::vector<float> ha(n), hb(n);
+  RGQA_CUDA_OK(cudaMemcpy(ha.data(), a, n * sizeof(float), cudaMemcpyDeviceToHost));
+  RGQA_CUDA_OK(cudaMemcpy(hb.data(), b, n * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) ha[i] += hb[i];
+  float* d = nullptr;
+  RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d), n * sizeof(float)));
+  h->owned.push_back(d);
+  RGQA_CUDA_OK(cudaMemcpy(d, ha.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
 int fold_qkv(rgqa_handle* h, const std::string& p, const char* self_name, const LNp* pred, Folded* out) {
   if (pred == nullptr) return 0;
   const std::string s = p + "." + self_name;
@@ -383,6 +400,8 @@ int fold_qkv(rgqa_handle* h, const std::string& p, const char* self_name, const 
 // folds of one BertLayer whose input comes out of LayerNorm `pred` (nullptr: not behind a LayerNorm)
 int fold_bert_layer(rgqa_handle* h, const std::string& p, LayerW* w, const LNp* pred) {
   if (fold_qkv(h, p + ".attention", "self", pred, &w->att.qkv_f)) return 1;
+  if (pred != nullptr && add_vecs(h, w->att.out.b, pred->b, h->cfg.hidden, &w->att.out_bb)) return 1;
+  if (add_vecs(h, w->ffn.out.b, w->att.ln.b, h->cfg.hidden, &w->ffn.out_bb)) return 1;
   return fold_stack(h, {p + ".intermediate.dense"}, h->cfg.intermediate, h->cfg.hidden, w->att.ln, &w->ffn.inter_f);
 }
 
@@ -700,7 +719,13 @@ int rgqa_finalize_weights(rgqa_handle* h) {
             fold_qkv(h, x + ".lang_self_att", "self", &w.cross.ln, &w.lang_self.qkv_f) ||
             fold_qkv(h, x + ".visn_self_att", "self", &w.cross.ln, &w.visn_self.qkv_f) ||
             fold_stack(h, {x + ".lang_inter.dense"}, c.intermediate, H, w.lang_self.ln, &w.lang_ffn.inter_f) ||
-            fold_stack(h, {x + ".visn_inter.dense"}, c.intermediate, H, w.visn_self.ln, &w.visn_ffn.inter_f))
+            fold_stack(h, {x + ".visn_inter.dense"}, c.intermediate, H, w.visn_self.ln, &w.visn_ffn.inter_f) ||
+            (pl != nullptr && add_vecs(h, w.cross.out.b, pl->b, H, &w.cross.out_bb)) ||
+            (pv != nullptr && add_vecs(h, w.cross.out.b, pv->b, H, &w.cross.out_bb2)) ||
+            add_vecs(h, w.lang_self.out.b, w.cross.ln.b, H, &w.lang_self.out_bb) ||
+            add_vecs(h, w.visn_self.out.b, w.cross.ln.b, H, &w.visn_self.out_bb) ||
+            add_vecs(h, w.lang_ffn.out.b, w.lang_self.ln.b, H, &w.lang_ffn.out_bb) ||
+            add_vecs(h, w.visn_ffn.out.b, w.visn_self.ln.b, H, &w.visn_ffn.out_bb))
           return 1;
         pl = &w.lang_ffn.ln;
         pv = &w.visn_ffn.ln;
@@ -770,11 +795,13 @@ struct DefCtx {
     return gemm_bf16_folded(st, hi_rows(in, r0), H, f.W, lin.K, f.b, nullptr, 0, out, ldo, 0, M, lin.N, lin.K, epi,
                             st_rows(in, r0), nullptr, h->cfg.ln_eps, 12);
   }
-  // out (pre-LayerNorm) = A · Wᵀ + b + LN_ln(in)
-  int produce(cudaStream_t st, const void* A, long long lda, const Linear& lin, const DState& in, const LNp* ln,
-              const DState& out, long long r0, int M) const {
-    return gemm_bf16_resid_hl(st, A, lda, lin.W, lin.K, lin.b, hi_rows(in, r0), lo_rows(in, r0), st_rows(in, r0),
-                              ln ? ln->g : h->ones, ln ? ln->b : h->zeros, h->cfg.ln_eps, hi_rows(out, r0), lo_rows(out, r0),
+  // out (pre-LayerNorm) = A · Wᵀ + b + LN_ln(in); bias_beta = b + ln->b precomputed (nullptr: ln == nullptr, beta = 0)
+  int produce(cudaStream_t st, const void* A, long long lda, const Linear& lin, const float* bias_beta, const DState& in,
+              const LNp* ln, const DState& out, long long r0, int M) const {
+    const float* bias = (ln != nullptr && bias_beta != nullptr) ? bias_beta : lin.b;
+    const float* beta = (ln != nullptr && bias_beta == nullptr) ? ln->b : nullptr;
+    return gemm_bf16_resid_hl(st, A, lda, lin.W, lin.K, bias, hi_rows(in, r0), lo_rows(in, r0), st_rows(in, r0),
+                              ln ? ln->g : h->ones, beta, h->cfg.ln_eps, hi_rows(out, r0), lo_rows(out, r0),
                               st_rows(out, r0), M, lin.N, lin.K);
   }
   // BertAttention (self) on rows [r0, r0 + B*S): in (LayerNorm ln_in) -> out (LayerNorm w.ln)
@@ -786,14 +813,14 @@ struct DefCtx {
     if (attention(st, DT_BF16, qkv, 3 * H, qkv + static_cast<size_t>(H) * 2, 3 * H, qkv + static_cast<size_t>(2 * H) * 2, 3 * H,
                   key_mask, ctx, H, B, S, S, h->cfg.heads))
       return 1;
-    return produce(st, ctx, H, w.out, in, ln_in, out, r0, B * S);
+    return produce(st, ctx, H, w.out, w.out_bb, in, ln_in, out, r0, B * S);
   }
   // BertIntermediate + BertOutput: in (LayerNorm ln_in) -> out (LayerNorm w.ln)
   int ffn(cudaStream_t st, const FfnW& w, const DState& in, const LNp* ln_in, const DState& out, long long r0, int M) const {
     const int I = h->cfg.intermediate;
     char* inter = rows_at(h->inter.p, r0, I, 2);
     if (consume(st, in, ln_in, w.inter, w.inter_f, r0, M, inter, I, EPI_GELU)) return 1;
-    return produce(st, inter, I, w.out, in, ln_in, out, r0, M);
+    return produce(st, inter, I, w.out, w.out_bb, in, ln_in, out, r0, M);
   }
 };
 }  // namespace
@@ -887,11 +914,11 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
       return 1;
     if (fork()) return 1;
     // cross output + self attention + FFN per modality (:455-475), the two chains side by side
-    if (d.produce(st, ctx, H, w.cross.out, cur, ln_l, alt, 0, static_cast<int>(Ml)) ||
+    if (d.produce(st, ctx, H, w.cross.out, w.cross.out_bb, cur, ln_l, alt, 0, static_cast<int>(Ml)) ||
         d.att(st, w.lang_self, alt, &w.cross.ln, cur, 0, B, L, mask) ||
         d.ffn(st, w.lang_ffn, cur, &w.lang_self.ln, alt, 0, static_cast<int>(Ml)))
       return 1;
-    if (d.produce(sv, rows_at(ctx, Ml, H, 2), H, w.cross.out, cur, ln_v, alt, Ml, static_cast<int>(Mv)) ||
+    if (d.produce(sv, rows_at(ctx, Ml, H, 2), H, w.cross.out, w.cross.out_bb2, cur, ln_v, alt, Ml, static_cast<int>(Mv)) ||
         d.att(sv, w.visn_self, alt, &w.cross.ln, cur, Ml, B, V, nullptr) ||
         d.ffn(sv, w.visn_ffn, cur, &w.visn_self.ln, alt, Ml, static_cast<int>(Mv)))
       return 1;

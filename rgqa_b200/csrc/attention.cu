@@ -596,8 +596,11 @@ int launch_attention_tma(cudaStream_t stream, const __nv_bfloat16* q, long long 
   p.items = B * heads;
   p.slot_bytes = (Lq + 2 * Lk) * 128;
   p.depth = depth;
-  const char* d = getenv("RGQA_ATTN_DEBUG");
-  p.debug = d ? atoi(d) : 0;
+  static const int debug_env = [] {  // measurement switches, read once
+    const char* d = getenv("RGQA_ATTN_DEBUG");
+    return d ? atoi(d) : 0;
+  }();
+  p.debug = debug_env;
   const int smem = kAttnWarps * depth * p.slot_bytes + 1024 + kAttnPad + 1024;
   static bool cfg = false;
   if (!cfg) {

@@ -653,6 +653,12 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if constexpr (kHiLo) {
             rin = row_norm(p.in_stats, row, row < p.M, p.ln_eps);
             st_sum2 = st_sq2 = make_float2(0.f, 0.f);
+            if (k + 4 < total) {  // this row's statistics of the NEXT tile: pull the line into L1 while this tile is processed
+              int nrow0, ncol;
+              coords(k + 4, nrow0, ncol);
+              if (nrow0 + lane < p.M)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.in_stats + static_cast<long long>(nrow0 + lane) * 12));
+            }
           }
           mbar_wait(&tmem_full_bar[acc], (itile >> 1) & 1u);
           tc_fence_after();
@@ -676,7 +682,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const float ra = rin.rstd, rb = -rin.mu * rin.rstd;
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
           const float4* g4 = reinterpret_cast<const float4*>(p.in_gamma + col);
-          const float4* e4 = reinterpret_cast<const float4*>(p.in_beta + col);
+          const bool has_beta = p.in_beta != nullptr;  // else the bias already carries beta (folded at load time)
+          const float4* e4 = reinterpret_cast<const float4*>((has_beta ? p.in_beta : p.bias) + col);
           uint32_t hw[16], lw[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -687,17 +694,23 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {  // columns 4i .. 4i+3 = bf16 words 2i, 2i+1
-            const float4 bb = __ldg(b4 + i), gg = __ldg(g4 + i), ee = __ldg(e4 + i);
+            float4 bb = __ldg(b4 + i);
+            const float4 gg = __ldg(g4 + i);
+            if (has_beta) {
+              const float4 ee = __ldg(e4 + i);
+              bb.x += ee.x;
+              bb.y += ee.y;
+              bb.z += ee.z;
+              bb.w += ee.w;
+            }
             const float2 h0 = unpack_bf16x2(hw[2 * i]), l0 = unpack_bf16x2(lw[2 * i]);
             const float2 h1 = unpack_bf16x2(hw[2 * i + 1]), l1 = unpack_bf16x2(lw[2 * i + 1]);
             // packed fp32 math (FFMA2 / FADD2): two columns per instruction
             const float2 ra2 = make_float2(ra, ra), rb2 = make_float2(rb, rb);
-            const float2 ra0 = __ffma2_rn(__ffma2_rn(__fadd2_rn(h0, l0), ra2, rb2), make_float2(gg.x, gg.y), make_float2(ee.x, ee.y));
-            const float2 ra1 = __ffma2_rn(__ffma2_rn(__fadd2_rn(h1, l1), ra2, rb2), make_float2(gg.z, gg.w), make_float2(ee.z, ee.w));
-            const float2 o0 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1])),
-                                                    make_float2(bb.x, bb.y)), ra0);
-            const float2 o1 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])),
-                                                    make_float2(bb.z, bb.w)), ra1);
+            const float2 ra0 = __ffma2_rn(__ffma2_rn(__fadd2_rn(h0, l0), ra2, rb2), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y));
+            const float2 ra1 = __ffma2_rn(__ffma2_rn(__fadd2_rn(h1, l1), ra2, rb2), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w));
+            const float2 o0 = __fadd2_rn(make_float2(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1])), ra0);
+            const float2 o1 = __fadd2_rn(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), ra1);
             f[4 * i + 0] = o0.x;
             f[4 * i + 1] = o0.y;
             f[4 * i + 2] = o1.x;
@@ -1039,7 +1052,7 @@ int gemm_bf16_resid_hl(cudaStream_t stream, const void* A, long long lda, const 
                        const float* in_beta, float eps, void* out_hi, void* out_lo, float* out_stats, int M, int N, int K) {
   RGQA_CHECK(M > 0 && K > 0 && K % BK == 0, "gemm_bf16_resid_hl: bad problem M=%d K=%d", M, K);
   RGQA_CHECK(N == 768, "gemm_bf16_resid_hl: built for N = 768 (got %d)", N);
-  RGQA_CHECK(bias && in_hi && in_lo && in_stats && in_gamma && in_beta && out_hi && out_lo && out_stats,
+  RGQA_CHECK(bias && in_hi && in_lo && in_stats && in_gamma && out_hi && out_lo && out_stats,
              "gemm_bf16_resid_hl: null argument");
   CUtensorMap tmA, tmB, tmOutHi, tmOutLo, tmInHi, tmInLo;
   if (make_tmap(&tmA, A, M, K, lda, BM, 2)) return 1;
