@@ -175,6 +175,11 @@ int rgqa_visn_combine(void* stream, int out_dtype, const float* x_pre, const flo
                       const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
                       const float* b2, void* out, int M, int H, float eps);
 int rgqa_cast_f32_to_bf16(void* stream, const float* in, void* out, int64_t n);
+/* Ensemble of K <= 8 checkpoints (src/tasks/gqa_ensemble.py:95-108, :165-177): `logits` is a HOST array of K device
+ * pointers to [B, A] f32 logit matrices (row stride ld); per class sigmoid values are summed and divided by K
+ * (method 0, "mean") or multiplied (method 1, "multiply") in checkpoint order; label = first arg-max, score = its value. */
+int rgqa_score_ensemble(void* stream, const float* const* logits, int K, int method, int64_t ld, int B, int A, float* score,
+                        int32_t* label);
 int rgqa_score_logits(void* stream, int mode, const float* logits, int64_t ld, int B, int A, float* score,
                       int32_t* label);
 /* Stand-alone Mahalanobis: x [B,H], mu [A,H], P [H,H] (symmetric) all f32 device pointers;

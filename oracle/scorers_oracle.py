@@ -85,3 +85,20 @@ def sample_estimator(features, targets):
     import scipy.linalg
     precision = scipy.linalg.pinvh(cov)
     return mean, precision
+
+
+def ensemble(score_vectors, method):
+    """src/tasks/gqa_ensemble.py:165-177 — ``score_vectors``: one float32 array [n, num_answers] of per-class sigmoid
+    probabilities per checkpoint (what ``ood_evaluate`` :95-108 stores per question).  In-place float32 accumulation in
+    checkpoint order, ``/ len`` for the mean, ``np.argmax`` (first index) and its value.  Returns (score [n], label [n])."""
+    final = np.array(score_vectors[0], dtype=np.float32, copy=True)
+    for r in score_vectors[1:]:
+        if method == "mean":
+            final += np.asarray(r, dtype=np.float32)
+        elif method == "multiply":
+            final *= np.asarray(r, dtype=np.float32)
+        else:
+            raise ValueError(f"Ensemble method {method} not implemented!")
+    scores = final / len(score_vectors) if method == "mean" else final
+    label = np.argmax(scores, axis=1)
+    return scores[np.arange(scores.shape[0]), label], label

@@ -104,6 +104,8 @@ enum ScoreMode : int {
   SCORE_LSE = 3,          // logsumexp(logits), label as MSP                     (gqa_energy.py:131)
   SCORE_MAHA = 4,         // max_c -0.5 (x-mu_c)^T P (x-mu_c), label = argmax_c  (gqa_maha.py:228-236,270)
 };
+int score_ensemble(cudaStream_t stream, const float* const* logits, int K, int multiply, long long ld, int B, int A,
+                   float* score, int32_t* label);
 int score_logits(cudaStream_t stream, int mode, const float* logits, long long ld, int B, int A, float* score,
                  int32_t* label);
 // Mahalanobis finish: S[b,c] = -0.5 * (q[b] - 2 G[b,c] + m[c]); row max / argmax.

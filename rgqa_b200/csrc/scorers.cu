@@ -7,6 +7,8 @@
 //   LSE          label as MSP; score = logsumexp(logit)                      src/tasks/gqa_energy.py:131
 //   MAHA         S[b,c] = -1/2 (x_b-mu_c)^T P (x_b-mu_c); score,label = S.max(1)   src/tasks/gqa_maha.py:228-236,270
 //                evaluated as -1/2 (q_b - 2 G_bc + m_c) with t = x P, q = <t,x>, G = t mu^T, m_c = mu_c^T P mu_c
+//   ENSEMBLE     per-class sigmoid vectors of K checkpoints summed (then / K) or multiplied, in checkpoint order,
+//                label = argmax, score = that entry                           src/tasks/gqa_ensemble.py:95-108,165-177
 #include "common.cuh"
 #include "kernels.h"
 
@@ -124,7 +126,51 @@ rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, float* _
   if (lane == 0) out[row] = s;
 }
 
+// K <= 8 logit matrices [B, A] (one per checkpoint); float32 accumulation in checkpoint order like the reference's
+// in-place numpy `+=` / `*=` on float32 arrays, then `/ K` for the mean; first-index arg-max (np.argmax)
+struct EnsemblePtrs {
+  const float* p[8];
+};
+__global__ void __launch_bounds__(kWarps * 32)
+ensemble_kernel(EnsemblePtrs logits, int K, int multiply, long long ld, int B, int A, float* __restrict__ score,
+                int32_t* __restrict__ label) {
+  const int row = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  ArgMax best{-INFINITY, 0x7fffffff};
+  const float kf = static_cast<float>(K);
+  for (int c = lane; c < A; c += 32) {
+    float v = sigmoid_ref(logits.p[0][static_cast<long long>(row) * ld + c]);
+    for (int k = 1; k < K; ++k) {
+      const float s = sigmoid_ref(logits.p[k][static_cast<long long>(row) * ld + c]);
+      v = multiply ? v * s : v + s;
+    }
+    if (!multiply) v = v / kf;
+    best = better(best, ArgMax{v, c});
+  }
+  best = warp_argmax(best);
+  if (lane == 0) {
+    score[row] = best.v;
+    label[row] = best.i;
+  }
+}
+
 }  // namespace
+
+int score_ensemble(cudaStream_t stream, const float* const* logits, int K, int multiply, long long ld, int B, int A,
+                   float* score, int32_t* label) {
+  RGQA_CHECK(logits != nullptr && K >= 1 && K <= 8, "score_ensemble: between 1 and 8 logit matrices (got %d)", K);
+  RGQA_CHECK(B > 0 && A > 0 && score != nullptr && label != nullptr, "score_ensemble: bad arguments");
+  EnsemblePtrs ptrs{};
+  for (int k = 0; k < K; ++k) {
+    RGQA_CHECK(logits[k] != nullptr, "score_ensemble: null logit matrix %d", k);
+    ptrs.p[k] = logits[k];
+  }
+  ensemble_kernel<<<(B + kWarps - 1) / kWarps, kWarps * 32, 0, stream>>>(ptrs, K, multiply, ld, B, A, score, label);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 int score_logits(cudaStream_t stream, int mode, const float* logits, long long ld, int B, int A, float* score,
                  int32_t* label) {

@@ -198,6 +198,25 @@ def cast_bf16(x):
     return out
 
 
+def score_ensemble(logits_list, method="mean"):
+    """(score f32 [B], label i32 [B]) of an ensemble of checkpoints: per-class sigmoid vectors averaged ("mean") or
+    multiplied ("multiply"), then arg-max — src/tasks/gqa_ensemble.py:165-177 on the device."""
+    import ctypes as C
+    assert method in ("mean", "multiply") and 1 <= len(logits_list) <= 8
+    first = logits_list[0]
+    _need_cuda(*logits_list)
+    B, A = first.shape
+    for t in logits_list:
+        assert t.dtype == torch.float32 and t.shape == first.shape and t.stride() == first.stride() and t.stride(1) == 1
+    score = torch.empty(B, dtype=torch.float32, device=first.device)
+    label = torch.empty(B, dtype=torch.int32, device=first.device)
+    arr = (C.c_void_p * len(logits_list))(*[L.ptr(t) for t in logits_list])
+    lib = L.load()
+    L.check(lib.rgqa_score_ensemble(L.current_stream_ptr(), arr, len(logits_list), 1 if method == "multiply" else 0,
+                                    first.stride(0), B, A, L.ptr(score), L.ptr(label)), "rgqa_score_ensemble")
+    return score, label
+
+
 def score_logits(logits, mode="msp"):
     """(score f32 [B], label int32 [B]) for the logit scorers (gqa_conf.py:326, gqa_energy.py:131,185,204-206)."""
     _need_cuda(logits)

@@ -3,6 +3,7 @@ fp32 PyTorch statement of the reference op it replaces (file:line in each test).
 written next to each comparison."""
 import math
 
+import numpy as np
 import pytest
 import torch
 
@@ -341,3 +342,25 @@ def test_mahalanobis_matches_reference_loop(cuda_device):  # src/tasks/gqa_maha.
     rs, rl = ref.max(1)
     torch.testing.assert_close(score, rs, rtol=1e-3, atol=0)
     assert torch.equal(label.long(), rl)
+
+
+@pytest.mark.parametrize("method", ["mean", "multiply"])
+@pytest.mark.parametrize("K", [1, 2, 3])
+def test_ensemble_scorer_matches_oracle(cuda_device, method, K):
+    """src/tasks/gqa_ensemble.py:165-177: per-class sigmoid of K checkpoints combined, arg-max — one kernel vs the oracle
+    (labels identical wherever the oracle's top-2 margin exceeds float rounding, scores to 1e-6 abs)."""
+    from oracle import scorers_oracle as S
+    from rgqa_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(K * 10 + len(method))
+    B, A = 133, 1842
+    logits = [torch.randn(B, A, generator=g) * 2.0 for _ in range(K)]
+    score, label = ops.score_ensemble([t.to(cuda_device) for t in logits], method)
+    torch.cuda.synchronize()
+    probs = [torch.sigmoid(t).numpy() for t in logits]
+    ref_s, ref_l = S.ensemble(probs, method)
+    assert np.abs(score.cpu().numpy() - ref_s).max() <= 1e-6
+    comb = np.stack(probs).sum(0) / K if method == "mean" else np.prod(np.stack(probs), axis=0)
+    top2 = np.sort(comb, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-6
+    assert clear.sum() >= B - 2
+    assert np.array_equal(label.cpu().numpy()[clear], ref_l[clear])

@@ -86,3 +86,32 @@ def test_mahalanobis_oracle_equals_expanded_form():
     m = ((mu.double() @ P.double()) * mu.double()).sum(1)
     torch.testing.assert_close(full, -0.5 * (q - 2 * G + m), rtol=1e-10, atol=1e-10)
     assert torch.equal(label, full.argmax(1))
+
+
+def test_ensemble_oracle_matches_the_reference_loop_literally():
+    """src/tasks/gqa_ensemble.py:165-177 executed as written (dict of per-question float32 vectors, in-place += / *=,
+    / len for the mean, np.argmax) against the vectorised oracle."""
+    from oracle import scorers_oracle as S
+    rng = np.random.default_rng(7)
+    n, A, K = 37, 1842, 3
+    per_model = [1.0 / (1.0 + np.exp(-rng.normal(0, 2.0, size=(n, A)))).astype(np.float32) for _ in range(K)]
+    per_model[1][5] = per_model[0][5]            # ties / identical rows are legal inputs
+    for method in ("mean", "multiply"):
+        results_list = [{q: per_model[k][q].copy() for q in range(n)} for k in range(K)]
+        final_results = results_list[0]
+        for results in results_list[1:]:
+            for qid in results:
+                if method == "mean":
+                    final_results[qid] += results[qid]
+                else:
+                    final_results[qid] *= results[qid]
+        want = {}
+        for qid in final_results:
+            scores = final_results[qid] / len(results_list) if method == "mean" else final_results[qid]
+            label = np.argmax(scores)
+            want[qid] = (label, scores[label])
+        score, label = S.ensemble(per_model, method)
+        assert [int(l) for l in label] == [int(want[q][0]) for q in range(n)]
+        assert np.array_equal(score, np.array([want[q][1] for q in range(n)], dtype=np.float32))
+    with pytest.raises(ValueError):
+        S.ensemble(per_model, "median")

@@ -97,3 +97,55 @@ def test_uniter_module_matches_golden(cuda_device):
     logits, _ = m.forward_ids(inp["feat"].to(cuda_device), inp["pos7"].to(cuda_device), inp["ids"].to(cuda_device),
                               inp["seg"].to(cuda_device), inp["mask"].to(cuda_device))
     assert np.abs(logits.cpu().numpy() - z["logits"]).max() <= 1e-4
+
+
+def test_bf16_feature_store_sweep_is_bit_identical_to_fp32_features(cuda_device, tmp_path):
+    """features converted ONCE to a bf16 memory-mapped store (round-to-nearest-even on the host) give
+    exactly the scores of fp32 features cast on the device — at half the H2D bytes.  TSV -> store -> SweepLoader ->
+    SweepRunner, against the same questions pushed through the model from fp32 tensors."""
+    import base64
+    from rgqa_b200 import ingest
+    from rgqa_b200.tasks.gqa_eval import SweepRunner
+    from rgqa_b200.tasks.gqa_model import GQAModel_maha
+    sys.argv = ["x"]
+    m = GQAModel_maha(1842, args=_args("bf16"), max_seq_length=20)
+    m.load_state_dict(syn.lxmert_state_dict(variant="rich", head_sigma=0.2, **LAYERS), strict=True)
+    m = m.to(cuda_device)
+    n_img = 5
+    inp = syn.make_inputs(n_img, 20, seed=77)
+    rng = np.random.default_rng(5)
+    lines = []
+    for i in range(n_img):
+        w, h = 500, 400
+        boxes = (inp["pos"][i].numpy() * np.array([w, h, w, h], dtype=np.float32)).astype(np.float32)
+        vals = {"img_id": f"img{i}", "img_h": h, "img_w": w, "num_boxes": 36,
+                "objects_id": rng.integers(0, 1600, 36).astype(np.int64), "objects_conf": rng.random(36).astype(np.float32),
+                "attrs_id": rng.integers(0, 400, 36).astype(np.int64), "attrs_conf": rng.random(36).astype(np.float32),
+                "boxes": boxes, "features": inp["feat"][i].numpy()}
+        lines.append("\t".join(base64.b64encode(np.ascontiguousarray(vals[k]).tobytes()).decode() if isinstance(vals[k], np.ndarray)
+                               else str(vals[k]) for k in ingest.FIELDNAMES))
+    tsv = tmp_path / "obj.tsv"
+    tsv.write_text("\n".join(lines) + "\n")
+    store = ingest.convert_obj_tsv(str(tsv), str(tmp_path / "store"), dtype="bf16")
+    sents = ["is the cat on the mat?", "what color is the bus", "are there zebras", "who holds the umbrella", "is it raining",
+             "how many dogs are there", "what is left of the tree"]
+    imgs = [f"img{i % n_img}" for i in range(len(sents))]
+    data = [{"question_id": f"q{i}", "img_id": im, "sent": s} for i, (im, s) in enumerate(zip(imgs, sents))]
+    tok = m.lxrt_encoder.tokenizer
+    runner = SweepRunner(m, "energy")
+    got_s, got_l, qids = [], [], []
+    for q, f, b, ids, mask in ingest.SweepLoader(store, data, tok, max_seq_length=20, batch_size=4):
+        assert f.dtype == torch.bfloat16 and f.is_pinned()
+        s, l = runner.submit(f, b, ids, mask)
+        got_s.append(s.cpu()); got_l.append(l.cpu()); qids += q
+    assert qids == [d["question_id"] for d in data]
+    # reference route: fp32 features and the reference's per-item box normalisation, straight to the model
+    rows = [int(d["img_id"][3:]) for d in data]
+    feat32 = inp["feat"][rows].to(cuda_device)
+    boxes = torch.from_numpy(np.stack([ingest.normalize_boxes(inp["pos"][r].numpy() * np.array([500, 400, 500, 400], dtype=np.float32), 500, 400)
+                                       for r in rows])).to(cuda_device)
+    ids, mask, seg = tok.encode_batch(sents, 20)
+    logits, pooled = m.forward_ids(feat32, boxes, torch.from_numpy(ids).to(cuda_device), torch.from_numpy(seg).to(cuda_device),
+                                   torch.from_numpy(mask).to(cuda_device))
+    ref_s, ref_l = m.engine().score("energy", logits=logits, pooled=pooled)
+    assert torch.equal(torch.cat(got_s), ref_s.cpu()) and torch.equal(torch.cat(got_l), ref_l.cpu())
