@@ -175,6 +175,13 @@ int rgqa_visn_combine(void* stream, int out_dtype, const float* x_pre, const flo
                       const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
                       const float* b2, void* out, int M, int H, float eps);
 int rgqa_cast_f32_to_bf16(void* stream, const float* in, void* out, int64_t n);
+/* Data pass of GQA.sample_estimator (src/tasks/gqa_maha.py:138-168) for one batch: x [B, D] f32 pooled features,
+ * target [B, >= C] f32 multi-hot rows (row stride ld_target; the reference drops the last class, :141).  Adds to the
+ * caller's zero-initialised fp64 device accumulators: class_count[c] += 1 and class_sum[c, :] += x_i for every class c
+ * sample i is labelled with; G += w_i * x_i x_i^T with w_i = that sample's label count.  w_scratch: [B] f32 device
+ * scratch.  The finish (class means, centred covariance, pseudo-inverse; :170-183) is host work over these sums. */
+int rgqa_estimator_accumulate(void* stream, const float* x, const float* target, int64_t ld_target, int B, int C, int D,
+                              double* G, double* class_sum, double* class_count, float* w_scratch);
 /* Ensemble of K <= 8 checkpoints (src/tasks/gqa_ensemble.py:95-108, :165-177): `logits` is a HOST array of K device
  * pointers to [B, A] f32 logit matrices (row stride ld); per class sigmoid values are summed and divided by K
  * (method 0, "mean") or multiplied (method 1, "multiply") in checkpoint order; label = first arg-max, score = its value. */

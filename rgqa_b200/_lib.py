@@ -63,6 +63,7 @@ SIGNATURES = {
     "rgqa_layernorm": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _f]),
     "rgqa_visn_combine": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f]),
     "rgqa_cast_f32_to_bf16": (_i, [_vp, _vp, _vp, _i64]),
+    "rgqa_estimator_accumulate": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "rgqa_score_ensemble": (_i, [_vp, C.POINTER(_vp), _i, _i, _i64, _i, _i, _vp, _vp]),
     "rgqa_score_logits": (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _vp]),
     "rgqa_mahalanobis": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),

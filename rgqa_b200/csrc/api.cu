@@ -1378,6 +1378,11 @@ int rgqa_visn_combine(void* stream, int out_dtype, const float* x_pre, const flo
 int rgqa_cast_f32_to_bf16(void* stream, const float* in, void* out, int64_t n) {
   return cast_f32_to_bf16(static_cast<cudaStream_t>(stream), in, out, n);
 }
+int rgqa_estimator_accumulate(void* stream, const float* x, const float* target, int64_t ld_target, int B, int C, int D,
+                              double* G, double* class_sum, double* class_count, float* w_scratch) {
+  return estimator_accumulate(static_cast<cudaStream_t>(stream), x, target, ld_target, B, C, D, G, class_sum, class_count,
+                              w_scratch);
+}
 int rgqa_score_ensemble(void* stream, const float* const* logits, int K, int method, int64_t ld, int B, int A, float* score,
                         int32_t* label) {
   RGQA_CHECK(method == 0 || method == 1, "rgqa_score_ensemble: method must be 0 (mean) or 1 (multiply)");

@@ -104,6 +104,10 @@ enum ScoreMode : int {
   SCORE_LSE = 3,          // logsumexp(logits), label as MSP                     (gqa_energy.py:131)
   SCORE_MAHA = 4,         // max_c -0.5 (x-mu_c)^T P (x-mu_c), label = argmax_c  (gqa_maha.py:228-236,270)
 };
+// Mahalanobis estimator, data pass (gqa_maha.py:138-168): adds one batch to the fp64 accumulators G [D,D] (sum of w_i x x^T),
+// class_sum [C,D], class_count [C]; w_scratch [B] f32 receives the per-sample label counts.
+int estimator_accumulate(cudaStream_t stream, const float* x, const float* target, long long ld_t, int B, int C, int D,
+                         double* G, double* class_sum, double* class_count, float* w_scratch);
 int score_ensemble(cudaStream_t stream, const float* const* logits, int K, int multiply, long long ld, int B, int A,
                    float* score, int32_t* label);
 int score_logits(cudaStream_t stream, int mode, const float* logits, long long ld, int B, int A, float* score,

@@ -198,6 +198,24 @@ def cast_bf16(x):
     return out
 
 
+def estimator_accumulate(x, target, G, class_sum, class_count):
+    """One batch of the Mahalanobis estimator's data pass (src/tasks/gqa_maha.py:138-168) into fp64 device accumulators:
+    x [B, D] f32, target [B, >= C] f32 multi-hot, G [D, D], class_sum [C, D], class_count [C] (all float64, zeroed by the
+    caller before the first batch)."""
+    _need_cuda(x, target, G, class_sum, class_count)
+    assert x.dtype == torch.float32 and target.dtype == torch.float32 and x.is_contiguous() and target.stride(1) == 1
+    assert G.dtype == class_sum.dtype == class_count.dtype == torch.float64
+    B, D = x.shape
+    C = class_count.numel()
+    assert G.shape == (D, D) and class_sum.shape == (C, D) and target.shape[0] == B and target.shape[1] >= C
+    assert G.is_contiguous() and class_sum.is_contiguous()
+    w = torch.empty(B, dtype=torch.float32, device=x.device)
+    lib = L.load()
+    L.check(lib.rgqa_estimator_accumulate(L.current_stream_ptr(), L.ptr(x), L.ptr(target), target.stride(0), B, C, D, L.ptr(G),
+                                          L.ptr(class_sum), L.ptr(class_count), L.ptr(w)), "rgqa_estimator_accumulate")
+    return w
+
+
 def score_ensemble(logits_list, method="mean"):
     """(score f32 [B], label i32 [B]) of an ensemble of checkpoints: per-class sigmoid vectors averaged ("mean") or
     multiplied ("multiply"), then arg-max — src/tasks/gqa_ensemble.py:165-177 on the device."""

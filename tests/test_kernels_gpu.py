@@ -364,3 +364,36 @@ def test_ensemble_scorer_matches_oracle(cuda_device, method, K):
     clear = (top2[:, 1] - top2[:, 0]) > 1e-6
     assert clear.sum() >= B - 2
     assert np.array_equal(label.cpu().numpy()[clear], ref_l[clear])
+
+
+@pytest.mark.parametrize("N,C,D", [(1500, 300, 256), (900, 41, 96)])
+def test_gpu_sample_estimator_matches_oracle(cuda_device, N, C, D):
+    """GQA.sample_estimator (src/tasks/gqa_maha.py:138-183): streamed fp64 sums on the device + closed-form finish vs the
+    oracle's literal list-building loop + pooled class-centred covariance (itself pinned to sklearn in the CPU suite).
+    Multi-label rows, empty classes and one densely labelled row included; three uneven batches."""
+    from oracle import scorers_oracle as S
+    from rgqa_b200.tasks.gqa_maha import MahaEstimator
+    g = torch.Generator(device="cpu").manual_seed(N + C)
+    x = torch.tanh(torch.randn(N, D, generator=g) * 0.8 + 0.1 * torch.randn(1, D, generator=g))     # pooler outputs live in (-1, 1)
+    lab = torch.randint(0, C - 3, (N,), generator=g)                                               # the last 3 classes stay empty
+    target = torch.zeros(N, C + 1)                                                                 # + the 'UQ' column the reference drops
+    target[torch.arange(N), lab] = 1.0
+    extra = torch.randint(0, C - 3, (N // 10,), generator=g)
+    target[torch.arange(N // 10) * 10, extra] = 1.0                                                # every 10th sample carries a second label
+    target[7, : min(C - 3, 80)] = 1.0                                                              # > 64 labels: the dense walk
+    target[:, C] = (torch.rand(N, generator=g) < 0.3).float()
+    ref_mean, ref_prec = S.sample_estimator(x, target[:, :C])
+    est = MahaEstimator(C, D, cuda_device)
+    for lo, hi in ((0, 700), (700, 701), (701, N)):
+        est.accumulate(x[lo:hi].to(cuda_device), target[lo:hi, :C + 1][:, :C].contiguous())
+    mean, prec = est.finish()
+    assert torch.equal(mean[C - 3:], torch.zeros(3, D))
+    assert (mean - ref_mean).abs().max().item() <= 2e-6
+    scale = np.abs(ref_prec).max()
+    assert np.abs(prec - ref_prec).max() <= 2e-4 * scale, (np.abs(prec - ref_prec).max(), scale)
+    # and the scorer fed with either pair agrees to the scorer tolerance (1e-3 rel)
+    q = x[:64]
+    s_ref, l_ref, _ = S.mahalanobis(q, ref_mean, torch.from_numpy(ref_prec).float())
+    s_got, l_got, _ = S.mahalanobis(q, mean, torch.from_numpy(prec).float())
+    assert torch.equal(l_ref, l_got)
+    torch.testing.assert_close(s_got, s_ref, rtol=1e-3, atol=1e-4)

@@ -115,3 +115,24 @@ def test_ensemble_oracle_matches_the_reference_loop_literally():
         assert np.array_equal(score, np.array([want[q][1] for q in range(n)], dtype=np.float32))
     with pytest.raises(ValueError):
         S.ensemble(per_model, "median")
+
+
+def test_estimator_closed_form_finish_matches_the_list_building_oracle():
+    """rgqa_b200.tasks.gqa_maha.finish_estimator turns streamed sums (n_c, s_c, G = sum w_i x x^T) into the reference's
+    (class means, precision) pair; here the sums are formed with numpy and the result compared with the oracle's literal
+    restatement of src/tasks/gqa_maha.py:150-183 (multi-label rows and empty classes included)."""
+    from oracle import scorers_oracle as S
+    from rgqa_b200.tasks.gqa_maha import finish_estimator
+    g = torch.Generator().manual_seed(1)
+    N, C, D = 600, 30, 64
+    x = torch.tanh(torch.randn(N, D, generator=g))
+    t = torch.zeros(N, C)
+    t[torch.arange(N), torch.randint(0, C - 2, (N,), generator=g)] = 1
+    t[5, :10] = 1
+    ref_mean, ref_prec = S.sample_estimator(x, t)
+    xd, td = x.double().numpy(), t.double().numpy()
+    w = td.sum(1)
+    mean, prec = finish_estimator((xd * w[:, None]).T @ xd, td.T @ xd, td.sum(0))
+    assert (mean - ref_mean).abs().max().item() <= 1e-6
+    assert torch.equal(mean[C - 2:], torch.zeros(2, D))
+    assert np.abs(prec - ref_prec).max() <= 1e-6 * np.abs(ref_prec).max()
