@@ -175,6 +175,17 @@ int rgqa_visn_combine(void* stream, int out_dtype, const float* x_pre, const flo
                       const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
                       const float* b2, void* out, int M, int H, float eps);
 int rgqa_cast_f32_to_bf16(void* stream, const float* in, void* out, int64_t n);
+/* ---- RP-finetune groundwork (the backward graph itself is not built yet) ---------------- */
+/* loss = BCEWithLogitsLoss(mean)(logit, target) * A (src/tasks/gqa_conf.py:193-194): adds the loss to *loss_acc (device
+ * f64, zeroed by the caller) and writes dlogit = (sigmoid(logit) - target) / B when dlogit != NULL.  [B, A] f32, dense. */
+int rgqa_bce_loss_grad(void* stream, const float* logit, const float* target, int B, int A, float* dlogit, double* loss_acc);
+/* *acc += sum g[i]^2 (device f64): called once per gradient tensor, gives the global norm of clip_grad_norm_ (:197). */
+int rgqa_grad_sumsq(void* stream, const float* g, int64_t n, double* acc);
+/* BertAdam.step for one tensor (src/lxrt/optimization.py:127-176; no bias correction): gradients scaled by
+ * min(1, max_norm / (sqrt(*grad_sumsq_acc) + 1e-6)) when grad_sumsq_acc != NULL and max_norm > 0, then
+ * m = b1 m + (1-b1) g, v = b2 v + (1-b2) g^2, p -= lr_scheduled * (m / (sqrt(v) + eps) + weight_decay * p). */
+int rgqa_bertadam_step(void* stream, float* p, const float* g, float* m, float* v, int64_t n, float lr_scheduled, double b1,
+                       double b2, float eps, float weight_decay, const double* grad_sumsq_acc, float max_norm);
 /* Data pass of GQA.sample_estimator (src/tasks/gqa_maha.py:138-168) for one batch: x [B, D] f32 pooled features,
  * target [B, >= C] f32 multi-hot rows (row stride ld_target; the reference drops the last class, :141).  Adds to the
  * caller's zero-initialised fp64 device accumulators: class_count[c] += 1 and class_sum[c, :] += x_i for every class c

@@ -63,6 +63,9 @@ SIGNATURES = {
     "rgqa_layernorm": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _f]),
     "rgqa_visn_combine": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f]),
     "rgqa_cast_f32_to_bf16": (_i, [_vp, _vp, _vp, _i64]),
+    "rgqa_bce_loss_grad": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "rgqa_grad_sumsq": (_i, [_vp, _vp, _i64, _vp]),
+    "rgqa_bertadam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, C.c_double, C.c_double, _f, _f, _vp, _f]),
     "rgqa_estimator_accumulate": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "rgqa_score_ensemble": (_i, [_vp, C.POINTER(_vp), _i, _i, _i64, _i, _i, _vp, _vp]),
     "rgqa_score_logits": (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _vp]),

@@ -1378,6 +1378,17 @@ int rgqa_visn_combine(void* stream, int out_dtype, const float* x_pre, const flo
 int rgqa_cast_f32_to_bf16(void* stream, const float* in, void* out, int64_t n) {
   return cast_f32_to_bf16(static_cast<cudaStream_t>(stream), in, out, n);
 }
+int rgqa_bce_loss_grad(void* stream, const float* logit, const float* target, int B, int A, float* dlogit, double* loss_acc) {
+  return bce_loss_grad(static_cast<cudaStream_t>(stream), logit, target, B, A, dlogit, loss_acc);
+}
+int rgqa_grad_sumsq(void* stream, const float* g, int64_t n, double* acc) {
+  return grad_sumsq(static_cast<cudaStream_t>(stream), g, n, acc);
+}
+int rgqa_bertadam_step(void* stream, float* p, const float* g, float* m, float* v, int64_t n, float lr_scheduled, double b1,
+                       double b2, float eps, float weight_decay, const double* grad_sumsq_acc, float max_norm) {
+  return bertadam_step(static_cast<cudaStream_t>(stream), p, g, m, v, n, lr_scheduled, b1, b2, eps, weight_decay,
+                       grad_sumsq_acc, max_norm);
+}
 int rgqa_estimator_accumulate(void* stream, const float* x, const float* target, int64_t ld_target, int B, int C, int D,
                               double* G, double* class_sum, double* class_count, float* w_scratch) {
   return estimator_accumulate(static_cast<cudaStream_t>(stream), x, target, ld_target, B, C, D, G, class_sum, class_count,

@@ -104,6 +104,11 @@ enum ScoreMode : int {
   SCORE_LSE = 3,          // logsumexp(logits), label as MSP                     (gqa_energy.py:131)
   SCORE_MAHA = 4,         // max_c -0.5 (x-mu_c)^T P (x-mu_c), label = argmax_c  (gqa_maha.py:228-236,270)
 };
+// RP-finetune groundwork (optim.cu): BCE-with-logits loss * A and its logit gradient, global gradient norm, BertAdam update
+int bce_loss_grad(cudaStream_t stream, const float* logit, const float* target, int B, int A, float* dlogit, double* loss_acc);
+int grad_sumsq(cudaStream_t stream, const float* g, long long n, double* acc);
+int bertadam_step(cudaStream_t stream, float* p, const float* g, float* m, float* v, long long n, float lr_scheduled, double b1,
+                  double b2, float eps, float weight_decay, const double* grad_sumsq_acc, float max_norm);
 // Mahalanobis estimator, data pass (gqa_maha.py:138-168): adds one batch to the fp64 accumulators G [D,D] (sum of w_i x x^T),
 // class_sum [C,D], class_count [C]; w_scratch [B] f32 receives the per-sample label counts.
 int estimator_accumulate(cudaStream_t stream, const float* x, const float* target, long long ld_t, int B, int C, int D,

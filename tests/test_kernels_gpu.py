@@ -397,3 +397,38 @@ def test_gpu_sample_estimator_matches_oracle(cuda_device, N, C, D):
     s_got, l_got, _ = S.mahalanobis(q, mean, torch.from_numpy(prec).float())
     assert torch.equal(l_ref, l_got)
     torch.testing.assert_close(s_got, s_ref, rtol=1e-3, atol=1e-4)
+
+
+def test_bertadam_and_clip_match_reference_optimizer(cuda_device):
+    """BertAdam.step (src/lxrt/optimization.py:127-176) after nn.utils.clip_grad_norm_(params, 5.) (gqa_conf.py:197):
+    four steps of three tensors against the UNMODIFIED reference optimiser (tests/golden/bertadam_steps.npz) — parameters
+    and both moment buffers to 1e-6 relative (fp32 formula order is kept; sqrt / divide are IEEE-rounded)."""
+    import os
+    from rgqa_b200.lxrt.optimization import BertAdam
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "bertadam_steps.npz"))
+    params = [torch.from_numpy(z[f"p0_{i}"].copy()).to(cuda_device) for i in range(3)]
+    opt = BertAdam(params, lr=1e-3, warmup=0.1, t_total=10)
+    for k in range(4):
+        assert opt.get_lr()[0] == pytest.approx(float(z[f"lr{k}"]), rel=1e-12, abs=0)
+        grads = [torch.from_numpy(z[f"g{k}_{i}"].copy()).to(cuda_device) for i in range(3)]
+        sumsq = opt.step(grads, clip_norm=5.0)
+        assert float(sumsq.sqrt()) == pytest.approx(float(z[f"norm{k}"]), rel=1e-6)
+        for i in range(3):
+            torch.testing.assert_close(params[i].cpu(), torch.from_numpy(z[f"p{k + 1}_{i}"]), rtol=1e-6, atol=5e-9)  # atol: 5e-6 of the 1e-3 update where p cancels
+    for i in range(3):
+        torch.testing.assert_close(opt.state[i]["next_m"].cpu(), torch.from_numpy(z[f"m_{i}"]), rtol=1e-6, atol=1e-8)  # m sums signed terms: 1e-7 of the largest
+        torch.testing.assert_close(opt.state[i]["next_v"].cpu(), torch.from_numpy(z[f"v_{i}"]), rtol=1e-6, atol=1e-12)
+    assert opt.state[0]["step"] == 4
+    opt.step([None, None, None])                                   # p.grad is None: untouched, no step counted
+    assert opt.state[0]["step"] == 4
+
+
+def test_bce_loss_times_answers_and_its_gradient(cuda_device):
+    """loss = BCEWithLogitsLoss()(logit, target) * logit.size(1) (gqa_conf.py:193-194) and d loss / d logit vs torch autograd
+    of the same expression (golden computed by make_golden_bertadam.py)."""
+    import os
+    from rgqa_b200.lxrt.optimization import bce_loss_and_grad
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "bertadam_steps.npz"))
+    loss, dlogit = bce_loss_and_grad(torch.from_numpy(z["bce_logit"]).to(cuda_device), torch.from_numpy(z["bce_target"]).to(cuda_device))
+    assert float(loss) == pytest.approx(float(z["bce_loss"]), rel=1e-6)
+    torch.testing.assert_close(dlogit.cpu(), torch.from_numpy(z["bce_dlogit"]), rtol=1e-5, atol=1e-8)
