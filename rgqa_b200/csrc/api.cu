@@ -397,6 +397,17 @@ int fold_qkv(rgqa_handle* h, const std::string& p, const char* self_name, const 
   const std::string s = p + "." + self_name;
   return fold_stack(h, {s + ".query", s + ".key", s + ".value"}, h->cfg.hidden, h->cfg.hidden, *pred, out);
 }
+int make_identity_ln(rgqa_handle* h) {  // gamma = 1, beta = 0: the "LayerNorm" owed to an already-normalised state
+  const int H = h->cfg.hidden;
+  std::vector<float> one(H, 1.0f), zero(H, 0.0f);
+  RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->ones), H * sizeof(float)));
+  h->owned.push_back(h->ones);
+  RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->zeros), H * sizeof(float)));
+  h->owned.push_back(h->zeros);
+  RGQA_CUDA_OK(cudaMemcpy(h->ones, one.data(), H * sizeof(float), cudaMemcpyHostToDevice));
+  RGQA_CUDA_OK(cudaMemcpy(h->zeros, zero.data(), H * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
 // folds of one BertLayer whose input comes out of LayerNorm `pred` (nullptr: not behind a LayerNorm)
 int fold_bert_layer(rgqa_handle* h, const std::string& p, LayerW* w, const LNp* pred) {
   if (fold_qkv(h, p + ".attention", "self", pred, &w->att.qkv_f)) return 1;
@@ -695,13 +706,7 @@ int rgqa_finalize_weights(rgqa_handle* h) {
     if (c.precision == RGQA_PREC_BF16) {
       // deferred LayerNorm: every consumer of a hidden state gets a copy of its weight folded with the LayerNorm that
       // (notionally) produced that state; the embeddings' outputs are not behind one (nullptr)
-      std::vector<float> one(H, 1.0f), zero(H, 0.0f);
-      RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->ones), H * sizeof(float)));
-      h->owned.push_back(h->ones);
-      RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->zeros), H * sizeof(float)));
-      h->owned.push_back(h->zeros);
-      RGQA_CUDA_OK(cudaMemcpy(h->ones, one.data(), H * sizeof(float), cudaMemcpyHostToDevice));
-      RGQA_CUDA_OK(cudaMemcpy(h->zeros, zero.data(), H * sizeof(float), cudaMemcpyHostToDevice));
+      if (make_identity_ln(h)) return 1;
       const LNp *pl = nullptr, *pv = nullptr;
       for (int i = 0; i < c.l_layers; ++i) {
         if (fold_bert_layer(h, b + "encoder.layer." + std::to_string(i), &h->l_layers[i], pl)) return 1;
@@ -749,6 +754,16 @@ int rgqa_finalize_weights(rgqa_handle* h) {
     for (int i = 0; i < c.l_layers; ++i)
       if (make_bert_layer(h, u + "encoder.layer." + std::to_string(i), &h->l_layers[i])) return 1;
     if (make_linear(h, u + "pooler.dense", H, H, &h->pooler)) return 1;
+    h->pooler_f = Folded{};
+    if (c.precision == RGQA_PREC_BF16) {  // deferred LayerNorm: same folding as the LXMERT language stack
+      if (make_identity_ln(h)) return 1;
+      const LNp* pl = nullptr;
+      for (int i = 0; i < c.l_layers; ++i) {
+        if (fold_bert_layer(h, u + "encoder.layer." + std::to_string(i), &h->l_layers[i], pl)) return 1;
+        pl = &h->l_layers[i].ffn.ln;
+      }
+      if (pl != nullptr && fold_stack(h, {u + "pooler.dense"}, H, H, *pl, &h->pooler_f)) return 1;
+    }
   }
   if (c.num_answers > 0) {
     if (make_linear(h, "logit_fc.0", 2 * H, H, &h->fc0) || make_ln(h, "logit_fc.2", 2 * H, &h->fc_ln) ||
@@ -1185,10 +1200,15 @@ int rgqa_uniter_forward(rgqa_handle* h, void* stream, const void* feat, int feat
                                  static_cast<size_t>(S) * H * es, rows_at(h->ctx.p, Ml, H, es),
                                  static_cast<size_t>(V) * H * es, static_cast<size_t>(V) * H * es, B,
                                  cudaMemcpyDeviceToDevice, st));
+  // large bf16 batches: deferred LayerNorm (see lxmert_forward_deferred); the fp32 copies of the embeddings are then
+  // interleaved into the idle FFN buffer and only feed identity_state
+  const bool defer = bf && option_get(OPT_DEFER_LN) != 0 && option_get(OPT_GEMM_PAIR) != 0 && option_get(OPT_GEMM_STAGED) != 0 &&
+                     H == 768 && Mt >= 1024 && h->ones != nullptr;
+  float* res_dst = defer ? static_cast<float*>(h->inter.p) : cur.res;
   if (bf) {  // the fp32 residual copies (written into `pre` by the two embedding kernels) take the same route
-    RGQA_CUDA_OK(cudaMemcpy2DAsync(cur.res, static_cast<size_t>(S) * H * 4, h->pre.p, static_cast<size_t>(L) * H * 4,
+    RGQA_CUDA_OK(cudaMemcpy2DAsync(res_dst, static_cast<size_t>(S) * H * 4, h->pre.p, static_cast<size_t>(L) * H * 4,
                                    static_cast<size_t>(L) * H * 4, B, cudaMemcpyDeviceToDevice, st));
-    RGQA_CUDA_OK(cudaMemcpy2DAsync(cur.res + static_cast<size_t>(L) * H, static_cast<size_t>(S) * H * 4,
+    RGQA_CUDA_OK(cudaMemcpy2DAsync(res_dst + static_cast<size_t>(L) * H, static_cast<size_t>(S) * H * 4,
                                    rows_at(h->pre.p, Ml, H, 4), static_cast<size_t>(V) * H * 4,
                                    static_cast<size_t>(V) * H * 4, B, cudaMemcpyDeviceToDevice, st));
   }
@@ -1200,6 +1220,22 @@ int rgqa_uniter_forward(rgqa_handle* h, void* stream, const void* feat, int feat
     // give 0x01010101 (non-zero = keep), which is all the attention kernel tests for
     RGQA_CUDA_OK(cudaMemset2DAsync(reinterpret_cast<char*>(jmask) + static_cast<size_t>(L) * 4, static_cast<size_t>(S) * 4,
                                    1, static_cast<size_t>(V) * 4, B, st));
+  }
+  if (defer) {
+    DState dc{static_cast<char*>(h->hidA.p), static_cast<char*>(h->resA.p),
+              reinterpret_cast<float*>(static_cast<char*>(h->resA.p) + static_cast<size_t>(Mt) * H * 2)};
+    DState da{static_cast<char*>(h->hidB.p), static_cast<char*>(h->resB.p),
+              reinterpret_cast<float*>(static_cast<char*>(h->resB.p) + static_cast<size_t>(Mt) * H * 2)};
+    const DefCtx d{h, H};
+    if (identity_state(st, res_dst, dc.hi, dc.lo, dc.stats, Mt, H)) return 1;
+    const LNp* ln = nullptr;
+    for (int i = 0; i < c.l_layers; ++i) {
+      const LayerW& w = h->l_layers[i];
+      if (d.att(st, w.att, dc, ln, da, 0, B, S, jmask) || d.ffn(st, w.ffn, da, &w.att.ln, dc, 0, static_cast<int>(Mt))) return 1;
+      ln = &w.ffn.ln;
+    }
+    if (pooled_out == nullptr && logits_out == nullptr) return 0;
+    return head_block(h, st, dc.hi, B, S, pooled_out, logits_out, ln != nullptr ? dc.stats : nullptr);
   }
   for (int i = 0; i < c.l_layers; ++i) {
     if (att_block(h, st, h->l_layers[i].att, cur, alt, 0, B, S, jmask)) return 1;

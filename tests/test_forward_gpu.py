@@ -247,3 +247,31 @@ def test_deferred_layernorm_forward_matches_oracle_and_standard_path(cuda_device
     top2 = l32.topk(2).values
     confident = (top2[:, 0] - top2[:, 1]) > 0.4
     assert torch.equal(l_def.argmax(1)[confident], l32.argmax(1)[confident])
+
+
+def test_uniter_deferred_layernorm_matches_fp32_and_standard_path(cuda_device):
+    """UNITER (12 BertLayers over the joint 56-token sequence) on the deferred-LayerNorm path (B * 56 >= 1024 rows):
+    same tolerances as the LayerNorm-kernel bf16 path, against the fp32 CUDA path (itself pinned to the reference goldens
+    above)."""
+    from rgqa_b200 import _lib as L_
+    lib = L_.load()
+    inp = syn.make_inputs(24, 20, seed=91, vocab=28996)
+    p32, l32 = _run(_engine("uniter", "rich", "fp32"), inp, "pos7")
+    eng = _engine("uniter", "rich", "bf16")
+    try:
+        lib.rgqa_set_option(b"defer_ln", 0)
+        n0 = lib.rgqa_launch_count()
+        p_std, l_std = _run(eng, inp, "pos7")
+        n_std = lib.rgqa_launch_count() - n0
+        lib.rgqa_set_option(b"defer_ln", 1)
+        n0 = lib.rgqa_launch_count()
+        p_def, l_def = _run(eng, inp, "pos7")
+        n_def = lib.rgqa_launch_count() - n0
+    finally:
+        lib.rgqa_set_option(b"defer_ln", 1)
+    assert n_def <= n_std - 20, (n_def, n_std)            # the 24 LayerNorm launches are gone (+1 identity_state)
+    _assert_bf16_close(l_def.numpy(), l32.numpy())
+    e_std = float((l_std - l32).pow(2).mean().sqrt())
+    e_def = float((l_def - l32).pow(2).mean().sqrt())
+    assert e_def <= 1.3 * e_std + 1e-3, (e_def, e_std)
+    assert (p_def - p32).abs().max().item() <= 3e-2
