@@ -175,6 +175,22 @@ int rgqa_visn_combine(void* stream, int out_dtype, const float* x_pre, const flo
                       const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
                       const float* b2, void* out, int M, int H, float eps);
 int rgqa_cast_f32_to_bf16(void* stream, const float* in, void* out, int64_t n);
+/* ---- input-gradient (dgrad) kernels, fp32 path: d loss / d (feats, boxes) for ODIN (src/tasks/gqa_odin.py:97-131) and the
+ * Mahalanobis input pre-processing (src/tasks/gqa_maha.py:238-268).  Linear layers: rgqa_gemm_f32 against transposed weights
+ * (EPI_RESID adds the residual branch's gradient).  Orchestration: rgqa_b200/lxrt/input_grad.py. ------------------------- */
+/* dx = rstd·(g − mean(g) − xh·mean(g·xh)) (+ add), g = scale·dy·gamma, xh = (x − mean x)·rstd: BertLayerNorm backward w.r.t. its
+ * input x [M, H] (src/lxrt/modeling.py:258-270); add may be NULL. */
+int rgqa_layernorm_bwd(void* stream, const float* dy, const float* x, const float* gamma, const float* add, float* dx, int M,
+                       int H, float eps, float scale);
+/* erf-GELU (modeling.py:112-118) forward and backward on n elements; tanh backward from the OUTPUT y (BertPooler :575-581). */
+int rgqa_gelu_fwd(void* stream, const float* x, float* y, int64_t n);
+int rgqa_gelu_bwd(void* stream, const float* dy, const float* x, float* dx, int64_t n);
+int rgqa_tanh_bwd(void* stream, const float* dy, const float* y, float* dx, int64_t n);
+/* BertAttention core backward (modeling.py:330-346): probabilities recomputed from q, k, v (f32, row strides ld*), gradients
+ * of the three operands written to dq / dk / dv (same [row, head*64] layout, own strides).  Lq, Lk <= 64. */
+int rgqa_attention_bwd(void* stream, const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                       const int32_t* key_mask, const float* dctx, int64_t ldo, float* dq, int64_t lddq, float* dk, int64_t lddk,
+                       float* dv, int64_t lddv, int B, int Lq, int Lk, int heads);
 /* ---- RP-finetune groundwork (the backward graph itself is not built yet) ---------------- */
 /* loss = BCEWithLogitsLoss(mean)(logit, target) * A (src/tasks/gqa_conf.py:193-194): adds the loss to *loss_acc (device
  * f64, zeroed by the caller) and writes dlogit = (sigmoid(logit) - target) / B when dlogit != NULL.  [B, A] f32, dense. */

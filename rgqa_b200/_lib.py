@@ -63,6 +63,11 @@ SIGNATURES = {
     "rgqa_layernorm": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _f]),
     "rgqa_visn_combine": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f]),
     "rgqa_cast_f32_to_bf16": (_i, [_vp, _vp, _vp, _i64]),
+    "rgqa_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f]),
+    "rgqa_gelu_fwd": (_i, [_vp, _vp, _vp, _i64]),
+    "rgqa_gelu_bwd": (_i, [_vp, _vp, _vp, _vp, _i64]),
+    "rgqa_tanh_bwd": (_i, [_vp, _vp, _vp, _vp, _i64]),
+    "rgqa_attention_bwd": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i]),
     "rgqa_bce_loss_grad": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "rgqa_grad_sumsq": (_i, [_vp, _vp, _i64, _vp]),
     "rgqa_bertadam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, C.c_double, C.c_double, _f, _f, _vp, _f]),

@@ -1414,6 +1414,23 @@ int rgqa_visn_combine(void* stream, int out_dtype, const float* x_pre, const flo
 int rgqa_cast_f32_to_bf16(void* stream, const float* in, void* out, int64_t n) {
   return cast_f32_to_bf16(static_cast<cudaStream_t>(stream), in, out, n);
 }
+int rgqa_layernorm_bwd(void* stream, const float* dy, const float* x, const float* gamma, const float* add, float* dx, int M,
+                       int H, float eps, float scale) {
+  return layernorm_bwd(static_cast<cudaStream_t>(stream), dy, x, gamma, add, dx, M, H, eps, scale);
+}
+int rgqa_gelu_fwd(void* stream, const float* x, float* y, int64_t n) { return gelu_fwd(static_cast<cudaStream_t>(stream), x, y, n); }
+int rgqa_gelu_bwd(void* stream, const float* dy, const float* x, float* dx, int64_t n) {
+  return gelu_bwd(static_cast<cudaStream_t>(stream), dy, x, dx, n);
+}
+int rgqa_tanh_bwd(void* stream, const float* dy, const float* y, float* dx, int64_t n) {
+  return tanh_bwd(static_cast<cudaStream_t>(stream), dy, y, dx, n);
+}
+int rgqa_attention_bwd(void* stream, const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                       const int32_t* key_mask, const float* dctx, int64_t ldo, float* dq, int64_t lddq, float* dk, int64_t lddk,
+                       float* dv, int64_t lddv, int B, int Lq, int Lk, int heads) {
+  return attention_bwd(static_cast<cudaStream_t>(stream), q, ldq, k, ldk, v, ldv, key_mask, dctx, ldo, dq, lddq, dk, lddk, dv, lddv,
+                       B, Lq, Lk, heads);
+}
 int rgqa_bce_loss_grad(void* stream, const float* logit, const float* target, int B, int A, float* dlogit, double* loss_acc) {
   return bce_loss_grad(static_cast<cudaStream_t>(stream), logit, target, B, A, dlogit, loss_acc);
 }

@@ -1,0 +1,213 @@
+// rgqa_b200 — input-gradient (dgrad) kernels of the fp32 path: what ODIN (src/tasks/gqa_odin.py:97-131) and the
+// Mahalanobis input pre-processing (src/tasks/gqa_maha.py:238-268) need from `loss.backward()` is d loss / d (feats, boxes)
+// only — no weight gradients.  The linear layers' dgrad is the forward fp32 GEMM against transposed weight copies
+// (gemm_f32 with EPI_RESID folds the residual branch's gradient in); this file holds the rest:
+//
+//   layernorm_bwd   BertLayerNorm (modeling.py:258-270):  xh = (x-mu)*rstd, g = dy*gamma,
+//                   dx = rstd * (g - mean(g) - xh * mean(g*xh))  [* scale, + add]
+//   gelu_fwd/bwd    gelu (modeling.py:112-118): y = x Phi(x);  dx = dy (Phi(x) + x phi(x))
+//   tanh_bwd        BertPooler (modeling.py:575-581): dx = dy (1 - y^2)
+//   attention_bwd   BertAttention core (modeling.py:330-346), probabilities recomputed:
+//                   dV = P^T dO;  dP = dO V^T;  dS = P (dP - rowsum(dP P));  dQ = dS K / 8;  dK = dS^T Q / 8
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rgqa {
+namespace {
+
+constexpr int HD = 64;
+
+__global__ void __launch_bounds__(128)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ add, float* __restrict__ dx, int M, int H, float eps, float scale) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + static_cast<long long>(row) * H;
+  const float* dr = dy + static_cast<long long>(row) * H;
+  float s = 0.f;
+  for (int c = lane; c < H; c += 32) s += xr[c];
+  const float mu = warp_sum(s) / static_cast<float>(H);
+  float q = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    const float d = xr[c] - mu;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(H) + eps);
+  float m1 = 0.f, m2 = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    const float g = dr[c] * gamma[c] * scale;
+    m1 += g;
+    m2 = fmaf(g, (xr[c] - mu) * rstd, m2);
+  }
+  m1 = warp_sum(m1) / static_cast<float>(H);
+  m2 = warp_sum(m2) / static_cast<float>(H);
+  for (int c = lane; c < H; c += 32) {
+    const float g = dr[c] * gamma[c] * scale;
+    float v = rstd * (g - m1 - (xr[c] - mu) * rstd * m2);
+    if (add != nullptr) v += add[static_cast<long long>(row) * H + c];
+    dx[static_cast<long long>(row) * H + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = gelu_erf(x[i]);
+}
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
+    dx[i] = dy[i] * fmaf(v, pdf, cdf);
+  }
+}
+__global__ void __launch_bounds__(256)
+tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dx[i] = dy[i] * (1.0f - y[i] * y[i]);
+}
+
+// one CTA per (sample, head); everything of the head lives in shared memory (Lq, Lk <= 64)
+__global__ void __launch_bounds__(256)
+attention_bwd_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k, long long ldk,
+                     const float* __restrict__ v, long long ldv, const int32_t* __restrict__ key_mask,
+                     const float* __restrict__ dctx, long long ldo, float* __restrict__ dq, long long lddq,
+                     float* __restrict__ dk, long long lddk, float* __restrict__ dv, long long lddv, int Lq, int Lk, int heads) {
+  extern __shared__ float sm_bwd[];
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  float* Qs = sm_bwd;                 // [Lq][65]
+  float* Ks = Qs + Lq * 65;           // [Lk][65]
+  float* Vs = Ks + Lk * 65;           // [Lk][65]
+  float* Os = Vs + Lk * 65;           // dO [Lq][65]
+  float* P = Os + Lq * 65;            // [Lq][Lk + 1]
+  float* dS = P + Lq * (Lk + 1);      // [Lq][Lk + 1]
+  const int tid = threadIdx.x;
+  for (int e = tid; e < Lq * HD; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    Qs[r * 65 + c] = q[(static_cast<long long>(b) * Lq + r) * ldq + h * HD + c];
+    Os[r * 65 + c] = dctx[(static_cast<long long>(b) * Lq + r) * ldo + h * HD + c];
+  }
+  for (int e = tid; e < Lk * HD; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    Ks[r * 65 + c] = k[(static_cast<long long>(b) * Lk + r) * ldk + h * HD + c];
+    Vs[r * 65 + c] = v[(static_cast<long long>(b) * Lk + r) * ldv + h * HD + c];
+  }
+  __syncthreads();
+  // scores + additive mask (modeling.py:333-336) and dP = dO V^T
+  for (int e = tid; e < Lq * Lk; e += 256) {
+    const int i = e / Lk, j = e % Lk;
+    float s = 0.f, dp = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < HD; ++c) {
+      s = fmaf(Qs[i * 65 + c], Ks[j * 65 + c], s);
+      dp = fmaf(Os[i * 65 + c], Vs[j * 65 + c], dp);
+    }
+    s *= 0.125f;
+    if (key_mask != nullptr && key_mask[b * Lk + j] == 0) s += -10000.0f;
+    P[i * (Lk + 1) + j] = s;
+    dS[i * (Lk + 1) + j] = dp;
+  }
+  __syncthreads();
+  // row softmax, then dS = P (dP - sum_j dP P): one warp per row
+  for (int i = tid >> 5; i < Lq; i += 8) {
+    const int lane = tid & 31;
+    float mx = -INFINITY;
+    for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, P[i * (Lk + 1) + j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < Lk; j += 32) {
+      const float p = expf(P[i * (Lk + 1) + j] - mx);
+      P[i * (Lk + 1) + j] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    float dot = 0.f;
+    for (int j = lane; j < Lk; j += 32) {
+      const float p = P[i * (Lk + 1) + j] * inv;
+      P[i * (Lk + 1) + j] = p;
+      dot = fmaf(dS[i * (Lk + 1) + j], p, dot);
+    }
+    dot = warp_sum(dot);
+    for (int j = lane; j < Lk; j += 32) dS[i * (Lk + 1) + j] = P[i * (Lk + 1) + j] * (dS[i * (Lk + 1) + j] - dot);
+  }
+  __syncthreads();
+  // dQ = dS K / 8
+  for (int e = tid; e < Lq * HD; e += 256) {
+    const int i = e >> 6, c = e & 63;
+    float a = 0.f;
+    for (int j = 0; j < Lk; ++j) a = fmaf(dS[i * (Lk + 1) + j], Ks[j * 65 + c], a);
+    dq[(static_cast<long long>(b) * Lq + i) * lddq + h * HD + c] = a * 0.125f;
+  }
+  // dK = dS^T Q / 8, dV = P^T dO
+  for (int e = tid; e < Lk * HD; e += 256) {
+    const int j = e >> 6, c = e & 63;
+    float a = 0.f, g = 0.f;
+    for (int i = 0; i < Lq; ++i) {
+      a = fmaf(dS[i * (Lk + 1) + j], Qs[i * 65 + c], a);
+      g = fmaf(P[i * (Lk + 1) + j], Os[i * 65 + c], g);
+    }
+    dk[(static_cast<long long>(b) * Lk + j) * lddk + h * HD + c] = a * 0.125f;
+    dv[(static_cast<long long>(b) * Lk + j) * lddv + h * HD + c] = g;
+  }
+}
+
+inline int ew_grid(long long n) {
+  long long g = (n + 255) / 256;
+  return static_cast<int>(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g));
+}
+
+}  // namespace
+
+int layernorm_bwd(cudaStream_t stream, const float* dy, const float* x, const float* gamma, const float* add, float* dx, int M,
+                  int H, float eps, float scale) {
+  RGQA_CHECK(dy && x && gamma && dx && M > 0 && H > 0, "layernorm_bwd: bad arguments");
+  layernorm_bwd_kernel<<<(M + 3) / 4, 128, 0, stream>>>(dy, x, gamma, add, dx, M, H, eps, scale);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int gelu_fwd(cudaStream_t stream, const float* x, float* y, long long n) {
+  RGQA_CHECK(x && y && n > 0, "gelu_fwd: bad arguments");
+  gelu_fwd_kernel<<<ew_grid(n), 256, 0, stream>>>(x, y, n);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int gelu_bwd(cudaStream_t stream, const float* dy, const float* x, float* dx, long long n) {
+  RGQA_CHECK(dy && x && dx && n > 0, "gelu_bwd: bad arguments");
+  gelu_bwd_kernel<<<ew_grid(n), 256, 0, stream>>>(dy, x, dx, n);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int tanh_bwd(cudaStream_t stream, const float* dy, const float* y, float* dx, long long n) {
+  RGQA_CHECK(dy && y && dx && n > 0, "tanh_bwd: bad arguments");
+  tanh_bwd_kernel<<<ew_grid(n), 256, 0, stream>>>(dy, y, dx, n);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int attention_bwd(cudaStream_t stream, const float* q, long long ldq, const float* k, long long ldk, const float* v,
+                  long long ldv, const int32_t* key_mask, const float* dctx, long long ldo, float* dq, long long lddq, float* dk,
+                  long long lddk, float* dv, long long lddv, int B, int Lq, int Lk, int heads) {
+  RGQA_CHECK(q && k && v && dctx && dq && dk && dv, "attention_bwd: null argument");
+  RGQA_CHECK(B > 0 && heads > 0 && Lq >= 1 && Lq <= 64 && Lk >= 1 && Lk <= 64, "attention_bwd: Lq=%d Lk=%d out of range [1,64]", Lq, Lk);
+  const size_t smem = (static_cast<size_t>(2 * Lq + 2 * Lk) * 65 + 2 * static_cast<size_t>(Lq) * (Lk + 1)) * sizeof(float);
+  static bool cfg = false;
+  if (!cfg) {
+    RGQA_CUDA_OK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    cfg = true;
+  }
+  attention_bwd_kernel<<<B * heads, 256, smem, stream>>>(q, ldq, k, ldk, v, ldv, key_mask, dctx, ldo, dq, lddq, dk, lddk, dv, lddv,
+                                                         Lq, Lk, heads);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rgqa

@@ -104,6 +104,15 @@ enum ScoreMode : int {
   SCORE_LSE = 3,          // logsumexp(logits), label as MSP                     (gqa_energy.py:131)
   SCORE_MAHA = 4,         // max_c -0.5 (x-mu_c)^T P (x-mu_c), label = argmax_c  (gqa_maha.py:228-236,270)
 };
+// input-gradient (dgrad) kernels of the fp32 path (backward.cu)
+int layernorm_bwd(cudaStream_t stream, const float* dy, const float* x, const float* gamma, const float* add, float* dx, int M,
+                  int H, float eps, float scale);
+int gelu_fwd(cudaStream_t stream, const float* x, float* y, long long n);
+int gelu_bwd(cudaStream_t stream, const float* dy, const float* x, float* dx, long long n);
+int tanh_bwd(cudaStream_t stream, const float* dy, const float* y, float* dx, long long n);
+int attention_bwd(cudaStream_t stream, const float* q, long long ldq, const float* k, long long ldk, const float* v,
+                  long long ldv, const int32_t* key_mask, const float* dctx, long long ldo, float* dq, long long lddq, float* dk,
+                  long long lddk, float* dv, long long lddv, int B, int Lq, int Lk, int heads);
 // RP-finetune groundwork (optim.cu): BCE-with-logits loss * A and its logit gradient, global gradient norm, BertAdam update
 int bce_loss_grad(cudaStream_t stream, const float* logit, const float* target, int B, int A, float* dlogit, double* loss_acc);
 int grad_sumsq(cudaStream_t stream, const float* g, long long n, double* acc);

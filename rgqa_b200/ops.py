@@ -262,3 +262,55 @@ def mahalanobis(x, mu, precision, return_full=False):
     L.check(lib.rgqa_mahalanobis(L.current_stream_ptr(), L.ptr(x), L.ptr(mu), L.ptr(precision), B, A, H, L.ptr(work),
                                  L.ptr(score), L.ptr(label), L.ptr(full)), "rgqa_mahalanobis")
     return (score, label, full) if return_full else (score, label)
+
+
+# ---- input-gradient (dgrad) kernels of the fp32 path (rgqa_b200/csrc/backward.cu) ----------------------------------
+def layernorm_bwd(dy, x, gamma, add=None, eps=1e-12, scale=1.0):
+    """d/dx of BertLayerNorm(x)·gamma + beta given dy (both [M, H] f32); ``add``: gradient of a parallel branch to sum in."""
+    _need_cuda(dy, x, gamma, add)
+    assert dy.dtype == x.dtype == torch.float32 and dy.shape == x.shape and dy.is_contiguous() and x.is_contiguous()
+    assert add is None or (add.is_contiguous() and add.shape == x.shape)
+    M, H = x.shape
+    dx = torch.empty_like(x)
+    L.check(L.load().rgqa_layernorm_bwd(L.current_stream_ptr(), L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(add), L.ptr(dx), M, H,
+                                        eps, scale), "rgqa_layernorm_bwd")
+    return dx
+
+
+def gelu_fwd(x):
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty_like(x)
+    L.check(L.load().rgqa_gelu_fwd(L.current_stream_ptr(), L.ptr(x), L.ptr(y), x.numel()), "rgqa_gelu_fwd")
+    return y
+
+
+def gelu_bwd(dy, x):
+    _need_cuda(dy, x)
+    assert dy.dtype == x.dtype == torch.float32 and dy.is_contiguous() and x.is_contiguous() and dy.shape == x.shape
+    dx = torch.empty_like(x)
+    L.check(L.load().rgqa_gelu_bwd(L.current_stream_ptr(), L.ptr(dy), L.ptr(x), L.ptr(dx), x.numel()), "rgqa_gelu_bwd")
+    return dx
+
+
+def tanh_bwd(dy, y):
+    _need_cuda(dy, y)
+    assert dy.dtype == y.dtype == torch.float32 and dy.is_contiguous() and y.is_contiguous() and dy.shape == y.shape
+    dx = torch.empty_like(y)
+    L.check(L.load().rgqa_tanh_bwd(L.current_stream_ptr(), L.ptr(dy), L.ptr(y), L.ptr(dx), y.numel()), "rgqa_tanh_bwd")
+    return dx
+
+
+def attention_bwd(qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv, B, Lq, Lk, key_mask=None, heads=12):
+    """Backward of :func:`attention`: Q from ``qkv_q`` [B*Lq, 3H], K / V from ``qkv_kv`` [B*Lk, 3H], ``dctx`` [B*Lq, H];
+    writes dQ into columns [0, H) of ``dqkv_q`` and dK, dV into columns [H, 3H) of ``dqkv_kv`` (f32, fused layout)."""
+    _need_cuda(qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv, key_mask)
+    H = heads * 64
+    for t in (qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert qkv_q.shape == dqkv_q.shape == (B * Lq, 3 * H) and qkv_kv.shape == dqkv_kv.shape == (B * Lk, 3 * H)
+    assert dctx.shape == (B * Lq, H)
+    L.check(L.load().rgqa_attention_bwd(L.current_stream_ptr(), L.ptr(qkv_q), 3 * H, qkv_kv.data_ptr() + H * 4, 3 * H,
+                                        qkv_kv.data_ptr() + 2 * H * 4, 3 * H, L.ptr(key_mask), L.ptr(dctx), H,
+                                        L.ptr(dqkv_q), 3 * H, dqkv_kv.data_ptr() + H * 4, 3 * H,
+                                        dqkv_kv.data_ptr() + 2 * H * 4, 3 * H, B, Lq, Lk, heads), "rgqa_attention_bwd")

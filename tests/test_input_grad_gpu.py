@@ -1,0 +1,103 @@
+"""SURVEY §8(f) rank 1 on the GPU: the taped fp32 forward, d loss / d (feats, boxes) against torch autograd through the
+CPU oracle, and the two scorers built on it (ODIN, Mahalanobis with noise) against the oracle's restatement of the
+reference lines."""
+import numpy as np
+import pytest
+import torch
+
+from rgqa_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+LAYERS = dict(l_layers=2, x_layers=2, r_layers=1)
+
+
+@pytest.fixture(scope="module")
+def setup(cuda_device):
+    from rgqa_b200.lxrt.input_grad import LXMERTInputGrad
+    sd = syn.lxmert_state_dict(variant="rich", **LAYERS)      # default head: max sigmoid ~0.9, so the BCE gradient is alive
+    ig = LXMERTInputGrad(sd, device=cuda_device, **LAYERS)
+    inp = syn.make_inputs(3, 20, seed=21)
+    return sd, ig, inp
+
+
+def _rel(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+def test_taped_forward_equals_engine_and_oracle(setup, cuda_device):
+    from oracle import lxmert_oracle as O
+    from rgqa_b200.engine import Engine, EngineConfig
+    sd, ig, inp = setup
+    logits, pooled = ig.forward(inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"])
+    ref_logits, ref_pooled = O.gqa_model_forward(sd, inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"])
+    assert (pooled.cpu() - ref_pooled).abs().max() <= 1e-4 and (logits.cpu() - ref_logits).abs().max() <= 1e-3
+    eng = Engine(EngineConfig(precision="fp32", **LAYERS), device=str(cuda_device))
+    eng.load_weights(sd.items())
+    d = eng.device
+    p2, l2 = eng.forward(*(inp[k].to(d) for k in ("feat", "pos", "ids", "seg", "mask")))
+    assert (l2 - logits).abs().max().item() <= 1e-4        # same kernels (GELU as a separate pass here)
+    eng.close()
+
+
+@pytest.mark.parametrize("what", ["logits", "pooled", "both"])
+def test_input_gradients_match_autograd_through_the_oracle(setup, what):
+    from oracle import lxmert_oracle as O
+    sd, ig, inp = setup
+    g = torch.Generator().manual_seed(5)
+    feats, boxes = inp["feat"].clone().requires_grad_(True), inp["pos"].clone().requires_grad_(True)
+    x = O.lxmert_encode(sd, feats, boxes, inp["ids"], inp["seg"], inp["mask"])
+    logit = O.gqa_head(sd, x)
+    wl, wp = torch.randn(logit.shape, generator=g), torch.randn(x.shape, generator=g)
+    loss = (logit * wl).sum() * (what != "pooled") + (x * wp).sum() * (what != "logits")
+    loss.backward()
+    ig.forward(inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"])
+    dfeat, dpos = ig.backward(dlogits=None if what == "pooled" else wl, dpooled=None if what == "logits" else wp)
+    assert _rel(dfeat.cpu(), feats.grad) <= 2e-4, _rel(dfeat.cpu(), feats.grad)
+    assert _rel(dpos.cpu(), boxes.grad) <= 2e-4, _rel(dpos.cpu(), boxes.grad)
+    big = feats.grad.abs() > 1e-3 * feats.grad.abs().max()
+    assert (torch.sign(dfeat.cpu())[big] == torch.sign(feats.grad)[big]).float().mean().item() >= 0.9999
+
+
+def test_odin_scores_match_oracle(setup):
+    from oracle import odin_oracle as OO
+    from rgqa_b200.tasks.gqa_odin import odin_scores
+    sd, ig, inp = setup
+    for T, noise in ((1.0, 1e-4), (2.0, 1e-3)):
+        ref_s, ref_l, ref_gf, ref_gb = OO.odin(sd, inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"], T, noise)
+        s, l, gf, gb = odin_scores(ig, inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"], T, noise)
+        assert _rel(gf.cpu(), ref_gf) <= 2e-4 and _rel(gb.cpu(), ref_gb) <= 2e-4
+        assert torch.equal(l.cpu().long(), ref_l)
+        torch.testing.assert_close(s.cpu(), ref_s, rtol=1e-3, atol=1e-6)
+
+
+def test_mahalanobis_with_noise_matches_oracle(setup):
+    from oracle import odin_oracle as OO
+    from rgqa_b200.tasks.gqa_odin import mahalanobis_noise_scores
+    sd, ig, inp = setup
+    mu, P = syn.maha_stats(num_answers=60)
+    ref_s, ref_l, ref_gf, ref_gb = OO.mahalanobis_with_noise(sd, inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"], mu, P, 1e-3)
+    s, l, gf, gb = mahalanobis_noise_scores(ig, inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"], mu, P, 1e-3)
+    assert _rel(gf.cpu(), ref_gf) <= 2e-4 and _rel(gb.cpu(), ref_gb) <= 2e-4
+    assert torch.equal(l.cpu().long(), ref_l)
+    torch.testing.assert_close(s.cpu(), ref_s, rtol=1e-3, atol=1e-5)
+
+
+def test_full_depth_lxmert_input_gradients(cuda_device):
+    """All 9 / 5 / 5 layers (five cross-modality layers in a row: gradients of both streams through the shared
+    cross-attention module), B = 2, against autograd through the oracle."""
+    from oracle import lxmert_oracle as O
+    from rgqa_b200.lxrt.input_grad import LXMERTInputGrad
+    sd = syn.lxmert_state_dict(variant="rich")
+    ig = LXMERTInputGrad(sd, device=cuda_device)
+    inp = syn.make_inputs(2, 20, seed=33)
+    feats, boxes = inp["feat"].clone().requires_grad_(True), inp["pos"].clone().requires_grad_(True)
+    x = O.lxmert_encode(sd, feats, boxes, inp["ids"], inp["seg"], inp["mask"])
+    logit = O.gqa_head(sd, x)
+    g = torch.Generator().manual_seed(6)
+    wl = torch.randn(logit.shape, generator=g)
+    (logit * wl).sum().backward()
+    logits, _ = ig.forward(inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"])
+    assert (logits.cpu() - logit.detach()).abs().max().item() <= 1e-3
+    dfeat, dpos = ig.backward(dlogits=wl)
+    assert _rel(dfeat.cpu(), feats.grad) <= 5e-4, _rel(dfeat.cpu(), feats.grad)
+    assert _rel(dpos.cpu(), boxes.grad) <= 5e-4, _rel(dpos.cpu(), boxes.grad)
