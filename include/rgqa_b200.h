@@ -191,6 +191,21 @@ int rgqa_tanh_bwd(void* stream, const float* dy, const float* y, float* dx, int6
 int rgqa_attention_bwd(void* stream, const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                        const int32_t* key_mask, const float* dctx, int64_t ldo, float* dq, int64_t lddq, float* dk, int64_t lddk,
                        float* dv, int64_t lddv, int B, int Lq, int Lk, int heads);
+/* ---- weight-gradient kernels, fp32 path (the parameter half of loss.backward(), src/tasks/gqa_conf.py:196).  Every one of
+ * them ADDS to its output; the caller zeroes the gradient buffers once per step.  Orchestration: rgqa_b200/lxrt/trainer.py. */
+/* dW[N, K] += dY[M, N]^T · X[M, K]  (nn.Linear weight; row strides lda / ldb / ldo). */
+int rgqa_gemm_f32_tn(void* stream, const float* A, int64_t lda, const float* B, int64_t ldb, float* out, int64_t ldo, int M, int N,
+                     int K);
+/* out[N] += sum over the M rows of X[M, N]  (nn.Linear bias). */
+int rgqa_colsum(void* stream, const float* X, int64_t ldx, float* out, int M, int N);
+/* BertLayerNorm parameters: dgamma[c] += sum_m scale·dy[m,c]·xh[m,c], dbeta[c] += sum_m scale·dy[m,c]; x is the LayerNorm INPUT
+ * (xh recomputed); H = 768 or 1536. */
+int rgqa_ln_param_grad(void* stream, const float* dy, const float* x, float* dgamma, float* dbeta, int M, int H, float eps,
+                       float scale);
+/* nn.Embedding: table[idx[r], :] += g[r, :] for r < rows; indices outside [0, table_rows) and idx == padding_idx are skipped
+ * (pass -1 for none; the reference's three BertEmbeddings tables all use padding_idx = 0, src/lxrt/modeling.py:272-274). */
+int rgqa_embedding_scatter(void* stream, const float* g, const int32_t* idx, float* table, int rows, int H, int table_rows,
+                           int padding_idx);
 /* ---- RP-finetune groundwork (the backward graph itself is not built yet) ---------------- */
 /* loss = BCEWithLogitsLoss(mean)(logit, target) * A (src/tasks/gqa_conf.py:193-194): adds the loss to *loss_acc (device
  * f64, zeroed by the caller) and writes dlogit = (sigmoid(logit) - target) / B when dlogit != NULL.  [B, A] f32, dense. */

@@ -68,6 +68,10 @@ SIGNATURES = {
     "rgqa_gelu_bwd": (_i, [_vp, _vp, _vp, _vp, _i64]),
     "rgqa_tanh_bwd": (_i, [_vp, _vp, _vp, _vp, _i64]),
     "rgqa_attention_bwd": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i]),
+    "rgqa_gemm_f32_tn": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i]),
+    "rgqa_colsum": (_i, [_vp, _vp, _i64, _vp, _i, _i]),
+    "rgqa_ln_param_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f]),
+    "rgqa_embedding_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "rgqa_bce_loss_grad": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "rgqa_grad_sumsq": (_i, [_vp, _vp, _i64, _vp]),
     "rgqa_bertadam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, C.c_double, C.c_double, _f, _f, _vp, _f]),

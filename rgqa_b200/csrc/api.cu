@@ -1431,6 +1431,21 @@ int rgqa_attention_bwd(void* stream, const float* q, int64_t ldq, const float* k
   return attention_bwd(static_cast<cudaStream_t>(stream), q, ldq, k, ldk, v, ldv, key_mask, dctx, ldo, dq, lddq, dk, lddk, dv, lddv,
                        B, Lq, Lk, heads);
 }
+int rgqa_gemm_f32_tn(void* stream, const float* A, int64_t lda, const float* B, int64_t ldb, float* out, int64_t ldo, int M, int N,
+                     int K) {
+  return gemm_f32_tn(static_cast<cudaStream_t>(stream), A, lda, B, ldb, out, ldo, M, N, K);
+}
+int rgqa_colsum(void* stream, const float* X, int64_t ldx, float* out, int M, int N) {
+  return colsum(static_cast<cudaStream_t>(stream), X, ldx, out, M, N);
+}
+int rgqa_ln_param_grad(void* stream, const float* dy, const float* x, float* dgamma, float* dbeta, int M, int H, float eps,
+                       float scale) {
+  return ln_param_grad(static_cast<cudaStream_t>(stream), dy, x, dgamma, dbeta, M, H, eps, scale);
+}
+int rgqa_embedding_scatter(void* stream, const float* g, const int32_t* idx, float* table, int rows, int H, int table_rows,
+                           int padding_idx) {
+  return embedding_scatter(static_cast<cudaStream_t>(stream), g, idx, table, rows, H, table_rows, padding_idx);
+}
 int rgqa_bce_loss_grad(void* stream, const float* logit, const float* target, int B, int A, float* dlogit, double* loss_acc) {
   return bce_loss_grad(static_cast<cudaStream_t>(stream), logit, target, B, A, dlogit, loss_acc);
 }

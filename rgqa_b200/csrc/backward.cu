@@ -211,3 +211,174 @@ int attention_bwd(cudaStream_t stream, const float* q, long long ldq, const floa
 }
 
 }  // namespace rgqa
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight-gradient (wgrad) kernels of the fp32 path — the parameter half of `loss.backward()` in GQA.train
+// (src/tasks/gqa_conf.py:196).  All of them ACCUMULATE into their outputs (shared modules — the cross-attention block
+// serves both directions — and tied uses simply call twice); the caller zeroes the gradient buffers once per step.
+//   gemm_f32_tn        dW[N, K] += dY[M, N]^T · X[M, K]                (nn.Linear weight)
+//   colsum             db[N]    += sum_m dY[m, n]                      (nn.Linear bias, LayerNorm beta is in ln_param_grad)
+//   ln_param_grad      dgamma[c] += sum_m dy[m,c]·xh[m,c],  dbeta[c] += sum_m dy[m,c]     (BertLayerNorm, xh recomputed)
+//   embedding_scatter  dE[idx[r], :] += g[r, :] unless idx[r] == padding_idx  (nn.Embedding; the reference builds all three
+//                      BertEmbeddings tables with padding_idx = 0, modeling.py:272-274, so word 0, POSITION 0 and token
+//                      type 0 never receive a gradient)
+// ------------------------------------------------------------------------------------------------------------------
+namespace rgqa {
+namespace {
+
+__global__ void __launch_bounds__(256)
+gemm_f32_tn_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ Bm, long long ldb, float* __restrict__ out,
+                   long long ldo, int M, int N, int K, int m_chunk) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lr = threadIdx.x >> 4, lc = (threadIdx.x & 15) * 4;   // loader: 16 rows (m) x 64 columns
+  const int m_lo = blockIdx.z * m_chunk, m_hi = min(M, m_lo + m_chunk);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int m0 = m_lo; m0 < m_hi; m0 += 16) {
+    const int m = m0 + lr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[lr][lc + i] = (m < m_hi && n0 + lc + i < N) ? A[static_cast<long long>(m) * lda + n0 + lc + i] : 0.f;
+      Bs[lr][lc + i] = (m < m_hi && k0 + lc + i < K) ? Bm[static_cast<long long>(m) * ldb + k0 + lc + i] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[s][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[s][tx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w};
+      const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + ty * 4 + i, k = k0 + tx * 4 + j;
+      if (n < N && k < K) atomicAdd(out + static_cast<long long>(n) * ldo + k, acc[i][j]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ X, long long ldx, float* __restrict__ out, int M, int N, int rows_per_block) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= N) return;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += X[static_cast<long long>(r) * ldx + c];
+  atomicAdd(out + c, s);
+}
+
+template <int NV>  // NV = H / 32 columns per lane
+__global__ void __launch_bounds__(256)
+ln_param_grad_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, int M, float eps, float scale) {
+  constexpr int H = NV * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float dg[NV], db[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) dg[j] = db[j] = 0.f;
+  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+    const float* xr = x + static_cast<long long>(row) * H;
+    const float* dr = dy + static_cast<long long>(row) * H;
+    float xv[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      xv[j] = xr[lane + 32 * j];
+      s += xv[j];
+    }
+    const float mu = warp_sum(s) / static_cast<float>(H);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float d = xv[j] - mu;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(H) + eps);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float g = dr[lane + 32 * j] * scale;
+      dg[j] = fmaf(g, (xv[j] - mu) * rstd, dg[j]);
+      db[j] += g;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    atomicAdd(dgamma + lane + 32 * j, dg[j]);
+    atomicAdd(dbeta + lane + 32 * j, db[j]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+embedding_scatter_kernel(const float* __restrict__ g, const int32_t* __restrict__ idx, float* __restrict__ table, int rows, int H,
+                         int table_rows, int padding_idx) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  const int t = idx[r];
+  if (t < 0 || t >= table_rows || t == padding_idx) return;  // nn.Embedding(padding_idx=...) rows get no gradient
+  for (int c = threadIdx.x; c < H; c += 256) atomicAdd(table + static_cast<long long>(t) * H + c, g[static_cast<long long>(r) * H + c]);
+}
+
+}  // namespace
+
+int gemm_f32_tn(cudaStream_t stream, const float* A, long long lda, const float* B, long long ldb, float* out, long long ldo, int M,
+                int N, int K) {
+  RGQA_CHECK(A && B && out && M > 0 && N > 0 && K > 0, "gemm_f32_tn: bad arguments");
+  // split the reduction over M so that small weight matrices still fill the GPU
+  const int tiles = ((N + 63) / 64) * ((K + 63) / 64);
+  int splits = tiles >= 296 ? 1 : (296 + tiles - 1) / tiles;
+  int m_chunk = ((M + splits - 1) / splits + 15) / 16 * 16;
+  if (m_chunk < 16) m_chunk = 16;
+  splits = (M + m_chunk - 1) / m_chunk;
+  gemm_f32_tn_kernel<<<dim3((K + 63) / 64, (N + 63) / 64, splits), 256, 0, stream>>>(A, lda, B, ldb, out, ldo, M, N, K, m_chunk);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int colsum(cudaStream_t stream, const float* X, long long ldx, float* out, int M, int N) {
+  RGQA_CHECK(X && out && M > 0 && N > 0, "colsum: bad arguments");
+  const int rows_per_block = 64;
+  colsum_kernel<<<dim3((N + 255) / 256, (M + rows_per_block - 1) / rows_per_block), 256, 0, stream>>>(X, ldx, out, M, N, rows_per_block);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int ln_param_grad(cudaStream_t stream, const float* dy, const float* x, float* dgamma, float* dbeta, int M, int H, float eps,
+                  float scale) {
+  RGQA_CHECK(dy && x && dgamma && dbeta && M > 0, "ln_param_grad: bad arguments");
+  int grid = (M + 7) / 8;
+  if (grid > 148 * 2) grid = 148 * 2;
+  if (H == 768)
+    ln_param_grad_kernel<24><<<grid, 256, 0, stream>>>(dy, x, dgamma, dbeta, M, eps, scale);
+  else if (H == 1536)
+    ln_param_grad_kernel<48><<<grid, 256, 0, stream>>>(dy, x, dgamma, dbeta, M, eps, scale);
+  else {
+    set_error("ln_param_grad: unsupported width %d (768 or 1536)", H);
+    return 1;
+  }
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int embedding_scatter(cudaStream_t stream, const float* g, const int32_t* idx, float* table, int rows, int H, int table_rows,
+                      int padding_idx) {
+  RGQA_CHECK(g && idx && table && rows > 0 && H > 0, "embedding_scatter: bad arguments");
+  embedding_scatter_kernel<<<rows, 256, 0, stream>>>(g, idx, table, rows, H, table_rows, padding_idx);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rgqa

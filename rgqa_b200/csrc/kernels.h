@@ -113,6 +113,14 @@ int tanh_bwd(cudaStream_t stream, const float* dy, const float* y, float* dx, lo
 int attention_bwd(cudaStream_t stream, const float* q, long long ldq, const float* k, long long ldk, const float* v,
                   long long ldv, const int32_t* key_mask, const float* dctx, long long ldo, float* dq, long long lddq, float* dk,
                   long long lddk, float* dv, long long lddv, int B, int Lq, int Lk, int heads);
+// weight-gradient kernels (backward.cu); all ACCUMULATE into their outputs
+int gemm_f32_tn(cudaStream_t stream, const float* A, long long lda, const float* B, long long ldb, float* out, long long ldo, int M,
+                int N, int K);
+int colsum(cudaStream_t stream, const float* X, long long ldx, float* out, int M, int N);
+int ln_param_grad(cudaStream_t stream, const float* dy, const float* x, float* dgamma, float* dbeta, int M, int H, float eps,
+                  float scale);
+int embedding_scatter(cudaStream_t stream, const float* g, const int32_t* idx, float* table, int rows, int H, int table_rows,
+                      int padding_idx);
 // RP-finetune groundwork (optim.cu): BCE-with-logits loss * A and its logit gradient, global gradient norm, BertAdam update
 int bce_loss_grad(cudaStream_t stream, const float* logit, const float* target, int B, int A, float* dlogit, double* loss_acc);
 int grad_sumsq(cudaStream_t stream, const float* g, long long n, double* acc);

@@ -1,0 +1,269 @@
+"""One RP-finetune optimisation step of the LXMERT GQA model on the GPU — ``GQA.train``'s loop body
+(``src/tasks/gqa_conf.py:148-198``): forward, ``BCEWithLogitsLoss × A``, ``backward()``, ``clip_grad_norm_(…, 5.)``,
+``BertAdam.step()`` — SURVEY §8 row a22 / config 5.  fp32 path (master weights, activations, gradients all fp32 on the CUDA
+cores); every operator is a kernel of this package behind the C ABI, PyTorch holds the tensors.
+
+* parameters, gradients and both Adam moments live in four FLAT fp32 buffers (the reference's single parameter group,
+  ``gqa_conf.py:123-127``): zeroing the gradients is one memset, the global norm one reduction, the optimiser ONE kernel
+  launch, and data parallelism ONE all-reduce of the flat gradient per step (mean over ranks, like DDP);
+* backward = the dgrad chain of ``input_grad.py`` extended down through the nine language layers and the embeddings, plus the
+  weight gradients (``rgqa_gemm_f32_tn``, ``rgqa_colsum``, ``rgqa_ln_param_grad``, ``rgqa_embedding_scatter``), accumulated
+  straight into the flat gradient buffer under the reference's parameter names;
+* **dropout is not implemented** (the reference trains with p = 0.1, ``modeling.py`` BertConfig): this is the "dropout off"
+  configuration SURVEY §8(d) config 5 asks parity for.  The golden trajectory it is tested against comes from the UNMODIFIED
+  reference modules + the reference's own BertAdam with both dropout probabilities set to 0.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .. import _lib as L
+from .. import ops
+from .optimization import SCHEDULES
+
+P = "lxrt_encoder.model.bert."
+
+
+class _Att:
+    def __init__(self, prefix, self_name):
+        s = prefix + "." + self_name
+        self.q, self.k, self.v = s + ".query", s + ".key", s + ".value"
+        self.out, self.ln = prefix + ".output.dense", prefix + ".output.LayerNorm"
+
+
+class _Ffn:
+    def __init__(self, inter, outp):
+        self.inter, self.out, self.ln = inter + ".dense", outp + ".dense", outp + ".LayerNorm"
+
+
+class LXMERTTrainer:
+    def __init__(self, state_dict, l_layers=9, x_layers=5, r_layers=5, heads=12, eps=1e-12, device="cuda:0", lr=5e-5, warmup=0.1,
+                 t_total=-1, schedule="warmup_linear", b1=0.9, b2=0.999, e=1e-6, weight_decay=0.01, clip_norm=5.0):
+        dev = torch.device(device)
+        self.dev, self.heads, self.eps, self.clip_norm = dev, heads, eps, clip_norm
+        self.hp = dict(lr=lr, warmup=warmup, t_total=t_total, schedule=schedule, b1=b1, b2=b2, e=e, weight_decay=weight_decay)
+        self.step_count = 0
+        names = list(state_dict.keys())
+        sizes = [state_dict[n].numel() for n in names]
+        total = sum(sizes)
+        self.flat_p = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.p, self.g = {}, {}
+        off = 0
+        for n, sz in zip(names, sizes):
+            self.p[n] = self.flat_p[off:off + sz].view(state_dict[n].shape)
+            self.g[n] = self.flat_g[off:off + sz].view(state_dict[n].shape)
+            self.p[n].copy_(state_dict[n].detach().to(dev, torch.float32))
+            off += sz
+        enc = P + "encoder."
+        self.l = [(_Att(f"{enc}layer.{i}.attention", "self"), _Ffn(f"{enc}layer.{i}.intermediate", f"{enc}layer.{i}.output")) for i in range(l_layers)]
+        self.r = [(_Att(f"{enc}r_layers.{i}.attention", "self"), _Ffn(f"{enc}r_layers.{i}.intermediate", f"{enc}r_layers.{i}.output"))
+                  for i in range(r_layers)]
+        self.x = [dict(cross=_Att(f"{enc}x_layers.{i}.visual_attention", "att"), ls=_Att(f"{enc}x_layers.{i}.lang_self_att", "self"),
+                       vs=_Att(f"{enc}x_layers.{i}.visn_self_att", "self"),
+                       lf=_Ffn(f"{enc}x_layers.{i}.lang_inter", f"{enc}x_layers.{i}.lang_output"),
+                       vf=_Ffn(f"{enc}x_layers.{i}.visn_inter", f"{enc}x_layers.{i}.visn_output")) for i in range(x_layers)]
+        self._derived = {}
+        self.tape = None
+
+    # ---- parameter access: stacked Q|K|V and transposed copies are rebuilt lazily after every optimiser step ----
+    def _w(self, name):
+        return self.p[name + ".weight"], self.p[name + ".bias"]
+
+    def _wt(self, name):
+        key = ("t", name)
+        if key not in self._derived:
+            self._derived[key] = self.p[name + ".weight"].t().contiguous()
+        return self._derived[key]
+
+    def _qkv(self, a):
+        key = ("qkv", a.q)
+        if key not in self._derived:
+            w = torch.cat([self.p[a.q + ".weight"], self.p[a.k + ".weight"], self.p[a.v + ".weight"]], 0)
+            b = torch.cat([self.p[a.q + ".bias"], self.p[a.k + ".bias"], self.p[a.v + ".bias"]], 0)
+            self._derived[key] = (w, b, w.t().contiguous())
+        return self._derived[key]
+
+    # ---- forward blocks ----
+    def _att_fwd(self, a, x_q, x_kv, B, Lq, Lk, mask, qkv_q=None, qkv_kv=None):
+        w, b, _ = self._qkv(a)
+        qkv_q = ops.linear_f32(x_q, w, b) if qkv_q is None else qkv_q
+        if qkv_kv is None:
+            qkv_kv = qkv_q if x_kv is x_q else ops.linear_f32(x_kv, w, b)
+        ctx = ops.attention(qkv_q, qkv_kv, B, Lq, Lk, key_mask=mask, heads=self.heads)
+        wo, bo = self._w(a.out)
+        pre = ops.linear_f32(ctx, wo, bo, epilogue=L.EPI_RESID, residual=x_q)
+        y = ops.layernorm(pre, *self._w(a.ln), self.eps)
+        return y, dict(x_q=x_q, qkv_q=qkv_q, qkv_kv=qkv_kv, ctx=ctx, pre=pre, B=B, Lq=Lq, Lk=Lk, mask=mask)
+
+    def _ffn_fwd(self, f, x):
+        pg = ops.linear_f32(x, *self._w(f.inter))
+        inter = ops.gelu_fwd(pg)
+        wo, bo = self._w(f.out)
+        pre = ops.linear_f32(inter, wo, bo, epilogue=L.EPI_RESID, residual=x)
+        return ops.layernorm(pre, *self._w(f.ln), self.eps), dict(x=x, pg=pg, inter=inter, pre=pre)
+
+    def forward(self, feat, pos, ids, seg, mask):
+        dev = self.dev
+        B, V, Lt = feat.shape[0], feat.shape[1], ids.shape[1]
+        ids32, mask32 = ids.to(dev, torch.int32).contiguous(), mask.to(dev, torch.int32).contiguous()
+        seg32 = torch.zeros_like(ids32) if seg is None else seg.to(dev, torch.int32).contiguous()
+        feat2 = feat.to(dev, torch.float32).reshape(B * V, -1).contiguous()
+        pos2 = pos.to(dev, torch.float32).reshape(B * V, -1).contiguous()
+        e = P + "embeddings."
+        word, posemb, typeemb = self.p[e + "word_embeddings.weight"], self.p[e + "position_embeddings.weight"], self.p[e + "token_type_embeddings.weight"]
+        t = dict(B=B, V=V, L=Lt, ids=ids32.view(-1), seg=seg32.view(-1), feat2=feat2, pos2=pos2)
+        # BertEmbeddings (:278-292); the pre-LayerNorm sum is re-formed with tensor indexing for the LayerNorm backward
+        t["e_pre"] = (word[ids32.long()] + posemb[:Lt][None, :, :] + typeemb[seg32.long()]).view(B * Lt, -1).contiguous()
+        lang = ops.embed_ln(ids32, seg32, word, posemb, typeemb, *self._w(e + "LayerNorm"), self.eps)
+        v = P + "encoder.visn_fc."
+        t["pre_v"] = ops.linear_f32(feat2, *self._w(v + "visn_fc"))
+        t["pre_b"] = ops.linear_f32(pos2, *self._w(v + "box_fc"))
+        visn = ops.visn_combine(t["pre_v"], pos2, *self._w(v + "box_fc"), *self._w(v + "visn_layer_norm"), *self._w(v + "box_layer_norm"), self.eps)
+        t["l"], t["r"], t["x"] = [], [], []
+        for a, f in self.l:
+            lang, ta = self._att_fwd(a, lang, lang, B, Lt, Lt, mask32)
+            lang, tf = self._ffn_fwd(f, lang)
+            t["l"].append((ta, tf))
+        for a, f in self.r:
+            visn, ta = self._att_fwd(a, visn, visn, B, V, V, None)
+            visn, tf = self._ffn_fwd(f, visn)
+            t["r"].append((ta, tf))
+        for w in self.x:
+            c = w["cross"]
+            wq, bq, _ = self._qkv(c)
+            qkv_l, qkv_v = ops.linear_f32(lang, wq, bq), ops.linear_f32(visn, wq, bq)
+            l1, tcl = self._att_fwd(c, lang, visn, B, Lt, V, None, qkv_q=qkv_l, qkv_kv=qkv_v)
+            v1, tcv = self._att_fwd(c, visn, lang, B, V, Lt, mask32, qkv_q=qkv_v, qkv_kv=qkv_l)
+            l2, tls = self._att_fwd(w["ls"], l1, l1, B, Lt, Lt, mask32)
+            v2, tvs = self._att_fwd(w["vs"], v1, v1, B, V, V, None)
+            lang, tlf = self._ffn_fwd(w["lf"], l2)
+            visn, tvf = self._ffn_fwd(w["vf"], v2)
+            t["x"].append(dict(cl=tcl, cv=tcv, ls=tls, vs=tvs, lf=tlf, vf=tvf))
+        t["first"] = lang.view(B, Lt, -1)[:, 0, :].contiguous()
+        t["pooled"] = ops.linear_f32(t["first"], *self._w(P + "pooler.dense"), epilogue=L.EPI_TANH)
+        t["h0"] = ops.linear_f32(t["pooled"], *self._w("logit_fc.0"))
+        t["g"] = ops.gelu_fwd(t["h0"])
+        t["n"] = ops.layernorm(t["g"], *self._w("logit_fc.2"), self.eps)
+        logits = ops.linear_f32(t["n"], *self._w("logit_fc.3"))
+        self.tape = t
+        return logits, t["pooled"]
+
+    # ---- backward blocks (input gradient returned, parameter gradients accumulated into self.g) ----
+    def _lin_wgrad(self, name, dy, x):
+        ops.linear_wgrad_(self.g[name + ".weight"], self.g[name + ".bias"], dy, x)
+
+    def _ln_bwd(self, name, dy, x, scale=1.0):
+        ops.layernorm_param_grad_(self.g[name + ".weight"], self.g[name + ".bias"], dy, x, self.eps, scale)
+        return ops.layernorm_bwd(dy, x, self.p[name + ".weight"], eps=self.eps, scale=scale)
+
+    def _ffn_bwd(self, f, tp, dy):
+        d_pre = self._ln_bwd(f.ln, dy, tp["pre"])
+        self._lin_wgrad(f.out, d_pre, tp["inter"])
+        d_pg = ops.gelu_bwd(ops.linear_f32(d_pre, self._wt(f.out)), tp["pg"])
+        self._lin_wgrad(f.inter, d_pg, tp["x"])
+        return ops.linear_f32(d_pg, self._wt(f.inter), epilogue=L.EPI_RESID, residual=d_pre)
+
+    def _att_bwd(self, a, tp, dy, dqkv_q, dqkv_kv):
+        d_pre = self._ln_bwd(a.ln, dy, tp["pre"])
+        self._lin_wgrad(a.out, d_pre, tp["ctx"])
+        d_ctx = ops.linear_f32(d_pre, self._wt(a.out))
+        ops.attention_bwd(tp["qkv_q"], tp["qkv_kv"], d_ctx, dqkv_q, dqkv_kv, tp["B"], tp["Lq"], tp["Lk"], key_mask=tp["mask"], heads=self.heads)
+        return d_pre
+
+    def _qkv_wgrad(self, a, dqkv, x):
+        H = dqkv.shape[1] // 3
+        for j, name in enumerate((a.q, a.k, a.v)):
+            ops.linear_wgrad_(self.g[name + ".weight"], self.g[name + ".bias"], dqkv[:, j * H:(j + 1) * H], x)
+
+    def _self_att_bwd(self, a, tp, dy):
+        dqkv = torch.empty_like(tp["qkv_q"])
+        d_pre = self._att_bwd(a, tp, dy, dqkv, dqkv)
+        self._qkv_wgrad(a, dqkv, tp["x_q"])
+        return ops.linear_f32(dqkv, self._qkv(a)[2], epilogue=L.EPI_RESID, residual=d_pre)
+
+    def backward(self, dlogits):
+        t = self.tape
+        B, V, Lt = t["B"], t["V"], t["L"]
+        H = t["pooled"].shape[1]
+        dlogits = dlogits.to(self.dev, torch.float32).contiguous()
+        self._lin_wgrad("logit_fc.3", dlogits, t["n"])
+        dn = ops.linear_f32(dlogits, self._wt("logit_fc.3"))
+        dg = self._ln_bwd("logit_fc.2", dn, t["g"])
+        dh0 = ops.gelu_bwd(dg, t["h0"])
+        self._lin_wgrad("logit_fc.0", dh0, t["pooled"])
+        d_pp = ops.tanh_bwd(ops.linear_f32(dh0, self._wt("logit_fc.0")), t["pooled"])
+        self._lin_wgrad(P + "pooler.dense", d_pp, t["first"])
+        dl = torch.zeros((B, Lt, H), dtype=torch.float32, device=self.dev)
+        dl[:, 0, :] = ops.linear_f32(d_pp, self._wt(P + "pooler.dense"))
+        dl = dl.view(B * Lt, H)
+        dv = torch.zeros((B * V, H), dtype=torch.float32, device=self.dev)
+        for w, tp in zip(reversed(self.x), reversed(t["x"])):
+            dl2, dv2 = self._ffn_bwd(w["lf"], tp["lf"], dl), self._ffn_bwd(w["vf"], tp["vf"], dv)
+            dl1, dv1 = self._self_att_bwd(w["ls"], tp["ls"], dl2), self._self_att_bwd(w["vs"], tp["vs"], dv2)
+            c = w["cross"]
+            dqkv_l, dqkv_v = torch.empty_like(tp["cl"]["qkv_q"]), torch.empty_like(tp["cv"]["qkv_q"])
+            d_pre_l = self._att_bwd(c, tp["cl"], dl1, dqkv_l, dqkv_v)
+            d_pre_v = self._att_bwd(c, tp["cv"], dv1, dqkv_v, dqkv_l)
+            self._qkv_wgrad(c, dqkv_l, tp["cl"]["x_q"])                 # ONE module, both modalities: gradients add up
+            self._qkv_wgrad(c, dqkv_v, tp["cv"]["x_q"])
+            wt = self._qkv(c)[2]
+            dl = ops.linear_f32(dqkv_l, wt, epilogue=L.EPI_RESID, residual=d_pre_l)
+            dv = ops.linear_f32(dqkv_v, wt, epilogue=L.EPI_RESID, residual=d_pre_v)
+        for (a, f), (ta, tf) in zip(reversed(self.r), reversed(t["r"])):
+            dv = self._self_att_bwd(a, ta, self._ffn_bwd(f, tf, dv))
+        for (a, f), (ta, tf) in zip(reversed(self.l), reversed(t["l"])):
+            dl = self._self_att_bwd(a, ta, self._ffn_bwd(f, tf, dl))
+        v = P + "encoder.visn_fc."
+        d_pre_v = self._ln_bwd(v + "visn_layer_norm", dv, t["pre_v"], scale=0.5)
+        d_pre_b = self._ln_bwd(v + "box_layer_norm", dv, t["pre_b"], scale=0.5)
+        self._lin_wgrad(v + "visn_fc", d_pre_v, t["feat2"])
+        self._lin_wgrad(v + "box_fc", d_pre_b, t["pos2"])
+        e = P + "embeddings."
+        d_e = self._ln_bwd(e + "LayerNorm", dl, t["e_pre"])
+        # all three tables are nn.Embedding(..., padding_idx=0) in the reference (modeling.py:272-274): word 0, position 0
+        # and token type 0 get no gradient
+        ops.embedding_scatter_(self.g[e + "word_embeddings.weight"], t["ids"], d_e, padding_idx=0)
+        ops.embedding_scatter_(self.g[e + "token_type_embeddings.weight"], t["seg"], d_e, padding_idx=0)
+        pos_ids = torch.arange(Lt, dtype=torch.int32, device=self.dev).repeat(B)
+        ops.embedding_scatter_(self.g[e + "position_embeddings.weight"], pos_ids, d_e, padding_idx=0)
+
+    # ---- one optimisation step (gqa_conf.py:148-198 without the data-side lines) ----
+    def lr_now(self):
+        hp = self.hp
+        if hp["t_total"] != -1:
+            return hp["lr"] * SCHEDULES[hp["schedule"]](self.step_count / hp["t_total"], hp["warmup"])
+        return hp["lr"]
+
+    def train_step(self, feat, pos, ids, seg, mask, target):
+        """Returns (loss, gradient norm before clipping) as Python floats."""
+        lib = L.load()
+        self.flat_g.zero_()
+        logits, _ = self.forward(feat, pos, ids, seg, mask)
+        target = target.to(self.dev, torch.float32).contiguous()
+        B, A = logits.shape
+        dlogits = torch.empty_like(logits)
+        loss = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        L.check(lib.rgqa_bce_loss_grad(L.current_stream_ptr(), L.ptr(logits), L.ptr(target), B, A, L.ptr(dlogits), L.ptr(loss)),
+                "rgqa_bce_loss_grad")
+        self.backward(dlogits)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            buf = self.flat_g if dist.get_backend() == "nccl" else self.flat_g.cpu()
+            dist.all_reduce(buf)                                        # ONE collective per step
+            self.flat_g.copy_(buf.to(self.dev) / dist.get_world_size())
+        sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        stream = L.current_stream_ptr()
+        L.check(lib.rgqa_grad_sumsq(stream, L.ptr(self.flat_g), self.flat_g.numel(), L.ptr(sumsq)), "rgqa_grad_sumsq")
+        hp = self.hp
+        L.check(lib.rgqa_bertadam_step(stream, L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.flat_m), L.ptr(self.flat_v),
+                                       self.flat_p.numel(), float(self.lr_now()), hp["b1"], hp["b2"], hp["e"], hp["weight_decay"],
+                                       L.ptr(sumsq), float(self.clip_norm)), "rgqa_bertadam_step")
+        self.step_count += 1
+        self._derived.clear()                                           # stacked / transposed copies are stale now
+        return float(loss), float(sumsq.sqrt())
+
+    def state_dict(self):
+        return {n: t.detach().clone() for n, t in self.p.items()}

@@ -314,3 +314,37 @@ def attention_bwd(qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv, B, Lq, Lk, key_mask=None
                                         qkv_kv.data_ptr() + 2 * H * 4, 3 * H, L.ptr(key_mask), L.ptr(dctx), H,
                                         L.ptr(dqkv_q), 3 * H, dqkv_kv.data_ptr() + H * 4, 3 * H,
                                         dqkv_kv.data_ptr() + 2 * H * 4, 3 * H, B, Lq, Lk, heads), "rgqa_attention_bwd")
+
+
+# ---- weight-gradient kernels (accumulating) --------------------------------------------------------------------------
+def linear_wgrad_(dw, db, dy, x):
+    """dw [N, K] += dy^T · x and db [N] += column sums of dy  (nn.Linear; dy [M, N], x [M, K], all f32, in place)."""
+    _need_cuda(dw, db, dy, x)
+    assert dy.dtype == x.dtype == dw.dtype == torch.float32 and dy.stride(1) == 1 and x.stride(1) == 1 and dw.is_contiguous()
+    M, N = dy.shape
+    K = x.shape[1]
+    assert x.shape[0] == M and dw.shape == (N, K)
+    lib = L.load()
+    L.check(lib.rgqa_gemm_f32_tn(L.current_stream_ptr(), L.ptr(dy), dy.stride(0), L.ptr(x), x.stride(0), L.ptr(dw), K, M, N, K),
+            "rgqa_gemm_f32_tn")
+    if db is not None:
+        assert db.shape == (N,) and db.is_contiguous()
+        L.check(lib.rgqa_colsum(L.current_stream_ptr(), L.ptr(dy), dy.stride(0), L.ptr(db), M, N), "rgqa_colsum")
+
+
+def layernorm_param_grad_(dgamma, dbeta, dy, x, eps=1e-12, scale=1.0):
+    """dgamma += sum_m scale·dy·xh, dbeta += sum_m scale·dy for BertLayerNorm with input x [M, H] (in place)."""
+    _need_cuda(dgamma, dbeta, dy, x)
+    assert dy.is_contiguous() and x.is_contiguous() and dy.shape == x.shape and dy.dtype == x.dtype == torch.float32
+    M, H = x.shape
+    L.check(L.load().rgqa_ln_param_grad(L.current_stream_ptr(), L.ptr(dy), L.ptr(x), L.ptr(dgamma), L.ptr(dbeta), M, H, eps, scale),
+            "rgqa_ln_param_grad")
+
+
+def embedding_scatter_(table_grad, idx, g, padding_idx=-1):
+    """table_grad[idx[r], :] += g[r, :] unless idx[r] == padding_idx (nn.Embedding backward; idx int32 [rows], g [rows, H])."""
+    _need_cuda(table_grad, idx, g)
+    assert idx.dtype == torch.int32 and idx.is_contiguous() and g.is_contiguous() and table_grad.is_contiguous()
+    rows, H = g.shape
+    L.check(L.load().rgqa_embedding_scatter(L.current_stream_ptr(), L.ptr(g), L.ptr(idx), L.ptr(table_grad), rows, H,
+                                            table_grad.shape[0], padding_idx), "rgqa_embedding_scatter")

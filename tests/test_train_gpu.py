@@ -1,0 +1,88 @@
+"""SURVEY §8 row a22 / config 5 on the GPU: the weight-gradient kernels against torch, and three optimisation steps of the
+trainer against the UNMODIFIED reference modules + reference BertAdam (tests/golden/train_steps.npz, dropout off)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from rgqa_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_wgrad_kernels_match_torch(cuda_device):
+    from rgqa_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for M, N, K in ((640, 768, 768), (1152, 2304, 768), (6, 1842, 1536), (216, 768, 4), (77, 130, 96)):
+        dy, x = torch.randn(M, N, generator=g), torch.randn(M, K, generator=g)
+        dw0, db0 = torch.randn(N, K, generator=g), torch.randn(N, generator=g)          # kernels accumulate
+        dw, db = dw0.clone().to(cuda_device), db0.clone().to(cuda_device)
+        ops.linear_wgrad_(dw, db, dy.to(cuda_device), x.to(cuda_device))
+        ref_w = dw0.double() + dy.double().t() @ x.double()
+        ref_b = db0.double() + dy.double().sum(0)
+        assert (dw.cpu().double() - ref_w).abs().max() <= 1e-4 * max(1.0, float(ref_w.abs().max()))
+        assert (db.cpu().double() - ref_b).abs().max() <= 1e-4 * max(1.0, float(ref_b.abs().max()))
+    # a strided dy (one third of a fused Q|K|V gradient)
+    dqkv, x = torch.randn(300, 2304, generator=g).to(cuda_device), torch.randn(300, 768, generator=g).to(cuda_device)
+    dw, db = torch.zeros(768, 768, device=cuda_device), torch.zeros(768, device=cuda_device)
+    ops.linear_wgrad_(dw, db, dqkv[:, 768:1536], x)
+    torch.testing.assert_close(dw, dqkv[:, 768:1536].t() @ x, rtol=1e-4, atol=1e-3)
+    for H in (768, 1536):
+        xx = torch.randn(333, H, generator=g, requires_grad=True)
+        gamma, beta = torch.randn(H, generator=g, requires_grad=True), torch.randn(H, generator=g, requires_grad=True)
+        dy = torch.randn(333, H, generator=g)
+        y = torch.nn.functional.layer_norm(xx, (H,), gamma, beta, eps=1e-12)
+        (y * dy).sum().backward()
+        dg, dbt = torch.zeros(H, device=cuda_device), torch.zeros(H, device=cuda_device)
+        ops.layernorm_param_grad_(dg, dbt, dy.to(cuda_device), xx.detach().to(cuda_device))
+        torch.testing.assert_close(dg.cpu(), gamma.grad, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(dbt.cpu(), beta.grad, rtol=1e-4, atol=1e-4)
+        dx = ops.layernorm_bwd(dy.to(cuda_device), xx.detach().to(cuda_device), gamma.detach().to(cuda_device))
+        torch.testing.assert_close(dx.cpu(), xx.grad, rtol=1e-4, atol=1e-5)
+    table = torch.zeros(50, 768, device=cuda_device)
+    idx = torch.randint(0, 50, (400,), generator=g).to(torch.int32)
+    gg = torch.randn(400, 768, generator=g)
+    ops.embedding_scatter_(table, idx.to(cuda_device), gg.to(cuda_device))
+    ref = torch.zeros(50, 768).index_add_(0, idx.long(), gg)
+    torch.testing.assert_close(table.cpu(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_three_training_steps_match_reference_trajectory(cuda_device):
+    """gqa_conf.py:148-198 with dropout off: loss and pre-clip gradient norm of each step, first-step gradients and the
+    parameters after step 3 of twelve watched tensors, against the reference modules + reference BertAdam."""
+    from rgqa_b200.lxrt.trainer import LXMERTTrainer
+    z = np.load(os.path.join(GOLD, "train_steps.npz"))
+    layers = dict(l_layers=2, x_layers=1, r_layers=1)
+    sd = syn.lxmert_state_dict(variant="rich", **layers)
+    tr = LXMERTTrainer(sd, device=cuda_device, lr=1e-4, warmup=0.1, t_total=20, **layers)
+    watch = sorted(k[len("final:"):] for k in z.files if k.startswith("final:"))
+    assert len(watch) == 12
+
+    def cut(t):
+        return t[:4] if t.numel() > 20000 else t
+
+    for step in range(3):
+        inp = syn.make_inputs(6, 20, seed=900 + step)
+        loss, norm = tr.train_step(inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"], torch.from_numpy(z[f"target{step}"]))
+        assert loss == pytest.approx(float(z[f"loss{step}"]), rel=2e-5), (step, loss)
+        assert norm == pytest.approx(float(z[f"norm{step}"]), rel=2e-4), (step, norm)
+        if step == 0:
+            for n in watch:
+                ref = torch.from_numpy(z["grad0:" + n])
+                got = cut(tr.g[n]).cpu()
+                if float(ref.norm()) == 0.0:      # token types are all 0 = padding_idx: the reference leaves that table's gradient at zero
+                    assert float(got.norm()) == 0.0, n
+                    continue
+                assert float((got - ref).norm() / ref.norm()) <= 5e-4, (n, float((got - ref).norm() / ref.norm()))
+            rows = tr.g["lxrt_encoder.model.bert.embeddings.word_embeddings.weight"][[101, 102, 0]].cpu()
+            ref = torch.from_numpy(z["grad0_word_rows"])
+            assert float((rows - ref).norm() / ref.norm()) <= 5e-4
+    for n in watch:
+        ref = torch.from_numpy(z["final:" + n])
+        got = cut(tr.p[n]).cpu()
+        start = cut(sd[n])
+        moved = float((ref - start).norm())
+        assert moved > 0
+        assert float((got - ref).norm()) <= 2e-3 * moved + 1e-7, (n, float((got - ref).norm()), moved)   # the UPDATE agrees to 0.2 %
