@@ -287,7 +287,7 @@ def run_ours(a):
     peak_tf, peak_gbs, peak_src = peaks()
     gemm_tf = (fl_sum[0] / (ms_sum[0] * 1e-3)) / 1e12 if ms_sum[0] > 0 else 0.0
     gq = GFLOP_PER_Q.get(Lq, GFLOP_PER_Q[20]) + MAHA_GFLOP_PER_Q
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all encoder/head GEMM launches)",
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_pair_kernel / gemm_bf16_tcgen05_kernel (all encoder/head tcgen05 GEMM launches)",
                 "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf, "traffic": measured_gemm_traffic() if (B == 1024 and Lq == 20) else None,
                 "traffic_unit": "bytes of DRAM traffic per GEMM launch (ncu, profiles/r01_launch_summary.json)",
                 "algorithmic_flops_per_launch": fl_sum[0] / max(cnt[0], 1),
