@@ -40,6 +40,15 @@ def get_parser():
     p.add_argument("--tau", type=float, default=0.5)
     p.add_argument("--noise", type=float, default=0.0)
     p.add_argument("--temperature", type=float, default=1.0)
+    # flows beyond the per-batch body: ensemble (param.py:60), RP finetune (:67, :88-91), loss variant (:114)
+    p.add_argument("--ensemble_method", default="mean", type=str)
+    p.add_argument("--sample_pair", action="store_const", default=False, const=True)
+    p.add_argument("--optim", default="bert")
+    p.add_argument("--lr", type=float, default=1e-4)
+    p.add_argument("--epochs", type=int, default=10)
+    p.add_argument("--dropout", type=float, default=0.1)
+    p.add_argument("--mceLoss", dest="mce_loss", action="store_const", default=False, const=True)
+    p.add_argument("--tqdm", action="store_const", default=False, const=True)
     # runtime (param.py:133-134)
     p.add_argument("--multiGPU", action="store_const", default=False, const=True)
     p.add_argument("--numWorkers", dest="num_workers", default=0, type=int)
@@ -48,7 +57,7 @@ def get_parser():
     p.add_argument("--maxSeqLength", dest="max_seq_length", type=int, default=None)
     p.add_argument("--vocab", type=str, default=os.environ.get("RGQA_BERT_VOCAB", None),
                    help="vocab.txt (or directory); without it a deterministic SyntheticTokenizer is used")
-    p.add_argument("--method", default="msp", choices=["msp", "energy", "energy_sum", "lse", "maha"])
+    p.add_argument("--method", default="msp", choices=["msp", "energy", "energy_sum", "lse", "maha", "odin", "ensemble"])
     return p
 
 
