@@ -93,3 +93,8 @@ def test_param_flags_follow_reference_names(monkeypatch):
     a = param.parse_args(["--test", "ClipEasy", "--load", "snap/x", "--batchSize", "32", "--llayers", "9", "--xlayers", "5",
                           "--rlayers", "5", "--tau", "0.3", "--noise", "0", "--mixup", "--unknownFlag", "1"])
     assert (a.test, a.load, a.batch_size, a.llayers, a.tau, a.precision) == ("ClipEasy", "snap/x", 32, 9, 0.3, "bf16")
+    # the flags of the ensemble / ODIN / RP-finetune scripts (param.py:51-53, :60, :67, :88-91)
+    b = param.parse_args(["--test", "GQAUQ_testdev", "--load", "snap/a,snap/b", "--ensemble_method", "multiply", "--sample_pair",
+                          "--lr", "5e-5", "--epochs", "4", "--noise", "1e-4", "--temperature", "2", "--mixup_alpha", "0.3"])
+    assert (b.ensemble_method, b.sample_pair, b.lr, b.epochs, b.noise, b.temperature) == ("multiply", True, 5e-5, 4, 1e-4, 2.0)
+    assert b.load.split(",") == ["snap/a", "snap/b"] and b.optim == "bert" and b.dropout == 0.1 and not b.mce_loss
