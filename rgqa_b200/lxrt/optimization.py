@@ -14,21 +14,24 @@ import torch
 from .. import _lib as L
 
 
+def _ramp(x, warmup):
+    """Linear ramp 0 -> 1 over the first `warmup` fraction of training (shared by the three schedules)."""
+    return x / warmup
+
+
 def warmup_cosine(x, warmup=0.002):
-    s = 1 if x <= warmup else 0
-    return s * (x / warmup) + (1 - s) * (0.5 * (1 + math.cos(math.pi * x)))   # optimization.py:24-26 (torch.cos there)
+    """optimization.py:24-28: ramp, then half a cosine period down to 0 at x = 1."""
+    return _ramp(x, warmup) if x <= warmup else 0.5 * (1.0 + math.cos(math.pi * x))
 
 
 def warmup_constant(x, warmup=0.002):
-    if x < warmup:
-        return x / warmup
-    return 1.0
+    """optimization.py:30-35: ramp, then 1."""
+    return _ramp(x, warmup) if x < warmup else 1.0
 
 
 def warmup_linear(x, warmup=0.002):
-    if x < warmup:
-        return x / warmup
-    return max((x - 1.) / (warmup - 1.), 0)
+    """optimization.py:37-42: ramp, then a straight line that reaches 0 at x = 1 (and stays there)."""
+    return _ramp(x, warmup) if x < warmup else max((x - 1.0) / (warmup - 1.0), 0)
 
 
 SCHEDULES = {"warmup_cosine": warmup_cosine, "warmup_constant": warmup_constant, "warmup_linear": warmup_linear}
@@ -42,18 +45,11 @@ class BertAdam:
 
     def __init__(self, params, lr, warmup=-1, t_total=-1, schedule="warmup_linear", b1=0.9, b2=0.999, e=1e-6,
                  weight_decay=0.01, max_grad_norm=1.0):
-        if lr < 0.0:
-            raise ValueError("Invalid learning rate: {} - should be >= 0.0".format(lr))
-        if schedule not in SCHEDULES:
-            raise ValueError("Invalid schedule parameter: {}".format(schedule))
-        if not 0.0 <= warmup < 1.0 and not warmup == -1:
-            raise ValueError("Invalid warmup: {} - should be in [0.0, 1.0[ or -1".format(warmup))
-        if not 0.0 <= b1 < 1.0:
-            raise ValueError("Invalid b1 parameter: {} - should be in [0.0, 1.0[".format(b1))
-        if not 0.0 <= b2 < 1.0:
-            raise ValueError("Invalid b2 parameter: {} - should be in [0.0, 1.0[".format(b2))
-        if not e >= 0.0:
-            raise ValueError("Invalid epsilon value: {} - should be >= 0.0".format(e))
+        checks = (("lr", lr >= 0.0), ("schedule", schedule in SCHEDULES), ("warmup", warmup == -1 or 0.0 <= warmup < 1.0),
+                  ("b1", 0.0 <= b1 < 1.0), ("b2", 0.0 <= b2 < 1.0), ("e", e >= 0.0))
+        for name, ok in checks:           # same admissible ranges as the reference constructor (optimization.py:66-79)
+            if not ok:
+                raise ValueError(f"BertAdam: argument {name} out of range")
         self.params = list(params)
         for p in self.params:
             if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
