@@ -667,11 +667,11 @@ int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, cons
     const __nv_bfloat16* vb = static_cast<const __nv_bfloat16*>(v);
     __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
     int rc = 0;
-    // large batches: TMA-fed persistent kernel (needs a few units per compute warp, room for two slots per warp, and
+    // large batches: TMA-fed persistent kernel (needs >= 2 units per compute warp, room for two slots per warp, and
     // 16-byte aligned operands)
     const int depth = attention_tma_depth(Lq, Lk);
     const bool tma_ok = option_get(OPT_ATTN_TMA) != 0 && depth >= 2 &&
-                        static_cast<long long>(B) * heads >= 8LL * num_sms() * kAttnWarps &&
+                        static_cast<long long>(B) * heads >= 2LL * num_sms() * kAttnWarps &&
                         (reinterpret_cast<uintptr_t>(q) % 16 == 0) && (reinterpret_cast<uintptr_t>(k) % 16 == 0) &&
                         (reinterpret_cast<uintptr_t>(v) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
                         ldk == ldv && vb > kb && ((vb - kb) * 2) % 16 == 0 && (vb - kb) <= ldk - heads * HD;

@@ -216,7 +216,7 @@ def test_attention_matches_torch(cuda_device, dtype, B, Lq, Lk, masked):
 @pytest.mark.parametrize("B,Lq,Lk,masked", [(800, 20, 20, True), (800, 36, 36, False), (800, 20, 36, False), (800, 36, 20, True),
                                             (801, 30, 30, True), (800, 56, 64, True), (800, 7, 9, True)])
 def test_attention_large_batch_tma_path_matches_torch_and_per_warp_kernel(cuda_device, B, Lq, Lk, masked):
-    """B * 12 heads >= 8 units per compute warp per SM: the TMA-fed persistent kernel (option attn_tma) takes over.
+    """B * 12 heads >= 2 units per compute warp per SM: the TMA-fed persistent kernel (option attn_tma) takes over.
     Checked against torch and bit-for-bit against the per-warp kernel (same mma.sync math on the same operands)."""
     from rgqa_b200 import ops, _lib as L
     lib = L.load()
