@@ -123,7 +123,7 @@ int rgqa_score(rgqa_handle* h, void* stream, int mode, const float* logits, cons
  * M >= 1024), "gemm_staged" (1 = swizzled-smem + TMA-store epilogue in the pair kernel), "gemm_ln" (1 = fused
  * GEMM + residual + LayerNorm kernel), "two_streams" (1 = visual branch on a second stream), "graphs" (1 = CUDA-graph replay of the forward for
  * B <= 128), "defer_ln" (1 = LXMERT bf16 batches of >= 1024 token rows run without LayerNorm kernels: hidden states stay
- * pre-LayerNorm as bf16 hi/lo pairs + row statistics, see rgqa_gemm_bf16_resid_hl), "attn_tma" (1 = TMA-fed persistent attention kernel for large batches), "pdl", "gemm_debug". */
+ * pre-LayerNorm as bf16 hi/lo pairs + row statistics, see rgqa_gemm_bf16_resid_hl), "attn_tma" (1 = TMA-fed persistent attention kernel for large batches), "qkv_planes" (1 = Q|K|V projections written head-major for that kernel), "pdl", "gemm_debug". */
 int rgqa_set_option(const char* name, int value);
 /* Kernels enqueued by this library since it was loaded. */
 long long rgqa_launch_count(void);

@@ -798,6 +798,24 @@ struct DState {
 struct DefCtx {
   rgqa_handle* h;
   int H;
+  bool planes = false;  // Q|K|V projections are written head-major (gemm_bf16_qkv_planes) and read by attention_planes
+  long long Mt = 0;     // rows of the plane tensor (all tokens of the batch)
+  // Q|K|V of rows [r0, r0 + M) of `in` (LayerNorm ln still owed) into the shared qkv buffer, in the layout `planes` selects
+  int qkv_proj(cudaStream_t st, const DState& in, const LNp* ln, const Linear& lin, const Folded& f, long long r0, int M) const {
+    if (!planes) return consume(st, in, ln, lin, f, r0, M, rows_at(h->qkv.p, r0, 3 * H, 2), 3 * H, EPI_BIAS);
+    RGQA_CHECK(ln == nullptr || f.W != nullptr, "deferred LayerNorm: folded weight missing");
+    return gemm_bf16_qkv_planes(st, hi_rows(in, r0), H, ln ? f.W : lin.W, lin.K, ln ? f.b : lin.b,
+                                static_cast<char*>(h->qkv.p) + static_cast<size_t>(r0) * 64 * 2, Mt, h->cfg.heads, M, lin.K,
+                                ln ? st_rows(in, r0) : nullptr, h->cfg.ln_eps);
+  }
+  // softmax(QK^T/8 + mask) V for B samples: queries rows [rq, rq + B*Lq), keys / values rows [rk, rk + B*Lk) of the qkv buffer
+  int attn(cudaStream_t st, long long rq, long long rk, const int32_t* key_mask, void* ctx_rows, int B, int Lq, int Lk) const {
+    if (planes) return attention_planes(st, h->qkv.p, Mt, rq, rk, key_mask, ctx_rows, H, B, Lq, Lk, h->cfg.heads);
+    char* q = rows_at(h->qkv.p, rq, 3 * H, 2);
+    char* kv = rows_at(h->qkv.p, rk, 3 * H, 2);
+    return attention(st, DT_BF16, q, 3 * H, kv + static_cast<size_t>(H) * 2, 3 * H, kv + static_cast<size_t>(2 * H) * 2, 3 * H, key_mask,
+                     ctx_rows, H, B, Lq, Lk, h->cfg.heads);
+  }
   char* hi_rows(const DState& s, long long r0) const { return s.hi + static_cast<size_t>(r0) * H * 2; }
   char* lo_rows(const DState& s, long long r0) const { return s.lo + static_cast<size_t>(r0) * H * 2; }
   float* st_rows(const DState& s, long long r0) const { return s.stats + r0 * 12; }
@@ -822,12 +840,9 @@ struct DefCtx {
   // BertAttention (self) on rows [r0, r0 + B*S): in (LayerNorm ln_in) -> out (LayerNorm w.ln)
   int att(cudaStream_t st, const AttW& w, const DState& in, const LNp* ln_in, const DState& out, long long r0, int B, int S,
           const int32_t* key_mask) const {
-    char* qkv = rows_at(h->qkv.p, r0, 3 * H, 2);
     char* ctx = rows_at(h->ctx.p, r0, H, 2);
-    if (consume(st, in, ln_in, w.qkv, w.qkv_f, r0, B * S, qkv, 3 * H, EPI_BIAS)) return 1;
-    if (attention(st, DT_BF16, qkv, 3 * H, qkv + static_cast<size_t>(H) * 2, 3 * H, qkv + static_cast<size_t>(2 * H) * 2, 3 * H,
-                  key_mask, ctx, H, B, S, S, h->cfg.heads))
-      return 1;
+    if (qkv_proj(st, in, ln_in, w.qkv, w.qkv_f, r0, B * S)) return 1;
+    if (attn(st, r0, r0, key_mask, ctx, B, S, S)) return 1;
     return produce(st, ctx, H, w.out, w.out_bb, in, ln_in, out, r0, B * S);
   }
   // BertIntermediate + BertOutput: in (LayerNorm ln_in) -> out (LayerNorm w.ln)
@@ -851,7 +866,10 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
              reinterpret_cast<float*>(static_cast<char*>(h->resA.p) + static_cast<size_t>(Mt) * H * 2)};
   DState alt{static_cast<char*>(h->hidB.p), static_cast<char*>(h->resB.p),
              reinterpret_cast<float*>(static_cast<char*>(h->resB.p) + static_cast<size_t>(Mt) * H * 2)};
-  const DefCtx d{h, H};
+  DefCtx d{h, H};
+  d.Mt = Mt;
+  d.planes = option_get(OPT_QKV_PLANES) != 0 && attention_planes_ok(B, L, L, c.heads) && attention_planes_ok(B, V, V, c.heads) &&
+             attention_planes_ok(B, L, V, c.heads) && attention_planes_ok(B, V, L, c.heads);
 
   const bool two = option_get(OPT_TWO_STREAMS) != 0;
   if (two && h->side == nullptr) {
@@ -875,10 +893,11 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
   if (fork()) return 1;
 
   // ---- embeddings (modeling.py:876) and visual feature encoder (:507-517): normalised rows -> identity states ----
-  // fp32 scratch for the normalised rows: language rows in the (idle) FFN buffer, visual rows in the visual part of the
-  // (idle) Q|K|V buffer -- regions only their own branch's stream touches
+  // fp32 scratch for the normalised rows: the (idle) FFN buffer, language rows in its language part, visual rows in its
+  // visual part -- regions only their own branch's stream touches (the Q|K|V buffer will not do: in the head-major layout
+  // the language branch's first projection writes rows of every plane, all over the buffer)
   float* y32 = static_cast<float*>(h->inter.p);
-  float* yv = reinterpret_cast<float*>(rows_at(h->qkv.p, Ml, 3 * H, 2));
+  float* yv = reinterpret_cast<float*>(rows_at(h->inter.p, Ml, c.intermediate, 2));
   if (embed_ln(st, DT_BF16, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, cur.hi, y32, B, L, H,
                c.vocab_size, c.max_position, c.type_vocab, c.ln_eps) ||
       identity_state(st, y32, cur.hi, cur.lo, cur.stats, Ml, H))
@@ -913,20 +932,15 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
   if (join()) return 1;
   for (int i = 0; i < c.x_layers; ++i) {  // modeling.py:477-488
     const XLayerW& w = h->x_layers[i];
-    char* qkv = static_cast<char*>(h->qkv.p);
-    char* qkv_v = rows_at(h->qkv.p, Ml, 3 * H, 2);
     char* ctx = static_cast<char*>(h->ctx.p);
     // ONE BertCrossattLayer for both directions (:455-459); its Q|K|V of each modality behind that modality's LayerNorm
     if (fork()) return 1;
-    if (d.consume(st, cur, ln_l, w.cross.qkv, w.cross.qkv_f, 0, static_cast<int>(Ml), qkv, 3 * H, EPI_BIAS) ||
-        d.consume(sv, cur, ln_v, w.cross.qkv, w.cross.qkv_f2, Ml, static_cast<int>(Mv), qkv_v, 3 * H, EPI_BIAS))
+    if (d.qkv_proj(st, cur, ln_l, w.cross.qkv, w.cross.qkv_f, 0, static_cast<int>(Ml)) ||
+        d.qkv_proj(sv, cur, ln_v, w.cross.qkv, w.cross.qkv_f2, Ml, static_cast<int>(Mv)))
       return 1;
     if (join()) return 1;
-    if (attention(st, DT_BF16, qkv, 3 * H, qkv_v + static_cast<size_t>(H) * 2, 3 * H, qkv_v + static_cast<size_t>(2 * H) * 2, 3 * H,
-                  nullptr, ctx, H, B, L, V, c.heads) ||
-        attention(st, DT_BF16, qkv_v, 3 * H, qkv + static_cast<size_t>(H) * 2, 3 * H, qkv + static_cast<size_t>(2 * H) * 2, 3 * H, mask,
-                  rows_at(ctx, Ml, H, 2), H, B, V, L, c.heads))
-      return 1;
+    // language queries over visual keys (no mask), visual queries over language keys (language mask)
+    if (d.attn(st, 0, Ml, nullptr, ctx, B, L, V) || d.attn(st, Ml, 0, mask, rows_at(ctx, Ml, H, 2), B, V, L)) return 1;
     if (fork()) return 1;
     // cross output + self attention + FFN per modality (:455-475), the two chains side by side
     if (d.produce(st, ctx, H, w.cross.out, w.cross.out_bb, cur, ln_l, alt, 0, static_cast<int>(Ml)) ||
@@ -1083,7 +1097,8 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
 
   const rgqa_config& c = h->cfg;
   const long long key = (static_cast<long long>(B) << 20) | (static_cast<long long>(L) << 8) | (feat_dtype << 4) |
-                        ((option_get(OPT_DEFER_LN) != 0) << 3) |
+                        ((option_get(OPT_DEFER_LN) != 0) << 3) | (static_cast<long long>(option_get(OPT_QKV_PLANES) != 0) << 40) |
+                        (static_cast<long long>(option_get(OPT_ATTN_TMA) != 0) << 41) |
                         ((seg != nullptr) << 2) | ((pooled_out != nullptr) << 1) | (logits_out != nullptr);
   if (h->graphs.size() > 16) {  // callers that never repeat a pointer: do not hoard graphs
     drop_graphs(h);
@@ -1329,6 +1344,10 @@ int rgqa_set_option(const char* name, int value) {
   }
   if (strcmp(name, "attn_tma") == 0) {
     option_set(OPT_ATTN_TMA, value);
+    return 0;
+  }
+  if (strcmp(name, "qkv_planes") == 0) {
+    option_set(OPT_QKV_PLANES, value);
     return 0;
   }
   if (strcmp(name, "two_streams") == 0) {

@@ -346,6 +346,8 @@ struct AttnTmaParams {
   int kv_stride;        // bytes between consecutive K (or V) lines: 384 merged, 256 otherwise
   int k_off, v_off;     // first K / V line, from the slot base
   int merged;           // self-attention: ONE 3-D box (64 cols x {q,k,v} x L rows) per unit; else Q box + {k,v} box
+  int planes;           // operands come from the head-major plane tensor of gemm_bf16_qkv_planes: boxes are (64, L, n planes)
+  int q_row0, kv_row0;  // planes: first query / key row of this call inside the plane tensor
   int depth;            // slots per compute warp
   int debug;            // measurement switches (RGQA_ATTN_DEBUG): 1 no stores, 2 no P.V, 4 no math at all
 };
@@ -409,7 +411,14 @@ attention_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint8_t* dst = smem + static_cast<size_t>(slot) * slot_bytes;
         if (k >= p.depth) mbar_wait(&empty_bar[slot], ((k / p.depth) - 1) & 1u);
         mbar_expect_tx(&full_bar[slot], bytes);
-        if (p.merged) {
+        if (p.planes) {  // plane index = head * 3 + {q, k, v}; Q, K, V tiles land back to back
+          if (p.merged) {
+            tma_load_3d(dst, &tmA, &full_bar[slot], 0, p.q_row0 + b * p.Lq, 3 * h);
+          } else {
+            tma_load_3d(dst, &tmA, &full_bar[slot], 0, p.q_row0 + b * p.Lq, 3 * h);
+            tma_load_3d(dst + p.k_off, &tmB, &full_bar[slot], 0, p.kv_row0 + b * p.Lk, 3 * h + 1);
+          }
+        } else if (p.merged) {
           tma_load_3d(dst, &tmA, &full_bar[slot], h * HD, 0, b * p.Lq);
         } else {
           tma_load_2d(dst, &tmA, &full_bar[slot], h * HD, b * p.Lq);
@@ -549,7 +558,7 @@ attention_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (lane == 0) {
       if (!(p.debug & 1)) {
         const uint8_t* src = smem + static_cast<size_t>(slot) * slot_bytes;
-        if (p.merged)
+        if (p.merged && !p.planes)
           tma_store_3d(&tmO, src, h * HD, 0, b * p.Lq);
         else
           tma_store_2d(&tmO, src, h * HD, b * p.Lq);
@@ -589,6 +598,8 @@ int launch_attention_tma(cudaStream_t stream, const __nv_bfloat16* q, long long 
     p.v_off = Lq * 128 + 128;
   }
   p.merged = merged ? 1 : 0;
+  p.planes = 0;
+  p.q_row0 = p.kv_row0 = 0;
   p.key_mask = key_mask;
   p.Lq = Lq;
   p.Lk = Lk;
@@ -601,6 +612,45 @@ int launch_attention_tma(cudaStream_t stream, const __nv_bfloat16* q, long long 
     return d ? atoi(d) : 0;
   }();
   p.debug = debug_env;
+  const int smem = kAttnWarps * depth * p.slot_bytes + 1024 + kAttnPad + 1024;
+  static bool cfg = false;
+  if (!cfg) {
+    RGQA_CUDA_OK(cudaFuncSetAttribute(attention_tma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cfg = true;
+  }
+  int grid = num_sms();
+  if (grid > p.items) grid = p.items;
+  RGQA_CUDA_OK(launch_pdl(attention_tma_kernel<KS>, dim3(grid), dim3((1 + kAttnWarps) * 32), smem, stream, tmA, tmB, tmO, p));
+  return 0;
+}
+
+template <int KS>
+int launch_attention_planes(cudaStream_t stream, const __nv_bfloat16* planes, long long plane_rows, long long q_row0,
+                            long long kv_row0, const int32_t* key_mask, __nv_bfloat16* out, long long ldo, int B, int Lq, int Lk,
+                            int heads, int depth) {
+  CUtensorMap tmA, tmB, tmO;
+  const bool self = (q_row0 == kv_row0) && (Lq == Lk);
+  const long long np = 3LL * heads;
+  if (make_tmap_3d(&tmA, planes, HD, plane_rows, np, 128, plane_rows * 128, HD, Lq, self ? 3 : 1) ||
+      make_tmap_3d(&tmB, planes, HD, plane_rows, np, 128, plane_rows * 128, HD, Lk, 2) ||
+      make_tmap_ex(&tmO, out, static_cast<long long>(B) * Lq, static_cast<long long>(heads) * HD, ldo, Lq, HD, 2, 128))
+    return 1;
+  AttnTmaParams p;
+  p.key_mask = key_mask;
+  p.Lq = Lq;
+  p.Lk = Lk;
+  p.heads = heads;
+  p.items = B * heads;
+  p.slot_bytes = (Lq + 2 * Lk) * 128;
+  p.q_stride = p.kv_stride = 128;
+  p.k_off = Lq * 128;
+  p.v_off = (Lq + Lk) * 128;
+  p.merged = self ? 1 : 0;
+  p.planes = 1;
+  p.q_row0 = static_cast<int>(q_row0);
+  p.kv_row0 = static_cast<int>(kv_row0);
+  p.depth = depth;
+  p.debug = 0;
   const int smem = kAttnWarps * depth * p.slot_bytes + 1024 + kAttnPad + 1024;
   static bool cfg = false;
   if (!cfg) {
@@ -638,6 +688,34 @@ int launch_attention_mma(cudaStream_t stream, const __nv_bfloat16* q, long long 
 }
 
 }  // namespace
+
+int attention_planes_ok(int B, int Lq, int Lk, int heads) {
+  return option_get(OPT_ATTN_TMA) != 0 && attention_tma_depth(Lq, Lk) >= 2 && static_cast<long long>(B) * heads >= 16LL * num_sms();
+}
+
+int attention_planes(cudaStream_t stream, const void* planes, long long plane_rows, long long q_row0, long long kv_row0,
+                     const int32_t* key_mask, void* out, long long ldo, int B, int Lq, int Lk, int heads) {
+  RGQA_CHECK(planes && out && B > 0 && heads > 0, "attention_planes: bad arguments");
+  RGQA_CHECK(attention_planes_ok(B, Lq, Lk, heads), "attention_planes: shape B=%d Lq=%d Lk=%d is not served by the TMA kernel", B, Lq, Lk);
+  RGQA_CHECK(q_row0 + static_cast<long long>(B) * Lq <= plane_rows && kv_row0 + static_cast<long long>(B) * Lk <= plane_rows,
+             "attention_planes: rows outside the plane tensor");
+  const int depth = attention_tma_depth(Lq, Lk);
+  const __nv_bfloat16* pb = static_cast<const __nv_bfloat16*>(planes);
+  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
+  void* tok = prof_begin(stream);
+  int rc = 0;
+  switch ((Lk + 15) / 16) {
+    case 1: rc = launch_attention_planes<1>(stream, pb, plane_rows, q_row0, kv_row0, key_mask, ob, ldo, B, Lq, Lk, heads, depth); break;
+    case 2: rc = launch_attention_planes<2>(stream, pb, plane_rows, q_row0, kv_row0, key_mask, ob, ldo, B, Lq, Lk, heads, depth); break;
+    case 3: rc = launch_attention_planes<3>(stream, pb, plane_rows, q_row0, kv_row0, key_mask, ob, ldo, B, Lq, Lk, heads, depth); break;
+    default: rc = launch_attention_planes<4>(stream, pb, plane_rows, q_row0, kv_row0, key_mask, ob, ldo, B, Lq, Lk, heads, depth); break;
+  }
+  if (rc) return 1;
+  prof_end(tok, stream, 4.0 * B * static_cast<double>(Lq) * Lk * heads * HD, PROF_ATTENTION);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, const void* k, long long ldk,
               const void* v, long long ldv, const int32_t* key_mask, void* out, long long ldo, int B, int Lq,

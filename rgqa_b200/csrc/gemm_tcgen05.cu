@@ -69,6 +69,8 @@ struct GemmParams {
   const float* ln_c;      // [N] sum_k W'[n,k]
   float ln_eps;
   long long ln_stats_ld;  // floats between the statistics of consecutive GEMM rows (12 when dense)
+  int out_heads;  // > 0: the output is the head-major Q|K|V plane tensor (gemm_bf16_qkv_planes); column block cb of 64 goes
+                  // to plane (cb % heads) * 3 + cb / heads
   int vec_ok;  // direct path: rows of out (and resid) are 16-byte aligned -> vector stores allowed
   int debug;   // measurement only (rgqa_set_option "gemm_debug"): bit0 skip TMA stores, bit1 skip epilogue math+smem
 };
@@ -826,7 +828,12 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
           if (issuer && tile_rows_live && !(p.debug & 1)) {
-            tma_store_2d(&tmOut, buf + quarter * kSubSlab, col_slab, m0 + quarter * 32);
+            if (p.out_heads > 0) {
+              const int cb = col_slab >> 6;
+              tma_store_3d(&tmOut, buf + quarter * kSubSlab, 0, m0 + quarter * 32, (cb % p.out_heads) * 3 + cb / p.out_heads);
+            } else {
+              tma_store_2d(&tmOut, buf + quarter * kSubSlab, col_slab, m0 + quarter * 32);
+            }
             tma_store_commit();
           }
           ++slab_ctr;
@@ -1083,6 +1090,36 @@ int gemm_bf16_resid_hl(cudaStream_t stream, const void* A, long long lda, const 
 int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
               const void* resid, long long ldr, void* out, long long ldo, int out_f32, int M, int N, int K, int epi) {
   return gemm_bf16_folded(stream, A, lda, W, ldw, bias, resid, ldr, out, ldo, out_f32, M, N, K, epi, nullptr, nullptr, 0.f);
+}
+
+// Q|K|V projection written HEAD-MAJOR: out[plane][row][64] with plane = head * 3 + {q, k, v}, every plane a contiguous
+// [plane_rows, 64] bf16 array (`out` points at this call's first row inside plane 0).  A (sample, head) unit of the attention
+// kernel is then three contiguous L x 128-byte blocks instead of 3 L pieces at a 4 608-byte stride, and every 32-row store of
+// this epilogue one contiguous 4 KB block.  bf16, bias epilogue, CTA-pair + staged kernel only (M >= 1024, N = 3 * heads * 64).
+int gemm_bf16_qkv_planes(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                         void* out, long long plane_rows, int heads, int M, int K, const float* ln_stats, float ln_eps) {
+  const int N = 3 * heads * 64;
+  RGQA_CHECK(M >= 1024 && K > 0 && K % BK == 0 && heads > 0 && plane_rows >= M, "gemm_bf16_qkv_planes: bad problem M=%d K=%d", M, K);
+  RGQA_CHECK(option_get(OPT_GEMM_PAIR) != 0 && option_get(OPT_GEMM_STAGED) != 0, "gemm_bf16_qkv_planes: needs the staged CTA-pair kernel");
+  RGQA_CHECK(ln_stats == nullptr || (bias != nullptr && K == 768), "gemm_bf16_qkv_planes: deferred LayerNorm needs K = 768 and the folded bias");
+  CUtensorMap tmA, tmB, tmOut;
+  if (make_tmap(&tmA, A, M, K, lda, BM, 2) || make_tmap(&tmB, W, N, K, ldw, kPairBN / 2, 2) ||
+      make_tmap_3d(&tmOut, out, 64, M, 3LL * heads, 128, plane_rows * 128, 64, 32, 1))
+    return 1;
+  GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.bias = bias;
+  p.out = out;
+  p.ldo = 64;
+  p.ln_stats = ln_stats;
+  p.ln_eps = ln_eps;
+  p.ln_stats_ld = 12;
+  p.out_heads = heads;
+  p.vec_ok = 1;
+  p.debug = option_get(OPT_GEMM_DEBUG);
+  return launch_pair<EPI_BIAS, __nv_bfloat16, true>(stream, tmA, tmB, tmOut, tmA, p);
 }
 
 int gemm_bf16_folded(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,

@@ -31,6 +31,16 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
 int gemm_bf16_folded(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
                      const void* resid, long long ldr, void* out, long long ldo, int out_f32, int M, int N, int K, int epi,
                      const float* ln_stats, const float* ln_c, float ln_eps, long long ln_stats_ld = 12);
+// Q|K|V projection with a head-major output: out[plane = head*3 + {q,k,v}][row][64] bf16, planes plane_rows rows apart; `out`
+// points at this call's first row of plane 0.  ln_stats != nullptr: deferred-LayerNorm consumer (folded weight / bias).
+int gemm_bf16_qkv_planes(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                         void* out, long long plane_rows, int heads, int M, int K, const float* ln_stats, float ln_eps);
+// attention over the head-major planes of gemm_bf16_qkv_planes (TMA kernel only): queries are rows [q_row0, q_row0 + B*Lq) and
+// keys / values rows [kv_row0, kv_row0 + B*Lk) of the same plane tensor; out [B*Lq, heads*64] bf16 (row stride ldo).
+int attention_planes(cudaStream_t stream, const void* planes, long long plane_rows, long long q_row0, long long kv_row0,
+                     const int32_t* key_mask, void* out, long long ldo, int B, int Lq, int Lk, int heads);
+// 1 when attention_planes can serve (B, Lq, Lk): enough units for the persistent kernel and room for two slots per warp
+int attention_planes_ok(int B, int Lq, int Lk, int heads);
 // Producer of a deferred-LayerNorm hidden state: v = A·Wᵀ + bias + LN_prev(x_prev) with x_prev = in_hi + in_lo (bf16
 // pair), LN_prev from (in_stats, in_gamma, in_beta); writes v as out_hi = bf16(v), out_lo = bf16(v - out_hi) and the
 // partial (sum, sumsq) statistics [M][6][2].  N must be 768.
@@ -144,7 +154,8 @@ int rowdot(cudaStream_t stream, const float* a, const float* b, float* out, int 
 // ---- runtime options (prof.cu): kernel-selection switches for A/B measurements ---------------------
 enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_GEMM_DEBUG = 2, OPT_PDL = 3, OPT_GEMM_LN = 4, OPT_TWO_STREAMS = 5, OPT_GRAPHS = 6,
   OPT_DEFER_LN = 7,
-  OPT_ATTN_TMA = 8, OPT_COUNT = 16 };
+  OPT_ATTN_TMA = 8,
+  OPT_QKV_PLANES = 9, OPT_COUNT = 16 };
 int option_get(int key);
 void option_set(int key, int value);
 

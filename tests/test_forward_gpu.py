@@ -275,3 +275,24 @@ def test_uniter_deferred_layernorm_matches_fp32_and_standard_path(cuda_device):
     e_def = float((l_def - l32).pow(2).mean().sqrt())
     assert e_def <= 1.3 * e_std + 1e-3, (e_def, e_std)
     assert (p_def - p32).abs().max().item() <= 3e-2
+
+
+def test_head_major_qkv_planes_forward_is_bit_identical(cuda_device):
+    """Option qkv_planes: the Q|K|V projections of the large-batch path are written head-major ([head*3 + {q,k,v}][row][64])
+    and the TMA attention reads contiguous tiles — a pure layout change: logits must equal the fused-layout path bit for bit
+    (and stay within the bf16 tolerance of the fp32 path)."""
+    from rgqa_b200 import _lib as L_
+    lib = L_.load()
+    inp = syn.make_inputs(200, 20, seed=123)            # 2 400 (sample, head) units: enough for the persistent attention kernel
+    eng = _engine("lxmert", "rich", "bf16", 0.2)
+    try:
+        lib.rgqa_set_option(b"qkv_planes", 0)
+        p0, l0 = _run(eng, inp)
+        lib.rgqa_set_option(b"qkv_planes", 1)
+        p1, l1 = _run(eng, inp)
+        p2, l2 = _run(eng, inp)                        # graph capture + replay of the same shape
+    finally:
+        lib.rgqa_set_option(b"qkv_planes", 0)
+    assert torch.equal(l0, l1) and torch.equal(p0, p1) and torch.equal(l1, l2)
+    p32, l32 = _run(_engine("lxmert", "rich", "fp32", 0.2), inp)
+    _assert_bf16_close(l1.numpy(), l32.numpy(), scale=10.0)
