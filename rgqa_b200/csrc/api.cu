@@ -893,14 +893,9 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
   if (fork()) return 1;
 
   // ---- embeddings (modeling.py:876) and visual feature encoder (:507-517): normalised rows -> identity states ----
-  // fp32 scratch for the normalised rows: the (idle) FFN buffer, language rows in its language part, visual rows in its
-  // visual part -- regions only their own branch's stream touches (the Q|K|V buffer will not do: in the head-major layout
-  // the language branch's first projection writes rows of every plane, all over the buffer)
-  float* y32 = static_cast<float*>(h->inter.p);
-  float* yv = reinterpret_cast<float*>(rows_at(h->inter.p, Ml, c.intermediate, 2));
-  if (embed_ln(st, DT_BF16, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, cur.hi, y32, B, L, H,
-               c.vocab_size, c.max_position, c.type_vocab, c.ln_eps) ||
-      identity_state(st, y32, cur.hi, cur.lo, cur.stats, Ml, H))
+  // the row kernels emit the identity state themselves (lo = bf16 remainder, statistics (0, 768)): no fp32 round trip
+  if (embed_ln(st, DT_BF16, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, cur.hi, nullptr, B, L, H,
+               c.vocab_size, c.max_position, c.type_vocab, c.ln_eps, cur.lo, cur.stats))
     return 1;
   {
     const void* a = feat;
@@ -912,8 +907,8 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
     if (gemm_bf16(sv, a, c.visual_feat_dim, h->visn_fc.W, h->visn_fc.K, h->visn_fc.b, nullptr, 0, pre, H, 1, static_cast<int>(Mv),
                   H, h->visn_fc.K, EPI_BIAS) ||
         visn_combine(sv, DT_BF16, pre, pos, c.visual_pos_dim, h->box_W, h->box_b, h->visn_ln.g, h->visn_ln.b, h->box_ln.g,
-                     h->box_ln.b, d.hi_rows(cur, Ml), yv, static_cast<int>(Mv), H, c.ln_eps) ||
-        identity_state(sv, yv, d.hi_rows(cur, Ml), d.lo_rows(cur, Ml), d.st_rows(cur, Ml), Mv, H))
+                     h->box_ln.b, d.hi_rows(cur, Ml), nullptr, static_cast<int>(Mv), H, c.ln_eps, d.lo_rows(cur, Ml),
+                     d.st_rows(cur, Ml)))
       return 1;
   }
   const LNp *ln_l = nullptr, *ln_v = nullptr;  // LayerNorm still owed to the language / visual rows of `cur`

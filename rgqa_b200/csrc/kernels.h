@@ -85,7 +85,7 @@ int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, cons
 // LN(word[ids] + pos[0..L) + type[seg]) (modeling.py:278-292); tables and gamma/beta fp32.
 int embed_ln(cudaStream_t stream, int out_dtype, const int32_t* ids, const int32_t* seg, const float* word,
              const float* pos, const float* type, const float* gamma, const float* beta, void* out, float* out32, int B,
-             int L, int H, int vocab, int max_pos, int n_types, float eps);
+             int L, int H, int vocab, int max_pos, int n_types, float eps, void* lo_out = nullptr, float* stats_out = nullptr);
 // y = LN(x) * gamma + beta; x fp32 [M,H] (row stride ldx), y fp32 or bf16 [M,H] dense.
 // Every row kernel takes an optional fp32 copy pointer (y32 / out32): in the bf16 path the hidden state is
 // kept twice, bf16 as the next GEMM's A operand and fp32 as the residual stream.
@@ -94,7 +94,8 @@ int layernorm(cudaStream_t stream, int out_dtype, const float* x, long long ldx,
 // (LN(x_pre) + LN(box·Wbᵀ + bb)) / 2 (modeling.py:507-517); x_pre = feat·Wfᵀ + bf, fp32 [M,H].
 int visn_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const float* boxes, int box_dim,
                  const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
-                 const float* b2, void* out, float* out32, int M, int H, float eps);
+                 const float* b2, void* out, float* out32, int M, int H, float eps, void* lo_out = nullptr,
+                 float* stats_out = nullptr);  // lo_out / stats_out (bf16 outputs): also emit the identity deferred-LayerNorm state
 // UNITER image embedding tail: LN3( LN1(x_pre) + LN2(pos7·Wpᵀ + bp) + type_emb ) (uniter/modeling.py:606-612).
 int uniter_img_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const float* pos, int pos_dim,
                        const float* Wp, const float* bp, const float* g1, const float* b1, const float* g2,

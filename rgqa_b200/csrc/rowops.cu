@@ -41,8 +41,11 @@ __device__ __forceinline__ void normalize(float4 (&x)[NV], float mean, float rst
   }
 }
 
+// `lo_row` / `stats_row` (bf16 outputs only): the row additionally leaves as an identity deferred-LayerNorm state —
+// lo = bf16(y - bf16(y)) and statistics (sum 0, sumsq H) so that mean = 0, rstd = 1 (see identity_state)
 template <int NV, typename OutT>
-__device__ __forceinline__ void store_row(const float4 (&x)[NV], OutT* out_row, int lane, float* copy_row = nullptr) {
+__device__ __forceinline__ void store_row(const float4 (&x)[NV], OutT* out_row, int lane, float* copy_row = nullptr,
+                                          __nv_bfloat16* lo_row = nullptr, float* stats_row = nullptr) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = i * 128 + lane * 4;
@@ -55,8 +58,14 @@ __device__ __forceinline__ void store_row(const float4 (&x)[NV], OutT* out_row, 
       u.x = pack_bf16x2(x[i].x, x[i].y);
       u.y = pack_bf16x2(x[i].z, x[i].w);
       *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out_row) + c) = u;
+      if (lo_row != nullptr) {
+        const float2 h0 = unpack_bf16x2(u.x), h1 = unpack_bf16x2(u.y);
+        *reinterpret_cast<uint2*>(lo_row + c) = make_uint2(pack_bf16x2(x[i].x - h0.x, x[i].y - h0.y), pack_bf16x2(x[i].z - h1.x, x[i].w - h1.y));
+      }
     }
   }
+  if (stats_row != nullptr && lane < 3)
+    reinterpret_cast<float4*>(stats_row)[lane] = make_float4(0.f, lane == 0 ? static_cast<float>(NV * 128) : 0.f, 0.f, 0.f);
 }
 
 // ---- embeddings + LayerNorm (src/lxrt/modeling.py:278-292) --------------------------------------
@@ -64,7 +73,8 @@ template <int NV, typename OutT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ seg, const float* __restrict__ word,
                 const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ gamma,
-                const float* __restrict__ beta, OutT* __restrict__ out, float* __restrict__ out32, int rows, int L, int H, float eps, int vocab,
+                const float* __restrict__ beta, OutT* __restrict__ out, float* __restrict__ out32, __nv_bfloat16* __restrict__ lo,
+                float* __restrict__ stats, int rows, int L, int H, float eps, int vocab,
                 int n_types) {
   pdl_launch_dependents();
   pdl_wait();
@@ -92,7 +102,9 @@ embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ seg
   row_stats<NV>(x, H, eps, mean, rstd);
   normalize<NV>(x, mean, rstd, gamma, beta, lane);
   store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane,
-                      out32 != nullptr ? out32 + static_cast<long long>(row) * H : nullptr);
+                      out32 != nullptr ? out32 + static_cast<long long>(row) * H : nullptr,
+                      lo != nullptr ? lo + static_cast<long long>(row) * H : nullptr,
+                      stats != nullptr ? stats + static_cast<long long>(row) * 12 : nullptr);
 }
 
 // ---- plain LayerNorm over fp32 rows ------------------------------------------------------------
@@ -153,7 +165,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 visn_combine_kernel(const float* __restrict__ x_pre, const float* __restrict__ boxes, int box_dim,
                     const float* __restrict__ Wb, const float* __restrict__ bb, const float* __restrict__ g1,
                     const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
-                    OutT* __restrict__ out, float* __restrict__ out32, int rows, int H, float eps) {
+                    OutT* __restrict__ out, float* __restrict__ out32, __nv_bfloat16* __restrict__ lo, float* __restrict__ stats,
+                    int rows, int H, float eps) {
   extern __shared__ __align__(16) float wsm[];
   pdl_launch_dependents();
   pdl_wait();
@@ -177,7 +190,9 @@ visn_combine_kernel(const float* __restrict__ x_pre, const float* __restrict__ b
     x[i] = make_float4((x[i].x + y[i].x) / 2.f, (x[i].y + y[i].y) / 2.f, (x[i].z + y[i].z) / 2.f,
                        (x[i].w + y[i].w) / 2.f);
   store_row<NV, OutT>(x, out + static_cast<long long>(row) * H, lane,
-                      out32 != nullptr ? out32 + static_cast<long long>(row) * H : nullptr);
+                      out32 != nullptr ? out32 + static_cast<long long>(row) * H : nullptr,
+                      lo != nullptr ? lo + static_cast<long long>(row) * H : nullptr,
+                      stats != nullptr ? stats + static_cast<long long>(row) * 12 : nullptr);
   }
 }
 
@@ -332,13 +347,13 @@ inline int row_grid(int rows) { return (rows + kWarpsPerBlock - 1) / kWarpsPerBl
 
 int embed_ln(cudaStream_t stream, int out_dtype, const int32_t* ids, const int32_t* seg, const float* word,
              const float* pos, const float* type, const float* gamma, const float* beta, void* out, float* out32, int B,
-             int L, int H, int vocab, int max_pos, int n_types, float eps) {
+             int L, int H, int vocab, int max_pos, int n_types, float eps, void* lo_out, float* stats_out) {
   RGQA_CHECK(B > 0 && L > 0 && L <= max_pos, "embed_ln: bad B=%d L=%d (max_pos=%d)", B, L, max_pos);
   const int M = B * L;
   if (out_dtype == DT_BF16) {
-    RGQA_DISPATCH_ROW(embed_ln_kernel, __nv_bfloat16, ids, seg, word, pos, type, gamma, beta, static_cast<__nv_bfloat16*>(out), out32, M, L, H, eps, vocab, n_types);
+    RGQA_DISPATCH_ROW(embed_ln_kernel, __nv_bfloat16, ids, seg, word, pos, type, gamma, beta, static_cast<__nv_bfloat16*>(out), out32, static_cast<__nv_bfloat16*>(lo_out), stats_out, M, L, H, eps, vocab, n_types);
   } else {
-    RGQA_DISPATCH_ROW(embed_ln_kernel, float, ids, seg, word, pos, type, gamma, beta, static_cast<float*>(out), out32, M, L, H, eps, vocab, n_types);
+    RGQA_DISPATCH_ROW(embed_ln_kernel, float, ids, seg, word, pos, type, gamma, beta, static_cast<float*>(out), out32, static_cast<__nv_bfloat16*>(nullptr), static_cast<float*>(nullptr), M, L, H, eps, vocab, n_types);
   }
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
@@ -361,12 +376,12 @@ int layernorm(cudaStream_t stream, int out_dtype, const float* x, long long ldx,
 
 int visn_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const float* boxes, int box_dim,
                  const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
-                 const float* b2, void* out, float* out32, int M, int H, float eps) {
+                 const float* b2, void* out, float* out32, int M, int H, float eps, void* lo_out, float* stats_out) {
   RGQA_CHECK(M > 0 && box_dim >= 1 && box_dim <= 8, "visn_combine: bad M=%d box_dim=%d", M, box_dim);
   if (out_dtype == DT_BF16) {
-    RGQA_DISPATCH_ROW_SMEM(visn_combine_kernel, __nv_bfloat16, (box_dim + 1) * H * sizeof(float), x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<__nv_bfloat16*>(out), out32, M, H, eps);
+    RGQA_DISPATCH_ROW_SMEM(visn_combine_kernel, __nv_bfloat16, (box_dim + 1) * H * sizeof(float), x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<__nv_bfloat16*>(out), out32, static_cast<__nv_bfloat16*>(lo_out), stats_out, M, H, eps);
   } else {
-    RGQA_DISPATCH_ROW_SMEM(visn_combine_kernel, float, (box_dim + 1) * H * sizeof(float), x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<float*>(out), out32, M, H, eps);
+    RGQA_DISPATCH_ROW_SMEM(visn_combine_kernel, float, (box_dim + 1) * H * sizeof(float), x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<float*>(out), out32, static_cast<__nv_bfloat16*>(nullptr), static_cast<float*>(nullptr), M, H, eps);
   }
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
