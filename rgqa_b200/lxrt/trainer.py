@@ -39,15 +39,22 @@ class _Ffn:
 
 class LXMERTTrainer:
     def __init__(self, state_dict, l_layers=9, x_layers=5, r_layers=5, heads=12, eps=1e-12, device="cuda:0", lr=5e-5, warmup=0.1,
-                 t_total=-1, schedule="warmup_linear", b1=0.9, b2=0.999, e=1e-6, weight_decay=0.01, clip_norm=5.0):
+                 t_total=-1, schedule="warmup_linear", b1=0.9, b2=0.999, e=1e-6, weight_decay=0.01, clip_norm=5.0, gemm="fp32"):
+        """``gemm="bf16"``: the large matrix products (forward, dgrad and wgrad of every nn.Linear with K a multiple of 64)
+        run on the tcgen05 tensor cores with bf16 operands cast on the fly and fp32 accumulation / outputs; master weights,
+        activations, gradients and the optimiser stay fp32 (mixed precision; not the reference's arithmetic — parity with
+        the fp32 trajectory holds to ~1e-2, see tests/test_train_gpu.py)."""
+        assert gemm in ("fp32", "bf16")
         dev = torch.device(device)
+        self.gemm = gemm
         self.dev, self.heads, self.eps, self.clip_norm = dev, heads, eps, clip_norm
         self.hp = dict(lr=lr, warmup=warmup, t_total=t_total, schedule=schedule, b1=b1, b2=b2, e=e, weight_decay=weight_decay)
         self.step_count = 0
         names = list(state_dict.keys())
         sizes = [state_dict[n].numel() for n in names]
-        total = sum(sizes)
-        self.flat_p = torch.empty(total, dtype=torch.float32, device=dev)
+        pad = lambda n: (n + 63) // 64 * 64            # every tensor starts 256-byte aligned (TMA operands / vector stores)
+        total = sum(pad(sz) for sz in sizes)
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -57,7 +64,7 @@ class LXMERTTrainer:
             self.p[n] = self.flat_p[off:off + sz].view(state_dict[n].shape)
             self.g[n] = self.flat_g[off:off + sz].view(state_dict[n].shape)
             self.p[n].copy_(state_dict[n].detach().to(dev, torch.float32))
-            off += sz
+            off += pad(sz)
         enc = P + "encoder."
         self.l = [(_Att(f"{enc}layer.{i}.attention", "self"), _Ffn(f"{enc}layer.{i}.intermediate", f"{enc}layer.{i}.output")) for i in range(l_layers)]
         self.r = [(_Att(f"{enc}r_layers.{i}.attention", "self"), _Ffn(f"{enc}r_layers.{i}.intermediate", f"{enc}r_layers.{i}.output"))
@@ -87,23 +94,48 @@ class LXMERTTrainer:
             self._derived[key] = (w, b, w.t().contiguous())
         return self._derived[key]
 
+    # ---- matrix products: fp32 CUDA cores, or bf16 tensor cores with fp32 in / out ----
+    def _b16(self, key, make):
+        if key not in self._derived:
+            self._derived[key] = ops.cast_bf16(make().contiguous())
+        return self._derived[key]
+
+    def _mm(self, x, w, b, epilogue=L.EPI_BIAS, residual=None, wkey=None):
+        """epilogue(x · wᵀ + b [+ residual]) with w [N, K] fp32 (``wkey`` names its cached bf16 copy)."""
+        if self.gemm == "bf16" and w.shape[1] % 64 == 0 and x.shape[0] >= 64:
+            wb = self._b16(("b16", wkey), lambda: w)
+            return ops.linear_bf16(ops.cast_bf16(x.contiguous()), wb, b, epilogue=epilogue, residual=residual, out_dtype=torch.float32)
+        return ops.linear_f32(x, w, b, epilogue=epilogue, residual=residual)
+
+    def _wgrad(self, wname, dy, x):
+        """G[w] += dyᵀ · x, G[b] += colsum(dy)."""
+        gw, gb = self.g[wname + ".weight"], self.g[wname + ".bias"]
+        M = dy.shape[0]
+        if self.gemm == "bf16" and M % 64 == 0 and M >= 64 and x.shape[1] >= 64 and dy.shape[1] >= 64:
+            a = ops.cast_bf16(dy.t().contiguous())          # [N, M]: the product runs over the rows
+            bt = ops.cast_bf16(x.t().contiguous())          # [K, M]
+            ops.linear_bf16(a, bt, None, epilogue=L.EPI_RESID, residual=gw, out_dtype=torch.float32, out=gw)
+            ops.linear_wgrad_bias_(gb, dy)
+        else:
+            ops.linear_wgrad_(gw, gb, dy, x)
+
     # ---- forward blocks ----
     def _att_fwd(self, a, x_q, x_kv, B, Lq, Lk, mask, qkv_q=None, qkv_kv=None):
         w, b, _ = self._qkv(a)
-        qkv_q = ops.linear_f32(x_q, w, b) if qkv_q is None else qkv_q
+        qkv_q = self._mm(x_q, w, b, wkey=a.q) if qkv_q is None else qkv_q
         if qkv_kv is None:
-            qkv_kv = qkv_q if x_kv is x_q else ops.linear_f32(x_kv, w, b)
+            qkv_kv = qkv_q if x_kv is x_q else self._mm(x_kv, w, b, wkey=a.q)
         ctx = ops.attention(qkv_q, qkv_kv, B, Lq, Lk, key_mask=mask, heads=self.heads)
         wo, bo = self._w(a.out)
-        pre = ops.linear_f32(ctx, wo, bo, epilogue=L.EPI_RESID, residual=x_q)
+        pre = self._mm(ctx, wo, bo, epilogue=L.EPI_RESID, residual=x_q, wkey=a.out)
         y = ops.layernorm(pre, *self._w(a.ln), self.eps)
         return y, dict(x_q=x_q, qkv_q=qkv_q, qkv_kv=qkv_kv, ctx=ctx, pre=pre, B=B, Lq=Lq, Lk=Lk, mask=mask)
 
     def _ffn_fwd(self, f, x):
-        pg = ops.linear_f32(x, *self._w(f.inter))
+        pg = self._mm(x, *self._w(f.inter), wkey=f.inter)
         inter = ops.gelu_fwd(pg)
         wo, bo = self._w(f.out)
-        pre = ops.linear_f32(inter, wo, bo, epilogue=L.EPI_RESID, residual=x)
+        pre = self._mm(inter, wo, bo, epilogue=L.EPI_RESID, residual=x, wkey=f.out)
         return ops.layernorm(pre, *self._w(f.ln), self.eps), dict(x=x, pg=pg, inter=inter, pre=pre)
 
     def forward(self, feat, pos, ids, seg, mask):
@@ -120,7 +152,7 @@ class LXMERTTrainer:
         t["e_pre"] = (word[ids32.long()] + posemb[:Lt][None, :, :] + typeemb[seg32.long()]).view(B * Lt, -1).contiguous()
         lang = ops.embed_ln(ids32, seg32, word, posemb, typeemb, *self._w(e + "LayerNorm"), self.eps)
         v = P + "encoder.visn_fc."
-        t["pre_v"] = ops.linear_f32(feat2, *self._w(v + "visn_fc"))
+        t["pre_v"] = self._mm(feat2, *self._w(v + "visn_fc"), wkey=v + "visn_fc")
         t["pre_b"] = ops.linear_f32(pos2, *self._w(v + "box_fc"))
         visn = ops.visn_combine(t["pre_v"], pos2, *self._w(v + "box_fc"), *self._w(v + "visn_layer_norm"), *self._w(v + "box_layer_norm"), self.eps)
         t["l"], t["r"], t["x"] = [], [], []
@@ -135,7 +167,7 @@ class LXMERTTrainer:
         for w in self.x:
             c = w["cross"]
             wq, bq, _ = self._qkv(c)
-            qkv_l, qkv_v = ops.linear_f32(lang, wq, bq), ops.linear_f32(visn, wq, bq)
+            qkv_l, qkv_v = self._mm(lang, wq, bq, wkey=c.q), self._mm(visn, wq, bq, wkey=c.q)
             l1, tcl = self._att_fwd(c, lang, visn, B, Lt, V, None, qkv_q=qkv_l, qkv_kv=qkv_v)
             v1, tcv = self._att_fwd(c, visn, lang, B, V, Lt, mask32, qkv_q=qkv_v, qkv_kv=qkv_l)
             l2, tls = self._att_fwd(w["ls"], l1, l1, B, Lt, Lt, mask32)
@@ -154,7 +186,11 @@ class LXMERTTrainer:
 
     # ---- backward blocks (input gradient returned, parameter gradients accumulated into self.g) ----
     def _lin_wgrad(self, name, dy, x):
-        ops.linear_wgrad_(self.g[name + ".weight"], self.g[name + ".bias"], dy, x)
+        self._wgrad(name, dy, x)
+
+    def _dgrad(self, dy, name, wt, residual=None):
+        """dy · W (+ residual): W given as its transposed fp32 copy wt [K, N]."""
+        return self._mm(dy, wt, None, epilogue=L.EPI_RESID if residual is not None else L.EPI_BIAS, residual=residual, wkey=("t", name))
 
     def _ln_bwd(self, name, dy, x, scale=1.0):
         ops.layernorm_param_grad_(self.g[name + ".weight"], self.g[name + ".bias"], dy, x, self.eps, scale)
@@ -163,27 +199,27 @@ class LXMERTTrainer:
     def _ffn_bwd(self, f, tp, dy):
         d_pre = self._ln_bwd(f.ln, dy, tp["pre"])
         self._lin_wgrad(f.out, d_pre, tp["inter"])
-        d_pg = ops.gelu_bwd(ops.linear_f32(d_pre, self._wt(f.out)), tp["pg"])
+        d_pg = ops.gelu_bwd(self._dgrad(d_pre, f.out, self._wt(f.out)), tp["pg"])
         self._lin_wgrad(f.inter, d_pg, tp["x"])
-        return ops.linear_f32(d_pg, self._wt(f.inter), epilogue=L.EPI_RESID, residual=d_pre)
+        return self._dgrad(d_pg, f.inter, self._wt(f.inter), residual=d_pre)
 
     def _att_bwd(self, a, tp, dy, dqkv_q, dqkv_kv):
         d_pre = self._ln_bwd(a.ln, dy, tp["pre"])
         self._lin_wgrad(a.out, d_pre, tp["ctx"])
-        d_ctx = ops.linear_f32(d_pre, self._wt(a.out))
+        d_ctx = self._dgrad(d_pre, a.out, self._wt(a.out))
         ops.attention_bwd(tp["qkv_q"], tp["qkv_kv"], d_ctx, dqkv_q, dqkv_kv, tp["B"], tp["Lq"], tp["Lk"], key_mask=tp["mask"], heads=self.heads)
         return d_pre
 
     def _qkv_wgrad(self, a, dqkv, x):
         H = dqkv.shape[1] // 3
         for j, name in enumerate((a.q, a.k, a.v)):
-            ops.linear_wgrad_(self.g[name + ".weight"], self.g[name + ".bias"], dqkv[:, j * H:(j + 1) * H], x)
+            self._wgrad(name, dqkv[:, j * H:(j + 1) * H], x)
 
     def _self_att_bwd(self, a, tp, dy):
         dqkv = torch.empty_like(tp["qkv_q"])
         d_pre = self._att_bwd(a, tp, dy, dqkv, dqkv)
         self._qkv_wgrad(a, dqkv, tp["x_q"])
-        return ops.linear_f32(dqkv, self._qkv(a)[2], epilogue=L.EPI_RESID, residual=d_pre)
+        return self._dgrad(dqkv, "qkv:" + a.q, self._qkv(a)[2], residual=d_pre)
 
     def backward(self, dlogits):
         t = self.tape
@@ -211,8 +247,8 @@ class LXMERTTrainer:
             self._qkv_wgrad(c, dqkv_l, tp["cl"]["x_q"])                 # ONE module, both modalities: gradients add up
             self._qkv_wgrad(c, dqkv_v, tp["cv"]["x_q"])
             wt = self._qkv(c)[2]
-            dl = ops.linear_f32(dqkv_l, wt, epilogue=L.EPI_RESID, residual=d_pre_l)
-            dv = ops.linear_f32(dqkv_v, wt, epilogue=L.EPI_RESID, residual=d_pre_v)
+            dl = self._dgrad(dqkv_l, "qkv:" + c.q, wt, residual=d_pre_l)
+            dv = self._dgrad(dqkv_v, "qkv:" + c.q, wt, residual=d_pre_v)
         for (a, f), (ta, tf) in zip(reversed(self.r), reversed(t["r"])):
             dv = self._self_att_bwd(a, ta, self._ffn_bwd(f, tf, dv))
         for (a, f), (ta, tf) in zip(reversed(self.l), reversed(t["l"])):

@@ -26,7 +26,7 @@ def _dt(t: torch.Tensor) -> int:
     raise TypeError(f"unsupported dtype {t.dtype}")
 
 
-def linear_bf16(x, weight, bias=None, epilogue=L.EPI_BIAS, residual=None, out_dtype=torch.bfloat16):
+def linear_bf16(x, weight, bias=None, epilogue=L.EPI_BIAS, residual=None, out_dtype=torch.bfloat16, out=None):
     """``epilogue(x @ weight.T + bias [+ residual])`` on the tcgen05 tensor cores.
 
     x: [M, K] bf16 (row stride may exceed K), weight: [N, K] bf16 (nn.Linear layout), bias: [N] f32,
@@ -39,7 +39,10 @@ def linear_bf16(x, weight, bias=None, epilogue=L.EPI_BIAS, residual=None, out_dt
     M, K = x.shape
     N = weight.shape[0]
     assert weight.shape[1] == K
-    out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    else:  # caller-provided destination (may alias `residual`: an accumulating update)
+        assert out.shape == (M, N) and out.stride(1) == 1 and out.is_cuda
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
     ldr = 0
@@ -330,6 +333,13 @@ def linear_wgrad_(dw, db, dy, x):
     if db is not None:
         assert db.shape == (N,) and db.is_contiguous()
         L.check(lib.rgqa_colsum(L.current_stream_ptr(), L.ptr(dy), dy.stride(0), L.ptr(db), M, N), "rgqa_colsum")
+
+
+def linear_wgrad_bias_(db, dy):
+    """db [N] += column sums of dy [M, N] (row stride allowed)."""
+    _need_cuda(db, dy)
+    assert dy.dtype == db.dtype == torch.float32 and dy.stride(1) == 1 and db.is_contiguous() and db.shape == (dy.shape[1],)
+    L.check(L.load().rgqa_colsum(L.current_stream_ptr(), L.ptr(dy), dy.stride(0), L.ptr(db), dy.shape[0], dy.shape[1]), "rgqa_colsum")
 
 
 def layernorm_param_grad_(dgamma, dbeta, dy, x, eps=1e-12, scale=1.0):

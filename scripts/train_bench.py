@@ -16,7 +16,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 B, L, A, K = 64, 20, 1842, int(os.environ.get("STEPS", 4))
 sd = syn.lxmert_state_dict(variant="init")
-tr = LXMERTTrainer(sd, device=f"cuda:{local}", lr=1e-5, warmup=0.1, t_total=1000)
+tr = LXMERTTrainer(sd, device=f"cuda:{local}", lr=1e-5, warmup=0.1, t_total=1000, gemm=os.environ.get("GEMM", "fp32"))
 rng = random.Random(1 + rank)
 def batch(step):
     inp = syn.make_inputs(B, L, seed=10_000 * rank + step)
@@ -41,6 +41,6 @@ if world > 1:
     dist.all_gather(allc, chk)
     assert all(torch.equal(c, allc[0]) for c in allc), "ranks diverged"
 if rank == 0:
-    print(f"config 5, {world} rank(s): {dt*1e3:.0f} ms/step, {1/dt:.2f} steps/s, {world*B/dt:.0f} questions/s ({world*2*B/dt:.0f} rows/s); losses {[round(l, 2) for l in losses]}")
+    print(f"config 5 [gemm={tr.gemm}], {world} rank(s): {dt*1e3:.0f} ms/step, {1/dt:.2f} steps/s, {world*B/dt:.0f} questions/s ({world*2*B/dt:.0f} rows/s); losses {[round(l, 2) for l in losses]}")
 if world > 1:
     dist.destroy_process_group()

@@ -86,3 +86,32 @@ def test_three_training_steps_match_reference_trajectory(cuda_device):
         moved = float((ref - start).norm())
         assert moved > 0
         assert float((got - ref).norm()) <= 2e-3 * moved + 1e-7, (n, float((got - ref).norm()), moved)   # the UPDATE agrees to 0.2 %
+
+
+def test_mixed_precision_training_step_tracks_the_fp32_trajectory(cuda_device):
+    """gemm="bf16": forward / dgrad / wgrad matrix products on the tcgen05 tensor cores with bf16 operands (fp32 master weights,
+    activations, gradients, optimiser).  Not the reference's arithmetic: the same three steps must stay within bf16-operand noise
+    of the reference trajectory — loss 2e-3, gradient norm 2 %, watched gradients 5 % (relative L2), updates 10 %."""
+    from rgqa_b200.lxrt.trainer import LXMERTTrainer
+    z = np.load(os.path.join(GOLD, "train_steps.npz"))
+    layers = dict(l_layers=2, x_layers=1, r_layers=1)
+    sd = syn.lxmert_state_dict(variant="rich", **layers)
+    tr = LXMERTTrainer(sd, device=cuda_device, lr=1e-4, warmup=0.1, t_total=20, gemm="bf16", **layers)
+    watch = sorted(k[len("final:"):] for k in z.files if k.startswith("final:"))
+    cut = lambda t: t[:4] if t.numel() > 20000 else t
+    for step in range(3):
+        inp = syn.make_inputs(6, 20, seed=900 + step)
+        loss, norm = tr.train_step(inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"], torch.from_numpy(z[f"target{step}"]))
+        assert loss == pytest.approx(float(z[f"loss{step}"]), rel=2e-3), (step, loss)
+        assert norm == pytest.approx(float(z[f"norm{step}"]), rel=2e-2), (step, norm)
+        if step == 0:
+            for n in watch:
+                ref = torch.from_numpy(z["grad0:" + n])
+                if float(ref.norm()) == 0.0:
+                    continue
+                got = cut(tr.g[n]).cpu()
+                assert float((got - ref).norm() / ref.norm()) <= 5e-2, (n, float((got - ref).norm() / ref.norm()))
+    for n in watch:
+        ref, got, start = torch.from_numpy(z["final:" + n]), cut(tr.p[n]).cpu(), cut(sd[n])
+        moved = float((ref - start).norm())
+        assert float((got - ref).norm()) <= 0.1 * moved + 1e-7, (n, float((got - ref).norm()), moved)
