@@ -25,6 +25,13 @@ class _Lin:
     def __init__(self, w, b):
         self.w, self.b = w.contiguous(), b.contiguous()
         self.wt = w.t().contiguous()          # [K, N]: the dgrad GEMM  dX = dY · W  is  linear_f32(dY, W^T)
+        self._b16 = {}
+
+    def b16(self, transposed):
+        """bf16 copy of w (or of its transpose) for the tensor-core mode, made on first use."""
+        if transposed not in self._b16:
+            self._b16[transposed] = ops.cast_bf16(self.wt if transposed else self.w)
+        return self._b16[transposed]
 
 
 class _Att:
@@ -48,7 +55,11 @@ class _Ffn:
 class LXMERTInputGrad:
     """Taped fp32 forward + input-gradient backward.  ``state_dict``: the reference GQAModel's keys (fp32)."""
 
-    def __init__(self, state_dict, l_layers=9, x_layers=5, r_layers=5, heads=12, eps=1e-12, device="cuda:0"):
+    def __init__(self, state_dict, l_layers=9, x_layers=5, r_layers=5, heads=12, eps=1e-12, device="cuda:0", gemm="fp32"):
+        """``gemm="bf16"``: the encoder's matrix products (forward and dgrad) run on the tcgen05 tensor cores with bf16
+        operands cast on the fly, fp32 accumulation and fp32 activations / gradients everywhere else (mixed precision)."""
+        assert gemm in ("fp32", "bf16")
+        self.gemm = gemm
         dev = torch.device(device)
         sd = {k: v.detach().to(dev, torch.float32) for k, v in state_dict.items()}
         self.dev, self.heads, self.eps = dev, heads, eps
@@ -78,19 +89,28 @@ class LXMERTInputGrad:
         self.fc3 = _Lin(sd["logit_fc.3.weight"], sd["logit_fc.3.bias"])
         self.tape = None
 
+    def _mm(self, x, lin, transposed=False, epilogue=L.EPI_BIAS, residual=None):
+        """epilogue(x · Wᵀ + b [+ residual]) (forward) or x · W [+ residual] (``transposed``: the dgrad product)."""
+        w = lin.wt if transposed else lin.w
+        b = None if transposed else lin.b
+        if self.gemm == "bf16" and w.shape[1] % 64 == 0 and x.shape[0] >= 64:
+            return ops.linear_bf16(ops.cast_bf16(x.contiguous()), lin.b16(transposed), b, epilogue=epilogue, residual=residual,
+                                   out_dtype=torch.float32)
+        return ops.linear_f32(x, w, b, epilogue=epilogue, residual=residual)
+
     # ---- forward blocks (each returns its output and what its backward needs) ----
     def _att_fwd(self, w, x_q, x_kv, B, Lq, Lk, mask, qkv_q=None, qkv_kv=None):
-        qkv_q = ops.linear_f32(x_q, w.qkv.w, w.qkv.b) if qkv_q is None else qkv_q
-        qkv_kv = qkv_q if x_kv is x_q and qkv_kv is None else (ops.linear_f32(x_kv, w.qkv.w, w.qkv.b) if qkv_kv is None else qkv_kv)
+        qkv_q = self._mm(x_q, w.qkv) if qkv_q is None else qkv_q
+        qkv_kv = qkv_q if x_kv is x_q and qkv_kv is None else (self._mm(x_kv, w.qkv) if qkv_kv is None else qkv_kv)
         ctx = ops.attention(qkv_q, qkv_kv, B, Lq, Lk, key_mask=mask, heads=self.heads)
-        pre = ops.linear_f32(ctx, w.out.w, w.out.b, epilogue=L.EPI_RESID, residual=x_q)
+        pre = self._mm(ctx, w.out, epilogue=L.EPI_RESID, residual=x_q)
         y = ops.layernorm(pre, w.g, w.beta, self.eps)
         return y, dict(qkv_q=qkv_q, qkv_kv=qkv_kv, pre=pre, B=B, Lq=Lq, Lk=Lk, mask=mask)
 
     def _ffn_fwd(self, w, x):
-        pg = ops.linear_f32(x, w.inter.w, w.inter.b)
+        pg = self._mm(x, w.inter)
         inter = ops.gelu_fwd(pg)
-        pre = ops.linear_f32(inter, w.out.w, w.out.b, epilogue=L.EPI_RESID, residual=x)
+        pre = self._mm(inter, w.out, epilogue=L.EPI_RESID, residual=x)
         return ops.layernorm(pre, w.g, w.beta, self.eps), dict(pg=pg, pre=pre)
 
     def forward(self, feat, pos, ids, seg, mask):
@@ -104,7 +124,7 @@ class LXMERTInputGrad:
         pos2 = pos.to(dev, torch.float32).reshape(B * V, -1).contiguous()
         t = dict(B=B, V=V, L=Lt)
         lang = ops.embed_ln(ids32, seg32, self.word, self.posemb, self.typeemb, self.emb_g, self.emb_b, self.eps)
-        t["pre_v"] = ops.linear_f32(feat2, self.visn_fc.w, self.visn_fc.b)
+        t["pre_v"] = self._mm(feat2, self.visn_fc)
         t["pre_b"] = ops.linear_f32(pos2, self.box_fc.w, self.box_fc.b)
         visn = ops.visn_combine(t["pre_v"], pos2, self.box_fc.w, self.box_fc.b, self.visn_g, self.visn_b, self.box_g, self.box_b, self.eps)
         for a, f in self.l:                                   # language only: no tape needed
@@ -118,8 +138,8 @@ class LXMERTInputGrad:
         t["x"] = []
         for w in self.x:
             c = w["cross"]
-            qkv_l = ops.linear_f32(lang, c.qkv.w, c.qkv.b)
-            qkv_v = ops.linear_f32(visn, c.qkv.w, c.qkv.b)
+            qkv_l = self._mm(lang, c.qkv)
+            qkv_v = self._mm(visn, c.qkv)
             l1, tcl = self._att_fwd(c, lang, visn, B, Lt, V, None, qkv_q=qkv_l, qkv_kv=qkv_v)        # lang queries, visual keys
             v1, tcv = self._att_fwd(c, visn, lang, B, V, Lt, mask32, qkv_q=qkv_v, qkv_kv=qkv_l)      # visual queries, lang keys
             l2, tls = self._att_fwd(w["ls"], l1, l1, B, Lt, Lt, mask32)
@@ -140,22 +160,22 @@ class LXMERTInputGrad:
     # ---- backward blocks ----
     def _ffn_bwd(self, w, tp, dy):
         d_pre = ops.layernorm_bwd(dy, tp["pre"], w.g, eps=self.eps)
-        d_inter = ops.linear_f32(d_pre, w.out.wt)
+        d_inter = self._mm(d_pre, w.out, transposed=True)
         d_pg = ops.gelu_bwd(d_inter, tp["pg"])
-        return ops.linear_f32(d_pg, w.inter.wt, epilogue=L.EPI_RESID, residual=d_pre)
+        return self._mm(d_pg, w.inter, transposed=True, epilogue=L.EPI_RESID, residual=d_pre)
 
     def _att_bwd(self, w, tp, dy, dqkv_q, dqkv_kv):
         """Gradient of one attention block w.r.t. its query-side input through the residual and the output projection;
         dQ / dK / dV land in the given fused gradient buffers (the caller turns those into input gradients)."""
         d_pre = ops.layernorm_bwd(dy, tp["pre"], w.g, eps=self.eps)
-        d_ctx = ops.linear_f32(d_pre, w.out.wt)
+        d_ctx = self._mm(d_pre, w.out, transposed=True)
         ops.attention_bwd(tp["qkv_q"], tp["qkv_kv"], d_ctx, dqkv_q, dqkv_kv, tp["B"], tp["Lq"], tp["Lk"], key_mask=tp["mask"], heads=self.heads)
         return d_pre
 
     def _self_att_bwd(self, w, tp, dy):
         dqkv = torch.empty_like(tp["qkv_q"])
         d_pre = self._att_bwd(w, tp, dy, dqkv, dqkv)
-        return ops.linear_f32(dqkv, w.qkv.wt, epilogue=L.EPI_RESID, residual=d_pre)
+        return self._mm(dqkv, w.qkv, transposed=True, epilogue=L.EPI_RESID, residual=d_pre)
 
     def backward(self, dlogits=None, dpooled=None):
         """(d loss / d feat [B,36,2048], d loss / d pos [B,36,4]) for the last forward, given d loss / d logits and / or
@@ -186,13 +206,13 @@ class LXMERTInputGrad:
             dqkv_v = torch.empty_like(tp["cv"]["qkv_q"])
             d_pre_l = self._att_bwd(c, tp["cl"], dl1, dqkv_l, dqkv_v)
             d_pre_v = self._att_bwd(c, tp["cv"], dv1, dqkv_v, dqkv_l)
-            dl = ops.linear_f32(dqkv_l, c.qkv.wt, epilogue=L.EPI_RESID, residual=d_pre_l)
-            dv = ops.linear_f32(dqkv_v, c.qkv.wt, epilogue=L.EPI_RESID, residual=d_pre_v)
+            dl = self._mm(dqkv_l, c.qkv, transposed=True, epilogue=L.EPI_RESID, residual=d_pre_l)
+            dv = self._mm(dqkv_v, c.qkv, transposed=True, epilogue=L.EPI_RESID, residual=d_pre_v)
         for (a, f), (ta, tf) in zip(reversed(self.r), reversed(t["r"])):
             dv = self._self_att_bwd(a, ta, self._ffn_bwd(f, tf, dv))
         # VisualFeatEncoder: output = (LN(visn_fc(feat)) + LN(box_fc(pos))) / 2
         d_pre_v = ops.layernorm_bwd(dv, t["pre_v"], self.visn_g, eps=self.eps, scale=0.5)
         d_pre_b = ops.layernorm_bwd(dv, t["pre_b"], self.box_g, eps=self.eps, scale=0.5)
-        dfeat = ops.linear_f32(d_pre_v, self.visn_fc.wt).view(B, V, -1)
+        dfeat = self._mm(d_pre_v, self.visn_fc, transposed=True).view(B, V, -1)
         dpos = ops.linear_f32(d_pre_b, self.box_fc.wt).view(B, V, -1)
         return dfeat, dpos

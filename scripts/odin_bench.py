@@ -6,7 +6,7 @@ from rgqa_b200 import synthetic as syn
 from rgqa_b200.lxrt.input_grad import LXMERTInputGrad
 from rgqa_b200.tasks.gqa_odin import odin_scores
 sd = syn.lxmert_state_dict(variant="init")
-ig = LXMERTInputGrad(sd)
+ig = LXMERTInputGrad(sd, gemm=os.environ.get("GEMM", "fp32"))
 for B in (32, 128):
     inp = syn.make_inputs(B, 20, seed=1)
     args = [inp[k].to(ig.dev) for k in ("feat", "pos", "ids", "seg", "mask")]
@@ -15,4 +15,4 @@ for B in (32, 128):
     K = 5
     for _ in range(K): odin_scores(ig, *args, 1.0, 1e-4)
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / K
-    print(f"ODIN B={B}: {dt*1e3:.1f} ms/batch  {B/dt:.0f} q/s (fp32 CUDA-core path)")
+    print(f"ODIN B={B}: {dt*1e3:.1f} ms/batch  {B/dt:.0f} q/s ({ig.gemm} matrix products)")

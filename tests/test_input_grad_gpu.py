@@ -101,3 +101,21 @@ def test_full_depth_lxmert_input_gradients(cuda_device):
     dfeat, dpos = ig.backward(dlogits=wl)
     assert _rel(dfeat.cpu(), feats.grad) <= 5e-4, _rel(dfeat.cpu(), feats.grad)
     assert _rel(dpos.cpu(), boxes.grad) <= 5e-4, _rel(dpos.cpu(), boxes.grad)
+
+
+def test_mixed_precision_input_gradients_and_odin(cuda_device):
+    """gemm="bf16" (tensor-core matrix products, fp32 elsewhere): the input gradient stays within bf16-operand noise of autograd
+    (5 % relative L2, >= 97 % sign agreement on the significant entries) and the ODIN scores within 1e-2 of the fp32 oracle."""
+    from oracle import odin_oracle as OO
+    from rgqa_b200.lxrt.input_grad import LXMERTInputGrad
+    from rgqa_b200.tasks.gqa_odin import odin_scores
+    sd = syn.lxmert_state_dict(variant="rich", **LAYERS)
+    ig = LXMERTInputGrad(sd, device=cuda_device, gemm="bf16", **LAYERS)
+    inp = syn.make_inputs(8, 20, seed=21)            # 160 / 288 token rows: above the tensor-core path's 64-row minimum
+    ref_s, ref_l, ref_gf, ref_gb = OO.odin(sd, inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"], 1.0, 1e-3)
+    s, l, gf, gb = odin_scores(ig, inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"], 1.0, 1e-3)
+    assert _rel(gf.cpu(), ref_gf) <= 5e-2 and _rel(gb.cpu(), ref_gb) <= 5e-2, (_rel(gf.cpu(), ref_gf), _rel(gb.cpu(), ref_gb))
+    big = ref_gf.abs() > 1e-2 * ref_gf.abs().max()
+    assert (torch.sign(gf.cpu())[big] == torch.sign(ref_gf)[big]).float().mean().item() >= 0.97
+    assert torch.equal(l.cpu().long(), ref_l)
+    torch.testing.assert_close(s.cpu(), ref_s, rtol=1e-2, atol=1e-3)
