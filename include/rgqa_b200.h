@@ -190,7 +190,17 @@ int rgqa_tanh_bwd(void* stream, const float* dy, const float* y, float* dx, int6
  * of the three operands written to dq / dk / dv (same [row, head*64] layout, own strides).  Lq, Lk <= 64. */
 int rgqa_attention_bwd(void* stream, const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                        const int32_t* key_mask, const float* dctx, int64_t ldo, float* dq, int64_t lddq, float* dk, int64_t lddk,
-                       float* dv, int64_t lddv, int B, int Lq, int Lk, int heads);
+                       float* dv, int64_t lddv, int B, int Lq, int Lk, int heads, float dropout_p, uint64_t seed);
+/* Training-mode dropout (the reference trains with p = 0.1: hidden_dropout_prob / attention_probs_dropout_prob of BertConfig).
+ * Masks come from a counter-based generator keyed by (seed, element index): the backward passes regenerate them, nothing is stored;
+ * they are NOT torch's masks, so parity with the reference under dropout is statistical only.
+ *  - rgqa_attention_dropout: rgqa_attention (fp32) with dropout on the attention probabilities (modeling.py:341); pass the same
+ *    (dropout_p, seed) to rgqa_attention_bwd.
+ *  - rgqa_dropout_add: y = dropout(x) [+ resid], n elements; the backward of the dropout is the same call on the gradient. */
+int rgqa_attention_dropout(void* stream, const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                           const int32_t* key_mask, float* out, int64_t ldo, int B, int Lq, int Lk, int heads, float dropout_p,
+                           uint64_t seed);
+int rgqa_dropout_add(void* stream, const float* x, const float* resid, float* y, int64_t n, float p, uint64_t seed);
 /* ---- weight-gradient kernels, fp32 path (the parameter half of loss.backward(), src/tasks/gqa_conf.py:196).  Every one of
  * them ADDS to its output; the caller zeroes the gradient buffers once per step.  Orchestration: rgqa_b200/lxrt/trainer.py. */
 /* dW[N, K] += dY[M, N]^T · X[M, K]  (nn.Linear weight; row strides lda / ldb / ldo). */

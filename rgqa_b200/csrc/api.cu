@@ -1441,9 +1441,18 @@ int rgqa_tanh_bwd(void* stream, const float* dy, const float* y, float* dx, int6
 }
 int rgqa_attention_bwd(void* stream, const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                        const int32_t* key_mask, const float* dctx, int64_t ldo, float* dq, int64_t lddq, float* dk, int64_t lddk,
-                       float* dv, int64_t lddv, int B, int Lq, int Lk, int heads) {
+                       float* dv, int64_t lddv, int B, int Lq, int Lk, int heads, float dropout_p, uint64_t seed) {
   return attention_bwd(static_cast<cudaStream_t>(stream), q, ldq, k, ldk, v, ldv, key_mask, dctx, ldo, dq, lddq, dk, lddk, dv, lddv,
-                       B, Lq, Lk, heads);
+                       B, Lq, Lk, heads, dropout_p, seed);
+}
+int rgqa_attention_dropout(void* stream, const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                           const int32_t* key_mask, float* out, int64_t ldo, int B, int Lq, int Lk, int heads, float dropout_p,
+                           uint64_t seed) {
+  return attention(static_cast<cudaStream_t>(stream), DT_F32, q, ldq, k, ldk, v, ldv, key_mask, out, ldo, B, Lq, Lk, heads, dropout_p,
+                   seed);
+}
+int rgqa_dropout_add(void* stream, const float* x, const float* resid, float* y, int64_t n, float p, uint64_t seed) {
+  return dropout_add(static_cast<cudaStream_t>(stream), x, resid, y, n, p, seed);
 }
 int rgqa_gemm_f32_tn(void* stream, const float* A, int64_t lda, const float* B, int64_t ldb, float* out, int64_t ldo, int M, int N,
                      int K) {

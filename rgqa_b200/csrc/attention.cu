@@ -60,7 +60,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 attention_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__ k, long long ldk,
                  const T* __restrict__ v, long long ldv, const int32_t* __restrict__ key_mask, T* __restrict__ out,
-                 long long ldo, int Lq, int Lk, int heads) {
+                 long long ldo, int Lq, int Lk, int heads, float drop_p, unsigned long long drop_seed) {
   extern __shared__ float sm[];
   float* Ks = sm;                   // [Lk][64]
   float* Vs = Ks + Lk * HD;         // [Lk][64]
@@ -118,8 +118,11 @@ attention_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__ k
     float sum = 0.f;
     for (int j = 0; j < Lk; ++j) {
       const float d = Ps[j * kThreads + tid] - mx;
-      const float pj = (sizeof(T) == 4) ? expf(d) : __expf(d);
+      float pj = (sizeof(T) == 4) ? expf(d) : __expf(d);
       sum += pj;
+      // attention-probability dropout (training, modeling.py:341): applied to the normalised row, i.e. after the sum
+      if (drop_p > 0.f)
+        pj = dropout_keep(drop_seed, (static_cast<unsigned long long>(blockIdx.x) * Lq + tid) * Lk + j, drop_p) ? pj / (1.0f - drop_p) : 0.f;
       const float4* vr = reinterpret_cast<const float4*>(Vs + j * HD);
 #pragma unroll
       for (int c = 0; c < HD / 4; ++c) {
@@ -719,7 +722,8 @@ int attention_planes(cudaStream_t stream, const void* planes, long long plane_ro
 
 int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, const void* k, long long ldk,
               const void* v, long long ldv, const int32_t* key_mask, void* out, long long ldo, int B, int Lq,
-              int Lk, int heads) {
+              int Lk, int heads, float drop_p, unsigned long long drop_seed) {
+  RGQA_CHECK(drop_p == 0.f || (dtype == DT_F32 && drop_p > 0.f && drop_p < 1.f), "attention: dropout is an fp32 training feature");
   RGQA_CHECK(B > 0 && heads > 0, "attention: empty batch");
   RGQA_CHECK(Lq >= 1 && Lq <= MAXL && Lk >= 1 && Lk <= MAXL, "attention: Lq=%d Lk=%d out of range [1,%d]", Lq, Lk,
              MAXL);
@@ -738,7 +742,7 @@ int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, cons
     }
     attention_kernel<float><<<grid, kThreads, smem, stream>>>(
         static_cast<const float*>(q), ldq, static_cast<const float*>(k), ldk, static_cast<const float*>(v), ldv,
-        key_mask, static_cast<float*>(out), ldo, Lq, Lk, heads);
+        key_mask, static_cast<float*>(out), ldo, Lq, Lk, heads, drop_p, drop_seed);
   } else {
     const __nv_bfloat16* qb = static_cast<const __nv_bfloat16*>(q);
     const __nv_bfloat16* kb = static_cast<const __nv_bfloat16*>(k);

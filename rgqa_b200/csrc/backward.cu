@@ -76,8 +76,15 @@ __global__ void __launch_bounds__(256)
 attention_bwd_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k, long long ldk,
                      const float* __restrict__ v, long long ldv, const int32_t* __restrict__ key_mask,
                      const float* __restrict__ dctx, long long ldo, float* __restrict__ dq, long long lddq,
-                     float* __restrict__ dk, long long lddk, float* __restrict__ dv, long long lddv, int Lq, int Lk, int heads) {
+                     float* __restrict__ dk, long long lddk, float* __restrict__ dv, long long lddv, int Lq, int Lk, int heads,
+                     float drop_p, unsigned long long drop_seed) {
   extern __shared__ float sm_bwd[];
+  // attention-probability dropout of the forward (same counter-based mask): O = (P o M) V with M = keep / (1 - p)
+  const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  auto mask_at = [&](int i, int j) -> float {
+    if (drop_p <= 0.f) return 1.0f;
+    return dropout_keep(drop_seed, (static_cast<unsigned long long>(blockIdx.x) * Lq + i) * Lk + j, drop_p) ? keep_scale : 0.f;
+  };
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   float* Qs = sm_bwd;                 // [Lq][65]
   float* Ks = Qs + Lq * 65;           // [Lk][65]
@@ -109,7 +116,7 @@ attention_bwd_kernel(const float* __restrict__ q, long long ldq, const float* __
     s *= 0.125f;
     if (key_mask != nullptr && key_mask[b * Lk + j] == 0) s += -10000.0f;
     P[i * (Lk + 1) + j] = s;
-    dS[i * (Lk + 1) + j] = dp;
+    dS[i * (Lk + 1) + j] = dp * mask_at(i, j);   // d loss / d P (the gradient reaches P through the dropout mask)
   }
   __syncthreads();
   // row softmax, then dS = P (dP - sum_j dP P): one warp per row
@@ -149,10 +156,24 @@ attention_bwd_kernel(const float* __restrict__ q, long long ldq, const float* __
     float a = 0.f, g = 0.f;
     for (int i = 0; i < Lq; ++i) {
       a = fmaf(dS[i * (Lk + 1) + j], Qs[i * 65 + c], a);
-      g = fmaf(P[i * (Lk + 1) + j], Os[i * 65 + c], g);
+      g = fmaf(P[i * (Lk + 1) + j] * mask_at(i, j), Os[i * 65 + c], g);
     }
     dk[(static_cast<long long>(b) * Lk + j) * lddk + h * HD + c] = a * 0.125f;
     dv[(static_cast<long long>(b) * Lk + j) * lddv + h * HD + c] = g;
+  }
+}
+
+// y = dropout(x) (+ resid): BertEmbeddings / BertAttOutput / BertOutput / VisualFeatEncoder dropout sites (modeling.py:291, :359,
+// :413, :516); the backward of the dropout itself is the same call on the gradient (same seed -> same mask)
+__global__ void __launch_bounds__(256)
+dropout_add_kernel(const float* __restrict__ x, const float* __restrict__ resid, float* __restrict__ y, long long n, float p,
+                   unsigned long long seed) {
+  const float scale = 1.0f / (1.0f - p);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = dropout_keep(seed, static_cast<unsigned long long>(i), p) ? x[i] * scale : 0.f;
+    if (resid != nullptr) v += resid[i];
+    y[i] = v;
   }
 }
 
@@ -192,10 +213,19 @@ int tanh_bwd(cudaStream_t stream, const float* dy, const float* y, float* dx, lo
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
 }
+int dropout_add(cudaStream_t stream, const float* x, const float* resid, float* y, long long n, float p, unsigned long long seed) {
+  RGQA_CHECK(x && y && n > 0 && p >= 0.f && p < 1.f, "dropout_add: bad arguments");
+  dropout_add_kernel<<<ew_grid(n), 256, 0, stream>>>(x, resid, y, n, p, seed);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 int attention_bwd(cudaStream_t stream, const float* q, long long ldq, const float* k, long long ldk, const float* v,
                   long long ldv, const int32_t* key_mask, const float* dctx, long long ldo, float* dq, long long lddq, float* dk,
-                  long long lddk, float* dv, long long lddv, int B, int Lq, int Lk, int heads) {
+                  long long lddk, float* dv, long long lddv, int B, int Lq, int Lk, int heads, float drop_p,
+                  unsigned long long drop_seed) {
   RGQA_CHECK(q && k && v && dctx && dq && dk && dv, "attention_bwd: null argument");
+  RGQA_CHECK(drop_p >= 0.f && drop_p < 1.f, "attention_bwd: dropout probability out of range");
   RGQA_CHECK(B > 0 && heads > 0 && Lq >= 1 && Lq <= 64 && Lk >= 1 && Lk <= 64, "attention_bwd: Lq=%d Lk=%d out of range [1,64]", Lq, Lk);
   const size_t smem = (static_cast<size_t>(2 * Lq + 2 * Lk) * 65 + 2 * static_cast<size_t>(Lq) * (Lk + 1)) * sizeof(float);
   static bool cfg = false;
@@ -204,7 +234,7 @@ int attention_bwd(cudaStream_t stream, const float* q, long long ldq, const floa
     cfg = true;
   }
   attention_bwd_kernel<<<B * heads, 256, smem, stream>>>(q, ldq, k, ldk, v, ldv, key_mask, dctx, ldo, dq, lddq, dk, lddk, dv, lddv,
-                                                         Lq, Lk, heads);
+                                                         Lq, Lk, heads, drop_p, drop_seed);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;

@@ -83,6 +83,16 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// Counter-based dropout mask (training step only): element idx of the site identified by `seed` is kept with probability
+// 1 - p.  splitmix64 of (seed, idx): forward and backward regenerate the same mask, nothing is stored.
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, float p) {
+  unsigned long long z = seed + (idx + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<float>(z >> 40) * (1.0f / 16777216.0f) >= p;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

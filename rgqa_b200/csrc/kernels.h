@@ -79,7 +79,8 @@ int num_sms();
 // or nullptr; masked keys get the reference's additive -10000 (modeling.py:865), not -inf.
 int attention(cudaStream_t stream, int dtype, const void* q, long long ldq, const void* k, long long ldk,
               const void* v, long long ldv, const int32_t* key_mask, void* out, long long ldo, int B, int Lq,
-              int Lk, int heads);
+              int Lk, int heads, float drop_p = 0.f,
+              unsigned long long drop_seed = 0)  /* drop_p > 0: attention-probability dropout (fp32 training step) */;
 
 // ---- row-wise ops ------------------------------------------------------------------------------
 // LN(word[ids] + pos[0..L) + type[seg]) (modeling.py:278-292); tables and gamma/beta fp32.
@@ -123,7 +124,9 @@ int gelu_bwd(cudaStream_t stream, const float* dy, const float* x, float* dx, lo
 int tanh_bwd(cudaStream_t stream, const float* dy, const float* y, float* dx, long long n);
 int attention_bwd(cudaStream_t stream, const float* q, long long ldq, const float* k, long long ldk, const float* v,
                   long long ldv, const int32_t* key_mask, const float* dctx, long long ldo, float* dq, long long lddq, float* dk,
-                  long long lddk, float* dv, long long lddv, int B, int Lq, int Lk, int heads);
+                  long long lddk, float* dv, long long lddv, int B, int Lq, int Lk, int heads, float drop_p = 0.f,
+                  unsigned long long drop_seed = 0);
+int dropout_add(cudaStream_t stream, const float* x, const float* resid, float* y, long long n, float p, unsigned long long seed);
 // weight-gradient kernels (backward.cu); all ACCUMULATE into their outputs
 int gemm_f32_tn(cudaStream_t stream, const float* A, long long lda, const float* B, long long ldb, float* out, long long ldo, int M,
                 int N, int K);

@@ -9,9 +9,10 @@ cores); every operator is a kernel of this package behind the C ABI, PyTorch hol
 * backward = the dgrad chain of ``input_grad.py`` extended down through the nine language layers and the embeddings, plus the
   weight gradients (``rgqa_gemm_f32_tn``, ``rgqa_colsum``, ``rgqa_ln_param_grad``, ``rgqa_embedding_scatter``), accumulated
   straight into the flat gradient buffer under the reference's parameter names;
-* **dropout is not implemented** (the reference trains with p = 0.1, ``modeling.py`` BertConfig): this is the "dropout off"
-  configuration SURVEY §8(d) config 5 asks parity for.  The golden trajectory it is tested against comes from the UNMODIFIED
-  reference modules + the reference's own BertAdam with both dropout probabilities set to 0.
+* ``dropout=0`` (default) is the "dropout off" configuration SURVEY §8(d) config 5 asks parity for: the golden trajectory comes
+  from the UNMODIFIED reference modules + the reference's own BertAdam with both dropout probabilities set to 0.  ``dropout=0.1``
+  is the reference's training configuration with this package's counter-based masks (regenerated in the backward, never stored;
+  not torch's random stream, so parity under dropout is statistical).
 """
 from __future__ import annotations
 
@@ -39,14 +40,18 @@ class _Ffn:
 
 class LXMERTTrainer:
     def __init__(self, state_dict, l_layers=9, x_layers=5, r_layers=5, heads=12, eps=1e-12, device="cuda:0", lr=5e-5, warmup=0.1,
-                 t_total=-1, schedule="warmup_linear", b1=0.9, b2=0.999, e=1e-6, weight_decay=0.01, clip_norm=5.0, gemm="fp32"):
+                 t_total=-1, schedule="warmup_linear", b1=0.9, b2=0.999, e=1e-6, weight_decay=0.01, clip_norm=5.0, gemm="fp32",
+                 dropout=0.0, seed=9595):
         """``gemm="bf16"``: the large matrix products (forward, dgrad and wgrad of every nn.Linear with K a multiple of 64)
         run on the tcgen05 tensor cores with bf16 operands cast on the fly and fp32 accumulation / outputs; master weights,
         activations, gradients and the optimiser stay fp32 (mixed precision; not the reference's arithmetic — parity with
         the fp32 trajectory holds to ~1e-2, see tests/test_train_gpu.py)."""
-        assert gemm in ("fp32", "bf16")
+        assert gemm in ("fp32", "bf16") and 0.0 <= dropout < 1.0
         dev = torch.device(device)
         self.gemm = gemm
+        # dropout > 0: the reference's training-mode dropout sites (embeddings, attention probabilities, the two output
+        # projections of every block, the visual feature encoder) with this package's counter-based masks (not torch's)
+        self.dropout, self.seed, self._site = dropout, seed, 0
         self.dev, self.heads, self.eps, self.clip_norm = dev, heads, eps, clip_norm
         self.hp = dict(lr=lr, warmup=warmup, t_total=t_total, schedule=schedule, b1=b1, b2=b2, e=e, weight_decay=weight_decay)
         self.step_count = 0
@@ -119,24 +124,40 @@ class LXMERTTrainer:
         else:
             ops.linear_wgrad_(gw, gb, dy, x)
 
+    def _next_seed(self):
+        """A fresh mask stream per dropout site and optimisation step."""
+        self._site += 1
+        return (self.seed * 1_000_003 + self.step_count) * 4096 + self._site
+
     # ---- forward blocks ----
     def _att_fwd(self, a, x_q, x_kv, B, Lq, Lk, mask, qkv_q=None, qkv_kv=None):
         w, b, _ = self._qkv(a)
         qkv_q = self._mm(x_q, w, b, wkey=a.q) if qkv_q is None else qkv_q
         if qkv_kv is None:
             qkv_kv = qkv_q if x_kv is x_q else self._mm(x_kv, w, b, wkey=a.q)
-        ctx = ops.attention(qkv_q, qkv_kv, B, Lq, Lk, key_mask=mask, heads=self.heads)
         wo, bo = self._w(a.out)
-        pre = self._mm(ctx, wo, bo, epilogue=L.EPI_RESID, residual=x_q, wkey=a.out)
+        s_att = s_out = 0
+        if self.dropout > 0:
+            s_att, s_out = self._next_seed(), self._next_seed()
+            ctx = ops.attention_dropout(qkv_q, qkv_kv, B, Lq, Lk, key_mask=mask, heads=self.heads, p=self.dropout, seed=s_att)
+            pre = ops.dropout_add(self._mm(ctx, wo, bo, wkey=a.out), x_q, self.dropout, s_out)       # dense -> dropout -> + input
+        else:
+            ctx = ops.attention(qkv_q, qkv_kv, B, Lq, Lk, key_mask=mask, heads=self.heads)
+            pre = self._mm(ctx, wo, bo, epilogue=L.EPI_RESID, residual=x_q, wkey=a.out)
         y = ops.layernorm(pre, *self._w(a.ln), self.eps)
-        return y, dict(x_q=x_q, qkv_q=qkv_q, qkv_kv=qkv_kv, ctx=ctx, pre=pre, B=B, Lq=Lq, Lk=Lk, mask=mask)
+        return y, dict(x_q=x_q, qkv_q=qkv_q, qkv_kv=qkv_kv, ctx=ctx, pre=pre, B=B, Lq=Lq, Lk=Lk, mask=mask, s_att=s_att, s_out=s_out)
 
     def _ffn_fwd(self, f, x):
         pg = self._mm(x, *self._w(f.inter), wkey=f.inter)
         inter = ops.gelu_fwd(pg)
         wo, bo = self._w(f.out)
-        pre = self._mm(inter, wo, bo, epilogue=L.EPI_RESID, residual=x, wkey=f.out)
-        return ops.layernorm(pre, *self._w(f.ln), self.eps), dict(x=x, pg=pg, inter=inter, pre=pre)
+        s_out = 0
+        if self.dropout > 0:
+            s_out = self._next_seed()
+            pre = ops.dropout_add(self._mm(inter, wo, bo, wkey=f.out), x, self.dropout, s_out)
+        else:
+            pre = self._mm(inter, wo, bo, epilogue=L.EPI_RESID, residual=x, wkey=f.out)
+        return ops.layernorm(pre, *self._w(f.ln), self.eps), dict(x=x, pg=pg, inter=inter, pre=pre, s_out=s_out)
 
     def forward(self, feat, pos, ids, seg, mask):
         dev = self.dev
@@ -150,11 +171,18 @@ class LXMERTTrainer:
         t = dict(B=B, V=V, L=Lt, ids=ids32.view(-1), seg=seg32.view(-1), feat2=feat2, pos2=pos2)
         # BertEmbeddings (:278-292); the pre-LayerNorm sum is re-formed with tensor indexing for the LayerNorm backward
         t["e_pre"] = (word[ids32.long()] + posemb[:Lt][None, :, :] + typeemb[seg32.long()]).view(B * Lt, -1).contiguous()
+        self._site = 0
         lang = ops.embed_ln(ids32, seg32, word, posemb, typeemb, *self._w(e + "LayerNorm"), self.eps)
+        if self.dropout > 0:
+            t["s_emb"] = self._next_seed()
+            lang = ops.dropout_add(lang, None, self.dropout, t["s_emb"])
         v = P + "encoder.visn_fc."
         t["pre_v"] = self._mm(feat2, *self._w(v + "visn_fc"), wkey=v + "visn_fc")
         t["pre_b"] = ops.linear_f32(pos2, *self._w(v + "box_fc"))
         visn = ops.visn_combine(t["pre_v"], pos2, *self._w(v + "box_fc"), *self._w(v + "visn_layer_norm"), *self._w(v + "box_layer_norm"), self.eps)
+        if self.dropout > 0:
+            t["s_visn"] = self._next_seed()
+            visn = ops.dropout_add(visn, None, self.dropout, t["s_visn"])
         t["l"], t["r"], t["x"] = [], [], []
         for a, f in self.l:
             lang, ta = self._att_fwd(a, lang, lang, B, Lt, Lt, mask32)
@@ -198,16 +226,19 @@ class LXMERTTrainer:
 
     def _ffn_bwd(self, f, tp, dy):
         d_pre = self._ln_bwd(f.ln, dy, tp["pre"])
-        self._lin_wgrad(f.out, d_pre, tp["inter"])
-        d_pg = ops.gelu_bwd(self._dgrad(d_pre, f.out, self._wt(f.out)), tp["pg"])
+        d_h = ops.dropout_add(d_pre, None, self.dropout, tp["s_out"]) if tp["s_out"] else d_pre    # through the output dropout
+        self._lin_wgrad(f.out, d_h, tp["inter"])
+        d_pg = ops.gelu_bwd(self._dgrad(d_h, f.out, self._wt(f.out)), tp["pg"])
         self._lin_wgrad(f.inter, d_pg, tp["x"])
         return self._dgrad(d_pg, f.inter, self._wt(f.inter), residual=d_pre)
 
     def _att_bwd(self, a, tp, dy, dqkv_q, dqkv_kv):
         d_pre = self._ln_bwd(a.ln, dy, tp["pre"])
-        self._lin_wgrad(a.out, d_pre, tp["ctx"])
-        d_ctx = self._dgrad(d_pre, a.out, self._wt(a.out))
-        ops.attention_bwd(tp["qkv_q"], tp["qkv_kv"], d_ctx, dqkv_q, dqkv_kv, tp["B"], tp["Lq"], tp["Lk"], key_mask=tp["mask"], heads=self.heads)
+        d_h = ops.dropout_add(d_pre, None, self.dropout, tp["s_out"]) if tp["s_out"] else d_pre
+        self._lin_wgrad(a.out, d_h, tp["ctx"])
+        d_ctx = self._dgrad(d_h, a.out, self._wt(a.out))
+        ops.attention_bwd(tp["qkv_q"], tp["qkv_kv"], d_ctx, dqkv_q, dqkv_kv, tp["B"], tp["Lq"], tp["Lk"], key_mask=tp["mask"], heads=self.heads,
+                          p=self.dropout if tp["s_att"] else 0.0, seed=tp["s_att"])
         return d_pre
 
     def _qkv_wgrad(self, a, dqkv, x):
@@ -254,6 +285,9 @@ class LXMERTTrainer:
         for (a, f), (ta, tf) in zip(reversed(self.l), reversed(t["l"])):
             dl = self._self_att_bwd(a, ta, self._ffn_bwd(f, tf, dl))
         v = P + "encoder.visn_fc."
+        if self.dropout > 0:
+            dv = ops.dropout_add(dv, None, self.dropout, t["s_visn"])
+            dl = ops.dropout_add(dl, None, self.dropout, t["s_emb"])
         d_pre_v = self._ln_bwd(v + "visn_layer_norm", dv, t["pre_v"], scale=0.5)
         d_pre_b = self._ln_bwd(v + "box_layer_norm", dv, t["pre_b"], scale=0.5)
         self._lin_wgrad(v + "visn_fc", d_pre_v, t["feat2"])

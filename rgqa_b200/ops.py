@@ -304,7 +304,29 @@ def tanh_bwd(dy, y):
     return dx
 
 
-def attention_bwd(qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv, B, Lq, Lk, key_mask=None, heads=12):
+def attention_dropout(qkv_q, qkv_kv, B, Lq, Lk, key_mask=None, heads=12, p=0.1, seed=0):
+    """:func:`attention` (fp32) with dropout on the attention probabilities (training step); pass (p, seed) to the backward."""
+    _need_cuda(qkv_q, qkv_kv, key_mask)
+    H = heads * 64
+    assert qkv_q.dtype == qkv_kv.dtype == torch.float32 and qkv_q.is_contiguous() and qkv_kv.is_contiguous()
+    out = torch.empty((B * Lq, H), dtype=torch.float32, device=qkv_q.device)
+    L.check(L.load().rgqa_attention_dropout(L.current_stream_ptr(), L.ptr(qkv_q), 3 * H, qkv_kv.data_ptr() + H * 4, 3 * H,
+                                            qkv_kv.data_ptr() + 2 * H * 4, 3 * H, L.ptr(key_mask), L.ptr(out), H, B, Lq, Lk, heads,
+                                            float(p), int(seed)), "rgqa_attention_dropout")
+    return out
+
+
+def dropout_add(x, resid=None, p=0.1, seed=0):
+    """dropout(x) [+ resid] with the counter-based mask of (seed, element index); also the dropout's own backward."""
+    _need_cuda(x, resid)
+    assert x.dtype == torch.float32 and x.is_contiguous() and (resid is None or (resid.is_contiguous() and resid.shape == x.shape))
+    y = torch.empty_like(x)
+    L.check(L.load().rgqa_dropout_add(L.current_stream_ptr(), L.ptr(x), L.ptr(resid), L.ptr(y), x.numel(), float(p), int(seed)),
+            "rgqa_dropout_add")
+    return y
+
+
+def attention_bwd(qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv, B, Lq, Lk, key_mask=None, heads=12, p=0.0, seed=0):
     """Backward of :func:`attention`: Q from ``qkv_q`` [B*Lq, 3H], K / V from ``qkv_kv`` [B*Lk, 3H], ``dctx`` [B*Lq, H];
     writes dQ into columns [0, H) of ``dqkv_q`` and dK, dV into columns [H, 3H) of ``dqkv_kv`` (f32, fused layout)."""
     _need_cuda(qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv, key_mask)
@@ -316,7 +338,7 @@ def attention_bwd(qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv, B, Lq, Lk, key_mask=None
     L.check(L.load().rgqa_attention_bwd(L.current_stream_ptr(), L.ptr(qkv_q), 3 * H, qkv_kv.data_ptr() + H * 4, 3 * H,
                                         qkv_kv.data_ptr() + 2 * H * 4, 3 * H, L.ptr(key_mask), L.ptr(dctx), H,
                                         L.ptr(dqkv_q), 3 * H, dqkv_kv.data_ptr() + H * 4, 3 * H,
-                                        dqkv_kv.data_ptr() + 2 * H * 4, 3 * H, B, Lq, Lk, heads), "rgqa_attention_bwd")
+                                        dqkv_kv.data_ptr() + 2 * H * 4, 3 * H, B, Lq, Lk, heads, float(p), int(seed)), "rgqa_attention_bwd")
 
 
 # ---- weight-gradient kernels (accumulating) --------------------------------------------------------------------------

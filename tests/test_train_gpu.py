@@ -115,3 +115,88 @@ def test_mixed_precision_training_step_tracks_the_fp32_trajectory(cuda_device):
         ref, got, start = torch.from_numpy(z["final:" + n]), cut(tr.p[n]).cpu(), cut(sd[n])
         moved = float((ref - start).norm())
         assert float((got - ref).norm()) <= 0.1 * moved + 1e-7, (n, float((got - ref).norm()), moved)
+
+
+def test_dropout_kernels_against_torch_with_the_same_mask(cuda_device):
+    """Counter-based dropout: keep rate, scaling, determinism; attention with dropout on the probabilities and its backward against
+    torch autograd fed the SAME mask (recovered by running the elementwise kernel on ones with the attention kernel's seed)."""
+    from rgqa_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(1 << 20, generator=g).to(cuda_device)
+    r = torch.randn(1 << 20, generator=g).to(cuda_device)
+    y = ops.dropout_add(x, None, 0.1, seed=77)
+    kept = (y != 0)
+    assert abs(float(kept.float().mean()) - 0.9) < 2e-3
+    torch.testing.assert_close(y[kept], (x / 0.9)[kept], rtol=1e-6, atol=0)
+    assert torch.equal(y, ops.dropout_add(x, None, 0.1, seed=77)) and not torch.equal(y, ops.dropout_add(x, None, 0.1, seed=78))
+    torch.testing.assert_close(ops.dropout_add(x, r, 0.1, seed=77), y + r)
+    B, Lq, Lk, heads, H, p, seed = 3, 20, 36, 12, 768, 0.1, 4242
+    qkv_q = torch.randn(B * Lq, 3 * H, generator=g).to(cuda_device)
+    qkv_kv = torch.randn(B * Lk, 3 * H, generator=g).to(cuda_device)
+    lens = torch.randint(1, Lk + 1, (B,), generator=g)
+    mask = (torch.arange(Lk)[None, :] < lens[:, None]).to(torch.int32).to(cuda_device)
+    out = ops.attention_dropout(qkv_q, qkv_kv, B, Lq, Lk, key_mask=mask, heads=heads, p=p, seed=seed)
+    keep = ops.dropout_add(torch.ones(B * heads * Lq * Lk, device=cuda_device), None, p, seed).view(B, heads, Lq, Lk)   # 0 or 1 / (1 - p)
+    q = qkv_q[:, :H].clone().requires_grad_(True)
+    k = qkv_kv[:, H:2 * H].clone().requires_grad_(True)
+    v = qkv_kv[:, 2 * H:].clone().requires_grad_(True)
+    ql, kl, vl = (t.view(B, -1, heads, 64).permute(0, 2, 1, 3) for t in (q, k, v))
+    s = torch.matmul(ql, kl.transpose(-1, -2)) / 8.0 + ((1.0 - mask.float()) * -10000.0)[:, None, None, :]
+    ref = torch.matmul(torch.softmax(s, dim=-1) * keep, vl).permute(0, 2, 1, 3).reshape(B * Lq, H)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-5)
+    dctx = torch.randn(B * Lq, H, generator=g).to(cuda_device)
+    (ref * dctx).sum().backward()
+    dqkv_q, dqkv_kv = torch.zeros_like(qkv_q), torch.zeros_like(qkv_kv)
+    ops.attention_bwd(qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv, B, Lq, Lk, key_mask=mask, heads=heads, p=p, seed=seed)
+    torch.testing.assert_close(dqkv_q[:, :H], q.grad, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(dqkv_kv[:, H:2 * H], k.grad, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(dqkv_kv[:, 2 * H:], v.grad, rtol=1e-3, atol=1e-5)
+
+
+def test_training_step_with_dropout_backward_matches_its_forward(cuda_device):
+    """dropout = 0.1 (the reference's training configuration; masks are this package's, not torch's): with the masks frozen by the
+    seed, the analytic gradient must be the derivative of the loss the forward computes — checked as a directional derivative along
+    a random parameter direction with central differences."""
+    from rgqa_b200 import _lib as L, ops
+    from rgqa_b200.lxrt.trainer import LXMERTTrainer
+    layers = dict(l_layers=1, x_layers=1, r_layers=1)
+    sd = syn.lxmert_state_dict(variant="rich", **layers)
+    tr = LXMERTTrainer(sd, device=cuda_device, dropout=0.1, seed=5, **layers)
+    inp = syn.make_inputs(4, 20, seed=17)
+    g = torch.Generator().manual_seed(3)
+    target = torch.zeros(4, 1842)
+    target[torch.arange(4), torch.randint(0, 1842, (4,), generator=g)] = 1.0
+
+    def loss_only():
+        logits, _ = tr.forward(inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"])
+        loss = torch.zeros(1, dtype=torch.float64, device=tr.dev)
+        dlog = torch.empty_like(logits)
+        t = target.to(tr.dev)
+        L.check(L.load().rgqa_bce_loss_grad(L.current_stream_ptr(), L.ptr(logits), L.ptr(t), 4, 1842, L.ptr(dlog), L.ptr(loss)), "bce")
+        return float(loss), dlog
+
+    l0, dlog = loss_only()
+    l0b, _ = loss_only()
+    assert l0 == l0b                                           # same step -> same masks -> same loss
+    tr.flat_g.zero_()
+    tr.backward(dlog)
+    names = ["lxrt_encoder.model.bert.encoder.x_layers.0.visual_attention.att.query.weight",
+             "lxrt_encoder.model.bert.encoder.layer.0.output.dense.weight",
+             "lxrt_encoder.model.bert.encoder.r_layers.0.attention.output.LayerNorm.weight", "logit_fc.0.weight"]
+    for n in names:
+        d = torch.randn(tr.p[n].shape, generator=g).to(tr.dev)
+        d = d / d.norm()
+        analytic = float((tr.g[n] * d).sum())
+        eps = 2e-2
+        tr.p[n].add_(eps * d); tr._derived.clear()
+        lp, _ = loss_only()
+        tr.p[n].sub_(2 * eps * d); tr._derived.clear()
+        lm, _ = loss_only()
+        tr.p[n].add_(eps * d); tr._derived.clear()
+        numeric = (lp - lm) / (2 * eps)
+        assert numeric == pytest.approx(analytic, rel=5e-2, abs=5e-3), (n, numeric, analytic)
+    # and the no-dropout trainer differs (the masks really are applied)
+    tr0 = LXMERTTrainer(sd, device=cuda_device, **layers)
+    lg0, _ = tr0.forward(inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"])
+    lg1, _ = tr.forward(inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"])
+    assert (lg0 - lg1).abs().max().item() > 1e-3
