@@ -46,6 +46,36 @@ class GQA:
     def save(self, name):
         torch.save(self.model.state_dict(), os.path.join(self.output, "%s.pth" % name))
 
+    def train(self, loader, img_of, steps_total=None, epochs=None, gemm=None):
+        """``GQA.train`` (gqa_conf.py:140-202) on the GPU: BCE x A, clip 5.0, BertAdam(lr, warmup 0.1, t_total) (:123-127), RP
+        negatives with ``--sample_pair`` (:155-170).  ``loader`` yields ``(ques_id, feats, boxes, sent, target)`` host batches
+        (``target`` with the trailing 'UQ' column, dropped as :153 does); ``img_of(qid)`` -> image id.  Returns the per-step
+        losses; the trained parameters are loaded back into ``self.model``."""
+        from ..lxrt.trainer import LXMERTTrainer
+        from .rp import build_rp_batch
+        args = self.args
+        epochs = args.epochs if epochs is None else epochs
+        batches_per_epoch = len(loader)
+        t_total = int(batches_per_epoch * epochs) if steps_total is None else steps_total        # :122
+        if gemm is None:
+            gemm = "bf16" if args.precision == "bf16" else "fp32"
+        dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+        tr = LXMERTTrainer(self.model.state_dict(), l_layers=args.llayers, x_layers=args.xlayers, r_layers=args.rlayers, device=dev,
+                           lr=args.lr, warmup=0.1, t_total=t_total, dropout=args.dropout, seed=args.seed, gemm=gemm)
+        tok, L = self.model.lxrt_encoder.tokenizer, self.model.lxrt_encoder.max_seq_length
+        losses = []
+        for _ in range(epochs):
+            for ques_id, feats, boxes, sent, target in loader:
+                target = target[:, :-1]
+                ques_id, sent = list(ques_id), list(sent)
+                if args.sample_pair:
+                    ques_id, feats, boxes, sent, target = build_rp_batch(ques_id, feats, boxes, sent, target, img_of)
+                ids, mask, seg = tok.encode_batch(sent, L)
+                loss, _ = tr.train_step(feats, boxes, torch.from_numpy(ids), torch.from_numpy(seg), torch.from_numpy(mask), target)
+                losses.append(loss)
+        self.model.load_state_dict(tr.state_dict(), strict=True)
+        return losses
+
     def ood_evaluate(self, dataset, batch_size, method, dump=None, maha=None):
         rank = dist.get_rank() if dist.is_initialized() else 0
         world = dist.get_world_size() if dist.is_initialized() else 1

@@ -149,3 +149,34 @@ def test_bf16_feature_store_sweep_is_bit_identical_to_fp32_features(cuda_device,
                                    torch.from_numpy(mask).to(cuda_device))
     ref_s, ref_l = m.engine().score("energy", logits=logits, pooled=pooled)
     assert torch.equal(torch.cat(got_s), ref_s.cpu()) and torch.equal(torch.cat(got_l), ref_l.cpu())
+
+
+def test_gqa_train_mirror_runs_rp_steps_and_updates_the_model(cuda_device):
+    """GQA.train (gqa_conf.py:140-202) through the host mirror: random-pairing batches, BCE x A, clip, BertAdam; the loss falls on
+    a batch it has seen and the trained parameters land back in the model the evaluation path uses."""
+    from rgqa_b200.tasks.gqa_conf import GQA
+    sys.argv = ["x"]
+    args = types.SimpleNamespace(backbone="lxmert", llayers=2, xlayers=1, rlayers=1, from_scratch=False, precision="fp32", vocab=None,
+                                 max_seq_length=20, output=str(os.path.join(os.path.dirname(__file__), "..", "gpurun_out", "train_tmp")),
+                                 lr=2e-4, epochs=3, dropout=0.0, seed=9595, sample_pair=True, tau=0.5)
+    gqa = GQA(args)
+    gqa.model.load_state_dict(syn.lxmert_state_dict(variant="rich", **LAYERS), strict=True)
+    gqa.model = gqa.model.to(cuda_device)
+    B = 6
+    inp = syn.make_inputs(B, 20, seed=41)
+    sents = [f"what is item {i} doing near the tree" for i in range(B)]
+    target = torch.zeros(B, 1843)
+    target[torch.arange(B), torch.tensor([3, 50, 700, 11, 1500, 90])] = 1.0
+    qids = [f"q{i}" for i in range(B)]
+    loader = [(qids, inp["feat"], inp["pos"], sents, target)]
+    before = gqa.model.state_dict()["logit_fc.3.bias"].clone()
+    logits_before = gqa.model(inp["feat"].to(cuda_device), inp["pos"].to(cuda_device), sents)[0].clone()
+    losses = gqa.train(loader, img_of=lambda q: "img" + q[1:], epochs=3)
+    assert len(losses) == 3 and losses[2] < losses[0]
+    after = gqa.model.state_dict()["logit_fc.3.bias"]
+    assert not torch.equal(before.cpu(), after.cpu())
+    logits_after = gqa.model(inp["feat"].to(cuda_device), inp["pos"].to(cuda_device), sents)[0]
+    # the evaluation path sees the trained weights: its BCE x A loss on the training batch fell as well
+    bce = torch.nn.BCEWithLogitsLoss()
+    t = target[:, :-1].to(logits_after.device)
+    assert float(bce(logits_after, t)) < float(bce(logits_before, t))
