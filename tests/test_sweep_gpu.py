@@ -151,13 +151,13 @@ def test_bf16_feature_store_sweep_is_bit_identical_to_fp32_features(cuda_device,
     assert torch.equal(torch.cat(got_s), ref_s.cpu()) and torch.equal(torch.cat(got_l), ref_l.cpu())
 
 
-def test_gqa_train_mirror_runs_rp_steps_and_updates_the_model(cuda_device):
+def test_gqa_train_mirror_runs_rp_steps_and_updates_the_model(cuda_device, tmp_path):
     """GQA.train (gqa_conf.py:140-202) through the host mirror: random-pairing batches, BCE x A, clip, BertAdam; the loss falls on
     a batch it has seen and the trained parameters land back in the model the evaluation path uses."""
     from rgqa_b200.tasks.gqa_conf import GQA
     sys.argv = ["x"]
     args = types.SimpleNamespace(backbone="lxmert", llayers=2, xlayers=1, rlayers=1, from_scratch=False, precision="fp32", vocab=None,
-                                 max_seq_length=20, output=str(os.path.join(os.path.dirname(__file__), "..", "gpurun_out", "train_tmp")),
+                                 max_seq_length=20, output=str(tmp_path / "out"),
                                  lr=2e-4, epochs=3, dropout=0.0, seed=9595, sample_pair=True, tau=0.5)
     gqa = GQA(args)
     gqa.model.load_state_dict(syn.lxmert_state_dict(variant="rich", **LAYERS), strict=True)
