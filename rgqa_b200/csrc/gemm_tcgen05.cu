@@ -481,7 +481,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                       const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                       const __grid_constant__ CUtensorMap tmOutLo, const __grid_constant__ CUtensorMap tmResLo,
                       const GemmParams p) {
-  constexpr bool kHiLo = STAGED && EPI == EPI_RESID_HL;  // deferred-LayerNorm producer (bf16 hi/lo pair + statistics)
+  // deferred-LayerNorm producer (bf16 hi/lo pair + statistics)
+  constexpr bool kHiLo = STAGED && (EPI == EPI_RESID_HL || EPI == EPI_RESID_HL_BETA);
+  constexpr bool kHasBeta = EPI == EPI_RESID_HL_BETA;  // else the bias already carries beta (folded at load time)
   constexpr bool kResidSmem = (STAGED && EPI == EPI_RESID && sizeof(OutT) == 4) || kHiLo;
   static_assert(EW == 8 || (EW == 16 && STAGED && !kResidSmem), "16 epilogue warps: staged, non-residual epilogues only");
   using PC = PairCfg<STAGED, kResidSmem, EW, RING>;
@@ -615,14 +617,18 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int my_tiles = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
       const int total = my_tiles * 4;
       const int r_local = quarter * 32 + lane;
-      auto coords = [&](int k, int& row0, int& col) {
-        const int t = pair + (k >> 2) * num_pairs;
-        row0 = (t / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM + quarter * 32;  // this warp's first row
-        col = (t % tiles_n) * kPairBN + half * kColsPerWarp + (k & 3) * 32;
+      // tile coordinates are divided out once per tile (not per slab): (row0, col0) of this warp's part of the current tile
+      // and of the next one, which the residual prefetch (kRing - 1 slabs ahead) and the statistics prefetch reach into
+      auto tile_coords = [&](int it, int& row0, int& col0) {
+        const int t = pair + it * num_pairs;
+        const int tm = t / tiles_n;
+        row0 = tm * (2 * BM) + static_cast<int>(rank) * BM + quarter * 32;  // this warp's first row
+        col0 = (t - tm * tiles_n) * kPairBN + half * kColsPerWarp;
       };
-      auto issue_load = [&](int k) {
-        int row0, col;
-        coords(k, row0, col);
+      int cur_row0, cur_col0, nxt_row0, nxt_col0;
+      tile_coords(0, cur_row0, cur_col0);
+      tile_coords(1, nxt_row0, nxt_col0);
+      auto issue_load = [&](int k, int row0, int col) {
         const int b = k % kRing;
         uint64_t* bar = &resid_bar[e * kRing + b];
         if (p.debug & 4) {  // measurement: no residual traffic
@@ -638,29 +644,30 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tma_load_2d(dst + quarter * kSubSlab, &tmRes, bar, col, row0);
         }
       };
+      static_assert(kRing - 1 <= 4, "the initial residual loads stay inside the first tile");
       if (issuer) {
-        if (total > 0) issue_load(0);
-        for (int j = 1; j < kRing - 1; ++j)
-          if (total > j) issue_load(j);
+        for (int j = 0; j < kRing - 1; ++j)
+          if (total > j) issue_load(j, cur_row0, cur_col0 + j * 32);
       }
       [[maybe_unused]] RowNorm rin{0.f, 1.f};
       [[maybe_unused]] float2 st_sum2 = make_float2(0.f, 0.f), st_sq2 = make_float2(0.f, 0.f);
       for (int k = 0; k < total; ++k) {
         const int itile = k >> 2, sl = k & 3;
         const int acc = itile & 1;
-        int row0, col;
-        coords(k, row0, col);
+        if (sl == 0 && k > 0) {
+          cur_row0 = nxt_row0;
+          cur_col0 = nxt_col0;
+          tile_coords(itile + 1, nxt_row0, nxt_col0);
+        }
+        const int row0 = cur_row0, col = cur_col0 + sl * 32;
         const int row = row0 + lane;
         if (sl == 0) {
           if constexpr (kHiLo) {
             rin = row_norm(p.in_stats, row, row < p.M, p.ln_eps);
             st_sum2 = st_sq2 = make_float2(0.f, 0.f);
-            if (k + 4 < total) {  // this row's statistics of the NEXT tile: pull the line into L1 while this tile is processed
-              int nrow0, ncol;
-              coords(k + 4, nrow0, ncol);
-              if (nrow0 + lane < p.M)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.in_stats + static_cast<long long>(nrow0 + lane) * 12));
-            }
+            // this row's statistics of the NEXT tile: pull the line into L1 while this tile is processed
+            if (k + 4 < total && nxt_row0 + lane < p.M)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(p.in_stats + static_cast<long long>(nxt_row0 + lane) * 12));
           }
           mbar_wait(&tmem_full_bar[acc], (itile >> 1) & 1u);
           tc_fence_after();
@@ -684,8 +691,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const float ra = rin.rstd, rb = -rin.mu * rin.rstd;
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
           const float4* g4 = reinterpret_cast<const float4*>(p.in_gamma + col);
-          const bool has_beta = p.in_beta != nullptr;  // else the bias already carries beta (folded at load time)
-          const float4* e4 = reinterpret_cast<const float4*>((has_beta ? p.in_beta : p.bias) + col);
+          [[maybe_unused]] const float4* e4 = reinterpret_cast<const float4*>((kHasBeta ? p.in_beta : p.bias) + col);
           uint32_t hw[16], lw[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -698,7 +704,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int i = 0; i < 8; ++i) {  // columns 4i .. 4i+3 = bf16 words 2i, 2i+1
             float4 bb = __ldg(b4 + i);
             const float4 gg = __ldg(g4 + i);
-            if (has_beta) {
+            if constexpr (kHasBeta) {
               const float4 ee = __ldg(e4 + i);
               bb.x += ee.x;
               bb.y += ee.y;
@@ -734,8 +740,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             *reinterpret_cast<uint4*>(lrow + ((i ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           if (sl == 3 && row < p.M) {  // this thread's 128 columns of the row are done: publish their partial statistics
-            float2* so = reinterpret_cast<float2*>(p.out_stats + static_cast<long long>(row) * 12) +
-                         (((pair + itile * num_pairs) % tiles_n) * 2 + half);
+            float2* so = reinterpret_cast<float2*>(p.out_stats + static_cast<long long>(row) * 12) + (cur_col0 >> 7);  // 128-column slice
             *so = make_float2(st_sum2.x + st_sum2.y, st_sq2.x + st_sq2.y);
           }
         } else {
@@ -778,7 +783,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tma_store_commit();
           if (k + kRing - 1 < total) {
             tma_store_wait_read<1>();  // the store of slab k-1 has drained the buffer slab k+2 will land in
-            issue_load(k + kRing - 1);
+            const int sn = sl + kRing - 1;  // slab k + kRing - 1: still in this tile, or slab sn - 4 of the next one
+            if (sn < 4) issue_load(k + kRing - 1, cur_row0, cur_col0 + sn * 32);
+            else issue_load(k + kRing - 1, nxt_row0, nxt_col0 + (sn - 4) * 32);
           }
         }
       }
@@ -1004,7 +1011,7 @@ int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& 
   constexpr int EW = 8;
   auto kern = gemm_bf16_pair_kernel<EPI, OutT, STAGED, EW, RING>;
   constexpr int smem =
-      PairCfg<STAGED, (STAGED && ((EPI == EPI_RESID && sizeof(OutT) == 4) || EPI == EPI_RESID_HL)), EW, RING>::kSmemBytes;
+      PairCfg<STAGED, (STAGED && ((EPI == EPI_RESID && sizeof(OutT) == 4) || EPI == EPI_RESID_HL || EPI == EPI_RESID_HL_BETA)), EW, RING>::kSmemBytes;
   static bool configured = false;
   if (!configured) {
     RGQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1083,6 +1090,10 @@ int gemm_bf16_resid_hl(cudaStream_t stream, const void* A, long long lda, const 
   p.ldo = N;
   p.vec_ok = 1;
   p.debug = option_get(OPT_GEMM_DEBUG);
+  if (in_beta != nullptr) {
+    if (K >= 2048) return launch_pair<EPI_RESID_HL_BETA, __nv_bfloat16, true, 2>(stream, tmA, tmB, tmOutHi, tmInHi, p, &tmOutLo, &tmInLo);
+    return launch_pair<EPI_RESID_HL_BETA, __nv_bfloat16, true>(stream, tmA, tmB, tmOutHi, tmInHi, p, &tmOutLo, &tmInLo);
+  }
   if (K >= 2048) return launch_pair<EPI_RESID_HL, __nv_bfloat16, true, 2>(stream, tmA, tmB, tmOutHi, tmInHi, p, &tmOutLo, &tmInLo);
   return launch_pair<EPI_RESID_HL, __nv_bfloat16, true>(stream, tmA, tmB, tmOutHi, tmInHi, p, &tmOutLo, &tmInLo);
 }

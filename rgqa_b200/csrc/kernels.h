@@ -15,6 +15,7 @@ enum Epilogue : int {
   EPI_TANH = 2,   // out = tanh(acc + bias)                (modeling.py:575-581 pooler)
   EPI_RESID = 3,  // out = acc + bias + residual           (pre-LayerNorm sum of modeling.py:357-361 / :411-415)
   EPI_RESID_HL = 4,  // same sum, residual recomputed from a deferred-LayerNorm hidden state, written as a bf16 hi/lo pair
+  EPI_RESID_HL_BETA = 5,  // EPI_RESID_HL with LN_prev's beta passed separately (the engine folds it into the bias at load time)
 };
 
 enum DType : int { DT_F32 = 0, DT_BF16 = 1 };

@@ -134,8 +134,9 @@ def test_gemm_folded_layernorm_consumer(cuda_device, M, N, epi):
     assert err.max().item() <= 3e-2 and err.pow(2).mean().sqrt().item() <= 5e-3, (err.max().item(), err.pow(2).mean().sqrt().item())
 
 
+@pytest.mark.parametrize("fold_beta", [False, True])
 @pytest.mark.parametrize("M,K", [(1024, 768), (2048, 3072), (1300, 768)])
-def test_gemm_residual_hilo_producer(cuda_device, M, K):
+def test_gemm_residual_hilo_producer(cuda_device, M, K, fold_beta):
     """v = A·Wᵀ + b + LN_prev(x_prev) written as a bf16 hi/lo pair + partial statistics (the producer half of the
     deferred LayerNorm: BertAttOutput / BertOutput modeling.py:357-361, :411-415 up to — not including — the LayerNorm)."""
     from rgqa_b200 import ops
@@ -146,7 +147,10 @@ def test_gemm_residual_hilo_producer(cuda_device, M, K):
     bias = (torch.randn(768, generator=g) * 0.1).to(cuda_device)
     gamma = (1 + 0.1 * torch.randn(768, generator=g)).to(cuda_device)
     beta = (0.1 * torch.randn(768, generator=g)).to(cuda_device)
-    hi, lo, stats = ops.linear_residual_hilo(a, w, bias, hi_in, lo_in, st_in, gamma, beta)
+    if fold_beta:   # the engine's form: LN_prev's beta rides in the bias (folded once at load time), kernel variant without beta
+        hi, lo, stats = ops.linear_residual_hilo(a, w, bias + beta, hi_in, lo_in, st_in, gamma, None)
+    else:
+        hi, lo, stats = ops.linear_residual_hilo(a, w, bias, hi_in, lo_in, st_in, gamma, beta)
     torch.cuda.synchronize()
     resid = torch.nn.functional.layer_norm(v_in.to(cuda_device), (768,), gamma.double(), beta.double(), eps=1e-12)
     ref = a.double() @ w.double().t() + bias.double() + resid
