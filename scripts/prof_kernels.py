@@ -22,10 +22,10 @@ for _ in range(3):
 for _ in range(3):
     ctx = ops.attention(qkv, qkv, 1024, 36, 36)                                            # visual self-attention
 for _ in range(3):
-    h2, l2, s2 = ops.linear_residual_hilo(ctx, wo, bo, hi, lo, st, g, b)                   # attention-output producer
+    h2, l2, s2 = ops.linear_residual_hilo(ctx, wo, bo, hi, lo, st, g, None)                  # attention-output producer
 for _ in range(3):
     inter = ops.linear_bf16_folded(h2, s2, w1, b1, epilogue=L.EPI_GELU)                    # FFN1 consumer (erf-GELU)
 for _ in range(3):
-    ops.linear_residual_hilo(inter, w2, bo, h2, l2, s2, g, b)                              # FFN2 producer
+    ops.linear_residual_hilo(inter, w2, bo, h2, l2, s2, g, None)                             # FFN2 producer
 torch.cuda.synchronize()
 print("ok")
