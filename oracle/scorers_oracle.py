@@ -1,14 +1,18 @@
 """ORACLE — test infrastructure, not product code.
 
-CPU restatement of the reference's rejection scorers.  The task drivers that hold these lines cannot
-be imported (``src/tasks/gqa_conf.py:27`` pulls in ``vilt`` -> ``timm``, absent), so each scorer is
-restated from the cited lines, literally (including the 1842-iteration Mahalanobis loop).
+CPU restatement of the reference's rejection scorers, each from the cited lines, literally (including the 1842-iteration
+Mahalanobis loop).
 
-Pinning: MSP / energy are one-line torch expressions copied in meaning from the cited lines;
-``sample_estimator`` is checked in ``tests/test_oracle_cpu.py`` against scikit-learn's
-``EmpiricalCovariance`` (the third-party routine the reference calls, pinned 1.1.1 in
-environment.yml:111, 1.9.0 here).  The reference ships no test or golden vector for these lines:
-**parity unpinned** beyond that.
+**Pinned** (tests/test_oracle_cpu.py::test_scorer_oracles_pinned_to_reference_drivers): the UNMODIFIED reference drivers
+``GQA.ood_evaluate`` of ``src/tasks/gqa_conf.py`` (MSP), ``gqa_energy.py`` (top-2 energy), ``gqa_maha.py`` (``sample_estimator``
+with scikit-learn's ``EmpiricalCovariance`` and the per-class Mahalanobis loop) and ``gqa_ensemble.py`` (per-question sigmoid
+vectors) were executed in the build container on a tiny stand-in model and synthetic questions
+(``tests/golden/make_golden_scorers.py`` -> ``tests/golden/scorers_reference.npz``); ``msp``, ``energy_top2``, ``mahalanobis`` and
+``sample_estimator`` reproduce their scores / labels / class means / precision matrix.  ``gqa_conf.py`` imports ``vilt`` -> ``timm``
+(absent): that one import is stubbed for the run, the driver code itself is untouched.  Still **unpinned**: ``energy_sum`` / ``lse``
+(training-time expressions, :131 / :185) and the ensemble's combine step (``gqa_ensemble.py:165-177`` sits in the script's
+``__main__`` block and cannot be called), both one-line numpy / torch expressions.  scikit-learn is 1.9.0 here, 1.1.1 in the
+reference's environment.yml:111.
 """
 from __future__ import annotations
 

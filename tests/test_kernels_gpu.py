@@ -436,3 +436,42 @@ def test_bce_loss_times_answers_and_its_gradient(cuda_device):
     loss, dlogit = bce_loss_and_grad(torch.from_numpy(z["bce_logit"]).to(cuda_device), torch.from_numpy(z["bce_target"]).to(cuda_device))
     assert float(loss) == pytest.approx(float(z["bce_loss"]), rel=1e-6)
     torch.testing.assert_close(dlogit.cpu(), torch.from_numpy(z["bce_dlogit"]), rtol=1e-5, atol=1e-8)
+
+
+def test_cuda_scorers_against_reference_driver_goldens(cuda_device):
+    """The scorer kernels against what the UNMODIFIED reference drivers returned (tests/golden/scorers_reference.npz, made by
+    tests/golden/make_golden_scorers.py from gqa_conf / gqa_energy / gqa_maha `GQA.ood_evaluate` + `sample_estimator` on the
+    tiny model of tests/golden/tiny_vqa.py) — not through the oracle."""
+    import json, os, sys
+    from rgqa_b200 import ops
+    from rgqa_b200.tasks.gqa_maha import MahaEstimator
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    sys.path.insert(0, gold)
+    from tiny_vqa import TinyVQA
+    z = np.load(os.path.join(gold, "scorers_reference.npz"))
+    with open(os.path.join(gold, "scorers_reference.json")) as f:
+        meta = json.load(f)
+    sd = {k[len("model."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("model.")}
+    C, D = sd["head.weight"].shape
+    model = TinyVQA(sd["fc_feat.weight"].shape[1], D, C, maha=True)
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        logit, x = model(torch.from_numpy(z["feat_test"]), torch.from_numpy(z["box_test"]), meta["sents_test"])
+        _, xtr = model(torch.from_numpy(z["feat_train"]), torch.from_numpy(z["box_train"]), meta["sents_train"])
+    for name, mode in (("msp", "msp"), ("energy", "energy")):           # gqa_conf.py:326, gqa_energy.py:204-206
+        s, l = ops.score_logits(logit.to(cuda_device), mode)
+        np.testing.assert_array_equal(l.cpu().numpy(), z[f"{name}.label"])
+        np.testing.assert_allclose(s.double().cpu().numpy(), z[f"{name}.score"], rtol=1e-5)
+    mu = torch.from_numpy(z["maha.mean"]).float().to(cuda_device)        # gqa_maha.py:228-236, :270
+    P = torch.from_numpy(z["maha.precision"]).float().to(cuda_device)
+    s, l = ops.mahalanobis(x.to(cuda_device), mu, P)[:2]
+    np.testing.assert_array_equal(l.cpu().numpy(), z["maha.label"])
+    np.testing.assert_allclose(s.double().cpu().numpy(), z["maha.score"], rtol=1e-3)   # north_star: rejection scores within 1e-3 rel
+    est = MahaEstimator(C, D, cuda_device)                               # gqa_maha.py:120-189 incl. sklearn's precision_
+    target = torch.from_numpy(z["target_train"])[:, :C].contiguous()
+    for lo in range(0, xtr.shape[0], 16):
+        est.accumulate(xtr[lo:lo + 16].to(cuda_device), target[lo:lo + 16].contiguous())
+    mean, prec = est.finish()
+    np.testing.assert_allclose(mean.numpy(), z["maha.mean"], atol=2e-6)
+    scale = np.abs(z["maha.precision"]).max()
+    assert np.abs(prec - z["maha.precision"]).max() <= 2e-4 * scale

@@ -136,3 +136,100 @@ def test_estimator_closed_form_finish_matches_the_list_building_oracle():
     assert (mean - ref_mean).abs().max().item() <= 1e-6
     assert torch.equal(mean[C - 2:], torch.zeros(2, D))
     assert np.abs(prec - ref_prec).max() <= 1e-6 * np.abs(ref_prec).max()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Scorers pinned to the UNMODIFIED reference drivers (tests/golden/make_golden_scorers.py ran gqa_conf / gqa_energy /
+# gqa_odin / gqa_maha / gqa_ensemble `GQA.ood_evaluate` + `sample_estimator` on the tiny model of tests/golden/tiny_vqa.py)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def scorer_golden():
+    import sys
+    sys.path.insert(0, GOLD)
+    from tiny_vqa import TinyVQA
+    z = np.load(os.path.join(GOLD, "scorers_reference.npz"))
+    with open(os.path.join(GOLD, "scorers_reference.json")) as f:
+        meta = json.load(f)
+    models = []
+    for tag in ("model", "model2"):
+        sd = {k[len(tag) + 1:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(tag + ".")}
+        C, D = sd["head.weight"].shape
+        m = TinyVQA(sd["fc_feat.weight"].shape[1], D, C, maha=True)
+        m.load_state_dict(sd, strict=True)
+        models.append(m.eval())
+    return z, meta, models
+
+
+def _batches(n, bs=16):   # the reference loader's batches (ODIN's loss is a batch mean: keep them identical)
+    return [slice(i, min(i + bs, n)) for i in range(0, n, bs)]
+
+
+def test_scorer_oracles_pinned_to_reference_drivers(scorer_golden):
+    from oracle import scorers_oracle as S
+    from oracle import odin_oracle as OD
+    z, meta, (model, model2) = scorer_golden
+    feat, box = torch.from_numpy(z["feat_test"]), torch.from_numpy(z["box_test"])
+    sents = meta["sents_test"]
+    n = feat.shape[0]
+    with torch.no_grad():
+        logit, x = model(feat, box, sents)
+        logit2, _ = model2(feat, box, sents)
+
+    # MSP (gqa_conf.py:326) and top-2 energy (gqa_energy.py:204-206): same floats, same labels
+    for name, fn in (("msp", S.msp), ("energy", S.energy_top2)):
+        s, l = fn(logit)
+        np.testing.assert_array_equal(l.numpy(), z[f"{name}.label"])
+        np.testing.assert_allclose(s.double().numpy(), z[f"{name}.score"], rtol=1e-6, atol=0)
+
+    # ensemble members (gqa_ensemble.py:95-110): the per-question sigmoid vectors the combine step consumes
+    np.testing.assert_allclose(torch.sigmoid(logit).numpy(), z["ens0.sigmoid"], rtol=1e-6)
+    np.testing.assert_allclose(torch.sigmoid(logit2).numpy(), z["ens1.sigmoid"], rtol=1e-6)
+
+    # sample_estimator (gqa_maha.py:120-189): class means + sklearn EmpiricalCovariance.precision_
+    ftr, btr = torch.from_numpy(z["feat_train"]), torch.from_numpy(z["box_train"])
+    with torch.no_grad():
+        _, xtr = model(ftr, btr, meta["sents_train"])
+    mean, precision = S.sample_estimator(xtr, torch.from_numpy(z["target_train"])[:, :-1])
+    np.testing.assert_allclose(mean.numpy(), z["maha.mean"], rtol=1e-6, atol=1e-7)
+    scale = np.abs(z["maha.precision"]).max()
+    np.testing.assert_allclose(precision, z["maha.precision"], rtol=1e-7, atol=1e-9 * scale)
+
+    # Mahalanobis score, noise = 0 (gqa_maha.py:228-236, :270) with the reference's own (mean, precision)
+    mu, P = torch.from_numpy(z["maha.mean"]).float(), torch.from_numpy(z["maha.precision"]).float()
+    s, l, _ = S.mahalanobis(x, mu, P)
+    np.testing.assert_array_equal(l.numpy(), z["maha.label"])
+    np.testing.assert_allclose(s.double().numpy(), z["maha.score"], rtol=2e-5)
+
+    # the two input-gradient scorers, batch by batch like the reference loader
+    def fwd(sl):
+        return lambda f, b: model(f, b, sents[sl])
+    got = {k: ([], []) for k in ("odin", "odin_plain", "maha_noise")}
+    for sl in _batches(n):
+        for key, T, noise in (("odin", meta["temperature"], meta["noise"]), ("odin_plain", 1.0, 0.0)):
+            s, l, _, _ = OD.odin(None, feat[sl], box[sl], None, None, None, T, noise, model=fwd(sl))
+            got[key][0].append(s), got[key][1].append(l)
+        s, l, _, _ = OD.mahalanobis_with_noise(None, feat[sl], box[sl], None, None, None, mu, P, meta["noise"], model=fwd(sl))
+        got["maha_noise"][0].append(s), got["maha_noise"][1].append(l)
+    for key, (ss, ll) in got.items():
+        np.testing.assert_array_equal(torch.cat(ll).numpy(), z[f"{key}.label"], err_msg=key)
+        np.testing.assert_allclose(torch.cat(ss).double().numpy(), z[f"{key}.score"], rtol=2e-5, err_msg=key)
+    # the perturbation does something on this model (otherwise the noise > 0 goldens would pin nothing)
+    assert np.abs(z["maha_noise.score"] - z["maha.score"]).max() > 1e-3
+    assert np.abs(z["odin.score"] - z["odin_plain.score"]).max() > 1e-3
+
+
+@pytest.mark.parametrize("name", ["msp", "energy", "odin", "maha", "maha_noise"])
+def test_evaluator_reproduces_reference_result_dicts_from_driver_scores(scorer_golden, name):
+    """Product host code (no GPU needed): the reference drivers' (answer, score) pairs through this package's evaluator give the
+    result dict the reference's ``GQAOODEvaluator`` printed for them, float for float."""
+    from rgqa_b200.tasks.gqa_data import GQAOODEvaluator
+    z, meta, _ = scorer_golden
+    qid2label = {q: {a: v for a, v in pairs} for q, pairs in zip(meta["qids_test"], meta["labels_test"])}
+    # the drivers hand the evaluator numpy float32 scalars (`score.cpu().numpy()` elements)
+    q2a = {q: (meta["label2ans"][int(l)], np.float32(s))
+           for q, l, s in zip(meta["qids_test"], z[f"{name}.label"], z[f"{name}.score"])}
+    got = GQAOODEvaluator(qid2label, 0.5).evaluate(q2a)
+    want = meta["results"][name]
+    assert set(got) == set(want)
+    for k in want:
+        assert float(got[k]) == want[k], (name, k, float(got[k]), want[k])
