@@ -21,7 +21,7 @@ class TinyVQA(nn.Module):
         self.maha = maha
 
     def forward(self, feats, boxes, sent):
-        lens = torch.tensor([len(s.split()) % 8 for s in sent], dtype=torch.long)
+        lens = torch.tensor([len(s.split()) % 8 for s in sent], dtype=torch.long, device=feats.device)
         x = torch.tanh(self.fc_feat(feats).mean(1) + self.fc_box(boxes).mean(1) + self.len_emb(lens))
         logit = self.head(x) * 4.0
         return (logit, x) if self.maha else logit

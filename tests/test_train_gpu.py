@@ -200,3 +200,53 @@ def test_training_step_with_dropout_backward_matches_its_forward(cuda_device):
     lg0, _ = tr0.forward(inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"])
     lg1, _ = tr.forward(inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"])
     assert (lg0 - lg1).abs().max().item() > 1e-3
+
+
+def test_rp_finetune_loop_kernels_follow_the_reference_train_loop(cuda_device):
+    """The trainer's own pieces — random-pairing batch (``tasks/rp.py``), ``BCEWithLogitsLoss x A`` + d/dlogit kernel, global-norm
+    clip 5.0 and the BertAdam kernel with the ``warmup_linear`` schedule over ``t_total = batches x epochs`` — driven around the tiny
+    stand-in model of tests/golden/tiny_vqa.py (torch autograd supplies its gradients: test scaffolding), against six steps of the
+    UNMODIFIED reference ``GQA.train`` loop (src/tasks/gqa_conf.py:140-245, tests/golden/make_golden_rp_train.py)."""
+    import json, random, sys
+    from rgqa_b200.lxrt.optimization import BertAdam, bce_loss_and_grad
+    from rgqa_b200.tasks.rp import build_rp_batch
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    sys.path.insert(0, gold)
+    from tiny_vqa import TinyVQA
+    z = np.load(os.path.join(gold, "rp_train_reference.npz"))
+    with open(os.path.join(gold, "rp_train_reference.json")) as f:
+        meta = json.load(f)
+    sd = {k[len("init."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("init.")}
+    C, D = sd["head.weight"].shape
+    model = TinyVQA(sd["fc_feat.weight"].shape[1], D, C)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda_device).train()
+    assert [k for k, _ in model.named_parameters()] == meta["param_order"]
+    params = [p.data for p in model.parameters()]
+    qids, sents, img = meta["qids"], meta["sents"], meta["img_of"]
+    feats, boxes, target = (torch.from_numpy(z[k]) for k in ("feat", "box", "target"))
+    bs = meta["batch"]
+    n_batches = (len(qids) + bs - 1) // bs
+    opt = BertAdam(params, lr=meta["lr"], warmup=0.1, t_total=n_batches * meta["epochs"])
+    random.seed(meta["seed"])
+    step = 0
+    for _ in range(meta["epochs"]):
+        for lo in range(0, len(qids), bs):
+            sl = slice(lo, lo + bs)
+            _, f2, b2, s2, t2 = build_rp_batch(qids[sl], feats[sl], boxes[sl], sents[sl], target[sl][:, :-1], img.__getitem__)
+            assert s2 == meta["steps"][step]["sent"]
+            model.zero_grad(set_to_none=True)
+            logit = model(f2.to(cuda_device), b2.to(cuda_device), s2)
+            loss, dlogit = bce_loss_and_grad(logit.detach().float().contiguous(), t2.to(cuda_device).float().contiguous())
+            logit.backward(dlogit)
+            opt.step([p.grad.contiguous() for p in model.parameters()], clip_norm=5.0)
+            torch.cuda.synchronize()
+            want_loss = meta["steps"][step]["loss_times_A"]
+            assert abs(float(loss.item()) - want_loss) <= 2e-5 * abs(want_loss), (step, float(loss.item()), want_loss)
+            got = torch.cat([p.reshape(-1) for p in params]).cpu().numpy()
+            np.testing.assert_allclose(got, z["params_after"][step], rtol=2e-4, atol=2e-6, err_msg=f"step {step}")
+            step += 1
+    assert step == len(meta["steps"]) == 6
+    # the six updates moved the parameters by far more than the tolerance (the comparison is not vacuous)
+    init = torch.cat([sd[k].reshape(-1) for k in meta["param_order"]]).numpy()
+    assert np.abs(z["params_after"][-1] - init).max() > 5e-3

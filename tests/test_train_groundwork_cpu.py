@@ -63,3 +63,35 @@ def test_gradient_sign_step_equals_reference_expression():
         gradient = (torch.ge(grad, 0).float() - 0.5) * 2
         want = torch.add(x, gradient, alpha=-noise)
         assert torch.equal(_step_against_gradient_sign(x, grad, noise), want)
+
+
+def _rp_golden():
+    import json
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    z = np.load(os.path.join(gold, "rp_train_reference.npz"))
+    with open(os.path.join(gold, "rp_train_reference.json")) as f:
+        meta = json.load(f)
+    return z, meta
+
+
+def test_rp_batches_equal_what_the_reference_train_loop_fed_its_model():
+    """``build_rp_batch`` against the UNMODIFIED ``GQA.train`` (src/tasks/gqa_conf.py:148-170, run by
+    tests/golden/make_golden_rp_train.py): same ``random`` seed -> the same sentences, in the same order, for every step of two
+    epochs — i.e. the same draws, the same redraws while the drawn question shares the row's image, the same batch layout."""
+    from rgqa_b200.tasks.rp import build_rp_batch
+    z, meta = _rp_golden()
+    qids, sents, img = meta["qids"], meta["sents"], meta["img_of"]
+    feats, boxes, target = (torch.from_numpy(z[k]) for k in ("feat", "box", "target"))
+    bs, step = meta["batch"], 0
+    random.seed(meta["seed"])
+    for _ in range(meta["epochs"]):
+        for lo in range(0, len(qids), bs):
+            sl = slice(lo, lo + bs)
+            q2, f2, b2, s2, t2 = build_rp_batch(qids[sl], feats[sl], boxes[sl], sents[sl], target[sl][:, :-1], img.__getitem__)
+            want = meta["steps"][step]
+            assert s2 == want["sent"], step
+            assert f2.shape[0] == b2.shape[0] == t2.shape[0] == len(q2) == want["rows"]
+            assert int((t2.abs().sum(1) > 0).sum()) == want["target_rows_nonzero"]
+            assert torch.equal(f2[:bs], f2[bs:]) and not t2[bs:].any()
+            step += 1
+    assert step == len(meta["steps"])
