@@ -233,3 +233,40 @@ def test_evaluator_reproduces_reference_result_dicts_from_driver_scores(scorer_g
     assert set(got) == set(want)
     for k in want:
         assert float(got[k]) == want[k], (name, k, float(got[k]), want[k])
+
+
+def test_oracle_and_host_code_reproduce_the_reference_stack_wire_files(tmp_path):
+    """CPU end to end: product tokenizer -> oracle LXMERT + scorers -> product evaluator / ``dump_result`` against the UNMODIFIED
+    reference stack (real ``GQAModel``, reference tokenizer, ``GQA.ood_evaluate`` of gqa_conf / gqa_energy / gqa_maha, real
+    ``GQAOODEvaluator``; tests/golden/make_golden_dropin.py).  MSP / energy: the ``*_predict.json`` files are byte-identical; Mahalanobis:
+    same answers, confidences within one unit of the 4th decimal; all three result dicts float for float."""
+    import gzip
+    from oracle import lxmert_oracle as O
+    from oracle import scorers_oracle as S
+    from rgqa_b200.lxrt.tokenization import BertTokenizer
+    from rgqa_b200.tasks.gqa_data import GQAOODEvaluator
+    d = json.load(gzip.open(os.path.join(GOLD, "dropin_reference.json.gz"), "rt"))
+    tok = BertTokenizer.from_pretrained(os.path.join(GOLD, "tokenizer_vocab.txt"), do_lower_case=True)
+    sd = syn.lxmert_state_dict(variant="rich", head_sigma=d["head_sigma"], **d["layers"])
+    inp = syn.make_inputs(len(d["qids"]), 20, seed=d["inputs_seed"])
+    ids, mask, seg = tok.encode_batch(d["sents"], d["max_seq_length"])
+    logit, x = O.gqa_model_forward(sd, inp["feat"], inp["pos"], torch.from_numpy(ids).long(), torch.from_numpy(seg).long(),
+                                   torch.from_numpy(mask).long())
+    mu, P = syn.maha_stats()
+    label2ans = [f"answer{j}" for j in range(d["num_answers"])] + ["UQ"]
+    qid2label = {q: dict(map(tuple, l)) for q, l in zip(d["qids"], d["labels"])}
+    for method, fn in (("msp", S.msp), ("energy", S.energy_top2), ("maha", lambda _: S.mahalanobis(x, mu, P)[:2])):
+        s, l = fn(logit)
+        q2a = {q: (label2ans[int(a)], b) for q, a, b in zip(d["qids"], l.numpy(), s.numpy())}
+        ev = GQAOODEvaluator(qid2label, 0.5)
+        res = ev.evaluate(q2a)
+        path = str(tmp_path / f"{method}_predict.json")
+        ev.dump_result(q2a, path)
+        rows, want = json.load(open(path)), json.loads(d["predict_json"][method])
+        assert [(r["questionId"], r["prediction"]) for r in rows] == [(w["questionId"], w["prediction"]) for w in want]
+        assert max(abs(r["confidence"] - w["confidence"]) for r, w in zip(rows, want)) <= (1.01e-4 if method == "maha" else 0.0)
+        if method != "maha":
+            assert open(path).read() == d["predict_json"][method]
+        assert set(res) == set(d["results"][method])
+        for k, v in d["results"][method].items():
+            assert float(res[k]) == v, (method, k)

@@ -180,3 +180,61 @@ def test_gqa_train_mirror_runs_rp_steps_and_updates_the_model(cuda_device, tmp_p
     bce = torch.nn.BCEWithLogitsLoss()
     t = target[:, :-1].to(logits_after.device)
     assert float(bce(logits_after, t)) < float(bce(logits_before, t))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_drop_in_flow_reproduces_the_reference_stack_end_to_end(cuda_device, tmp_path, precision):
+    """Sentences in -> ``<method>_predict.json`` + result dict out, against the UNMODIFIED reference stack run end to end in the
+    build container (tests/golden/make_golden_dropin.py: the real ``GQAModel`` / ``GQAModel_maha`` built by their own constructors,
+    the reference tokenizer, ``GQA.ood_evaluate`` of gqa_conf / gqa_energy / gqa_maha, the real evaluator's ``dump_result``).
+    This side: ``GQAModel_maha.forward(feat, pos, sent)`` (same state dict, same vocab, MAX_GQA_LENGTH = 30), the device
+    scorers, the product evaluator — the loop is the drivers' (gqa_conf.py:301-330)."""
+    import gzip
+    from rgqa_b200.tasks.gqa_data import GQAOODEvaluator
+    from rgqa_b200.tasks.gqa_model import GQAModel_maha
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    d = json.load(gzip.open(os.path.join(gold, "dropin_reference.json.gz"), "rt"))
+    sys.argv = ["x"]
+    a = types.SimpleNamespace(llayers=d["layers"]["l_layers"], xlayers=d["layers"]["x_layers"], rlayers=d["layers"]["r_layers"],
+                              from_scratch=False, precision=precision, vocab=os.path.join(gold, "tokenizer_vocab.txt"),
+                              max_seq_length=d["max_seq_length"])
+    m = GQAModel_maha(d["num_answers"], args=a, max_seq_length=d["max_seq_length"])
+    m.load_state_dict(syn.lxmert_state_dict(variant="rich", head_sigma=d["head_sigma"], **d["layers"]), strict=True)
+    m = m.to(cuda_device)
+    mu, P = syn.maha_stats()
+    m.engine().set_maha(mu, P)
+    inp = syn.make_inputs(len(d["qids"]), 20, seed=d["inputs_seed"])
+    label2ans = [f"answer{j}" for j in range(d["num_answers"])] + ["UQ"]
+    qid2label = {q: dict(map(tuple, l)) for q, l in zip(d["qids"], d["labels"])}
+    bs = d["batch"]
+    # bf16 operands move the logits by ~1e-2 (DESIGN §4): MSP sits on the flat part of the sigmoid, the other two scale with it
+    tol = {"fp32": {"msp": 1.5e-4, "energy": 2e-4, "maha": 2e-3}, "bf16": {"msp": 1.5e-3, "energy": 6e-2, "maha": 1.0}}[precision]
+    for method in ("msp", "energy", "maha"):
+        quesid2ans = {}
+        for lo in range(0, len(d["qids"]), bs):
+            sl = slice(lo, lo + bs)
+            logit, x = m(inp["feat"][sl].to(cuda_device), inp["pos"][sl].to(cuda_device), d["sents"][sl])
+            score, label = m.engine().score(method, logits=logit, pooled=x)
+            for qid, l, s in zip(d["qids"][sl], label.cpu().numpy(), score.cpu().numpy()):
+                quesid2ans[qid] = (label2ans[l], s)
+        ev = GQAOODEvaluator(qid2label, 0.5)
+        res = ev.evaluate(quesid2ans)
+        path = str(tmp_path / f"{method}_predict.json")
+        ev.dump_result(quesid2ans, path)
+        rows, want = json.load(open(path)), json.loads(d["predict_json"][method])
+        assert [r["questionId"] for r in rows] == [r["questionId"] for r in want]
+        same = [r["prediction"] == w["prediction"] for r, w in zip(rows, want)]
+        if precision == "fp32":
+            assert all(same), (method, same)
+        else:
+            # the smallest top-2 MSP margin of this random-init batch is 3e-5, inside bf16's logit noise (DESIGN §4): labels of
+            # near-tied classes may swap; the rows that agree must still carry the reference's confidence
+            assert sum(same) >= len(same) // 2, (method, same)
+        conf_err = max(abs(r["confidence"] - w["confidence"]) for r, w, ok in zip(rows, want, same) if ok)
+        assert conf_err <= tol[method], (method, conf_err)
+        if precision == "fp32":
+            assert set(res) == set(d["results"][method])
+            for k, v in d["results"][method].items():
+                assert abs(float(res[k]) - v) <= 1e-6 + 2e-2 * abs(v), (method, k, float(res[k]), v)
+            if all(r["confidence"] == w["confidence"] for r, w in zip(rows, want)):
+                assert open(path).read() == d["predict_json"][method]          # byte-identical wire file
