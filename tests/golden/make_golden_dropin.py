@@ -2,7 +2,8 @@
 
     real ``tasks.gqa_model.GQAModel`` / ``GQAModel_maha`` (own constructor: ``LXRTEncoder`` -> ``BertTokenizer`` +
     ``VisualBertForLXRFeature.from_pretrained``, 2 / 1 / 1 layers, MAX_GQA_LENGTH = 30)  ->  ``GQA.ood_evaluate`` of
-    ``gqa_conf.py`` (MSP), ``gqa_energy.py`` (top-2 energy), ``gqa_maha.py`` (Mahalanobis, --noise 0)  ->  real
+    ``gqa_conf.py`` (MSP), ``gqa_energy.py`` (top-2 energy), ``gqa_maha.py`` (Mahalanobis, --noise 0 and 1e-3), ``gqa_odin.py``
+    (ODIN, --noise 1e-3)  ->  real
     ``GQAOODEvaluator.evaluate`` + ``dump_result``  ->  ``<method>_predict.json`` as the reference writes it.
 
     python tests/golden/make_golden_dropin.py         # build container only; writes dropin_reference.json.gz
@@ -30,6 +31,7 @@ sys.dont_write_bytecode = True
 import make_golden_scorers as G   # noqa: E402
 
 N, BS, A, SEED = 40, 16, 1842, 2718
+NOISE = 1e-3
 HEAD_SIGMA = 0.05          # logits of a few units: sigmoids stay distinct (0.2 saturates fp32 sigmoid to 1.0: every MSP label ties)
 LAYERS = dict(l_layers=2, x_layers=1, r_layers=1)
 BERT_BASE = {"attention_probs_dropout_prob": 0.1, "hidden_act": "gelu", "hidden_dropout_prob": 0.1, "hidden_size": 768,
@@ -69,6 +71,7 @@ def main():
         import tasks.gqa_conf as conf
         import tasks.gqa_energy as energy
         import tasks.gqa_maha as maha
+        import tasks.gqa_odin as odin
         from tasks.gqa_model import GQAModel, GQAModel_maha
         torch.manual_seed(0)
         model = GQAModel(A)
@@ -108,10 +111,21 @@ def main():
     out = {"qids": qids, "sents": sents, "labels": labels, "inputs_seed": SEED, "layers": LAYERS, "max_seq_length": 30,
            "num_answers": A, "batch": BS, "head_sigma": HEAD_SIGMA, "predict_json": {}, "results": {}, "versions": {"torch": torch.__version__}}
     mu, P = syn.maha_stats()
+    out["scores"], out["answers"] = {}, {}
+    captured = {}
+    orig_eval = gqa_data.GQAOODEvaluator.evaluate
+
+    def spy(self, quesid2ans):                                        # full-precision scores (the wire file rounds to 4 decimals)
+        captured["q"] = dict(quesid2ans)
+        return orig_eval(self, quesid2ans)
+    gqa_data.GQAOODEvaluator.evaluate = spy
     with tempfile.TemporaryDirectory() as tmp:
         def run(name, fn):
             path = os.path.join(tmp, f"{name}_predict.json")
             res = fn(path)
+            q = captured.pop("q")
+            out["scores"][name] = [float(q[k][1]) for k in qids]
+            out["answers"][name] = [q[k][0] for k in qids]
             out["predict_json"][name] = open(path).read()
             out["results"][name] = {k: float(v) for k, v in res.items()}
             print(name, {k: round(float(v), 4) for k, v in res.items()})
@@ -119,6 +133,11 @@ def main():
         run("energy", lambda p: energy.GQA.ood_evaluate(types.SimpleNamespace(model=model), tup, dump=p))
         me = types.SimpleNamespace(model=model_maha, train_tuple=tup)
         run("maha", lambda p: maha.GQA.ood_evaluate(me, tup, (mu.clone(), P.clone()), dump=p))
+        # the two input-gradient scorers on the real model (autograd through the reference LXMERT)
+        args.noise, args.temperature = NOISE, 1.0
+        out["noise"] = NOISE
+        run("odin", lambda p: odin.GQA.ood_evaluate(types.SimpleNamespace(model=model), tup, dump=p))
+        run("maha_noise", lambda p: maha.GQA.ood_evaluate(me, tup, (mu.clone(), P.clone()), dump=p))
     with gzip.open(os.path.join(HERE, "dropin_reference.json.gz"), "wt", compresslevel=9) as f:
         json.dump(out, f)
 

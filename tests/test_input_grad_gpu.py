@@ -119,3 +119,39 @@ def test_mixed_precision_input_gradients_and_odin(cuda_device):
     assert (torch.sign(gf.cpu())[big] == torch.sign(ref_gf)[big]).float().mean().item() >= 0.97
     assert torch.equal(l.cpu().long(), ref_l)
     torch.testing.assert_close(s.cpu(), ref_s, rtol=1e-2, atol=1e-3)
+
+
+def test_odin_and_mahalanobis_with_noise_against_the_reference_stack(cuda_device):
+    """The two input-gradient scorers end to end against the UNMODIFIED reference: ``gqa_odin.GQA.ood_evaluate`` and
+    ``gqa_maha.GQA.ood_evaluate`` (--noise 1e-3) run on the real ``GQAModel`` / ``GQAModel_maha`` with torch autograd through the
+    reference LXMERT (tests/golden/make_golden_dropin.py), sentences tokenised by the product tokenizer, batches of the
+    reference loader (the losses are batch means).  The perturbation moves the reference's own scores by up to 8.6e-5 (ODIN)
+    and 0.084 (Mahalanobis); the CUDA path must land on the perturbed scores, not the plain ones."""
+    import gzip, json, os
+    from rgqa_b200.lxrt.input_grad import LXMERTInputGrad
+    from rgqa_b200.lxrt.tokenization import BertTokenizer
+    from rgqa_b200.tasks.gqa_odin import mahalanobis_noise_scores, odin_scores
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    d = json.load(gzip.open(os.path.join(gold, "dropin_reference.json.gz"), "rt"))
+    sd = syn.lxmert_state_dict(variant="rich", head_sigma=d["head_sigma"], **d["layers"])
+    ig = LXMERTInputGrad(sd, device=cuda_device, **d["layers"])
+    tok = BertTokenizer.from_pretrained(os.path.join(gold, "tokenizer_vocab.txt"), do_lower_case=True)
+    ids, mask, seg = (torch.from_numpy(a).long() for a in tok.encode_batch(d["sents"], d["max_seq_length"]))
+    inp = syn.make_inputs(len(d["qids"]), 20, seed=d["inputs_seed"])
+    mu, P = syn.maha_stats()
+    label2ans = [f"answer{j}" for j in range(d["num_answers"])]
+    got = {"odin": ([], []), "maha_noise": ([], [])}
+    for lo in range(0, len(d["qids"]), d["batch"]):
+        sl = slice(lo, lo + d["batch"])
+        s, l, _, _ = odin_scores(ig, inp["feat"][sl], inp["pos"][sl], ids[sl], seg[sl], mask[sl], 1.0, d["noise"])
+        got["odin"][0].append(s.cpu()), got["odin"][1].append(l.cpu())
+        s, l, _, _ = mahalanobis_noise_scores(ig, inp["feat"][sl], inp["pos"][sl], ids[sl], seg[sl], mask[sl], mu, P, d["noise"])
+        got["maha_noise"][0].append(s.cpu()), got["maha_noise"][1].append(l.cpu())
+    for name, plain, tol in (("odin", "msp", 4e-6), ("maha_noise", "maha", 1e-2)):
+        s = torch.cat(got[name][0]).double().numpy()
+        ans = [label2ans[int(i)] for i in torch.cat(got[name][1])]
+        want, base = np.asarray(d["scores"][name]), np.asarray(d["scores"][plain])
+        assert ans == d["answers"][name], name
+        err = np.abs(s - want).max()
+        shift = np.abs(want - base).max()
+        assert err <= tol and shift >= 8 * err, (name, err, shift)
