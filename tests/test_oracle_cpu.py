@@ -270,3 +270,34 @@ def test_oracle_and_host_code_reproduce_the_reference_stack_wire_files(tmp_path)
         assert set(res) == set(d["results"][method])
         for k, v in d["results"][method].items():
             assert float(res[k]) == v, (method, k)
+
+
+def test_uniter_oracle_and_host_code_reproduce_the_reference_stack_wire_files(tmp_path):
+    """BASELINE config 3 on the CPU: product tokenizer -> oracle UNITER + scorers -> product evaluator against the UNMODIFIED
+    reference ``GQAUNITER`` driven by ``gqa_conf`` / ``gqa_energy`` ``GQA.ood_evaluate`` (tests/golden/make_golden_dropin_uniter.py)."""
+    import gzip
+    from oracle import lxmert_oracle as O
+    from oracle import scorers_oracle as S
+    from rgqa_b200.lxrt.tokenization import BertTokenizer
+    from rgqa_b200.tasks.gqa_data import GQAOODEvaluator
+    d = json.load(gzip.open(os.path.join(GOLD, "dropin_uniter_reference.json.gz"), "rt"))
+    tok = BertTokenizer.from_pretrained(os.path.join(GOLD, "tokenizer_vocab.txt"), do_lower_case=True)
+    sd = syn.uniter_state_dict(variant="rich", head_sigma=d["head_sigma"])
+    inp = syn.make_inputs(len(d["qids"]), 20, seed=d["inputs_seed"], vocab=28996)
+    ids, mask, seg = tok.encode_batch(d["sents"], d["max_seq_length"])
+    logit, _ = O.gqa_uniter_forward(sd, inp["feat"], inp["pos7"], torch.from_numpy(ids).long(), torch.from_numpy(seg).long(),
+                                    torch.from_numpy(mask).long())
+    label2ans = [f"answer{j}" for j in range(d["num_answers"])] + ["UQ"]
+    qid2label = {q: dict(map(tuple, l)) for q, l in zip(d["qids"], d["labels"])}
+    for method, fn in (("msp", S.msp), ("energy", S.energy_top2)):
+        s, l = fn(logit)
+        q2a = {q: (label2ans[int(a)], b) for q, a, b in zip(d["qids"], l.numpy(), s.numpy())}
+        ev = GQAOODEvaluator(qid2label, 0.5)
+        res = ev.evaluate(q2a)
+        path = str(tmp_path / f"{method}_predict.json")
+        ev.dump_result(q2a, path)
+        rows, want = json.load(open(path)), json.loads(d["predict_json"][method])
+        assert [(r["questionId"], r["prediction"]) for r in rows] == [(w["questionId"], w["prediction"]) for w in want]
+        assert max(abs(r["confidence"] - w["confidence"]) for r, w in zip(rows, want)) <= 1.01e-4
+        for k, v in d["results"][method].items():
+            assert abs(float(res[k]) - v) <= 1e-12, (method, k)

@@ -238,3 +238,41 @@ def test_drop_in_flow_reproduces_the_reference_stack_end_to_end(cuda_device, tmp
                 assert abs(float(res[k]) - v) <= 1e-6 + 2e-2 * abs(v), (method, k, float(res[k]), v)
             if all(r["confidence"] == w["confidence"] for r, w in zip(rows, want)):
                 assert open(path).read() == d["predict_json"][method]          # byte-identical wire file
+
+
+def test_uniter_drop_in_flow_reproduces_the_reference_stack_end_to_end(cuda_device, tmp_path):
+    """BASELINE config 3: ``GQAUNITER.forward(feat, pos7, sent)`` + device scorers + product evaluator against the UNMODIFIED
+    reference ``GQAUNITER`` (12 layers, own constructor and tokenizer) driven by ``gqa_conf`` / ``gqa_energy`` ``GQA.ood_evaluate``
+    (tests/golden/make_golden_dropin_uniter.py), fp32 path."""
+    import gzip
+    from rgqa_b200.tasks.gqa_data import GQAOODEvaluator
+    from rgqa_b200.uniter.uniter import GQAUNITER
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    d = json.load(gzip.open(os.path.join(gold, "dropin_uniter_reference.json.gz"), "rt"))
+    sys.argv = ["x"]
+    a = _args("fp32")
+    a.vocab = os.path.join(gold, "tokenizer_vocab.txt")
+    m = GQAUNITER(d["num_answers"], args=a)
+    m.load_state_dict(syn.uniter_state_dict(variant="rich", head_sigma=d["head_sigma"]), strict=True)
+    m = m.to(cuda_device)
+    inp = syn.make_inputs(len(d["qids"]), 20, seed=d["inputs_seed"], vocab=28996)
+    label2ans = [f"answer{j}" for j in range(d["num_answers"])] + ["UQ"]
+    qid2label = {q: dict(map(tuple, l)) for q, l in zip(d["qids"], d["labels"])}
+    bs = d["batch"]
+    for method in ("msp", "energy"):
+        quesid2ans = {}
+        for lo in range(0, len(d["qids"]), bs):
+            sl = slice(lo, lo + bs)
+            logit = m(inp["feat"][sl].to(cuda_device), inp["pos7"][sl].to(cuda_device), d["sents"][sl])
+            score, label = m.engine().score(method, logits=logit)
+            for qid, l, s in zip(d["qids"][sl], label.cpu().numpy(), score.cpu().numpy()):
+                quesid2ans[qid] = (label2ans[l], s)
+        ev = GQAOODEvaluator(qid2label, 0.5)
+        res = ev.evaluate(quesid2ans)
+        path = str(tmp_path / f"{method}_predict.json")
+        ev.dump_result(quesid2ans, path)
+        rows, want = json.load(open(path)), json.loads(d["predict_json"][method])
+        assert [(r["questionId"], r["prediction"]) for r in rows] == [(w["questionId"], w["prediction"]) for w in want]
+        assert max(abs(r["confidence"] - w["confidence"]) for r, w in zip(rows, want)) <= 2e-4
+        for k, v in d["results"][method].items():
+            assert abs(float(res[k]) - v) <= 1e-6 + 2e-2 * abs(v), (method, k, float(res[k]), v)
