@@ -9,9 +9,10 @@ with scikit-learn's ``EmpiricalCovariance`` and the per-class Mahalanobis loop) 
 vectors) were executed in the build container on a tiny stand-in model and synthetic questions
 (``tests/golden/make_golden_scorers.py`` -> ``tests/golden/scorers_reference.npz``); ``msp``, ``energy_top2``, ``mahalanobis`` and
 ``sample_estimator`` reproduce their scores / labels / class means / precision matrix.  ``gqa_conf.py`` imports ``vilt`` -> ``timm``
-(absent): that one import is stubbed for the run, the driver code itself is untouched.  Still **unpinned**: ``energy_sum`` / ``lse``
-(training-time expressions, :131 / :185) and the ensemble's combine step (``gqa_ensemble.py:165-177`` sits in the script's
-``__main__`` block and cannot be called), both one-line numpy / torch expressions.  scikit-learn is 1.9.0 here, 1.1.1 in the
+(absent): that one import is stubbed for the run, the driver code itself is untouched.  ``ensemble`` is pinned too: the combine step
+(``gqa_ensemble.py:155-177``) sits in the script's ``__main__`` block, whose statements the golden script compiles from the
+reference file at run time and executes unmodified.  Still **unpinned**: ``energy_sum`` / ``lse`` (training-time expressions,
+:131 / :185), one-line torch expressions.  scikit-learn is 1.9.0 here, 1.1.1 in the
 reference's environment.yml:111.
 """
 from __future__ import annotations

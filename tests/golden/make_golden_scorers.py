@@ -4,7 +4,8 @@
 
 The reference's task drivers are executed as they are — ``GQA.ood_evaluate`` of ``src/tasks/gqa_conf.py`` (MSP, :296-330),
 ``gqa_energy.py`` (:194-213), ``gqa_maha.py`` (``sample_estimator`` :120-189, ``ood_evaluate`` :191-276 with ``--noise`` 0 and
-> 0), ``gqa_odin.py`` (:85-137) and ``gqa_ensemble.py`` (:95-110) — as unbound methods on a stand-in ``self`` that carries a
+> 0), ``gqa_odin.py`` (:85-137) and ``gqa_ensemble.py`` (:95-110, and its ``__main__`` combine step :135-215, whose statements are
+compiled from the reference file at run time) — as unbound methods on a stand-in ``self`` that carries a
 tiny differentiable model (``tiny_vqa.TinyVQA``) and an in-memory loader, so that every line between "batch comes out of
 the loader" and "``quesid2ans`` goes into the evaluator" is the reference's own.  The real ``GQAOODEvaluator`` then produces
 the result dict.  What is stubbed, and why it does not touch the lines under test:
@@ -151,6 +152,28 @@ def main():
     for tag, m in (("ens0", model), ("ens1", model2)):
         q = ens.GQA.ood_evaluate(types.SimpleNamespace(model=m), test_tuple)
         out[f"{tag}.sigmoid"] = np.stack([q[k] for k in te[0]])
+    # ---- the ensemble's combine step (gqa_ensemble.py:135-215) sits in the script's `__main__` block: its statements are read
+    # from the reference file at run time and executed, unmodified, in the module's own namespace, where only `GQA` (-> a
+    # stand-in whose `load` switches between the two tiny checkpoints and whose `ood_evaluate` / `get_target` are the reference
+    # methods) and `get_tuple` (-> the in-memory test tuple) are replaced
+    import ast
+    src = open(ens.__file__).read()
+    main_if = [n for n in ast.parse(src).body if isinstance(n, ast.If) and "__main__" in ast.get_source_segment(src, n.test)][0]
+    main_code = compile(ast.Module(body=main_if.body, type_ignores=[]), ens.__file__, "exec")
+
+    class EnsGQA:
+        ood_evaluate = ens.GQA.ood_evaluate
+        get_target = ens.GQA.get_target
+
+        def load(self, path):
+            self.model = {"ckpt0": model, "ckpt1": model2}[path]
+    for method in ("mean", "multiply"):
+        with tempfile.TemporaryDirectory() as tmp:
+            ns = dict(vars(ens), GQA=EnsGQA, get_tuple=lambda *a, **k: test_tuple)
+            args.load, args.test, args.batch_size, args.ensemble_method = "ckpt0,ckpt1", "testdev", BS, method
+            args.predict, args.predict_closeset, args.output = False, False, tmp
+            exec(main_code, ns)
+            record(f"ens_{method}", json.load(open(os.path.join(tmp, "testdev_result.json"))))
     # ---- Mahalanobis: sample_estimator (gqa_maha.py:120-189) then ood_evaluate (:191-276)
     model.maha = True
     with tempfile.TemporaryDirectory() as tmp:

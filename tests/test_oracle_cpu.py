@@ -185,6 +185,13 @@ def test_scorer_oracles_pinned_to_reference_drivers(scorer_golden):
     np.testing.assert_allclose(torch.sigmoid(logit).numpy(), z["ens0.sigmoid"], rtol=1e-6)
     np.testing.assert_allclose(torch.sigmoid(logit2).numpy(), z["ens1.sigmoid"], rtol=1e-6)
 
+    # ... and the combine step itself (gqa_ensemble.py:155-177, executed from the reference script's __main__ block)
+    for method in ("mean", "multiply"):
+        es, el = S.ensemble([z["ens0.sigmoid"], z["ens1.sigmoid"]], method)
+        np.testing.assert_array_equal(el, z[f"ens_{method}.label"])
+        np.testing.assert_allclose(es.astype(np.float64), z[f"ens_{method}.score"], rtol=1e-6)
+    assert np.abs(z["ens_mean.score"] - z["ens_multiply.score"]).max() > 1e-3
+
     # sample_estimator (gqa_maha.py:120-189): class means + sklearn EmpiricalCovariance.precision_
     ftr, btr = torch.from_numpy(z["feat_train"]), torch.from_numpy(z["box_train"])
     with torch.no_grad():
@@ -218,7 +225,7 @@ def test_scorer_oracles_pinned_to_reference_drivers(scorer_golden):
     assert np.abs(z["odin.score"] - z["odin_plain.score"]).max() > 1e-3
 
 
-@pytest.mark.parametrize("name", ["msp", "energy", "odin", "maha", "maha_noise"])
+@pytest.mark.parametrize("name", ["msp", "energy", "odin", "maha", "maha_noise", "ens_mean", "ens_multiply"])
 def test_evaluator_reproduces_reference_result_dicts_from_driver_scores(scorer_golden, name):
     """Product host code (no GPU needed): the reference drivers' (answer, score) pairs through this package's evaluator give the
     result dict the reference's ``GQAOODEvaluator`` printed for them, float for float."""
