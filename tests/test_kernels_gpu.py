@@ -462,6 +462,15 @@ def test_cuda_scorers_against_reference_driver_goldens(cuda_device):
         s, l = ops.score_logits(logit.to(cuda_device), mode)
         np.testing.assert_array_equal(l.cpu().numpy(), z[f"{name}.label"])
         np.testing.assert_allclose(s.double().cpu().numpy(), z[f"{name}.score"], rtol=1e-5)
+    sd2 = {k[len("model2."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("model2.")}
+    model2 = TinyVQA(sd["fc_feat.weight"].shape[1], D, C, maha=True)
+    model2.load_state_dict(sd2, strict=True)
+    with torch.no_grad():
+        logit2, _ = model2(torch.from_numpy(z["feat_test"]), torch.from_numpy(z["box_test"]), meta["sents_test"])
+    for method in ("mean", "multiply"):                                  # gqa_ensemble.py:155-177 (the script's __main__ block)
+        s, l = ops.score_ensemble([logit.to(cuda_device).contiguous(), logit2.to(cuda_device).contiguous()], method)
+        np.testing.assert_array_equal(l.cpu().numpy(), z[f"ens_{method}.label"])
+        np.testing.assert_allclose(s.double().cpu().numpy(), z[f"ens_{method}.score"], rtol=1e-5)
     mu = torch.from_numpy(z["maha.mean"]).float().to(cuda_device)        # gqa_maha.py:228-236, :270
     P = torch.from_numpy(z["maha.precision"]).float().to(cuda_device)
     s, l = ops.mahalanobis(x.to(cuda_device), mu, P)[:2]
