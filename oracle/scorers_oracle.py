@@ -11,8 +11,8 @@ vectors) were executed in the build container on a tiny stand-in model and synth
 ``sample_estimator`` reproduce their scores / labels / class means / precision matrix.  ``gqa_conf.py`` imports ``vilt`` -> ``timm``
 (absent): that one import is stubbed for the run, the driver code itself is untouched.  ``ensemble`` is pinned too: the combine step
 (``gqa_ensemble.py:155-177``) sits in the script's ``__main__`` block, whose statements the golden script compiles from the
-reference file at run time and executes unmodified.  Still **unpinned**: ``energy_sum`` / ``lse`` (training-time expressions,
-:131 / :185), one-line torch expressions.  scikit-learn is 1.9.0 here, 1.1.1 in the
+reference file at run time and executes unmodified.  ``energy_sum`` / ``lse`` (training-time expressions, :135 / :131) are pinned to the
+values the local ``E_f`` takes inside the unmodified ``gqa_energy.GQA.train`` loop (read with a trace function).  scikit-learn is 1.9.0 here, 1.1.1 in the
 reference's environment.yml:111.
 """
 from __future__ import annotations

@@ -174,6 +174,42 @@ def main():
             args.predict, args.predict_closeset, args.output = False, False, tmp
             exec(main_code, ns)
             record(f"ens_{method}", json.load(open(os.path.join(tmp, "testdev_result.json"))))
+    # ---- the two training-time energies (gqa_energy.py:131 logsumexp with --mceLoss, :135 sum of softplus): locals of the
+    # UNMODIFIED `GQA.train` loop, read with a trace function while one epoch runs on a throw-away copy of the tiny model
+    import copy
+    from lxrt.optimization import BertAdam
+
+    def run_energy_train(mce):
+        seen, rec = set(), []
+
+        def tracer(frame, event, arg):
+            if frame.f_code.co_name != "train" or not frame.f_code.co_filename.endswith("gqa_energy.py"):
+                return None
+
+            def local(fr, ev, a):
+                e = fr.f_locals.get("E_f")
+                if ev == "line" and e is not None and id(e) not in seen:
+                    seen.add(id(e))
+                    rec.append((fr.f_locals["logit"].detach().clone(), e.detach().clone()))
+                return local
+            return local
+        m = copy.deepcopy(model)
+        m.maha = False
+        args.mce_loss, args.epochs, args.chart = mce, 1, False
+        with tempfile.TemporaryDirectory() as tmp:
+            me_tr = types.SimpleNamespace(model=m, optim=BertAdam(list(m.parameters()), lr=1e-3, warmup=0.1, t_total=4),
+                                          bce_loss=torch.nn.BCEWithLogitsLoss(), mce_loss=torch.nn.CrossEntropyLoss(ignore_index=-1),
+                                          valid_tuple=None, output=tmp, save=lambda name: None)
+            tr_tuple = DataTuple(dset_tr, train_tuple.loader, types.SimpleNamespace(evaluate=lambda q: 0.0, dataset=dset_tr))
+            sys.settrace(tracer)
+            try:
+                energy.GQA.train(me_tr, tr_tuple, None)
+            finally:
+                sys.settrace(None)
+        assert len(rec) == len(train_tuple.loader)
+        return torch.cat([r[0] for r in rec]).numpy(), torch.cat([r[1] for r in rec]).numpy()
+    out["train_energy_sum.logit"], out["train_energy_sum.E_f"] = run_energy_train(False)
+    out["train_lse.logit"], out["train_lse.E_f"] = run_energy_train(True)
     # ---- Mahalanobis: sample_estimator (gqa_maha.py:120-189) then ood_evaluate (:191-276)
     model.maha = True
     with tempfile.TemporaryDirectory() as tmp:

@@ -462,6 +462,9 @@ def test_cuda_scorers_against_reference_driver_goldens(cuda_device):
         s, l = ops.score_logits(logit.to(cuda_device), mode)
         np.testing.assert_array_equal(l.cpu().numpy(), z[f"{name}.label"])
         np.testing.assert_allclose(s.double().cpu().numpy(), z[f"{name}.score"], rtol=1e-5)
+    for name, mode in (("train_energy_sum", "energy_sum"), ("train_lse", "lse")):   # gqa_energy.py:135, :131 (locals of GQA.train)
+        s, _ = ops.score_logits(torch.from_numpy(z[f"{name}.logit"]).to(cuda_device), mode)
+        np.testing.assert_allclose(s.cpu().numpy(), z[f"{name}.E_f"], rtol=1e-4)
     sd2 = {k[len("model2."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("model2.")}
     model2 = TinyVQA(sd["fc_feat.weight"].shape[1], D, C, maha=True)
     model2.load_state_dict(sd2, strict=True)

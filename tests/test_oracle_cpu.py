@@ -181,6 +181,11 @@ def test_scorer_oracles_pinned_to_reference_drivers(scorer_golden):
         np.testing.assert_array_equal(l.numpy(), z[f"{name}.label"])
         np.testing.assert_allclose(s.double().numpy(), z[f"{name}.score"], rtol=1e-6, atol=0)
 
+    # the two training-time energies, locals of the reference `GQA.train` loop (gqa_energy.py:131 with --mceLoss, :135)
+    for name, fn in (("train_energy_sum", S.energy_sum), ("train_lse", S.lse)):
+        e, _ = fn(torch.from_numpy(z[f"{name}.logit"]))
+        np.testing.assert_allclose(e.numpy(), z[f"{name}.E_f"], rtol=1e-6)
+
     # ensemble members (gqa_ensemble.py:95-110): the per-question sigmoid vectors the combine step consumes
     np.testing.assert_allclose(torch.sigmoid(logit).numpy(), z["ens0.sigmoid"], rtol=1e-6)
     np.testing.assert_allclose(torch.sigmoid(logit2).numpy(), z["ens1.sigmoid"], rtol=1e-6)
