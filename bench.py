@@ -21,6 +21,11 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 when the variable is unset.  The reference arm is meant to use every host core it can, so
+# that default is undone before the OpenMP runtime reads it (torch.set_num_threads below then sizes the pools).
+if "reference" in sys.argv and os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+    del os.environ["OMP_NUM_THREADS"]
+
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
