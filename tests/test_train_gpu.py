@@ -244,7 +244,7 @@ def test_rp_finetune_loop_kernels_follow_the_reference_train_loop(cuda_device):
             want_loss = meta["steps"][step]["loss_times_A"]
             assert abs(float(loss.item()) - want_loss) <= 2e-5 * abs(want_loss), (step, float(loss.item()), want_loss)
             got = torch.cat([p.reshape(-1) for p in params]).cpu().numpy()
-            np.testing.assert_allclose(got, z["params_after"][step], rtol=2e-4, atol=2e-6, err_msg=f"step {step}")
+            np.testing.assert_allclose(got, z["params_after"][step], rtol=2e-4, atol=1e-5, err_msg=f"step {step}")
             step += 1
     assert step == len(meta["steps"]) == 6
     # the six updates moved the parameters by far more than the tolerance (the comparison is not vacuous)
