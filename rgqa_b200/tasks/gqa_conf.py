@@ -76,7 +76,14 @@ class GQA:
         self.model.load_state_dict(tr.state_dict(), strict=True)
         return losses
 
-    def ood_evaluate(self, dataset, batch_size, method, dump=None, maha=None):
+    def ood_evaluate(self, dataset, batch_size=None, method=None, dump=None, maha=None):
+        """Two call forms.  ``ood_evaluate(dataset, batch_size, method, dump=, maha=)``: the batch-sharded sweep over a pre-tokenised
+        data set (``GQAEval``).  ``ood_evaluate(eval_tuple, dump=)`` / ``ood_evaluate(eval_tuple, (mean, precision), dump=)``: the
+        reference's own signature (gqa_conf.py:296, gqa_energy.py:194, gqa_maha.py:191) — ``eval_tuple = (dset, loader, _)`` whose
+        loader yields ``(ques_id, feats, boxes, sent, ...)`` host batches with SENTENCES; the scorer is ``args.method``."""
+        if isinstance(dataset, tuple) and len(dataset) == 3:
+            pack = batch_size if batch_size is not None else maha
+            return self._ood_evaluate_tuple(dataset, self.args.method if method is None else method, dump, pack)
         rank = dist.get_rank() if dist.is_initialized() else 0
         world = dist.get_world_size() if dist.is_initialized() else 1
         lo, hi = shard_range(dataset.n, rank, world)
@@ -86,6 +93,31 @@ class GQA:
             self.model.engine().set_maha(*maha)
         ev = GQAEval(self.model, dataset, method=method, tau=self.args.tau)
         return ev.ood_evaluate(dataset.loader(batch_size, lo, hi), dump=dump if rank == 0 else None)
+
+
+    def _ood_evaluate_tuple(self, eval_tuple, method, dump, pack):
+        """The reference loop (gqa_conf.py:301-330): model call on each loader batch, device scorer, ``quesid2ans`` in loader order,
+        ``GQAOODEvaluator.evaluate`` + ``dump_result``."""
+        from .gqa_data import GQAOODEvaluator
+        dset, loader, _ = eval_tuple
+        if method == "maha":
+            if pack is None:
+                raise RuntimeError("Mahalanobis needs {mean, precision} (sample_estimator pickle, gqa_maha.py:185-188)")
+            mean, precision = (torch.as_tensor(t).float() for t in pack)     # gqa_maha.py:194-201
+            self.model.engine().set_maha(mean, precision)
+        dev = next(self.model.parameters()).device
+        evaluator = GQAOODEvaluator(dset, self.args.tau)
+        quesid2ans = {}
+        for datum_tuple in loader:
+            ques_id, feats, boxes, sent = datum_tuple[:4]   # avoid handling target
+            logit, x = self.model(feats.to(dev), boxes.to(dev), list(sent))
+            score, label = self.model.engine().score(method, logits=logit, pooled=x)
+            for qid, l, s in zip(ques_id, label.cpu().numpy(), score.cpu().numpy()):
+                quesid2ans[qid] = (dset.label2ans[l], s)
+        results = evaluator.evaluate(quesid2ans)
+        if dump is not None:
+            evaluator.dump_result(quesid2ans, dump)
+        return results
 
 
 def main(argv=None):
