@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RGQA_ABI_VERSION 1
+#define RGQA_ABI_VERSION 2
 
 /* architectures */
 #define RGQA_ARCH_LXMERT 0
@@ -111,6 +111,18 @@ int rgqa_uniter_forward(rgqa_handle* h, void* stream, const void* feat, int feat
                         const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
                         float* pooled_out, float* logits_out);
 
+/* Forward + rejection scorers in ONE call (either architecture; BASELINE north_star item 3).  score_mask has bit
+ * (1 << RGQA_SCORE_*) set per scorer wanted.  In bf16 handles the answer-head GEMM's epilogue reduces its own logit rows
+ * (arg-max of sigmoid, top-2, softplus sum, logsumexp: src/tasks/gqa_conf.py:326, gqa_energy.py:131,185,204-206) and the
+ * Mahalanobis scorer (gqa_maha.py:228-236,270) is one split-bf16 tensor-core GEMM with the arg-max in its epilogue, so
+ * neither [B, num_answers] matrix reaches HBM unless logits_out is given.
+ * scores_out: [5][B] f32, row = RGQA_SCORE_* code (rows of scorers not requested are untouched);
+ * labels_out: [2][B] int32, row 0 = arg-max of sigmoid(logit) (label of MSP / ENERGY_* / LSE), row 1 = Mahalanobis class.
+ * pooled_out / logits_out as in rgqa_lxmert_forward (may be NULL). */
+int rgqa_forward_scored(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos,
+                        const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L, unsigned score_mask,
+                        float* pooled_out, float* logits_out, float* scores_out, int32_t* labels_out);
+
 /* Mahalanobis statistics: class means mu [num_answers, hidden] f32 and precision P [hidden, hidden] f32. */
 int rgqa_set_maha(rgqa_handle* h, const float* mu, const float* precision, int on_device);
 /* score_out: [B] f32, label_out: [B] int32.  MSP / ENERGY_* / LSE read `logits` [B, num_answers];
@@ -123,10 +135,15 @@ int rgqa_score(rgqa_handle* h, void* stream, int mode, const float* logits, cons
  * M >= 1024), "gemm_staged" (1 = swizzled-smem + TMA-store epilogue in the pair kernel), "gemm_ln" (1 = fused
  * GEMM + residual + LayerNorm kernel), "two_streams" (1 = visual branch on a second stream), "graphs" (1 = CUDA-graph replay of the forward for
  * B <= 128), "defer_ln" (1 = LXMERT bf16 batches of >= 1024 token rows run without LayerNorm kernels: hidden states stay
- * pre-LayerNorm as bf16 hi/lo pairs + row statistics, see rgqa_gemm_bf16_resid_hl), "attn_tma" (1 = TMA-fed persistent attention kernel for large batches), "qkv_planes" (1 = Q|K|V projections written head-major for that kernel), "pdl", "gemm_debug". */
+ * pre-LayerNorm as bf16 hi/lo pairs + row statistics, see rgqa_gemm_bf16_resid_hl), "attn_tma" (1 = TMA-fed persistent attention kernel for large batches), "qkv_planes" (1 = Q|K|V projections written head-major for that kernel), "maha_tc" (1 = Mahalanobis on the tensor
+ * cores in bf16 handles), "visn_fused" (1 = one-kernel visual feature encoder), "attn_fused" (1 = self-attention inside the
+ * Q|K|V projection's epilogue), "pdl", "gemm_debug". */
 int rgqa_set_option(const char* name, int value);
 /* Kernels enqueued by this library since it was loaded. */
 long long rgqa_launch_count(void);
+/* CUDA graphs this handle has instantiated: large batches are captured per (shape, feature / box pointers), so a caller
+ * that hands a fresh buffer every call keeps capturing (and pays for it); a sweep over two staging slots captures twice. */
+long long rgqa_graph_captures(const rgqa_handle* h);
 /* When on, every GEMM / attention launch is bracketed by CUDA events on its own stream. */
 void rgqa_prof_enable(int on);
 /* Sum of event-timed durations (ms), algorithmic FLOPs and launch counts per kernel kind since the last
@@ -138,6 +155,25 @@ int rgqa_prof_collect(double* ms_sum, double* flops_sum, long long* count);
 int rgqa_gemm_bf16(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                    const void* resid, int64_t ldr, void* out, int64_t ldo, int out_dtype, int M, int N, int K,
                    int epilogue);
+/* BertAttention.forward for self-attention (src/lxrt/modeling.py:320-347, :376-386) as ONE kernel: the Q|K|V projection on
+ * tcgen05 with the attention of each (sample, head) in its epilogue.  A: bf16 [B*S, 768] rows (pre-LayerNorm when ln_stats
+ * [B*S][12] is given, with W_hm / bias_hm folded accordingly); W_hm bf16 [2304, 768] and bias_hm f32 [2304] packed head-major
+ * ([head][q|k|v][64] rows); key_mask int32 [B, S] or NULL; ctx bf16 [B*S, 768] (row stride ldo).  12 heads of 64, S <= 64. */
+int rgqa_qkv_attention_fused(void* stream, const void* A, int64_t lda, const void* W_hm, const float* bias_hm, const float* ln_stats,
+                             float ln_eps, const int32_t* key_mask, void* ctx, int64_t ldo, int B, int S, int heads);
+/* VisualFeatEncoder.forward (src/lxrt/modeling.py:507-517) as ONE tcgen05 kernel: (LN(feat·W1ᵀ + b1) + LN(box·W2ᵀ + b2)) / 2
+ * as a bf16 hi/lo pair [M, 768] (hi + lo = the fp32 value to 2^-17) and identity row statistics [M, 12].  feat [M, K] and
+ * W1 [768, K] are both fp32 (feat_dtype F32: kind::tf32 MMAs read them as they are) or both bf16; box [M, box_dim] f32. */
+int rgqa_visn_embed(void* stream, const void* feat, int feat_dtype, const void* W1, const float* b1, const float* g1,
+                    const float* be1, const float* boxes, int box_dim, const float* W2, const float* b2, const float* g2,
+                    const float* be2, float eps, void* out_hi, void* out_lo, float* out_stats, int M, int K);
+/* logits = A·Wᵀ + bias with the logit scorers reduced in the epilogue (the answer head's last GEMM, gqa_model.py:27 +
+ * gqa_conf.py:326 / gqa_energy.py:204-206): scores [4][M] f32 in RGQA_SCORE_* order, labels [M] int32; logits_out
+ * ([M, N] f32 dense) may be NULL.  flags: bit0 also ENERGY_SUM, bit1 also LSE.  work: rgqa_reduce_work_bytes(M, N) bytes. */
+int rgqa_gemm_bf16_reduce_logits(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                 float* logits_out, int M, int N, int K, int flags, void* work, int64_t work_bytes,
+                                 float* scores, int32_t* labels);
+int64_t rgqa_reduce_work_bytes(int M, int N);
 /* out_act (bf16 [M,768]) and out_res (f32 [M,768], may be NULL) = LayerNorm(A·Wᵀ + bias + resid) * gamma + beta,
  * one kernel; N must be 768 (BertAttOutput / BertOutput, src/lxrt/modeling.py:357-361, :411-415). */
 int rgqa_gemm_bf16_ln(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,

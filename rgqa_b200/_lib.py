@@ -10,6 +10,7 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
+ABI_VERSION = 2  # include/rgqa_b200.h: RGQA_ABI_VERSION
 LIB_PATH = _PKG / "_C" / "librgqa_b200.so"
 
 # constants mirrored from include/rgqa_b200.h
@@ -46,10 +47,16 @@ SIGNATURES = {
     "rgqa_finalize_weights": (_i, [_vp]),
     "rgqa_lxmert_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "rgqa_uniter_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "rgqa_forward_scored": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, C.c_uint, _vp, _vp, _vp, _vp]),
     "rgqa_set_maha": (_i, [_vp, _vp, _vp, _i]),
     "rgqa_score": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "rgqa_set_option": (_i, [C.c_char_p, _i]),
     "rgqa_launch_count": (C.c_longlong, []),
+    "rgqa_graph_captures": (C.c_longlong, [_vp]),
+    "rgqa_gemm_bf16_reduce_logits": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp, _vp]),
+    "rgqa_reduce_work_bytes": (_i64, [_i, _i]),
+    "rgqa_qkv_attention_fused": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _f, _vp, _vp, _i64, _i, _i, _i]),
+    "rgqa_visn_embed": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i]),
     "rgqa_prof_enable": (None, [_i]),
     "rgqa_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "rgqa_gemm_bf16": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i]),
@@ -91,9 +98,12 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists() and build_if_missing and os.environ.get("RGQA_B200_NO_BUILD") != "1":
+    if build_if_missing and os.environ.get("RGQA_B200_NO_BUILD") != "1":
+        # a library older than its sources would be called with a stale ABI: rebuild (a no-op when it is up to date;
+        # skipped when there is no nvcc and a library exists, e.g. a deployment box that received the prebuilt .so)
         from . import build as _build
-        _build.build()
+        if not LIB_PATH.exists() or (_build.have_nvcc() and _build.stale()):
+            _build.build()
     if not LIB_PATH.exists():
         raise RuntimeError(
             f"rgqa_b200: CUDA extension {LIB_PATH} is missing; run `python -m rgqa_b200.build` "
@@ -103,6 +113,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
+    got = lib.rgqa_abi_version()
+    if got != ABI_VERSION:
+        raise RuntimeError(f"rgqa_b200: {LIB_PATH} has ABI version {got}, the Python binding expects {ABI_VERSION}; "
+                           "rebuild with `python -m rgqa_b200.build --force`")
     _lib = lib
     return lib
 

@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT_DIR = PKG / "_C"
 LIB = OUT_DIR / "librgqa_b200.so"
-SOURCES = ["api.cu", "prof.cu", "gemm_tcgen05.cu", "gemm_ln_tcgen05.cu", "gemm_simt.cu", "attention.cu", "rowops.cu", "scorers.cu", "estimator.cu", "optim.cu", "backward.cu"]
+SOURCES = ["api.cu", "prof.cu", "gemm_tcgen05.cu", "gemm_ln_tcgen05.cu", "visn_embed_tcgen05.cu", "qkv_attn_tcgen05.cu", "gemm_simt.cu", "attention.cu", "rowops.cu", "scorers.cu", "estimator.cu", "optim.cu", "backward.cu"]
 HEADERS = ["common.cuh", "kernels.h", "../../include/rgqa_b200.h"]
 
 NVCC_FLAGS = [
@@ -35,7 +35,11 @@ def _nvcc() -> str:
     return cand
 
 
-def _stale() -> bool:
+def have_nvcc() -> bool:
+    return bool(shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"))
+
+
+def stale() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
@@ -44,7 +48,7 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not _stale():
+    if not force and not stale():
         return LIB
     OUT_DIR.mkdir(exist_ok=True)
     obj_dir = OUT_DIR / "obj"

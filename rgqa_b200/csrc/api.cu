@@ -86,6 +86,8 @@ struct AttW {
   LNp ln;
   Folded qkv_f;   // folded with the LayerNorm that produced this block's input (language rows for the cross block)
   Folded qkv_f2;  // cross block only: folded with the visual branch's LayerNorm
+  void* qkv_hm = nullptr;    // self-attention blocks: the Q|K|V weight this block's forward uses (folded when it has a
+  float* qkv_hm_b = nullptr;  // predecessor LayerNorm) re-packed head-major [head][q|k|v][64] for qkv_attention_fused
   float* out_bb = nullptr;   // out.b + beta of the LayerNorm owed to the block's input (the producer epilogue's bias)
   float* out_bb2 = nullptr;  // cross block only: with the visual branch's beta
 };
@@ -125,6 +127,8 @@ struct rgqa_handle {
   // visual embedding
   Linear visn_fc;                 // [H, 2048]
   float *box_W = nullptr, *box_b = nullptr;  // [H, pos_dim], [H] fp32
+  float *visn_W32 = nullptr;                 // [H, 2048] fp32 copy of visn_fc (tf32 operand of the one-kernel visual encoder)
+  float *box_Wp = nullptr, *box_stat = nullptr;  // [H][8] zero-padded box_fc weight; closed-form LayerNorm statistics (make_box_stats)
   LNp visn_ln, box_ln, img_ln;    // img_ln: UNITER's third LN
   std::vector<LayerW> l_layers, r_layers;
   std::vector<XLayerW> x_layers;
@@ -134,7 +138,9 @@ struct rgqa_handle {
   LNp fc_ln;
   // Mahalanobis
   float *maha_mu = nullptr, *maha_P = nullptr, *maha_m = nullptr;
+  void* maha_Ws = nullptr;  // bf16 [H + A, 3H]: split-bf16 rows of the stack [P; mu·P] (tensor-core Mahalanobis, bf16 handles)
   bool has_maha = false;
+  long long graph_captures = 0;  // CUDA graphs instantiated so far (a caller that never repeats its buffers keeps capturing)
 
   // second stream for the visual branch (language / visual layers are independent between joins)
   cudaStream_t side = nullptr;
@@ -147,7 +153,7 @@ struct rgqa_handle {
     int seen = 0;
     int kernels = 0;
     cudaGraphExec_t exec = nullptr;
-    DevBuf feat, pos, ids, seg, mask, pooled, logits;
+    DevBuf feat, pos, ids, seg, mask, pooled, logits, scores, labels;
   };
   struct GraphKey {
     long long shape;
@@ -163,6 +169,18 @@ struct rgqa_handle {
 
   // workspace
   DevBuf hidA, hidB, resA, resB, qkv, ctx, inter, pre, featb, headbuf, mahabuf;
+  DevBuf maha_xs, red_fc, red_maha, red_cnt;  // fused row reductions: split pooled rows, partial records, arrival counters
+};
+
+// What one forward call produces.  score_mask: bit (1 << RGQA_SCORE_*) per scorer wanted; scores [5][B] (row = scorer code),
+// labels [2][B] (row 0: arg-max of sigmoid(logit), the MSP / energy label; row 1: Mahalanobis arg-max class).
+struct FwdOut {
+  float* pooled = nullptr;
+  float* logits = nullptr;
+  unsigned score_mask = 0;
+  float* scores = nullptr;
+  int32_t* labels = nullptr;
+  bool any() const { return pooled != nullptr || logits != nullptr || score_mask != 0; }
 };
 
 namespace {
@@ -355,6 +373,47 @@ int copy_raw(rgqa_handle* h, const std::string& name, int64_t d0, int64_t d1, fl
   return pack_vec(h, s, n, 1, out);
 }
 
+// box_fc has K <= 8: its LayerNorm statistics over the 768 outputs are closed forms of the box vector.  With v = (box, 1):
+// mean_n y_n = v · (colmean(W2), mean(b2)) and var_n y_n = vᵀ C v, C = second moments of the CENTRED rows (fp64 here).
+// Layout of bstat: [0..7] colmean, [8] mean(b2), [16..96] C (9 x 9, index 8 = the constant).  W2p = W2 padded to [H][8].
+int make_box_stats(const float* W2_dev, const float* b2_dev, int H, int K, std::vector<float>* W2p, std::vector<float>* bstat) {
+  std::vector<float> w(static_cast<size_t>(H) * K), b(H);
+  RGQA_CUDA_OK(cudaMemcpy(w.data(), W2_dev, w.size() * 4, cudaMemcpyDeviceToHost));
+  RGQA_CUDA_OK(cudaMemcpy(b.data(), b2_dev, b.size() * 4, cudaMemcpyDeviceToHost));
+  W2p->assign(static_cast<size_t>(H) * 8, 0.f);
+  bstat->assign(16 + 81, 0.f);
+  double cm[9] = {0};
+  for (int n = 0; n < H; ++n) {
+    for (int j = 0; j < K; ++j) {
+      (*W2p)[static_cast<size_t>(n) * 8 + j] = w[static_cast<size_t>(n) * K + j];
+      cm[j] += w[static_cast<size_t>(n) * K + j];
+    }
+    cm[8] += b[n];
+  }
+  for (int j = 0; j < 9; ++j) cm[j] /= H;
+  double C[9][9] = {{0}};
+  for (int n = 0; n < H; ++n) {
+    double r[9] = {0};
+    for (int j = 0; j < K; ++j) r[j] = w[static_cast<size_t>(n) * K + j] - cm[j];
+    r[8] = b[n] - cm[8];
+    for (int a = 0; a < 9; ++a)
+      for (int c = 0; c < 9; ++c) C[a][c] += r[a] * r[c];
+  }
+  for (int j = 0; j < 8; ++j) (*bstat)[j] = static_cast<float>(cm[j]);
+  (*bstat)[8] = static_cast<float>(cm[8]);
+  for (int a = 0; a < 9; ++a)
+    for (int c = 0; c < 9; ++c) (*bstat)[16 + a * 9 + c] = static_cast<float>(C[a][c] / H);
+  return 0;
+}
+int upload_vec(rgqa_handle* h, const std::vector<float>& v, float** out) {
+  float* d = nullptr;
+  RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d), v.size() * sizeof(float)));
+  h->owned.push_back(d);
+  RGQA_CUDA_OK(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
+
 // ---- deferred-LayerNorm weight folding (bf16 path) ------------------------------------------------
 // names[i] (+ ".weight" / ".bias") are stacked row-wise, each [rows, K]; folded with the LayerNorm `ln` of the input.
 int fold_stack(rgqa_handle* h, const std::vector<std::string>& names, int rows, int K, const LNp& ln, Folded* out) {
@@ -396,6 +455,30 @@ int fold_qkv(rgqa_handle* h, const std::string& p, const char* self_name, const 
   if (pred == nullptr) return 0;
   const std::string s = p + "." + self_name;
   return fold_stack(h, {s + ".query", s + ".key", s + ".value"}, h->cfg.hidden, h->cfg.hidden, *pred, out);
+}
+// [q rows | k rows | v rows] -> [head][q | k | v][64 rows]: one 192-row tile of the fused projection + attention kernel is
+// one head.  Source = the folded weight when the block sits behind a LayerNorm, else the plain one.
+int pack_head_major(rgqa_handle* h, AttW* w) {
+  const int H = h->cfg.hidden, heads = h->cfg.heads, hd = H / heads;
+  const char* W = static_cast<const char*>(w->qkv_f.W != nullptr ? w->qkv_f.W : w->qkv.W);
+  const float* b = w->qkv_f.W != nullptr ? w->qkv_f.b : w->qkv.b;
+  char* Wo = nullptr;
+  float* bo = nullptr;
+  RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&Wo), static_cast<size_t>(3) * H * H * 2));
+  h->owned.push_back(Wo);
+  RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&bo), static_cast<size_t>(3) * H * sizeof(float)));
+  h->owned.push_back(bo);
+  const size_t blk = static_cast<size_t>(hd) * H * 2;  // 64 weight rows
+  for (int head = 0; head < heads; ++head)
+    for (int part = 0; part < 3; ++part) {
+      const size_t src_row = static_cast<size_t>(part) * H + static_cast<size_t>(head) * hd;
+      const size_t dst_row = (static_cast<size_t>(head) * 3 + part) * hd;
+      RGQA_CUDA_OK(cudaMemcpyAsync(Wo + dst_row * H * 2, W + src_row * H * 2, blk, cudaMemcpyDeviceToDevice, nullptr));
+      RGQA_CUDA_OK(cudaMemcpyAsync(bo + dst_row, b + src_row, hd * sizeof(float), cudaMemcpyDeviceToDevice, nullptr));
+    }
+  w->qkv_hm = Wo;
+  w->qkv_hm_b = bo;
+  return 0;
 }
 int make_identity_ln(rgqa_handle* h) {  // gamma = 1, beta = 0: the "LayerNorm" owed to an already-normalised state
   const int H = h->cfg.hidden;
@@ -520,15 +603,44 @@ int ensure_workspace(rgqa_handle* h, long long Mt, long long Mv, int B) {
   return h->headbuf.ensure(head + 1024);
 }
 
-// pooler + answer head on the hidden rows `hid` (first token of each sample, row stride S*H)
+int ensure_reduce_ws(rgqa_handle* h, DevBuf& part, int M, int N) {
+  if (part.ensure(row_reduce_part_bytes(M, N))) return 1;
+  const size_t need = static_cast<size_t>(row_reduce_counters(M) > 64 ? row_reduce_counters(M) : 64) * sizeof(int);
+  if (need > h->red_cnt.bytes) {
+    if (h->red_cnt.ensure(need * 2)) return 1;
+    RGQA_CUDA_OK(cudaMemset(h->red_cnt.p, 0, h->red_cnt.bytes));  // the kernels leave every counter at zero again
+  }
+  return 0;
+}
+
+// Mahalanobis on the tensor cores: [t | G] = xs · [P; mu·P]^T as ONE split-bf16 GEMM (K' = 3H) whose epilogue forms
+// q = <t, x> and max / arg-max_c (G_c - m_c/2); score = max - q/2 (gqa_maha.py:228-236,270).  The [B, A] matrix stays on chip.
+int maha_tc(rgqa_handle* h, cudaStream_t st, const float* x, int B, float* score, int32_t* label) {
+  const int H = h->cfg.hidden, A = h->cfg.num_answers;
+  if (h->maha_xs.ensure(static_cast<size_t>(B) * 3 * H * 2) || ensure_reduce_ws(h, h->red_maha, B, H + A)) return 1;
+  if (split_bf16x3(st, x, H, h->maha_xs.p, B, H, 0)) return 1;
+  RowReduce r;
+  r.kind = RED_MAHA;
+  r.split = H;
+  r.x = x;
+  r.m = h->maha_m;
+  r.part = static_cast<float*>(h->red_maha.p);
+  r.counter = static_cast<int*>(h->red_cnt.p);
+  r.scores = score;
+  r.labels = label;
+  return gemm_bf16_reduce(st, h->maha_xs.p, 3 * H, h->maha_Ws, 3 * H, nullptr, nullptr, 0, B, H + A, 3 * H, r);
+}
+
+int maha_core(cudaStream_t st, const float* x, const float* mu, const float* Psym, const float* m, int B, int A, int H,
+              float* work, float* score, int32_t* label, float* full);
+
+// pooler + answer head (+ fused scorers) on the hidden rows `hid` (first token of each sample, row stride S*H)
 // `stats` != nullptr: `hid` is a deferred-LayerNorm state (un-normalised bf16 rows + statistics) and the pooler uses its
 // folded weight.
-int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, float* pooled_out, float* logits_out,
-               const float* stats = nullptr) {
+int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, const FwdOut& o, const float* stats = nullptr) {
   const int H = h->cfg.hidden, A = h->cfg.num_answers;
   const size_t es = act_size(h);
   const int dt = act_dtype(h);
-  const int of32 = dt == DT_F32;
   char* base = static_cast<char*>(h->headbuf.p);
   float* pooled = reinterpret_cast<float*>(base);
   char* pooled_act = base + static_cast<size_t>(B) * H * 4;
@@ -537,8 +649,12 @@ int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, f
   float* logits_ws = reinterpret_cast<float*>(h1n + static_cast<size_t>(B) * 2 * H * es);
   // 16-byte align the logits scratch
   logits_ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(logits_ws) + 15) & ~static_cast<uintptr_t>(15));
+  const unsigned logit_scorers = o.score_mask & 0xFu;
+  const bool want_maha = (o.score_mask >> RGQA_SCORE_MAHA) & 1u;
+  RGQA_CHECK(o.score_mask == 0 || (o.scores != nullptr && o.labels != nullptr), "forward: scorers requested without score / label outputs");
+  RGQA_CHECK(!want_maha || h->has_maha, "forward: Mahalanobis statistics were not set (rgqa_set_maha)");
 
-  float* pdst = pooled_out != nullptr ? pooled_out : pooled;
+  float* pdst = o.pooled != nullptr ? o.pooled : pooled;
   if (stats != nullptr) {
     if (gemm_bf16_folded(st, hid, static_cast<long long>(S) * H, h->pooler_f.W, H, h->pooler_f.b, nullptr, 0, pdst, H, 1, B, H,
                          H, EPI_TANH, stats, nullptr, h->cfg.ln_eps, static_cast<long long>(S) * 12))
@@ -546,7 +662,17 @@ int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, f
   } else if (gemm(h, st, hid, static_cast<long long>(S) * H, h->pooler, nullptr, 0, pdst, H, 1, B, EPI_TANH)) {
     return 1;
   }
-  if (A <= 0 || logits_out == nullptr) return 0;
+  if (want_maha) {  // scores row RGQA_SCORE_MAHA, labels row 1
+    float* sc = o.scores + static_cast<size_t>(RGQA_SCORE_MAHA) * B;
+    int32_t* lb = o.labels + B;
+    if (h->maha_Ws != nullptr && option_get(OPT_MAHA_TC) != 0) {
+      if (maha_tc(h, st, pdst, B, sc, lb)) return 1;
+    } else {
+      if (h->mahabuf.ensure((static_cast<size_t>(B) * (H + A + 1) + 16) * 4)) return 1;
+      if (maha_core(st, pdst, h->maha_mu, h->maha_P, h->maha_m, B, A, H, static_cast<float*>(h->mahabuf.p), sc, lb, nullptr)) return 1;
+    }
+  }
+  if (A <= 0 || (o.logits == nullptr && logit_scorers == 0)) return 0;
   const void* a0 = pdst;
   if (dt == DT_BF16) {
     if (cast_f32_to_bf16(st, pdst, pooled_act, static_cast<long long>(B) * H)) return 1;
@@ -554,9 +680,26 @@ int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, f
   }
   if (gemm(h, st, a0, H, h->fc0, nullptr, 0, h1, 2 * H, 1, B, EPI_GELU)) return 1;
   if (layernorm(st, dt, h1, 2 * H, h->fc_ln.g, h->fc_ln.b, h1n, nullptr, B, 2 * H, h->cfg.ln_eps)) return 1;
-  (void)of32;
-  (void)logits_ws;
-  return gemm(h, st, h1n, 2 * H, h->fc3, nullptr, 0, logits_out, A, 1, B, EPI_BIAS);
+  if (logit_scorers == 0) return gemm(h, st, h1n, 2 * H, h->fc3, nullptr, 0, o.logits, A, 1, B, EPI_BIAS);
+  if (dt == DT_BF16) {
+    // the answer-head GEMM reduces its own rows: MSP / energy / logsumexp leave the epilogue, the logits only if asked for
+    if (ensure_reduce_ws(h, h->red_fc, B, A)) return 1;
+    RowReduce r;
+    r.kind = RED_LOGITS;
+    r.flags = ((o.score_mask >> RGQA_SCORE_ENERGY_SUM) & 1u) | (((o.score_mask >> RGQA_SCORE_LSE) & 1u) << 1);
+    r.part = static_cast<float*>(h->red_fc.p);
+    r.counter = static_cast<int*>(h->red_cnt.p);
+    r.scores = o.scores;
+    r.labels = o.labels;
+    return gemm_bf16_reduce(st, h1n, 2 * H, h->fc3.W, h->fc3.K, h->fc3.b, o.logits, A, B, A, h->fc3.K, r);
+  }
+  // fp32 handles: logits through the fp32 GEMM, then the row kernels
+  float* lg = o.logits != nullptr ? o.logits : logits_ws;
+  if (gemm(h, st, h1n, 2 * H, h->fc3, nullptr, 0, lg, A, 1, B, EPI_BIAS)) return 1;
+  for (int mode = RGQA_SCORE_MSP; mode <= RGQA_SCORE_LSE; ++mode)
+    if ((o.score_mask >> mode) & 1u)
+      if (score_logits(st, mode, lg, A, B, A, o.scores + static_cast<size_t>(mode) * B, o.labels)) return 1;
+  return 0;
 }
 
 }  // namespace
@@ -601,6 +744,7 @@ void rgqa_destroy(rgqa_handle* h) {
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     kv.second.feat.release(); kv.second.pos.release(); kv.second.ids.release(); kv.second.seg.release();
     kv.second.mask.release(); kv.second.pooled.release(); kv.second.logits.release();
+    kv.second.scores.release(); kv.second.labels.release();
   }
   if (h->cap) cudaStreamDestroy(h->cap);
   if (h->side) cudaStreamDestroy(h->side);
@@ -617,6 +761,11 @@ void rgqa_destroy(rgqa_handle* h) {
   h->featb.release();
   h->headbuf.release();
   h->mahabuf.release();
+  h->maha_xs.release();
+  h->red_fc.release();
+  h->red_maha.release();
+  h->red_cnt.release();
+  if (h->maha_Ws) cudaFree(h->maha_Ws);
   if (h->maha_mu) cudaFree(h->maha_mu);
   if (h->maha_P) cudaFree(h->maha_P);
   if (h->maha_m) cudaFree(h->maha_m);
@@ -704,6 +853,14 @@ int rgqa_finalize_weights(rgqa_handle* h) {
     if (make_linear(h, b + "pooler.dense", H, H, &h->pooler)) return 1;
     h->pooler_f = Folded{};
     if (c.precision == RGQA_PREC_BF16) {
+      // one-kernel visual feature encoder: fp32 copy of visn_fc for the tf32 path, padded box_fc weight, closed-form statistics
+      {
+        std::vector<float> w2p, bst;
+        if (copy_raw(h, b + "encoder.visn_fc.visn_fc.weight", H, c.visual_feat_dim, &h->visn_W32) ||
+            make_box_stats(h->box_W, h->box_b, H, c.visual_pos_dim, &w2p, &bst) || upload_vec(h, w2p, &h->box_Wp) ||
+            upload_vec(h, bst, &h->box_stat))
+          return 1;
+      }
       // deferred LayerNorm: every consumer of a hidden state gets a copy of its weight folded with the LayerNorm that
       // (notionally) produced that state; the embeddings' outputs are not behind one (nullptr)
       if (make_identity_ln(h)) return 1;
@@ -736,6 +893,11 @@ int rgqa_finalize_weights(rgqa_handle* h) {
         pv = &w.visn_ffn.ln;
       }
       if (pl != nullptr && fold_stack(h, {b + "pooler.dense"}, H, H, *pl, &h->pooler_f)) return 1;
+      if (H == 768 && c.heads == 12) {
+        for (auto& w : h->l_layers) if (pack_head_major(h, &w.att)) return 1;
+        for (auto& w : h->r_layers) if (pack_head_major(h, &w.att)) return 1;
+        for (auto& w : h->x_layers) if (pack_head_major(h, &w.lang_self) || pack_head_major(h, &w.visn_self)) return 1;
+      }
     }
   } else {
     const std::string u = "uniter.";
@@ -763,6 +925,8 @@ int rgqa_finalize_weights(rgqa_handle* h) {
         pl = &h->l_layers[i].ffn.ln;
       }
       if (pl != nullptr && fold_stack(h, {u + "pooler.dense"}, H, H, *pl, &h->pooler_f)) return 1;
+      if (H == 768 && c.heads == 12)
+        for (auto& w : h->l_layers) if (pack_head_major(h, &w.att)) return 1;
     }
   }
   if (c.num_answers > 0) {
@@ -841,8 +1005,15 @@ struct DefCtx {
   int att(cudaStream_t st, const AttW& w, const DState& in, const LNp* ln_in, const DState& out, long long r0, int B, int S,
           const int32_t* key_mask) const {
     char* ctx = rows_at(h->ctx.p, r0, H, 2);
-    if (qkv_proj(st, in, ln_in, w.qkv, w.qkv_f, r0, B * S)) return 1;
-    if (attn(st, r0, r0, key_mask, ctx, B, S, S)) return 1;
+    if (w.qkv_hm != nullptr && qkv_attention_fused_ok(B, S, h->cfg.heads, H)) {
+      // the projection tile is consumed where it is produced: no [rows, 2304] round trip, no attention launch
+      if (qkv_attention_fused(st, hi_rows(in, r0), H, w.qkv_hm, w.qkv_hm_b, ln_in != nullptr ? st_rows(in, r0) : nullptr, h->cfg.ln_eps,
+                              key_mask, ctx, H, B, S, h->cfg.heads))
+        return 1;
+    } else {
+      if (qkv_proj(st, in, ln_in, w.qkv, w.qkv_f, r0, B * S)) return 1;
+      if (attn(st, r0, r0, key_mask, ctx, B, S, S)) return 1;
+    }
     return produce(st, ctx, H, w.out, w.out_bb, in, ln_in, out, r0, B * S);
   }
   // BertIntermediate + BertOutput: in (LayerNorm ln_in) -> out (LayerNorm w.ln)
@@ -857,7 +1028,7 @@ struct DefCtx {
 
 static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* feat, int feat_dtype, const float* pos,
                                    const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
-                                   float* pooled_out, float* logits_out) {
+                                   const FwdOut& out) {
   const rgqa_config& c = h->cfg;
   const int H = c.hidden, V = c.num_rois;
   const long long Ml = static_cast<long long>(B) * L, Mv = static_cast<long long>(B) * V, Mt = Ml + Mv;
@@ -897,7 +1068,14 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
   if (embed_ln(st, DT_BF16, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, cur.hi, nullptr, B, L, H,
                c.vocab_size, c.max_position, c.type_vocab, c.ln_eps, cur.lo, cur.stats))
     return 1;
-  {
+  if (option_get(OPT_VISN_FUSED) != 0 && h->box_stat != nullptr && c.visual_feat_dim % 64 == 0) {
+    // ONE kernel: projection (tf32 straight from fp32 features, or bf16), both LayerNorms, box branch, average, hi/lo state
+    const bool f32 = feat_dtype == RGQA_DT_F32;
+    if (visn_embed(sv, feat, f32 ? 1 : 0, c.visual_feat_dim, f32 ? static_cast<const void*>(h->visn_W32) : h->visn_fc.W, h->visn_fc.b,
+                   h->visn_ln.g, h->visn_ln.b, pos, c.visual_pos_dim, h->box_Wp, h->box_b, h->box_ln.g, h->box_ln.b, h->box_stat,
+                   c.ln_eps, d.hi_rows(cur, Ml), d.lo_rows(cur, Ml), d.st_rows(cur, Ml), static_cast<int>(Mv), c.visual_feat_dim))
+      return 1;
+  } else {
     const void* a = feat;
     if (feat_dtype == RGQA_DT_F32) {
       if (cast_f32_to_bf16(sv, static_cast<const float*>(feat), h->featb.p, Mv * c.visual_feat_dim)) return 1;
@@ -953,14 +1131,14 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
     cur = alt;
     alt = t;
   }
-  if (pooled_out == nullptr && logits_out == nullptr) return 0;
-  if (ln_l == nullptr) return head_block(h, st, cur.hi, B, L, pooled_out, logits_out);
-  return head_block(h, st, cur.hi, B, L, pooled_out, logits_out, cur.stats);
+  if (!out.any()) return 0;
+  if (ln_l == nullptr) return head_block(h, st, cur.hi, B, L, out);
+  return head_block(h, st, cur.hi, B, L, out, cur.stats);
 }
 
 static int lxmert_forward_impl(rgqa_handle* h, cudaStream_t st, const void* feat, int feat_dtype, const float* pos,
                                const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
-                               float* pooled_out, float* logits_out) {
+                               const FwdOut& out) {
   const rgqa_config& c = h->cfg;
   const int H = c.hidden, V = c.num_rois;
   const long long Ml = static_cast<long long>(B) * L, Mv = static_cast<long long>(B) * V, Mt = Ml + Mv;
@@ -972,7 +1150,7 @@ static int lxmert_forward_impl(rgqa_handle* h, cudaStream_t st, const void* feat
   // large bf16 batches: no LayerNorm kernels at all (every encoder GEMM then runs on the CTA-pair kernel)
   if (bf && option_get(OPT_DEFER_LN) != 0 && option_get(OPT_GEMM_PAIR) != 0 && option_get(OPT_GEMM_STAGED) != 0 &&
       H == 768 && Ml >= 1024 && h->ones != nullptr)
-    return lxmert_forward_deferred(h, st, feat, feat_dtype, pos, ids, seg, mask, B, L, pooled_out, logits_out);
+    return lxmert_forward_deferred(h, st, feat, feat_dtype, pos, ids, seg, mask, B, L, out);
   Hid cur{h->hidA.p, bf ? static_cast<float*>(h->resA.p) : static_cast<float*>(h->hidA.p)};
   Hid alt{h->hidB.p, bf ? static_cast<float*>(h->resB.p) : static_cast<float*>(h->hidB.p)};
 
@@ -1062,8 +1240,8 @@ static int lxmert_forward_impl(rgqa_handle* h, cudaStream_t st, const void* feat
     alt = t;
   }
   // ---- pooler + answer head (modeling.py:884, gqa_model.py:40-41) ----
-  if (pooled_out == nullptr && logits_out == nullptr) return 0;
-  return head_block(h, st, cur.act, B, L, pooled_out, logits_out);
+  if (!out.any()) return 0;
+  return head_block(h, st, cur.act, B, L, out);
 }
 
 // Small batches are launch-bound (170-210 kernels + ~330 tensor-map encodes per forward: ~3 ms of host time at B = 32,
@@ -1074,32 +1252,37 @@ static int lxmert_forward_impl(rgqa_handle* h, cudaStream_t st, const void* feat
 // keyed additionally by the caller's feature / box pointers, which are then used in place (a sweep feeds them from two
 // alternating staging buffers); only the small id / mask inputs and the outputs go through staging copies.
 // The first call of a key runs eagerly (lazy per-kernel attribute setup must not happen under capture).
-int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos,
-                        const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
-                        float* pooled_out, float* logits_out) {
+static int lxmert_forward_graphed(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos,
+                                 const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L, const FwdOut& out) {
   RGQA_CHECK(h != nullptr, "rgqa_lxmert_forward: null handle");
   RGQA_CHECK(h->cfg.arch == RGQA_ARCH_LXMERT, "rgqa_lxmert_forward: handle was created for another architecture");
   RGQA_CHECK(h->finalized, "rgqa_lxmert_forward: weights are not finalized");
   RGQA_CHECK(feat != nullptr && pos != nullptr && ids != nullptr && mask != nullptr, "rgqa_lxmert_forward: null input");
   RGQA_CHECK(B > 0, "rgqa_lxmert_forward: empty batch");
   RGQA_CHECK(L >= 2 && L <= 64, "rgqa_lxmert_forward: L=%d out of range [2,64]", L);
-  RGQA_CHECK(logits_out == nullptr || h->cfg.num_answers > 0, "rgqa_lxmert_forward: handle has no answer head");
+  RGQA_CHECK((out.logits == nullptr && (out.score_mask & 0xFu) == 0) || h->cfg.num_answers > 0, "rgqa_lxmert_forward: handle has no answer head");
+  RGQA_CHECK(out.score_mask == 0 || (out.scores != nullptr && out.labels != nullptr), "rgqa_forward_scored: null score / label output");
+  RGQA_CHECK((out.score_mask >> (RGQA_SCORE_MAHA + 1)) == 0, "rgqa_forward_scored: unknown scorer bits 0x%x", out.score_mask);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool use_graph = option_get(OPT_GRAPHS) != 0 && !prof_on();
   const bool big = B > 128;  // large batch: feat / pos are used in place
-  if (!use_graph)
-    return lxmert_forward_impl(h, st, feat, feat_dtype, pos, ids, seg, mask, B, L, pooled_out, logits_out);
+  if (!use_graph) return lxmert_forward_impl(h, st, feat, feat_dtype, pos, ids, seg, mask, B, L, out);
 
   const rgqa_config& c = h->cfg;
   const long long key = (static_cast<long long>(B) << 20) | (static_cast<long long>(L) << 8) | (feat_dtype << 4) |
                         ((option_get(OPT_DEFER_LN) != 0) << 3) | (static_cast<long long>(option_get(OPT_QKV_PLANES) != 0) << 40) |
                         (static_cast<long long>(option_get(OPT_ATTN_TMA) != 0) << 41) |
-                        ((seg != nullptr) << 2) | ((pooled_out != nullptr) << 1) | (logits_out != nullptr);
+                        (static_cast<long long>(option_get(OPT_MAHA_TC) != 0) << 42) |
+                        (static_cast<long long>(option_get(OPT_VISN_FUSED) != 0) << 43) |
+                        (static_cast<long long>(option_get(OPT_ATTN_FUSED) != 0) << 44) |
+                        (static_cast<long long>(out.score_mask & 0x1Fu) << 48) |
+                        ((seg != nullptr) << 2) | ((out.pooled != nullptr) << 1) | (out.logits != nullptr);
   if (h->graphs.size() > 16) {  // callers that never repeat a pointer: do not hoard graphs
     drop_graphs(h);
     for (auto& kv : h->graphs) {
       kv.second.feat.release(); kv.second.pos.release(); kv.second.ids.release(); kv.second.seg.release();
       kv.second.mask.release(); kv.second.pooled.release(); kv.second.logits.release();
+      kv.second.scores.release(); kv.second.labels.release();
     }
     h->graphs.clear();
   }
@@ -1110,24 +1293,29 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
   const size_t n_ids = static_cast<size_t>(B) * L * 4;
   if (g.seen == 0) {  // first sight of this shape: eager run (also grows the workspace), capture on the next call
     g.seen = 1;
-    return lxmert_forward_impl(h, st, feat, feat_dtype, pos, ids, seg, mask, B, L, pooled_out, logits_out);
+    return lxmert_forward_impl(h, st, feat, feat_dtype, pos, ids, seg, mask, B, L, out);
   }
   if (g.exec == nullptr) {
     if ((!big && (g.feat.ensure(n_feat) || g.pos.ensure(n_pos))) || g.ids.ensure(n_ids) || g.seg.ensure(n_ids) || g.mask.ensure(n_ids) ||
         g.pooled.ensure(static_cast<size_t>(B) * c.hidden * 4) ||
-        g.logits.ensure(static_cast<size_t>(B) * (c.num_answers > 0 ? c.num_answers : 1) * 4))
+        g.logits.ensure(static_cast<size_t>(B) * (c.num_answers > 0 ? c.num_answers : 1) * 4) ||
+        g.scores.ensure(static_cast<size_t>(B) * 5 * 4) || g.labels.ensure(static_cast<size_t>(B) * 2 * 4))
       return 1;
     cudaGraph_t graph = nullptr;
     const long long n0 = launch_count();
     // capture on a handle-owned stream: the caller's stream is usually the legacy default stream, which cannot capture
     if (h->cap == nullptr) RGQA_CUDA_OK(cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking));
+    FwdOut go;
+    go.pooled = out.pooled != nullptr ? static_cast<float*>(g.pooled.p) : nullptr;
+    go.logits = out.logits != nullptr ? static_cast<float*>(g.logits.p) : nullptr;
+    go.score_mask = out.score_mask;
+    go.scores = static_cast<float*>(g.scores.p);
+    go.labels = static_cast<int32_t*>(g.labels.p);
     RGQA_CUDA_OK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal));
     const int rc = lxmert_forward_impl(h, h->cap, big ? feat : g.feat.p, feat_dtype, big ? pos : static_cast<const float*>(g.pos.p),
                                        static_cast<const int32_t*>(g.ids.p),
                                        seg != nullptr ? static_cast<const int32_t*>(g.seg.p) : nullptr,
-                                       static_cast<const int32_t*>(g.mask.p), B, L,
-                                       pooled_out != nullptr ? static_cast<float*>(g.pooled.p) : nullptr,
-                                       logits_out != nullptr ? static_cast<float*>(g.logits.p) : nullptr);
+                                       static_cast<const int32_t*>(g.mask.p), B, L, go);
     const cudaError_t ce = cudaStreamEndCapture(h->cap, &graph);
     g.kernels = static_cast<int>(launch_count() - n0);
     note_launch(-g.kernels);  // captured, not launched: each replay is counted below
@@ -1138,6 +1326,7 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
     RGQA_CUDA_OK(ce);
     RGQA_CUDA_OK(cudaGraphInstantiate(&g.exec, graph, 0));
     RGQA_CUDA_OK(cudaGraphDestroy(graph));
+    ++h->graph_captures;
   }
   if (!big) {
     RGQA_CUDA_OK(cudaMemcpyAsync(g.feat.p, feat, n_feat, cudaMemcpyDeviceToDevice, st));
@@ -1148,16 +1337,64 @@ int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat
   RGQA_CUDA_OK(cudaMemcpyAsync(g.mask.p, mask, n_ids, cudaMemcpyDeviceToDevice, st));
   RGQA_CUDA_OK(cudaGraphLaunch(g.exec, st));
   note_launch(g.kernels);
-  if (pooled_out != nullptr)
-    RGQA_CUDA_OK(cudaMemcpyAsync(pooled_out, g.pooled.p, static_cast<size_t>(B) * c.hidden * 4, cudaMemcpyDeviceToDevice, st));
-  if (logits_out != nullptr)
-    RGQA_CUDA_OK(cudaMemcpyAsync(logits_out, g.logits.p, static_cast<size_t>(B) * c.num_answers * 4, cudaMemcpyDeviceToDevice, st));
+  if (out.pooled != nullptr)
+    RGQA_CUDA_OK(cudaMemcpyAsync(out.pooled, g.pooled.p, static_cast<size_t>(B) * c.hidden * 4, cudaMemcpyDeviceToDevice, st));
+  if (out.logits != nullptr)
+    RGQA_CUDA_OK(cudaMemcpyAsync(out.logits, g.logits.p, static_cast<size_t>(B) * c.num_answers * 4, cudaMemcpyDeviceToDevice, st));
+  if (out.score_mask != 0) {  // only the rows that were computed
+    for (int m = RGQA_SCORE_MSP; m <= RGQA_SCORE_MAHA; ++m)
+      if ((out.score_mask >> m) & 1u)
+        RGQA_CUDA_OK(cudaMemcpyAsync(out.scores + static_cast<size_t>(m) * B, static_cast<float*>(g.scores.p) + static_cast<size_t>(m) * B,
+                                     static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, st));
+    if (out.score_mask & 0xFu)
+      RGQA_CUDA_OK(cudaMemcpyAsync(out.labels, g.labels.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, st));
+    if ((out.score_mask >> RGQA_SCORE_MAHA) & 1u)
+      RGQA_CUDA_OK(cudaMemcpyAsync(out.labels + B, static_cast<int32_t*>(g.labels.p) + B, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, st));
+  }
   return 0;
 }
+
+int rgqa_lxmert_forward(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos,
+                        const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
+                        float* pooled_out, float* logits_out) {
+  FwdOut out;
+  out.pooled = pooled_out;
+  out.logits = logits_out;
+  return lxmert_forward_graphed(h, stream, feat, feat_dtype, pos, ids, seg, mask, B, L, out);
+}
+
+static int uniter_forward_impl(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos7,
+                               const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L, const FwdOut& out);
+
+// Forward + rejection scorers in one call (north_star item 3): the answer-head GEMM's epilogue reduces its own logit rows and
+// the Mahalanobis scorer runs on the tensor cores, so neither [B, A] matrix has to reach HBM (logits_out may be NULL).
+int rgqa_forward_scored(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos,
+                        const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L, unsigned score_mask,
+                        float* pooled_out, float* logits_out, float* scores_out, int32_t* labels_out) {
+  RGQA_CHECK(h != nullptr, "rgqa_forward_scored: null handle");
+  FwdOut out;
+  out.pooled = pooled_out;
+  out.logits = logits_out;
+  out.score_mask = score_mask;
+  out.scores = scores_out;
+  out.labels = labels_out;
+  if (h->cfg.arch == RGQA_ARCH_UNITER) return uniter_forward_impl(h, stream, feat, feat_dtype, pos, ids, seg, mask, B, L, out);
+  return lxmert_forward_graphed(h, stream, feat, feat_dtype, pos, ids, seg, mask, B, L, out);
+}
+
+long long rgqa_graph_captures(const rgqa_handle* h) { return h == nullptr ? 0 : h->graph_captures; }
 
 int rgqa_uniter_forward(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos7,
                         const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,
                         float* pooled_out, float* logits_out) {
+  FwdOut out;
+  out.pooled = pooled_out;
+  out.logits = logits_out;
+  return uniter_forward_impl(h, stream, feat, feat_dtype, pos7, ids, seg, mask, B, L, out);
+}
+
+static int uniter_forward_impl(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos7,
+                               const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L, const FwdOut& out) {
   RGQA_CHECK(h != nullptr, "rgqa_uniter_forward: null handle");
   RGQA_CHECK(h->cfg.arch == RGQA_ARCH_UNITER, "rgqa_uniter_forward: handle was created for another architecture");
   RGQA_CHECK(h->finalized, "rgqa_uniter_forward: weights are not finalized");
@@ -1244,15 +1481,15 @@ int rgqa_uniter_forward(rgqa_handle* h, void* stream, const void* feat, int feat
       if (d.att(st, w.att, dc, ln, da, 0, B, S, jmask) || d.ffn(st, w.ffn, da, &w.att.ln, dc, 0, static_cast<int>(Mt))) return 1;
       ln = &w.ffn.ln;
     }
-    if (pooled_out == nullptr && logits_out == nullptr) return 0;
-    return head_block(h, st, dc.hi, B, S, pooled_out, logits_out, ln != nullptr ? dc.stats : nullptr);
+    if (!out.any()) return 0;
+    return head_block(h, st, dc.hi, B, S, out, ln != nullptr ? dc.stats : nullptr);
   }
   for (int i = 0; i < c.l_layers; ++i) {
     if (att_block(h, st, h->l_layers[i].att, cur, alt, 0, B, S, jmask)) return 1;
     if (ffn_block(h, st, h->l_layers[i].ffn, alt, cur, 0, static_cast<int>(Mt))) return 1;
   }
-  if (pooled_out == nullptr && logits_out == nullptr) return 0;
-  return head_block(h, st, cur.act, B, S, pooled_out, logits_out);
+  if (!out.any()) return 0;
+  return head_block(h, st, cur.act, B, S, out);
 }
 
 int rgqa_set_maha(rgqa_handle* h, const float* mu, const float* precision, int on_device) {
@@ -1281,6 +1518,15 @@ int rgqa_set_maha(rgqa_handle* h, const float* mu, const float* precision, int o
   }
   rc = gemm_f32(nullptr, h->maha_mu, H, PT, H, nullptr, nullptr, 0, T, H, A, H, H, EPI_BIAS);
   if (!rc) rc = rowdot(nullptr, T, h->maha_mu, h->maha_m, A, H);
+  if (!rc && h->cfg.precision == RGQA_PREC_BF16) {
+    // tensor-core form: rows of [P; mu·P] as split-bf16 operands (hi | lo | hi), see maha_tc
+    if (h->maha_Ws == nullptr && cudaMalloc(&h->maha_Ws, static_cast<size_t>(H + A) * 3 * H * 2) != cudaSuccess) {
+      set_error("rgqa_set_maha: out of device memory");
+      rc = 1;
+    }
+    if (!rc) rc = split_bf16x3(nullptr, h->maha_P, H, h->maha_Ws, H, H, 1);
+    if (!rc) rc = split_bf16x3(nullptr, T, H, static_cast<char*>(h->maha_Ws) + static_cast<size_t>(H) * 3 * H * 2, A, H, 1);
+  }
   cudaDeviceSynchronize();
   cudaFree(PT);
   cudaFree(T);
@@ -1289,8 +1535,10 @@ int rgqa_set_maha(rgqa_handle* h, const float* mu, const float* precision, int o
   return 0;
 }
 
-static int maha_core(cudaStream_t st, const float* x, const float* mu, const float* Psym, const float* m, int B, int A,
-                     int H, float* work, float* score, int32_t* label, float* full) {
+extern "C++" {
+namespace {
+int maha_core(cudaStream_t st, const float* x, const float* mu, const float* Psym, const float* m, int B, int A,
+              int H, float* work, float* score, int32_t* label, float* full) {
   float* t = work;                                   // [B, H]
   float* q = t + static_cast<size_t>(B) * H;         // [B]
   float* G = q + ((static_cast<size_t>(B) + 3) & ~static_cast<size_t>(3));  // [B, A]
@@ -1299,6 +1547,8 @@ static int maha_core(cudaStream_t st, const float* x, const float* mu, const flo
   if (gemm_f32(st, t, H, mu, H, nullptr, nullptr, 0, G, A, B, A, H, EPI_BIAS)) return 1;    // G = t·muᵀ
   return maha_finish(st, q, G, A, m, B, A, score, label, full);
 }
+}  // namespace
+}  // extern "C++"
 
 int rgqa_score(rgqa_handle* h, void* stream, int mode, const float* logits, const float* pooled, int B,
                float* score_out, int32_t* label_out, float* maha_full_out) {
@@ -1310,6 +1560,9 @@ int rgqa_score(rgqa_handle* h, void* stream, int mode, const float* logits, cons
   if (mode == RGQA_SCORE_MAHA) {
     RGQA_CHECK(h->has_maha, "rgqa_score: Mahalanobis statistics were not set (rgqa_set_maha)");
     RGQA_CHECK(pooled != nullptr, "rgqa_score: MAHA needs the pooled feature");
+    if (h->maha_Ws != nullptr && option_get(OPT_MAHA_TC) != 0 && maha_full_out == nullptr &&
+        reinterpret_cast<uintptr_t>(pooled) % 16 == 0)
+      return maha_tc(h, st, pooled, B, score_out, label_out);
     if (h->mahabuf.ensure((static_cast<size_t>(B) * (H + A + 1) + 16) * 4)) return 1;
     return maha_core(st, pooled, h->maha_mu, h->maha_P, h->maha_m, B, A, H, static_cast<float*>(h->mahabuf.p), score_out,
                      label_out, maha_full_out);
@@ -1357,6 +1610,18 @@ int rgqa_set_option(const char* name, int value) {
     option_set(OPT_PDL, value);
     return 0;
   }
+  if (strcmp(name, "maha_tc") == 0) {
+    option_set(OPT_MAHA_TC, value);
+    return 0;
+  }
+  if (strcmp(name, "visn_fused") == 0) {
+    option_set(OPT_VISN_FUSED, value);
+    return 0;
+  }
+  if (strcmp(name, "attn_fused") == 0) {
+    option_set(OPT_ATTN_FUSED, value);
+    return 0;
+  }
   if (strcmp(name, "gemm_debug") == 0) {  // measurement only: results are wrong while non-zero
     option_set(OPT_GEMM_DEBUG, value);
     return 0;
@@ -1377,6 +1642,47 @@ int rgqa_gemm_bf16(void* stream, const void* A, int64_t lda, const void* W, int6
                    int epilogue) {
   return gemm_bf16(static_cast<cudaStream_t>(stream), A, lda, W, ldw, bias, resid, ldr, out, ldo,
                    out_dtype == RGQA_DT_F32 ? 1 : 0, M, N, K, epilogue);
+}
+int rgqa_gemm_bf16_reduce_logits(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                 float* logits_out, int M, int N, int K, int flags, void* work, int64_t work_bytes,
+                                 float* scores, int32_t* labels) {
+  RGQA_CHECK(work != nullptr && scores != nullptr && labels != nullptr, "rgqa_gemm_bf16_reduce_logits: null argument");
+  const size_t part = row_reduce_part_bytes(M, N), cnt = static_cast<size_t>(row_reduce_counters(M)) * sizeof(int);
+  RGQA_CHECK(static_cast<size_t>(work_bytes) >= part + cnt, "rgqa_gemm_bf16_reduce_logits: work needs %zu bytes", part + cnt);
+  RGQA_CUDA_OK(cudaMemsetAsync(static_cast<char*>(work) + part, 0, cnt, static_cast<cudaStream_t>(stream)));
+  RowReduce r;
+  r.kind = RED_LOGITS;
+  r.flags = flags;
+  r.part = static_cast<float*>(work);
+  r.counter = reinterpret_cast<int*>(static_cast<char*>(work) + part);
+  r.scores = scores;
+  r.labels = labels;
+  return gemm_bf16_reduce(static_cast<cudaStream_t>(stream), A, lda, W, ldw, bias, logits_out, N, M, N, K, r);
+}
+int64_t rgqa_reduce_work_bytes(int M, int N) {
+  return static_cast<int64_t>(row_reduce_part_bytes(M, N) + static_cast<size_t>(row_reduce_counters(M)) * sizeof(int));
+}
+int rgqa_qkv_attention_fused(void* stream, const void* A, int64_t lda, const void* W_hm, const float* bias_hm, const float* ln_stats,
+                             float ln_eps, const int32_t* key_mask, void* ctx, int64_t ldo, int B, int S, int heads) {
+  return qkv_attention_fused(static_cast<cudaStream_t>(stream), A, lda, W_hm, bias_hm, ln_stats, ln_eps, key_mask, ctx, ldo, B, S, heads);
+}
+int rgqa_visn_embed(void* stream, const void* feat, int feat_dtype, const void* W1, const float* b1, const float* g1,
+                    const float* be1, const float* boxes, int box_dim, const float* W2, const float* b2, const float* g2,
+                    const float* be2, float eps, void* out_hi, void* out_lo, float* out_stats, int M, int K) {
+  RGQA_CHECK(W2 != nullptr && b2 != nullptr && box_dim >= 1 && box_dim <= 8, "rgqa_visn_embed: bad box projection");
+  std::vector<float> w2p, bst;
+  if (make_box_stats(W2, b2, 768, box_dim, &w2p, &bst)) return 1;
+  float *dw = nullptr, *ds = nullptr;
+  RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&dw), w2p.size() * 4));
+  RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ds), bst.size() * 4));
+  RGQA_CUDA_OK(cudaMemcpy(dw, w2p.data(), w2p.size() * 4, cudaMemcpyHostToDevice));
+  RGQA_CUDA_OK(cudaMemcpy(ds, bst.data(), bst.size() * 4, cudaMemcpyHostToDevice));
+  const int rc = visn_embed(static_cast<cudaStream_t>(stream), feat, feat_dtype == RGQA_DT_F32 ? 1 : 0, K, W1, b1, g1, be1, boxes, box_dim,
+                            dw, b2, g2, be2, ds, eps, out_hi, out_lo, out_stats, M, K);
+  cudaStreamSynchronize(static_cast<cudaStream_t>(stream));  // test entry point: the scratch tables are freed right away
+  cudaFree(dw);
+  cudaFree(ds);
+  return rc;
 }
 int rgqa_gemm_bf16_ln(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                       const float* resid, int64_t ldr, const float* gamma, const float* beta, float eps, void* out_act,

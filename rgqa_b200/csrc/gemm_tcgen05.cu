@@ -73,6 +73,7 @@ struct GemmParams {
                   // to plane (cb % heads) * 3 + cb / heads
   int vec_ok;  // direct path: rows of out (and resid) are 16-byte aligned -> vector stores allowed
   int debug;   // measurement only (rgqa_set_option "gemm_debug"): bit0 skip TMA stores, bit1 skip epilogue math+smem
+  RowReduce red;  // EPI_REDUCE: row reductions fused into the epilogue (answer-head scorers, Mahalanobis)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -294,6 +295,44 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// ---- EPI_REDUCE: per-row reductions over the tile's columns (see RowReduce in kernels.h) ----------------------------
+struct RedArgMax {
+  float v;
+  int i;
+};
+// larger value wins; on equal values the lower index wins (first-occurrence semantics of torch.max)
+__device__ __forceinline__ RedArgMax red_better(RedArgMax a, RedArgMax b) {
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+__device__ __forceinline__ float red_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }  // == scorers.cu sigmoid_ref
+__device__ __forceinline__ float red_softplus(float x) { return logf(1.0f + expf(x)); }     // as written in the reference
+// one thread's running record over the columns it sees
+struct RedRec {
+  RedArgMax best{-INFINITY, 0x7fffffff};
+  float m1 = -INFINITY, m2 = -INFINITY;  // two largest values (duplicates count twice, like topk)
+  float sp = 0.f;                        // sum of log(1 + exp(v))
+  float lmax = -INFINITY, lsum = 0.f;    // online logsumexp
+  float q = 0.f;                         // RED_MAHA: partial <t, x>
+};
+__device__ __forceinline__ void red_top2(float& m1, float& m2, float v) {
+  if (v > m1) {
+    m2 = m1;
+    m1 = v;
+  } else if (v > m2) {
+    m2 = v;
+  }
+}
+__device__ __forceinline__ void red_lse(float& lmax, float& lsum, float m, float s) {  // merge (m, s) into (lmax, lsum)
+  if (m == -INFINITY) return;
+  if (m > lmax) {
+    lsum = lsum * expf(lmax - m) + s;  // lmax = -inf: lsum is 0 and exp(-inf) = 0
+    lmax = m;
+  } else {
+    lsum += s * expf(m - lmax);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // single-CTA kernel (small M): 128 x BN tiles, direct epilogue
 // ------------------------------------------------------------------------------------------------
@@ -419,6 +458,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc * BN + half * kColsPerWarp);
+      [[maybe_unused]] RedRec rec;
 #pragma unroll 1
       for (int c = 0; c < kColsPerWarp; c += 32) {
         const int col0 = n0 + half * kColsPerWarp + c;
@@ -426,12 +466,92 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint32_t v[32];
         tmem_ld32(t_row + static_cast<uint32_t>(c), v);
         tmem_ld_wait_dep(v);
-        epilogue_chunk<EPI, OutT>(v, row, row_ok, col0, p, rn);
+        if constexpr (EPI == EPI_REDUCE) {
+          if (p.red.kind == RED_LOGITS) {
+            float* orow = (p.out != nullptr && row_ok) ? reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo : nullptr;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = col0 + i;
+              if (col < p.N) {
+                const float x = __uint_as_float(v[i]) + __ldg(p.bias + col);
+                if (orow != nullptr) orow[col] = x;
+                rec.best = red_better(rec.best, RedArgMax{red_sigmoid(x), col});
+                red_top2(rec.m1, rec.m2, x);
+                if (p.red.flags & 1) rec.sp += red_softplus(x);
+                if (p.red.flags & 2) red_lse(rec.lmax, rec.lsum, x, 1.0f);
+              }
+            }
+          } else {  // RED_MAHA
+            if (col0 < p.red.split) {  // t = x·P columns (split is a multiple of 32): q += t * x
+              const float* xr = p.red.x + static_cast<long long>(row_ok ? row : 0) * p.red.split + col0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 xx = __ldg(reinterpret_cast<const float4*>(xr + i));
+                rec.q = fmaf(__uint_as_float(v[i + 0]), xx.x, rec.q);
+                rec.q = fmaf(__uint_as_float(v[i + 1]), xx.y, rec.q);
+                rec.q = fmaf(__uint_as_float(v[i + 2]), xx.z, rec.q);
+                rec.q = fmaf(__uint_as_float(v[i + 3]), xx.w, rec.q);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int col = col0 + i;
+                if (col < p.N) {
+                  const int cls = col - p.red.split;
+                  const float s = fmaf(-0.5f, __ldg(p.red.m + cls), __uint_as_float(v[i]));
+                  rec.best = red_better(rec.best, RedArgMax{s, cls});
+                }
+              }
+            }
+          }
+        } else {
+          epilogue_chunk<EPI, OutT>(v, row, row_ok, col0, p, rn);
+        }
       }
       // all TMEM reads of this accumulator buffer are complete (wait::ld above): hand it back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if constexpr (EPI == EPI_REDUCE) {
+        // this thread's record of (row, column tile, half), then the last CTA of the row tile merges
+        const int tm = t / tiles_n, tn = t - tm * tiles_n;
+        const int slots = 2 * tiles_n;
+        float4* rp = reinterpret_cast<float4*>(p.red.part + (static_cast<size_t>(row) * slots + (2 * tn + half)) * 8);
+        rp[0] = make_float4(rec.best.v, __int_as_float(rec.best.i), rec.m1, rec.m2);
+        rp[1] = make_float4(rec.sp, rec.lmax, rec.lsum, rec.q);
+        volatile uint32_t* last_flag = tmem_ptr_smem + 1;
+        __threadfence();
+        named_bar_sync(2, kNumEpiWarps * 32);
+        if (threadIdx.x == 4 * 32) *last_flag = (atomicAdd(p.red.counter + tm, 1) == tiles_n - 1) ? 1u : 0u;
+        named_bar_sync(2, kNumEpiWarps * 32);
+        if (*last_flag != 0u) {
+          __threadfence();
+          if (half == 0 && row_ok) {
+            RedRec tot;
+            const float4* pr = reinterpret_cast<const float4*>(p.red.part + static_cast<size_t>(row) * slots * 8);
+            for (int s = 0; s < slots; ++s) {  // ascending columns: ties keep the lowest index
+              const float4 a = __ldcg(pr + 2 * s), b = __ldcg(pr + 2 * s + 1);
+              tot.best = red_better(tot.best, RedArgMax{a.x, __float_as_int(a.y)});
+              red_top2(tot.m1, tot.m2, a.z);
+              red_top2(tot.m1, tot.m2, a.w);
+              tot.sp += b.x;
+              red_lse(tot.lmax, tot.lsum, b.y, b.z);
+              tot.q += b.w;
+            }
+            if (p.red.kind == RED_LOGITS) {
+              p.red.scores[row] = tot.best.v;
+              p.red.scores[static_cast<size_t>(p.M) + row] = red_softplus(tot.m1) + (p.N > 1 ? red_softplus(tot.m2) : 0.f);
+              p.red.scores[2 * static_cast<size_t>(p.M) + row] = tot.sp;
+              p.red.scores[3 * static_cast<size_t>(p.M) + row] = tot.lmax + logf(tot.lsum);
+            } else {
+              p.red.scores[row] = fmaf(-0.5f, tot.q, tot.best.v);
+            }
+            p.red.labels[row] = tot.best.i;
+          }
+          if (threadIdx.x == 4 * 32) p.red.counter[tm] = 0;  // ready for the next launch (stream order)
+        }
+        named_bar_sync(2, kNumEpiWarps * 32);  // last_flag is rewritten by the next tile
+      }
     }
   }
 
@@ -1096,6 +1216,29 @@ int gemm_bf16_resid_hl(cudaStream_t stream, const void* A, long long lda, const 
   }
   if (K >= 2048) return launch_pair<EPI_RESID_HL, __nv_bfloat16, true, 2>(stream, tmA, tmB, tmOutHi, tmInHi, p, &tmOutLo, &tmInLo);
   return launch_pair<EPI_RESID_HL, __nv_bfloat16, true>(stream, tmA, tmB, tmOutHi, tmInHi, p, &tmOutLo, &tmInLo);
+}
+
+int gemm_bf16_reduce(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                     float* out, long long ldo, int M, int N, int K, const RowReduce& red) {
+  RGQA_CHECK(M > 0 && N > 0 && K > 0 && K % BK == 0, "gemm_bf16_reduce: bad problem M=%d N=%d K=%d", M, N, K);
+  RGQA_CHECK(red.kind == RED_LOGITS || red.kind == RED_MAHA, "gemm_bf16_reduce: unknown reduction %d", red.kind);
+  RGQA_CHECK(red.part && red.counter && red.scores && red.labels, "gemm_bf16_reduce: null workspace / output");
+  RGQA_CHECK(red.kind != RED_LOGITS || bias != nullptr, "gemm_bf16_reduce: the logit reduction needs the bias");
+  RGQA_CHECK(red.kind != RED_MAHA || (red.x && red.m && red.split > 0 && red.split % 128 == 0 && red.split < N && out == nullptr &&
+                                      reinterpret_cast<uintptr_t>(red.x) % 16 == 0),
+             "gemm_bf16_reduce: Mahalanobis reduction needs x, m, a split that is a multiple of 128 and no matrix output");
+  CUtensorMap tmA, tmB;
+  if (make_tmap(&tmA, A, M, K, lda, BM, 2) || make_tmap(&tmB, W, N, K, ldw, 128, 2)) return 1;
+  GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.bias = bias;
+  p.out = out;
+  p.ldo = ldo;
+  p.ln_stats_ld = 12;
+  p.red = red;
+  return launch<128, EPI_REDUCE, float>(stream, tmA, tmB, p);
 }
 
 int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,

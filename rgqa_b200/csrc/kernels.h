@@ -16,7 +16,33 @@ enum Epilogue : int {
   EPI_RESID = 3,  // out = acc + bias + residual           (pre-LayerNorm sum of modeling.py:357-361 / :411-415)
   EPI_RESID_HL = 4,  // same sum, residual recomputed from a deferred-LayerNorm hidden state, written as a bf16 hi/lo pair
   EPI_RESID_HL_BETA = 5,  // EPI_RESID_HL with LN_prev's beta passed separately (the engine folds it into the bias at load time)
+  EPI_REDUCE = 6,  // acc + bias reduced along each row inside the epilogue (scorers of the answer head / Mahalanobis), see RowReduce
 };
+
+// Row reductions fused into a GEMM epilogue (gemm_bf16_reduce).  Every (row tile, column tile) CTA leaves one partial
+// record per (row, column half); the CTA that finishes a row tile LAST (atomic arrival counter, no waiting) merges that
+// tile's records and writes the final scores, so the [M, N] matrix itself never has to reach HBM.
+//   RED_LOGITS  v = acc + bias[n]: arg-max of sigmoid(v) (first index on ties, torch.max), two largest v, sum of
+//               log(1 + exp(v)), logsumexp  ->  scores [4][M] in ScoreMode order (MSP, ENERGY_TOP2, ENERGY_SUM, LSE)
+//               src/tasks/gqa_conf.py:326, gqa_energy.py:131,185,204-206
+//   RED_MAHA    columns n < split are t = x·P: q += acc * x[row, n]; columns n >= split are classes c = n - split with
+//               v = acc - m[c]/2 (acc = x·P·mu_c): arg-max_c v  ->  scores[row] = max_c v - q/2 = max_c -1/2 (x-mu_c)^T P (x-mu_c)
+//               src/tasks/gqa_maha.py:228-236,270
+enum RowReduceKind : int { RED_NONE = 0, RED_LOGITS = 1, RED_MAHA = 2 };
+struct RowReduce {
+  int kind = RED_NONE;
+  int flags = 0;            // RED_LOGITS: bit0 also the all-class softplus sum, bit1 also logsumexp (both cost exp/log per element)
+  int split = 0;            // RED_MAHA: first class column
+  const float* x = nullptr;  // RED_MAHA: fp32 [M, split] rows the t columns are dotted with
+  const float* m = nullptr;  // RED_MAHA: m_c = mu_c^T P mu_c, [N - split]
+  float* part = nullptr;     // workspace: [ceil(M/128)*128][2*ceil(N/128)][8] floats
+  int* counter = nullptr;    // workspace: [ceil(M/128)] arrival counters, zero on entry, left zero on exit
+  float* scores = nullptr;   // RED_LOGITS: [4][M]; RED_MAHA: [M]
+  int32_t* labels = nullptr;  // [M]
+};
+// bytes of `part` / ints of `counter` for an M x N problem
+inline size_t row_reduce_part_bytes(int M, int N) { return static_cast<size_t>((M + 127) / 128) * 128 * 2 * ((N + 127) / 128) * 8 * sizeof(float); }
+inline int row_reduce_counters(int M) { return (M + 127) / 128; }
 
 enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
 
@@ -32,6 +58,10 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
 int gemm_bf16_folded(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
                      const void* resid, long long ldr, void* out, long long ldo, int out_f32, int M, int N, int K, int epi,
                      const float* ln_stats, const float* ln_c, float ln_eps, long long ln_stats_ld = 12);
+// out = A·Wᵀ + bias reduced per row in the epilogue (see RowReduce); `out` (fp32 [M, N], row stride ldo) may be nullptr: the
+// matrix is then never written.  Single-CTA 128 x 128 tiles (the head GEMMs have M = batch rows).
+int gemm_bf16_reduce(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                     float* out, long long ldo, int M, int N, int K, const RowReduce& red);
 // Q|K|V projection with a head-major output: out[plane = head*3 + {q,k,v}][row][64] bf16, planes plane_rows rows apart; `out`
 // points at this call's first row of plane 0.  ln_stats != nullptr: deferred-LayerNorm consumer (folded weight / bias).
 int gemm_bf16_qkv_planes(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
@@ -59,6 +89,19 @@ int identity_state(cudaStream_t stream, const float* y_f32, const void* hi, void
 int gemm_f32(cudaStream_t stream, const float* A, long long lda, const float* W, long long ldw, const float* bias,
              const float* resid, long long ldr, float* out, long long ldo, int M, int N, int K, int epi);
 
+// Self-attention inside the Q|K|V projection (qkv_attn_tcgen05.cu; modeling.py:320-347 for blocks whose queries and keys are
+// the same rows): ctx[M, heads*64] = attention(LN(A)·W_hmᵀ + b_hm) with W_hm / b_hm packed head-major ([head][q|k|v][64] rows),
+// A = bf16 [B*S, 768] pre-LayerNorm rows + ln_stats (or already-normalised rows and nullptr), key_mask [B, S] or nullptr.
+int qkv_attention_fused(cudaStream_t stream, const void* A, long long lda, const void* W_hm, const float* bias_hm,
+                        const float* ln_stats, float ln_eps, const int32_t* key_mask, void* ctx, long long ldo, int B, int S,
+                        int heads);
+int qkv_attention_fused_ok(int B, int S, int heads, int K);
+// VisualFeatEncoder in ONE kernel (visn_embed_tcgen05.cu; modeling.py:507-517): (LN1(feat·W1ᵀ + b1) + LN2(box·W2ᵀ + b2)) / 2
+// written as the identity deferred-LayerNorm state (hi, lo bf16 [M,768], stats [M,12]).  feat / W1 are fp32 (kind::tf32
+// MMAs, no cast kernel) when feat_f32, else bf16.  W2p = box_fc weight padded to [768][8]; bstat from make_box_stats.
+int visn_embed(cudaStream_t stream, const void* feat, int feat_f32, long long ldf, const void* W1, const float* b1, const float* g1,
+               const float* be1, const float* boxes, int box_dim, const float* W2p, const float* b2, const float* g2,
+               const float* be2, const float* bstat, float eps, void* hi, void* lo, float* stats, int M, int K);
 // Full-row GEMM + LayerNorm (bf16 path): out_act/out_res = LN(A·Wᵀ + bias + resid) for N == 768, one kernel
 // (BertAttOutput / BertOutput, modeling.py:357-361, :411-415).  out_res may be null.
 int gemm_bf16_ln(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
@@ -104,6 +147,9 @@ int uniter_img_combine(cudaStream_t stream, int out_dtype, const float* x_pre, c
                        const float* b2, const float* type_row, const float* g3, const float* b3, void* out,
                        float* out32, int M, int H, float eps);
 int cast_f32_to_bf16(cudaStream_t stream, const float* in, void* out, long long n);
+// fp32 [M, K] -> bf16 [M, 3K] split operand (hi | hi | lo, or hi | lo | hi on the weight side): one bf16 GEMM over 3K then
+// evaluates the product to ~16 mantissa bits per operand (the tensor-core Mahalanobis)
+int split_bf16x3(cudaStream_t stream, const float* in, long long ld, void* out, long long M, int K, int weight_side);
 int cast_bf16_to_f32(cudaStream_t stream, const void* in, float* out, long long n);
 // copy rows: dst[r, :] = src[r*src_stride_rows .. ] for r < rows (strided gather of whole rows)
 int gather_rows(cudaStream_t stream, int dtype, const void* src, long long src_ld, void* dst, long long dst_ld,
@@ -160,7 +206,11 @@ int rowdot(cudaStream_t stream, const float* a, const float* b, float* out, int 
 enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_GEMM_DEBUG = 2, OPT_PDL = 3, OPT_GEMM_LN = 4, OPT_TWO_STREAMS = 5, OPT_GRAPHS = 6,
   OPT_DEFER_LN = 7,
   OPT_ATTN_TMA = 8,
-  OPT_QKV_PLANES = 9, OPT_COUNT = 16 };
+  OPT_QKV_PLANES = 9,
+  OPT_MAHA_TC = 10,    // Mahalanobis on the tensor cores (split-bf16, fused arg-max) in bf16 handles
+  OPT_VISN_FUSED = 11, // visual feature encoder as one tcgen05 kernel (visn_embed_tcgen05.cu)
+  OPT_ATTN_FUSED = 12, // self-attention inside the Q|K|V projection's epilogue (qkv_attn_tcgen05.cu)
+  OPT_COUNT = 16 };
 int option_get(int key);
 void option_set(int key, int value);
 

@@ -315,6 +315,26 @@ __global__ void __launch_bounds__(256) identity_state_kernel(const float* __rest
     stats[i] = (i % 12 == 1) ? width : 0.f;
 }
 
+// fp32 [M, K] (row stride ld) -> bf16 [M, 3K]: hi = bf16(x), lo = bf16(x - hi) laid out hi | hi | lo (activation side) or
+// hi | lo | hi (weight side), so that one bf16 GEMM over K' = 3K computes hi·hi + hi·lo + lo·hi (fp32 accumulate)
+__global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ in, long long ld, __nv_bfloat16* __restrict__ out,
+                                                           long long M, int K, int weight_side) {
+  const int k4 = K / 4;
+  const long long n4 = M * k4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / k4;
+    const int c = static_cast<int>(i - r * k4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(in + r * ld + c);
+    const uint2 h = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    const float2 h0 = unpack_bf16x2(h.x), h1 = unpack_bf16x2(h.y);
+    const uint2 l = make_uint2(pack_bf16x2(v.x - h0.x, v.y - h0.y), pack_bf16x2(v.z - h1.x, v.w - h1.y));
+    __nv_bfloat16* o = out + r * 3 * K + c;
+    *reinterpret_cast<uint2*>(o) = h;
+    *reinterpret_cast<uint2*>(o + K) = weight_side ? l : h;
+    *reinterpret_cast<uint2*>(o + 2 * K) = weight_side ? h : l;
+  }
+}
+
 inline int row_grid(int rows) { return (rows + kWarpsPerBlock - 1) / kWarpsPerBlock; }
 
 }  // namespace
@@ -421,6 +441,17 @@ int fold_ln_weight(cudaStream_t stream, const float* W, const float* bias, const
   RGQA_CHECK(N > 0 && K > 0, "fold_ln_weight: empty weight");
   fold_ln_kernel<<<(N + 3) / 4, 128, 0, stream>>>(W, bias, gamma, beta, N, K, static_cast<__nv_bfloat16*>(W_out_bf16), c_out,
                                                   bias_out);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int split_bf16x3(cudaStream_t stream, const float* in, long long ld, void* out, long long M, int K, int weight_side) {
+  RGQA_CHECK(M > 0 && K > 0 && K % 4 == 0 && ld % 4 == 0, "split_bf16x3: bad shape M=%lld K=%d ld=%lld", M, K, ld);
+  RGQA_CHECK(reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 8 == 0, "split_bf16x3: unaligned operand");
+  long long blocks = (M * (K / 4) + 255) / 256;
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  split_bf16x3_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(in, ld, static_cast<__nv_bfloat16*>(out), M, K, weight_side);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;

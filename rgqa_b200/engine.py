@@ -124,6 +124,33 @@ class Engine:
                     f"rgqa_{self.cfg.arch}_forward")
         return pooled, logits
 
+    def forward_scored(self, feat, pos, ids, seg, mask, modes, want_logits=False, want_pooled=False):
+        """Forward + rejection scorers in ONE C-ABI call (``rgqa_forward_scored``): the scorer reductions run in the
+        answer-head GEMM's epilogue / on the tensor cores, the logit and Mahalanobis matrices stay on chip.
+        ``modes``: iterable of msp|energy|energy_sum|lse|maha.  Returns ({mode: (score f32 [B], label i32 [B])}, pooled, logits)."""
+        feat, pos, ids, seg, mask, B, Lq = self._prep_common(feat, pos, ids, seg, mask)
+        codes = [L.SCORE_MODES[m] for m in modes]
+        if L.SCORE_MAHA in codes and not self.has_maha:
+            raise RuntimeError("rgqa_b200.Engine: Mahalanobis statistics were not set (set_maha)")
+        bits = 0
+        for c in codes:
+            bits |= 1 << c
+        dev = feat.device
+        scores = torch.empty((5, B), dtype=torch.float32, device=dev)
+        labels = torch.empty((2, B), dtype=torch.int32, device=dev)
+        pooled = torch.empty((B, self.cfg.hidden), dtype=torch.float32, device=dev) if want_pooled else None
+        logits = torch.empty((B, self.cfg.num_answers), dtype=torch.float32, device=dev) if want_logits else None
+        with torch.cuda.device(dev):
+            L.check(self._lib.rgqa_forward_scored(self._h, L.current_stream_ptr(), feat.data_ptr(),
+                                                  L.DT_F32 if feat.dtype == torch.float32 else L.DT_BF16, pos.data_ptr(),
+                                                  ids.data_ptr(), seg.data_ptr(), mask.data_ptr(), B, Lq, bits, L.ptr(pooled),
+                                                  L.ptr(logits), scores.data_ptr(), labels.data_ptr()), "rgqa_forward_scored")
+        out = {m: (scores[c], labels[1 if c == L.SCORE_MAHA else 0]) for m, c in zip(modes, codes)}
+        return out, pooled, logits
+
+    def graph_captures(self) -> int:
+        return int(self._lib.rgqa_graph_captures(self._h))
+
     # ---- scorers --------------------------------------------------------------------------------
     def set_maha(self, sample_mean, precision):
         """{mean, precision} from ``sample_estimator`` (src/tasks/gqa_maha.py:120-201); numpy or torch."""

@@ -31,9 +31,10 @@ def shard_range(n, rank, world):
 class SweepRunner:
     """Runs batches through ``model`` + scorer with overlapped H2D, keeps results on the device."""
 
-    def __init__(self, model, method="msp", device=None):
+    def __init__(self, model, method="msp", device=None, fused=True):
         self.model = model
         self.method = method
+        self.fused = fused  # False: logits / pooled leave the forward and the stand-alone scorer kernels run (A/B, tests)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self._slots = [None, None]
@@ -68,15 +69,30 @@ class SweepRunner:
         stream.wait_event(self._ready[slot])
         out = self.score_device_batch(f, b, i, m, s)
         self._free[slot].record(stream)
+        # Bound the host's run-ahead to ONE batch: a loader that recycles two pinned buffer sets (ingest.SweepLoader) refills
+        # the set of batch k when it builds batch k+2, so the async H2D of batch k must have executed before submit(k+1)
+        # returns.  Waiting for the PREVIOUS upload here keeps this batch's copy overlapped with the previous compute.
+        if self._n >= 2:
+            self._ready[slot ^ 1].synchronize()
         return out
+
+    def drain(self):
+        """Block until every upload issued so far has executed (call before reusing the LAST batch's host buffers)."""
+        for ev in self._ready:
+            ev.synchronize()
 
     def score_device_batch(self, feats, boxes, ids, mask, seg=None):
         """One forward + scorer on device tensors: the reference's per-batch body (gqa_conf.py:305-326)."""
-        logits, pooled = self.model.forward_ids(feats, boxes, ids, seg, mask)
-        eng = self.model.engine()
-        if isinstance(self.method, (tuple, list)):  # several scorers over ONE forward: [(score, label), ...]
-            return [eng.score(m, logits=logits, pooled=pooled) for m in self.method]
-        return eng.score(self.method, logits=logits, pooled=pooled)
+        many = isinstance(self.method, (tuple, list))  # several scorers over ONE forward: [(score, label), ...]
+        methods = list(self.method) if many else [self.method]
+        if self.fused and hasattr(self.model, "forward_scored_ids"):
+            # scorer reductions inside the forward (answer-head GEMM epilogue, tensor-core Mahalanobis): one engine call
+            res = self.model.forward_scored_ids(feats, boxes, ids, seg, mask, methods)
+        else:
+            logits, pooled = self.model.forward_ids(feats, boxes, ids, seg, mask)
+            eng = self.model.engine()
+            res = [eng.score(m, logits=logits, pooled=pooled) for m in methods]
+        return res if many else res[0]
 
 
 class GQAEval:

@@ -61,6 +61,11 @@ class GQAModel(nn.Module):
         pooled, logits = self.engine().forward(feat, pos, input_ids, segment_ids, input_mask)
         return logits, pooled
 
+    def forward_scored_ids(self, feat, pos, input_ids, segment_ids, input_mask, methods):
+        """Tensor-only forward + scorers in one engine call: [(score f32 [B], label i32 [B]) per method]."""
+        out, _, _ = self.engine().forward_scored(feat, pos, input_ids, segment_ids, input_mask, list(methods))
+        return [out[m] for m in methods]
+
     def forward(self, feat, pos, sent):
         """
         :param feat: (b, o, f) float32 (or pre-staged bfloat16) CUDA tensor

@@ -42,6 +42,11 @@ class GQAUNITER(nn.Module):
         pooled, logits = self.engine().forward(feat, pos7, input_ids, segment_ids, input_mask)
         return logits, pooled
 
+    def forward_scored_ids(self, feat, pos7, input_ids, segment_ids, input_mask, methods):
+        """Tensor-only forward + scorers in one engine call: [(score f32 [B], label i32 [B]) per method]."""
+        out, _, _ = self.engine().forward_scored(feat, pos7, input_ids, segment_ids, input_mask, list(methods))
+        return [out[m] for m in methods]
+
     def forward(self, feat, pos, sent):
         assert feat.shape[1] == 36, "Not Using 36 ROIs, please change the following 2 lines"
         ids, mask, seg = self.encoder.tokenize(sent, feat.device)
