@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the UNITER (configs[2]) side measurement")
     ap.add_argument("--ref-batch", type=int, default=32)
     return ap.parse_args()
 
@@ -174,6 +176,100 @@ def run_reference(a):
             "e2e": {"value": r["value"], "unit": "questions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# parity of the TIMED configuration (same process, same handle, same kernels and CUDA graphs as the timed region)
+# ------------------------------------------------------------------------------------------------
+LOGIT_TOL = 2e-2  # BASELINE north_star: bf16 logits within 2e-2 abs
+
+
+def parity_block(model, eng, dev, batch_dev, batch_host, mu, P, precision, rows=8):
+    """(1) first `rows` questions of the timed batch against the CPU oracle (logits, energy, Mahalanobis score / label);
+    (2) the whole timed batch against the fp32 CUDA path of the same weights (itself pinned to the oracle at 1e-4 by the GPU
+    tests): answer agreement overall and on the buckets whose fp32 top-2 logit margin exceeds 2x / 4x the logit tolerance.
+    Raises when out of tolerance: a bench number without parity is not a number."""
+    from oracle import lxmert_oracle as O
+    from oracle import scorers_oracle as S
+    from rgqa_b200 import synthetic as syn
+    from rgqa_b200.engine import Engine
+    f, p, ids, mask, seg = batch_dev
+    out, pooled, logits = eng.forward_scored(f, p, ids, seg, mask, ["energy", "maha"], want_logits=True, want_pooled=True)
+    torch.cuda.synchronize()
+    sd = syn.lxmert_state_dict(seed=9595, variant="init")
+    hf, hp, hids, hmask, hseg = (t[:rows] for t in batch_host)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref_logit, ref_x = O.gqa_model_forward(sd, hf.float(), hp, hids.long(), hseg.long(), hmask.long())
+    e_ref, el_ref = S.energy_top2(ref_logit)
+    m_ref, ml_ref, m_full = S.mahalanobis(ref_x, mu, P)
+    dlogit = float((logits[:rows].cpu() - ref_logit).abs().max())
+    e_rel = float(((out["energy"][0][:rows].cpu() - e_ref).abs() / e_ref.abs()).max())
+    m_rel = float(((out["maha"][0][:rows].cpu() - m_ref).abs() / m_ref.abs()).max())
+    # labels: a swap is a failure only where the reference margin is clear of the tolerance
+    top2 = ref_logit.topk(2, dim=1).values
+    clear_l = (top2[:, 0] - top2[:, 1]) > 2 * LOGIT_TOL
+    mt2 = m_full.topk(2, dim=1).values
+    clear_m = (mt2[:, 0] - mt2[:, 1]) > 2e-3 * mt2[:, 0].abs()
+    lab_e = out["energy"][1][:rows].cpu().long() == el_ref.long()
+    lab_m = out["maha"][1][:rows].cpu().long() == ml_ref.long()
+    # fp32 CUDA path on the whole batch
+    cfg32 = model.lxrt_encoder.model.engine_config(model.num_answers)
+    cfg32.precision = "fp32"
+    e32 = Engine(cfg32, device=dev)
+    e32.load_weights(sd.items())
+    _, l32 = e32.forward(f.float(), p, ids, seg, mask, want_pooled=False)
+    torch.cuda.synchronize()
+    e32.close()
+    d_all = (logits - l32).abs()
+    t2 = l32.topk(2, dim=1).values
+    margin = t2[:, 0] - t2[:, 1]
+    same = out["energy"][1].long() == l32.argmax(1)
+    agree = {"n": int(same.numel()), "overall": float(same.float().mean())}
+    for k in (2, 4):
+        sel = margin > k * LOGIT_TOL
+        agree[f"margin_gt_{k}tol"] = {"n": int(sel.sum()), "agree": float(same[sel].float().mean()) if int(sel.sum()) else None}
+    par = {"rows_vs_oracle": rows, "max_dlogit": dlogit, "energy_rel": e_rel, "maha_rel": m_rel,
+           "labels_equal": {"energy": int(lab_e.sum()), "maha": int(lab_m.sum()), "of": rows},
+           "batch_vs_fp32_cuda": {"max_dlogit": float(d_all.max()), "rms_dlogit": float(d_all.pow(2).mean().sqrt()),
+                                  "frac_within_2e-2": float((d_all <= LOGIT_TOL).float().mean()), "answer_agreement": agree},
+           "tolerances": {"logit_abs_hard_cap": 3e-2 if precision == "bf16" else 1e-4, "score_rel": 2e-2 if precision == "bf16" else 1e-3}}
+    cap, srel = par["tolerances"]["logit_abs_hard_cap"], par["tolerances"]["score_rel"]
+    ok = (dlogit <= cap and float(d_all.max()) <= (4e-2 if precision == "bf16" else 1e-4) and e_rel <= srel and m_rel <= srel and
+          bool(lab_e[clear_l].all()) and bool(lab_m[clear_m].all()) and
+          (agree["margin_gt_4tol"]["agree"] in (None, 1.0)))
+    par["ok"] = bool(ok)
+    return par
+
+
+def uniter_extra(dev, steps=6):
+    """BASELINE configs[2] next to the headline: UNITER-base (12 layers over the joint 56-token sequence), B = 1024, forward +
+    MSP through rgqa_forward_scored, device-resident inputs; 9.7511 GFLOP / question."""
+    from rgqa_b200 import synthetic as syn
+    from rgqa_b200.engine import Engine, EngineConfig
+    cfg = EngineConfig(arch="uniter", precision="bf16", l_layers=12, x_layers=0, r_layers=0, vocab_size=28996, visual_pos_dim=7)
+    eng = Engine(cfg, device=dev)
+    eng.load_weights(syn.uniter_state_dict(variant="init").items())
+    B = 1024
+    ins = []
+    for j in range(2):
+        inp = syn.make_inputs(B, 20, seed=3 + j, vocab=28996)
+        ins.append([inp[k].to(dev) for k in ("feat", "pos7")] + [inp[k].to(torch.int32).to(dev) for k in ("ids", "seg", "mask")])
+    for i in range(4):
+        eng.forward_scored(*ins[i & 1], ["msp"])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        eng.forward_scored(*ins[i & 1], ["msp"])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    eng.close()
+    qps = B / ms * 1e3
+    peak_tf = peaks()[0]
+    return {"uniter_b1024_qps": qps, "uniter_ms_per_step": ms, "uniter_tflops": qps * 9.7511e9 / 1e12,
+            "uniter_frac_of_sustained_peak": qps * 9.7511e9 / 1e12 / peak_tf, "uniter_steps": steps,
+            "uniter_workload": "UNITER-base 12 layers, 36 RoI + 20 tokens, forward + MSP, B=1024, bf16 (BASELINE.json configs[2])"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -311,6 +407,29 @@ def run_ours(a):
         e2e = {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": "questions/s", "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / a.steps,
                "host_feature_dtype": "f32 (reference loader format, src/tasks/gqa_data.py:173-238)"}
+        # the same sweep from the ingest store's format (rgqa_b200/ingest.py: bf16 features, RNE = the device cast bit for bit):
+        # half the H2D bytes, which is what eight ranks pulling out of one host DRAM need
+        host_b = [(hb[0].to(torch.bfloat16).pin_memory(),) + tuple(hb[1:]) for hb in host]
+
+        def e2e_step_b(i):
+            f, p, ids, mask, seg = host_b[i & 1]
+            res = runner_b.submit(f, p, ids, mask, seg)
+            for (s, l), (hs, hl) in zip(res, out_host[i & 1]):
+                hs.copy_(s, non_blocking=True)
+                hl.copy_(l, non_blocking=True)
+        runner_b = SweepRunner(model, methods, device=dev)
+        for i in range(4 + a.warmup):
+            e2e_step_b(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(a.steps):
+            e2e_step_b(i)
+        e1.record()
+        barrier()
+        ms_b = max_over_ranks(e0.elapsed_time(e1))
+        e2e["bf16_host_features"] = {"value": world * B * a.steps / (ms_b * 1e-3), "ms_per_step": ms_b / a.steps,
+                                     "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host_b[0])}
 
     # region 2: the same K steps again with CUDA events bracketing every GEMM / attention launch on its own
     # stream (per-kernel durations for the roofline); the events cost ~3-4 % so they stay out of `value`, and
@@ -333,6 +452,31 @@ def run_ours(a):
                 "whole_step_tflops": (value / world) * gq * 1e9 / 1e12,
                 "whole_step_frac": (value / world) * gq * 1e9 / 1e12 / peak_tf}
 
+    # ---------------- parity of the timed configuration ----------------
+    parity = None
+    if not a.no_parity and rank == 0:
+        parity = parity_block(model, eng, dev, resident[0], host[0], mu, P, a.precision)
+    # ---------------- N ranks == 1 rank ----------------
+    sharded = None
+    if world > 1:
+        mine = [dev_step(i) for i in range(2)]            # this rank's two batches through the timed path
+        torch.cuda.synchronize()
+        gathered = [gather_results(torch.cat([k[m][0] for k in mine]), torch.cat([k[m][1] for k in mine])) for m in range(len(methods))]
+        if rank == 0:
+            same = True
+            for r in range(world):                         # rank 0 recomputes every rank's shard on its own GPU
+                for i in range(2):
+                    inp = syn.make_inputs(B, Lq, seed=1234 + 17 * i + 1000 * r)
+                    t = [inp["feat"].to(dev), inp["pos"].to(dev)] + [inp[k].to(torch.int32).to(dev) for k in ("ids", "mask", "seg")]
+                    res = runner.score_device_batch(*t)
+                    for m in range(len(methods)):
+                        sl = slice((2 * r + i) * B, (2 * r + i + 1) * B)
+                        same &= bool(torch.equal(res[m][0].cpu(), gathered[m][0][sl])) and bool(torch.equal(res[m][1].cpu(), gathered[m][1][sl]))
+            sharded = same
+    extra = None
+    if rank == 0 and world == 1 and not a.no_extra and B == 1024:
+        extra = uniter_extra(dev)
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = {k: v for k, v in cpu_reference_rate(Lq, a.ref_batch, 16, 1, budget_s=25).items()
@@ -347,8 +491,17 @@ def run_ours(a):
                                        "random-init seed 9595",
                            "questions_per_step": world * B, "parallelism": f"batch-sharded x{world}, one all-gather per sweep",
                            "l2": "inputs larger than L2: two alternating 302 MB fp32 feature batches per GPU"},
-                "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+                "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+                "parity": parity, "extra": extra}
+        if world > 1:
+            line["sharded_equals_single"] = sharded
         print(json.dumps(line), flush=True)
+        if parity is not None and not parity["ok"]:
+            print("bench.py: PARITY FAILED on the timed configuration: " + json.dumps(parity), file=sys.stderr, flush=True)
+            sys.exit(3)
+        if world > 1 and sharded is False:
+            print("bench.py: the N-rank sweep does not reproduce the 1-rank results bit for bit", file=sys.stderr, flush=True)
+            sys.exit(4)
     if world > 1:
         dist.destroy_process_group()
 

@@ -141,6 +141,10 @@ int rgqa_score(rgqa_handle* h, void* stream, int mode, const float* logits, cons
 int rgqa_set_option(const char* name, int value);
 /* Kernels enqueued by this library since it was loaded. */
 long long rgqa_launch_count(void);
+/* Deferred LayerNorm bookkeeping of a finalized bf16 handle: returns max |c[n]| over every folded consumer weight (c = row sums
+ * of the centred bf16 weight, the term the consumer epilogue drops) and, through exact_consumers, how many consumers kept the
+ * exact epilogue because their residue was too large to drop (max|c| * 8 > 1e-3). */
+float rgqa_fold_residue(const rgqa_handle* h, int* exact_consumers);
 /* CUDA graphs this handle has instantiated: large batches are captured per (shape, feature / box pointers), so a caller
  * that hands a fresh buffer every call keeps capturing (and pays for it); a sweep over two staging slots captures twice. */
 long long rgqa_graph_captures(const rgqa_handle* h);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "rgqa_set_option": (_i, [C.c_char_p, _i]),
     "rgqa_launch_count": (C.c_longlong, []),
     "rgqa_graph_captures": (C.c_longlong, [_vp]),
+    "rgqa_fold_residue": (_f, [_vp, C.POINTER(_i)]),
     "rgqa_gemm_bf16_reduce_logits": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp, _vp]),
     "rgqa_reduce_work_bytes": (_i64, [_i, _i]),
     "rgqa_qkv_attention_fused": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _f, _vp, _vp, _i64, _i, _i, _i]),

@@ -17,6 +17,7 @@
 // of the tcgen05 GEMM), cast to bf16 in PREC_BF16; Q, K, V are concatenated along N.
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
@@ -79,6 +80,7 @@ struct LNp {
 struct Folded {
   void* W = nullptr;
   float* b = nullptr;
+  float* c = nullptr;  // row sums of W' (the centring's rounding residue); non-null only when too large to drop (fold_stack)
 };
 struct AttW {
   Linear qkv;  // [3H, H]
@@ -140,6 +142,8 @@ struct rgqa_handle {
   float *maha_mu = nullptr, *maha_P = nullptr, *maha_m = nullptr;
   void* maha_Ws = nullptr;  // bf16 [H + A, 3H]: split-bf16 rows of the stack [P; mu·P] (tensor-core Mahalanobis, bf16 handles)
   bool has_maha = false;
+  float max_fold_residue = 0.f;  // largest |c[n]| over every folded consumer weight (fold_stack)
+  int exact_folds = 0;           // consumers whose residue was too large to drop: they run the exact epilogue (ln_c)
   long long graph_captures = 0;  // CUDA graphs instantiated so far (a caller that never repeats its buffers keeps capturing)
 
   // second stream for the visual branch (language / visual layers are independent between joins)
@@ -435,6 +439,19 @@ int fold_stack(rgqa_handle* h, const std::vector<std::string>& names, int rows, 
   }
   out->W = W;
   out->b = b;
+  // Guard for the dropped - rstd * mean * c[n] term of the consumer epilogue: error-feedback rounding leaves |c| <= half an ulp
+  // of a weight (~6e-5 at |w| ~ 0.03); with hidden rows at |mean| / std up to kLnMeanBound the dropped term stays below 1e-3
+  // while max|c| * kLnMeanBound <= 1e-3.  Otherwise (very large weights) this consumer keeps c and runs the exact epilogue.
+  {
+    std::vector<float> hc(n * rows);
+    RGQA_CUDA_OK(cudaMemcpy(hc.data(), c, hc.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    float mx = 0.f;
+    for (float v : hc) mx = std::fabs(v) > mx ? std::fabs(v) : mx;
+    if (mx > h->max_fold_residue) h->max_fold_residue = mx;
+    constexpr float kLnMeanBound = 8.0f;
+    out->c = (mx * kLnMeanBound > 1e-3f) ? c : nullptr;
+    if (out->c != nullptr) ++h->exact_folds;
+  }
   return 0;
 }
 // bias + beta (both [n] f32 on the device) as one vector: the residual term LN(x) = (x-mu)*rstd*gamma + beta of a producer
@@ -460,6 +477,7 @@ int fold_qkv(rgqa_handle* h, const std::string& p, const char* self_name, const 
 // one head.  Source = the folded weight when the block sits behind a LayerNorm, else the plain one.
 int pack_head_major(rgqa_handle* h, AttW* w) {
   const int H = h->cfg.hidden, heads = h->cfg.heads, hd = H / heads;
+  if (w->qkv_f.c != nullptr) return 0;  // this block needs the exact consumer epilogue: it stays on the separate kernels
   const char* W = static_cast<const char*>(w->qkv_f.W != nullptr ? w->qkv_f.W : w->qkv.W);
   const float* b = w->qkv_f.W != nullptr ? w->qkv_f.b : w->qkv.b;
   char* Wo = nullptr;
@@ -657,7 +675,7 @@ int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, c
   float* pdst = o.pooled != nullptr ? o.pooled : pooled;
   if (stats != nullptr) {
     if (gemm_bf16_folded(st, hid, static_cast<long long>(S) * H, h->pooler_f.W, H, h->pooler_f.b, nullptr, 0, pdst, H, 1, B, H,
-                         H, EPI_TANH, stats, nullptr, h->cfg.ln_eps, static_cast<long long>(S) * 12))
+                         H, EPI_TANH, stats, h->pooler_f.c, h->cfg.ln_eps, static_cast<long long>(S) * 12))
       return 1;
   } else if (gemm(h, st, hid, static_cast<long long>(S) * H, h->pooler, nullptr, 0, pdst, H, 1, B, EPI_TANH)) {
     return 1;
@@ -812,6 +830,8 @@ int rgqa_load_weight(rgqa_handle* h, const char* ref_key, const float* data, int
 
 int rgqa_finalize_weights(rgqa_handle* h) {
   RGQA_CHECK(h != nullptr, "rgqa_finalize_weights: null handle");
+  h->max_fold_residue = 0.f;
+  h->exact_folds = 0;
   for (const auto& n : h->names)
     RGQA_CHECK(h->raw.count(n) == 1, "rgqa_finalize_weights: missing tensor '%s'", n.c_str());
   drop_graphs(h);
@@ -990,7 +1010,7 @@ struct DefCtx {
       return gemm_bf16(st, hi_rows(in, r0), H, lin.W, lin.K, lin.b, nullptr, 0, out, ldo, 0, M, lin.N, lin.K, epi);
     RGQA_CHECK(f.W != nullptr, "deferred LayerNorm: folded weight missing");
     return gemm_bf16_folded(st, hi_rows(in, r0), H, f.W, lin.K, f.b, nullptr, 0, out, ldo, 0, M, lin.N, lin.K, epi,
-                            st_rows(in, r0), nullptr, h->cfg.ln_eps, 12);
+                            st_rows(in, r0), f.c, h->cfg.ln_eps, 12);
   }
   // out (pre-LayerNorm) = A · Wᵀ + b + LN_ln(in); bias_beta = b + ln->b precomputed (nullptr: ln == nullptr, beta = 0)
   int produce(cudaStream_t st, const void* A, long long lda, const Linear& lin, const float* bias_beta, const DState& in,
@@ -1005,7 +1025,7 @@ struct DefCtx {
   int att(cudaStream_t st, const AttW& w, const DState& in, const LNp* ln_in, const DState& out, long long r0, int B, int S,
           const int32_t* key_mask) const {
     char* ctx = rows_at(h->ctx.p, r0, H, 2);
-    if (w.qkv_hm != nullptr && qkv_attention_fused_ok(B, S, h->cfg.heads, H)) {
+    if (!planes && w.qkv_hm != nullptr && qkv_attention_fused_ok(B, S, h->cfg.heads, H)) {
       // the projection tile is consumed where it is produced: no [rows, 2304] round trip, no attention launch
       if (qkv_attention_fused(st, hi_rows(in, r0), H, w.qkv_hm, w.qkv_hm_b, ln_in != nullptr ? st_rows(in, r0) : nullptr, h->cfg.ln_eps,
                               key_mask, ctx, H, B, S, h->cfg.heads))
@@ -1383,6 +1403,11 @@ int rgqa_forward_scored(rgqa_handle* h, void* stream, const void* feat, int feat
 }
 
 long long rgqa_graph_captures(const rgqa_handle* h) { return h == nullptr ? 0 : h->graph_captures; }
+float rgqa_fold_residue(const rgqa_handle* h, int* exact_consumers) {
+  if (h == nullptr) return 0.f;
+  if (exact_consumers != nullptr) *exact_consumers = h->exact_folds;
+  return h->max_fold_residue;
+}
 
 int rgqa_uniter_forward(rgqa_handle* h, void* stream, const void* feat, int feat_dtype, const float* pos7,
                         const int32_t* ids, const int32_t* seg, const int32_t* mask, int B, int L,

@@ -14,7 +14,7 @@
 //   whole sample are computed and ignored.  A (sample, head) attention unit therefore never straddles CTAs.
 // * CTA pair (cta_group::2): one 256 x 192 x 16 MMA per step, accumulators double-buffered in TMEM (2 x 192 of 512 columns),
 //   so the whole attention of tile i runs under the main loop of tile i+1.
-// * Epilogue = the 8 epilogue warps: (1) TMEM -> rstd * acc + bias' (deferred LayerNorm) -> bf16 -> three
+// * Epilogue = 12 epilogue warps: (1) TMEM -> rstd * acc + bias' (deferred LayerNorm) -> bf16 -> three
 //   128B-swizzled [128 x 64] matrices Q, K, V in shared memory; (2) the (sample, 16-query tile) tasks of the tile are dealt
 //   over the warps: mma.sync m16n8k16 QKᵀ, quad-shuffle softmax in fp32, P·V, exactly the arithmetic of attention.cu;
 //   (3) the context tile overwrites the consumed Q lines and leaves through ONE TMA store.
@@ -34,7 +34,7 @@ constexpr int HD = 64;
 constexpr int kTileN = 192;                                  // one head: q | k | v
 constexpr int kStageBytes = BM * BK * 2 + (kTileN / 2) * BK * 2;  // 16 KB of A + this CTA's 96 rows of W (12 KB)
 constexpr int kStages = 4;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 12;  // 3 per scheduler: the attention tasks of a tile (9 visual, 12 language) run in ONE round
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kMatBytes = BM * 128;                          // one [128 x 64] bf16 matrix
 constexpr int kPadBytes = 2048;                              // zeroed: V fragment rows up to 15 lines past the tile land here
@@ -52,6 +52,7 @@ struct QkvAttnParams {
   const float* ln_stats;   // [M][6][2] or nullptr (A rows are already normalised)
   float ln_eps;
   const int32_t* key_mask;  // [B, S] (1 = keep) or nullptr
+  int debug;                // measurement only (rgqa_set_option "gemm_debug"): bit0 no attention tasks, bit1 no projection stores, bit2 no context store
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
@@ -121,7 +122,7 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   if (warp == 2) tmem_alloc_pair<512>(tmem_ptr_smem);
   if (warp >= 4) {  // the overrun pads must hold zeros (0 x NaN would poison P·V); nothing ever writes them
-    for (int i = threadIdx.x - 128; i < 2 * (kPadBytes / 16); i += kEpiWarps * 32) {
+    for (int i = threadIdx.x - 128; i < 2 * (kPadBytes / 16); i += kEpiWarps * 32) {  // 256 pieces, 384 threads
       const int b = i / (kPadBytes / 16), o = i % (kPadBytes / 16);
       reinterpret_cast<uint4*>(bufs + b * kBufBytes + 3 * kMatBytes)[o] = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -195,7 +196,7 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ------------------------------ epilogue: projection tile -> shared memory -> attention -> context tile ------------------------------
     const int e = warp - 4;
     const int quarter = e & 3;   // TMEM lane quarter == rows 32 quarter .. + 31 of the CTA tile
-    const int half = e >> 2;     // columns [96 half, 96 half + 96) of the 192-column head tile
+    const int third = e >> 2;    // columns [64 third, 64 third + 64) of the 192-column head tile: exactly Q, K or V
     const int r_local = quarter * 32 + lane;
     const uint32_t leader_tmem_empty0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t leader_tmem_empty1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
@@ -214,19 +215,18 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const float rstd = (p.ln_stats != nullptr && row < p.M) ? row_rstd(p.ln_stats, row, p.ln_eps) : 1.0f;
       mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1u);
       tc_fence_after();
-      // ---- (1) this warp's 32 rows x 96 columns: rstd * acc + bias' -> bf16 -> swizzled Q / K / V lines ----
+      // ---- (1) this warp's 32 rows x 64 columns (one of Q / K / V): rstd * acc + bias' -> bf16 -> swizzled lines ----
       {
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kAccStride + half * 96);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kAccStride + third * 64);
+        uint8_t* line = buf + third * kMatBytes + r_local * 128;
+        const int sw = r_local & 7;
 #pragma unroll 1
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
           tmem_ld32(t_row + static_cast<uint32_t>(c * 32), v);
-          const int col = half * 96 + c * 32;         // column inside the head tile: matrix col / 64, byte (col % 64) * 2
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + head * kTileN + col);
-          uint8_t* line = buf + (col >> 6) * kMatBytes + r_local * 128;
-          const int piece0 = (col & 63) >> 3;
-          const int sw = r_local & 7;
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + head * kTileN + third * 64 + c * 32);
           tmem_ld_wait_dep(v);
+          if (p.debug & 2) continue;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 ba = __ldg(b4 + 2 * i), bb = __ldg(b4 + 2 * i + 1);
@@ -235,7 +235,7 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             o.y = pack_bf16x2(fmaf(rstd, __uint_as_float(v[8 * i + 2]), ba.z), fmaf(rstd, __uint_as_float(v[8 * i + 3]), ba.w));
             o.z = pack_bf16x2(fmaf(rstd, __uint_as_float(v[8 * i + 4]), bb.x), fmaf(rstd, __uint_as_float(v[8 * i + 5]), bb.y));
             o.w = pack_bf16x2(fmaf(rstd, __uint_as_float(v[8 * i + 6]), bb.z), fmaf(rstd, __uint_as_float(v[8 * i + 7]), bb.w));
-            *reinterpret_cast<uint4*>(line + (((piece0 + i) ^ sw) << 4)) = o;
+            *reinterpret_cast<uint4*>(line + (((4 * c + i) ^ sw) << 4)) = o;
           }
         }
         // all TMEM reads of this accumulator buffer are complete: hand it back to the MMA issuer
@@ -246,7 +246,7 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       named_bar_sync(1, kEpiWarps * 32);  // the tile's Q, K, V are in shared memory
       // ---- (2) attention: task = (sample u of this tile, 16-query tile mt) ----
       const uint32_t Qb = smem_u32(buf), Kb = Qb + kMatBytes, Vb = Kb + kMatBytes;
-      for (int task = e; task < tasks; task += kEpiWarps) {
+      for (int task = e; task < ((p.debug & 1) ? 0 : tasks); task += kEpiWarps) {
         const int u = task / MT, mt = task - u * MT;
         const int b = sample0 + u;
         if (b >= p.B) continue;  // tail tile: no such sample
@@ -351,7 +351,7 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                              // free again before any warp passes the barrier below into the next tile
       named_bar_sync(1, kEpiWarps * 32);
       if (issuer) {
-        if (m0 < p.M) tma_store_2d(&tmO, buf, head * HD, m0);
+        if (m0 < p.M && !(p.debug & 4)) tma_store_2d(&tmO, buf, head * HD, m0);
         tma_store_commit();
       }
     }
@@ -402,6 +402,7 @@ int qkv_attention_fused(cudaStream_t stream, const void* A, long long lda, const
   p.ln_stats = ln_stats;
   p.ln_eps = ln_eps;
   p.key_mask = key_mask;
+  p.debug = option_get(OPT_GEMM_DEBUG);
   CUtensorMap tmA, tmB, tmO;
   if (make_tmap(&tmA, A, M, 768, lda, BM, 2)) return 1;
   if (make_tmap(&tmB, W_hm, static_cast<long long>(heads) * kTileN, 768, 768, kTileN / 2, 2)) return 1;

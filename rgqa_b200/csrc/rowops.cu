@@ -272,7 +272,14 @@ __global__ void gather_rows_kernel(const T* __restrict__ src, long long src_ld, 
   }
 }
 
-// LayerNorm folding into the consumer's weight (deferred LayerNorm): one warp per output row n
+// LayerNorm folding into the consumer's weight (deferred LayerNorm): one warp per output row n.
+// The consumer epilogue computes rstd * acc + b' and DROPS the exact form's - rstd * mean * c[n], c[n] = sum_k W'[n,k]: the
+// folded row is centred in fp32, so c is only the sum of its 768 bf16 rounding errors (~2e-3 for |w| ~ 0.03) — harmless for
+// rows with mean / std ~ 0.1, but a trained checkpoint's hidden rows can sit at mean / std ~ 5-10 (outlier channels), where
+// the dropped term would reach the bf16 noise floor.  So the rounding is done with ERROR FEEDBACK along k (each element
+// absorbs the rounding error accumulated so far, staying within one bf16 ulp of its target) and the element of SMALLEST
+// magnitude goes last: it takes whatever the row sum still owes (<= half an ulp of the largest weight, ~1e-4) and leaves
+// only ITS rounding error, half an ulp of ~1e-4: |c[n]| ~ 1e-7 |w|max instead of ~2e-3.
 __global__ void __launch_bounds__(128) fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ bias,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       int N, int K, __nv_bfloat16* __restrict__ Wo,
@@ -284,18 +291,33 @@ __global__ void __launch_bounds__(128) fold_ln_kernel(const float* __restrict__ 
   float ms = 0.f;
   for (int k = lane; k < K; k += 32) ms = fmaf(W[static_cast<long long>(n) * K + k], gamma[k], ms);
   const float wmean = warp_sum(ms) / static_cast<float>(K);
-  float cs = 0.f, bs = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    const float w = W[static_cast<long long>(n) * K + k];
-    const __nv_bfloat16 wb = __float2bfloat16_rn(fmaf(w, gamma[k], -wmean));
-    Wo[static_cast<long long>(n) * K + k] = wb;
-    cs += __bfloat162float(wb);
-    bs = fmaf(w, beta[k], bs);
-  }
-  cs = warp_sum(cs);
+  float bs = 0.f;
+  for (int k = lane; k < K; k += 32) bs = fmaf(W[static_cast<long long>(n) * K + k], beta[k], bs);
   bs = warp_sum(bs);
   if (lane == 0) {
-    c_out[n] = cs;
+    // sequential error-feedback rounding (load time only: ~2 x 768 steps per row, rows in parallel)
+    int klast = 0;
+    float amin = INFINITY;
+    for (int k = 0; k < K; ++k) {
+      const float a = fabsf(fmaf(W[static_cast<long long>(n) * K + k], gamma[k], -wmean));
+      if (a < amin) {
+        amin = a;
+        klast = k;
+      }
+    }
+    float err = 0.f;
+    double cs = 0.0;
+    for (int i = 0; i <= K; ++i) {
+      if (i == klast) continue;          // the smallest element is rounded last (i == K)
+      const int k = i < K ? i : klast;
+      const float target = fmaf(W[static_cast<long long>(n) * K + k], gamma[k], -wmean);
+      const __nv_bfloat16 wb = __float2bfloat16_rn(target + err);
+      Wo[static_cast<long long>(n) * K + k] = wb;
+      const float got = __bfloat162float(wb);
+      err += target - got;   // what the row sum still owes
+      cs += got;
+    }
+    c_out[n] = static_cast<float>(cs);
     b_out[n] = bias[n] + bs;
   }
 }

@@ -25,10 +25,11 @@
 //               (48 KB), 3-stage ring; completion bytes credited to the leader's barrier
 //   warp 1      MMA issuer (leader CTA): 3 x 4 tcgen05.mma.cta_group::2 (128 x 256 x 16 bf16 | x 8 tf32) per k-block
 //   warp 2      TMEM allocator (512 columns)
-//   warps 4-7   epilogue, one TMEM lane (= one row, one column half: 384 values) per thread:
+//   warps 4-11  epilogue, one TMEM lane (= one row, one column half) per thread, two warps per lane quarter (even / odd
+//               32-column chunks); per-column parameters sit in shared memory (36 B per column, staged once per CTA):
 //               pass 1  row sum of acc + b1          pass 1b  centred sum of squares (two-pass variance, as torch)
 //               pass 2  both LayerNorms, average, hi/lo split; each warp transposes its 32 rows x 32 columns through a
-//                       swizzled 4 KB buffer so that global stores are row-contiguous
+//                       swizzled 2 KB buffer so that global stores are row-contiguous
 // The accumulator is single-buffered (384 of 512 columns): the next tile's MMAs wait for pass 2, its TMA loads do not.
 #include <cuda.h>
 
@@ -46,10 +47,12 @@ constexpr int kABytes = kRowsPerCta * kRowBytes;          // 8 KB
 constexpr int kBTileBytes = 128 * kRowBytes;              // this CTA's half (128 rows) of one 256-row W tile: 16 KB
 constexpr int kStageBytes = kABytes + kNT * kBTileBytes;  // 56 KB
 constexpr int kStages = 3;
-constexpr int kEpiWarps = 4;
+constexpr int kEpiWarps = 8;         // two per TMEM lane quarter: even / odd 32-column chunks
 constexpr int kThreads = (4 + kEpiWarps) * 32;
-constexpr int kBufBytes = 32 * 128;  // staging: 32 rows x (64 B hi + 64 B lo), 16-byte pieces XOR-swizzled by row
-constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kBufBytes + 128 * 4 + 1024 + 512;
+constexpr int kBufBytes = 32 * 64;   // staging: 32 rows x 64 B (32 bf16), 16-byte pieces XOR-swizzled by row (64-byte swizzle)
+// per-output-column parameters staged once per CTA: {b1, g1, be1 + be2, g2}, W2[n][0..3] * g2[n], b2[n] * g2[n]
+constexpr int kParamBytes = N_LN * (16 + 16 + 4);
+constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kBufBytes + kParamBytes + 256 * 4 + 1024 + 512;
 
 struct VisnParams {
   int M, K;           // K in elements of the feature type
@@ -58,7 +61,7 @@ struct VisnParams {
   const float* be1;
   const float* boxes;  // [M, box_dim]
   int box_dim;
-  const float* W2p;   // [768][8] box_fc weight, zero padded
+  const float* W2p;   // [768][8] box_fc weight, zero padded (columns >= 4 unused: box_dim <= 4)
   const float* b2;    // [768]
   const float* g2;    // box_layer_norm
   const float* be2;
@@ -99,9 +102,12 @@ visn_embed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* stage_bufs = smem + kStages * kStageBytes;  // [kEpiWarps][4 KB], 1024-aligned (stage size is 56 KB)
-  float* xch = reinterpret_cast<float*>(stage_bufs + kEpiWarps * kBufBytes);  // [128] per-lane partials
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(xch + 128);
+  uint8_t* stage_bufs = smem + kStages * kStageBytes;  // [kEpiWarps][2 KB], 1024-aligned (stage size is 56 KB)
+  float4* pA = reinterpret_cast<float4*>(stage_bufs + kEpiWarps * kBufBytes);  // [768] {b1, g1, be1 + be2, g2}
+  float4* pW = pA + N_LN;                                                       // [768] W2[n][0..3] * g2[n]
+  float* pB = reinterpret_cast<float*>(pW + N_LN);                              // [768] b2[n] * g2[n]
+  float* xch = pB + N_LN;                                                       // [2][128] per-lane partial sums
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(xch + 256);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 1;
@@ -129,6 +135,14 @@ visn_embed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<512>(tmem_ptr_smem);
+  // parameters are weights (never written by a preceding kernel): staged before the dependency wait
+  for (int n = threadIdx.x; n < N_LN; n += kThreads) {
+    const float g2 = __ldg(p.g2 + n);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(p.W2p + n * 8));
+    pA[n] = make_float4(__ldg(p.b1 + n), __ldg(p.g1 + n), __ldg(p.be1 + n) + __ldg(p.be2 + n), g2);
+    pW[n] = make_float4(w.x * g2, w.y * g2, w.z * g2, w.w * g2);
+    pB[n] = __ldg(p.b2 + n) * g2;
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -199,16 +213,18 @@ visn_embed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------ epilogue (both CTAs): one TMEM lane per thread ------------------------------
-    const int q = warp - 4;                 // TMEM lane quarter (== warp % 4)
+    // ------------------------------ epilogue (both CTAs): one TMEM lane per thread, two warps per lane quarter ------------------------------
+    const int e = warp - 4;
+    const int q = e & 3;                    // TMEM lane quarter (== warp % 4)
+    const int grp = e >> 2;                 // chunk parity handled by this warp: chunks c with (c & 1) == grp
     const int tl = q * 32 + lane;           // TMEM lane of this thread
     const int half = tl >> 6;               // column half held by this lane
-    uint8_t* buf = stage_bufs + q * kBufBytes;
+    uint8_t* buf = stage_bufs + e * kBufBytes;
     const uint32_t leader_tmem_empty = mapa_u32(smem_u32(tmem_empty_bar), 0);
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    // coalesced side of the staging transpose: lane l handles row (l >> 3) + 4*i, 16-byte piece (l & 7)
-    const int crow = lane >> 3, cpiece = lane & 7;
-    const int sw = lane & 7;  // swizzle key of this thread's own row (row index within the 32-row buffer = lane)
+    // coalesced side of the staging transpose: lane l handles row (l >> 2) + 8*i, 16-byte piece (l & 3)
+    const int crow = lane >> 2, cpiece = lane & 3;
+    const int sw = (lane >> 1) & 3;  // 64-byte swizzle key of this thread's own row (row index within the 32-row buffer = lane)
     const int KB = p.box_dim;
     int it = 0;
     for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
@@ -216,22 +232,23 @@ visn_embed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int row = row_base + lane;
       // the box branch of this row while the main loop still runs: y_n = box · W2[n] + b2[n]; its LayerNorm statistics are
       // closed forms of the box (file header)
-      float bx[8];
+      float bx[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) bx[j] = (j < KB && row < p.M) ? __ldg(p.boxes + static_cast<long long>(row) * KB + j) : 0.f;
+      for (int j = 0; j < 4; ++j) bx[j] = (j < KB && row < p.M) ? __ldg(p.boxes + static_cast<long long>(row) * KB + j) : 0.f;
       float ymean = __ldg(p.bstat + 8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ymean = fmaf(bx[j], __ldg(p.bstat + j), ymean);
+      for (int j = 0; j < 4; ++j) ymean = fmaf(bx[j], __ldg(p.bstat + j), ymean);
       float yvar = 0.f;
       {
         const float* Cm = p.bstat + 16;
+        const float vv[5] = {bx[0], bx[1], bx[2], bx[3], 1.0f};
+        const int idx[5] = {0, 1, 2, 3, 8};
 #pragma unroll
-        for (int a = 0; a < 9; ++a) {
-          const float va = a < 8 ? bx[a] : 1.0f;
+        for (int a = 0; a < 5; ++a) {
           float acc = 0.f;
 #pragma unroll
-          for (int b = 0; b < 9; ++b) acc = fmaf(__ldg(Cm + a * 9 + b), b < 8 ? bx[b] : 1.0f, acc);
-          yvar = fmaf(va, acc, yvar);
+          for (int b = 0; b < 5; ++b) acc = fmaf(__ldg(Cm + idx[a] * 9 + idx[b]), vv[b], acc);
+          yvar = fmaf(vv[a], acc, yvar);
         }
       }
       const float yrstd = 1.0f / sqrtf(fmaxf(yvar, 0.f) + p.eps);
@@ -239,133 +256,107 @@ visn_embed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(tmem_full_bar, it & 1u);
       tc_fence_after();
 
-      // ---------------- pass 1: row sum of x = acc + b1 ----------------
+      // ---------------- pass 1: row sum of x = acc + b1 (this warp's six chunks) ----------------
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 12; c += 2) {
+      for (int c = grp; c < 12; c += 4) {
         uint32_t v0[32], v1[32];
         tmem_ld32(t_lane + chunk_tcol(c), v0);
-        tmem_ld32(t_lane + chunk_tcol(c + 1), v1);
+        tmem_ld32(t_lane + chunk_tcol(c + 2), v1);
+        const float4* a0 = pA + chunk_col(c, half);
+        const float4* a1 = pA + chunk_col(c + 2, half);
         tmem_ld_wait_dep(v0);
         tmem_ld_wait_dep(v1);
-        const float4* b40 = reinterpret_cast<const float4*>(p.b1 + chunk_col(c, half));
-        const float4* b41 = reinterpret_cast<const float4*>(p.b1 + chunk_col(c + 1, half));
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 ba = __ldg(b40 + i), bb = __ldg(b41 + i);
-          s0 += ((__uint_as_float(v0[4 * i + 0]) + ba.x) + (__uint_as_float(v0[4 * i + 1]) + ba.y)) +
-                ((__uint_as_float(v0[4 * i + 2]) + ba.z) + (__uint_as_float(v0[4 * i + 3]) + ba.w));
-          s1 += ((__uint_as_float(v1[4 * i + 0]) + bb.x) + (__uint_as_float(v1[4 * i + 1]) + bb.y)) +
-                ((__uint_as_float(v1[4 * i + 2]) + bb.z) + (__uint_as_float(v1[4 * i + 3]) + bb.w));
+        for (int i = 0; i < 32; ++i) {
+          s0 += __uint_as_float(v0[i]) + a0[i].x;
+          s1 += __uint_as_float(v1[i]) + a1[i].x;
         }
         sum += s0 + s1;
       }
-      // row mean: the other column half of this row lives in lane tl ^ 64 (another warp)
-      xch[tl] = sum;
+      // row mean: the row's other chunk parity lives in the partner warp, its other column half in lane tl ^ 64
+      xch[grp * 128 + tl] = sum;
       named_bar(1, kEpiWarps * 32);
-      const float mean = (sum + xch[tl ^ 64]) * (1.0f / N_LN);
+      const float mean = ((xch[tl] + xch[128 + tl]) + (xch[tl ^ 64] + xch[128 + (tl ^ 64)])) * (1.0f / N_LN);
       named_bar(1, kEpiWarps * 32);
 
       // ---------------- pass 1b: centred sum of squares ----------------
       float sq = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 12; c += 2) {
+      for (int c = grp; c < 12; c += 4) {
         uint32_t v0[32], v1[32];
         tmem_ld32(t_lane + chunk_tcol(c), v0);
-        tmem_ld32(t_lane + chunk_tcol(c + 1), v1);
+        tmem_ld32(t_lane + chunk_tcol(c + 2), v1);
+        const float4* a0 = pA + chunk_col(c, half);
+        const float4* a1 = pA + chunk_col(c + 2, half);
         tmem_ld_wait_dep(v0);
         tmem_ld_wait_dep(v1);
-        const float4* b40 = reinterpret_cast<const float4*>(p.b1 + chunk_col(c, half));
-        const float4* b41 = reinterpret_cast<const float4*>(p.b1 + chunk_col(c + 1, half));
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 ba = __ldg(b40 + i), bb = __ldg(b41 + i);
-          const float a0 = (__uint_as_float(v0[4 * i + 0]) + ba.x) - mean, a1 = (__uint_as_float(v0[4 * i + 1]) + ba.y) - mean;
-          const float a2 = (__uint_as_float(v0[4 * i + 2]) + ba.z) - mean, a3 = (__uint_as_float(v0[4 * i + 3]) + ba.w) - mean;
-          const float c0 = (__uint_as_float(v1[4 * i + 0]) + bb.x) - mean, c1 = (__uint_as_float(v1[4 * i + 1]) + bb.y) - mean;
-          const float c2 = (__uint_as_float(v1[4 * i + 2]) + bb.z) - mean, c3 = (__uint_as_float(v1[4 * i + 3]) + bb.w) - mean;
-          s0 = fmaf(a0, a0, s0); s0 = fmaf(a1, a1, s0); s0 = fmaf(a2, a2, s0); s0 = fmaf(a3, a3, s0);
-          s1 = fmaf(c0, c0, s1); s1 = fmaf(c1, c1, s1); s1 = fmaf(c2, c2, s1); s1 = fmaf(c3, c3, s1);
+        for (int i = 0; i < 32; ++i) {
+          const float d0 = (__uint_as_float(v0[i]) + a0[i].x) - mean, d1 = (__uint_as_float(v1[i]) + a1[i].x) - mean;
+          s0 = fmaf(d0, d0, s0);
+          s1 = fmaf(d1, d1, s1);
         }
         sq += s0 + s1;
       }
-      xch[tl] = sq;
+      xch[grp * 128 + tl] = sq;
       named_bar(1, kEpiWarps * 32);
-      const float rstd = 1.0f / sqrtf((sq + xch[tl ^ 64]) * (1.0f / N_LN) + p.eps);
+      const float rstd = 1.0f / sqrtf(((xch[tl] + xch[128 + tl]) + (xch[tl ^ 64] + xch[128 + (tl ^ 64)])) * (1.0f / N_LN) + p.eps);
       named_bar(1, kEpiWarps * 32);
 
       // ---------------- pass 2: both LayerNorms, average, hi/lo split, row-contiguous stores ----------------
       const float xa = rstd, xb = -mean * rstd;        // LN_1: (x - mean) * rstd = x * xa + xb
       const float ya = yrstd, yb = -ymean * yrstd;
 #pragma unroll 1
-      for (int c = 0; c < 12; ++c) {
+      for (int c = grp; c < 12; c += 2) {
         uint32_t v[32];
         tmem_ld32(t_lane + chunk_tcol(c), v);
-        tmem_ld_wait_dep(v);
         const int col0 = chunk_col(c, half);
-        uint8_t* rowp = buf + lane * 128;
+        tmem_ld_wait_dep(v);
+        uint8_t* rowp = buf + lane * 64;
         uint32_t hw[16], lw[16];
-        const float4* b14 = reinterpret_cast<const float4*>(p.b1 + col0);
-        const float4* g14 = reinterpret_cast<const float4*>(p.g1 + col0);
-        const float4* e14 = reinterpret_cast<const float4*>(p.be1 + col0);
-        const float4* b24 = reinterpret_cast<const float4*>(p.b2 + col0);
-        const float4* g24 = reinterpret_cast<const float4*>(p.g2 + col0);
-        const float4* e24 = reinterpret_cast<const float4*>(p.be2 + col0);
-        const float4* w24 = reinterpret_cast<const float4*>(p.W2p + static_cast<long long>(col0) * 8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {  // columns col0 + 4i .. col0 + 4i + 3 (all lanes of the warp read the same parameters)
-          const float4 b1v = __ldg(b14 + i), g1v = __ldg(g14 + i), e1v = __ldg(e14 + i);
-          const float4 b2v = __ldg(b24 + i), g2v = __ldg(g24 + i), e2v = __ldg(e24 + i);
-          const float b1a[4] = {b1v.x, b1v.y, b1v.z, b1v.w}, g1a[4] = {g1v.x, g1v.y, g1v.z, g1v.w}, e1a[4] = {e1v.x, e1v.y, e1v.z, e1v.w};
-          const float b2a[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, g2a[4] = {g2v.x, g2v.y, g2v.z, g2v.w}, e2a[4] = {e2v.x, e2v.y, e2v.z, e2v.w};
-          float o[4];
+        for (int i = 0; i < 16; ++i) {  // columns col0 + 2i, col0 + 2i + 1 (all lanes of the warp read the same parameters)
+          float o[2];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float x = __uint_as_float(v[4 * i + e]) + b1a[e];
-            const float xn = fmaf(fmaf(x, xa, xb), g1a[e], e1a[e]);
-            const float4 w0 = __ldg(w24 + (4 * i + e) * 2);
-            float y = fmaf(bx[0], w0.x, 0.f);  // torch addmm order: sum_k box[k] W2[n,k], then + bias
-            y = fmaf(bx[1], w0.y, y);
-            y = fmaf(bx[2], w0.z, y);
-            y = fmaf(bx[3], w0.w, y);
-            if (KB > 4) {
-              const float4 w1 = __ldg(w24 + (4 * i + e) * 2 + 1);
-              y = fmaf(bx[4], w1.x, y);
-              y = fmaf(bx[5], w1.y, y);
-              y = fmaf(bx[6], w1.z, y);
-              y = fmaf(bx[7], w1.w, y);
-            }
-            y += b2a[e];
-            const float yn = fmaf(fmaf(y, ya, yb), g2a[e], e2a[e]);
-            o[e] = (xn + yn) / 2.f;
+          for (int ee = 0; ee < 2; ++ee) {
+            const int n = col0 + 2 * i + ee;
+            const float4 a = pA[n], w = pW[n];
+            const float x = __uint_as_float(v[2 * i + ee]) + a.x;
+            const float xn = fmaf(x, xa, xb);
+            float yg = fmaf(bx[0], w.x, pB[n]);   // (box · W2[n] + b2[n]) * g2[n]
+            yg = fmaf(bx[1], w.y, yg);
+            yg = fmaf(bx[2], w.z, yg);
+            yg = fmaf(bx[3], w.w, yg);
+            const float yn = fmaf(yg, ya, yb * a.w);
+            o[ee] = (fmaf(xn, a.y, yn) + a.z) * 0.5f;   // (LN_1(x) g1 + be1 + LN_2(y) g2 + be2) / 2
           }
-          hw[2 * i] = pack_bf16x2(o[0], o[1]);
-          hw[2 * i + 1] = pack_bf16x2(o[2], o[3]);
-          const float2 h0 = unpack_bf16x2(hw[2 * i]), h1 = unpack_bf16x2(hw[2 * i + 1]);
-          lw[2 * i] = pack_bf16x2(o[0] - h0.x, o[1] - h0.y);
-          lw[2 * i + 1] = pack_bf16x2(o[2] - h1.x, o[3] - h1.y);
+          hw[i] = pack_bf16x2(o[0], o[1]);
+          const float2 hf = unpack_bf16x2(hw[i]);
+          lw[i] = pack_bf16x2(o[0] - hf.x, o[1] - hf.y);
         }
-        // this thread's row of the staging buffer: pieces 0-3 = 32 hi values, pieces 4-7 = 32 lo values
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          *reinterpret_cast<uint4*>(rowp + ((i ^ sw) << 4)) = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
-          *reinterpret_cast<uint4*>(rowp + (((4 + i) ^ sw) << 4)) = make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
-        }
-        __syncwarp();
-        __nv_bfloat16* dst = (cpiece < 4 ? p.hi : p.lo) + col0 + (cpiece & 3) * 8;
+        for (int pass = 0; pass < 2; ++pass) {  // hi rows, then lo rows, through the same 2 KB buffer
+          const uint32_t* src = pass == 0 ? hw : lw;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = crow + 4 * i;
-          const int r = row_base + rl;
-          const uint4 y = *reinterpret_cast<const uint4*>(buf + rl * 128 + ((cpiece ^ (rl & 7)) << 4));
-          if (r < p.M) *reinterpret_cast<uint4*>(dst + static_cast<long long>(r) * N_LN) = y;
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(rowp + ((i ^ sw) << 4)) = make_uint4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
+          __syncwarp();
+          __nv_bfloat16* dst = (pass == 0 ? p.hi : p.lo) + col0 + cpiece * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = crow + 8 * i;
+            const int r = row_base + rl;
+            const uint4 y = *reinterpret_cast<const uint4*>(buf + rl * 64 + ((cpiece ^ ((rl >> 1) & 3)) << 4));
+            if (r < p.M) *reinterpret_cast<uint4*>(dst + static_cast<long long>(r) * N_LN) = y;
+          }
+          __syncwarp();  // the buffer is rewritten by the next pass / chunk
         }
-        __syncwarp();  // the buffer is rewritten by the next chunk
       }
       // identity statistics: (sum 0, sumsq 768) -> mean 0, rstd 1 for the next consumer / producer
-      if (half == 0 && row < p.M) {
+      if (half == 0 && grp == 0 && row < p.M) {
         float4* so = reinterpret_cast<float4*>(p.stats + static_cast<long long>(row) * 12);
         so[0] = make_float4(0.f, static_cast<float>(N_LN), 0.f, 0.f);
         so[1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -391,7 +382,7 @@ int visn_embed(cudaStream_t stream, const void* feat, int feat_f32, long long ld
   RGQA_CHECK(M > 0 && K > 0, "visn_embed: empty problem");
   const int bk = feat_f32 ? 32 : 64;
   RGQA_CHECK(K % bk == 0, "visn_embed: K=%d must be a multiple of %d", K, bk);
-  RGQA_CHECK(box_dim >= 1 && box_dim <= 8, "visn_embed: box_dim %d out of range", box_dim);
+  RGQA_CHECK(box_dim >= 1 && box_dim <= 4, "visn_embed: box_dim %d out of range [1,4] (the LXMERT box projection)", box_dim);
   RGQA_CHECK(feat && W1 && b1 && g1 && be1 && boxes && W2p && b2 && g2 && be2 && bstat && hi && lo && stats, "visn_embed: null argument");
   RGQA_CHECK(reinterpret_cast<uintptr_t>(hi) % 16 == 0 && reinterpret_cast<uintptr_t>(lo) % 16 == 0 &&
                  reinterpret_cast<uintptr_t>(stats) % 16 == 0 && reinterpret_cast<uintptr_t>(b1) % 16 == 0 &&

@@ -148,6 +148,11 @@ class Engine:
         out = {m: (scores[c], labels[1 if c == L.SCORE_MAHA else 0]) for m, c in zip(modes, codes)}
         return out, pooled, logits
 
+    def fold_residue(self):
+        """(max |c[n]| over the folded consumer weights, number of consumers that kept the exact epilogue) — deferred LayerNorm."""
+        n = C.c_int(0)
+        return float(self._lib.rgqa_fold_residue(self._h, C.byref(n))), int(n.value)
+
     def graph_captures(self) -> int:
         return int(self._lib.rgqa_graph_captures(self._h))
 

@@ -4,6 +4,7 @@ the model.  Same class, attributes (``.model``, ``.tokenizer``, ``.max_seq_lengt
 from __future__ import annotations
 
 import os
+import warnings
 
 import torch
 import torch.nn as nn
@@ -31,14 +32,35 @@ def set_visual_config(args):
 
 
 def make_tokenizer(args, name="bert-base-uncased", vocab_size=30522):
+    """The reference downloads the vocabulary from S3 and fails loudly without it (tokenization.py:27-35).  Here the
+    vocabulary comes from ``--vocab`` / ``RGQA_BERT_VOCAB`` (a file or directory) or ``RGQA_BERT_VOCAB_DIR``.  The hash-based
+    ``SyntheticTokenizer`` is used only when asked for (``--vocab synthetic``) or, WITH A WARNING, for models that carry no
+    checkpoint (random-init parity / benchmark runs); as soon as a checkpoint is involved (``--load*`` flags, ``load()``)
+    an unresolved vocabulary is an error: trained embeddings fed hash ids would produce garbage silently."""
     vocab = getattr(args, "vocab", None)
+    if vocab == "synthetic":
+        return SyntheticTokenizer(vocab_size)
     if vocab:
         return BertTokenizer.from_pretrained(vocab, do_lower_case=True)
     try:
         return BertTokenizer.from_pretrained(name, do_lower_case=True)
-    except EnvironmentError:
-        # no vocab offline: deterministic hash tokenizer (documented in DESIGN.md; parity runs pass ids directly)
-        return SyntheticTokenizer(vocab_size)
+    except EnvironmentError as e:
+        if any(getattr(args, k, None) for k in ("load", "load_lxmert", "load_lxmert_qa")):
+            raise EnvironmentError(
+                f"a checkpoint is being loaded but the '{name}' vocabulary cannot be resolved: pass --vocab <vocab.txt> or set "
+                "RGQA_BERT_VOCAB_DIR (use --vocab synthetic only for random-init runs)") from e
+        warnings.warn(f"no '{name}' vocabulary available offline: using the deterministic SyntheticTokenizer "
+                      "(random-init runs only; loading a checkpoint into this model will be refused)", stacklevel=2)
+        tok = SyntheticTokenizer(vocab_size)
+        tok.is_fallback = True
+        return tok
+
+
+def require_real_vocab(tokenizer, what):
+    """Refuse to put trained weights behind the fallback tokenizer (see make_tokenizer)."""
+    if getattr(tokenizer, "is_fallback", False):
+        raise EnvironmentError(f"{what}: the model was built without a vocabulary (SyntheticTokenizer fallback); pass --vocab "
+                               "<vocab.txt> / set RGQA_BERT_VOCAB_DIR, or --vocab synthetic if hash ids are really intended")
 
 
 class LXRTEncoder(nn.Module):
@@ -80,6 +102,7 @@ class LXRTEncoder(nn.Module):
 
     def load(self, path):
         """entry.py:126-152: strip a DataParallel ``module.`` prefix, report key differences, load non-strictly."""
+        require_real_vocab(self.tokenizer, "LXRTEncoder.load")
         print("Load LXMERT pre-trained model from %s" % path)
         state_dict = torch.load("%s_LXRT.pth" % path, map_location="cpu")
         state_dict = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in state_dict.items()}

@@ -38,6 +38,9 @@ class GQA:
 
     def load(self, path):
         """gqa_conf.py:375-381: strip '.module', non-strict load."""
+        from ..lxrt.entry import require_real_vocab
+        enc = getattr(self.model, "lxrt_encoder", None) or getattr(self.model, "encoder")
+        require_real_vocab(enc.tokenizer, "GQA.load")
         print("Load model from %s" % path)
         state_dict = torch.load("%s.pth" % path, map_location="cpu")
         state_dict = {k.replace(".module", ""): v for k, v in state_dict.items()}

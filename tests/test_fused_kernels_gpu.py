@@ -21,7 +21,7 @@ def _ln(x, g, b):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("M,box_dim", [(100, 4), (1152, 4), (5000, 4), (333, 7)])
+@pytest.mark.parametrize("M,box_dim", [(100, 4), (1152, 4), (5000, 4), (333, 3)])
 def test_visual_feature_encoder_in_one_kernel(cuda_device, dtype, M, box_dim):
     """(LN(feat W1^T + b1) + LN(box W2^T + b2)) / 2 as a bf16 hi/lo pair + identity statistics.  bf16 operands: exact products,
     fp32 accumulation -> 5e-5 abs on unit-variance outputs; fp32 operands go through kind::tf32 (10 mantissa bits)."""
@@ -35,7 +35,7 @@ def test_visual_feature_encoder_in_one_kernel(cuda_device, dtype, M, box_dim):
         feat, W1 = feat.to(torch.bfloat16), W1.to(torch.bfloat16)
     b1 = torch.randn(768, generator=g) * 0.1
     g1, be1 = 1 + 0.1 * torch.randn(768, generator=g), 0.1 * torch.randn(768, generator=g)
-    box = torch.rand(M, box_dim, generator=g) * (1.0 if box_dim == 4 else 300.0)   # UNITER boxes are un-normalised pixels
+    box = torch.rand(M, box_dim, generator=g) * (1.0 if box_dim == 4 else 300.0)   # also un-normalised (pixel-scale) boxes
     W2 = torch.randn(768, box_dim, generator=g) * 0.02
     b2 = torch.randn(768, generator=g) * 0.1
     g2, be2 = 1 + 0.1 * torch.randn(768, generator=g), 0.1 * torch.randn(768, generator=g)

@@ -207,8 +207,28 @@ def test_drop_in_flow_reproduces_the_reference_stack_end_to_end(cuda_device, tmp
     label2ans = [f"answer{j}" for j in range(d["num_answers"])] + ["UQ"]
     qid2label = {q: dict(map(tuple, l)) for q, l in zip(d["qids"], d["labels"])}
     bs = d["batch"]
-    # bf16 operands move the logits by ~1e-2: MSP sits on the flat part of the sigmoid, the other two scale with it
-    tol = {"fp32": {"msp": 1.5e-4, "energy": 2e-4, "maha": 2e-3}, "bf16": {"msp": 1.5e-3, "energy": 6e-2, "maha": 1.0}}[precision]
+    # bf16 operands move the logits by ~1e-2: MSP sits on the flat part of the sigmoid, energy scales with the logits,
+    # Mahalanobis (|score| ~ 400 here) is held to a RELATIVE bound
+    tol = {"fp32": {"msp": 1.5e-4, "energy": 2e-4, "maha": 2e-3}, "bf16": {"msp": 1.5e-3, "energy": 6e-2, "maha": 5e-3}}[precision]
+    ref32 = None
+    if precision == "bf16":   # the fp32 CUDA path on the same inputs gives the margins that decide which label swaps are legitimate
+        a32 = types.SimpleNamespace(**{**vars(a), "precision": "fp32"})
+        m32 = GQAModel_maha(d["num_answers"], args=a32, max_seq_length=d["max_seq_length"])
+        m32.load_state_dict(syn.lxmert_state_dict(variant="rich", head_sigma=d["head_sigma"], **d["layers"]), strict=True)
+        m32 = m32.to(cuda_device)
+        m32.engine().set_maha(mu, P)
+        lg, xs, full = [], [], []
+        for lo in range(0, len(d["qids"]), bs):
+            sl = slice(lo, lo + bs)
+            logit, x = m32(inp["feat"][sl].to(cuda_device), inp["pos"][sl].to(cuda_device), d["sents"][sl])
+            lg.append(logit)
+            full.append(m32.engine().score("maha", pooled=x, return_full=True)[2])
+        lg, full = torch.cat(lg), torch.cat(full)
+        t2l, t2m = lg.topk(2, dim=1).values, full.topk(2, dim=1).values
+        # a label may differ from the reference's only where the reference's own top-2 margin is inside the bf16 noise:
+        # 2 x the 2e-2 logit tolerance for the logit scorers, 2 x 1e-3 relative for the Mahalanobis score
+        ref32 = {"msp": (t2l[:, 0] - t2l[:, 1]).cpu() > 4e-2, "energy": (t2l[:, 0] - t2l[:, 1]).cpu() > 4e-2,
+                 "maha": ((t2m[:, 0] - t2m[:, 1]) > 2e-3 * t2m[:, 0].abs()).cpu()}
     for method in ("msp", "energy", "maha"):
         quesid2ans = {}
         for lo in range(0, len(d["qids"]), bs):
@@ -227,10 +247,15 @@ def test_drop_in_flow_reproduces_the_reference_stack_end_to_end(cuda_device, tmp
         if precision == "fp32":
             assert all(same), (method, same)
         else:
-            # the smallest top-2 MSP margin of this random-init batch is 3e-5, inside bf16's logit noise: labels of
-            # near-tied classes may swap; the rows that agree must still carry the reference's confidence
-            assert sum(same) >= len(same) // 2, (method, same)
-        conf_err = max(abs(r["confidence"] - w["confidence"]) for r, w, ok in zip(rows, want, same) if ok)
+            # labels of near-tied classes may swap under bf16's logit noise — but ONLY those: every question whose
+            # fp32 margin is clear of the tolerance must carry the reference's answer
+            clear = ref32[method]
+            assert all(ok for ok, c in zip(same, clear.tolist()) if c), (method, [i for i, (ok, c) in enumerate(zip(same, clear.tolist())) if c and not ok])
+            assert int(clear.sum()) >= len(same) // 4, (method, int(clear.sum()))   # the check is not vacuous
+        if precision == "bf16" and method == "maha":   # relative: |score| ~ 400
+            conf_err = max(abs(r["confidence"] - w["confidence"]) / abs(w["confidence"]) for r, w, ok in zip(rows, want, same) if ok)
+        else:
+            conf_err = max(abs(r["confidence"] - w["confidence"]) for r, w, ok in zip(rows, want, same) if ok)
         assert conf_err <= tol[method], (method, conf_err)
         if precision == "fp32":
             assert set(res) == set(d["results"][method])

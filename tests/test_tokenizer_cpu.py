@@ -54,3 +54,31 @@ def test_roundtrip_and_errors(tmp_path):
     ids, mask, _ = s.encode_batch(["Is the cat on the mat?", ""], 20)
     assert ids[0, 0] == 101 and ids[0, mask[0].sum() - 1] == 102 and ids[1, 1] == 102
     assert (ids[0, 1:mask[0].sum() - 1] >= 1000).all() and ids.max() < 30522
+
+
+def test_tokenizer_fallback_is_loud_and_refused_with_checkpoints(monkeypatch):
+    """the hash-based SyntheticTokenizer must never sit silently in front of trained embeddings.  Without a
+    vocabulary: a warning for checkpoint-free models, an error as soon as a checkpoint is involved; `--vocab synthetic` is
+    the explicit opt-in; a real vocab file resolves to the WordPiece tokenizer."""
+    import types
+    import warnings
+    import pytest
+    from rgqa_b200.lxrt import entry
+    from rgqa_b200.lxrt.tokenization import BertTokenizer, SyntheticTokenizer
+    monkeypatch.delenv("RGQA_BERT_VOCAB_DIR", raising=False)
+    ns = lambda **kw: types.SimpleNamespace(**{"vocab": None, "load": None, "load_lxmert": None, "load_lxmert_qa": None, **kw})
+    with pytest.warns(UserWarning, match="SyntheticTokenizer"):
+        tok = entry.make_tokenizer(ns())
+    assert isinstance(tok, SyntheticTokenizer) and tok.is_fallback
+    with pytest.raises(EnvironmentError, match="vocabulary"):
+        entry.require_real_vocab(tok, "GQA.load")
+    with pytest.raises(EnvironmentError, match="checkpoint is being loaded"):
+        entry.make_tokenizer(ns(load="snap/gqa/x/BEST"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        explicit = entry.make_tokenizer(ns(vocab="synthetic", load="snap/gqa/x/BEST"))
+    assert isinstance(explicit, SyntheticTokenizer) and not getattr(explicit, "is_fallback", False)
+    entry.require_real_vocab(explicit, "GQA.load")
+    vocab = os.path.join(os.path.dirname(__file__), "golden", "tokenizer_vocab.txt")
+    real = entry.make_tokenizer(ns(vocab=vocab, load="snap/gqa/x/BEST"))
+    assert isinstance(real, BertTokenizer)
