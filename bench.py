@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="eval", choices=["eval", "train"],
+                    help="eval = the headline (BASELINE.json configs[1]); train = the RP-finetune step (configs[4]), a side measurement")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the UNITER (configs[2]) side measurement")
     ap.add_argument("--ref-batch", type=int, default=32)
@@ -506,9 +508,91 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# --workload train: BASELINE.json configs[4], the RP-finetune step, data parallel (NOT the headline metric)
+# ------------------------------------------------------------------------------------------------
+def run_train(a):
+    """Per rank: B = 64 questions + 64 random-pairing negatives = 128 rows (src/tasks/gqa_conf.py:148-202: forward, BCE x A,
+    backward, clip 5.0, BertAdam); gradients all-reduced (mean) in per-layer buckets overlapped with the backward.  Mixed
+    precision: bf16 tensor-core GEMMs, fp32 master weights / activations / gradients / optimiser."""
+    import random
+    import torch.distributed as dist
+    from rgqa_b200 import synthetic as syn
+    from rgqa_b200.lxrt.trainer import LXMERTTrainer
+    from rgqa_b200.tasks.rp import build_rp_batch
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, Lq, A = 64, a.seq_len, 1842
+    tr = LXMERTTrainer(syn.lxmert_state_dict(variant="init"), device=dev, lr=1e-5, warmup=0.1, t_total=10000,
+                       gemm="bf16" if a.precision == "bf16" else "fp32")
+    rng = random.Random(1 + rank)
+
+    def batch(step):
+        inp = syn.make_inputs(B, Lq, seed=10_000 * rank + step)
+        qids = [f"q{rank}_{step}_{i}" for i in range(B)]
+        img = {q: f"img{i}" for i, q in enumerate(qids)}
+        g = torch.Generator().manual_seed(77 * rank + step)
+        target = torch.zeros(B, A)
+        target[torch.arange(B), torch.randint(0, A, (B,), generator=g)] = 1.0
+        q2, f2, b2, s2, t2 = build_rp_batch(qids, inp["feat"], inp["pos"], list(range(B)), target,
+                                            lambda q: img[q.split("+")[-1]] if "+" in q else img[q], rng)
+        rows = torch.tensor(s2)
+        return [t.to(dev) for t in (f2, b2, inp["ids"][rows], inp["seg"][rows], inp["mask"][rows], t2)]
+    batches = [batch(i) for i in range(4)]     # resident: the step is timed, not the synthetic data generator
+
+    def timed(k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = [tr.train_step(*batches[i & 3]) for i in range(k)]
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / k, out
+    for i in range(max(a.warmup, 2)):
+        tr.train_step(*batches[i & 3])
+    ms_step, out = timed(a.steps)
+    blocking = None
+    if world > 1:            # A/B: the single blocking all-reduce after the backward (round-1 behaviour)
+        tr.bucketed = False
+        tr.train_step(*batches[0])
+        blocking, _ = timed(a.steps)
+        tr.bucketed = True
+        chk = tr.flat_p.double().sum().reshape(1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        identical = all(bool(torch.equal(c, allc[0])) for c in allc)
+    if rank == 0:
+        line = {"metric": "RP-finetune questions/sec (BASELINE.json configs[4]; side workload, not the headline)", "value": world * B / (ms_step * 1e-3),
+                "unit": "questions/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 2), "ms_per_step": ms_step,
+                "steps_per_s": 1e3 / ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16 GEMMs / fp32 master" if a.precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": "LXMERT-base 9/5/5 RP-finetune step: 64 questions + 64 random-pairing negatives per rank, forward + BCE x A + "
+                                       "backward + clip 5.0 + BertAdam, dropout off, gradients all-reduced in per-layer buckets overlapped with the backward",
+                           "rows_per_step": world * 2 * B, "grad_buckets": tr.comm_stats["buckets"], "grad_bytes": tr.comm_stats["bytes"]},
+                "loss_last": out[-1][0], "grad_norm_last": out[-1][1]}
+        if world > 1:
+            line["ms_per_step_blocking_allreduce"] = blocking
+            line["ranks_identical"] = identical
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_ours(args)

@@ -68,6 +68,17 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 __device__ __forceinline__ uint32_t sw128_addr(uint32_t line_addr, int chunk) {
   return line_addr + ((static_cast<uint32_t>(chunk) ^ ((line_addr >> 7) & 7u)) << 4);
 }
+__device__ __forceinline__ float ex2_fast(float x) {  // same expression as attention.cu (bit-identical paths)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
 __device__ __forceinline__ float row_rstd(const float* __restrict__ stats, int row, float eps) {
   const float4* s4 = reinterpret_cast<const float4*>(stats + static_cast<long long>(row) * 12);
   const float4 a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(s4 + 2);
@@ -250,37 +261,39 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int u = task / MT, mt = task - u * MT;
         const int b = sample0 + u;
         if (b >= p.B) continue;  // tail tile: no such sample
+        if (((p.debug & 8) && u != 0) || ((p.debug & 16) && mt != 0)) continue;  // measurement: a third of the tasks
         const uint32_t rb = static_cast<uint32_t>(u * p.S);  // first line of this sample in each matrix
         const int m0q = mt * 16;
-        float madd[NT][2];
+        // every fragment row of this task has the same (row & 7) up to the lane's own offset: the 128B-swizzle XOR is computed
+        // once per task, every ldmatrix address below is base + immediate
+        const uint32_t r7 = (rb + static_cast<uint32_t>(lane & 7)) & 7u;
+        const uint32_t c16 = static_cast<uint32_t>(lane >> 4), c8 = static_cast<uint32_t>(lane >> 3);
+        uint32_t offq[4], offk[2];   // byte offsets of chunk 2x + (lane >> 4) (Q, V) and 4x + (lane >> 3) (K) inside a line
 #pragma unroll
-        for (int j = 0; j < NT; ++j)
+        for (int x = 0; x < 4; ++x) offq[x] = ((static_cast<uint32_t>(2 * x) + c16) ^ r7) << 4;
 #pragma unroll
-          for (int ee = 0; ee < 2; ++ee) {
-            const int key = 8 * j + 2 * tq + ee;
-            madd[j][ee] = key >= p.S ? -INFINITY
-                                     : ((p.key_mask != nullptr && __ldg(p.key_mask + b * p.S + key) == 0) ? -10000.f * kLog2e : 0.f);
-          }
-        uint32_t qa[4][4];
-        {
-          const uint32_t line = Qb + (rb + static_cast<uint32_t>(m0q + (lane & 15))) * 128u;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(qa[ks][0]), "=r"(qa[ks][1]), "=r"(qa[ks][2]), "=r"(qa[ks][3])
-                         : "r"(sw128_addr(line, 2 * ks + (lane >> 4))));
+        for (int x = 0; x < 2; ++x) offk[x] = ((static_cast<uint32_t>(4 * x) + c8) ^ r7) << 4;
+        const uint32_t qline = Qb + (rb + static_cast<uint32_t>(m0q + (lane & 15))) * 128u;
+        const uint32_t kline = Kb + (rb + static_cast<uint32_t>(lane & 7)) * 128u;
+        const uint32_t vline = Vb + (rb + static_cast<uint32_t>((lane & 7) + ((lane >> 3) & 1) * 8)) * 128u;
+        // key mask of this sample as bits (one ballot per 32 keys) instead of one global load per score column
+        uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;
+        if (p.key_mask != nullptr) {
+          const int32_t* mrow = p.key_mask + static_cast<long long>(b) * p.S;
+          keep_lo = __ballot_sync(0xffffffffu, lane < p.S ? __ldg(mrow + lane) != 0 : false);
+          if (NT > 4) keep_hi = __ballot_sync(0xffffffffu, lane + 32 < p.S ? __ldg(mrow + lane + 32) != 0 : false);
         }
+        uint32_t qa[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ldsm_x4(qa[ks], qline + offq[ks]);
         float s[NT][4];
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-          const uint32_t line = Kb + (rb + static_cast<uint32_t>(8 * j + (lane & 7))) * 128u;
 #pragma unroll
           for (int kp = 0; kp < 2; ++kp) {
             uint32_t kb4[4];
-            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(kb4[0]), "=r"(kb4[1]), "=r"(kb4[2]), "=r"(kb4[3])
-                         : "r"(sw128_addr(line, 4 * kp + (lane >> 3))));
+            ldsm_x4(kb4, kline + static_cast<uint32_t>(j * 1024) + offk[kp]);
             mma_bf16_16816(s[j], qa[2 * kp], kb4[0], kb4[1]);
             mma_bf16_16816(s[j], qa[2 * kp + 1], kb4[2], kb4[3]);
           }
@@ -289,10 +302,17 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-          s[j][0] = fmaf(s[j][0], kScaleLog2e, madd[j][0]);
-          s[j][1] = fmaf(s[j][1], kScaleLog2e, madd[j][1]);
-          s[j][2] = fmaf(s[j][2], kScaleLog2e, madd[j][0]);
-          s[j][3] = fmaf(s[j][3], kScaleLog2e, madd[j][1]);
+          float madd[2];
+#pragma unroll
+          for (int ee = 0; ee < 2; ++ee) {
+            const int key = 8 * j + 2 * tq + ee;
+            const uint32_t bits = (8 * j < 32) ? keep_lo : keep_hi;   // compile-time per j
+            madd[ee] = key >= p.S ? -INFINITY : (((bits >> (key & 31)) & 1u) ? 0.f : -10000.f * kLog2e);
+          }
+          s[j][0] = fmaf(s[j][0], kScaleLog2e, madd[0]);
+          s[j][1] = fmaf(s[j][1], kScaleLog2e, madd[1]);
+          s[j][2] = fmaf(s[j][2], kScaleLog2e, madd[0]);
+          s[j][3] = fmaf(s[j][3], kScaleLog2e, madd[1]);
           mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
           mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
         }
@@ -304,8 +324,8 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint32_t pa[KS][4];
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-          const float p0 = exp2f(s[j][0] - mx0), p1 = exp2f(s[j][1] - mx0);
-          const float p2 = exp2f(s[j][2] - mx1), p3 = exp2f(s[j][3] - mx1);
+          const float p0 = ex2_fast(s[j][0] - mx0), p1 = ex2_fast(s[j][1] - mx0);
+          const float p2 = ex2_fast(s[j][2] - mx1), p3 = ex2_fast(s[j][3] - mx1);
           sum0 += p0 + p1;
           sum1 += p2 + p3;
           pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
@@ -320,13 +340,10 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int d = 0; d < 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          const uint32_t line = Vb + (rb + static_cast<uint32_t>(ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8)) * 128u;
 #pragma unroll
           for (int dp = 0; dp < 4; ++dp) {
             uint32_t vb4[4];
-            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(vb4[0]), "=r"(vb4[1]), "=r"(vb4[2]), "=r"(vb4[3])
-                         : "r"(sw128_addr(line, 2 * dp + (lane >> 4))));
+            ldsm_x4_trans(vb4, vline + static_cast<uint32_t>(ks * 2048) + offq[dp]);
             mma_bf16_16816(o[2 * dp], pa[ks], vb4[0], vb4[1]);
             mma_bf16_16816(o[2 * dp + 1], pa[ks], vb4[2], vb4[3]);
           }
@@ -336,13 +353,15 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
         __syncwarp();
         const int r0 = m0q + g, r1 = r0 + 8;
-        const uint32_t l0 = Qb + (rb + static_cast<uint32_t>(r0)) * 128u, l1 = Qb + (rb + static_cast<uint32_t>(r1)) * 128u;
+        const uint32_t r7o = (rb + static_cast<uint32_t>(g)) & 7u;   // (row & 7) of both output rows (r1 = r0 + 8)
+        const uint32_t l0 = Qb + (rb + static_cast<uint32_t>(r0)) * 128u + 4u * tq, l1 = l0 + 1024u;
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
+          const uint32_t off = (static_cast<uint32_t>(d) ^ r7o) << 4;
           if (r0 < p.S)
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw128_addr(l0, d) + 4u * tq), "r"(pack_bf16x2(o[d][0] * inv0, o[d][1] * inv0)) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(l0 + off), "r"(pack_bf16x2(o[d][0] * inv0, o[d][1] * inv0)) : "memory");
           if (r1 < p.S)
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw128_addr(l1, d) + 4u * tq), "r"(pack_bf16x2(o[d][2] * inv1, o[d][3] * inv1)) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(l1 + off), "r"(pack_bf16x2(o[d][2] * inv1, o[d][3] * inv1)) : "memory");
         }
       }
       // ---- (3) context tile out: ONE TMA store of the whole-sample rows (rows >= M are clipped by the tensor map) ----

@@ -5,7 +5,8 @@ cores); every operator is a kernel of this package behind the C ABI, PyTorch hol
 
 * parameters, gradients and both Adam moments live in four FLAT fp32 buffers (the reference's single parameter group,
   ``gqa_conf.py:123-127``): zeroing the gradients is one memset, the global norm one reduction, the optimiser ONE kernel
-  launch, and data parallelism ONE all-reduce of the flat gradient per step (mean over ranks, like DDP);
+  launch; data parallelism = one NCCL all-reduce (mean over ranks, like DDP) per finished layer's contiguous slice of the flat
+  gradient, issued during the backward and overlapped with it (``buckets``), the optimiser waiting only for the last one;
 * backward = the dgrad chain of ``input_grad.py`` extended down through the nine language layers and the embeddings, plus the
   weight gradients (``rgqa_gemm_f32_tn``, ``rgqa_colsum``, ``rgqa_ln_param_grad``, ``rgqa_embedding_scatter``), accumulated
   straight into the flat gradient buffer under the reference's parameter names;
@@ -41,7 +42,7 @@ class _Ffn:
 class LXMERTTrainer:
     def __init__(self, state_dict, l_layers=9, x_layers=5, r_layers=5, heads=12, eps=1e-12, device="cuda:0", lr=5e-5, warmup=0.1,
                  t_total=-1, schedule="warmup_linear", b1=0.9, b2=0.999, e=1e-6, weight_decay=0.01, clip_norm=5.0, gemm="fp32",
-                 dropout=0.0, seed=9595):
+                 dropout=0.0, seed=9595, bucketed=True):
         """``gemm="bf16"``: the large matrix products (forward, dgrad and wgrad of every nn.Linear with K a multiple of 64)
         run on the tcgen05 tensor cores with bf16 operands cast on the fly and fp32 accumulation / outputs; master weights,
         activations, gradients and the optimiser stay fp32 (mixed precision; not the reference's arithmetic — parity with
@@ -49,6 +50,7 @@ class LXMERTTrainer:
         assert gemm in ("fp32", "bf16") and 0.0 <= dropout < 1.0
         dev = torch.device(device)
         self.gemm = gemm
+        self.bucketed = bucketed   # False: the single blocking all-reduce after the backward (A/B of the overlap)
         # dropout > 0: the reference's training-mode dropout sites (embeddings, attention probabilities, the two output
         # projections of every block, the visual feature encoder) with this package's counter-based masks (not torch's)
         self.dropout, self.seed, self._site = dropout, seed, 0
@@ -64,11 +66,13 @@ class LXMERTTrainer:
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
         self.p, self.g = {}, {}
+        self._span = {}                                  # name -> (offset, padded size) inside the flat buffers
         off = 0
         for n, sz in zip(names, sizes):
             self.p[n] = self.flat_p[off:off + sz].view(state_dict[n].shape)
             self.g[n] = self.flat_g[off:off + sz].view(state_dict[n].shape)
             self.p[n].copy_(state_dict[n].detach().to(dev, torch.float32))
+            self._span[n] = (off, pad(sz))
             off += pad(sz)
         enc = P + "encoder."
         self.l = [(_Att(f"{enc}layer.{i}.attention", "self"), _Ffn(f"{enc}layer.{i}.intermediate", f"{enc}layer.{i}.output")) for i in range(l_layers)]
@@ -80,6 +84,34 @@ class LXMERTTrainer:
                        vf=_Ffn(f"{enc}x_layers.{i}.visn_inter", f"{enc}x_layers.{i}.visn_output")) for i in range(x_layers)]
         self._derived = {}
         self.tape = None
+        # Gradient buckets in the order the backward FINISHES them (data parallelism): answer head + pooler, the
+        # cross-modality layers last to first, the object-relational and language layers last to first, then the visual feature
+        # encoder + embeddings.  Each bucket is one contiguous slice of the flat gradient (the state dict groups a layer's tensors
+        # together), all-reduced on NCCL's own stream the moment its last weight gradient is enqueued, i.e. overlapped with the rest
+        # of the backward; only the last bucket's collective is exposed.
+        groups = [["logit_fc.", P + "pooler."]] + [[f"{enc}x_layers.{i}."] for i in reversed(range(x_layers))] + \
+                 [[f"{enc}r_layers.{i}."] for i in reversed(range(r_layers))] + [[f"{enc}layer.{i}."] for i in reversed(range(l_layers))] + \
+                 [[enc + "visn_fc.", P + "embeddings."]]
+        self.buckets = []
+        owner = {}
+        for gi, prefixes in enumerate(groups):
+            mine = [n for n in names if any(n.startswith(px) for px in prefixes)]
+            for n in mine:
+                owner[n] = gi
+            spans = sorted(self._span[n] for n in mine)
+            # split into maximal contiguous runs (head and pooler, or visn_fc and the embeddings, need not be neighbours)
+            runs, cur = [], None
+            for o, ln in spans:
+                if cur is not None and o == cur[1]:
+                    cur[1] = o + ln
+                else:
+                    cur = [o, o + ln]
+                    runs.append(cur)
+            self.buckets.append([(lo, hi) for lo, hi in runs])
+        assert set(owner) == set(names), sorted(set(names) - set(owner))[:5]
+        assert sum(hi - lo for b in self.buckets for lo, hi in b) == total
+        self._works, self._overlap = [], False
+        self.comm_stats = {"buckets": len(self.buckets), "bytes": 4 * total}
 
     # ---- parameter access: stacked Q|K|V and transposed copies are rebuilt lazily after every optimiser step ----
     def _w(self, name):
@@ -252,6 +284,13 @@ class LXMERTTrainer:
         self._qkv_wgrad(a, dqkv, tp["x_q"])
         return self._dgrad(dqkv, "qkv:" + a.q, self._qkv(a)[2], residual=d_pre)
 
+    def _bucket_done(self, k):
+        """Every weight gradient of bucket k is enqueued: start its all-reduce (mean over ranks) behind them, on NCCL's stream."""
+        if not self._overlap:
+            return
+        for lo, hi in self.buckets[k]:
+            self._works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.AVG, async_op=True))
+
     def backward(self, dlogits):
         t = self.tape
         B, V, Lt = t["B"], t["V"], t["L"]
@@ -264,6 +303,8 @@ class LXMERTTrainer:
         self._lin_wgrad("logit_fc.0", dh0, t["pooled"])
         d_pp = ops.tanh_bwd(ops.linear_f32(dh0, self._wt("logit_fc.0")), t["pooled"])
         self._lin_wgrad(P + "pooler.dense", d_pp, t["first"])
+        nb = 0
+        self._bucket_done(nb)
         dl = torch.zeros((B, Lt, H), dtype=torch.float32, device=self.dev)
         dl[:, 0, :] = ops.linear_f32(d_pp, self._wt(P + "pooler.dense"))
         dl = dl.view(B * Lt, H)
@@ -280,10 +321,16 @@ class LXMERTTrainer:
             wt = self._qkv(c)[2]
             dl = self._dgrad(dqkv_l, "qkv:" + c.q, wt, residual=d_pre_l)
             dv = self._dgrad(dqkv_v, "qkv:" + c.q, wt, residual=d_pre_v)
+            nb += 1
+            self._bucket_done(nb)
         for (a, f), (ta, tf) in zip(reversed(self.r), reversed(t["r"])):
             dv = self._self_att_bwd(a, ta, self._ffn_bwd(f, tf, dv))
+            nb += 1
+            self._bucket_done(nb)
         for (a, f), (ta, tf) in zip(reversed(self.l), reversed(t["l"])):
             dl = self._self_att_bwd(a, ta, self._ffn_bwd(f, tf, dl))
+            nb += 1
+            self._bucket_done(nb)
         v = P + "encoder.visn_fc."
         if self.dropout > 0:
             dv = ops.dropout_add(dv, None, self.dropout, t["s_visn"])
@@ -300,6 +347,7 @@ class LXMERTTrainer:
         ops.embedding_scatter_(self.g[e + "token_type_embeddings.weight"], t["seg"], d_e, padding_idx=0)
         pos_ids = torch.arange(Lt, dtype=torch.int32, device=self.dev).repeat(B)
         ops.embedding_scatter_(self.g[e + "position_embeddings.weight"], pos_ids, d_e, padding_idx=0)
+        self._bucket_done(nb + 1)
 
     # ---- one optimisation step (gqa_conf.py:148-198 without the data-side lines) ----
     def lr_now(self):
@@ -319,8 +367,17 @@ class LXMERTTrainer:
         loss = torch.zeros(1, dtype=torch.float64, device=self.dev)
         L.check(lib.rgqa_bce_loss_grad(L.current_stream_ptr(), L.ptr(logits), L.ptr(target), B, A, L.ptr(dlogits), L.ptr(loss)),
                 "rgqa_bce_loss_grad")
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        # NCCL: one bucket per finished layer, each all-reduce overlapped with the remaining backward (see __init__);
+        # other backends (the gloo CPU tests): one blocking all-reduce of the flat gradient after the backward
+        self._overlap = multi and dist.get_backend() == "nccl" and self.bucketed
+        self._works = []
         self.backward(dlogits)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if self._overlap:
+            for w in self._works:
+                w.wait()                                                # the compute stream waits; the host does not
+            self._works = []
+        elif multi:
             buf = self.flat_g if dist.get_backend() == "nccl" else self.flat_g.cpu()
             dist.all_reduce(buf)                                        # ONE collective per step
             self.flat_g.copy_(buf.to(self.dev) / dist.get_world_size())

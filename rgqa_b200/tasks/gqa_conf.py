@@ -24,13 +24,14 @@ from .gqa_model import GQAModel_maha
 
 
 class GQA:
-    def __init__(self, args):
+    def __init__(self, args, num_answers=1842):
+        """num_answers: the answer table WITHOUT the extra 'UQ' class (gqa_conf.py:80: ``GQAModel(num_answers - 1)``)."""
         self.args = args
         if args.backbone == "uniter":
             from ..uniter.uniter import GQAUNITER_maha
-            self.model = GQAUNITER_maha(1842, args=args)
+            self.model = GQAUNITER_maha(num_answers, args=args)
         elif args.backbone == "lxmert":
-            self.model = GQAModel_maha(1842, args=args, max_seq_length=args.max_seq_length)
+            self.model = GQAModel_maha(num_answers, args=args, max_seq_length=args.max_seq_length)
         else:
             raise ValueError("Backbone is not defined")  # gqa_conf.py:91
         self.output = args.output
@@ -123,33 +124,87 @@ class GQA:
         return results
 
 
+def get_tuple(args, splits, tokenizer, max_seq_length, rank=0, world=1):
+    """``get_tuple`` of the reference (gqa_conf.py:34-60) for the evaluation flows: the GQA-UQ data set (+ the 'UQ' class), this
+    rank's contiguous shard of it as a ``SweepLoader`` over the memory-mapped feature store, and the evaluator."""
+    from ..ingest import SweepLoader
+    from .gqa_data import FAST_IMG_NUM, TINY_IMG_NUM, GQADataset, GQAOODEvaluator, open_feature_store
+    dset = GQADataset(splits, root=args.data_root)
+    dset.add_uq_class()
+    topk = TINY_IMG_NUM if args.tiny else (FAST_IMG_NUM if args.fast else None)
+    store = open_feature_store(dset.splits, root=args.data_root, backbone=args.backbone, dtype=args.feature_dtype, topk=topk,
+                               store_dir=args.feature_store)
+    rows = [d for d in dset.data if d["img_id"] in store]       # GQATorchDataset keeps only questions whose image was loaded
+    print("Use %d data in torch dataset" % len(rows))
+    lo, hi = shard_range(len(rows), rank, world)
+    loader = SweepLoader(store, rows, tokenizer, max_seq_length=max_seq_length, batch_size=args.batch_size, lo=lo, hi=hi)
+    return dset, loader, GQAOODEvaluator(dset, args.tau)
+
+
 def main(argv=None):
     p = argparse.ArgumentParser(parents=[get_parser()])
-    p.add_argument("--syntheticN", type=int, default=4096)
+    p.add_argument("--syntheticN", type=int, default=None, help="evaluate on N synthetic questions instead of a data set")
+    p.add_argument("--dataRoot", dest="data_root", default="data", help="where gqa/<split>.json and vg_gqa_imgfeat/ live")
+    p.add_argument("--featureStore", dest="feature_store", default=None, help="a converted feature store (rgqa_b200.ingest)")
+    p.add_argument("--featureDtype", dest="feature_dtype", default="bf16", choices=["bf16", "f32"])
+    p.add_argument("--maha", default=None, help="pickle {mean, precision} written by sample_estimator (gqa_maha.py:185-188)")
     args, _ = p.parse_known_args(argv)
     if not torch.cuda.is_available():
         raise RuntimeError("rgqa_b200 needs a CUDA device; there is no CPU path")
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("RGQA_SINGLE_GPU") == "1":   # several ranks on one GPU (tests): every rank drives device 0
+        local = 0
     torch.cuda.set_device(local)
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        backend = os.environ.get("RGQA_DIST_BACKEND", "nccl")
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    rank = dist.get_rank() if dist.is_initialized() else 0
     if args.max_seq_length is None:
         args.max_seq_length = 30  # MAX_GQA_LENGTH, gqa_model.py:11
-    gqa = GQA(args)
+    if args.syntheticN is not None and args.vocab is None:
+        args.vocab = "synthetic"     # explicit: a synthetic data set has no real sentences to tokenise
+    num_answers = 1842
+    if args.syntheticN is None and args.test is not None:
+        import json
+        with open(os.path.join(args.data_root, "gqa", "trainval_label2ans.json")) as f:
+            num_answers = len(json.load(f))
+    gqa = GQA(args, num_answers)
     if args.load is not None:
         gqa.load(args.load)
     gqa.model = gqa.model.cuda()
     test = args.test or "synthetic"
-    L = 20 if args.backbone == "uniter" else args.max_seq_length
-    dataset = SyntheticRGQA(args.syntheticN, L=L, seed=args.seed)
-    if args.backbone == "uniter":
-        raise SystemExit("the synthetic data set carries 4-d boxes; drive GQAUNITER through GQAEval with 7-d boxes")
+    L = 20 if args.backbone == "uniter" else args.max_seq_length   # UniterEncoder hard-codes 20 (uniter/entry.py:66)
+    dump = os.path.join(args.output, "%s_predict.json" % test)
     maha = None
     if args.method == "maha":
-        from .. import synthetic as syn
-        maha = syn.maha_stats()
-    results = gqa.ood_evaluate(dataset, args.batch_size, args.method,
-                               dump=os.path.join(args.output, "%s_predict.json" % test), maha=maha)
+        if args.maha is not None:
+            import pickle
+            with open(args.maha, "rb") as f:
+                pack = pickle.load(f)
+            maha = (pack["mean"], pack["precision"])
+        elif args.syntheticN is not None:
+            from .. import synthetic as syn
+            maha = syn.maha_stats()
+        else:
+            raise RuntimeError("--method maha needs --maha <sample_estimator pickle> (gqa_maha.py:185-188)")
+    if args.syntheticN is not None:
+        if args.backbone == "uniter":
+            raise SystemExit("the synthetic data set carries 4-d boxes; drive GQAUNITER through a real feature store (7-d boxes)")
+        dataset = SyntheticRGQA(args.syntheticN, L=L, seed=args.seed)
+        results = gqa.ood_evaluate(dataset, args.batch_size, args.method, dump=dump, maha=maha)
+    else:
+        if args.test is None:
+            raise SystemExit("--test SPLIT (a file <dataRoot>/gqa/SPLIT.json) or --syntheticN N is required")
+        enc = getattr(gqa.model, "lxrt_encoder", None) or gqa.model.encoder
+        dset, loader, _ = get_tuple(args, args.test, enc.tokenizer, L, rank, world)
+        if maha is not None:
+            gqa.model.engine().set_maha(*maha)
+        ev = GQAEval(gqa.model, dset, method=args.method, tau=args.tau)
+        results = ev.ood_evaluate(loader, dump=dump if rank == 0 else None)
     if results is not None:
         print(results)
         dump_results_json(results, os.path.join(args.output, "%s_result.json" % test))

@@ -29,6 +29,73 @@ class LabelTable:
             return cls(json.load(f))
 
 
+TINY_IMG_NUM = 512     # gqa_data.py:21-22
+FAST_IMG_NUM = 5000
+
+
+class GQADataset:
+    """``GQADataset`` of the reference (gqa_data.py:25-60), same files under ``root`` (the reference hard-codes ``data``):
+    ``<root>/gqa/<split>.json`` rows ``{img_id, label, question_id, sent}`` for every comma-separated split,
+    ``<root>/gqa/trainval_ans2label.json`` / ``trainval_label2ans.json``; attributes ``data``, ``id2datum``, ``ans2label``,
+    ``label2ans``, ``num_answers``."""
+
+    def __init__(self, splits: str, root: str = "data"):
+        import os
+        self.name = splits
+        self.splits = splits.split(',')
+        self.data = []
+        for split in self.splits:
+            with open(os.path.join(root, "gqa", "%s.json" % split)) as f:
+                self.data.extend(json.load(f))
+        print("Load %d data from split(s) %s." % (len(self.data), self.name))
+        self.id2datum = {datum['question_id']: datum for datum in self.data}
+        with open(os.path.join(root, "gqa", "trainval_ans2label.json")) as f:
+            self.ans2label = json.load(f)
+        with open(os.path.join(root, "gqa", "trainval_label2ans.json")) as f:
+            self.label2ans = json.load(f)
+        assert len(self.ans2label) == len(self.label2ans)
+        for ans, label in self.ans2label.items():
+            assert self.label2ans[label] == ans
+        self.num_answers = len(self.ans2label)
+
+    def __len__(self):
+        return len(self.data)
+
+    def add_uq_class(self):
+        """get_tuple's "one more class" for gqa-uq (gqa_conf.py:36-40)."""
+        self.ans2label['UQ'] = self.num_answers
+        self.label2ans.append('UQ')
+        self.num_answers = len(self.label2ans)
+        print(f"One more answer added for {self.name}. Now there are {self.num_answers} answers.")
+
+
+def feature_tsv_path(splits, root="data"):
+    """GQABufferLoader.load_data (gqa_data.py:115-119): testdev splits read their own TSV, everything else Visual Genome's."""
+    import os
+    testdev = all('testdev' in s for s in splits)
+    return os.path.join(root, "vg_gqa_imgfeat", "gqa_testdev_obj36.tsv" if testdev else "vg_gqa_obj36.tsv")
+
+
+def open_feature_store(splits, root="data", backbone="lxmert", dtype="bf16", topk=None, store_dir=None):
+    """The image features of ``splits`` as a memory-mapped store (rgqa_b200.ingest): ``store_dir`` if given, else a
+    ``<tsv>.store_<dtype>_<backbone>[_topK]`` directory next to the reference's TSV, converted from it on first use (one
+    streaming pass instead of the reference's decode-everything-into-dicts on every start, src/utils.py:16-54)."""
+    import os
+    from ..ingest import FeatureStore, convert_obj_tsv
+    if store_dir is None:
+        tsv = feature_tsv_path(splits, root)
+        store_dir = "%s.store_%s_%s%s" % (tsv, dtype, backbone, "" if topk in (None, -1) else "_top%d" % topk)
+        if not os.path.exists(os.path.join(store_dir, "meta.json")):
+            if not os.path.exists(tsv):
+                raise FileNotFoundError(f"image features not found: neither {store_dir} nor {tsv} exists")
+            print("Converting %s -> %s" % (tsv, store_dir))
+            return convert_obj_tsv(tsv, store_dir, topk=None if topk in (None, -1) else topk, dtype=dtype, backbone=backbone)
+    store = FeatureStore(store_dir)
+    if store.meta["backbone"] != backbone:
+        raise ValueError(f"{store_dir} was converted for backbone {store.meta['backbone']!r}, not {backbone!r} (box format differs)")
+    return store
+
+
 class GQAOODEvaluator:
     def __init__(self, dataset, tau=0.5):
         # `dataset` is anything with .id2datum (GQADataset / LabelTable) or a plain {qid: label-dict}

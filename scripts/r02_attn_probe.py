@@ -1,5 +1,5 @@
 """Where does the fused projection + attention kernel spend its time?  gemm_debug bits: 1 no attention tasks, 2 no projection
-stores, 4 no context store (results are wrong while set).  python scripts/r02_attn_probe.py"""
+stores, 4 no context store, 8 only the first sample's tasks, 16 only the first query tile's tasks (results are wrong while set).  python scripts/r02_attn_probe.py"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -23,7 +23,7 @@ for name, S, masked in (("visual_S36", 36, False), ("language_S20", 20, True)):
     def fused(i):
         L.check(lib.rgqa_qkv_attention_fused(L.current_stream_ptr(), his[i].data_ptr(), 768, w_hm.data_ptr(), b_hm.data_ptr(),
                                              stats.data_ptr(), 1e-12, L.ptr(mask), ctx.data_ptr(), 768, B, S, 12), "fused")
-    for dbg in (0, 1, 2, 3, 4, 7):
+    for dbg in (0, 1, 7, 8, 16, 24):
         lib.rgqa_set_option(b"gemm_debug", dbg)
         print(f"{name} debug={dbg}: {timeit(fused):8.1f} us")
     lib.rgqa_set_option(b"gemm_debug", 0)
