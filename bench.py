@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="eval", choices=["eval", "train"],
                     help="eval = the headline (BASELINE.json configs[1]); train = the RP-finetune step (configs[4]), a side measurement")
+    ap.add_argument("--no-graph", action="store_true", help="--workload train: issue the ~1 000 launches of a step from Python")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the UNITER (configs[2]) side measurement")
     ap.add_argument("--ref-batch", type=int, default=32)
@@ -527,7 +528,7 @@ def run_train(a):
         dist.init_process_group("nccl", device_id=dev)
     B, Lq, A = 64, a.seq_len, 1842
     tr = LXMERTTrainer(syn.lxmert_state_dict(variant="init"), device=dev, lr=1e-5, warmup=0.1, t_total=10000,
-                       gemm="bf16" if a.precision == "bf16" else "fp32")
+                       gemm="bf16" if a.precision == "bf16" else "fp32", use_graph=not a.no_graph)
     rng = random.Random(1 + rank)
 
     def batch(step):
@@ -558,13 +559,15 @@ def run_train(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms / k, out
-    for i in range(max(a.warmup, 2)):
+    for i in range(max(a.warmup, 3)):     # eager, capture, first replay
         tr.train_step(*batches[i & 3])
     ms_step, out = timed(a.steps)
     blocking = None
     if world > 1:            # A/B: the single blocking all-reduce after the backward (round-1 behaviour)
         tr.bucketed = False
-        tr.train_step(*batches[0])
+        tr._graphs.clear()
+        for i in range(3):
+            tr.train_step(*batches[i & 3])
         blocking, _ = timed(a.steps)
         tr.bucketed = True
         chk = tr.flat_p.double().sum().reshape(1)
@@ -579,7 +582,7 @@ def run_train(a):
                 "config": {"workload": "LXMERT-base 9/5/5 RP-finetune step: 64 questions + 64 random-pairing negatives per rank, forward + BCE x A + "
                                        "backward + clip 5.0 + BertAdam, dropout off, gradients all-reduced in per-layer buckets overlapped with the backward",
                            "rows_per_step": world * 2 * B, "grad_buckets": tr.comm_stats["buckets"], "grad_bytes": tr.comm_stats["bytes"]},
-                "loss_last": out[-1][0], "grad_norm_last": out[-1][1]}
+                "loss_last": out[-1][0], "grad_norm_last": out[-1][1], "cuda_graph": bool(tr.use_graph)}
         if world > 1:
             line["ms_per_step_blocking_allreduce"] = blocking
             line["ranks_identical"] = identical

@@ -42,7 +42,7 @@ class _Ffn:
 class LXMERTTrainer:
     def __init__(self, state_dict, l_layers=9, x_layers=5, r_layers=5, heads=12, eps=1e-12, device="cuda:0", lr=5e-5, warmup=0.1,
                  t_total=-1, schedule="warmup_linear", b1=0.9, b2=0.999, e=1e-6, weight_decay=0.01, clip_norm=5.0, gemm="fp32",
-                 dropout=0.0, seed=9595, bucketed=True):
+                 dropout=0.0, seed=9595, bucketed=True, use_graph=False):
         """``gemm="bf16"``: the large matrix products (forward, dgrad and wgrad of every nn.Linear with K a multiple of 64)
         run on the tcgen05 tensor cores with bf16 operands cast on the fly and fp32 accumulation / outputs; master weights,
         activations, gradients and the optimiser stay fp32 (mixed precision; not the reference's arithmetic — parity with
@@ -51,6 +51,8 @@ class LXMERTTrainer:
         dev = torch.device(device)
         self.gemm = gemm
         self.bucketed = bucketed   # False: the single blocking all-reduce after the backward (A/B of the overlap)
+        self.use_graph = use_graph  # capture the gradient pass of each input shape into a CUDA graph (dropout off only)
+        self._graphs = {}
         # dropout > 0: the reference's training-mode dropout sites (embeddings, attention probabilities, the two output
         # projections of every block, the visual feature encoder) with this package's counter-based masks (not torch's)
         self.dropout, self.seed, self._site = dropout, seed, 0
@@ -356,8 +358,9 @@ class LXMERTTrainer:
             return hp["lr"] * SCHEDULES[hp["schedule"]](self.step_count / hp["t_total"], hp["warmup"])
         return hp["lr"]
 
-    def train_step(self, feat, pos, ids, seg, mask, target):
-        """Returns (loss, gradient norm before clipping) as Python floats."""
+    def _grad_pass(self, feat, pos, ids, seg, mask, target):
+        """zero grads, forward, loss, backward (+ the bucketed all-reduces): everything of a step that does not depend on the
+        step counter, i.e. what a CUDA graph can replay.  Returns the fp64 loss accumulator (device)."""
         lib = L.load()
         self.flat_g.zero_()
         logits, _ = self.forward(feat, pos, ids, seg, mask)
@@ -381,6 +384,42 @@ class LXMERTTrainer:
             buf = self.flat_g if dist.get_backend() == "nccl" else self.flat_g.cpu()
             dist.all_reduce(buf)                                        # ONE collective per step
             self.flat_g.copy_(buf.to(self.dev) / dist.get_world_size())
+        return loss
+
+    def _graphed_grad_pass(self, feat, pos, ids, seg, mask, target):
+        """The ~1 000 kernel launches of a gradient pass are issued from Python (~40 ms of host time against ~25 ms of GPU
+        work): capture them ONCE per input shape into a CUDA graph over static input buffers and replay.  Only with dropout
+        off (the mask seeds depend on the step counter).  The first call of a shape runs eagerly (lazy kernel attributes, NCCL
+        channel set-up must not happen under capture)."""
+        args = [feat, pos, ids, torch.zeros_like(ids) if seg is None else seg, mask, target]
+        key = tuple((tuple(t.shape), t.dtype) for t in args)
+        st = self._graphs.get(key)
+        if st is None:
+            self._graphs[key] = {"seen": 1}
+            return self._grad_pass(feat, pos, ids, seg, mask, target)
+        if "graph" not in st:
+            st["inputs"] = [torch.empty(t.shape, dtype=t.dtype, device=self.dev) for t in args]
+            for dst, src in zip(st["inputs"], args):
+                dst.copy_(src, non_blocking=True)
+            self._derived.clear()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["loss"] = self._grad_pass(*st["inputs"])
+            st["graph"] = g
+            self._derived.clear()          # tensors created under capture live in the graph's pool: never reuse them eagerly
+        for dst, src in zip(st["inputs"], args):
+            dst.copy_(src, non_blocking=True)
+        st["graph"].replay()
+        return st["loss"]
+
+    def train_step(self, feat, pos, ids, seg, mask, target):
+        """Returns (loss, gradient norm before clipping) as Python floats."""
+        lib = L.load()
+        if self.use_graph and self.dropout == 0:
+            loss = self._graphed_grad_pass(feat, pos, ids, seg, mask, target)
+        else:
+            loss = self._grad_pass(feat, pos, ids, seg, mask, target)
         sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
         stream = L.current_stream_ptr()
         L.check(lib.rgqa_grad_sumsq(stream, L.ptr(self.flat_g), self.flat_g.numel(), L.ptr(sumsq)), "rgqa_grad_sumsq")

@@ -250,3 +250,29 @@ def test_rp_finetune_loop_kernels_follow_the_reference_train_loop(cuda_device):
     # the six updates moved the parameters by far more than the tolerance (the comparison is not vacuous)
     init = torch.cat([sd[k].reshape(-1) for k in meta["param_order"]]).numpy()
     assert np.abs(z["params_after"][-1] - init).max() > 5e-3
+
+
+@pytest.mark.parametrize("gemm", ["fp32", "bf16"])
+def test_cuda_graph_replay_of_the_gradient_pass_matches_eager_steps(cuda_device, gemm):
+    """`use_graph=True` captures zero-grad + forward + loss + backward once per input shape and replays it (the ~1 000 launches of
+    a step otherwise come from Python); the optimiser and the schedule stay outside.  Five steps — eager, capture, three
+    replays — must leave the same losses, gradient norms and parameters as five eager steps (up to the run-to-run order of the
+    weight-gradient atomics)."""
+    from rgqa_b200.lxrt.trainer import LXMERTTrainer
+    layers = dict(l_layers=2, x_layers=1, r_layers=1)
+    sd = syn.lxmert_state_dict(variant="rich", **layers)
+    runs = []
+    for use_graph in (False, True):
+        tr = LXMERTTrainer(sd, device=cuda_device, lr=1e-4, warmup=0.1, t_total=20, gemm=gemm, use_graph=use_graph, **layers)
+        log = []
+        for step in range(5):
+            inp = syn.make_inputs(8, 20, seed=300 + step)
+            g = torch.Generator().manual_seed(step)
+            target = torch.zeros(8, 1842)
+            target[torch.arange(8), torch.randint(0, 1842, (8,), generator=g)] = 1.0
+            log.append(tr.train_step(inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"], target))
+        runs.append((log, tr.flat_p.clone()))
+    # the weight-gradient kernels accumulate with float atomics (order varies run to run, graph or not): equality to ~1e-9
+    for (l0, n0), (l1, n1) in zip(runs[0][0], runs[1][0]):
+        assert l1 == pytest.approx(l0, rel=1e-7) and n1 == pytest.approx(n0, rel=1e-6), (runs[0][0], runs[1][0])
+    torch.testing.assert_close(runs[1][1], runs[0][1], rtol=0, atol=2e-7)
