@@ -240,6 +240,9 @@ int rgqa_attention_bwd(void* stream, const float* q, int64_t ldq, const float* k
 int rgqa_attention_dropout(void* stream, const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                            const int32_t* key_mask, float* out, int64_t ldo, int B, int Lq, int Lk, int heads, float dropout_p,
                            uint64_t seed);
+/* y = x - noise * sign(grad), sign = +1 where grad >= 0 else -1: the input pre-processing step of ODIN and of the Mahalanobis
+ * scorer with --noise (src/tasks/gqa_odin.py:118-120, src/tasks/gqa_maha.py:246-252); n fp32 elements. */
+int rgqa_sign_step(void* stream, const float* x, const float* grad, float* y, int64_t n, float noise);
 int rgqa_dropout_add(void* stream, const float* x, const float* resid, float* y, int64_t n, float p, uint64_t seed);
 /* ---- weight-gradient kernels, fp32 path (the parameter half of loss.backward(), src/tasks/gqa_conf.py:196).  Every one of
  * them ADDS to its output; the caller zeroes the gradient buffers once per step.  Orchestration: rgqa_b200/lxrt/trainer.py. */

@@ -1782,6 +1782,10 @@ int rgqa_attention_dropout(void* stream, const float* q, int64_t ldq, const floa
   return attention(static_cast<cudaStream_t>(stream), DT_F32, q, ldq, k, ldk, v, ldv, key_mask, out, ldo, B, Lq, Lk, heads, dropout_p,
                    seed);
 }
+int rgqa_sign_step(void* stream, const float* x, const float* grad, float* y, int64_t n, float noise) {
+  RGQA_CHECK(x && grad && y, "rgqa_sign_step: null argument");
+  return sign_step(static_cast<cudaStream_t>(stream), x, grad, y, n, noise);
+}
 int rgqa_dropout_add(void* stream, const float* x, const float* resid, float* y, int64_t n, float p, uint64_t seed) {
   return dropout_add(static_cast<cudaStream_t>(stream), x, resid, y, n, p, seed);
 }

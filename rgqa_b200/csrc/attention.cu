@@ -403,6 +403,11 @@ attention_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   fence_proxy_async_smem();
   __syncthreads();
+  // launched with the programmatic-stream-serialization attribute (launch_pdl): everything above overlapped the producing
+  // GEMM's tail; Q / K / V and the key mask are read only below (the producer warp could otherwise TMA-load a
+  // projection the Q|K|V GEMM was still writing when option "pdl" is on)
+  pdl_launch_dependents();
+  pdl_wait();
 
   // contiguous range of units for this CTA: consecutive heads of consecutive samples (adjacent 128-byte columns of the
   // same token rows) are requested back to back

@@ -411,4 +411,31 @@ int embedding_scatter(cudaStream_t stream, const float* g, const int32_t* idx, f
   return 0;
 }
 
+// x - noise * sign(grad), sign = +1 where grad >= 0 else -1: the input pre-processing step of ODIN / Mahalanobis with --noise
+// (src/tasks/gqa_odin.py:118-120, gqa_maha.py:246-252), one pass over the [B, 36, 2048] features
+namespace {
+__global__ void __launch_bounds__(256) sign_step_kernel(const float* __restrict__ x, const float* __restrict__ grad, float* __restrict__ y,
+                                                        long long n4, long long n, float noise) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = reinterpret_cast<const float4*>(x)[i], g = reinterpret_cast<const float4*>(grad)[i];
+    reinterpret_cast<float4*>(y)[i] = make_float4(g.x >= 0.f ? a.x - noise : a.x + noise, g.y >= 0.f ? a.y - noise : a.y + noise,
+                                                  g.z >= 0.f ? a.z - noise : a.z + noise, g.w >= 0.f ? a.w - noise : a.w + noise);
+  }
+  for (long long i = 4 * n4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = grad[i] >= 0.f ? x[i] - noise : x[i] + noise;
+}
+}  // namespace
+int sign_step(cudaStream_t stream, const float* x, const float* grad, float* y, long long n, float noise) {
+  if (n <= 0) return 0;
+  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0;
+  const long long n4 = al ? n / 4 : 0;
+  long long blocks = ((n4 > 0 ? n4 : n) + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  sign_step_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, grad, y, n4, n, noise);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace rgqa

@@ -173,6 +173,8 @@ int attention_bwd(cudaStream_t stream, const float* q, long long ldq, const floa
                   long long ldv, const int32_t* key_mask, const float* dctx, long long ldo, float* dq, long long lddq, float* dk,
                   long long lddk, float* dv, long long lddv, int B, int Lq, int Lk, int heads, float drop_p = 0.f,
                   unsigned long long drop_seed = 0);
+// y = x - noise * sign(grad) (sign = +1 where grad >= 0): ODIN / Mahalanobis-with-noise input step (gqa_odin.py:118-120)
+int sign_step(cudaStream_t stream, const float* x, const float* grad, float* y, long long n, float noise);
 int dropout_add(cudaStream_t stream, const float* x, const float* resid, float* y, long long n, float p, unsigned long long seed);
 // weight-gradient kernels (backward.cu); all ACCUMULATE into their outputs
 int gemm_f32_tn(cudaStream_t stream, const float* A, long long lda, const float* B, long long ldb, float* out, long long ldo, int M,

@@ -15,7 +15,11 @@ from .. import ops
 
 def _step_against_gradient_sign(x, grad, noise):
     """x - noise * sign, sign = +1 where grad >= 0 else -1 (gqa_odin.py:118-120): one fused elementwise pass."""
-    return torch.where(grad >= 0, x - noise, x + noise)
+    x, grad = x.contiguous(), grad.contiguous()
+    y = torch.empty_like(x)
+    L.check(L.load().rgqa_sign_step(L.current_stream_ptr(), x.data_ptr(), grad.data_ptr(), y.data_ptr(), x.numel(), float(noise)),
+            "rgqa_sign_step")
+    return y
 
 
 def odin_scores(ig, feat, pos, ids, seg, mask, temperature=1.0, noise=1e-4):

@@ -178,3 +178,37 @@ def test_uniter_forward_attention_epilogue_bit_identical(cuda_device):
     finally:
         lib.rgqa_set_option(b"attn_fused", 1)
     assert torch.equal(p0, p1) and torch.equal(l0, l1)
+
+
+@pytest.mark.parametrize("attn_fused", [0, 1])
+def test_programmatic_dependent_launch_is_bit_identical(cuda_device, attn_fused):
+    """Option `pdl` launches the hot kernels with the programmatic-stream-serialization attribute: each kernel's prologue may
+    then overlap its predecessor's tail, and every such kernel must `griddepcontrol.wait` before its first global access.
+    ADVICE r01 found `attention_tma_kernel` launched that way without the wait (its producer warp could TMA-load a projection
+    still being written).  With the wait in place the whole forward — TMA attention (attn_fused = 0: all 34 blocks; = 1: the 10
+    cross blocks) — is bit-identical with and without PDL."""
+    sys.argv = ["x"]
+    from rgqa_b200 import _lib as L
+    from rgqa_b200.engine import Engine, EngineConfig
+    lib = L.load()
+    cfg = EngineConfig(precision="bf16", l_layers=2, x_layers=2, r_layers=2)
+    eng = Engine(cfg)
+    eng.load_weights(syn.lxmert_state_dict(variant="rich", l_layers=2, x_layers=2, r_layers=2).items())
+    B = 260   # 260 x 12 units: above the TMA attention kernel's threshold
+    inp = syn.make_inputs(B, 20, seed=77)
+    t = [inp["feat"].to(cuda_device), inp["pos"].to(cuda_device)] + [inp[k].to(torch.int32).to(cuda_device) for k in ("ids", "seg", "mask")]
+    out = []
+    try:
+        lib.rgqa_set_option(b"graphs", 0)
+        lib.rgqa_set_option(b"attn_fused", attn_fused)
+        for pdl in (0, 1, 1):
+            lib.rgqa_set_option(b"pdl", pdl)
+            out.append(eng.forward(*t))
+            torch.cuda.synchronize()
+    finally:
+        lib.rgqa_set_option(b"pdl", 0)
+        lib.rgqa_set_option(b"graphs", 1)
+        lib.rgqa_set_option(b"attn_fused", 1)
+    eng.close()
+    for pooled, logits in out[1:]:
+        assert torch.equal(pooled, out[0][0]) and torch.equal(logits, out[0][1])

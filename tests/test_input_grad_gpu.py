@@ -156,3 +156,16 @@ def test_odin_and_mahalanobis_with_noise_against_the_reference_stack(cuda_device
         err = np.abs(s - want).max()
         shift = np.abs(want - base).max()
         assert err <= tol and shift >= 4 * err, (name, err, shift)
+
+
+def test_sign_step_kernel(cuda_device):
+    """x - noise * sign(grad) with sign(0) = +1 (gqa_odin.py:118-120: `gradient = torch.ge(grad, 0); gradient = (gradient.float() - 0.5) * 2`)."""
+    from rgqa_b200.tasks.gqa_odin import _step_against_gradient_sign
+    g = torch.Generator().manual_seed(3)
+    for n in (7, 4096, 36 * 2048 * 3 + 5):
+        x = torch.randn(n, generator=g).to(cuda_device)
+        grad = torch.randn(n, generator=g).to(cuda_device)
+        grad[::5] = 0.0
+        y = _step_against_gradient_sign(x, grad, 1e-3)
+        ref = x - 1e-3 * ((grad >= 0).float() - 0.5) * 2
+        torch.testing.assert_close(y, ref, rtol=0, atol=1e-7)
