@@ -240,6 +240,9 @@ int rgqa_attention_bwd(void* stream, const float* q, int64_t ldq, const float* k
 int rgqa_attention_dropout(void* stream, const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                            const int32_t* key_mask, float* out, int64_t ldo, int B, int Lq, int Lk, int heads, float dropout_p,
                            uint64_t seed);
+/* out bf16 [C, R] = transpose(in fp32 [R, C], row stride ld): operand re-layout + cast of the weight-gradient products
+ * (dy^T x of src/tasks/gqa_conf.py:196's backward runs over the rows), one pass. */
+int rgqa_transpose_cast_bf16(void* stream, const float* in, int64_t ld, void* out, int R, int C);
 /* y = x - noise * sign(grad), sign = +1 where grad >= 0 else -1: the input pre-processing step of ODIN and of the Mahalanobis
  * scorer with --noise (src/tasks/gqa_odin.py:118-120, src/tasks/gqa_maha.py:246-252); n fp32 elements. */
 int rgqa_sign_step(void* stream, const float* x, const float* grad, float* y, int64_t n, float noise);

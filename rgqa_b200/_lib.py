@@ -77,6 +77,7 @@ SIGNATURES = {
     "rgqa_tanh_bwd": (_i, [_vp, _vp, _vp, _vp, _i64]),
     "rgqa_attention_bwd": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _f, C.c_uint64]),
     "rgqa_attention_dropout": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _f, C.c_uint64]),
+    "rgqa_transpose_cast_bf16": (_i, [_vp, _vp, _i64, _vp, _i, _i]),
     "rgqa_sign_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f]),
     "rgqa_dropout_add": (_i, [_vp, _vp, _vp, _vp, _i64, _f, C.c_uint64]),
     "rgqa_gemm_f32_tn": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i]),

@@ -1782,6 +1782,10 @@ int rgqa_attention_dropout(void* stream, const float* q, int64_t ldq, const floa
   return attention(static_cast<cudaStream_t>(stream), DT_F32, q, ldq, k, ldk, v, ldv, key_mask, out, ldo, B, Lq, Lk, heads, dropout_p,
                    seed);
 }
+int rgqa_transpose_cast_bf16(void* stream, const float* in, int64_t ld, void* out, int R, int C) {
+  RGQA_CHECK(in && out, "rgqa_transpose_cast_bf16: null argument");
+  return transpose_cast_bf16(static_cast<cudaStream_t>(stream), in, ld, out, R, C);
+}
 int rgqa_sign_step(void* stream, const float* x, const float* grad, float* y, int64_t n, float noise) {
   RGQA_CHECK(x && grad && y, "rgqa_sign_step: null argument");
   return sign_step(static_cast<cudaStream_t>(stream), x, grad, y, n, noise);

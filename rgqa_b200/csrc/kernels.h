@@ -150,6 +150,8 @@ int cast_f32_to_bf16(cudaStream_t stream, const float* in, void* out, long long 
 // fp32 [M, K] -> bf16 [M, 3K] split operand (hi | hi | lo, or hi | lo | hi on the weight side): one bf16 GEMM over 3K then
 // evaluates the product to ~16 mantissa bits per operand (the tensor-core Mahalanobis)
 int split_bf16x3(cudaStream_t stream, const float* in, long long ld, void* out, long long M, int K, int weight_side);
+// fp32 [R, C] (row stride ld) -> bf16 [C, R] in one pass (operands of the weight-gradient GEMMs)
+int transpose_cast_bf16(cudaStream_t stream, const float* in, long long ld, void* out, int R, int C);
 int cast_bf16_to_f32(cudaStream_t stream, const void* in, float* out, long long n);
 // copy rows: dst[r, :] = src[r*src_stride_rows .. ] for r < rows (strided gather of whole rows)
 int gather_rows(cudaStream_t stream, int dtype, const void* src, long long src_ld, void* dst, long long dst_ld,

@@ -89,12 +89,13 @@ __device__ __forceinline__ float row_rstd(const float* __restrict__ stats, int r
   return 1.0f / sqrtf(var + eps);
 }
 
-// KS = ceil(S / 16): 16-key steps of P·V (and NT = 2 KS 8-key score tiles)
-template <int KS>
+// KS = ceil(S / 16): 16-key steps of P·V; NT = ceil(S / 8) <= 2 KS: 8-key score tiles of QKᵀ (a tile wholly beyond the last
+// key has probability exactly 0 everywhere — it is not computed at all: S = 36 runs 5 score tiles, S = 20 three)
+template <int KS, int NT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmO, const QkvAttnParams p) {
-  constexpr int NT = 2 * KS;
+  static_assert(NT == 2 * KS || NT == 2 * KS - 1, "NT = ceil(S / 8), KS = ceil(S / 16)");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -322,6 +323,7 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         float sum0 = 0.f, sum1 = 0.f;
         uint32_t pa[KS][4];
+        if (NT < 2 * KS) pa[KS - 1][2] = pa[KS - 1][3] = 0u;   // the score tile that was not computed: probability 0
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           const float p0 = ex2_fast(s[j][0] - mx0), p1 = ex2_fast(s[j][1] - mx0);
@@ -382,9 +384,9 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 2) tmem_dealloc_pair<512>(tmem_base);
 }
 
-template <int KS>
+template <int KS, int NT>
 int launch_qkv_attn(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const QkvAttnParams& p) {
-  auto kern = qkv_attn_pair_kernel<KS>;
+  auto kern = qkv_attn_pair_kernel<KS, NT>;
   static bool configured = false;
   if (!configured) {
     RGQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -428,11 +430,15 @@ int qkv_attention_fused(cudaStream_t stream, const void* A, long long lda, const
   if (make_tmap_ex(&tmO, ctx, M, static_cast<long long>(heads) * HD, ldo, p.ns * S, HD, 2, 128)) return 1;
   void* tok = prof_begin(stream);
   int rc;
-  switch ((S + 15) / 16) {
-    case 1: rc = launch_qkv_attn<1>(stream, tmA, tmB, tmO, p); break;
-    case 2: rc = launch_qkv_attn<2>(stream, tmA, tmB, tmO, p); break;
-    case 3: rc = launch_qkv_attn<3>(stream, tmA, tmB, tmO, p); break;
-    default: rc = launch_qkv_attn<4>(stream, tmA, tmB, tmO, p); break;
+  switch ((S + 7) / 8) {
+    case 1: rc = launch_qkv_attn<1, 1>(stream, tmA, tmB, tmO, p); break;
+    case 2: rc = launch_qkv_attn<1, 2>(stream, tmA, tmB, tmO, p); break;
+    case 3: rc = launch_qkv_attn<2, 3>(stream, tmA, tmB, tmO, p); break;
+    case 4: rc = launch_qkv_attn<2, 4>(stream, tmA, tmB, tmO, p); break;
+    case 5: rc = launch_qkv_attn<3, 5>(stream, tmA, tmB, tmO, p); break;
+    case 6: rc = launch_qkv_attn<3, 6>(stream, tmA, tmB, tmO, p); break;
+    case 7: rc = launch_qkv_attn<4, 7>(stream, tmA, tmB, tmO, p); break;
+    default: rc = launch_qkv_attn<4, 8>(stream, tmA, tmB, tmO, p); break;
   }
   if (rc) return 1;
   // the projection's FLOPs (2 M N K over the whole-sample rows) + the attention's (4 S S 64 per head)

@@ -357,6 +357,36 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restri
   }
 }
 
+// fp32 [R, C] (row stride ld) -> bf16 [C, R]: the operand re-layout of a weight-gradient product (G = dy^T x runs over the
+// ROWS of dy and x, the tensor-core GEMM wants that dimension contiguous) in one pass — 6 bytes per element instead of the
+// 14 of a transposing copy followed by a cast.  64 x 32 tiles through padded shared memory: 128-byte reads along C, 128-byte
+// bf16x2 writes along R.
+__global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ in, long long ld, __nv_bfloat16* __restrict__ out,
+                                                             int R, int C) {
+  __shared__ float tile[32][65];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    tile[tx][ty + 8 * i] = (r < R && c < C) ? in[static_cast<long long>(r) * ld + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + 2 * tx;
+    if (c < C && r < R) {
+      __nv_bfloat16* o = out + static_cast<long long>(c) * R + r;
+      if (r + 1 < R && (R & 1) == 0)
+        *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(tile[ty + 8 * i][2 * tx], tile[ty + 8 * i][2 * tx + 1]);
+      else {
+        o[0] = __float2bfloat16_rn(tile[ty + 8 * i][2 * tx]);
+        if (r + 1 < R) o[1] = __float2bfloat16_rn(tile[ty + 8 * i][2 * tx + 1]);
+      }
+    }
+  }
+}
+
 inline int row_grid(int rows) { return (rows + kWarpsPerBlock - 1) / kWarpsPerBlock; }
 
 }  // namespace
@@ -474,6 +504,15 @@ int split_bf16x3(cudaStream_t stream, const float* in, long long ld, void* out, 
   long long blocks = (M * (K / 4) + 255) / 256;
   if (blocks > 148LL * 8) blocks = 148LL * 8;
   split_bf16x3_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(in, ld, static_cast<__nv_bfloat16*>(out), M, K, weight_side);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int transpose_cast_bf16(cudaStream_t stream, const float* in, long long ld, void* out, int R, int C) {
+  RGQA_CHECK(R > 0 && C > 0 && ld >= C, "transpose_cast_bf16: bad shape R=%d C=%d ld=%lld", R, C, ld);
+  RGQA_CHECK(reinterpret_cast<uintptr_t>(out) % 4 == 0, "transpose_cast_bf16: unaligned output");
+  transpose_cast_kernel<<<dim3((C + 31) / 32, (R + 63) / 64), 256, 0, stream>>>(in, ld, static_cast<__nv_bfloat16*>(out), R, C);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;

@@ -152,8 +152,8 @@ class LXMERTTrainer:
         gw, gb = self.g[wname + ".weight"], self.g[wname + ".bias"]
         M = dy.shape[0]
         if self.gemm == "bf16" and M % 64 == 0 and M >= 64 and x.shape[1] >= 64 and dy.shape[1] >= 64:
-            a = ops.cast_bf16(dy.t().contiguous())          # [N, M]: the product runs over the rows
-            bt = ops.cast_bf16(x.t().contiguous())          # [K, M]
+            a = ops.transpose_cast_bf16(dy)                  # [N, M]: the product runs over the rows
+            bt = ops.transpose_cast_bf16(x)                  # [K, M]   (transposing copy + cast in one pass)
             ops.linear_bf16(a, bt, None, epilogue=L.EPI_RESID, residual=gw, out_dtype=torch.float32, out=gw)
             ops.linear_wgrad_bias_(gb, dy)
         else:
@@ -252,8 +252,16 @@ class LXMERTTrainer:
         self._wgrad(name, dy, x)
 
     def _dgrad(self, dy, name, wt, residual=None):
-        """dy · W (+ residual): W given as its transposed fp32 copy wt [K, N]."""
-        return self._mm(dy, wt, None, epilogue=L.EPI_RESID if residual is not None else L.EPI_BIAS, residual=residual, wkey=("t", name))
+        """dy · W (+ residual): W given as its transposed fp32 copy wt [K, N] (a callable builds it only if the fp32 path needs it)."""
+        epi = L.EPI_RESID if residual is not None else L.EPI_BIAS
+        w = self.p.get(name + ".weight")                  # [N, K]; absent for the stacked Q|K|V pseudo-names
+        if self.gemm == "bf16" and w is not None and w.shape[0] % 64 == 0 and dy.shape[0] >= 64:
+            key = ("b16", ("t", name))
+            if key not in self._derived:                  # bf16 W^T straight from the fp32 master weight: one pass, no fp32 transposed copy
+                self._derived[key] = ops.transpose_cast_bf16(w)
+            return ops.linear_bf16(ops.cast_bf16(dy.contiguous()), self._derived[key], None, epilogue=epi, residual=residual,
+                                   out_dtype=torch.float32)
+        return self._mm(dy, wt() if callable(wt) else wt, None, epilogue=epi, residual=residual, wkey=("t", name))
 
     def _ln_bwd(self, name, dy, x, scale=1.0):
         ops.layernorm_param_grad_(self.g[name + ".weight"], self.g[name + ".bias"], dy, x, self.eps, scale)
@@ -263,15 +271,15 @@ class LXMERTTrainer:
         d_pre = self._ln_bwd(f.ln, dy, tp["pre"])
         d_h = ops.dropout_add(d_pre, None, self.dropout, tp["s_out"]) if tp["s_out"] else d_pre    # through the output dropout
         self._lin_wgrad(f.out, d_h, tp["inter"])
-        d_pg = ops.gelu_bwd(self._dgrad(d_h, f.out, self._wt(f.out)), tp["pg"])
+        d_pg = ops.gelu_bwd(self._dgrad(d_h, f.out, lambda: self._wt(f.out)), tp["pg"])
         self._lin_wgrad(f.inter, d_pg, tp["x"])
-        return self._dgrad(d_pg, f.inter, self._wt(f.inter), residual=d_pre)
+        return self._dgrad(d_pg, f.inter, lambda: self._wt(f.inter), residual=d_pre)
 
     def _att_bwd(self, a, tp, dy, dqkv_q, dqkv_kv):
         d_pre = self._ln_bwd(a.ln, dy, tp["pre"])
         d_h = ops.dropout_add(d_pre, None, self.dropout, tp["s_out"]) if tp["s_out"] else d_pre
         self._lin_wgrad(a.out, d_h, tp["ctx"])
-        d_ctx = self._dgrad(d_h, a.out, self._wt(a.out))
+        d_ctx = self._dgrad(d_h, a.out, lambda: self._wt(a.out))
         ops.attention_bwd(tp["qkv_q"], tp["qkv_kv"], d_ctx, dqkv_q, dqkv_kv, tp["B"], tp["Lq"], tp["Lk"], key_mask=tp["mask"], heads=self.heads,
                           p=self.dropout if tp["s_att"] else 0.0, seed=tp["s_att"])
         return d_pre

@@ -201,6 +201,16 @@ def cast_bf16(x):
     return out
 
 
+def transpose_cast_bf16(x):
+    """bf16 [C, R] = x.t() for fp32 x [R, C] (any row stride): transposing copy + cast in one kernel."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    R, C = x.shape
+    out = torch.empty((C, R), dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().rgqa_transpose_cast_bf16(L.current_stream_ptr(), L.ptr(x), x.stride(0), L.ptr(out), R, C), "rgqa_transpose_cast_bf16")
+    return out
+
+
 def estimator_accumulate(x, target, G, class_sum, class_count):
     """One batch of the Mahalanobis estimator's data pass (src/tasks/gqa_maha.py:138-168) into fp64 device accumulators:
     x [B, D] f32, target [B, >= C] f32 multi-hot, G [D, D], class_sum [C, D], class_count [C] (all float64, zeroed by the
