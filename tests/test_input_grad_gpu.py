@@ -165,7 +165,10 @@ def test_sign_step_kernel(cuda_device):
     for n in (7, 4096, 36 * 2048 * 3 + 5):
         x = torch.randn(n, generator=g).to(cuda_device)
         grad = torch.randn(n, generator=g).to(cuda_device)
-        grad[::5] = 0.0
-        y = _step_against_gradient_sign(x, grad, 1e-3)
-        ref = x - 1e-3 * ((grad >= 0).float() - 0.5) * 2
-        torch.testing.assert_close(y, ref, rtol=0, atol=1e-7)
+        grad[::5] = 0.0                                    # ge(0, 0) is True: a zero gradient steps DOWN
+        grad[1::10] = -0.0
+        for noise in (1e-3, 1e-4, 0.0):
+            y = _step_against_gradient_sign(x, grad, noise)
+            gradient = (torch.ge(grad, 0).float() - 0.5) * 2   # the reference's two statements, literally
+            want = torch.add(x, gradient, alpha=-noise)
+            torch.testing.assert_close(y, want, rtol=0, atol=1e-7)

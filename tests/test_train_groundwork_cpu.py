@@ -52,19 +52,6 @@ def test_rp_batch_matches_reference_lines():
         build_rp_batch(["a", "b"], feats[:2], boxes[:2], sent[:2], target[:2], lambda q: "same")
 
 
-def test_gradient_sign_step_equals_reference_expression():
-    """gqa_odin.py:118-120 / gqa_maha.py:247-253: gradient = (ge(grad, 0).float() - 0.5) * 2; xPt = add(x, gradient, alpha=-noise)."""
-    from rgqa_b200.tasks.gqa_odin import _step_against_gradient_sign
-    g = torch.Generator().manual_seed(2)
-    x, grad = torch.rand(5, 36, 64, generator=g), torch.randn(5, 36, 64, generator=g)
-    grad[0, 0, :8] = 0.0                                   # ge(0, 0) is True: a zero gradient steps DOWN
-    grad[0, 1, :4] = -0.0
-    for noise in (1e-4, 1e-3, 0.0):
-        gradient = (torch.ge(grad, 0).float() - 0.5) * 2
-        want = torch.add(x, gradient, alpha=-noise)
-        assert torch.equal(_step_against_gradient_sign(x, grad, noise), want)
-
-
 def _rp_golden():
     import json
     gold = os.path.join(os.path.dirname(__file__), "golden")
