@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RGQA_ABI_VERSION 2
+#define RGQA_ABI_VERSION 3
 
 /* architectures */
 #define RGQA_ARCH_LXMERT 0
@@ -48,6 +48,7 @@ extern "C" {
 /* element types of borrowed buffers */
 #define RGQA_DT_F32 0
 #define RGQA_DT_BF16 1
+#define RGQA_DT_F16 2 /* the single-word deferred-LayerNorm state: operands of the *_a16 GEMMs, output of rgqa_gemm_bf16_resid_h16 */
 /* GEMM epilogues */
 #define RGQA_EPI_BIAS 0
 #define RGQA_EPI_GELU 1
@@ -166,7 +167,8 @@ int rgqa_gemm_bf16(void* stream, const void* A, int64_t lda, const void* W, int6
 int rgqa_qkv_attention_fused(void* stream, const void* A, int64_t lda, const void* W_hm, const float* bias_hm, const float* ln_stats,
                              float ln_eps, const int32_t* key_mask, void* ctx, int64_t ldo, int B, int S, int heads);
 /* VisualFeatEncoder.forward (src/lxrt/modeling.py:507-517) as ONE tcgen05 kernel: (LN(feat·W1ᵀ + b1) + LN(box·W2ᵀ + b2)) / 2
- * as a bf16 hi/lo pair [M, 768] (hi + lo = the fp32 value to 2^-17) and identity row statistics [M, 12].  feat [M, K] and
+ * as a bf16 hi/lo pair [M, 768] (hi + lo = the fp32 value to 2^-17; out_lo == NULL: out_hi is written as ONE fp16 word per
+ * element, the single-word state) and identity row statistics [M, 12].  feat [M, K] and
  * W1 [768, K] are both fp32 (feat_dtype F32: kind::tf32 MMAs read them as they are) or both bf16; box [M, box_dim] f32. */
 int rgqa_visn_embed(void* stream, const void* feat, int feat_dtype, const void* W1, const float* b1, const float* g1,
                     const float* be1, const float* boxes, int box_dim, const float* W2, const float* b2, const float* g2,
@@ -202,6 +204,28 @@ int rgqa_gemm_bf16_resid_hl(void* stream, const void* A, int64_t lda, const void
                             const void* in_hi, const void* in_lo, const float* in_stats, const float* in_gamma,
                             const float* in_beta, float eps, void* out_hi, void* out_lo, float* out_stats, int M, int N,
                             int K);
+/* Single-word form of the deferred-LayerNorm state (option "state_f16", read by rgqa_finalize_weights; the default of the bf16
+ * forward): the pre-LayerNorm hidden rows are ONE fp16 word per element (11 significand bits, saturating at +-65504) + the same
+ * row statistics.  The consumer GEMMs read them as an fp16 A operand against an fp16 copy of their folded weight (tcgen05
+ * kind::f16 wants both operands in the same format: fp16 x bf16 is an illegal instruction on B200); every other GEMM operand of
+ * the forward (context rows, GELU intermediates, their weights) stays bf16.  A producer moves 4 608 instead of 7 680 B of HBM
+ * traffic per row at K = 768.
+ *  - rgqa_fold_ln_weight_f16: rgqa_fold_ln_weight with W' rounded to fp16 (same centring and error feedback).
+ *  - rgqa_gemm_bf16_folded_a16: rgqa_gemm_bf16_folded with A and W fp16 (ln_stats may be NULL: plain epilogue(A·Wᵀ + bias)).
+ *  - rgqa_qkv_attention_fused_a16: rgqa_qkv_attention_fused with A and W_hm fp16 (Q, K, V and the context stay bf16).
+ *  - rgqa_gemm_bf16_resid_h16: v = A·Wᵀ + bias + LayerNorm_prev(in_h) (A, W bf16; in_h fp16); writes out_h = fp16(v) and
+ *    out_stats = the partial (sum, sumsq) of the ROUNDED row.  N = 768.  src/lxrt/modeling.py:357-361, :411-415. */
+int rgqa_fold_ln_weight_f16(void* stream, const float* W, const float* bias, const float* gamma, const float* beta, int N,
+                            int K, void* W_out_f16, float* c_out, float* bias_out);
+int rgqa_gemm_bf16_folded_a16(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* out,
+                              int64_t ldo, int out_dtype, int M, int N, int K, int epilogue, const float* ln_stats,
+                              const float* ln_c, float eps);
+int rgqa_qkv_attention_fused_a16(void* stream, const void* A, int64_t lda, const void* W_hm, const float* bias_hm,
+                                 const float* ln_stats, float ln_eps, const int32_t* key_mask, void* ctx, int64_t ldo, int B, int S,
+                                 int heads);
+int rgqa_gemm_bf16_resid_h16(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                             const void* in_h, const float* in_stats, const float* in_gamma, const float* in_beta, float eps,
+                             void* out_h, float* out_stats, int M, int N, int K);
 int rgqa_gemm_f32(void* stream, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                   const float* resid, int64_t ldr, float* out, int64_t ldo, int M, int N, int K, int epilogue);
 int rgqa_attention(void* stream, int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,

@@ -10,13 +10,13 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-ABI_VERSION = 2  # include/rgqa_b200.h: RGQA_ABI_VERSION
+ABI_VERSION = 3  # include/rgqa_b200.h: RGQA_ABI_VERSION
 LIB_PATH = _PKG / "_C" / "librgqa_b200.so"
 
 # constants mirrored from include/rgqa_b200.h
 ARCH_LXMERT, ARCH_UNITER = 0, 1
 PREC_FP32, PREC_BF16 = 0, 1
-DT_F32, DT_BF16 = 0, 1
+DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 EPI_BIAS, EPI_GELU, EPI_TANH, EPI_RESID = 0, 1, 2, 3
 SCORE_MSP, SCORE_ENERGY_TOP2, SCORE_ENERGY_SUM, SCORE_LSE, SCORE_MAHA = 0, 1, 2, 3, 4
 SCORE_MODES = {"msp": SCORE_MSP, "energy": SCORE_ENERGY_TOP2, "energy_top2": SCORE_ENERGY_TOP2,
@@ -65,6 +65,10 @@ SIGNATURES = {
     "rgqa_fold_ln_weight": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "rgqa_gemm_bf16_folded": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _f]),
     "rgqa_gemm_bf16_resid_hl": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i]),
+    "rgqa_fold_ln_weight_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "rgqa_gemm_bf16_folded_a16": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _f]),
+    "rgqa_qkv_attention_fused_a16": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _f, _vp, _vp, _i64, _i, _i, _i]),
+    "rgqa_gemm_bf16_resid_h16": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i]),
     "rgqa_gemm_f32": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i]),
     "rgqa_attention": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i]),
     "rgqa_embed_ln": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f]),
@@ -120,6 +124,11 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     if got != ABI_VERSION:
         raise RuntimeError(f"rgqa_b200: {LIB_PATH} has ABI version {got}, the Python binding expects {ABI_VERSION}; "
                            "rebuild with `python -m rgqa_b200.build --force`")
+    # RGQA_OPTS=name=value,... : kernel-selection switches for A/B measurements (rgqa_set_option), applied once at load
+    for kv in filter(None, os.environ.get("RGQA_OPTS", "").split(",")):
+        k, _, v = kv.partition("=")
+        if lib.rgqa_set_option(k.strip().encode(), int(v)) != 0:
+            raise RuntimeError(f"rgqa_b200: RGQA_OPTS: {lib.rgqa_last_error().decode('utf-8', 'replace')}")
     _lib = lib
     return lib
 

@@ -77,7 +77,7 @@ struct LNp {
 };
 // A consumer weight with the LayerNorm of its input folded in (deferred LayerNorm): W' = bf16(W∘gamma -
 // rowmean), b' = b + W·beta.  W == nullptr when the input is not behind a LayerNorm (first layer) or in fp32 mode.
-struct Folded {
+struct Folded {  // state_f16 handles: W is fp16, and a consumer WITHOUT a predecessor LayerNorm gets a plain fp16 copy here too
   void* W = nullptr;
   float* b = nullptr;
   float* c = nullptr;  // row sums of W' (the centring's rounding residue); non-null only when too large to drop (fold_stack)
@@ -122,6 +122,8 @@ struct rgqa_handle {
   std::map<std::string, RawTensor> raw;     // uploaded fp32 tensors
   std::vector<void*> owned;                 // packed allocations
   bool finalized = false;
+  bool state_f16 = false;  // set by rgqa_finalize_weights (option "state_f16"): the deferred forward keeps its state as one fp16 word per
+                           // element and every consumer weight (folded, or plain in front of the first layer) is an fp16 copy
 
   // embeddings (fp32)
   float *word = nullptr, *posemb = nullptr, *typeemb = nullptr;
@@ -434,7 +436,7 @@ int fold_stack(rgqa_handle* h, const std::vector<std::string>& names, int rows, 
     float *w, *bias;
     if (get_raw(h, names[i] + ".weight", rows, K, &w) || get_raw(h, names[i] + ".bias", rows, 0, &bias)) return 1;
     if (fold_ln_weight(nullptr, w, bias, ln.g, ln.b, rows, K, static_cast<char*>(W) + i * rows * static_cast<size_t>(K) * 2,
-                       c + i * rows, b + i * rows))
+                       c + i * rows, b + i * rows, h->state_f16 ? 1 : 0))
       return 1;
   }
   out->W = W;
@@ -446,7 +448,9 @@ int fold_stack(rgqa_handle* h, const std::vector<std::string>& names, int rows, 
     std::vector<float> hc(n * rows);
     RGQA_CUDA_OK(cudaMemcpy(hc.data(), c, hc.size() * sizeof(float), cudaMemcpyDeviceToHost));
     float mx = 0.f;
-    for (float v : hc) mx = std::fabs(v) > mx ? std::fabs(v) : mx;
+    for (float v : hc) mx = (std::fabs(v) > mx || !std::isfinite(v)) ? std::fabs(v) : mx;
+    RGQA_CHECK(std::isfinite(mx), "deferred LayerNorm: a folded weight of '%s' leaves the fp16 range; load with rgqa_set_option(\"state_f16\", 0)",
+               names[0].c_str());
     if (mx > h->max_fold_residue) h->max_fold_residue = mx;
     constexpr float kLnMeanBound = 8.0f;
     out->c = (mx * kLnMeanBound > 1e-3f) ? c : nullptr;
@@ -468,9 +472,33 @@ int add_vecs(rgqa_handle* h, const float* a, const float* b, int n, float** out)
   *out = d;
   return 0;
 }
+// state_f16 handles: a consumer that sits directly behind the embeddings (identity state, no LayerNorm to fold) still needs its
+// weight in the state's format — a plain fp16 copy of the stacked rows, bias unchanged
+int plain_f16_stack(rgqa_handle* h, const std::vector<std::string>& names, int rows, int K, Folded* out) {
+  const size_t n = names.size();
+  void* W = nullptr;
+  float* b = nullptr;
+  RGQA_CUDA_OK(cudaMalloc(&W, n * rows * static_cast<size_t>(K) * 2));
+  h->owned.push_back(W);
+  RGQA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b), n * rows * sizeof(float)));
+  h->owned.push_back(b);
+  for (size_t i = 0; i < n; ++i) {
+    float *w, *bias;
+    if (get_raw(h, names[i] + ".weight", rows, K, &w) || get_raw(h, names[i] + ".bias", rows, 0, &bias)) return 1;
+    if (cast_f32_to_f16(nullptr, w, static_cast<char*>(W) + i * rows * static_cast<size_t>(K) * 2, static_cast<long long>(rows) * K)) return 1;
+    RGQA_CUDA_OK(cudaMemcpyAsync(b + i * rows, bias, rows * sizeof(float), cudaMemcpyDeviceToDevice, nullptr));
+  }
+  out->W = W;
+  out->b = b;
+  out->c = nullptr;
+  return 0;
+}
 int fold_qkv(rgqa_handle* h, const std::string& p, const char* self_name, const LNp* pred, Folded* out) {
-  if (pred == nullptr) return 0;
   const std::string s = p + "." + self_name;
+  if (pred == nullptr) {
+    if (!h->state_f16) return 0;
+    return plain_f16_stack(h, {s + ".query", s + ".key", s + ".value"}, h->cfg.hidden, h->cfg.hidden, out);
+  }
   return fold_stack(h, {s + ".query", s + ".key", s + ".value"}, h->cfg.hidden, h->cfg.hidden, *pred, out);
 }
 // [q rows | k rows | v rows] -> [head][q | k | v][64 rows]: one 192-row tile of the fused projection + attention kernel is
@@ -655,7 +683,8 @@ int maha_core(cudaStream_t st, const float* x, const float* mu, const float* Psy
 // pooler + answer head (+ fused scorers) on the hidden rows `hid` (first token of each sample, row stride S*H)
 // `stats` != nullptr: `hid` is a deferred-LayerNorm state (un-normalised bf16 rows + statistics) and the pooler uses its
 // folded weight.
-int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, const FwdOut& o, const float* stats = nullptr) {
+int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, const FwdOut& o, const float* stats = nullptr,
+               int hid_f16 = 0 /* the rows are the fp16 single-word state */) {
   const int H = h->cfg.hidden, A = h->cfg.num_answers;
   const size_t es = act_size(h);
   const int dt = act_dtype(h);
@@ -675,7 +704,12 @@ int head_block(rgqa_handle* h, cudaStream_t st, const void* hid, int B, int S, c
   float* pdst = o.pooled != nullptr ? o.pooled : pooled;
   if (stats != nullptr) {
     if (gemm_bf16_folded(st, hid, static_cast<long long>(S) * H, h->pooler_f.W, H, h->pooler_f.b, nullptr, 0, pdst, H, 1, B, H,
-                         H, EPI_TANH, stats, h->pooler_f.c, h->cfg.ln_eps, static_cast<long long>(S) * 12))
+                         H, EPI_TANH, stats, h->pooler_f.c, h->cfg.ln_eps, static_cast<long long>(S) * 12, hid_f16))
+      return 1;
+  } else if (hid_f16) {  // identity state straight into the pooler (a model without encoder layers)
+    RGQA_CHECK(h->pooler_f.W != nullptr, "forward: fp16 copy of the pooler weight missing");
+    if (gemm_bf16_folded(st, hid, static_cast<long long>(S) * H, h->pooler_f.W, H, h->pooler_f.b, nullptr, 0, pdst, H, 1, B, H, H, EPI_TANH,
+                         nullptr, nullptr, 0.f, 12, 1))
       return 1;
   } else if (gemm(h, st, hid, static_cast<long long>(S) * H, h->pooler, nullptr, 0, pdst, H, 1, B, EPI_TANH)) {
     return 1;
@@ -884,6 +918,7 @@ int rgqa_finalize_weights(rgqa_handle* h) {
       // deferred LayerNorm: every consumer of a hidden state gets a copy of its weight folded with the LayerNorm that
       // (notionally) produced that state; the embeddings' outputs are not behind one (nullptr)
       if (make_identity_ln(h)) return 1;
+      h->state_f16 = option_get(OPT_STATE_F16) != 0 && H == 768;
       const LNp *pl = nullptr, *pv = nullptr;
       for (int i = 0; i < c.l_layers; ++i) {
         if (fold_bert_layer(h, b + "encoder.layer." + std::to_string(i), &h->l_layers[i], pl)) return 1;
@@ -913,6 +948,7 @@ int rgqa_finalize_weights(rgqa_handle* h) {
         pv = &w.visn_ffn.ln;
       }
       if (pl != nullptr && fold_stack(h, {b + "pooler.dense"}, H, H, *pl, &h->pooler_f)) return 1;
+      if (pl == nullptr && h->state_f16 && plain_f16_stack(h, {b + "pooler.dense"}, H, H, &h->pooler_f)) return 1;
       if (H == 768 && c.heads == 12) {
         for (auto& w : h->l_layers) if (pack_head_major(h, &w.att)) return 1;
         for (auto& w : h->r_layers) if (pack_head_major(h, &w.att)) return 1;
@@ -939,12 +975,14 @@ int rgqa_finalize_weights(rgqa_handle* h) {
     h->pooler_f = Folded{};
     if (c.precision == RGQA_PREC_BF16) {  // deferred LayerNorm: same folding as the LXMERT language stack
       if (make_identity_ln(h)) return 1;
+      h->state_f16 = option_get(OPT_STATE_F16) != 0 && H == 768;
       const LNp* pl = nullptr;
       for (int i = 0; i < c.l_layers; ++i) {
         if (fold_bert_layer(h, u + "encoder.layer." + std::to_string(i), &h->l_layers[i], pl)) return 1;
         pl = &h->l_layers[i].ffn.ln;
       }
       if (pl != nullptr && fold_stack(h, {u + "pooler.dense"}, H, H, *pl, &h->pooler_f)) return 1;
+      if (pl == nullptr && h->state_f16 && plain_f16_stack(h, {u + "pooler.dense"}, H, H, &h->pooler_f)) return 1;
       if (H == 768 && c.heads == 12)
         for (auto& w : h->l_layers) if (pack_head_major(h, &w.att)) return 1;
     }
@@ -975,22 +1013,26 @@ int rgqa_finalize_weights(rgqa_handle* h) {
 // Same math as modeling.py:357-361 / :411-415, 53 fewer kernels and ~10 B per hidden element less HBM traffic per block.
 namespace {
 struct DState {
-  char* hi;      // bf16 [Mt, H]
-  char* lo;      // bf16 [Mt, H]
+  char* hi;      // bf16 [Mt, H]; fp16 in the single-word form (DefCtx::f16), where it is the whole state
+  char* lo;      // bf16 [Mt, H]; unused in the single-word form
   float* stats;  // [Mt, 6, 2]
 };
 struct DefCtx {
   rgqa_handle* h;
   int H;
+  // single-word state (option "state_f16", default): the pre-LayerNorm rows are ONE fp16 word per element — A operand of the
+  // consumers (fp16 x bf16 weights, kind::f16 takes the two formats independently) and residual carrier of the producers
+  // (11 significand bits; a producer moves 4 608 instead of 7 680 B per row at K = 768)
+  bool f16 = false;
   bool planes = false;  // Q|K|V projections are written head-major (gemm_bf16_qkv_planes) and read by attention_planes
   long long Mt = 0;     // rows of the plane tensor (all tokens of the batch)
   // Q|K|V of rows [r0, r0 + M) of `in` (LayerNorm ln still owed) into the shared qkv buffer, in the layout `planes` selects
   int qkv_proj(cudaStream_t st, const DState& in, const LNp* ln, const Linear& lin, const Folded& f, long long r0, int M) const {
     if (!planes) return consume(st, in, ln, lin, f, r0, M, rows_at(h->qkv.p, r0, 3 * H, 2), 3 * H, EPI_BIAS);
-    RGQA_CHECK(ln == nullptr || f.W != nullptr, "deferred LayerNorm: folded weight missing");
-    return gemm_bf16_qkv_planes(st, hi_rows(in, r0), H, ln ? f.W : lin.W, lin.K, ln ? f.b : lin.b,
+    RGQA_CHECK((ln == nullptr && !f16) || f.W != nullptr, "deferred LayerNorm: folded weight missing");
+    return gemm_bf16_qkv_planes(st, hi_rows(in, r0), H, (ln || f16) ? f.W : lin.W, lin.K, (ln || f16) ? f.b : lin.b,
                                 static_cast<char*>(h->qkv.p) + static_cast<size_t>(r0) * 64 * 2, Mt, h->cfg.heads, M, lin.K,
-                                ln ? st_rows(in, r0) : nullptr, h->cfg.ln_eps);
+                                ln ? st_rows(in, r0) : nullptr, h->cfg.ln_eps, f16 ? 1 : 0);
   }
   // softmax(QK^T/8 + mask) V for B samples: queries rows [rq, rq + B*Lq), keys / values rows [rk, rk + B*Lk) of the qkv buffer
   int attn(cudaStream_t st, long long rq, long long rk, const int32_t* key_mask, void* ctx_rows, int B, int Lq, int Lk) const {
@@ -1006,17 +1048,23 @@ struct DefCtx {
   // out = epi(LN_ln(in) · Wᵀ + b); ln == nullptr: `in` holds already-normalised rows
   int consume(cudaStream_t st, const DState& in, const LNp* ln, const Linear& lin, const Folded& f, long long r0, int M,
               void* out, long long ldo, int epi) const {
-    if (ln == nullptr)
-      return gemm_bf16(st, hi_rows(in, r0), H, lin.W, lin.K, lin.b, nullptr, 0, out, ldo, 0, M, lin.N, lin.K, epi);
+    if (ln == nullptr) {  // identity state: plain weight (its fp16 copy when the state is fp16)
+      RGQA_CHECK(!f16 || f.W != nullptr, "deferred LayerNorm: fp16 copy of the weight missing");
+      return gemm_bf16_folded(st, hi_rows(in, r0), H, f16 ? f.W : lin.W, lin.K, f16 ? f.b : lin.b, nullptr, 0, out, ldo, 0, M, lin.N,
+                              lin.K, epi, nullptr, nullptr, 0.f, 12, f16 ? 1 : 0);
+    }
     RGQA_CHECK(f.W != nullptr, "deferred LayerNorm: folded weight missing");
     return gemm_bf16_folded(st, hi_rows(in, r0), H, f.W, lin.K, f.b, nullptr, 0, out, ldo, 0, M, lin.N, lin.K, epi,
-                            st_rows(in, r0), f.c, h->cfg.ln_eps, 12);
+                            st_rows(in, r0), f.c, h->cfg.ln_eps, 12, f16 ? 1 : 0);
   }
   // out (pre-LayerNorm) = A · Wᵀ + b + LN_ln(in); bias_beta = b + ln->b precomputed (nullptr: ln == nullptr, beta = 0)
   int produce(cudaStream_t st, const void* A, long long lda, const Linear& lin, const float* bias_beta, const DState& in,
               const LNp* ln, const DState& out, long long r0, int M) const {
     const float* bias = (ln != nullptr && bias_beta != nullptr) ? bias_beta : lin.b;
     const float* beta = (ln != nullptr && bias_beta == nullptr) ? ln->b : nullptr;
+    if (f16)
+      return gemm_bf16_resid_h16(st, A, lda, lin.W, lin.K, bias, hi_rows(in, r0), st_rows(in, r0), ln ? ln->g : h->ones, beta,
+                                 h->cfg.ln_eps, hi_rows(out, r0), st_rows(out, r0), M, lin.N, lin.K);
     return gemm_bf16_resid_hl(st, A, lda, lin.W, lin.K, bias, hi_rows(in, r0), lo_rows(in, r0), st_rows(in, r0),
                               ln ? ln->g : h->ones, beta, h->cfg.ln_eps, hi_rows(out, r0), lo_rows(out, r0),
                               st_rows(out, r0), M, lin.N, lin.K);
@@ -1028,7 +1076,7 @@ struct DefCtx {
     if (!planes && w.qkv_hm != nullptr && qkv_attention_fused_ok(B, S, h->cfg.heads, H)) {
       // the projection tile is consumed where it is produced: no [rows, 2304] round trip, no attention launch
       if (qkv_attention_fused(st, hi_rows(in, r0), H, w.qkv_hm, w.qkv_hm_b, ln_in != nullptr ? st_rows(in, r0) : nullptr, h->cfg.ln_eps,
-                              key_mask, ctx, H, B, S, h->cfg.heads))
+                              key_mask, ctx, H, B, S, h->cfg.heads, f16 ? 1 : 0))
         return 1;
     } else {
       if (qkv_proj(st, in, ln_in, w.qkv, w.qkv_f, r0, B * S)) return 1;
@@ -1059,6 +1107,8 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
              reinterpret_cast<float*>(static_cast<char*>(h->resB.p) + static_cast<size_t>(Mt) * H * 2)};
   DefCtx d{h, H};
   d.Mt = Mt;
+  d.f16 = h->state_f16;
+  const int sdt = d.f16 ? DT_F16 : DT_BF16;  // what the embedding kernels write into `hi`
   d.planes = option_get(OPT_QKV_PLANES) != 0 && attention_planes_ok(B, L, L, c.heads) && attention_planes_ok(B, V, V, c.heads) &&
              attention_planes_ok(B, L, V, c.heads) && attention_planes_ok(B, V, L, c.heads);
 
@@ -1085,15 +1135,16 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
 
   // ---- embeddings (modeling.py:876) and visual feature encoder (:507-517): normalised rows -> identity states ----
   // the row kernels emit the identity state themselves (lo = bf16 remainder, statistics (0, 768)): no fp32 round trip
-  if (embed_ln(st, DT_BF16, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, cur.hi, nullptr, B, L, H,
-               c.vocab_size, c.max_position, c.type_vocab, c.ln_eps, cur.lo, cur.stats))
+  if (embed_ln(st, sdt, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, cur.hi, nullptr, B, L, H,
+               c.vocab_size, c.max_position, c.type_vocab, c.ln_eps, d.f16 ? nullptr : cur.lo, cur.stats))
     return 1;
   if (option_get(OPT_VISN_FUSED) != 0 && h->box_stat != nullptr && c.visual_feat_dim % 64 == 0) {
     // ONE kernel: projection (tf32 straight from fp32 features, or bf16), both LayerNorms, box branch, average, hi/lo state
     const bool f32 = feat_dtype == RGQA_DT_F32;
     if (visn_embed(sv, feat, f32 ? 1 : 0, c.visual_feat_dim, f32 ? static_cast<const void*>(h->visn_W32) : h->visn_fc.W, h->visn_fc.b,
                    h->visn_ln.g, h->visn_ln.b, pos, c.visual_pos_dim, h->box_Wp, h->box_b, h->box_ln.g, h->box_ln.b, h->box_stat,
-                   c.ln_eps, d.hi_rows(cur, Ml), d.lo_rows(cur, Ml), d.st_rows(cur, Ml), static_cast<int>(Mv), c.visual_feat_dim))
+                   c.ln_eps, d.hi_rows(cur, Ml), d.f16 ? nullptr : d.lo_rows(cur, Ml), d.st_rows(cur, Ml), static_cast<int>(Mv),
+                   c.visual_feat_dim))
       return 1;
   } else {
     const void* a = feat;
@@ -1104,8 +1155,8 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
     float* pre = reinterpret_cast<float*>(rows_at(h->pre.p, Ml, H, 4));
     if (gemm_bf16(sv, a, c.visual_feat_dim, h->visn_fc.W, h->visn_fc.K, h->visn_fc.b, nullptr, 0, pre, H, 1, static_cast<int>(Mv),
                   H, h->visn_fc.K, EPI_BIAS) ||
-        visn_combine(sv, DT_BF16, pre, pos, c.visual_pos_dim, h->box_W, h->box_b, h->visn_ln.g, h->visn_ln.b, h->box_ln.g,
-                     h->box_ln.b, d.hi_rows(cur, Ml), nullptr, static_cast<int>(Mv), H, c.ln_eps, d.lo_rows(cur, Ml),
+        visn_combine(sv, sdt, pre, pos, c.visual_pos_dim, h->box_W, h->box_b, h->visn_ln.g, h->visn_ln.b, h->box_ln.g,
+                     h->box_ln.b, d.hi_rows(cur, Ml), nullptr, static_cast<int>(Mv), H, c.ln_eps, d.f16 ? nullptr : d.lo_rows(cur, Ml),
                      d.st_rows(cur, Ml)))
       return 1;
   }
@@ -1152,8 +1203,8 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
     alt = t;
   }
   if (!out.any()) return 0;
-  if (ln_l == nullptr) return head_block(h, st, cur.hi, B, L, out);
-  return head_block(h, st, cur.hi, B, L, out, cur.stats);
+  if (ln_l == nullptr) return head_block(h, st, cur.hi, B, L, out, nullptr, d.f16 ? 1 : 0);
+  return head_block(h, st, cur.hi, B, L, out, cur.stats, d.f16 ? 1 : 0);
 }
 
 static int lxmert_forward_impl(rgqa_handle* h, cudaStream_t st, const void* feat, int feat_dtype, const float* pos,
@@ -1295,6 +1346,7 @@ static int lxmert_forward_graphed(rgqa_handle* h, void* stream, const void* feat
                         (static_cast<long long>(option_get(OPT_MAHA_TC) != 0) << 42) |
                         (static_cast<long long>(option_get(OPT_VISN_FUSED) != 0) << 43) |
                         (static_cast<long long>(option_get(OPT_ATTN_FUSED) != 0) << 44) |
+
                         (static_cast<long long>(out.score_mask & 0x1Fu) << 48) |
                         ((seg != nullptr) << 2) | ((out.pooled != nullptr) << 1) | (out.logits != nullptr);
   if (h->graphs.size() > 16) {  // callers that never repeat a pointer: do not hoard graphs
@@ -1498,8 +1550,9 @@ static int uniter_forward_impl(rgqa_handle* h, void* stream, const void* feat, i
               reinterpret_cast<float*>(static_cast<char*>(h->resA.p) + static_cast<size_t>(Mt) * H * 2)};
     DState da{static_cast<char*>(h->hidB.p), static_cast<char*>(h->resB.p),
               reinterpret_cast<float*>(static_cast<char*>(h->resB.p) + static_cast<size_t>(Mt) * H * 2)};
-    const DefCtx d{h, H};
-    if (identity_state(st, res_dst, dc.hi, dc.lo, dc.stats, Mt, H)) return 1;
+    DefCtx d{h, H};
+    d.f16 = h->state_f16;
+    if (identity_state(st, res_dst, dc.hi, d.f16 ? nullptr : dc.lo, dc.stats, Mt, H)) return 1;
     const LNp* ln = nullptr;
     for (int i = 0; i < c.l_layers; ++i) {
       const LayerW& w = h->l_layers[i];
@@ -1507,7 +1560,7 @@ static int uniter_forward_impl(rgqa_handle* h, void* stream, const void* feat, i
       ln = &w.ffn.ln;
     }
     if (!out.any()) return 0;
-    return head_block(h, st, dc.hi, B, S, out, ln != nullptr ? dc.stats : nullptr);
+    return head_block(h, st, dc.hi, B, S, out, ln != nullptr ? dc.stats : nullptr, d.f16 ? 1 : 0);
   }
   for (int i = 0; i < c.l_layers; ++i) {
     if (att_block(h, st, h->l_layers[i].att, cur, alt, 0, B, S, jmask)) return 1;
@@ -1647,6 +1700,10 @@ int rgqa_set_option(const char* name, int value) {
     option_set(OPT_ATTN_FUSED, value);
     return 0;
   }
+  if (strcmp(name, "state_f16") == 0) {
+    option_set(OPT_STATE_F16, value);
+    return 0;
+  }
   if (strcmp(name, "gemm_debug") == 0) {  // measurement only: results are wrong while non-zero
     option_set(OPT_GEMM_DEBUG, value);
     return 0;
@@ -1731,6 +1788,28 @@ int rgqa_gemm_bf16_resid_hl(void* stream, const void* A, int64_t lda, const void
                             int K) {
   return gemm_bf16_resid_hl(static_cast<cudaStream_t>(stream), A, lda, W, ldw, bias, in_hi, in_lo, in_stats, in_gamma,
                             in_beta, eps, out_hi, out_lo, out_stats, M, N, K);
+}
+int rgqa_fold_ln_weight_f16(void* stream, const float* W, const float* bias, const float* gamma, const float* beta, int N,
+                            int K, void* W_out_f16, float* c_out, float* bias_out) {
+  return fold_ln_weight(static_cast<cudaStream_t>(stream), W, bias, gamma, beta, N, K, W_out_f16, c_out, bias_out, 1);
+}
+int rgqa_gemm_bf16_folded_a16(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* out,
+                              int64_t ldo, int out_dtype, int M, int N, int K, int epilogue, const float* ln_stats,
+                              const float* ln_c, float eps) {
+  return gemm_bf16_folded(static_cast<cudaStream_t>(stream), A, lda, W, ldw, bias, nullptr, 0, out, ldo,
+                          out_dtype == RGQA_DT_F32 ? 1 : 0, M, N, K, epilogue, ln_stats, ln_c, eps, 12, 1);
+}
+int rgqa_qkv_attention_fused_a16(void* stream, const void* A, int64_t lda, const void* W_hm, const float* bias_hm,
+                                 const float* ln_stats, float ln_eps, const int32_t* key_mask, void* ctx, int64_t ldo, int B, int S,
+                                 int heads) {
+  return qkv_attention_fused(static_cast<cudaStream_t>(stream), A, lda, W_hm, bias_hm, ln_stats, ln_eps, key_mask, ctx, ldo, B, S,
+                             heads, 1);
+}
+int rgqa_gemm_bf16_resid_h16(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                             const void* in_h, const float* in_stats, const float* in_gamma, const float* in_beta, float eps,
+                             void* out_h, float* out_stats, int M, int N, int K) {
+  return gemm_bf16_resid_h16(static_cast<cudaStream_t>(stream), A, lda, W, ldw, bias, in_h, in_stats, in_gamma, in_beta, eps,
+                             out_h, out_stats, M, N, K);
 }
 int rgqa_gemm_f32(void* stream, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                   const float* resid, int64_t ldr, float* out, int64_t ldo, int M, int N, int K, int epilogue) {

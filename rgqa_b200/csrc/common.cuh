@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -101,6 +102,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // two 16-bit extracts and compiles to three or four instructions per word)
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+// fp16 pair (the single-word deferred-LayerNorm state): round to nearest, saturating to +-65504 instead of inf
+// (one F2FP.SATFINITE); unpack = two HADD2.F32
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -345,7 +356,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B     [61,64)
   return d;
 }
-// Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M x N tile.
+// Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M x N tile.  kind::f16 has one format field per operand
+// (0 = fp16, 1 = bf16) but the hardware wants them EQUAL (fp16 x bf16 raises an illegal-instruction error on B200): clearing
+// kIdescABf16 turns the MMA into fp16 x fp16 (the fp16 deferred-LayerNorm state against fp16 copies of the folded weights).
+constexpr uint32_t kIdescABf16 = (1u << 7) | (1u << 10);
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4)            // D format: F32
          | (1u << 7)          // A format: BF16

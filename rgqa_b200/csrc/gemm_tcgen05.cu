@@ -71,6 +71,7 @@ struct GemmParams {
   long long ln_stats_ld;  // floats between the statistics of consecutive GEMM rows (12 when dense)
   int out_heads;  // > 0: the output is the head-major Q|K|V plane tensor (gemm_bf16_qkv_planes); column block cb of 64 goes
                   // to plane (cb % heads) * 3 + cb / heads
+  int a_f16;   // A and W are fp16 (the single-word deferred-LayerNorm state against the fp16 copy of its consumer's weight)
   int vec_ok;  // direct path: rows of out (and resid) are 16-byte aligned -> vector stores allowed
   int debug;   // measurement only (rgqa_set_option "gemm_debug"): bit0 skip TMA stores, bit1 skip epilogue math+smem
   RowReduce red;  // EPI_REDUCE: row reductions fused into the epilogue (answer-head scorers, Mahalanobis)
@@ -407,7 +408,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    const uint32_t idesc = umma_idesc_bf16(BM, BN) & ~(p.a_f16 ? kIdescABf16 : 0u);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -586,14 +587,19 @@ constexpr int kResidRing = 3;
 constexpr int kResidStages = 4;
 // RING = 2 (K >= 2048): one residual slab of prefetch is enough when a tile's main loop lasts 48 k-blocks, and the
 // smem it frees buys a fifth main-loop stage.
-template <bool STAGED, bool RESID_SMEM, int EW, int RING = kResidRing>
+// H16 (fp16 single-word state, EPI_RESID_H16*): a ring buffer is 128 rows x 64 B = 8 KB instead of 16 KB (hi + lo), which
+// buys the K = 768 producer a fifth and the K = 3072 producer a sixth main-loop stage.
+template <bool STAGED, bool RESID_SMEM, int EW, int RING = kResidRing, bool H16 = false>
 struct PairCfg {
   static constexpr int kGroups = EW / 4;
-  static constexpr int kStages = RESID_SMEM ? (RING == 2 ? kResidStages + 1 : kResidStages) : (STAGED ? 5 : 6);
+  static constexpr int kBufBytes = H16 ? kSlabBytes / 2 : kSlabBytes;
+  static constexpr int kStages = RESID_SMEM ? ((RING == 2 ? kResidStages + 1 : kResidStages) + (H16 ? 1 : 0)) : (STAGED ? 5 : 6);
   static constexpr int kBufsPerGroup = RESID_SMEM ? RING : (STAGED ? (EW == 16 ? 1 : 2) : 0);
-  static constexpr int kSlabRegion = kGroups * kBufsPerGroup * kSlabBytes;
+  static constexpr int kSlabRegion = kGroups * kBufsPerGroup * kBufBytes;
   static constexpr int kSmemBytes = kStages * kPairStageBytes + kSlabRegion + 1024 + 512;
 };
+constexpr bool epi_is_h16(int epi) { return epi == EPI_RESID_H16 || epi == EPI_RESID_H16_BETA; }
+constexpr bool epi_is_hilo(int epi) { return epi == EPI_RESID_HL || epi == EPI_RESID_HL_BETA; }
 
 template <int EPI, typename OutT, bool STAGED, int EW, int RING>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + EW) * 32, 1)
@@ -602,11 +608,13 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                       const __grid_constant__ CUtensorMap tmOutLo, const __grid_constant__ CUtensorMap tmResLo,
                       const GemmParams p) {
   // deferred-LayerNorm producer (bf16 hi/lo pair + statistics)
-  constexpr bool kHiLo = STAGED && (EPI == EPI_RESID_HL || EPI == EPI_RESID_HL_BETA);
-  constexpr bool kHasBeta = EPI == EPI_RESID_HL_BETA;  // else the bias already carries beta (folded at load time)
-  constexpr bool kResidSmem = (STAGED && EPI == EPI_RESID && sizeof(OutT) == 4) || kHiLo;
+  constexpr bool kHiLo = STAGED && epi_is_hilo(EPI);
+  constexpr bool kH16 = STAGED && epi_is_h16(EPI);  // deferred-LayerNorm producer, fp16 single-word state + statistics
+  constexpr bool kHasBeta = EPI == EPI_RESID_HL_BETA || EPI == EPI_RESID_H16_BETA;  // else the bias already carries beta (folded at load time)
+  constexpr bool kResidSmem = (STAGED && EPI == EPI_RESID && sizeof(OutT) == 4) || kHiLo || kH16;
   static_assert(EW == 8 || (EW == 16 && STAGED && !kResidSmem), "16 epilogue warps: staged, non-residual epilogues only");
-  using PC = PairCfg<STAGED, kResidSmem, EW, RING>;
+  using PC = PairCfg<STAGED, kResidSmem, EW, RING, kH16>;
+  constexpr int kBufBytes = PC::kBufBytes;
   constexpr int kRing = RING;
   constexpr int kStages = PC::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -688,7 +696,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA only) ------------------------------
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, kPairBN);
+      const uint32_t idesc = umma_idesc_bf16(2 * BM, kPairBN) & ~(p.a_f16 ? kIdescABf16 : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -755,9 +763,11 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_arrive(bar);
           return;
         }
-        mbar_expect_tx(bar, kSubSlab);
-        uint8_t* dst = slabs + (half * kRing + b) * kSlabBytes;
-        if constexpr (kHiLo) {  // hi rows then lo rows, 128 x 64 B each, 64-byte swizzle
+        mbar_expect_tx(bar, kBufBytes / 4);
+        uint8_t* dst = slabs + (half * kRing + b) * kBufBytes;
+        if constexpr (kH16) {  // 128 x 64 B of fp16 rows, 64-byte swizzle
+          tma_load_2d(dst + quarter * (kBufBytes / 4), &tmRes, bar, col, row0);
+        } else if constexpr (kHiLo) {  // hi rows then lo rows, 128 x 64 B each, 64-byte swizzle
           tma_load_2d(dst + quarter * (kSubSlab / 2), &tmRes, bar, col, row0);
           tma_load_2d(dst + kSlabBytes / 2 + quarter * (kSubSlab / 2), &tmResLo, bar, col, row0);
         } else {
@@ -782,7 +792,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int row0 = cur_row0, col = cur_col0 + sl * 32;
         const int row = row0 + lane;
         if (sl == 0) {
-          if constexpr (kHiLo) {
+          if constexpr (kHiLo || kH16) {
             rin = row_norm(p.in_stats, row, row < p.M, p.ln_eps);
             st_sum2 = st_sq2 = make_float2(0.f, 0.f);
             // this row's statistics of the NEXT tile: pull the line into L1 while this tile is processed
@@ -793,7 +803,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tc_fence_after();
         }
         const int b = k % kRing;
-        uint8_t* buf = slabs + (half * kRing + b) * kSlabBytes;
+        uint8_t* buf = slabs + (half * kRing + b) * kBufBytes;
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                       static_cast<uint32_t>(acc * kPairBN + half * kColsPerWarp + sl * 32), v);
@@ -802,6 +812,51 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         float f[32];
         if (p.debug & 2) {
           // measurement: no epilogue math / shared-memory traffic
+        } else if constexpr (kH16) {
+          // residual = LN_prev(x_prev), x_prev = the fp16 state row; v = acc + bias + residual; v goes back as fp16 (saturating)
+          // and the statistics are those of the ROUNDED values — what every later reader of the state sees
+          uint8_t* hrow = buf + r_local * 64;
+          const int sw = (r_local >> 1) & 3;
+          const float ra = rin.rstd, rb = -rin.mu * rin.rstd;
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+          const float4* g4 = reinterpret_cast<const float4*>(p.in_gamma + col);
+          [[maybe_unused]] const float4* e4 = reinterpret_cast<const float4*>((kHasBeta ? p.in_beta : p.bias) + col);
+          uint32_t hw[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 h4 = *reinterpret_cast<const uint4*>(hrow + ((i ^ sw) << 4));
+            hw[4 * i + 0] = h4.x; hw[4 * i + 1] = h4.y; hw[4 * i + 2] = h4.z; hw[4 * i + 3] = h4.w;
+          }
+          const float2 ra2 = make_float2(ra, ra), rb2 = make_float2(rb, rb);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {  // columns 4i .. 4i+3 = fp16 words 2i, 2i+1
+            float4 bb = __ldg(b4 + i);
+            const float4 gg = __ldg(g4 + i);
+            if constexpr (kHasBeta) {
+              const float4 ee = __ldg(e4 + i);
+              bb.x += ee.x;
+              bb.y += ee.y;
+              bb.z += ee.z;
+              bb.w += ee.w;
+            }
+            const float2 h0 = unpack_f16x2(hw[2 * i]), h1 = unpack_f16x2(hw[2 * i + 1]);
+            const float2 ra0 = __ffma2_rn(__ffma2_rn(h0, ra2, rb2), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y));
+            const float2 ra1 = __ffma2_rn(__ffma2_rn(h1, ra2, rb2), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w));
+            const float2 o0 = __fadd2_rn(make_float2(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1])), ra0);
+            const float2 o1 = __fadd2_rn(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), ra1);
+            hw[2 * i] = pack_f16x2_sat(o0.x, o0.y);
+            hw[2 * i + 1] = pack_f16x2_sat(o1.x, o1.y);
+            const float2 q0 = unpack_f16x2(hw[2 * i]), q1 = unpack_f16x2(hw[2 * i + 1]);
+            st_sum2 = __fadd2_rn(st_sum2, __fadd2_rn(q0, q1));
+            st_sq2 = __ffma2_rn(q1, q1, __ffma2_rn(q0, q0, st_sq2));
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(hrow + ((i ^ sw) << 4)) = make_uint4(hw[4 * i + 0], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+          if (sl == 3 && row < p.M) {  // this thread's 128 columns of the row are done: publish their partial statistics
+            float2* so = reinterpret_cast<float2*>(p.out_stats + static_cast<long long>(row) * 12) + (cur_col0 >> 7);  // 128-column slice
+            *so = make_float2(st_sum2.x + st_sum2.y, st_sq2.x + st_sq2.y);
+          }
         } else if constexpr (kHiLo) {
           // residual = LN_prev(x_prev) with x_prev = hi + lo; v = acc + bias + residual; then split v again
           // 64-byte swizzle: 16-byte piece i of row r sits at piece i ^ ((r >> 1) & 3) -> conflict-free row-per-lane access
@@ -893,7 +948,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         __syncwarp();
         if (issuer) {
           if (row0 < p.M && !(p.debug & 1)) {
-            if constexpr (kHiLo) {
+            if constexpr (kH16) {
+              tma_store_2d(&tmOut, buf + quarter * (kBufBytes / 4), col, row0);
+            } else if constexpr (kHiLo) {
               tma_store_2d(&tmOut, buf + quarter * (kSubSlab / 2), col, row0);
               tma_store_2d(&tmOutLo, buf + kSlabBytes / 2 + quarter * (kSubSlab / 2), col, row0);
             } else {
@@ -1131,7 +1188,7 @@ int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& 
   constexpr int EW = 8;
   auto kern = gemm_bf16_pair_kernel<EPI, OutT, STAGED, EW, RING>;
   constexpr int smem =
-      PairCfg<STAGED, (STAGED && ((EPI == EPI_RESID && sizeof(OutT) == 4) || EPI == EPI_RESID_HL || EPI == EPI_RESID_HL_BETA)), EW, RING>::kSmemBytes;
+      PairCfg<STAGED, (STAGED && ((EPI == EPI_RESID && sizeof(OutT) == 4) || epi_is_hilo(EPI) || epi_is_h16(EPI))), EW, RING, STAGED && epi_is_h16(EPI)>::kSmemBytes;
   static bool configured = false;
   if (!configured) {
     RGQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1218,6 +1275,40 @@ int gemm_bf16_resid_hl(cudaStream_t stream, const void* A, long long lda, const 
   return launch_pair<EPI_RESID_HL, __nv_bfloat16, true>(stream, tmA, tmB, tmOutHi, tmInHi, p, &tmOutLo, &tmInLo);
 }
 
+int gemm_bf16_resid_h16(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                        const void* in_h, const float* in_stats, const float* in_gamma, const float* in_beta, float eps,
+                        void* out_h, float* out_stats, int M, int N, int K) {
+  RGQA_CHECK(M > 0 && K > 0 && K % BK == 0, "gemm_bf16_resid_h16: bad problem M=%d K=%d", M, K);
+  RGQA_CHECK(N == 768, "gemm_bf16_resid_h16: built for N = 768 (got %d)", N);
+  RGQA_CHECK(bias && in_h && in_stats && in_gamma && out_h && out_stats, "gemm_bf16_resid_h16: null argument");
+  CUtensorMap tmA, tmB, tmOut, tmIn;
+  if (make_tmap(&tmA, A, M, K, lda, BM, 2)) return 1;
+  if (make_tmap(&tmB, W, N, K, ldw, kPairBN / 2, 2)) return 1;
+  // 32 rows (one epilogue warp) x 32 fp16 columns (64 B), 64-byte swizzle
+  if (make_tmap_ex(&tmOut, out_h, M, N, N, 32, 32, 2, 64) || make_tmap_ex(&tmIn, in_h, M, N, N, 32, 32, 2, 64)) return 1;
+  GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.bias = bias;
+  p.in_stats = in_stats;
+  p.in_gamma = in_gamma;
+  p.in_beta = in_beta;
+  p.out_stats = out_stats;
+  p.ln_eps = eps;
+  p.ln_stats_ld = 12;
+  p.out = out_h;
+  p.ldo = N;
+  p.vec_ok = 1;
+  p.debug = option_get(OPT_GEMM_DEBUG);
+  if (in_beta != nullptr) {
+    if (K >= 2048) return launch_pair<EPI_RESID_H16_BETA, __nv_bfloat16, true, 2>(stream, tmA, tmB, tmOut, tmIn, p);
+    return launch_pair<EPI_RESID_H16_BETA, __nv_bfloat16, true>(stream, tmA, tmB, tmOut, tmIn, p);
+  }
+  if (K >= 2048) return launch_pair<EPI_RESID_H16, __nv_bfloat16, true, 2>(stream, tmA, tmB, tmOut, tmIn, p);
+  return launch_pair<EPI_RESID_H16, __nv_bfloat16, true>(stream, tmA, tmB, tmOut, tmIn, p);
+}
+
 int gemm_bf16_reduce(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
                      float* out, long long ldo, int M, int N, int K, const RowReduce& red) {
   RGQA_CHECK(M > 0 && N > 0 && K > 0 && K % BK == 0, "gemm_bf16_reduce: bad problem M=%d N=%d K=%d", M, N, K);
@@ -1251,7 +1342,7 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
 // kernel is then three contiguous L x 128-byte blocks instead of 3 L pieces at a 4 608-byte stride, and every 32-row store of
 // this epilogue one contiguous 4 KB block.  bf16, bias epilogue, CTA-pair + staged kernel only (M >= 1024, N = 3 * heads * 64).
 int gemm_bf16_qkv_planes(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
-                         void* out, long long plane_rows, int heads, int M, int K, const float* ln_stats, float ln_eps) {
+                         void* out, long long plane_rows, int heads, int M, int K, const float* ln_stats, float ln_eps, int a_f16) {
   const int N = 3 * heads * 64;
   RGQA_CHECK(M >= 1024 && K > 0 && K % BK == 0 && heads > 0 && plane_rows >= M, "gemm_bf16_qkv_planes: bad problem M=%d K=%d", M, K);
   RGQA_CHECK(option_get(OPT_GEMM_PAIR) != 0 && option_get(OPT_GEMM_STAGED) != 0, "gemm_bf16_qkv_planes: needs the staged CTA-pair kernel");
@@ -1271,6 +1362,7 @@ int gemm_bf16_qkv_planes(cudaStream_t stream, const void* A, long long lda, cons
   p.ln_eps = ln_eps;
   p.ln_stats_ld = 12;
   p.out_heads = heads;
+  p.a_f16 = a_f16;
   p.vec_ok = 1;
   p.debug = option_get(OPT_GEMM_DEBUG);
   return launch_pair<EPI_BIAS, __nv_bfloat16, true>(stream, tmA, tmB, tmOut, tmA, p);
@@ -1278,7 +1370,7 @@ int gemm_bf16_qkv_planes(cudaStream_t stream, const void* A, long long lda, cons
 
 int gemm_bf16_folded(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
                      const void* resid, long long ldr, void* out, long long ldo, int out_f32, int M, int N, int K, int epi,
-                     const float* ln_stats, const float* ln_c, float ln_eps, long long ln_stats_ld) {
+                     const float* ln_stats, const float* ln_c, float ln_eps, long long ln_stats_ld, int a_f16) {
   RGQA_CHECK(ln_stats == nullptr || (bias != nullptr && K == 768 && epi != EPI_RESID),
              "gemm_bf16: deferred LayerNorm needs K = 768, the folded bias and a non-residual epilogue");
   RGQA_CHECK(M > 0 && N > 0 && K > 0, "gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
@@ -1331,6 +1423,7 @@ int gemm_bf16_folded(cudaStream_t stream, const void* A, long long lda, const vo
   p.ln_eps = ln_eps;
   p.ln_stats_ld = ln_stats_ld > 0 ? ln_stats_ld : 12;
   p.vec_ok = (out_al && res_al && bias_al) ? 1 : 0;
+  p.a_f16 = a_f16;
   p.debug = option_get(OPT_GEMM_DEBUG);
   if (use_pair) return dispatch_pair(stream, tmA, tmB, tmOut, tmRes, p, epi, out_f32, staged);
   if (bn == 256) return dispatch_epi<256>(stream, tmA, tmB, p, epi, out_f32);

@@ -17,6 +17,8 @@ enum Epilogue : int {
   EPI_RESID_HL = 4,  // same sum, residual recomputed from a deferred-LayerNorm hidden state, written as a bf16 hi/lo pair
   EPI_RESID_HL_BETA = 5,  // EPI_RESID_HL with LN_prev's beta passed separately (the engine folds it into the bias at load time)
   EPI_REDUCE = 6,  // acc + bias reduced along each row inside the epilogue (scorers of the answer head / Mahalanobis), see RowReduce
+  EPI_RESID_H16 = 7,       // EPI_RESID_HL with the state as ONE fp16 word per element (no lo): half the residual bytes
+  EPI_RESID_H16_BETA = 8,  // ... with LN_prev's beta passed separately
 };
 
 // Row reductions fused into a GEMM epilogue (gemm_bf16_reduce).  Every (row tile, column tile) CTA leaves one partial
@@ -44,7 +46,7 @@ struct RowReduce {
 inline size_t row_reduce_part_bytes(int M, int N) { return static_cast<size_t>((M + 127) / 128) * 128 * 2 * ((N + 127) / 128) * 8 * sizeof(float); }
 inline int row_reduce_counters(int M) { return (M + 127) / 128; }
 
-enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+enum DType : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 /* the fp16 deferred-LayerNorm state (embed_ln / visn_combine outputs, GEMM A operands) */ };
 
 // ---- GEMMs -------------------------------------------------------------------------------------
 // bf16 tensor-core path: A [M,K] bf16 (row stride lda), W [N,K] bf16 (row stride ldw), bias fp32,
@@ -57,7 +59,8 @@ int gemm_bf16(cudaStream_t stream, const void* A, long long lda, const void* W, 
 // centring: when given, the epilogue also subtracts mu*c[n] from acc (exact form, one more FMA per element).  K = 768.
 int gemm_bf16_folded(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
                      const void* resid, long long ldr, void* out, long long ldo, int out_f32, int M, int N, int K, int epi,
-                     const float* ln_stats, const float* ln_c, float ln_eps, long long ln_stats_ld = 12);
+                     const float* ln_stats, const float* ln_c, float ln_eps, long long ln_stats_ld = 12,
+                     int a_f16 = 0 /* A AND W are fp16 (the fp16 deferred-LayerNorm state against fp16 weight copies) */);
 // out = A·Wᵀ + bias reduced per row in the epilogue (see RowReduce); `out` (fp32 [M, N], row stride ldo) may be nullptr: the
 // matrix is then never written.  Single-CTA 128 x 128 tiles (the head GEMMs have M = batch rows).
 int gemm_bf16_reduce(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
@@ -65,7 +68,8 @@ int gemm_bf16_reduce(cudaStream_t stream, const void* A, long long lda, const vo
 // Q|K|V projection with a head-major output: out[plane = head*3 + {q,k,v}][row][64] bf16, planes plane_rows rows apart; `out`
 // points at this call's first row of plane 0.  ln_stats != nullptr: deferred-LayerNorm consumer (folded weight / bias).
 int gemm_bf16_qkv_planes(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
-                         void* out, long long plane_rows, int heads, int M, int K, const float* ln_stats, float ln_eps);
+                         void* out, long long plane_rows, int heads, int M, int K, const float* ln_stats, float ln_eps,
+                         int a_f16 = 0);
 // attention over the head-major planes of gemm_bf16_qkv_planes (TMA kernel only): queries are rows [q_row0, q_row0 + B*Lq) and
 // keys / values rows [kv_row0, kv_row0 + B*Lk) of the same plane tensor; out [B*Lq, heads*64] bf16 (row stride ldo).
 int attention_planes(cudaStream_t stream, const void* planes, long long plane_rows, long long q_row0, long long kv_row0,
@@ -78,13 +82,19 @@ int attention_planes_ok(int B, int Lq, int Lk, int heads);
 int gemm_bf16_resid_hl(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
                        const void* in_hi, const void* in_lo, const float* in_stats, const float* in_gamma,
                        const float* in_beta, float eps, void* out_hi, void* out_lo, float* out_stats, int M, int N, int K);
+// The same producer over the single-word state: x_prev = in_h (fp16 [M, 768]), v written as out_h = fp16(v) (saturating at
+// +-65504) and the partial statistics of the rounded row.  4 608 instead of 7 680 B of HBM traffic per row at K = 768.
+int gemm_bf16_resid_h16(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                        const void* in_h, const float* in_stats, const float* in_gamma, const float* in_beta, float eps,
+                        void* out_h, float* out_stats, int M, int N, int K);
 // W'[n,k] = bf16(W[n,k]*gamma[k] - mean_k(W[n,:]*gamma)), c[n] = sum_k float(W'[n,k]) (the bf16 rounding residue of the
 // centring), bias_out[n] = bias[n] + sum_k W[n,k]*beta[k]
 int fold_ln_weight(cudaStream_t stream, const float* W, const float* bias, const float* gamma, const float* beta, int N,
-                   int K, void* W_out_bf16, float* c_out, float* bias_out);
+                   int K, void* W_out_bf16, float* c_out, float* bias_out, int f16 = 0 /* W' as fp16 instead of bf16 */);
 // A normalised hidden state y (bf16 rows `hi` + their fp32 copy) as a deferred-LayerNorm state whose LayerNorm is the
-// identity: lo = bf16(y - hi), stats = (0, 768, 0, ...) so that mean = 0 and rstd = 1.
-int identity_state(cudaStream_t stream, const float* y_f32, const void* hi, void* lo, float* stats, long long M, int H);
+// identity: lo = bf16(y - hi), stats = (0, 768, 0, ...) so that mean = 0 and rstd = 1.  lo == nullptr: the fp16 single-word
+// state — `hi` is rewritten as fp16(y).
+int identity_state(cudaStream_t stream, const float* y_f32, void* hi, void* lo, float* stats, long long M, int H);
 // fp32 SIMT path (precise mode): everything fp32.
 int gemm_f32(cudaStream_t stream, const float* A, long long lda, const float* W, long long ldw, const float* bias,
              const float* resid, long long ldr, float* out, long long ldo, int M, int N, int K, int epi);
@@ -94,7 +104,7 @@ int gemm_f32(cudaStream_t stream, const float* A, long long lda, const float* W,
 // A = bf16 [B*S, 768] pre-LayerNorm rows + ln_stats (or already-normalised rows and nullptr), key_mask [B, S] or nullptr.
 int qkv_attention_fused(cudaStream_t stream, const void* A, long long lda, const void* W_hm, const float* bias_hm,
                         const float* ln_stats, float ln_eps, const int32_t* key_mask, void* ctx, long long ldo, int B, int S,
-                        int heads);
+                        int heads, int a_f16 = 0 /* A rows are the fp16 state and W_hm is fp16 */);
 int qkv_attention_fused_ok(int B, int S, int heads, int K);
 // VisualFeatEncoder in ONE kernel (visn_embed_tcgen05.cu; modeling.py:507-517): (LN1(feat·W1ᵀ + b1) + LN2(box·W2ᵀ + b2)) / 2
 // written as the identity deferred-LayerNorm state (hi, lo bf16 [M,768], stats [M,12]).  feat / W1 are fp32 (kind::tf32
@@ -147,6 +157,7 @@ int uniter_img_combine(cudaStream_t stream, int out_dtype, const float* x_pre, c
                        const float* b2, const float* type_row, const float* g3, const float* b3, void* out,
                        float* out32, int M, int H, float eps);
 int cast_f32_to_bf16(cudaStream_t stream, const float* in, void* out, long long n);
+int cast_f32_to_f16(cudaStream_t stream, const float* in, void* out, long long n);  // load time: fp16 copies of consumer weights
 // fp32 [M, K] -> bf16 [M, 3K] split operand (hi | hi | lo, or hi | lo | hi on the weight side): one bf16 GEMM over 3K then
 // evaluates the product to ~16 mantissa bits per operand (the tensor-core Mahalanobis)
 int split_bf16x3(cudaStream_t stream, const float* in, long long ld, void* out, long long M, int K, int weight_side);
@@ -214,6 +225,8 @@ enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_GEMM_DEBUG = 2, 
   OPT_MAHA_TC = 10,    // Mahalanobis on the tensor cores (split-bf16, fused arg-max) in bf16 handles
   OPT_VISN_FUSED = 11, // visual feature encoder as one tcgen05 kernel (visn_embed_tcgen05.cu)
   OPT_ATTN_FUSED = 12, // self-attention inside the Q|K|V projection's epilogue (qkv_attn_tcgen05.cu)
+  OPT_STATE_F16 = 13,  // read by rgqa_finalize_weights: deferred-LayerNorm state as ONE fp16 word per element (consumers run fp16 x fp16
+                       // against fp16 copies of their folded weights) instead of a bf16 hi/lo pair
   OPT_COUNT = 16 };
 int option_get(int key);
 void option_set(int key, int value);

@@ -52,6 +52,7 @@ struct QkvAttnParams {
   const float* ln_stats;   // [M][6][2] or nullptr (A rows are already normalised)
   float ln_eps;
   const int32_t* key_mask;  // [B, S] (1 = keep) or nullptr
+  int a_f16;                // A rows are fp16 (the single-word deferred-LayerNorm state) and so is W
   int debug;                // measurement only (rgqa_set_option "gemm_debug"): bit0 no attention tasks, bit1 no projection stores, bit2 no context store
 };
 
@@ -174,7 +175,7 @@ qkv_attn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA only) ------------------------------
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, kTileN);
+      const uint32_t idesc = umma_idesc_bf16(2 * BM, kTileN) & ~(p.a_f16 ? kIdescABf16 : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -408,7 +409,7 @@ int qkv_attention_fused_ok(int B, int S, int heads, int K) {
 
 int qkv_attention_fused(cudaStream_t stream, const void* A, long long lda, const void* W_hm, const float* bias_hm,
                         const float* ln_stats, float ln_eps, const int32_t* key_mask, void* ctx, long long ldo, int B, int S,
-                        int heads) {
+                        int heads, int a_f16) {
   RGQA_CHECK(A && W_hm && bias_hm && ctx && B > 0, "qkv_attention_fused: null argument");
   RGQA_CHECK(heads == 12 && S >= 1 && S <= 64, "qkv_attention_fused: built for 12 heads of 64 and S <= 64 (got heads=%d S=%d)", heads, S);
   RGQA_CHECK(reinterpret_cast<uintptr_t>(bias_hm) % 16 == 0, "qkv_attention_fused: bias must be 16-byte aligned");
@@ -423,6 +424,7 @@ int qkv_attention_fused(cudaStream_t stream, const void* A, long long lda, const
   p.ln_stats = ln_stats;
   p.ln_eps = ln_eps;
   p.key_mask = key_mask;
+  p.a_f16 = a_f16;
   p.debug = option_get(OPT_GEMM_DEBUG);
   CUtensorMap tmA, tmB, tmO;
   if (make_tmap(&tmA, A, M, 768, lda, BM, 2)) return 1;

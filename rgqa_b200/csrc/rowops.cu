@@ -2,6 +2,8 @@
 // feature/box combine, dtype casts.  One warp owns one row; a row of H = 128*NV floats sits in
 // registers as NV float4 per lane (fully coalesced 512 B per warp per load), statistics are
 // two-pass fp32 (mean, then variance of the centred values) with warp-shuffle reductions.
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -53,6 +55,8 @@ __device__ __forceinline__ void store_row(const float4 (&x)[NV], OutT* out_row, 
     if (copy_row != nullptr) *reinterpret_cast<float4*>(copy_row + c) = x[i];
     if constexpr (sizeof(OutT) == 4) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_row) + c) = x[i];
+    } else if constexpr (std::is_same<OutT, __half>::value) {  // the fp16 single-word deferred-LayerNorm state: no lo row
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out_row) + c) = make_uint2(pack_f16x2_sat(x[i].x, x[i].y), pack_f16x2_sat(x[i].z, x[i].w));
     } else {
       uint2 u;
       u.x = pack_bf16x2(x[i].x, x[i].y);
@@ -256,6 +260,11 @@ __global__ void cast_f32_bf16_tail(const float* in, __nv_bfloat16* out, long lon
   const long long i = start + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) out[i] = __float2bfloat16_rn(in[i]);
 }
+__global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __float2half_rn(in[i]);
+}
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -283,7 +292,7 @@ __global__ void gather_rows_kernel(const T* __restrict__ src, long long src_ld, 
 __global__ void __launch_bounds__(128) fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ bias,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       int N, int K, __nv_bfloat16* __restrict__ Wo,
-                                                      float* __restrict__ c_out, float* __restrict__ b_out) {
+                                                      float* __restrict__ c_out, float* __restrict__ b_out, int f16) {
   const int n = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -311,9 +320,16 @@ __global__ void __launch_bounds__(128) fold_ln_kernel(const float* __restrict__ 
       if (i == klast) continue;          // the smallest element is rounded last (i == K)
       const int k = i < K ? i : klast;
       const float target = fmaf(W[static_cast<long long>(n) * K + k], gamma[k], -wmean);
-      const __nv_bfloat16 wb = __float2bfloat16_rn(target + err);
-      Wo[static_cast<long long>(n) * K + k] = wb;
-      const float got = __bfloat162float(wb);
+      float got;
+      if (f16) {  // fp16 copy (consumers of the single-word fp16 state): same error feedback, 11 significand bits
+        const __half wh = __float2half_rn(target + err);
+        reinterpret_cast<__half*>(Wo)[static_cast<long long>(n) * K + k] = wh;
+        got = __half2float(wh);
+      } else {
+        const __nv_bfloat16 wb = __float2bfloat16_rn(target + err);
+        Wo[static_cast<long long>(n) * K + k] = wb;
+        got = __bfloat162float(wb);
+      }
       err += target - got;   // what the row sum still owes
       cs += got;
     }
@@ -323,12 +339,16 @@ __global__ void __launch_bounds__(128) fold_ln_kernel(const float* __restrict__ 
 }
 
 // identity deferred-LayerNorm state from a normalised row pair (bf16 hi + fp32 copy)
-__global__ void __launch_bounds__(256) identity_state_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict__ hi,
+__global__ void __launch_bounds__(256) identity_state_kernel(const float* __restrict__ y, __nv_bfloat16* __restrict__ hi,
                                                              __nv_bfloat16* __restrict__ lo, float* __restrict__ stats,
                                                              long long n4, long long nstat, float width) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = reinterpret_cast<const float4*>(y)[i];
+    if (lo == nullptr) {  // fp16 single-word state: `hi` is REWRITTEN as fp16(y)
+      reinterpret_cast<uint2*>(hi)[i] = make_uint2(pack_f16x2_sat(v.x, v.y), pack_f16x2_sat(v.z, v.w));
+      continue;
+    }
     const uint2 h = reinterpret_cast<const uint2*>(hi)[i];
     const float2 h0 = unpack_bf16x2(h.x), h1 = unpack_bf16x2(h.y);
     reinterpret_cast<uint2*>(lo)[i] = make_uint2(pack_bf16x2(v.x - h0.x, v.y - h0.y), pack_bf16x2(v.z - h1.x, v.w - h1.y));
@@ -422,7 +442,10 @@ int embed_ln(cudaStream_t stream, int out_dtype, const int32_t* ids, const int32
              int L, int H, int vocab, int max_pos, int n_types, float eps, void* lo_out, float* stats_out) {
   RGQA_CHECK(B > 0 && L > 0 && L <= max_pos, "embed_ln: bad B=%d L=%d (max_pos=%d)", B, L, max_pos);
   const int M = B * L;
-  if (out_dtype == DT_BF16) {
+  if (out_dtype == DT_F16) {  // fp16 identity state (single word, statistics (0, H)); lo_out is not used
+    RGQA_CHECK(stats_out != nullptr, "embed_ln: the fp16 state needs its statistics buffer");
+    RGQA_DISPATCH_ROW(embed_ln_kernel, __half, ids, seg, word, pos, type, gamma, beta, static_cast<__half*>(out), out32, static_cast<__nv_bfloat16*>(nullptr), stats_out, M, L, H, eps, vocab, n_types);
+  } else if (out_dtype == DT_BF16) {
     RGQA_DISPATCH_ROW(embed_ln_kernel, __nv_bfloat16, ids, seg, word, pos, type, gamma, beta, static_cast<__nv_bfloat16*>(out), out32, static_cast<__nv_bfloat16*>(lo_out), stats_out, M, L, H, eps, vocab, n_types);
   } else {
     RGQA_DISPATCH_ROW(embed_ln_kernel, float, ids, seg, word, pos, type, gamma, beta, static_cast<float*>(out), out32, static_cast<__nv_bfloat16*>(nullptr), static_cast<float*>(nullptr), M, L, H, eps, vocab, n_types);
@@ -450,7 +473,10 @@ int visn_combine(cudaStream_t stream, int out_dtype, const float* x_pre, const f
                  const float* Wb, const float* bb, const float* g1, const float* b1, const float* g2,
                  const float* b2, void* out, float* out32, int M, int H, float eps, void* lo_out, float* stats_out) {
   RGQA_CHECK(M > 0 && box_dim >= 1 && box_dim <= 8, "visn_combine: bad M=%d box_dim=%d", M, box_dim);
-  if (out_dtype == DT_BF16) {
+  if (out_dtype == DT_F16) {
+    RGQA_CHECK(stats_out != nullptr, "visn_combine: the fp16 state needs its statistics buffer");
+    RGQA_DISPATCH_ROW_SMEM(visn_combine_kernel, __half, (box_dim + 1) * H * sizeof(float), x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<__half*>(out), out32, static_cast<__nv_bfloat16*>(nullptr), stats_out, M, H, eps);
+  } else if (out_dtype == DT_BF16) {
     RGQA_DISPATCH_ROW_SMEM(visn_combine_kernel, __nv_bfloat16, (box_dim + 1) * H * sizeof(float), x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<__nv_bfloat16*>(out), out32, static_cast<__nv_bfloat16*>(lo_out), stats_out, M, H, eps);
   } else {
     RGQA_DISPATCH_ROW_SMEM(visn_combine_kernel, float, (box_dim + 1) * H * sizeof(float), x_pre, boxes, box_dim, Wb, bb, g1, b1, g2, b2, static_cast<float*>(out), out32, static_cast<__nv_bfloat16*>(nullptr), static_cast<float*>(nullptr), M, H, eps);
@@ -475,12 +501,22 @@ int uniter_img_combine(cudaStream_t stream, int out_dtype, const float* x_pre, c
   return 0;
 }
 
-int identity_state(cudaStream_t stream, const float* y_f32, const void* hi, void* lo, float* stats, long long M, int H) {
+int cast_f32_to_f16(cudaStream_t stream, const float* in, void* out, long long n) {
+  RGQA_CHECK(n > 0 && in != nullptr && out != nullptr, "cast_f32_to_f16: bad arguments");
+  long long grid = (n + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  cast_f32_f16_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(in, static_cast<__half*>(out), n);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int identity_state(cudaStream_t stream, const float* y_f32, void* hi, void* lo, float* stats, long long M, int H) {
   RGQA_CHECK(M > 0 && H % 4 == 0, "identity_state: bad shape");
   const long long n4 = M * H / 4;
   long long grid = (n4 + 255) / 256;
   if (grid > 148 * 16) grid = 148 * 16;
-  identity_state_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(y_f32, static_cast<const __nv_bfloat16*>(hi),
+  identity_state_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(y_f32, static_cast<__nv_bfloat16*>(hi),
                                                                        static_cast<__nv_bfloat16*>(lo), stats, n4, M * 12,
                                                                        static_cast<float>(H));
   note_launch();
@@ -489,10 +525,10 @@ int identity_state(cudaStream_t stream, const float* y_f32, const void* hi, void
 }
 
 int fold_ln_weight(cudaStream_t stream, const float* W, const float* bias, const float* gamma, const float* beta, int N,
-                   int K, void* W_out_bf16, float* c_out, float* bias_out) {
+                   int K, void* W_out_bf16, float* c_out, float* bias_out, int f16) {
   RGQA_CHECK(N > 0 && K > 0, "fold_ln_weight: empty weight");
   fold_ln_kernel<<<(N + 3) / 4, 128, 0, stream>>>(W, bias, gamma, beta, N, K, static_cast<__nv_bfloat16*>(W_out_bf16), c_out,
-                                                  bias_out);
+                                                  bias_out, f16);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;

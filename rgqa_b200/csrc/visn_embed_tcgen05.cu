@@ -307,6 +307,7 @@ visn_embed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       named_bar(1, kEpiWarps * 32);
 
       // ---------------- pass 2: both LayerNorms, average, hi/lo split, row-contiguous stores ----------------
+      const bool f16_state = p.lo == nullptr;
       const float xa = rstd, xb = -mean * rstd;        // LN_1: (x - mean) * rstd = x * xa + xb
       const float ya = yrstd, yb = -ymean * yrstd;
 #pragma unroll 1
@@ -333,12 +334,18 @@ visn_embed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const float yn = fmaf(yg, ya, yb * a.w);
             o[ee] = (fmaf(xn, a.y, yn) + a.z) * 0.5f;   // (LN_1(x) g1 + be1 + LN_2(y) g2 + be2) / 2
           }
-          hw[i] = pack_bf16x2(o[0], o[1]);
-          const float2 hf = unpack_bf16x2(hw[i]);
-          lw[i] = pack_bf16x2(o[0] - hf.x, o[1] - hf.y);
+          if (f16_state) {  // single-word fp16 state (p.lo == nullptr): no remainder
+            hw[i] = pack_f16x2_sat(o[0], o[1]);
+            lw[i] = 0u;
+          } else {
+            hw[i] = pack_bf16x2(o[0], o[1]);
+            const float2 hf = unpack_bf16x2(hw[i]);
+            lw[i] = pack_bf16x2(o[0] - hf.x, o[1] - hf.y);
+          }
         }
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {  // hi rows, then lo rows, through the same 2 KB buffer
+          if (pass == 1 && f16_state) break;
           const uint32_t* src = pass == 0 ? hw : lw;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -383,7 +390,7 @@ int visn_embed(cudaStream_t stream, const void* feat, int feat_f32, long long ld
   const int bk = feat_f32 ? 32 : 64;
   RGQA_CHECK(K % bk == 0, "visn_embed: K=%d must be a multiple of %d", K, bk);
   RGQA_CHECK(box_dim >= 1 && box_dim <= 4, "visn_embed: box_dim %d out of range [1,4] (the LXMERT box projection)", box_dim);
-  RGQA_CHECK(feat && W1 && b1 && g1 && be1 && boxes && W2p && b2 && g2 && be2 && bstat && hi && lo && stats, "visn_embed: null argument");
+  RGQA_CHECK(feat && W1 && b1 && g1 && be1 && boxes && W2p && b2 && g2 && be2 && bstat && hi && stats, "visn_embed: null argument");
   RGQA_CHECK(reinterpret_cast<uintptr_t>(hi) % 16 == 0 && reinterpret_cast<uintptr_t>(lo) % 16 == 0 &&
                  reinterpret_cast<uintptr_t>(stats) % 16 == 0 && reinterpret_cast<uintptr_t>(b1) % 16 == 0 &&
                  reinterpret_cast<uintptr_t>(W2p) % 16 == 0,

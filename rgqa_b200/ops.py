@@ -71,11 +71,19 @@ def linear_residual_layernorm_bf16(x, weight, bias, residual, gamma, beta, eps=1
     return out, out32
 
 
-def fold_layernorm_weight(weight, bias, gamma, beta):
+def fold_layernorm_weight(weight, bias, gamma, beta, dtype=torch.bfloat16):
     """(W' bf16 [N,K], c f32 [N], bias' f32 [N]) with the LayerNorm affine of the *input* folded into an nn.Linear:
-    LN(x)·Wᵀ + b = rstd·(x·W'ᵀ − mean·c) + bias', W' = bf16(W∘gamma − rowmean(W∘gamma)), c = rowsum(W') ≈ 0."""
+    LN(x)·Wᵀ + b = rstd·(x·W'ᵀ − mean·c) + bias', W' = bf16(W∘gamma − rowmean(W∘gamma)), c = rowsum(W') ≈ 0.
+    ``dtype=torch.float16``: W' rounded to fp16 instead (consumers of the single-word fp16 state)."""
     _need_cuda(weight, bias, gamma, beta)
     N, K = weight.shape
+    if dtype == torch.float16:
+        wf = torch.empty((N, K), dtype=torch.float16, device=weight.device)
+        c = torch.empty(N, dtype=torch.float32, device=weight.device)
+        b2 = torch.empty(N, dtype=torch.float32, device=weight.device)
+        L.check(L.load().rgqa_fold_ln_weight_f16(L.current_stream_ptr(), L.ptr(weight), L.ptr(bias), L.ptr(gamma), L.ptr(beta), N, K,
+                                                 L.ptr(wf), L.ptr(c), L.ptr(b2)), "rgqa_fold_ln_weight_f16")
+        return wf, c, b2
     wf = torch.empty((N, K), dtype=torch.bfloat16, device=weight.device)
     c = torch.empty(N, dtype=torch.float32, device=weight.device)
     b2 = torch.empty(N, dtype=torch.float32, device=weight.device)
@@ -116,6 +124,37 @@ def linear_residual_hilo(x, weight, bias, in_hi, in_lo, in_stats, in_gamma, in_b
                                         L.ptr(in_beta), eps, L.ptr(hi), L.ptr(lo), L.ptr(stats), M, N, K),
             "rgqa_gemm_bf16_resid_hl")
     return hi, lo, stats
+
+
+def linear_a16_folded(x_h, stats, w_folded, bias_folded, c=None, epilogue=L.EPI_BIAS, out_dtype=torch.bfloat16, eps=1e-12):
+    """:func:`linear_bf16_folded` over the single-word state: ``x_h`` fp16 [M,768] (A operand) against the fp16 folded weight;
+    ``stats`` None = plain epilogue(x_h·Wᵀ + b) (the identity state in front of the first layer)."""
+    _need_cuda(x_h, stats, w_folded, c, bias_folded)
+    assert x_h.dtype == torch.float16 and w_folded.dtype == torch.float16
+    M, K = x_h.shape
+    N = w_folded.shape[0]
+    out = torch.empty((M, N), dtype=out_dtype, device=x_h.device)
+    lib = L.load()
+    L.check(lib.rgqa_gemm_bf16_folded_a16(L.current_stream_ptr(), L.ptr(x_h), x_h.stride(0), L.ptr(w_folded), w_folded.stride(0),
+                                          L.ptr(bias_folded), L.ptr(out), out.stride(0), _dt(out), M, N, K, epilogue,
+                                          L.ptr(stats), L.ptr(c), eps), "rgqa_gemm_bf16_folded_a16")
+    return out
+
+
+def linear_residual_h16(x, weight, bias, in_h, in_stats, in_gamma, in_beta, eps=1e-12):
+    """Producer of the single-word deferred-LayerNorm state: v = x·Wᵀ + b + LN_prev(in_h); returns (h, stats) with
+    h = fp16(v) (saturating) and stats [M,6,2] = per-128-column (sum, sumsq) of the rounded row."""
+    _need_cuda(x, weight, bias, in_h, in_stats, in_gamma, in_beta)
+    assert in_h.dtype == torch.float16
+    M, K = x.shape
+    N = weight.shape[0]
+    h = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    stats = torch.empty((M, 6, 2), dtype=torch.float32, device=x.device)
+    lib = L.load()
+    L.check(lib.rgqa_gemm_bf16_resid_h16(L.current_stream_ptr(), L.ptr(x), x.stride(0), L.ptr(weight), weight.stride(0),
+                                         L.ptr(bias), L.ptr(in_h), L.ptr(in_stats), L.ptr(in_gamma), L.ptr(in_beta), eps,
+                                         L.ptr(h), L.ptr(stats), M, N, K), "rgqa_gemm_bf16_resid_h16")
+    return h, stats
 
 
 def linear_f32(x, weight, bias=None, epilogue=L.EPI_BIAS, residual=None):

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/rgqa_b200.h but not exported"
     assert set(L.SIGNATURES) == declared, set(L.SIGNATURES) ^ declared
-    assert lib.rgqa_abi_version() == L.ABI_VERSION == 2
+    assert lib.rgqa_abi_version() == L.ABI_VERSION == 3
 
 
 def test_no_cpu_path():
