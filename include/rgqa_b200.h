@@ -246,6 +246,9 @@ int rgqa_cast_f32_to_bf16(void* stream, const float* in, void* out, int64_t n);
  * input x [M, H] (src/lxrt/modeling.py:258-270); add may be NULL. */
 int rgqa_layernorm_bwd(void* stream, const float* dy, const float* x, const float* gamma, const float* add, float* dx, int M,
                        int H, float eps, float scale);
+/* rgqa_layernorm_bwd and rgqa_ln_param_grad (below) in ONE pass over (dy, x): dx written, dgamma / dbeta accumulated.  H = 768 or 1536. */
+int rgqa_layernorm_bwd_params(void* stream, const float* dy, const float* x, const float* gamma, const float* add, float* dx,
+                              float* dgamma, float* dbeta, int M, int H, float eps, float scale);
 /* erf-GELU (modeling.py:112-118) forward and backward on n elements; tanh backward from the OUTPUT y (BertPooler :575-581). */
 int rgqa_gelu_fwd(void* stream, const float* x, float* y, int64_t n);
 int rgqa_gelu_bwd(void* stream, const float* dy, const float* x, float* dx, int64_t n);
@@ -267,6 +270,8 @@ int rgqa_attention_dropout(void* stream, const float* q, int64_t ldq, const floa
 /* out bf16 [C, R] = transpose(in fp32 [R, C], row stride ld): operand re-layout + cast of the weight-gradient products
  * (dy^T x of src/tasks/gqa_conf.py:196's backward runs over the rows), one pass. */
 int rgqa_transpose_cast_bf16(void* stream, const float* in, int64_t ld, void* out, int R, int C);
+/* the same pass also ADDS the column sums of `in` to colsum [C] (the nn.Linear bias gradient of the dy being re-laid out). */
+int rgqa_transpose_cast_bf16_colsum(void* stream, const float* in, int64_t ld, void* out, int R, int C, float* colsum);
 /* y = x - noise * sign(grad), sign = +1 where grad >= 0 else -1: the input pre-processing step of ODIN and of the Mahalanobis
  * scorer with --noise (src/tasks/gqa_odin.py:118-120, src/tasks/gqa_maha.py:246-252); n fp32 elements. */
 int rgqa_sign_step(void* stream, const float* x, const float* grad, float* y, int64_t n, float noise);

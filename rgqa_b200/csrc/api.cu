@@ -1842,6 +1842,10 @@ int rgqa_layernorm_bwd(void* stream, const float* dy, const float* x, const floa
                        int H, float eps, float scale) {
   return layernorm_bwd(static_cast<cudaStream_t>(stream), dy, x, gamma, add, dx, M, H, eps, scale);
 }
+int rgqa_layernorm_bwd_params(void* stream, const float* dy, const float* x, const float* gamma, const float* add, float* dx,
+                              float* dgamma, float* dbeta, int M, int H, float eps, float scale) {
+  return layernorm_bwd_params(static_cast<cudaStream_t>(stream), dy, x, gamma, add, dx, dgamma, dbeta, M, H, eps, scale);
+}
 int rgqa_gelu_fwd(void* stream, const float* x, float* y, int64_t n) { return gelu_fwd(static_cast<cudaStream_t>(stream), x, y, n); }
 int rgqa_gelu_bwd(void* stream, const float* dy, const float* x, float* dx, int64_t n) {
   return gelu_bwd(static_cast<cudaStream_t>(stream), dy, x, dx, n);
@@ -1864,6 +1868,10 @@ int rgqa_attention_dropout(void* stream, const float* q, int64_t ldq, const floa
 int rgqa_transpose_cast_bf16(void* stream, const float* in, int64_t ld, void* out, int R, int C) {
   RGQA_CHECK(in && out, "rgqa_transpose_cast_bf16: null argument");
   return transpose_cast_bf16(static_cast<cudaStream_t>(stream), in, ld, out, R, C);
+}
+int rgqa_transpose_cast_bf16_colsum(void* stream, const float* in, int64_t ld, void* out, int R, int C, float* colsum) {
+  RGQA_CHECK(in && out && colsum, "rgqa_transpose_cast_bf16_colsum: null argument");
+  return transpose_cast_bf16(static_cast<cudaStream_t>(stream), in, ld, out, R, C, colsum);
 }
 int rgqa_sign_step(void* stream, const float* x, const float* grad, float* y, int64_t n, float noise) {
   RGQA_CHECK(x && grad && y, "rgqa_sign_step: null argument");

@@ -50,6 +50,75 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
   }
 }
 
+// layernorm_bwd + ln_param_grad in ONE pass over (dy, x): the training step calls them back to back on the same rows (61 pairs per
+// step).  A warp walks rows, keeps its per-column dgamma / dbeta partials in registers, the CTA merges them through shared-memory
+// atomics and issues ONE global atomic per column (the stand-alone ln_param_grad issues one per warp).
+template <int NV>  // NV = H / 32 columns per lane
+__global__ void __launch_bounds__(256)
+layernorm_bwd_params_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                            const float* __restrict__ add, float* __restrict__ dx, float* __restrict__ dgamma,
+                            float* __restrict__ dbeta, int M, float eps, float scale) {
+  constexpr int H = NV * 32;
+  __shared__ float sdg[H], sdb[H];
+  for (int c = threadIdx.x; c < H; c += 256) sdg[c] = sdb[c] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float gm[NV], dg[NV], db[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    gm[j] = gamma[lane + 32 * j];
+    dg[j] = db[j] = 0.f;
+  }
+  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+    const float* xr = x + static_cast<long long>(row) * H;
+    const float* dr = dy + static_cast<long long>(row) * H;
+    float xv[NV], gv[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      xv[j] = xr[lane + 32 * j];
+      gv[j] = dr[lane + 32 * j] * scale;
+      s += xv[j];
+    }
+    const float mu = warp_sum(s) / static_cast<float>(H);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      xv[j] -= mu;
+      q = fmaf(xv[j], xv[j], q);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(H) + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      xv[j] *= rstd;                        // xh
+      dg[j] = fmaf(gv[j], xv[j], dg[j]);    // parameter gradients see scale * dy
+      db[j] += gv[j];
+      gv[j] *= gm[j];                       // g = scale * dy * gamma
+      m1 += gv[j];
+      m2 = fmaf(gv[j], xv[j], m2);
+    }
+    m1 = warp_sum(m1) / static_cast<float>(H);
+    m2 = warp_sum(m2) / static_cast<float>(H);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float v = rstd * (gv[j] - m1 - xv[j] * m2);
+      if (add != nullptr) v += add[static_cast<long long>(row) * H + lane + 32 * j];
+      dx[static_cast<long long>(row) * H + lane + 32 * j] = v;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    atomicAdd(&sdg[lane + 32 * j], dg[j]);
+    atomicAdd(&sdb[lane + 32 * j], db[j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += 256) {
+    atomicAdd(dgamma + c, sdg[c]);
+    atomicAdd(dbeta + c, sdb[c]);
+  }
+}
+
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = gelu_erf(x[i]);
@@ -71,14 +140,31 @@ tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float
     dx[i] = dy[i] * (1.0f - y[i] * y[i]);
 }
 
-// one CTA per (sample, head); everything of the head lives in shared memory (Lq, Lk <= 64)
+// one CTA per (sample, head); everything of the head lives in shared memory (Lq, Lk <= 64).  Rows are staged at a stride of
+// 68 floats (16-byte aligned, four banks of skew per row: eight consecutive rows tile the 32 banks for float4 reads) and every
+// product is register-tiled 4 x 4 (scores / dP: 4 query rows x 4 key rows per thread, 32 FMAs per 16 LDS.128; dQ / dK / dV:
+// 4 rows x 4 columns, 16 - 32 FMAs per 2 - 5 loads) — the first version read two shared-memory words per FMA and ran at an
+// eighth of the FMA rate (119 us per launch at B = 128, L = 36).
+constexpr int BLD = 68;
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  return fmaf(a.w, b.w, acc);
+}
+__device__ __forceinline__ void axpy4(float4& acc, float s, const float4 x) {
+  acc.x = fmaf(s, x.x, acc.x);
+  acc.y = fmaf(s, x.y, acc.y);
+  acc.z = fmaf(s, x.z, acc.z);
+  acc.w = fmaf(s, x.w, acc.w);
+}
 __global__ void __launch_bounds__(256)
 attention_bwd_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k, long long ldk,
                      const float* __restrict__ v, long long ldv, const int32_t* __restrict__ key_mask,
                      const float* __restrict__ dctx, long long ldo, float* __restrict__ dq, long long lddq,
                      float* __restrict__ dk, long long lddk, float* __restrict__ dv, long long lddv, int Lq, int Lk, int heads,
-                     float drop_p, unsigned long long drop_seed) {
-  extern __shared__ float sm_bwd[];
+                     float drop_p, unsigned long long drop_seed, int vec) {
+  extern __shared__ __align__(16) float sm_bwd[];
   // attention-probability dropout of the forward (same counter-based mask): O = (P o M) V with M = keep / (1 - p)
   const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   auto mask_at = [&](int i, int j) -> float {
@@ -86,80 +172,179 @@ attention_bwd_kernel(const float* __restrict__ q, long long ldq, const float* __
     return dropout_keep(drop_seed, (static_cast<unsigned long long>(blockIdx.x) * Lq + i) * Lk + j, drop_p) ? keep_scale : 0.f;
   };
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
-  float* Qs = sm_bwd;                 // [Lq][65]
-  float* Ks = Qs + Lq * 65;           // [Lk][65]
-  float* Vs = Ks + Lk * 65;           // [Lk][65]
-  float* Os = Vs + Lk * 65;           // dO [Lq][65]
-  float* P = Os + Lq * 65;            // [Lq][Lk + 1]
-  float* dS = P + Lq * (Lk + 1);      // [Lq][Lk + 1]
+  float* Qs = sm_bwd;               // [Lq][BLD]
+  float* Ks = Qs + Lq * BLD;        // [Lk][BLD]
+  float* Vs = Ks + Lk * BLD;        // [Lk][BLD]
+  float* Os = Vs + Lk * BLD;        // dO [Lq][BLD]
+  float* P = Os + Lq * BLD;         // [Lq][BLD] scores, then probabilities
+  float* dS = P + Lq * BLD;         // [Lq][BLD] dP o M, then dS
   const int tid = threadIdx.x;
-  for (int e = tid; e < Lq * HD; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    Qs[r * 65 + c] = q[(static_cast<long long>(b) * Lq + r) * ldq + h * HD + c];
-    Os[r * 65 + c] = dctx[(static_cast<long long>(b) * Lq + r) * ldo + h * HD + c];
-  }
-  for (int e = tid; e < Lk * HD; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    Ks[r * 65 + c] = k[(static_cast<long long>(b) * Lk + r) * ldk + h * HD + c];
-    Vs[r * 65 + c] = v[(static_cast<long long>(b) * Lk + r) * ldv + h * HD + c];
+  const float* qg = q + static_cast<long long>(b) * Lq * ldq + h * HD;
+  const float* og = dctx + static_cast<long long>(b) * Lq * ldo + h * HD;
+  const float* kg = k + static_cast<long long>(b) * Lk * ldk + h * HD;
+  const float* vg = v + static_cast<long long>(b) * Lk * ldv + h * HD;
+  if (vec) {
+    for (int e = tid; e < Lq * 16; e += 256) {
+      const int r = e >> 4, c = (e & 15) * 4;
+      *reinterpret_cast<float4*>(Qs + r * BLD + c) = *reinterpret_cast<const float4*>(qg + r * ldq + c);
+      *reinterpret_cast<float4*>(Os + r * BLD + c) = *reinterpret_cast<const float4*>(og + r * ldo + c);
+    }
+    for (int e = tid; e < Lk * 16; e += 256) {
+      const int r = e >> 4, c = (e & 15) * 4;
+      *reinterpret_cast<float4*>(Ks + r * BLD + c) = *reinterpret_cast<const float4*>(kg + r * ldk + c);
+      *reinterpret_cast<float4*>(Vs + r * BLD + c) = *reinterpret_cast<const float4*>(vg + r * ldv + c);
+    }
+  } else {
+    for (int e = tid; e < Lq * HD; e += 256) {
+      const int r = e >> 6, c = e & 63;
+      Qs[r * BLD + c] = qg[r * ldq + c];
+      Os[r * BLD + c] = og[r * ldo + c];
+    }
+    for (int e = tid; e < Lk * HD; e += 256) {
+      const int r = e >> 6, c = e & 63;
+      Ks[r * BLD + c] = kg[r * ldk + c];
+      Vs[r * BLD + c] = vg[r * ldv + c];
+    }
   }
   __syncthreads();
-  // scores + additive mask (modeling.py:333-336) and dP = dO V^T
-  for (int e = tid; e < Lq * Lk; e += 256) {
-    const int i = e / Lk, j = e % Lk;
-    float s = 0.f, dp = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < HD; ++c) {
-      s = fmaf(Qs[i * 65 + c], Ks[j * 65 + c], s);
-      dp = fmaf(Os[i * 65 + c], Vs[j * 65 + c], dp);
+  const int nI = (Lq + 3) >> 2, nJ = (Lk + 3) >> 2;
+  // scores + additive mask (modeling.py:333-336) and dP = dO V^T.  Thread tile: rows i = ti + nI * ii, keys j = tj + nJ * jj
+  // (interleaved, so that the lanes of a warp read CONSECUTIVE K / V rows: conflict-free float4 reads)
+  if (tid < nI * nJ) {
+    const int ti = tid / nJ, tj = tid - ti * nJ;
+    int ri[4], rj[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      ri[a] = min(ti + nI * a, Lq - 1);   // rows past the end recompute the last one; nothing is stored for them
+      rj[a] = min(tj + nJ * a, Lk - 1);
     }
-    s *= 0.125f;
-    if (key_mask != nullptr && key_mask[b * Lk + j] == 0) s += -10000.0f;
-    P[i * (Lk + 1) + j] = s;
-    dS[i * (Lk + 1) + j] = dp * mask_at(i, j);   // d loss / d P (the gradient reaches P through the dropout mask)
+    float s[4][4], dp[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[a][c] = dp[a][c] = 0.f;
+#pragma unroll 2
+    for (int c4 = 0; c4 < 16; ++c4) {
+      float4 q4[4], o4[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        q4[a] = *reinterpret_cast<const float4*>(Qs + ri[a] * BLD + c4 * 4);
+        o4[a] = *reinterpret_cast<const float4*>(Os + ri[a] * BLD + c4 * 4);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 k4 = *reinterpret_cast<const float4*>(Ks + rj[c] * BLD + c4 * 4);
+        const float4 v4 = *reinterpret_cast<const float4*>(Vs + rj[c] * BLD + c4 * 4);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          s[a][c] = dot4(q4[a], k4, s[a][c]);
+          dp[a][c] = dot4(o4[a], v4, dp[a][c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = ti + nI * a;
+      if (i >= Lq) continue;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = tj + nJ * c;
+        if (j >= Lk) continue;
+        float sc = s[a][c] * 0.125f;
+        if (key_mask != nullptr && key_mask[b * Lk + j] == 0) sc += -10000.0f;
+        P[i * BLD + j] = sc;
+        dS[i * BLD + j] = dp[a][c] * mask_at(i, j);   // d loss / d P (the gradient reaches P through the dropout mask)
+      }
+    }
   }
   __syncthreads();
   // row softmax, then dS = P (dP - sum_j dP P): one warp per row
   for (int i = tid >> 5; i < Lq; i += 8) {
     const int lane = tid & 31;
     float mx = -INFINITY;
-    for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, P[i * (Lk + 1) + j]);
+    for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, P[i * BLD + j]);
     mx = warp_max(mx);
     float sum = 0.f;
     for (int j = lane; j < Lk; j += 32) {
-      const float p = expf(P[i * (Lk + 1) + j] - mx);
-      P[i * (Lk + 1) + j] = p;
+      const float p = expf(P[i * BLD + j] - mx);
+      P[i * BLD + j] = p;
       sum += p;
     }
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
     float dot = 0.f;
     for (int j = lane; j < Lk; j += 32) {
-      const float p = P[i * (Lk + 1) + j] * inv;
-      P[i * (Lk + 1) + j] = p;
-      dot = fmaf(dS[i * (Lk + 1) + j], p, dot);
+      const float p = P[i * BLD + j] * inv;
+      P[i * BLD + j] = p;
+      dot = fmaf(dS[i * BLD + j], p, dot);
     }
     dot = warp_sum(dot);
-    for (int j = lane; j < Lk; j += 32) dS[i * (Lk + 1) + j] = P[i * (Lk + 1) + j] * (dS[i * (Lk + 1) + j] - dot);
+    for (int j = lane; j < Lk; j += 32) {
+      dS[i * BLD + j] = P[i * BLD + j] * (dS[i * BLD + j] - dot);
+      if (drop_p > 0.f) P[i * BLD + j] *= mask_at(i, j);   // dV sees the dropped probabilities
+    }
+    // the float4 reads of the dK / dV pass run up to three keys past Lk: zero them (a stale NaN times zero would still be NaN)
+    for (int j = Lk + lane; j < ((Lk + 3) & ~3); j += 32) P[i * BLD + j] = dS[i * BLD + j] = 0.f;
   }
   __syncthreads();
-  // dQ = dS K / 8
-  for (int e = tid; e < Lq * HD; e += 256) {
-    const int i = e >> 6, c = e & 63;
-    float a = 0.f;
-    for (int j = 0; j < Lk; ++j) a = fmaf(dS[i * (Lk + 1) + j], Ks[j * 65 + c], a);
-    dq[(static_cast<long long>(b) * Lq + i) * lddq + h * HD + c] = a * 0.125f;
-  }
-  // dK = dS^T Q / 8, dV = P^T dO
-  for (int e = tid; e < Lk * HD; e += 256) {
-    const int j = e >> 6, c = e & 63;
-    float a = 0.f, g = 0.f;
-    for (int i = 0; i < Lq; ++i) {
-      a = fmaf(dS[i * (Lk + 1) + j], Qs[i * 65 + c], a);
-      g = fmaf(P[i * (Lk + 1) + j] * mask_at(i, j), Os[i * 65 + c], g);
+  // dQ = dS K / 8: 4 query rows x 4 columns per thread
+  if (tid < nI * 16) {
+    const int ti = tid >> 4, c0 = (tid & 15) * 4;
+    int ri[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) ri[a] = min(ti + nI * a, Lq - 1);
+    float4 acc[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int j = 0; j < Lk; ++j) {
+      const float4 k4 = *reinterpret_cast<const float4*>(Ks + j * BLD + c0);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) axpy4(acc[a], dS[ri[a] * BLD + j], k4);
     }
-    dk[(static_cast<long long>(b) * Lk + j) * lddk + h * HD + c] = a * 0.125f;
-    dv[(static_cast<long long>(b) * Lk + j) * lddv + h * HD + c] = g;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = ti + nI * a;
+      if (i >= Lq) continue;
+      float* dst = dq + (static_cast<long long>(b) * Lq + i) * lddq + h * HD + c0;
+      const float4 o = make_float4(acc[a].x * 0.125f, acc[a].y * 0.125f, acc[a].z * 0.125f, acc[a].w * 0.125f);
+      if (vec) {
+        *reinterpret_cast<float4*>(dst) = o;
+      } else {
+        dst[0] = o.x; dst[1] = o.y; dst[2] = o.z; dst[3] = o.w;
+      }
+    }
+  }
+  // dK = dS^T Q / 8, dV = (P o M)^T dO: 4 consecutive keys x 4 columns per thread
+  if (tid < nJ * 16) {
+    const int j0 = (tid >> 4) * 4, c0 = (tid & 15) * 4;
+    float4 ak[4], av[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) ak[a] = av[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int i = 0; i < Lq; ++i) {
+      const float4 ds4 = *reinterpret_cast<const float4*>(dS + i * BLD + j0);
+      const float4 p4 = *reinterpret_cast<const float4*>(P + i * BLD + j0);
+      const float4 q4 = *reinterpret_cast<const float4*>(Qs + i * BLD + c0);
+      const float4 o4 = *reinterpret_cast<const float4*>(Os + i * BLD + c0);
+      axpy4(ak[0], ds4.x, q4); axpy4(ak[1], ds4.y, q4); axpy4(ak[2], ds4.z, q4); axpy4(ak[3], ds4.w, q4);
+      axpy4(av[0], p4.x, o4); axpy4(av[1], p4.y, o4); axpy4(av[2], p4.z, o4); axpy4(av[3], p4.w, o4);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int j = j0 + a;
+      if (j >= Lk) continue;
+      float* dkp = dk + (static_cast<long long>(b) * Lk + j) * lddk + h * HD + c0;
+      float* dvp = dv + (static_cast<long long>(b) * Lk + j) * lddv + h * HD + c0;
+      const float4 okk = make_float4(ak[a].x * 0.125f, ak[a].y * 0.125f, ak[a].z * 0.125f, ak[a].w * 0.125f);
+      if (vec) {
+        *reinterpret_cast<float4*>(dkp) = okk;
+        *reinterpret_cast<float4*>(dvp) = av[a];
+      } else {
+        dkp[0] = okk.x; dkp[1] = okk.y; dkp[2] = okk.z; dkp[3] = okk.w;
+        dvp[0] = av[a].x; dvp[1] = av[a].y; dvp[2] = av[a].z; dvp[3] = av[a].w;
+      }
+    }
   }
 }
 
@@ -188,6 +373,23 @@ int layernorm_bwd(cudaStream_t stream, const float* dy, const float* x, const fl
                   int H, float eps, float scale) {
   RGQA_CHECK(dy && x && gamma && dx && M > 0 && H > 0, "layernorm_bwd: bad arguments");
   layernorm_bwd_kernel<<<(M + 3) / 4, 128, 0, stream>>>(dy, x, gamma, add, dx, M, H, eps, scale);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int layernorm_bwd_params(cudaStream_t stream, const float* dy, const float* x, const float* gamma, const float* add, float* dx,
+                         float* dgamma, float* dbeta, int M, int H, float eps, float scale) {
+  RGQA_CHECK(dy && x && gamma && dx && dgamma && dbeta && M > 0, "layernorm_bwd_params: bad arguments");
+  int grid = (M + 7) / 8;
+  if (grid > 148 * 2) grid = 148 * 2;
+  if (H == 768)
+    layernorm_bwd_params_kernel<24><<<grid, 256, 0, stream>>>(dy, x, gamma, add, dx, dgamma, dbeta, M, eps, scale);
+  else if (H == 1536)
+    layernorm_bwd_params_kernel<48><<<grid, 256, 0, stream>>>(dy, x, gamma, add, dx, dgamma, dbeta, M, eps, scale);
+  else {
+    set_error("layernorm_bwd_params: unsupported width %d (768 or 1536)", H);
+    return 1;
+  }
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;
@@ -227,14 +429,16 @@ int attention_bwd(cudaStream_t stream, const float* q, long long ldq, const floa
   RGQA_CHECK(q && k && v && dctx && dq && dk && dv, "attention_bwd: null argument");
   RGQA_CHECK(drop_p >= 0.f && drop_p < 1.f, "attention_bwd: dropout probability out of range");
   RGQA_CHECK(B > 0 && heads > 0 && Lq >= 1 && Lq <= 64 && Lk >= 1 && Lk <= 64, "attention_bwd: Lq=%d Lk=%d out of range [1,64]", Lq, Lk);
-  const size_t smem = (static_cast<size_t>(2 * Lq + 2 * Lk) * 65 + 2 * static_cast<size_t>(Lq) * (Lk + 1)) * sizeof(float);
+  const size_t smem = static_cast<size_t>(4 * Lq + 2 * Lk) * BLD * sizeof(float);
+  auto al16 = [](const void* p, long long ld) { return reinterpret_cast<uintptr_t>(p) % 16 == 0 && ld % 4 == 0; };
+  const int vec = (al16(q, ldq) && al16(k, ldk) && al16(v, ldv) && al16(dctx, ldo) && al16(dq, lddq) && al16(dk, lddk) && al16(dv, lddv)) ? 1 : 0;
   static bool cfg = false;
   if (!cfg) {
     RGQA_CUDA_OK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     cfg = true;
   }
   attention_bwd_kernel<<<B * heads, 256, smem, stream>>>(q, ldq, k, ldk, v, ldv, key_mask, dctx, ldo, dq, lddq, dk, lddk, dv, lddv,
-                                                         Lq, Lk, heads, drop_p, drop_seed);
+                                                         Lq, Lk, heads, drop_p, drop_seed, vec);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;

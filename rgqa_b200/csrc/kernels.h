@@ -162,7 +162,8 @@ int cast_f32_to_f16(cudaStream_t stream, const float* in, void* out, long long n
 // evaluates the product to ~16 mantissa bits per operand (the tensor-core Mahalanobis)
 int split_bf16x3(cudaStream_t stream, const float* in, long long ld, void* out, long long M, int K, int weight_side);
 // fp32 [R, C] (row stride ld) -> bf16 [C, R] in one pass (operands of the weight-gradient GEMMs)
-int transpose_cast_bf16(cudaStream_t stream, const float* in, long long ld, void* out, int R, int C);
+// colsum != nullptr: colsum[c] += sum_r in[r, c] as well (the bias gradient rides on the same read)
+int transpose_cast_bf16(cudaStream_t stream, const float* in, long long ld, void* out, int R, int C, float* colsum = nullptr);
 int cast_bf16_to_f32(cudaStream_t stream, const void* in, float* out, long long n);
 // copy rows: dst[r, :] = src[r*src_stride_rows .. ] for r < rows (strided gather of whole rows)
 int gather_rows(cudaStream_t stream, int dtype, const void* src, long long src_ld, void* dst, long long dst_ld,
@@ -179,6 +180,9 @@ enum ScoreMode : int {
 // input-gradient (dgrad) kernels of the fp32 path (backward.cu)
 int layernorm_bwd(cudaStream_t stream, const float* dy, const float* x, const float* gamma, const float* add, float* dx, int M,
                   int H, float eps, float scale);
+// layernorm_bwd and ln_param_grad (below) in one pass over (dy, x): dx as above, dgamma / dbeta ACCUMULATED
+int layernorm_bwd_params(cudaStream_t stream, const float* dy, const float* x, const float* gamma, const float* add, float* dx,
+                         float* dgamma, float* dbeta, int M, int H, float eps, float scale);
 int gelu_fwd(cudaStream_t stream, const float* x, float* y, long long n);
 int gelu_bwd(cudaStream_t stream, const float* dy, const float* x, float* dx, long long n);
 int tanh_bwd(cudaStream_t stream, const float* dy, const float* y, float* dx, long long n);

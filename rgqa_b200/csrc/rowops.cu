@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restri
 // 14 of a transposing copy followed by a cast.  64 x 32 tiles through padded shared memory: 128-byte reads along C, 128-byte
 // bf16x2 writes along R.
 __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ in, long long ld, __nv_bfloat16* __restrict__ out,
-                                                             int R, int C) {
+                                                             int R, int C, float* __restrict__ colsum) {
   __shared__ float tile[32][65];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -392,6 +392,13 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __rest
     tile[tx][ty + 8 * i] = (r < R && c < C) ? in[static_cast<long long>(r) * ld + c] : 0.f;
   }
   __syncthreads();
+  // optional column sums of the fp32 input (the bias gradient of the same nn.Linear: its dy is read here anyway)
+  if (colsum != nullptr && ty == 0 && c0 + tx < C) {
+    float s = 0.f;
+#pragma unroll 16
+    for (int r = 0; r < 64; ++r) s += tile[tx][r];
+    atomicAdd(colsum + c0 + tx, s);
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = c0 + ty + 8 * i, r = r0 + 2 * tx;
@@ -545,10 +552,10 @@ int split_bf16x3(cudaStream_t stream, const float* in, long long ld, void* out, 
   return 0;
 }
 
-int transpose_cast_bf16(cudaStream_t stream, const float* in, long long ld, void* out, int R, int C) {
+int transpose_cast_bf16(cudaStream_t stream, const float* in, long long ld, void* out, int R, int C, float* colsum) {
   RGQA_CHECK(R > 0 && C > 0 && ld >= C, "transpose_cast_bf16: bad shape R=%d C=%d ld=%lld", R, C, ld);
   RGQA_CHECK(reinterpret_cast<uintptr_t>(out) % 4 == 0, "transpose_cast_bf16: unaligned output");
-  transpose_cast_kernel<<<dim3((C + 31) / 32, (R + 63) / 64), 256, 0, stream>>>(in, ld, static_cast<__nv_bfloat16*>(out), R, C);
+  transpose_cast_kernel<<<dim3((C + 31) / 32, (R + 63) / 64), 256, 0, stream>>>(in, ld, static_cast<__nv_bfloat16*>(out), R, C, colsum);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;

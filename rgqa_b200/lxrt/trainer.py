@@ -147,15 +147,19 @@ class LXMERTTrainer:
             return ops.linear_bf16(ops.cast_bf16(x.contiguous()), wb, b, epilogue=epilogue, residual=residual, out_dtype=torch.float32)
         return ops.linear_f32(x, w, b, epilogue=epilogue, residual=residual)
 
-    def _wgrad(self, wname, dy, x):
-        """G[w] += dyᵀ · x, G[b] += colsum(dy)."""
+    def _wgrad(self, wname, dy, x, xt=None):
+        """G[w] += dyᵀ · x, G[b] += colsum(dy).  ``xt``: a one-element list caching the bf16 transpose of x across calls that share x."""
         gw, gb = self.g[wname + ".weight"], self.g[wname + ".bias"]
         M = dy.shape[0]
         if self.gemm == "bf16" and M % 64 == 0 and M >= 64 and x.shape[1] >= 64 and dy.shape[1] >= 64:
-            a = ops.transpose_cast_bf16(dy)                  # [N, M]: the product runs over the rows
-            bt = ops.transpose_cast_bf16(x)                  # [K, M]   (transposing copy + cast in one pass)
+            a = ops.transpose_cast_bf16(dy, colsum_into=gb)  # [N, M]: the product runs over the rows; G[b] rides on the same read of dy
+            if xt is not None and xt:
+                bt = xt[0]
+            else:
+                bt = ops.transpose_cast_bf16(x)              # [K, M]   (transposing copy + cast in one pass)
+                if xt is not None:
+                    xt.append(bt)
             ops.linear_bf16(a, bt, None, epilogue=L.EPI_RESID, residual=gw, out_dtype=torch.float32, out=gw)
-            ops.linear_wgrad_bias_(gb, dy)
         else:
             ops.linear_wgrad_(gw, gb, dy, x)
 
@@ -264,6 +268,9 @@ class LXMERTTrainer:
         return self._mm(dy, wt() if callable(wt) else wt, None, epilogue=epi, residual=residual, wkey=("t", name))
 
     def _ln_bwd(self, name, dy, x, scale=1.0):
+        if x.shape[1] in (768, 1536):     # one pass over (dy, x): dx and both parameter gradients
+            return ops.layernorm_bwd_params_(self.g[name + ".weight"], self.g[name + ".bias"], dy, x, self.p[name + ".weight"],
+                                             eps=self.eps, scale=scale)
         ops.layernorm_param_grad_(self.g[name + ".weight"], self.g[name + ".bias"], dy, x, self.eps, scale)
         return ops.layernorm_bwd(dy, x, self.p[name + ".weight"], eps=self.eps, scale=scale)
 
@@ -286,8 +293,9 @@ class LXMERTTrainer:
 
     def _qkv_wgrad(self, a, dqkv, x):
         H = dqkv.shape[1] // 3
+        xt = []                                               # Q, K and V share their input: transpose it once
         for j, name in enumerate((a.q, a.k, a.v)):
-            self._wgrad(name, dqkv[:, j * H:(j + 1) * H], x)
+            self._wgrad(name, dqkv[:, j * H:(j + 1) * H], x, xt)
 
     def _self_att_bwd(self, a, tp, dy):
         dqkv = torch.empty_like(tp["qkv_q"])

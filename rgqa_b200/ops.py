@@ -240,12 +240,18 @@ def cast_bf16(x):
     return out
 
 
-def transpose_cast_bf16(x):
-    """bf16 [C, R] = x.t() for fp32 x [R, C] (any row stride): transposing copy + cast in one kernel."""
-    _need_cuda(x)
+def transpose_cast_bf16(x, colsum_into=None):
+    """bf16 [C, R] = x.t() for fp32 x [R, C] (any row stride): transposing copy + cast in one kernel.  ``colsum_into`` [C] f32:
+    the column sums of x are ADDED to it in the same pass (the bias gradient of the nn.Linear whose dy is x)."""
+    _need_cuda(x, colsum_into)
     assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
     R, C = x.shape
     out = torch.empty((C, R), dtype=torch.bfloat16, device=x.device)
+    if colsum_into is not None:
+        assert colsum_into.dtype == torch.float32 and colsum_into.is_contiguous() and colsum_into.shape == (C,)
+        L.check(L.load().rgqa_transpose_cast_bf16_colsum(L.current_stream_ptr(), L.ptr(x), x.stride(0), L.ptr(out), R, C,
+                                                         L.ptr(colsum_into)), "rgqa_transpose_cast_bf16_colsum")
+        return out
     L.check(L.load().rgqa_transpose_cast_bf16(L.current_stream_ptr(), L.ptr(x), x.stride(0), L.ptr(out), R, C), "rgqa_transpose_cast_bf16")
     return out
 
@@ -326,6 +332,18 @@ def layernorm_bwd(dy, x, gamma, add=None, eps=1e-12, scale=1.0):
     dx = torch.empty_like(x)
     L.check(L.load().rgqa_layernorm_bwd(L.current_stream_ptr(), L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(add), L.ptr(dx), M, H,
                                         eps, scale), "rgqa_layernorm_bwd")
+    return dx
+
+
+def layernorm_bwd_params_(dgamma, dbeta, dy, x, gamma, add=None, eps=1e-12, scale=1.0):
+    """:func:`layernorm_bwd` and :func:`layernorm_param_grad_` in one pass: returns dx, ADDS to dgamma / dbeta (H = 768 / 1536)."""
+    _need_cuda(dy, x, gamma, add, dgamma, dbeta)
+    assert dy.dtype == x.dtype == torch.float32 and dy.shape == x.shape and dy.is_contiguous() and x.is_contiguous()
+    assert add is None or (add.is_contiguous() and add.shape == x.shape)
+    M, H = x.shape
+    dx = torch.empty_like(x)
+    L.check(L.load().rgqa_layernorm_bwd_params(L.current_stream_ptr(), L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(add), L.ptr(dx),
+                                               L.ptr(dgamma), L.ptr(dbeta), M, H, eps, scale), "rgqa_layernorm_bwd_params")
     return dx
 
 

@@ -294,3 +294,83 @@ def test_transpose_cast_kernel(cuda_device, R, C, ld):
     x = base[:, ld - C:] if ld > C else base
     y = ops.transpose_cast_bf16(x)
     assert y.shape == (C, R) and torch.equal(y, x.t().contiguous().to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,Lq,Lk,masked", [(3, 20, 20, True), (2, 36, 36, False), (2, 20, 36, False), (2, 36, 20, True),
+                                            (1, 64, 64, True), (2, 17, 7, True), (1, 1, 5, False), (2, 56, 56, True)])
+def test_attention_backward_kernel_against_autograd(cuda_device, B, Lq, Lk, masked):
+    """dQ / dK / dV of softmax(QK^T/8 + mask) V (src/lxrt/modeling.py:330-346) for every (Lq, Lk) of the path, ragged lengths
+    (not multiples of the 4 x 4 register tile) and the 64-row maximum, against torch autograd in fp64."""
+    from rgqa_b200 import ops
+    heads, H = 12, 768
+    g = torch.Generator().manual_seed(B * 1000 + Lq * 10 + Lk)
+    qkv_q = torch.randn(B * Lq, 3 * H, generator=g).to(cuda_device)
+    qkv_kv = torch.randn(B * Lk, 3 * H, generator=g).to(cuda_device)
+    mask = None
+    if masked:
+        lens = torch.randint(1, Lk + 1, (B,), generator=g)
+        mask = (torch.arange(Lk)[None, :] < lens[:, None]).to(torch.int32).to(cuda_device)
+    dctx = torch.randn(B * Lq, H, generator=g).to(cuda_device)
+    q = qkv_q[:, :H].double().clone().requires_grad_(True)
+    k = qkv_kv[:, H:2 * H].double().clone().requires_grad_(True)
+    v = qkv_kv[:, 2 * H:].double().clone().requires_grad_(True)
+    ql, kl, vl = (t.view(B, -1, heads, 64).permute(0, 2, 1, 3) for t in (q, k, v))
+    s = torch.matmul(ql, kl.transpose(-1, -2)) / 8.0
+    if mask is not None:
+        s = s + ((1.0 - mask.double()) * -10000.0)[:, None, None, :]
+    ref = torch.matmul(torch.softmax(s, dim=-1), vl).permute(0, 2, 1, 3).reshape(B * Lq, H)
+    (ref * dctx.double()).sum().backward()
+    dqkv_q = torch.full_like(qkv_q, float("nan"))
+    dqkv_kv = torch.full_like(qkv_kv, float("nan"))
+    ops.attention_bwd(qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv, B, Lq, Lk, key_mask=mask, heads=heads)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dqkv_q[:, :H].double(), q.grad, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(dqkv_kv[:, H:2 * H].double(), k.grad, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(dqkv_kv[:, 2 * H:].double(), v.grad, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("M,H,with_add", [(2560, 768, False), (4608, 768, True), (37, 768, True), (128, 1536, False)])
+def test_layernorm_backward_with_parameter_gradients_in_one_pass(cuda_device, M, H, with_add):
+    """rgqa_layernorm_bwd_params == rgqa_layernorm_bwd + rgqa_ln_param_grad (BertLayerNorm backward, src/lxrt/modeling.py:258-270)
+    and both against torch autograd in fp64."""
+    from rgqa_b200 import ops
+    g = torch.Generator().manual_seed(M + H)
+    x = (torch.randn(M, H, generator=g) * 1.7 + 0.3).to(cuda_device)
+    dy = torch.randn(M, H, generator=g).to(cuda_device)
+    gamma = (1 + 0.1 * torch.randn(H, generator=g)).to(cuda_device)
+    add = torch.randn(M, H, generator=g).to(cuda_device) if with_add else None
+    dg0 = torch.randn(H, generator=g).to(cuda_device)          # the kernels ACCUMULATE into the parameter gradients
+    db0 = torch.randn(H, generator=g).to(cuda_device)
+    dg, db = dg0.clone(), db0.clone()
+    dx = ops.layernorm_bwd_params_(dg, db, dy, x, gamma, add=add, scale=0.5)
+    dg2, db2 = dg0.clone(), db0.clone()
+    ops.layernorm_param_grad_(dg2, db2, dy, x, 1e-12, 0.5)
+    dx2 = ops.layernorm_bwd(dy, x, gamma, add=add, scale=0.5)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dx, dx2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(dg, dg2, rtol=1e-4, atol=2e-3)   # summation order of M rows (float atomics)
+    torch.testing.assert_close(db, db2, rtol=1e-4, atol=2e-3)
+    xd = x.double().requires_grad_(True)
+    gd = gamma.double().requires_grad_(True)
+    bd = torch.zeros(H, dtype=torch.float64, device=cuda_device, requires_grad=True)
+    y = torch.nn.functional.layer_norm(xd, (H,), gd, bd, eps=1e-12)
+    (y * dy.double() * 0.5).sum().backward()
+    want_dx = xd.grad + (add.double() if with_add else 0.0)
+    torch.testing.assert_close(dx.double(), want_dx, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close((dg - dg0).double(), gd.grad, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close((db - db0).double(), bd.grad, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("R,C,ld", [(2560, 768, 768), (4608, 768, 2304), (130, 70, 70), (64, 3072, 3072)])
+def test_transpose_cast_kernel_with_column_sums(cuda_device, R, C, ld):
+    """The bias gradient rides on the re-layout of dy: colsum += sum over rows, same bf16 transpose."""
+    from rgqa_b200 import ops
+    g = torch.Generator().manual_seed(R + C + 1)
+    base = torch.randn(R, ld, generator=g).to(cuda_device)
+    x = base[:, ld - C:] if ld > C else base
+    acc0 = torch.randn(C, generator=g).to(cuda_device)
+    acc = acc0.clone()
+    y = ops.transpose_cast_bf16(x, colsum_into=acc)
+    torch.cuda.synchronize()
+    assert torch.equal(y, x.t().contiguous().to(torch.bfloat16))
+    torch.testing.assert_close((acc - acc0).double(), x.double().sum(0), rtol=1e-5, atol=2e-4)
