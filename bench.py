@@ -245,6 +245,15 @@ def parity_block(model, eng, dev, batch_dev, batch_host, mu, P, precision, rows=
     return par
 
 
+DTYPE_DETAIL = {
+    "bf16": "16-bit tensor-core operands, fp32 accumulation (tcgen05 kind::f16): weights, attention context, GELU intermediates and "
+            "Q|K|V in bf16; the pre-LayerNorm hidden state — A operand of the Q|K|V / FFN1 / pooler GEMMs — and the copies of those "
+            "GEMMs' folded weights in fp16 (11 instead of 8 significand bits, saturating; option state_f16, extra.all_bf16_hilo_state "
+            "is the all-bf16 variant); LayerNorm / softmax statistics, pooled output, logits and scores fp32",
+    "fp32": "fp32 end to end on the CUDA cores",
+}
+
+
 def uniter_extra(dev, steps=6):
     """BASELINE configs[2] next to the headline: UNITER-base (12 layers over the joint 56-token sequence), B = 1024, forward +
     MSP through rgqa_forward_scored, device-resident inputs; 9.7511 GFLOP / question."""
@@ -480,6 +489,32 @@ def run_ours(a):
     extra = None
     if rank == 0 and world == 1 and not a.no_extra and B == 1024:
         extra = uniter_extra(dev)
+        if a.precision == "bf16" and "state_f16=0" not in os.environ.get("RGQA_OPTS", ""):
+            # the same step with every GEMM operand in bf16 (the deferred-LayerNorm state as a bf16 hi/lo pair instead of one fp16
+            # word per element): a second handle finalized with state_f16 = 0, same weights, same resident batches
+            L.check(lib.rgqa_set_option(b"state_f16", 0), "rgqa_set_option")
+            try:
+                model_hl = GQAModel_maha(1842, args=Ns, max_seq_length=a.seq_len)
+                model_hl.load_state_dict(syn.lxmert_state_dict(seed=9595, variant="init"), strict=True)
+                model_hl = model_hl.to(dev)
+                model_hl.engine().set_maha(mu, P)
+                runner_hl = SweepRunner(model_hl, methods, device=dev)
+                for i in range(4 + a.warmup):
+                    runner_hl.score_device_batch(*resident[i & 1])
+                torch.cuda.synchronize()
+                h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                h0.record()
+                for i in range(a.steps):
+                    runner_hl.score_device_batch(*resident[i & 1])
+                h1.record()
+                torch.cuda.synchronize()
+                ms_hl = h0.elapsed_time(h1) / a.steps
+                extra["all_bf16_hilo_state"] = {"value": B / (ms_hl * 1e-3), "unit": "questions/s", "ms_per_step": ms_hl,
+                                                "what": "same workload with rgqa_set_option('state_f16', 0): hidden state as a bf16 hi/lo "
+                                                        "pair, every GEMM bf16 x bf16 (the round-2a build)"}
+                del runner_hl, model_hl
+            finally:
+                L.check(lib.rgqa_set_option(b"state_f16", 1), "rgqa_set_option")
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -489,7 +524,7 @@ def run_ours(a):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "questions/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
+                "vs_baseline": None, "dtype": a.precision, "dtype_detail": DTYPE_DETAIL.get(a.precision, a.precision), "data": "synthetic",
                 "config": {"workload": "LXMERT-base 9/5/5 GQA eval forward + energy(top-2) + Mahalanobis scoring "
                                        f"(BASELINE.json configs[1]), B={B} questions per GPU per step, L={Lq}, 36x2048 RoI, "
                                        "random-init seed 9595",

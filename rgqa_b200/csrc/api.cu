@@ -1700,6 +1700,10 @@ int rgqa_set_option(const char* name, int value) {
     option_set(OPT_ATTN_FUSED, value);
     return 0;
   }
+  if (strcmp(name, "gelu_ew16") == 0) {
+    option_set(OPT_GELU_EW16, value);
+    return 0;
+  }
   if (strcmp(name, "state_f16") == 0) {
     option_set(OPT_STATE_F16, value);
     return 0;

@@ -1179,13 +1179,12 @@ int dispatch_epi(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, con
   }
 }
 
-template <int EPI, typename OutT, bool STAGED, int RING = kResidRing>
+template <int EPI, typename OutT, bool STAGED, int RING = kResidRing, int EW = 8>
 int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                 const CUtensorMap& tmRes, const GemmParams& p, const CUtensorMap* tmOutLo = nullptr,
                 const CUtensorMap* tmResLo = nullptr) {
   // 16 epilogue warps were measured on B200 (bf16 outputs): FFN1 1043 vs 1056 TFLOP/s, QKV 1180 vs 1274 — no gain,
   // the erf-GELU epilogue is bound by its dependent FMA/MUFU chains, not by warps in flight.  8 it is.
-  constexpr int EW = 8;
   auto kern = gemm_bf16_pair_kernel<EPI, OutT, STAGED, EW, RING>;
   constexpr int smem =
       PairCfg<STAGED, (STAGED && ((EPI == EPI_RESID && sizeof(OutT) == 4) || epi_is_hilo(EPI) || epi_is_h16(EPI))), EW, RING, STAGED && epi_is_h16(EPI)>::kSmemBytes;
@@ -1211,6 +1210,9 @@ int launch_pair_sel(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, 
                     const GemmParams& p, bool staged) {
   if constexpr (EPI == EPI_RESID && sizeof(OutT) == 4) {
     if (staged && p.K >= 2048) return launch_pair<EPI, OutT, true, 2>(s, a, b, o, r, p);
+  }
+  if constexpr (EPI == EPI_GELU && sizeof(OutT) == 2) {  // option "gelu_ew16": 16 epilogue warps (96 registers) for the erf-GELU
+    if (staged && option_get(OPT_GELU_EW16) != 0) return launch_pair<EPI, OutT, true, kResidRing, 16>(s, a, b, o, r, p);
   }
   return staged ? launch_pair<EPI, OutT, true>(s, a, b, o, r, p) : launch_pair<EPI, OutT, false>(s, a, b, o, r, p);
 }
