@@ -59,9 +59,9 @@ def parse():
 def measured_gemm_traffic():
     """dram__bytes_read + dram__bytes_write per tcgen05 GEMM-class launch (average over the 121 launches of one step: the plain
     GEMMs, the Q|K|V + attention kernels, the visual encoder), from the committed ncu capture of this same command
-    (profiles/r02_launch_summary.json); None if absent."""
+    (profiles/r02b_launch_summary.json); None if absent."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r02_launch_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02b_launch_summary.json")) as f:
             return float(json.load(f)["tcgen05_gemm"]["dram_bytes_per_launch"])
     except Exception:
         return None
@@ -456,7 +456,7 @@ def run_ours(a):
     gq = GFLOP_PER_Q.get(Lq, GFLOP_PER_Q[20]) + MAHA_GFLOP_PER_Q
     roofline = {"bound": "tensor", "kernel": "all tcgen05 GEMM-class launches of a step: gemm_bf16_pair_kernel (FFN1, FFN2 / attention-output producers, cross Q|K|V), qkv_attn_pair_kernel (Q|K|V projection + self-attention in its epilogue; its attention time is inside the denominator), visn_embed_kernel, gemm_bf16_tcgen05_kernel (head)",
                 "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf, "traffic": measured_gemm_traffic() if (B == 1024 and Lq == 20) else None,
-                "traffic_unit": "bytes of DRAM traffic per GEMM-class launch (ncu, profiles/r02_launch_summary.json)",
+                "traffic_unit": "bytes of DRAM traffic per GEMM-class launch (ncu, profiles/r02b_launch_summary.json)",
                 "algorithmic_flops_per_launch": fl_sum[0] / max(cnt[0], 1),
                 "peak_source": peak_src, "launches_per_step": int(cnt[0] // max(a.steps, 1)),
                 "gemm_ms_per_step": ms_sum[0] / a.steps, "gemm_share_of_step": (ms_sum[0] / a.steps) / (ms_prof / a.steps),

@@ -31,10 +31,12 @@ for r in rd:
 allk = list(per.values())
 if a.per_step > 0:
     launches = allk[-a.per_step:]
-else:  # one forward + scoring: from the last embedding kernel to the last Mahalanobis finish
+else:  # one forward + scoring: the library's own kernels from the last embedding kernel on (the visual encoder of the same step
+    # may have been enqueued just before it on the side stream)
     i0 = max(i for i, l in enumerate(allk) if "embed_ln_kernel" in l["kernel"])
-    i1 = max(i for i, l in enumerate(allk) if "maha_finish_kernel" in l["kernel"])
-    launches = [l for l in allk[i0:i1 + 1] if "rgqa::" in l["kernel"]]
+    if i0 > 0 and "visn_embed_kernel" in allk[i0 - 1]["kernel"]:
+        i0 -= 1
+    launches = [l for l in allk[i0:] if "rgqa::" in l["kernel"]]
 tot = sum(l["us"] for l in launches)
 agg = collections.OrderedDict()
 for l in launches:
@@ -48,7 +50,7 @@ ks = sorted(agg.values(), key=lambda g: -g["us"])
 for g in ks:
     g["share"] = round(g["us"] / tot, 4)
     g["us"] = round(g["us"], 1)
-gem = [g for g in ks if "gemm_bf16" in g["kernel"]]
+gem = [g for g in ks if any(t in g["kernel"] for t in ("gemm_bf16", "qkv_attn_pair", "visn_embed"))]  # every tcgen05 GEMM-class launch
 out = {"source": a.source, "step_kernel_time_us": round(tot, 1), "launches": len(launches), "kernels": ks,
        "tcgen05_gemm": {"launches": sum(g["launches"] for g in gem), "us": round(sum(g["us"] for g in gem), 1),
                         "share": round(sum(g["us"] for g in gem) / tot, 4),
