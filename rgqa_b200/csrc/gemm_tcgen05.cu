@@ -593,7 +593,7 @@ template <bool STAGED, bool RESID_SMEM, int EW, int RING = kResidRing, bool H16 
 struct PairCfg {
   static constexpr int kGroups = EW / 4;
   static constexpr int kBufBytes = H16 ? kSlabBytes / 2 : kSlabBytes;
-  static constexpr int kStages = RESID_SMEM ? ((RING == 2 ? kResidStages + 1 : kResidStages) + (H16 ? 1 : 0)) : (STAGED ? 5 : 6);
+  static constexpr int kStages = RESID_SMEM ? (H16 ? (RING == 2 ? 6 : 5) : (RING == 2 ? kResidStages + 1 : kResidStages)) : (STAGED ? 5 : 6);
   static constexpr int kBufsPerGroup = RESID_SMEM ? RING : (STAGED ? (EW == 16 ? 1 : 2) : 0);
   static constexpr int kSlabRegion = kGroups * kBufsPerGroup * kBufBytes;
   static constexpr int kSmemBytes = kStages * kPairStageBytes + kSlabRegion + 1024 + 512;
