@@ -232,6 +232,8 @@ enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_GEMM_DEBUG = 2, 
   OPT_STATE_F16 = 13,  // read by rgqa_finalize_weights: deferred-LayerNorm state as ONE fp16 word per element (consumers run fp16 x fp16
                        // against fp16 copies of their folded weights) instead of a bf16 hi/lo pair
   OPT_GELU_EW16 = 14,  // FFN1 (erf-GELU consumer) with 16 epilogue warps instead of 8 (A/B measurement)
+  OPT_ATTN_STRADDLE = 15,  // fused projection + attention, S = 36: seven whole samples per CTA pair, sample 3's K / V through DSMEM (off:
+                           // 14 % fewer tiles, same time — the kernel is bound by its attention tasks, not by its main loop)
   OPT_COUNT = 16 };
 int option_get(int key);
 void option_set(int key, int value);

@@ -32,7 +32,7 @@ cudaEvent_t get_event() {
 }  // namespace
 
 namespace {
-int g_options[OPT_COUNT] = {/*OPT_GEMM_PAIR*/ 1, /*OPT_GEMM_STAGED*/ 1, /*OPT_GEMM_DEBUG*/ 0, /*OPT_PDL (no measurable gain on B200: off)*/ 0, /*OPT_GEMM_LN (slower than GEMM + LN kernel)*/ 0, /*OPT_TWO_STREAMS*/ 1, /*OPT_GRAPHS*/ 1, /*OPT_DEFER_LN*/ 1, /*OPT_ATTN_TMA*/ 1, /*OPT_QKV_PLANES*/ 0, /*OPT_MAHA_TC*/ 1, /*OPT_VISN_FUSED*/ 1, /*OPT_ATTN_FUSED*/ 1, /*OPT_STATE_F16*/ 1, /*OPT_GELU_EW16*/ 0};
+int g_options[OPT_COUNT] = {/*OPT_GEMM_PAIR*/ 1, /*OPT_GEMM_STAGED*/ 1, /*OPT_GEMM_DEBUG*/ 0, /*OPT_PDL (no measurable gain on B200: off)*/ 0, /*OPT_GEMM_LN (slower than GEMM + LN kernel)*/ 0, /*OPT_TWO_STREAMS*/ 1, /*OPT_GRAPHS*/ 1, /*OPT_DEFER_LN*/ 1, /*OPT_ATTN_TMA*/ 1, /*OPT_QKV_PLANES*/ 0, /*OPT_MAHA_TC*/ 1, /*OPT_VISN_FUSED*/ 1, /*OPT_ATTN_FUSED*/ 1, /*OPT_STATE_F16*/ 1, /*OPT_GELU_EW16*/ 0, /*OPT_ATTN_STRADDLE (measured: no gain, the kernel is bound by its attention tasks) */ 0};
 }
 bool pdl_enabled() { return g_options[OPT_PDL] != 0; }
 int option_get(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }

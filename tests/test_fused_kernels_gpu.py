@@ -212,3 +212,51 @@ def test_programmatic_dependent_launch_is_bit_identical(cuda_device, attn_fused)
     eng.close()
     for pooled, logits in out[1:]:
         assert torch.equal(pooled, out[0][0]) and torch.equal(logits, out[0][1])
+
+
+@pytest.mark.parametrize("B,masked,f16", [(29, False, False), (35, True, True), (300, False, True), (1023, True, False), (1024, False, True),
+                                          (1030, True, True)])
+def test_seven_samples_per_cta_pair_equals_three_per_cta(cuda_device, B, masked, f16):
+    """S = 36 (visual stream): the straddle form (seven whole samples per CTA pair, the middle sample's K / V lines crossing the pair
+    through distributed shared memory, its query tiles split 1 + 2 between the CTAs) is bit-identical to the 3-samples-per-CTA form
+    and to the separate projection + attention kernels — every residue of B mod 7 (tail tiles with 1..6 samples, with and without
+    a straddling sample), bf16 and fp16 operands, several launches back to back (the halo buffers' hand-shake across tiles)."""
+    from rgqa_b200 import ops, _lib as L
+    lib = L.load()
+    S = 36
+    g = torch.Generator().manual_seed(B)
+    M = B * S
+    x = torch.randn(M, 768, generator=g) * 2.0 + 0.2
+    hi = x.to(torch.float16 if f16 else torch.bfloat16)
+    v = hi.double()
+    stats = torch.stack([v.view(M, 6, 128).sum(-1), (v * v).view(M, 6, 128).sum(-1)], dim=-1).float().contiguous().to(cuda_device)
+    hi = hi.to(cuda_device)
+    w = (torch.randn(2304, 768, generator=g) * 0.03).to(cuda_device)
+    bias = (torch.randn(2304, generator=g) * 0.1).to(cuda_device)
+    gamma = (1 + 0.1 * torch.randn(768, generator=g)).to(cuda_device)
+    beta = (0.1 * torch.randn(768, generator=g)).to(cuda_device)
+    wq, _, bq = ops.fold_layernorm_weight(w, bias, gamma, beta, dtype=torch.float16 if f16 else torch.bfloat16)
+    qkv = (ops.linear_a16_folded if f16 else ops.linear_bf16_folded)(hi, stats, wq, bq, out_dtype=torch.bfloat16)
+    mask = None
+    if masked:
+        lens = torch.randint(1, S + 1, (B,), generator=g)
+        mask = (torch.arange(S)[None, :] < lens[:, None]).to(torch.int32).to(cuda_device)
+    want = ops.attention(qkv, qkv, B, S, S, key_mask=mask)
+    w_hm, b_hm = _head_major(wq, bq)
+    fn = lib.rgqa_qkv_attention_fused_a16 if f16 else lib.rgqa_qkv_attention_fused
+    got = {}
+    for straddle in (1, 0):
+        L.check(lib.rgqa_set_option(b"attn_straddle", straddle), "opt")
+        try:
+            ctx = torch.full((M + 64, 768), float("nan"), dtype=torch.bfloat16, device=cuda_device)   # guard rows behind the last sample
+            for _ in range(3):
+                L.check(fn(L.current_stream_ptr(), hi.data_ptr(), 768, w_hm.data_ptr(), b_hm.data_ptr(), stats.data_ptr(), 1e-12, L.ptr(mask),
+                           ctx.data_ptr(), 768, B, S, 12), "fused")
+            torch.cuda.synchronize()
+        finally:
+            L.check(lib.rgqa_set_option(b"attn_straddle", 0), "opt")
+        assert torch.isnan(ctx[M:].float()).all()           # nothing written behind the last sample's rows
+        got[straddle] = ctx[:M]
+        assert torch.isfinite(got[straddle].float()).all()
+    assert torch.equal(got[1], got[0]), (got[1].float() - got[0].float()).abs().max().item()
+    assert torch.equal(got[1], want), (got[1].float() - want.float()).abs().max().item()
