@@ -621,7 +621,7 @@ def run_train(a):
                 "steps_per_s": 1e3 / ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16 GEMMs / fp32 master" if a.precision == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": "LXMERT-base 9/5/5 RP-finetune step: 64 questions + 64 random-pairing negatives per rank, forward + BCE x A + "
-                                       "backward + clip 5.0 + BertAdam, dropout off; gradient pass replayed as ONE CUDA graph + one NCCL all-reduce (mean) of the flat fp32 gradient (eager mode: per-layer buckets overlapped with the backward)",
+                                       "backward + clip 5.0 + BertAdam, dropout off; gradient pass replayed as THREE CUDA graphs cut at layer boundaries, each finished segment's fp32 gradients all-reduced (mean) on NCCL's stream under the next segment's replay (eager mode: per-layer buckets overlapped with the backward)",
                            "rows_per_step": world * 2 * B, "grad_buckets": tr.comm_stats["buckets"], "grad_bytes": tr.comm_stats["bytes"]},
                 "loss_last": out[-1][0], "grad_norm_last": out[-1][1], "cuda_graph": bool(tr.use_graph)}
         if world > 1:

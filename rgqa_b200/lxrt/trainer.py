@@ -17,6 +17,8 @@ cores); every operator is a kernel of this package behind the C ABI, PyTorch hol
 """
 from __future__ import annotations
 
+import gc
+
 import torch
 import torch.distributed as dist
 
@@ -115,6 +117,11 @@ class LXMERTTrainer:
         assert sum(hi - lo for b in self.buckets for lo, hi in b) == total
         self._works, self._overlap = [], False
         self.comm_stats = {"buckets": len(self.buckets), "bytes": 4 * total}
+        # CUDA-graph mode: the gradient pass is captured as THREE graphs cut at bucket boundaries (after the cross-modality layers,
+        # and half-way down the language stack), so that the all-reduce of a finished segment's gradients runs on NCCL's stream
+        # while the next segment replays; only the last segment's collective (~28 % of the bytes) is exposed.
+        self._graph_cuts = sorted({x_layers, x_layers + r_layers + l_layers // 2} - {len(self.buckets) - 1}) if len(self.buckets) > 2 else []
+        self._capture = None
 
     # ---- parameter access: stacked Q|K|V and transposed copies are rebuilt lazily after every optimiser step ----
     def _w(self, name):
@@ -305,6 +312,13 @@ class LXMERTTrainer:
 
     def _bucket_done(self, k):
         """Every weight gradient of bucket k is enqueued: start its all-reduce (mean over ranks) behind them, on NCCL's stream."""
+        cap = self._capture
+        if cap is not None and k in self._graph_cuts:      # under capture: close this segment's graph, open the next one
+            cap["graphs"][-1].capture_end()
+            cap["ends"].append(k)
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin(pool=cap["graphs"][0].pool())
+            cap["graphs"].append(g)
         if not self._overlap:
             return
         for lo, hi in self.buckets[k]:
@@ -422,27 +436,54 @@ class LXMERTTrainer:
                 dst.copy_(src, non_blocking=True)
             self._derived.clear()
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
+            gc.collect()
+            side = torch.cuda.Stream(device=self.dev)       # capture needs a non-default stream
+            side.wait_stream(torch.cuda.current_stream(self.dev))
             self._capturing = True
+            cap = {"graphs": [torch.cuda.CUDAGraph()], "ends": []}
             try:
-                with torch.cuda.graph(g):
-                    st["loss"] = self._grad_pass(*st["inputs"])
+                with torch.cuda.stream(side):
+                    cap["graphs"][0].capture_begin()
+                    self._capture = cap
+                    st["loss"] = self._grad_pass(*st["inputs"])     # _bucket_done cuts the capture at self._graph_cuts
+                    cap["graphs"][-1].capture_end()
+                    cap["ends"].append(len(self.buckets) - 1)
             finally:
+                self._capture = None
                 self._capturing = False
-            st["graph"] = g
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            st["graphs"] = cap["graphs"]
+            # the flat-gradient slices each segment finishes, contiguous runs merged (a segment's layers are neighbours)
+            st["runs"], first = [], 0
+            for end in cap["ends"]:
+                spans = sorted(r for k in range(first, end + 1) for r in self.buckets[k])
+                runs = []
+                for lo, hi in spans:
+                    if runs and runs[-1][1] == lo:
+                        runs[-1][1] = hi
+                    else:
+                        runs.append([lo, hi])
+                st["runs"].append(runs)
+                first = end + 1
+            st["graph"] = st["graphs"][0]
             self._derived.clear()          # tensors created under capture live in the graph's pool: never reuse them eagerly
         for dst, src in zip(st["inputs"], args):
             dst.copy_(src, non_blocking=True)
-        st["graph"].replay()
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            # the graph holds the whole backward, so there is nothing left to overlap with: ONE all-reduce (mean) of the flat
-            # gradient on the compute stream (848 MB over NVLink 5: ~2.5 ms at 8 ranks, against ~31 ms of replay)
-            if dist.get_backend() == "nccl":
-                dist.all_reduce(self.flat_g, op=dist.ReduceOp.AVG)
-            else:
-                buf = self.flat_g.cpu()
-                dist.all_reduce(buf)
-                self.flat_g.copy_(buf.to(self.dev) / dist.get_world_size())
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        works = []
+        for g, runs in zip(st["graphs"], st["runs"]):
+            g.replay()
+            if multi and dist.get_backend() == "nccl":
+                # this segment's gradients are final: their all-reduce (mean) goes to NCCL's stream behind the replay just
+                # enqueued and overlaps the next segment's replay
+                for lo, hi in runs:
+                    works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.AVG, async_op=True))
+        for w in works:
+            w.wait()                                        # the compute stream waits; the host does not
+        if multi and dist.get_backend() != "nccl":
+            buf = self.flat_g.cpu()
+            dist.all_reduce(buf)
+            self.flat_g.copy_(buf.to(self.dev) / dist.get_world_size())
         return st["loss"]
 
     def train_step(self, feat, pos, ids, seg, mask, target):
