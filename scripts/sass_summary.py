@@ -1,5 +1,6 @@
 """Per-kernel counts of the SASS mnemonics that prove the Blackwell-native paths (B200_PROFILING.md): UTC*MMA (tcgen05.mma),
-LDTM / STTM (tcgen05.ld / st), UTMALDG / UTMASTG (TMA load / store), HMMA (mma.sync), from `cuobjdump -sass` of the shipped .so.
+LDTM / STTM (tcgen05.ld / st), UTMALDG / UTMASTG (TMA load / store), HMMA (mma.sync), STAS (st.async, distributed shared memory),
+F2FP.SATFINITE (the fp16 state's saturating pack), from `cuobjdump -sass` of the shipped .so.
   python scripts/sass_summary.py > profiles/r02_sass_summary.txt"""
 import collections
 import os
@@ -11,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "rgqa_b200", "_C", "librgqa_b200.so")
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
 pat = {"UTC*MMA": r"\bUTC[A-Z]*MMA", "LDTM": r"\bLDTM", "STTM": r"\bSTTM", "UTMALDG": r"\bUTMALDG", "UTMASTG": r"\bUTMASTG",
-       "HMMA": r"\bHMMA", "UTCBAR": r"\bUTCBAR", "SYNCS": r"\bSYNCS", "LDSM": r"\bLDSM", "FFMA2": r"\bFFMA2"}
+       "HMMA": r"\bHMMA", "UTCBAR": r"\bUTCBAR", "SYNCS": r"\bSYNCS", "LDSM": r"\bLDSM", "FFMA2": r"\bFFMA2",
+       "STAS": r"\bSTAS", "F2FP.SATFINITE": r"\bF2FP\.SATFINITE"}   # st.async into the peer CTA's shared memory; saturating fp16 pack
 cur = None
 counts = collections.OrderedDict()
 for line in txt.splitlines():
