@@ -281,6 +281,11 @@ int rgqa_dropout_add(void* stream, const float* x, const float* resid, float* y,
 /* dW[N, K] += dY[M, N]^T · X[M, K]  (nn.Linear weight; row strides lda / ldb / ldo). */
 int rgqa_gemm_f32_tn(void* stream, const float* A, int64_t lda, const float* B, int64_t ldb, float* out, int64_t ldo, int M, int N,
                      int K);
+/* out[M, N] (f32, row stride ldo) += A[M, K] · W[N, K]^T with bf16 operands on the tensor cores, accumulated atomically (TMA
+ * reduce-add / red.global) with the K range split over several CTAs: the weight-gradient product dW += dY^T · X of the
+ * mixed-precision training step, whose output is a handful of tiles and whose K is the batch's token rows. */
+int rgqa_gemm_bf16_accum(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo, int M, int N,
+                         int K);
 /* out[N] += sum over the M rows of X[M, N]  (nn.Linear bias). */
 int rgqa_colsum(void* stream, const float* X, int64_t ldx, float* out, int M, int N);
 /* BertLayerNorm parameters: dgamma[c] += sum_m scale·dy[m,c]·xh[m,c], dbeta[c] += sum_m scale·dy[m,c]; x is the LayerNorm INPUT

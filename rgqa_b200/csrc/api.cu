@@ -1892,6 +1892,10 @@ int rgqa_gemm_f32_tn(void* stream, const float* A, int64_t lda, const float* B, 
                      int K) {
   return gemm_f32_tn(static_cast<cudaStream_t>(stream), A, lda, B, ldb, out, ldo, M, N, K);
 }
+int rgqa_gemm_bf16_accum(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo, int M, int N,
+                         int K) {
+  return gemm_bf16_accum(static_cast<cudaStream_t>(stream), A, lda, W, ldw, out, ldo, M, N, K);
+}
 int rgqa_colsum(void* stream, const float* X, int64_t ldx, float* out, int M, int N) {
   return colsum(static_cast<cudaStream_t>(stream), X, ldx, out, M, N);
 }

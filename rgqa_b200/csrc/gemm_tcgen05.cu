@@ -71,6 +71,7 @@ struct GemmParams {
   long long ln_stats_ld;  // floats between the statistics of consecutive GEMM rows (12 when dense)
   int out_heads;  // > 0: the output is the head-major Q|K|V plane tensor (gemm_bf16_qkv_planes); column block cb of 64 goes
                   // to plane (cb % heads) * 3 + cb / heads
+  int splits;  // EPI_ACCUM: every output tile is computed by `splits` CTAs (pairs), each over K / splits (0 or 1: no split)
   int a_f16;   // A and W are fp16 (the single-word deferred-LayerNorm state against the fp16 copy of its consumer's weight)
   int vec_ok;  // direct path: rows of out (and resid) are 16-byte aligned -> vector stores allowed
   int debug;   // measurement only (rgqa_set_option "gemm_debug"): bit0 skip TMA stores, bit1 skip epilogue math+smem
@@ -238,6 +239,13 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row,
   float f[32];
   epilogue_math<EPI>(v, f, row, row_ok, col0, p, p.vec_ok != 0, rn);
   if (!row_ok) return;
+  if constexpr (EPI == EPI_ACCUM) {  // out += acc, one red.global.add per element (several CTAs share the tile along K)
+    float* orow = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (col0 + i < p.N) atomicAdd(orow + i, f[i]);
+    return;
+  }
   if (col0 + 32 <= p.N && p.vec_ok) {
     if constexpr (sizeof(OutT) == 2) {
       uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col0);
@@ -357,8 +365,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_m = (p.M + BM - 1) / BM;
-  const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = p.K / BK;
+  const int splits = (EPI == EPI_ACCUM && p.splits > 1) ? p.splits : 1;   // work item t = (tile t / splits, K slice t % splits)
+  const int num_tiles = tiles_m * tiles_n * splits;
+  const int num_kb = (p.K / BK) / splits;   // k-blocks per work item (the host makes K / BK a multiple of splits)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -388,16 +397,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t / tiles_n) * BM;
-      const int n0 = (t % tiles_n) * BN;
+      const int tile = t / splits, kb0 = (t - tile * splits) * num_kb;
+      const int m0 = (tile / tiles_n) * BM;
+      const int n0 = (tile % tiles_n) * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         if (lane == 0) {
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          tma_load_2d(sa, &tmA, &full_bar[stage], (kb0 + kb) * BK, m0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], (kb0 + kb) * BK, n0);
         }
         __syncwarp();
         if (++stage == C::kStages) {
@@ -450,8 +460,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int m0 = (t / tiles_n) * BM;
-      const int n0 = (t % tiles_n) * BN;
+      const int tile = t / splits;
+      const int m0 = (tile / tiles_n) * BM;
+      const int n0 = (tile % tiles_n) * BN;
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       const RowNorm rn = row_norm(p.ln_stats, row, row_ok, p.ln_eps, p.ln_stats_ld);
@@ -636,8 +647,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   const int tiles_n = (p.N + kPairBN - 1) / kPairBN;
   const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
-  const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = p.K / BK;
+  const int splits = (EPI == EPI_ACCUM && p.splits > 1) ? p.splits : 1;   // work item t = (tile t / splits, K slice t % splits)
+  const int num_tiles = tiles_m * tiles_n * splits;
+  const int num_kb = (p.K / BK) / splits;   // k-blocks per work item
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -674,8 +686,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     int stage = 0;
     uint32_t phase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
-      const int m0 = (t / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
-      const int n0 = (t % tiles_n) * kPairBN + static_cast<int>(rank) * (kPairBN / 2);
+      const int tile = t / splits, kb0 = (t - tile * splits) * num_kb;
+      const int m0 = (tile / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = (tile % tiles_n) * kPairBN + static_cast<int>(rank) * (kPairBN / 2);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         if (lane == 0) {
@@ -683,8 +696,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           uint8_t* sb = sa + BM * BK * 2;
           const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
-          tma_load_2d_pair(sa, &tmA, leader_full, kb * BK, m0);
-          tma_load_2d_pair(sb, &tmB, leader_full, kb * BK, n0);
+          tma_load_2d_pair(sa, &tmA, leader_full, (kb0 + kb) * BK, m0);
+          tma_load_2d_pair(sb, &tmB, leader_full, (kb0 + kb) * BK, n0);
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -972,8 +985,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int m0 = (t / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
-      const int n0 = (t % tiles_n) * kPairBN;
+      const int tile = t / splits;
+      const int m0 = (tile / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = (tile % tiles_n) * kPairBN;
       const int r_local = quarter * 32 + lane;
       const int row = m0 + r_local;
       const bool row_ok = row < p.M;
@@ -1015,6 +1029,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (p.out_heads > 0) {
               const int cb = col_slab >> 6;
               tma_store_3d(&tmOut, buf + quarter * kSubSlab, 0, m0 + quarter * 32, (cb % p.out_heads) * 3 + cb / p.out_heads);
+            } else if constexpr (EPI == EPI_ACCUM) {
+              tma_reduce_add_2d(&tmOut, buf + quarter * kSubSlab, col_slab, m0 + quarter * 32);   // out += this K slice's tile
             } else {
               tma_store_2d(&tmOut, buf + quarter * kSubSlab, col_slab, m0 + quarter * 32);
             }
@@ -1151,7 +1167,7 @@ int launch(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     RGQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
-  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * ((EPI == EPI_ACCUM && p.splits > 1) ? p.splits : 1);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   void* tok = prof_begin(stream);
   RGQA_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kNumThreads), C::kSmemBytes, stream, tmA, tmB, p));
@@ -1193,7 +1209,7 @@ int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& 
     RGQA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + kPairBN - 1) / kPairBN);
+  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + kPairBN - 1) / kPairBN) * ((EPI == EPI_ACCUM && p.splits > 1) ? p.splits : 1);
   const int max_pairs = num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   void* tok = prof_begin(stream);
@@ -1309,6 +1325,38 @@ int gemm_bf16_resid_h16(cudaStream_t stream, const void* A, long long lda, const
   }
   if (K >= 2048) return launch_pair<EPI_RESID_H16, __nv_bfloat16, true, 2>(stream, tmA, tmB, tmOut, tmIn, p);
   return launch_pair<EPI_RESID_H16, __nv_bfloat16, true>(stream, tmA, tmB, tmOut, tmIn, p);
+}
+
+int gemm_bf16_accum(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, float* out, long long ldo,
+                    int M, int N, int K) {
+  RGQA_CHECK(A && W && out && M > 0 && N > 0 && K > 0 && K % BK == 0, "gemm_bf16_accum: bad problem M=%d N=%d K=%d", M, N, K);
+  const int num_kb = K / BK;
+  const bool out_al = (reinterpret_cast<uintptr_t>(out) % 16 == 0) && ((ldo * 4) % 16 == 0);
+  const bool use_pair = option_get(OPT_GEMM_PAIR) != 0 && option_get(OPT_GEMM_STAGED) != 0 && M >= 1024 && out_al && N % 32 == 0;
+  const int bn = use_pair ? kPairBN : ((N % 128 == 0 || N >= 512) ? 128 : 64);
+  const int tiles = use_pair ? ((M + 2 * BM - 1) / (2 * BM)) * ((N + kPairBN - 1) / kPairBN) : ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+  // split K until every SM (pair) has a work item, keeping at least 8 k-blocks per item and K / 64 a multiple of the split
+  const int want = use_pair ? num_sms() / 2 : num_sms();
+  int splits = 1;
+  while (splits < 16 && tiles * splits * 2 <= want + tiles && num_kb % (splits * 2) == 0 && num_kb / (splits * 2) >= 8) splits *= 2;
+  CUtensorMap tmA, tmB, tmOut;
+  if (make_tmap(&tmA, A, M, K, lda, BM, 2)) return 1;
+  if (make_tmap(&tmB, W, N, K, ldw, use_pair ? kPairBN / 2 : bn, 2)) return 1;
+  GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.out = out;
+  p.ldo = ldo;
+  p.ln_stats_ld = 12;
+  p.splits = splits;
+  p.vec_ok = out_al ? 1 : 0;
+  p.debug = 0;
+  if (use_pair) {
+    if (make_tmap(&tmOut, out, M, N, ldo, 32, 4)) return 1;
+    return launch_pair<EPI_ACCUM, float, true>(stream, tmA, tmB, tmOut, tmA, p);
+  }
+  return bn == 128 ? launch<128, EPI_ACCUM, float>(stream, tmA, tmB, p) : launch<64, EPI_ACCUM, float>(stream, tmA, tmB, p);
 }
 
 int gemm_bf16_reduce(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,

@@ -19,6 +19,7 @@ enum Epilogue : int {
   EPI_REDUCE = 6,  // acc + bias reduced along each row inside the epilogue (scorers of the answer head / Mahalanobis), see RowReduce
   EPI_RESID_H16 = 7,       // EPI_RESID_HL with the state as ONE fp16 word per element (no lo): half the residual bytes
   EPI_RESID_H16_BETA = 8,  // ... with LN_prev's beta passed separately
+  EPI_ACCUM = 9,           // out (fp32) += acc, atomically (TMA reduce-add / red.global): weight gradients, split along K
 };
 
 // Row reductions fused into a GEMM epilogue (gemm_bf16_reduce).  Every (row tile, column tile) CTA leaves one partial
@@ -63,6 +64,11 @@ int gemm_bf16_folded(cudaStream_t stream, const void* A, long long lda, const vo
                      int a_f16 = 0 /* A AND W are fp16 (the fp16 deferred-LayerNorm state against fp16 weight copies) */);
 // out = A·Wᵀ + bias reduced per row in the epilogue (see RowReduce); `out` (fp32 [M, N], row stride ldo) may be nullptr: the
 // matrix is then never written.  Single-CTA 128 x 128 tiles (the head GEMMs have M = batch rows).
+// out[M, N] (fp32, row stride ldo) += A[M, K] · W[N, K]ᵀ, bf16 operands, accumulated ATOMICALLY so that the K range can be split
+// over several CTAs (weight gradients of the training step: M, N = a weight's shape, K = the batch's token rows — a handful of
+// output tiles, thousands of k-blocks).  The summation order varies from run to run, like every other wgrad kernel here.
+int gemm_bf16_accum(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, float* out, long long ldo,
+                    int M, int N, int K);
 int gemm_bf16_reduce(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
                      float* out, long long ldo, int M, int N, int K, const RowReduce& red);
 // Q|K|V projection with a head-major output: out[plane = head*3 + {q,k,v}][row][64] bf16, planes plane_rows rows apart; `out`

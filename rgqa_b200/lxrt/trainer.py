@@ -166,7 +166,7 @@ class LXMERTTrainer:
                 bt = ops.transpose_cast_bf16(x)              # [K, M]   (transposing copy + cast in one pass)
                 if xt is not None:
                     xt.append(bt)
-            ops.linear_bf16(a, bt, None, epilogue=L.EPI_RESID, residual=gw, out_dtype=torch.float32, out=gw)
+            ops.linear_bf16_accumulate_(gw, a, bt)           # G[w] += a · btᵀ, K (= the token rows) split over the SMs
         else:
             ops.linear_wgrad_(gw, gb, dy, x)
 

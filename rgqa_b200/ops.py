@@ -157,6 +157,20 @@ def linear_residual_h16(x, weight, bias, in_h, in_stats, in_gamma, in_beta, eps=
     return h, stats
 
 
+def linear_bf16_accumulate_(out, x, weight):
+    """out [M, N] f32 += x [M, K] · weight [N, K]ᵀ (bf16 operands, tensor cores, K split over CTAs, atomic accumulation): the
+    weight-gradient product of the mixed-precision training step.  In place."""
+    _need_cuda(out, x, weight)
+    assert x.dtype == weight.dtype == torch.bfloat16 and out.dtype == torch.float32
+    assert x.stride(1) == 1 and weight.stride(1) == 1 and out.stride(1) == 1
+    M, K = x.shape
+    N = weight.shape[0]
+    assert out.shape == (M, N) and weight.shape[1] == K
+    L.check(L.load().rgqa_gemm_bf16_accum(L.current_stream_ptr(), L.ptr(x), x.stride(0), L.ptr(weight), weight.stride(0), L.ptr(out),
+                                          out.stride(0), M, N, K), "rgqa_gemm_bf16_accum")
+    return out
+
+
 def linear_f32(x, weight, bias=None, epilogue=L.EPI_BIAS, residual=None):
     """fp32 CUDA-core GEMM with the same contract as :func:`linear_bf16` (precise path)."""
     _need_cuda(x, weight, bias, residual)

@@ -172,3 +172,26 @@ def test_sign_step_kernel(cuda_device):
             gradient = (torch.ge(grad, 0).float() - 0.5) * 2   # the reference's two statements, literally
             want = torch.add(x, gradient, alpha=-noise)
             torch.testing.assert_close(y, want, rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("kind", ["odin", "maha"])
+def test_graph_replay_of_the_input_gradient_scorers_equals_the_eager_pass(setup, kind):
+    """`GraphedInputGradScorer`: forward + input-gradient backward + sign step + forward captured once per batch shape and replayed;
+    four different batches through the same graph must give the eager scorer's scores (same kernels; the scorers have no
+    atomics on this path, so equality is exact) and labels."""
+    from rgqa_b200.tasks.gqa_odin import GraphedInputGradScorer, mahalanobis_noise_scores, odin_scores
+    sd, ig, _ = setup
+    mu, P = syn.maha_stats(num_answers=60)
+    gs = GraphedInputGradScorer(ig, kind, temperature=2.0, noise=1e-3, sample_mean=mu, precision=P)
+    for step in range(5):
+        inp = syn.make_inputs(3, 20, seed=100 + step)
+        a = [inp[k] for k in ("feat", "pos", "ids", "seg", "mask")]
+        if kind == "odin":
+            ws, wl, _, _ = odin_scores(ig, *a, 2.0, 1e-3)
+        else:
+            ws, wl, _, _ = mahalanobis_noise_scores(ig, *a, mu, P, 1e-3)
+        ws, wl = ws.clone(), wl.clone()
+        s, l = gs(*a)
+        torch.cuda.synchronize()
+        assert torch.equal(l, wl) and torch.equal(s, ws), (step, (s - ws).abs().max().item())
+    assert gs.captures == 1

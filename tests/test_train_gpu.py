@@ -374,3 +374,21 @@ def test_transpose_cast_kernel_with_column_sums(cuda_device, R, C, ld):
     torch.cuda.synchronize()
     assert torch.equal(y, x.t().contiguous().to(torch.bfloat16))
     torch.testing.assert_close((acc - acc0).double(), x.double().sum(0), rtol=1e-5, atol=2e-4)
+
+
+@pytest.mark.parametrize("M,N,K", [(768, 768, 4608), (3072, 768, 2560), (768, 3072, 4608), (768, 768, 2560), (1842, 1536, 128),
+                                   (1536, 768, 128), (2304, 768, 4608), (130, 70, 64)])
+def test_accumulating_weight_gradient_gemm(cuda_device, M, N, K):
+    """out += A · Wᵀ with the K range split over CTAs and atomic accumulation (TMA reduce-add in the CTA-pair kernel, red.global in
+    the single-CTA one): the weight-gradient product dW += dYᵀ · X of `gqa_conf.py:196`'s backward at the RP-finetune shapes."""
+    from rgqa_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).to(cuda_device)
+    w = torch.randn(N, K, generator=g).to(torch.bfloat16).to(cuda_device)
+    out0 = torch.randn(M, N, generator=g).to(cuda_device)
+    out = out0.clone()
+    ops.linear_bf16_accumulate_(out, a, w)
+    ops.linear_bf16_accumulate_(out, a, w)               # accumulates: twice the product
+    torch.cuda.synchronize()
+    ref = out0.double() + 2.0 * (a.double() @ w.double().t())
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=2e-3 * (K / 128) ** 0.5)   # fp32 accumulation order only
