@@ -1332,7 +1332,9 @@ int gemm_bf16_accum(cudaStream_t stream, const void* A, long long lda, const voi
   RGQA_CHECK(A && W && out && M > 0 && N > 0 && K > 0 && K % BK == 0, "gemm_bf16_accum: bad problem M=%d N=%d K=%d", M, N, K);
   const int num_kb = K / BK;
   const bool out_al = (reinterpret_cast<uintptr_t>(out) % 16 == 0) && ((ldo * 4) % 16 == 0);
-  const bool use_pair = option_get(OPT_GEMM_PAIR) != 0 && option_get(OPT_GEMM_STAGED) != 0 && M >= 1024 && out_al && N % 32 == 0;
+  // the CTA-pair kernel for every weight-sized output: its epilogue adds whole 128-byte lines (TMA reduce-add), the single-CTA
+  // kernel's direct epilogue one element per atomic with a row per lane (32 sectors per instruction)
+  const bool use_pair = option_get(OPT_GEMM_PAIR) != 0 && option_get(OPT_GEMM_STAGED) != 0 && M >= 256 && out_al && N % 32 == 0;
   const int bn = use_pair ? kPairBN : ((N % 128 == 0 || N >= 512) ? 128 : 64);
   const int tiles = use_pair ? ((M + 2 * BM - 1) / (2 * BM)) * ((N + kPairBN - 1) / kPairBN) : ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
   // split K until every SM (pair) has a work item, keeping at least 8 k-blocks per item and K / 64 a multiple of the split
