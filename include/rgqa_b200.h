@@ -286,6 +286,13 @@ int rgqa_gemm_f32_tn(void* stream, const float* A, int64_t lda, const float* B, 
  * mixed-precision training step, whose output is a handful of tiles and whose K is the batch's token rows. */
 int rgqa_gemm_bf16_accum(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo, int M, int N,
                          int K);
+/* The same accumulation from TRANSPOSED operands, out[M, N] += At[K, M]^T · Bt[K, N] (bf16, row-major, row strides ldat / ldbt): the
+ * tensor cores read both tiles MN-major, so dW += dY^T · X needs no transposing copies of dY and X.  K % 64 == 0, N % 32 == 0. */
+int rgqa_gemm_bf16_accum_tn(void* stream, const void* At, int64_t ldat, const void* Bt, int64_t ldbt, float* out, int64_t ldo, int M,
+                            int N, int K);
+/* out bf16 [R, C] (row stride ldo) = bf16(in f32 [R, C], row stride ld); colsum (may be NULL) [C] += column sums of `in`: one pass
+ * over a linear layer's dy gives the bf16 operand of its dgrad / wgrad GEMMs and its bias gradient. */
+int rgqa_cast_bf16_colsum(void* stream, const float* in, int64_t ld, void* out, int64_t ldo, int R, int C, float* colsum);
 /* out[N] += sum over the M rows of X[M, N]  (nn.Linear bias). */
 int rgqa_colsum(void* stream, const float* X, int64_t ldx, float* out, int M, int N);
 /* BertLayerNorm parameters: dgamma[c] += sum_m scale·dy[m,c]·xh[m,c], dbeta[c] += sum_m scale·dy[m,c]; x is the LayerNorm INPUT

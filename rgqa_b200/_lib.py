@@ -82,6 +82,8 @@ SIGNATURES = {
     "rgqa_attention_bwd": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _f, C.c_uint64]),
     "rgqa_attention_dropout": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _f, C.c_uint64]),
     "rgqa_transpose_cast_bf16": (_i, [_vp, _vp, _i64, _vp, _i, _i]),
+    "rgqa_gemm_bf16_accum_tn": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i]),
+    "rgqa_cast_bf16_colsum": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _vp]),
     "rgqa_gemm_bf16_accum": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i]),
     "rgqa_transpose_cast_bf16_colsum": (_i, [_vp, _vp, _i64, _vp, _i, _i, _vp]),
     "rgqa_layernorm_bwd_params": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f]),

@@ -1896,6 +1896,13 @@ int rgqa_gemm_bf16_accum(void* stream, const void* A, int64_t lda, const void* W
                          int K) {
   return gemm_bf16_accum(static_cast<cudaStream_t>(stream), A, lda, W, ldw, out, ldo, M, N, K);
 }
+int rgqa_gemm_bf16_accum_tn(void* stream, const void* At, int64_t ldat, const void* Bt, int64_t ldbt, float* out, int64_t ldo, int M,
+                            int N, int K) {
+  return gemm_bf16_accum_tn(static_cast<cudaStream_t>(stream), At, ldat, Bt, ldbt, out, ldo, M, N, K);
+}
+int rgqa_cast_bf16_colsum(void* stream, const float* in, int64_t ld, void* out, int64_t ldo, int R, int C, float* colsum) {
+  return cast_bf16_colsum(static_cast<cudaStream_t>(stream), in, ld, out, ldo, R, C, colsum);
+}
 int rgqa_colsum(void* stream, const float* X, int64_t ldx, float* out, int M, int N) {
   return colsum(static_cast<cudaStream_t>(stream), X, ldx, out, M, N);
 }

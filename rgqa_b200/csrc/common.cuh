@@ -363,6 +363,20 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B     [61,64)
   return d;
 }
+// MN-major operand tile (the matrix is stored K-rows x MN-columns, MN contiguous — a transposed operand read in place): TMA
+// boxes of 64 MN elements (128 B) x BK k-rows, 128-byte swizzle.  Canonical layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in
+// elements: 64 contiguous MN elements per 128-byte line, consecutive k = consecutive lines, SBO = 1024 B between 8-k groups,
+// LBO = bytes between 64-element MN groups (= one box).  A k16 MMA step advances the start address by 16 lines = 2048 B.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+constexpr uint32_t kIdescMnMajorAB = (1u << 15) | (1u << 16);   // a_major, b_major = MN
 // Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M x N tile.  kind::f16 has one format field per operand
 // (0 = fp16, 1 = bf16) but the hardware wants them EQUAL (fp16 x bf16 raises an illegal-instruction error on B200): clearing
 // kIdescABf16 turns the MMA into fp16 x fp16 (the fp16 deferred-LayerNorm state against fp16 copies of the folded weights).

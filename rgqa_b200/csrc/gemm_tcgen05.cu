@@ -71,6 +71,7 @@ struct GemmParams {
   long long ln_stats_ld;  // floats between the statistics of consecutive GEMM rows (12 when dense)
   int out_heads;  // > 0: the output is the head-major Q|K|V plane tensor (gemm_bf16_qkv_planes); column block cb of 64 goes
                   // to plane (cb % heads) * 3 + cb / heads
+  int tn;      // EPI_ACCUM, CTA-pair kernel: both operands are given TRANSPOSED ([K, M] and [K, N] row-major) and read MN-major
   int splits;  // EPI_ACCUM: every output tile is computed by `splits` CTAs (pairs), each over K / splits (0 or 1: no split)
   int a_f16;   // A and W are fp16 (the single-word deferred-LayerNorm state against the fp16 copy of its consumer's weight)
   int vec_ok;  // direct path: rows of out (and resid) are 16-byte aligned -> vector stores allowed
@@ -696,8 +697,15 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           uint8_t* sb = sa + BM * BK * 2;
           const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
-          tma_load_2d_pair(sa, &tmA, leader_full, (kb0 + kb) * BK, m0);
-          tma_load_2d_pair(sb, &tmB, leader_full, (kb0 + kb) * BK, n0);
+          if (EPI == EPI_ACCUM && p.tn) {  // transposed operands: two [64 MN x 64 k] boxes each (tensor maps over [K, M] / [K, N])
+            tma_load_2d_pair(sa, &tmA, leader_full, m0, (kb0 + kb) * BK);
+            tma_load_2d_pair(sa + 8192, &tmA, leader_full, m0 + 64, (kb0 + kb) * BK);
+            tma_load_2d_pair(sb, &tmB, leader_full, n0, (kb0 + kb) * BK);
+            tma_load_2d_pair(sb + 8192, &tmB, leader_full, n0 + 64, (kb0 + kb) * BK);
+          } else {
+            tma_load_2d_pair(sa, &tmA, leader_full, (kb0 + kb) * BK, m0);
+            tma_load_2d_pair(sb, &tmB, leader_full, (kb0 + kb) * BK, n0);
+          }
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -709,7 +717,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA only) ------------------------------
     if (rank == 0) {
-      const uint32_t idesc = umma_idesc_bf16(2 * BM, kPairBN) & ~(p.a_f16 ? kIdescABf16 : 0u);
+      const bool tn = EPI == EPI_ACCUM && p.tn != 0;
+      const uint32_t idesc = (umma_idesc_bf16(2 * BM, kPairBN) & ~(p.a_f16 ? kIdescABf16 : 0u)) | (tn ? kIdescMnMajorAB : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -724,11 +733,19 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tc_fence_after();
           if (lane == 0) {
             const uint32_t sa = smem_u32(smem + stage * kPairStageBytes);
+            if (tn) {  // MN-major tiles: 64-element MN groups 8 KB apart, a k16 step = 16 lines = 2048 B = 128 address units
+              const uint64_t adesc = umma_smem_desc_sw128_mn(sa, 8192u);
+              const uint64_t bdesc = umma_smem_desc_sw128_mn(sa + BM * BK * 2, 8192u);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16_pair(d_tmem, adesc + 128u * k, bdesc + 128u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            } else {
             const uint64_t adesc = umma_smem_desc_sw128(sa);
             const uint64_t bdesc = umma_smem_desc_sw128(sa + BM * BK * 2);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
               umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
             umma_commit_pair(&empty_bar[stage]);
             if (kb == num_kb - 1) umma_commit_pair(&tmem_full_bar[acc]);
           }
@@ -1325,6 +1342,35 @@ int gemm_bf16_resid_h16(cudaStream_t stream, const void* A, long long lda, const
   }
   if (K >= 2048) return launch_pair<EPI_RESID_H16, __nv_bfloat16, true, 2>(stream, tmA, tmB, tmOut, tmIn, p);
   return launch_pair<EPI_RESID_H16, __nv_bfloat16, true>(stream, tmA, tmB, tmOut, tmIn, p);
+}
+
+int gemm_bf16_accum_tn(cudaStream_t stream, const void* At, long long ldat, const void* Bt, long long ldbt, float* out, long long ldo,
+                       int M, int N, int K) {
+  RGQA_CHECK(At && Bt && out && M > 0 && N > 0 && K > 0 && K % BK == 0, "gemm_bf16_accum_tn: bad problem M=%d N=%d K=%d", M, N, K);
+  RGQA_CHECK(option_get(OPT_GEMM_PAIR) != 0 && option_get(OPT_GEMM_STAGED) != 0, "gemm_bf16_accum_tn: needs the staged CTA-pair kernel");
+  RGQA_CHECK((reinterpret_cast<uintptr_t>(out) % 16 == 0) && ((ldo * 4) % 16 == 0) && N % 32 == 0,
+             "gemm_bf16_accum_tn: out must be 16-byte aligned with N a multiple of 32");
+  const int num_kb = K / BK;
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + kPairBN - 1) / kPairBN);
+  const int want = num_sms() / 2;
+  int splits = 1;
+  while (splits < 16 && tiles * splits * 2 <= want + tiles && num_kb % (splits * 2) == 0 && num_kb / (splits * 2) >= 8) splits *= 2;
+  CUtensorMap tmA, tmB, tmOut;
+  // [K rows, M (N) columns] row-major, box = 64 columns (128 B) x 64 k-rows, 128-byte swizzle; columns / rows past the end read as zero
+  if (make_tmap_ex(&tmA, At, K, M, ldat, BK, 64, 2, 128) || make_tmap_ex(&tmB, Bt, K, N, ldbt, BK, 64, 2, 128) ||
+      make_tmap(&tmOut, out, M, N, ldo, 32, 4))
+    return 1;
+  GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.out = out;
+  p.ldo = ldo;
+  p.ln_stats_ld = 12;
+  p.splits = splits;
+  p.tn = 1;
+  p.vec_ok = 1;
+  return launch_pair<EPI_ACCUM, float, true>(stream, tmA, tmB, tmOut, tmA, p);
 }
 
 int gemm_bf16_accum(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, float* out, long long ldo,

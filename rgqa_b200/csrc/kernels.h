@@ -69,6 +69,13 @@ int gemm_bf16_folded(cudaStream_t stream, const void* A, long long lda, const vo
 // output tiles, thousands of k-blocks).  The summation order varies from run to run, like every other wgrad kernel here.
 int gemm_bf16_accum(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, float* out, long long ldo,
                     int M, int N, int K);
+// The same product from TRANSPOSED operands: out[M, N] += At[K, M]ᵀ · Bt[K, N] (both row-major, read MN-major by the tensor
+// cores): dW += dYᵀ · X straight from the bf16 rows of dY and X, no transposing copies.  K % 64 == 0, N % 32 == 0.
+int gemm_bf16_accum_tn(cudaStream_t stream, const void* At, long long ldat, const void* Bt, long long ldbt, float* out, long long ldo,
+                       int M, int N, int K);
+// bf16(in) for an fp32 [R, C] view (row stride ld) into a bf16 [R, C] view (row stride ldo), optionally adding the column sums of `in`
+// to colsum [C]
+int cast_bf16_colsum(cudaStream_t stream, const float* in, long long ld, void* out, long long ldo, int R, int C, float* colsum);
 int gemm_bf16_reduce(cudaStream_t stream, const void* A, long long lda, const void* W, long long ldw, const float* bias,
                      float* out, long long ldo, int M, int N, int K, const RowReduce& red);
 // Q|K|V projection with a head-major output: out[plane = head*3 + {q,k,v}][row][64] bf16, planes plane_rows rows apart; `out`

@@ -414,6 +414,37 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __rest
   }
 }
 
+// fp32 [R, C] (row stride ld) -> bf16 [R, C] (row stride ldo), with the column sums of the fp32 input added to colsum (optional): the
+// training step's ONE pass over a linear layer's dy — its bf16 copy feeds both the dgrad and the (transposed-operand) wgrad GEMM,
+// the column sums are the bias gradient.  Block = 64 rows x 128 columns; a thread owns 4 columns of 8 rows.
+__global__ void __launch_bounds__(256) cast_colsum_kernel(const float* __restrict__ in, long long ld, __nv_bfloat16* __restrict__ out,
+                                                          long long ldo, int R, int C, float* __restrict__ colsum) {
+  __shared__ float part[8][128];
+  const int c = blockIdx.x * 128 + (threadIdx.x & 31) * 4, ry = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * 64;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + ry + 8 * i;
+      if (r < R) {
+        const float4 v = *reinterpret_cast<const float4*>(in + static_cast<long long>(r) * ld + c);
+        *reinterpret_cast<uint2*>(out + static_cast<long long>(r) * ldo + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    }
+  }
+  if (colsum == nullptr) return;
+  *reinterpret_cast<float4*>(&part[ry][(threadIdx.x & 31) * 4]) = s;
+  __syncthreads();
+  if (threadIdx.x < 128 && blockIdx.x * 128 + threadIdx.x < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+    atomicAdd(colsum + blockIdx.x * 128 + threadIdx.x, t);
+  }
+}
+
 inline int row_grid(int rows) { return (rows + kWarpsPerBlock - 1) / kWarpsPerBlock; }
 
 }  // namespace
@@ -556,6 +587,16 @@ int transpose_cast_bf16(cudaStream_t stream, const float* in, long long ld, void
   RGQA_CHECK(R > 0 && C > 0 && ld >= C, "transpose_cast_bf16: bad shape R=%d C=%d ld=%lld", R, C, ld);
   RGQA_CHECK(reinterpret_cast<uintptr_t>(out) % 4 == 0, "transpose_cast_bf16: unaligned output");
   transpose_cast_kernel<<<dim3((C + 31) / 32, (R + 63) / 64), 256, 0, stream>>>(in, ld, static_cast<__nv_bfloat16*>(out), R, C, colsum);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int cast_bf16_colsum(cudaStream_t stream, const float* in, long long ld, void* out, long long ldo, int R, int C, float* colsum) {
+  RGQA_CHECK(in && out && R > 0 && C > 0 && C % 4 == 0 && ld % 4 == 0 && ldo % 4 == 0 && ldo >= C &&
+                 reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 8 == 0,
+             "cast_bf16_colsum: needs C and the row strides multiples of 4 and a 16-byte aligned input");
+  cast_colsum_kernel<<<dim3((C + 127) / 128, (R + 63) / 64), 256, 0, stream>>>(in, ld, static_cast<__nv_bfloat16*>(out), ldo, R, C, colsum);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;

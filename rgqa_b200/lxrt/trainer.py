@@ -88,6 +88,7 @@ class LXMERTTrainer:
                        lf=_Ffn(f"{enc}x_layers.{i}.lang_inter", f"{enc}x_layers.{i}.lang_output"),
                        vf=_Ffn(f"{enc}x_layers.{i}.visn_inter", f"{enc}x_layers.{i}.visn_output")) for i in range(x_layers)]
         self._derived = {}
+        self._a16 = {}          # per-step bf16 copies of activations / gradients (_act16)
         self.tape = None
         # Gradient buckets in the order the backward FINISHES them (data parallelism): answer head + pooler, the
         # cross-modality layers last to first, the object-relational and language layers last to first, then the visual feature
@@ -147,18 +148,49 @@ class LXMERTTrainer:
             self._derived[key] = ops.cast_bf16(make().contiguous())
         return self._derived[key]
 
+    @staticmethod
+    def _castable(t):
+        return t.dim() == 2 and t.stride(1) == 1 and t.shape[1] % 8 == 0 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0
+
+    def _act16(self, t, colsum_into=None):
+        """bf16 copy of an fp32 activation or gradient, made ONCE per step: the forward's GEMM operand is the weight gradient's, a
+        layer's dy feeds both its dgrad and its wgrad.  ``colsum_into``: the column sums of t (the bias gradient) ride on the cast.
+        The source tensor is kept alive with its copy, so that a recycled address can never alias a stale entry."""
+        key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()))
+        hit = self._a16.get(key)
+        if hit is not None:
+            if colsum_into is not None:
+                ops.linear_wgrad_bias_(colsum_into, t)
+            return hit[1]
+        if self._castable(t):
+            out = ops.cast_bf16_colsum(t, colsum_into)
+        else:
+            out = ops.cast_bf16(t.contiguous())
+            if colsum_into is not None:
+                ops.linear_wgrad_bias_(colsum_into, t)
+        self._a16[key] = (t, out)
+        return out
+
     def _mm(self, x, w, b, epilogue=L.EPI_BIAS, residual=None, wkey=None):
         """epilogue(x · wᵀ + b [+ residual]) with w [N, K] fp32 (``wkey`` names its cached bf16 copy)."""
         if self.gemm == "bf16" and w.shape[1] % 64 == 0 and x.shape[0] >= 64:
             wb = self._b16(("b16", wkey), lambda: w)
-            return ops.linear_bf16(ops.cast_bf16(x.contiguous()), wb, b, epilogue=epilogue, residual=residual, out_dtype=torch.float32)
+            return ops.linear_bf16(self._act16(x), wb, b, epilogue=epilogue, residual=residual, out_dtype=torch.float32)
         return ops.linear_f32(x, w, b, epilogue=epilogue, residual=residual)
+
+    def _tn_ok(self, dy, x):
+        """dW += dyᵀ · x straight from the bf16 rows (tensor cores read both operands MN-major): needs 64-row multiples and 16-byte rows."""
+        return (self.gemm == "bf16" and dy.shape[0] % 64 == 0 and dy.shape[0] >= 64 and dy.shape[1] % 8 == 0 and dy.shape[1] >= 64 and
+                x.shape[1] % 32 == 0 and x.shape[1] >= 64 and self._castable(dy) and self._castable(x))
 
     def _wgrad(self, wname, dy, x, xt=None):
         """G[w] += dyᵀ · x, G[b] += colsum(dy).  ``xt``: a one-element list caching the bf16 transpose of x across calls that share x."""
         gw, gb = self.g[wname + ".weight"], self.g[wname + ".bias"]
         M = dy.shape[0]
-        if self.gemm == "bf16" and M % 64 == 0 and M >= 64 and x.shape[1] >= 64 and dy.shape[1] >= 64:
+        if self._tn_ok(dy, x):
+            # one pass over dy: its bf16 copy (the dgrad GEMM reuses it) + the bias gradient; x's bf16 copy is the forward's
+            ops.linear_bf16_accumulate_tn_(gw, self._act16(dy, colsum_into=gb), self._act16(x))
+        elif self.gemm == "bf16" and M % 64 == 0 and M >= 64 and x.shape[1] >= 64 and dy.shape[1] >= 64:
             a = ops.transpose_cast_bf16(dy, colsum_into=gb)  # [N, M]: the product runs over the rows; G[b] rides on the same read of dy
             if xt is not None and xt:
                 bt = xt[0]
@@ -270,7 +302,7 @@ class LXMERTTrainer:
             key = ("b16", ("t", name))
             if key not in self._derived:                  # bf16 W^T straight from the fp32 master weight: one pass, no fp32 transposed copy
                 self._derived[key] = ops.transpose_cast_bf16(w)
-            return ops.linear_bf16(ops.cast_bf16(dy.contiguous()), self._derived[key], None, epilogue=epi, residual=residual,
+            return ops.linear_bf16(self._act16(dy), self._derived[key], None, epilogue=epi, residual=residual,
                                    out_dtype=torch.float32)
         return self._mm(dy, wt() if callable(wt) else wt, None, epilogue=epi, residual=residual, wkey=("t", name))
 
@@ -300,6 +332,17 @@ class LXMERTTrainer:
 
     def _qkv_wgrad(self, a, dqkv, x):
         H = dqkv.shape[1] // 3
+        if self._tn_ok(dqkv[:, :H], x) and self._castable(dqkv):
+            # the three column blocks of dqkv are cast (with their bias gradients) into ONE bf16 [rows, 3H] buffer: its blocks are the
+            # transposed-operand wgrad GEMMs' dy, the whole of it the stacked dgrad GEMM's
+            d16 = torch.empty(dqkv.shape, dtype=torch.bfloat16, device=dqkv.device)
+            for j, name in enumerate((a.q, a.k, a.v)):
+                ops.cast_bf16_colsum(dqkv[:, j * H:(j + 1) * H], colsum_into=self.g[name + ".bias"], out=d16[:, j * H:(j + 1) * H])
+            self._a16[(dqkv.data_ptr(), tuple(dqkv.shape), tuple(dqkv.stride()))] = (dqkv, d16)
+            x16 = self._act16(x)
+            for j, name in enumerate((a.q, a.k, a.v)):
+                ops.linear_bf16_accumulate_tn_(self.g[name + ".weight"], d16[:, j * H:(j + 1) * H], x16)
+            return
         xt = []                                               # Q, K and V share their input: transpose it once
         for j, name in enumerate((a.q, a.k, a.v)):
             self._wgrad(name, dqkv[:, j * H:(j + 1) * H], x, xt)
@@ -393,6 +436,7 @@ class LXMERTTrainer:
         """zero grads, forward, loss, backward (+ the bucketed all-reduces): everything of a step that does not depend on the
         step counter, i.e. what a CUDA graph can replay.  Returns the fp64 loss accumulator (device)."""
         lib = L.load()
+        self._a16.clear()
         self.flat_g.zero_()
         logits, _ = self.forward(feat, pos, ids, seg, mask)
         target = target.to(self.dev, torch.float32).contiguous()
@@ -467,6 +511,7 @@ class LXMERTTrainer:
                 first = end + 1
             st["graph"] = st["graphs"][0]
             self._derived.clear()          # tensors created under capture live in the graph's pool: never reuse them eagerly
+            self._a16.clear()
         for dst, src in zip(st["inputs"], args):
             dst.copy_(src, non_blocking=True)
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
@@ -502,6 +547,7 @@ class LXMERTTrainer:
                                        L.ptr(sumsq), float(self.clip_norm)), "rgqa_bertadam_step")
         self.step_count += 1
         self._derived.clear()                                           # stacked / transposed copies are stale now
+        self._a16.clear()
         return float(loss), float(sumsq.sqrt())
 
     def state_dict(self):

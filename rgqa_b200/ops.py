@@ -171,6 +171,34 @@ def linear_bf16_accumulate_(out, x, weight):
     return out
 
 
+def linear_bf16_accumulate_tn_(out, at, bt):
+    """out [M, N] f32 += atᵀ · bt for bf16 at [K, M], bt [K, N] (row strides allowed): the weight gradient dW += dYᵀ · X straight
+    from the rows of dY and X — the tensor cores read both operands MN-major, nothing is transposed in memory.  In place."""
+    _need_cuda(out, at, bt)
+    assert at.dtype == bt.dtype == torch.bfloat16 and out.dtype == torch.float32
+    assert at.stride(1) == 1 and bt.stride(1) == 1 and out.stride(1) == 1 and at.shape[0] == bt.shape[0]
+    K, M = at.shape
+    N = bt.shape[1]
+    assert out.shape == (M, N)
+    L.check(L.load().rgqa_gemm_bf16_accum_tn(L.current_stream_ptr(), L.ptr(at), at.stride(0), L.ptr(bt), bt.stride(0), L.ptr(out),
+                                             out.stride(0), M, N, K), "rgqa_gemm_bf16_accum_tn")
+    return out
+
+
+def cast_bf16_colsum(x, colsum_into=None, out=None):
+    """bf16 copy of an fp32 [R, C] view (row stride allowed) — dense, or into ``out`` (a bf16 [R, C] view, e.g. a column block of a
+    wider buffer); ``colsum_into`` [C] f32 += the column sums of x (same pass)."""
+    _need_cuda(x, colsum_into, out)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    R, C = x.shape
+    if out is None:
+        out = torch.empty((R, C), dtype=torch.bfloat16, device=x.device)
+    assert out.dtype == torch.bfloat16 and out.shape == (R, C) and out.stride(1) == 1
+    L.check(L.load().rgqa_cast_bf16_colsum(L.current_stream_ptr(), L.ptr(x), x.stride(0), L.ptr(out), out.stride(0), R, C,
+                                           L.ptr(colsum_into)), "rgqa_cast_bf16_colsum")
+    return out
+
+
 def linear_f32(x, weight, bias=None, epilogue=L.EPI_BIAS, residual=None):
     """fp32 CUDA-core GEMM with the same contract as :func:`linear_bf16` (precise path)."""
     _need_cuda(x, weight, bias, residual)

@@ -392,3 +392,40 @@ def test_accumulating_weight_gradient_gemm(cuda_device, M, N, K):
     torch.cuda.synchronize()
     ref = out0.double() + 2.0 * (a.double() @ w.double().t())
     torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=2e-3 * (K / 128) ** 0.5)   # fp32 accumulation order only
+
+
+@pytest.mark.parametrize("M,N,K", [(768, 768, 4608), (3072, 768, 2560), (768, 3072, 4608), (2304, 768, 128), (1840, 1536, 128),
+                                   (768, 2048, 4608), (768, 64, 2560)])
+def test_weight_gradient_gemm_from_transposed_operands(cuda_device, M, N, K):
+    """out += Atᵀ · Bt with At [K, M], Bt [K, N] row-major bf16 read MN-major by the tensor cores (dW += dYᵀ · X without any
+    transposing copy), strided operands (dY as a column slice of the stacked Q|K|V gradient), twice to check the accumulation."""
+    from rgqa_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    wide = torch.randn(K, M + 256, generator=g).to(torch.bfloat16).to(cuda_device)
+    at = wide[:, 128:128 + M]                                            # row stride M + 256, 256-byte aligned start
+    bt = torch.randn(K, N, generator=g).to(torch.bfloat16).to(cuda_device)
+    out0 = torch.randn(M, N, generator=g).to(cuda_device)
+    out = out0.clone()
+    ops.linear_bf16_accumulate_tn_(out, at, bt)
+    ops.linear_bf16_accumulate_tn_(out, at, bt)
+    torch.cuda.synchronize()
+    ref = out0.double() + 2.0 * (at.double().t() @ bt.double())
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=2e-3 * (K / 128) ** 0.5)
+
+
+@pytest.mark.parametrize("R,C,ld", [(2560, 768, 768), (4608, 768, 2304), (130, 72, 72), (128, 1844, 1844)])
+def test_cast_with_column_sums(cuda_device, R, C, ld):
+    from rgqa_b200 import ops
+    g = torch.Generator().manual_seed(R + C)
+    base = torch.randn(R, ld, generator=g).to(cuda_device)
+    x = base[:, ld - C:] if ld > C else base
+    acc0 = torch.randn(C, generator=g).to(cuda_device)
+    acc = acc0.clone()
+    y = ops.cast_bf16_colsum(x, colsum_into=acc)
+    y2 = ops.cast_bf16_colsum(x)
+    wide = torch.zeros(R, C + 16, dtype=torch.bfloat16, device=cuda_device)
+    ops.cast_bf16_colsum(x, out=wide[:, 8:8 + C])                       # into a column block of a wider buffer
+    torch.cuda.synchronize()
+    assert torch.equal(y, x.to(torch.bfloat16)) and torch.equal(y2, y) and torch.equal(wide[:, 8:8 + C], y)
+    assert not wide[:, :8].any() and not wide[:, 8 + C:].any()
+    torch.testing.assert_close((acc - acc0).double(), x.double().sum(0), rtol=1e-5, atol=2e-4)
