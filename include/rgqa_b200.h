@@ -258,6 +258,11 @@ int rgqa_tanh_bwd(void* stream, const float* dy, const float* y, float* dx, int6
 int rgqa_attention_bwd(void* stream, const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                        const int32_t* key_mask, const float* dctx, int64_t ldo, float* dq, int64_t lddq, float* dk, int64_t lddk,
                        float* dv, int64_t lddv, int B, int Lq, int Lk, int heads, float dropout_p, uint64_t seed);
+/* The same backward with bf16 operands on the tensor cores (mma.sync, fp32 accumulation and softmax; no dropout): the
+ * mixed-precision training step's form, ~2e-2 relative to rgqa_attention_bwd. */
+int rgqa_attention_bwd_bf16(void* stream, const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                            const int32_t* key_mask, const float* dctx, int64_t ldo, float* dq, int64_t lddq, float* dk, int64_t lddk,
+                            float* dv, int64_t lddv, int B, int Lq, int Lk, int heads);
 /* Training-mode dropout (the reference trains with p = 0.1: hidden_dropout_prob / attention_probs_dropout_prob of BertConfig).
  * Masks come from a counter-based generator keyed by (seed, element index): the backward passes regenerate them, nothing is stored;
  * they are NOT torch's masks, so parity with the reference under dropout is statistical only.

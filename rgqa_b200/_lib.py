@@ -79,6 +79,7 @@ SIGNATURES = {
     "rgqa_gelu_fwd": (_i, [_vp, _vp, _vp, _i64]),
     "rgqa_gelu_bwd": (_i, [_vp, _vp, _vp, _vp, _i64]),
     "rgqa_tanh_bwd": (_i, [_vp, _vp, _vp, _vp, _i64]),
+    "rgqa_attention_bwd_bf16": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i]),
     "rgqa_attention_bwd": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _f, C.c_uint64]),
     "rgqa_attention_dropout": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _f, C.c_uint64]),
     "rgqa_transpose_cast_bf16": (_i, [_vp, _vp, _i64, _vp, _i, _i]),

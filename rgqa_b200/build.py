@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT_DIR = PKG / "_C"
 LIB = OUT_DIR / "librgqa_b200.so"
-SOURCES = ["api.cu", "prof.cu", "gemm_tcgen05.cu", "gemm_ln_tcgen05.cu", "visn_embed_tcgen05.cu", "qkv_attn_tcgen05.cu", "gemm_simt.cu", "attention.cu", "rowops.cu", "scorers.cu", "estimator.cu", "optim.cu", "backward.cu"]
+SOURCES = ["api.cu", "prof.cu", "gemm_tcgen05.cu", "gemm_ln_tcgen05.cu", "visn_embed_tcgen05.cu", "qkv_attn_tcgen05.cu", "gemm_simt.cu", "attention.cu", "rowops.cu", "scorers.cu", "estimator.cu", "optim.cu", "backward.cu", "attention_bwd_mma.cu"]
 HEADERS = ["common.cuh", "kernels.h", "../../include/rgqa_b200.h"]
 
 NVCC_FLAGS = [

@@ -1867,6 +1867,12 @@ int rgqa_attention_bwd(void* stream, const float* q, int64_t ldq, const float* k
   return attention_bwd(static_cast<cudaStream_t>(stream), q, ldq, k, ldk, v, ldv, key_mask, dctx, ldo, dq, lddq, dk, lddk, dv, lddv,
                        B, Lq, Lk, heads, dropout_p, seed);
 }
+int rgqa_attention_bwd_bf16(void* stream, const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                            const int32_t* key_mask, const float* dctx, int64_t ldo, float* dq, int64_t lddq, float* dk, int64_t lddk,
+                            float* dv, int64_t lddv, int B, int Lq, int Lk, int heads) {
+  return attention_bwd_bf16(static_cast<cudaStream_t>(stream), q, ldq, k, ldk, v, ldv, key_mask, dctx, ldo, dq, lddq, dk, lddk, dv, lddv,
+                            B, Lq, Lk, heads);
+}
 int rgqa_attention_dropout(void* stream, const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                            const int32_t* key_mask, float* out, int64_t ldo, int B, int Lq, int Lk, int heads, float dropout_p,
                            uint64_t seed) {

@@ -203,6 +203,11 @@ int attention_bwd(cudaStream_t stream, const float* q, long long ldq, const floa
                   long long ldv, const int32_t* key_mask, const float* dctx, long long ldo, float* dq, long long lddq, float* dk,
                   long long lddk, float* dv, long long lddv, int B, int Lq, int Lk, int heads, float drop_p = 0.f,
                   unsigned long long drop_seed = 0);
+// The same backward on the tensor cores (attention_bwd_mma.cu): q / k / v / dctx cast to bf16 on the way into shared memory, the five
+// products as mma.sync m16n8k16 with fp32 accumulation, softmax in fp32; no dropout.  The mixed-precision training step's kernel.
+int attention_bwd_bf16(cudaStream_t stream, const float* q, long long ldq, const float* k, long long ldk, const float* v,
+                       long long ldv, const int32_t* key_mask, const float* dctx, long long ldo, float* dq, long long lddq, float* dk,
+                       long long lddk, float* dv, long long lddv, int B, int Lq, int Lk, int heads);
 // y = x - noise * sign(grad) (sign = +1 where grad >= 0): ODIN / Mahalanobis-with-noise input step (gqa_odin.py:118-120)
 int sign_step(cudaStream_t stream, const float* x, const float* grad, float* y, long long n, float noise);
 int dropout_add(cudaStream_t stream, const float* x, const float* resid, float* y, long long n, float p, unsigned long long seed);

@@ -327,7 +327,8 @@ class LXMERTTrainer:
         self._lin_wgrad(a.out, d_h, tp["ctx"])
         d_ctx = self._dgrad(d_h, a.out, lambda: self._wt(a.out))
         ops.attention_bwd(tp["qkv_q"], tp["qkv_kv"], d_ctx, dqkv_q, dqkv_kv, tp["B"], tp["Lq"], tp["Lk"], key_mask=tp["mask"], heads=self.heads,
-                          p=self.dropout if tp["s_att"] else 0.0, seed=tp["s_att"])
+                          p=self.dropout if tp["s_att"] else 0.0, seed=tp["s_att"],
+                          bf16=self.gemm == "bf16" and not tp["s_att"])     # mixed precision: the attention products on the tensor cores too
         return d_pre
 
     def _qkv_wgrad(self, a, dqkv, x):

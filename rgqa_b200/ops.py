@@ -435,15 +435,23 @@ def dropout_add(x, resid=None, p=0.1, seed=0):
     return y
 
 
-def attention_bwd(qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv, B, Lq, Lk, key_mask=None, heads=12, p=0.0, seed=0):
+def attention_bwd(qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv, B, Lq, Lk, key_mask=None, heads=12, p=0.0, seed=0, bf16=False):
     """Backward of :func:`attention`: Q from ``qkv_q`` [B*Lq, 3H], K / V from ``qkv_kv`` [B*Lk, 3H], ``dctx`` [B*Lq, H];
-    writes dQ into columns [0, H) of ``dqkv_q`` and dK, dV into columns [H, 3H) of ``dqkv_kv`` (f32, fused layout)."""
+    writes dQ into columns [0, H) of ``dqkv_q`` and dK, dV into columns [H, 3H) of ``dqkv_kv`` (f32, fused layout).
+    ``bf16=True`` (no dropout): the five products on the tensor cores with bf16 operands (the mixed-precision training step)."""
     _need_cuda(qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv, key_mask)
     H = heads * 64
     for t in (qkv_q, qkv_kv, dctx, dqkv_q, dqkv_kv):
         assert t.dtype == torch.float32 and t.is_contiguous()
     assert qkv_q.shape == dqkv_q.shape == (B * Lq, 3 * H) and qkv_kv.shape == dqkv_kv.shape == (B * Lk, 3 * H)
     assert dctx.shape == (B * Lq, H)
+    if bf16:
+        assert p == 0.0, "the tensor-core attention backward has no dropout"
+        L.check(L.load().rgqa_attention_bwd_bf16(L.current_stream_ptr(), L.ptr(qkv_q), 3 * H, qkv_kv.data_ptr() + H * 4, 3 * H,
+                                                 qkv_kv.data_ptr() + 2 * H * 4, 3 * H, L.ptr(key_mask), L.ptr(dctx), H,
+                                                 L.ptr(dqkv_q), 3 * H, dqkv_kv.data_ptr() + H * 4, 3 * H,
+                                                 dqkv_kv.data_ptr() + 2 * H * 4, 3 * H, B, Lq, Lk, heads), "rgqa_attention_bwd_bf16")
+        return
     L.check(L.load().rgqa_attention_bwd(L.current_stream_ptr(), L.ptr(qkv_q), 3 * H, qkv_kv.data_ptr() + H * 4, 3 * H,
                                         qkv_kv.data_ptr() + 2 * H * 4, 3 * H, L.ptr(key_mask), L.ptr(dctx), H,
                                         L.ptr(dqkv_q), 3 * H, dqkv_kv.data_ptr() + H * 4, 3 * H,

@@ -19,8 +19,9 @@ for Lq, Lk in ((36, 36), (20, 20), (20, 36), (36, 20)):
         for _ in range(3):
             ops.attention_bwd(qkv_q, qkv_kv, dctx, dq, dkv, B, Lq, Lk)
         continue
-    for name, fn in (("bwd", lambda: ops.attention_bwd(qkv_q, qkv_kv, dctx, dq, dkv, B, Lq, Lk)),
-                     ("fwd", lambda: ops.attention(qkv_q, qkv_kv, B, Lq, Lk))):
+    for name, fn in (("bwd fp32 CUDA cores", lambda: ops.attention_bwd(qkv_q, qkv_kv, dctx, dq, dkv, B, Lq, Lk)),
+                     ("bwd bf16 tensor cores", lambda: ops.attention_bwd(qkv_q, qkv_kv, dctx, dq, dkv, B, Lq, Lk, bf16=True)),
+                     ("fwd fp32", lambda: ops.attention(qkv_q, qkv_kv, B, Lq, Lk))):
         for _ in range(5):
             fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -30,5 +31,5 @@ for Lq, Lk in ((36, 36), (20, 20), (20, 36), (36, 20)):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        print(f"attention {name} B={B} Lq={Lq} Lk={Lk}: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us")
+        print(f"attention {name:22s} B={B} Lq={Lq} Lk={Lk}: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us")
 torch.cuda.synchronize()
