@@ -169,7 +169,8 @@ class LXMERTInputGrad:
         dQ / dK / dV land in the given fused gradient buffers (the caller turns those into input gradients)."""
         d_pre = ops.layernorm_bwd(dy, tp["pre"], w.g, eps=self.eps)
         d_ctx = self._mm(d_pre, w.out, transposed=True)
-        ops.attention_bwd(tp["qkv_q"], tp["qkv_kv"], d_ctx, dqkv_q, dqkv_kv, tp["B"], tp["Lq"], tp["Lk"], key_mask=tp["mask"], heads=self.heads)
+        ops.attention_bwd(tp["qkv_q"], tp["qkv_kv"], d_ctx, dqkv_q, dqkv_kv, tp["B"], tp["Lq"], tp["Lk"], key_mask=tp["mask"], heads=self.heads,
+                          bf16=self.gemm == "bf16")      # mixed precision: the attention products on the tensor cores as well
         return d_pre
 
     def _self_att_bwd(self, w, tp, dy):
