@@ -252,6 +252,11 @@ int rgqa_layernorm_bwd_params(void* stream, const float* dy, const float* x, con
 /* erf-GELU (modeling.py:112-118) forward and backward on n elements; tanh backward from the OUTPUT y (BertPooler :575-581). */
 int rgqa_gelu_fwd(void* stream, const float* x, float* y, int64_t n);
 int rgqa_gelu_bwd(void* stream, const float* dy, const float* x, float* dx, int64_t n);
+/* Mixed-precision training step: GELU with a bf16 result (n even), and BertLayerNorm writing its row twice — bf16 (the next GEMM's
+ * operand) and fp32 (the residual stream / the tape) — so that neither needs a separate cast kernel. */
+int rgqa_gelu_fwd_bf16(void* stream, const float* x, void* y_bf16, int64_t n);
+int rgqa_layernorm_dual(void* stream, const float* x, int64_t ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                        int M, int H, float eps);
 int rgqa_tanh_bwd(void* stream, const float* dy, const float* y, float* dx, int64_t n);
 /* BertAttention core backward (modeling.py:330-346): probabilities recomputed from q, k, v (f32, row strides ld*), gradients
  * of the three operands written to dq / dk / dv (same [row, head*64] layout, own strides).  Lq, Lk <= 64. */

@@ -75,6 +75,8 @@ SIGNATURES = {
     "rgqa_layernorm": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _f]),
     "rgqa_visn_combine": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f]),
     "rgqa_cast_f32_to_bf16": (_i, [_vp, _vp, _vp, _i64]),
+    "rgqa_gelu_fwd_bf16": (_i, [_vp, _vp, _vp, _i64]),
+    "rgqa_layernorm_dual": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _f]),
     "rgqa_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f]),
     "rgqa_gelu_fwd": (_i, [_vp, _vp, _vp, _i64]),
     "rgqa_gelu_bwd": (_i, [_vp, _vp, _vp, _vp, _i64]),

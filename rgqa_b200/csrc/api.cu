@@ -1858,6 +1858,14 @@ int rgqa_gelu_fwd(void* stream, const float* x, float* y, int64_t n) { return ge
 int rgqa_gelu_bwd(void* stream, const float* dy, const float* x, float* dx, int64_t n) {
   return gelu_bwd(static_cast<cudaStream_t>(stream), dy, x, dx, n);
 }
+int rgqa_gelu_fwd_bf16(void* stream, const float* x, void* y_bf16, int64_t n) {
+  return gelu_fwd_bf16(static_cast<cudaStream_t>(stream), x, y_bf16, n);
+}
+int rgqa_layernorm_dual(void* stream, const float* x, int64_t ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                        int M, int H, float eps) {
+  RGQA_CHECK(y_bf16 != nullptr && y_f32 != nullptr, "rgqa_layernorm_dual: null output");
+  return layernorm(static_cast<cudaStream_t>(stream), DT_BF16, x, ldx, gamma, beta, y_bf16, y_f32, M, H, eps);
+}
 int rgqa_tanh_bwd(void* stream, const float* dy, const float* y, float* dx, int64_t n) {
   return tanh_bwd(static_cast<cudaStream_t>(stream), dy, y, dx, n);
 }

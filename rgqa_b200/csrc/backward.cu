@@ -123,6 +123,14 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = gelu_erf(x[i]);
 }
+// the same activation with a bf16 result: in the mixed-precision step GELU(x) is only ever a GEMM operand (FFN2, and its weight gradient)
+__global__ void __launch_bounds__(256) gelu_fwd_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n2) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    const float2 v = reinterpret_cast<const float2*>(x)[i];
+    reinterpret_cast<uint32_t*>(y)[i] = pack_bf16x2(gelu_erf(v.x), gelu_erf(v.y));
+  }
+}
 __global__ void __launch_bounds__(256)
 gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, long long n) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -397,6 +405,14 @@ int layernorm_bwd_params(cudaStream_t stream, const float* dy, const float* x, c
 int gelu_fwd(cudaStream_t stream, const float* x, float* y, long long n) {
   RGQA_CHECK(x && y && n > 0, "gelu_fwd: bad arguments");
   gelu_fwd_kernel<<<ew_grid(n), 256, 0, stream>>>(x, y, n);
+  note_launch();
+  RGQA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int gelu_fwd_bf16(cudaStream_t stream, const float* x, void* y, long long n) {
+  RGQA_CHECK(x && y && n > 0 && n % 2 == 0 && reinterpret_cast<uintptr_t>(x) % 8 == 0 && reinterpret_cast<uintptr_t>(y) % 4 == 0,
+             "gelu_fwd_bf16: bad arguments (n must be even, pointers aligned)");
+  gelu_fwd_bf16_kernel<<<ew_grid(n / 2), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(y), n / 2);
   note_launch();
   RGQA_CUDA_OK(cudaGetLastError());
   return 0;

@@ -197,6 +197,7 @@ int layernorm_bwd(cudaStream_t stream, const float* dy, const float* x, const fl
 int layernorm_bwd_params(cudaStream_t stream, const float* dy, const float* x, const float* gamma, const float* add, float* dx,
                          float* dgamma, float* dbeta, int M, int H, float eps, float scale);
 int gelu_fwd(cudaStream_t stream, const float* x, float* y, long long n);
+int gelu_fwd_bf16(cudaStream_t stream, const float* x, void* y_bf16, long long n);   // n even
 int gelu_bwd(cudaStream_t stream, const float* dy, const float* x, float* dx, long long n);
 int tanh_bwd(cudaStream_t stream, const float* dy, const float* y, float* dx, long long n);
 int attention_bwd(cudaStream_t stream, const float* q, long long ldq, const float* k, long long ldk, const float* v,

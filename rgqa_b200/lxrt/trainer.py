@@ -148,6 +148,14 @@ class LXMERTTrainer:
             self._derived[key] = ops.cast_bf16(make().contiguous())
         return self._derived[key]
 
+    def _ln(self, x, name):
+        """LayerNorm(x); in mixed precision the kernel also leaves the bf16 copy the next GEMM wants (no cast kernel for it)."""
+        if self.gemm == "bf16" and x.shape[1] in (768, 1536):
+            y32, y16 = ops.layernorm_dual(x, *self._w(name), self.eps)
+            self._a16[(y32.data_ptr(), tuple(y32.shape), tuple(y32.stride()))] = (y32, y16)
+            return y32
+        return ops.layernorm(x, *self._w(name), self.eps)
+
     @staticmethod
     def _castable(t):
         return t.dim() == 2 and t.stride(1) == 1 and t.shape[1] % 8 == 0 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0
@@ -156,6 +164,9 @@ class LXMERTTrainer:
         """bf16 copy of an fp32 activation or gradient, made ONCE per step: the forward's GEMM operand is the weight gradient's, a
         layer's dy feeds both its dgrad and its wgrad.  ``colsum_into``: the column sums of t (the bias gradient) ride on the cast.
         The source tensor is kept alive with its copy, so that a recycled address can never alias a stale entry."""
+        if t.dtype == torch.bfloat16:          # already a GEMM operand (bf16 attention context / GELU output of the mixed-precision step)
+            assert colsum_into is None
+            return t
         key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()))
         hit = self._a16.get(key)
         if hit is not None:
@@ -187,6 +198,8 @@ class LXMERTTrainer:
         """G[w] += dyᵀ · x, G[b] += colsum(dy).  ``xt``: a one-element list caching the bf16 transpose of x across calls that share x."""
         gw, gb = self.g[wname + ".weight"], self.g[wname + ".bias"]
         M = dy.shape[0]
+        if x.dtype != torch.float32 and not self._tn_ok(dy, x):
+            x = x.float()                          # (a bf16 operand copy met a shape the transposed-operand GEMM does not take)
         if self._tn_ok(dy, x):
             # one pass over dy: its bf16 copy (the dgrad GEMM reuses it) + the bias gradient; x's bf16 copy is the forward's
             ops.linear_bf16_accumulate_tn_(gw, self._act16(dy, colsum_into=gb), self._act16(x))
@@ -219,15 +232,20 @@ class LXMERTTrainer:
             s_att, s_out = self._next_seed(), self._next_seed()
             ctx = ops.attention_dropout(qkv_q, qkv_kv, B, Lq, Lk, key_mask=mask, heads=self.heads, p=self.dropout, seed=s_att)
             pre = ops.dropout_add(self._mm(ctx, wo, bo, wkey=a.out), x_q, self.dropout, s_out)       # dense -> dropout -> + input
+        elif self.gemm == "bf16" and qkv_q.shape[0] % 64 == 0 and self._castable(qkv_q) and self._castable(qkv_kv):
+            # mixed precision: the attention on the tensor cores too (bf16 Q, K, V; bf16 context = the output projection's operand)
+            q16 = self._act16(qkv_q)
+            ctx = ops.attention(q16, q16 if qkv_kv is qkv_q else self._act16(qkv_kv), B, Lq, Lk, key_mask=mask, heads=self.heads)
+            pre = self._mm(ctx, wo, bo, epilogue=L.EPI_RESID, residual=x_q, wkey=a.out)
         else:
             ctx = ops.attention(qkv_q, qkv_kv, B, Lq, Lk, key_mask=mask, heads=self.heads)
             pre = self._mm(ctx, wo, bo, epilogue=L.EPI_RESID, residual=x_q, wkey=a.out)
-        y = ops.layernorm(pre, *self._w(a.ln), self.eps)
+        y = self._ln(pre, a.ln)
         return y, dict(x_q=x_q, qkv_q=qkv_q, qkv_kv=qkv_kv, ctx=ctx, pre=pre, B=B, Lq=Lq, Lk=Lk, mask=mask, s_att=s_att, s_out=s_out)
 
     def _ffn_fwd(self, f, x):
         pg = self._mm(x, *self._w(f.inter), wkey=f.inter)
-        inter = ops.gelu_fwd(pg)
+        inter = ops.gelu_fwd(pg, out_dtype=torch.bfloat16 if (self.gemm == "bf16" and pg.shape[0] % 64 == 0 and self.dropout == 0) else torch.float32)
         wo, bo = self._w(f.out)
         s_out = 0
         if self.dropout > 0:
@@ -235,7 +253,7 @@ class LXMERTTrainer:
             pre = ops.dropout_add(self._mm(inter, wo, bo, wkey=f.out), x, self.dropout, s_out)
         else:
             pre = self._mm(inter, wo, bo, epilogue=L.EPI_RESID, residual=x, wkey=f.out)
-        return ops.layernorm(pre, *self._w(f.ln), self.eps), dict(x=x, pg=pg, inter=inter, pre=pre, s_out=s_out)
+        return self._ln(pre, f.ln), dict(x=x, pg=pg, inter=inter, pre=pre, s_out=s_out)
 
     def forward(self, feat, pos, ids, seg, mask):
         dev = self.dev

@@ -260,6 +260,19 @@ def layernorm(x, gamma, beta, eps=1e-12, out_dtype=torch.float32):
     return out
 
 
+def layernorm_dual(x, gamma, beta, eps=1e-12):
+    """(fp32 y, bf16 y) = LayerNorm(x) written twice by one kernel: the fp32 rows are the residual stream / the tape, the bf16
+    rows the next GEMM's operand (mixed-precision training step)."""
+    _need_cuda(x, gamma, beta)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    M, H = x.shape
+    y32 = torch.empty((M, H), dtype=torch.float32, device=x.device)
+    y16 = torch.empty((M, H), dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().rgqa_layernorm_dual(L.current_stream_ptr(), L.ptr(x), x.stride(0), L.ptr(gamma), L.ptr(beta), L.ptr(y16), L.ptr(y32),
+                                         M, H, eps), "rgqa_layernorm_dual")
+    return y32, y16
+
+
 def visn_combine(x_pre, boxes, box_w, box_b, g1, b1, g2, b2, eps=1e-12, out_dtype=torch.float32):
     """Tail of VisualFeatEncoder.forward (src/lxrt/modeling.py:507-517): (LN(x_pre) + LN(box_fc(boxes))) / 2."""
     _need_cuda(x_pre, boxes, box_w, box_b, g1, b1, g2, b2)
@@ -389,9 +402,13 @@ def layernorm_bwd_params_(dgamma, dbeta, dy, x, gamma, add=None, eps=1e-12, scal
     return dx
 
 
-def gelu_fwd(x):
+def gelu_fwd(x, out_dtype=torch.float32):
     _need_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous()
+    if out_dtype == torch.bfloat16:
+        y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        L.check(L.load().rgqa_gelu_fwd_bf16(L.current_stream_ptr(), L.ptr(x), L.ptr(y), x.numel()), "rgqa_gelu_fwd_bf16")
+        return y
     y = torch.empty_like(x)
     L.check(L.load().rgqa_gelu_fwd(L.current_stream_ptr(), L.ptr(x), L.ptr(y), x.numel()), "rgqa_gelu_fwd")
     return y

@@ -471,3 +471,35 @@ def test_tensor_core_attention_backward(cuda_device, B, Lq, Lk, masked):
         assert float((got - want).norm() / want.norm()) <= 6e-3
     for got, want in zip(dq_kv[True], dq_kv[False]):
         assert float((got - want).norm() / want.norm()) <= 6e-3
+
+
+def test_mixed_precision_step_at_64_row_multiples_tracks_the_fp32_step(cuda_device):
+    """B = 16 (320 language rows, 576 visual rows: multiples of 64) switches the mixed-precision step onto its tensor-core forms
+    everywhere — bf16 attention forward and backward, LayerNorm / GELU kernels that leave the next GEMM's bf16 operand, weight
+    gradients from transposed operands with K split over CTA pairs, one cast + bias-gradient pass per dy.  Against the fp32 step of the
+    same trainer class (itself pinned to the reference trajectory above): loss 2e-3, gradient norm 2 %, every parameter tensor's
+    gradient 6 % in relative L2 (biases and LayerNorm parameters included), flat gradient cosine >= 0.999."""
+    from rgqa_b200.lxrt.trainer import LXMERTTrainer
+    layers = dict(l_layers=2, x_layers=2, r_layers=1)
+    sd = syn.lxmert_state_dict(variant="rich", **layers)
+    inp = syn.make_inputs(16, 20, seed=31)
+    g = torch.Generator().manual_seed(7)
+    target = torch.zeros(16, 1842)
+    target[torch.arange(16), torch.randint(0, 1842, (16,), generator=g)] = 1.0
+    out = {}
+    for gemm in ("fp32", "bf16"):
+        tr = LXMERTTrainer(sd, device=cuda_device, lr=1e-4, warmup=0.1, t_total=20, gemm=gemm, **layers)
+        loss = tr._grad_pass(inp["feat"], inp["pos"], inp["ids"], inp["seg"], inp["mask"], target)
+        torch.cuda.synchronize()
+        out[gemm] = (float(loss), tr.flat_g.clone(), {n: t.clone() for n, t in tr.g.items()})
+    (l32, f32, g32), (l16, f16, g16) = out["fp32"], out["bf16"]
+    assert l16 == pytest.approx(l32, rel=2e-3)
+    assert float(f16.norm()) == pytest.approx(float(f32.norm()), rel=2e-2)
+    assert float((f16 * f32).sum() / (f16.norm() * f32.norm())) >= 0.999
+    # (key biases have a mathematically zero gradient — softmax ignores a shift of all scores of a row — so theirs is rounding noise
+    # in both runs; tensors below 1e-4 of the global norm are compared on the absolute scale instead)
+    floor = 1e-4 * float(f32.norm())
+    rel = sorted(((float((g16[n] - g32[n]).norm() / g32[n].norm()), n) for n in g32 if float(g32[n].norm()) > floor), reverse=True)
+    assert len(rel) >= 0.7 * len(g32) and rel[0][0] <= 6e-2, rel[:5]
+    small = max((float((g16[n] - g32[n]).norm()) for n in g32 if float(g32[n].norm()) <= floor), default=0.0)
+    assert small <= floor, small
