@@ -1700,6 +1700,10 @@ int rgqa_set_option(const char* name, int value) {
     option_set(OPT_ATTN_FUSED, value);
     return 0;
   }
+  if (strcmp(name, "pair_deep") == 0) {
+    option_set(OPT_PAIR_DEEP, value);
+    return 0;
+  }
   if (strcmp(name, "attn_straddle") == 0) {
     option_set(OPT_ATTN_STRADDLE, value);
     return 0;

@@ -605,8 +605,11 @@ template <bool STAGED, bool RESID_SMEM, int EW, int RING = kResidRing, bool H16 
 struct PairCfg {
   static constexpr int kGroups = EW / 4;
   static constexpr int kBufBytes = H16 ? kSlabBytes / 2 : kSlabBytes;
-  static constexpr int kStages = RESID_SMEM ? (H16 ? (RING == 2 ? 6 : 5) : (RING == 2 ? kResidStages + 1 : kResidStages)) : (STAGED ? 5 : 6);
-  static constexpr int kBufsPerGroup = RESID_SMEM ? RING : (STAGED ? (EW == 16 ? 1 : 2) : 0);
+  // plain staged epilogues (no residual ring): RING == 2 selects the "deep" variant — one staging slab per group instead of two,
+  // the 32 KB it frees is a sixth main-loop stage (A/B option pair_deep)
+  static constexpr int kStages = RESID_SMEM ? (H16 ? (RING == 2 ? 6 : 5) : (RING == 2 ? kResidStages + 1 : kResidStages))
+                                            : (STAGED ? (RING == 2 ? 6 : 5) : 6);
+  static constexpr int kBufsPerGroup = RESID_SMEM ? RING : (STAGED ? ((EW == 16 || RING == 2) ? 1 : 2) : 0);
   static constexpr int kSlabRegion = kGroups * kBufsPerGroup * kBufBytes;
   static constexpr int kSmemBytes = kStages * kPairStageBytes + kSlabRegion + 1024 + 512;
 };
@@ -1246,6 +1249,9 @@ int launch_pair_sel(cudaStream_t s, const CUtensorMap& a, const CUtensorMap& b, 
   }
   if constexpr (EPI == EPI_GELU && sizeof(OutT) == 2) {  // option "gelu_ew16": 16 epilogue warps (96 registers) for the erf-GELU
     if (staged && option_get(OPT_GELU_EW16) != 0) return launch_pair<EPI, OutT, true, kResidRing, 16>(s, a, b, o, r, p);
+  }
+  if constexpr ((EPI == EPI_GELU || EPI == EPI_BIAS) && sizeof(OutT) == 2) {  // option "pair_deep": six stages, one staging slab
+    if (staged && option_get(OPT_PAIR_DEEP) != 0) return launch_pair<EPI, OutT, true, 2>(s, a, b, o, r, p);
   }
   return staged ? launch_pair<EPI, OutT, true>(s, a, b, o, r, p) : launch_pair<EPI, OutT, false>(s, a, b, o, r, p);
 }

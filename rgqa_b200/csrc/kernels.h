@@ -253,7 +253,8 @@ enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_GEMM_DEBUG = 2, 
   OPT_GELU_EW16 = 14,  // FFN1 (erf-GELU consumer) with 16 epilogue warps instead of 8 (A/B measurement)
   OPT_ATTN_STRADDLE = 15,  // fused projection + attention, S = 36: seven whole samples per CTA pair, sample 3's K / V through DSMEM (off:
                            // 14 % fewer tiles, same time — the kernel is bound by its attention tasks, not by its main loop)
-  OPT_COUNT = 16 };
+  OPT_PAIR_DEEP = 16,  // bf16-output consumers (Q|K|V, FFN1): six main-loop stages and one staging slab per group (A/B measurement)
+  OPT_COUNT = 20 };
 int option_get(int key);
 void option_set(int key, int value);
 

@@ -8,7 +8,8 @@ from rgqa_b200 import ops, _lib as L
 lib = L.load()
 dev = torch.device("cuda")
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-variants = [("gelu", L.EPI_GELU, 0, 0), ("gelu, 16 epilogue warps", L.EPI_GELU, 0, 1), ("bias only", L.EPI_BIAS, 0, 0),
+variants = [("gelu", L.EPI_GELU, 0, 0), ("gelu, 16 epilogue warps", L.EPI_GELU, 0, 1), ("gelu, 6 stages / 1 slab", L.EPI_GELU, 0, 2),
+            ("bias only", L.EPI_BIAS, 0, 0), ("bias only, 6 stages / 1 slab", L.EPI_BIAS, 0, 2),
             ("gelu, no TMA stores", L.EPI_GELU, 1, 0), ("bias, no TMA stores", L.EPI_BIAS, 1, 0),
             ("no math, no staging (stores of stale smem)", L.EPI_GELU, 2, 0), ("bare main loop", L.EPI_GELU, 3, 0)]
 for M in (36864, 20480):
@@ -18,7 +19,8 @@ for M in (36864, 20480):
     res = {v[0]: [] for v in variants}
     for rep in range(12):
         for name, epi, dbg, ew in variants:
-            lib.rgqa_set_option(b"gelu_ew16", ew)
+            lib.rgqa_set_option(b"gelu_ew16", 1 if ew == 1 else 0)
+            lib.rgqa_set_option(b"pair_deep", 1 if ew == 2 else 0)
             lib.rgqa_set_option(b"gemm_debug", dbg)
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -32,4 +34,5 @@ for M in (36864, 20480):
         ms = sorted(res[name])[len(res[name]) // 2]
         print(f"N=3072 K=768 M={M} {name:44s}: {ms * 1e3:7.1f} us  {2.0 * M * 3072 * 768 / ms / 1e9:7.1f} TFLOP/s")
 lib.rgqa_set_option(b"gelu_ew16", 0)
+lib.rgqa_set_option(b"pair_deep", 0)
 lib.rgqa_set_option(b"gemm_debug", 0)
