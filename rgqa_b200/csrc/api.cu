@@ -1119,6 +1119,16 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
     RGQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   }
   cudaStream_t sv = two ? h->side : st;
+  // option "sm_split": while both chains are in flight their persistent kernels get disjoint shares of the SMs (pairs), in
+  // proportion to the rows they process, so that they run side by side instead of taking turns on the whole chip
+  const bool split = two && option_get(OPT_SM_SPLIT) != 0;
+  const int all = num_sms();
+  auto share = [&](double frac) { int s = static_cast<int>(all * frac / 2.0 + 0.5) * 2; return s < 2 ? 2 : (s > all - 2 ? all - 2 : s); };
+  // phase 1: c.l_layers language layers against c.r_layers visual layers; phase 2 (cross-modality layers): Ml against Mv rows
+  const double w_l1 = static_cast<double>(c.l_layers) * Ml, w_v1 = static_cast<double>(c.r_layers) * Mv + 0.35 * Mv;
+  const int sms_l1 = split && w_l1 > 0 && w_v1 > 0 ? share(w_l1 / (w_l1 + w_v1)) : 0, sms_v1 = sms_l1 ? all - sms_l1 : 0;
+  const int sms_l2 = split ? share(static_cast<double>(Ml) / Mt) : 0, sms_v2 = sms_l2 ? all - sms_l2 : 0;
+  struct BudgetReset { ~BudgetReset() { set_launch_sms(0); } } budget_reset;
   auto fork = [&]() -> int {
     if (!two) return 0;
     RGQA_CUDA_OK(cudaEventRecord(h->ev_fork, st));
@@ -1135,6 +1145,7 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
 
   // ---- embeddings (modeling.py:876) and visual feature encoder (:507-517): normalised rows -> identity states ----
   // the row kernels emit the identity state themselves (lo = bf16 remainder, statistics (0, 768)): no fp32 round trip
+  set_launch_sms(sms_v1);   // the visual encoder and the relational layers (side stream)
   if (embed_ln(st, sdt, ids, seg, h->word, h->posemb, h->typeemb, h->emb_ln.g, h->emb_ln.b, cur.hi, nullptr, B, L, H,
                c.vocab_size, c.max_position, c.type_vocab, c.ln_eps, d.f16 ? nullptr : cur.lo, cur.stats))
     return 1;
@@ -1161,40 +1172,48 @@ static int lxmert_forward_deferred(rgqa_handle* h, cudaStream_t st, const void* 
       return 1;
   }
   const LNp *ln_l = nullptr, *ln_v = nullptr;  // LayerNorm still owed to the language / visual rows of `cur`
+  set_launch_sms(sms_l1);
   for (int i = 0; i < c.l_layers; ++i) {  // modeling.py:553-554
     const LayerW& w = h->l_layers[i];
     if (d.att(st, w.att, cur, ln_l, alt, 0, B, L, mask) || d.ffn(st, w.ffn, alt, &w.att.ln, cur, 0, static_cast<int>(Ml)))
       return 1;
     ln_l = &w.ffn.ln;
   }
+  set_launch_sms(sms_v1);
   for (int i = 0; i < c.r_layers; ++i) {  // modeling.py:557-558
     const LayerW& w = h->r_layers[i];
     if (d.att(sv, w.att, cur, ln_v, alt, Ml, B, V, nullptr) || d.ffn(sv, w.ffn, alt, &w.att.ln, cur, Ml, static_cast<int>(Mv)))
       return 1;
     ln_v = &w.ffn.ln;
   }
+  set_launch_sms(0);
   if (join()) return 1;
   for (int i = 0; i < c.x_layers; ++i) {  // modeling.py:477-488
     const XLayerW& w = h->x_layers[i];
     char* ctx = static_cast<char*>(h->ctx.p);
     // ONE BertCrossattLayer for both directions (:455-459); its Q|K|V of each modality behind that modality's LayerNorm
     if (fork()) return 1;
-    if (d.qkv_proj(st, cur, ln_l, w.cross.qkv, w.cross.qkv_f, 0, static_cast<int>(Ml)) ||
-        d.qkv_proj(sv, cur, ln_v, w.cross.qkv, w.cross.qkv_f2, Ml, static_cast<int>(Mv)))
-      return 1;
+    set_launch_sms(sms_l2);
+    if (d.qkv_proj(st, cur, ln_l, w.cross.qkv, w.cross.qkv_f, 0, static_cast<int>(Ml))) return 1;
+    set_launch_sms(sms_v2);
+    if (d.qkv_proj(sv, cur, ln_v, w.cross.qkv, w.cross.qkv_f2, Ml, static_cast<int>(Mv))) return 1;
+    set_launch_sms(0);
     if (join()) return 1;
     // language queries over visual keys (no mask), visual queries over language keys (language mask)
     if (d.attn(st, 0, Ml, nullptr, ctx, B, L, V) || d.attn(st, Ml, 0, mask, rows_at(ctx, Ml, H, 2), B, V, L)) return 1;
     if (fork()) return 1;
     // cross output + self attention + FFN per modality (:455-475), the two chains side by side
+    set_launch_sms(sms_l2);
     if (d.produce(st, ctx, H, w.cross.out, w.cross.out_bb, cur, ln_l, alt, 0, static_cast<int>(Ml)) ||
         d.att(st, w.lang_self, alt, &w.cross.ln, cur, 0, B, L, mask) ||
         d.ffn(st, w.lang_ffn, cur, &w.lang_self.ln, alt, 0, static_cast<int>(Ml)))
       return 1;
+    set_launch_sms(sms_v2);
     if (d.produce(sv, rows_at(ctx, Ml, H, 2), H, w.cross.out, w.cross.out_bb2, cur, ln_v, alt, Ml, static_cast<int>(Mv)) ||
         d.att(sv, w.visn_self, alt, &w.cross.ln, cur, Ml, B, V, nullptr) ||
         d.ffn(sv, w.visn_ffn, cur, &w.visn_self.ln, alt, Ml, static_cast<int>(Mv)))
       return 1;
+    set_launch_sms(0);
     if (join()) return 1;
     ln_l = &w.lang_ffn.ln;
     ln_v = &w.visn_ffn.ln;
@@ -1698,6 +1717,10 @@ int rgqa_set_option(const char* name, int value) {
   }
   if (strcmp(name, "attn_fused") == 0) {
     option_set(OPT_ATTN_FUSED, value);
+    return 0;
+  }
+  if (strcmp(name, "sm_split") == 0) {
+    option_set(OPT_SM_SPLIT, value);
     return 0;
   }
   if (strcmp(name, "pair_deep") == 0) {

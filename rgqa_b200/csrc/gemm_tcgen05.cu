@@ -1176,6 +1176,10 @@ int num_sms() {
   return n;
 }
 
+static int g_launch_sms = 0;
+int launch_sms() { return (g_launch_sms > 0 && g_launch_sms < num_sms()) ? g_launch_sms : num_sms(); }
+void set_launch_sms(int sms) { g_launch_sms = sms; }
+
 namespace {
 
 template <int BN, int EPI, typename OutT>
@@ -1230,7 +1234,7 @@ int launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& 
     configured = true;
   }
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + kPairBN - 1) / kPairBN) * ((EPI == EPI_ACCUM && p.splits > 1) ? p.splits : 1);
-  const int max_pairs = num_sms() / 2;
+  const int max_pairs = launch_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   void* tok = prof_begin(stream);
   RGQA_CUDA_OK(launch_pdl(kern, dim3(2 * pairs), dim3((4 + EW) * 32), smem, stream, tmA, tmB, tmOut, tmRes,

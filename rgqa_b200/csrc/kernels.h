@@ -139,6 +139,10 @@ int make_tmap_ex(::CUtensorMap_st* map, const void* ptr, long long rows, long lo
 int make_tmap_3d(::CUtensorMap_st* map, const void* ptr, long long d0, long long d1, long long d2, long long stride1_bytes,
                  long long stride2_bytes, int b0, int b1, int b2);
 int num_sms();
+// SMs a persistent kernel launched NOW may occupy (its grid): num_sms() unless the engine has set a budget for the stream it is
+// enqueueing on (option "sm_split": the language and visual chains of a forward run side by side on disjoint SM sets)
+int launch_sms();
+void set_launch_sms(int sms);   // 0 = no budget
 
 // ---- attention (small sequences, Lq, Lk <= 64, 12 heads x 64) -----------------------------------
 // q/k/v point at the first row of sample 0 (head 0); rows are ldq/ldk/ldv elements apart; sample b
@@ -254,6 +258,7 @@ enum Option : int { OPT_GEMM_PAIR = 0, OPT_GEMM_STAGED = 1, OPT_GEMM_DEBUG = 2, 
   OPT_ATTN_STRADDLE = 15,  // fused projection + attention, S = 36: seven whole samples per CTA pair, sample 3's K / V through DSMEM (off:
                            // 14 % fewer tiles, same time — the kernel is bound by its attention tasks, not by its main loop)
   OPT_PAIR_DEEP = 16,  // bf16-output consumers (Q|K|V, FFN1): six main-loop stages and one staging slab per group (A/B measurement)
+  OPT_SM_SPLIT = 17,   // two-stream forward: give the language / visual kernels fixed shares of the SMs (A/B measurement)
   OPT_COUNT = 20 };
 int option_get(int key);
 void option_set(int key, int value);

@@ -515,7 +515,7 @@ int launch_qkv_attn(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorM
   }
   const int row_tiles = STR ? (p.B + kStrSamples - 1) / kStrSamples : (p.B + 2 * p.ns - 1) / (2 * p.ns);
   const int tiles = row_tiles * p.heads;
-  const int max_pairs = num_sms() / 2;
+  const int max_pairs = launch_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   RGQA_CUDA_OK(launch_pdl(kern, dim3(2 * pairs), dim3(kThreads), smem, stream, tmA, tmB, tmO, tmO2 ? *tmO2 : tmO, p));
   return 0;

@@ -417,7 +417,7 @@ int visn_embed(cudaStream_t stream, const void* feat, int feat_f32, long long ld
   p.lo = static_cast<__nv_bfloat16*>(lo);
   p.stats = stats;
   const int tiles = (M + 2 * kRowsPerCta - 1) / (2 * kRowsPerCta);
-  const int max_pairs = num_sms() / 2;
+  const int max_pairs = launch_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   void* tok = prof_begin(stream);
   if (feat_f32) {
